@@ -1,0 +1,81 @@
+"""Synthetic signature / location tables of the BASELINE.json shapes.
+
+All draws come from ``numpy.random.Generator(PCG64(seed))`` with seed = 20241019 +
+config number, so the bench, the GPU parity tests and the CPU baseline see the same
+tables.  Table semantics follow the reference's producer
+(app/utils/parallel_sig_generator.py:46,135,205-209): ``sig`` = best HMMER bit-score per
+PPHMM (0 = absent), ``loc`` = signed mid-point of the best hit (0 = absent); float64,
+C-order, shape (N, P).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+SEED_BASE = 20241019
+
+# name -> (N, P, G, B, density)
+CONFIGS = {
+    "cfg1": dict(n=20, p=150, g=7, b=100, density=0.2),          # cli/example_run.py shape
+    "cfg2": dict(n=1000, p=5000, g=50, b=100, density=0.01),
+    "cfg3": dict(n=10000, p=30000, g=200, b=1000, density=0.01),
+    "cfg4": dict(n=50000, p=30000, g=200, b=0, density=0.01),     # presence/popcount
+    "cfg5": dict(n=25000, p=30000, g=200, b=0, density=0.01),     # 5k query + 20k ref
+}
+
+
+@dataclass
+class Tables:
+    sig: np.ndarray        # (N, P) float64 bit-scores
+    loc: np.ndarray        # (N, P) float64 signed locations
+    taxo: np.ndarray       # (N,) str taxon label per genome
+    gom_ids: list          # G taxon labels, GOM column order
+
+
+def make_tables(n: int, p: int, g: int, density: float = 0.01, seed: int = SEED_BASE,
+                chunk_rows: int = 1024) -> Tables:
+    """Per-taxon core PPHMM set ~ Bernoulli(density); a genome keeps each core PPHMM of its
+    taxon with probability 0.8 and gains Bernoulli(0.1*density) noise hits.  Bit-scores
+    ``round(Gamma(2, 60), 1)`` clipped to >= 0.1; locations ``+-U{1..L}``,
+    ``L ~ U{5000..200000}`` per genome."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = min(g, n)
+    taxon = rng.integers(0, g, n)
+    taxon[:g] = np.arange(g)                      # every taxon non-empty
+    core = rng.random((g, p)) < density
+    sig = np.zeros((n, p), dtype=np.float64)
+    loc = np.zeros((n, p), dtype=np.float64)
+    for r0 in range(0, n, chunk_rows):
+        r1 = min(n, r0 + chunk_rows)
+        m = r1 - r0
+        pres = (core[taxon[r0:r1]] & (rng.random((m, p)) < 0.8)) | (rng.random((m, p)) < 0.1 * density)
+        score = np.maximum(np.round(rng.gamma(2.0, 60.0, (m, p)), 1), 0.1)
+        sig[r0:r1] = np.where(pres, score, 0.0)
+        length = rng.integers(5000, 200001, m)
+        pos = np.floor(rng.random((m, p)) * length[:, None]) + 1.0
+        sign = np.where(rng.random((m, p)) < 0.5, -1.0, 1.0)
+        loc[r0:r1] = np.where(pres, pos * sign, 0.0)
+    gom_ids = [f"T{k:03d}" for k in range(g)]
+    taxo = np.array([gom_ids[t] for t in taxon])
+    return Tables(sig=sig, loc=loc, taxo=taxo, gom_ids=gom_ids)
+
+
+def make_config(name: str, **override) -> Tables:
+    c = dict(CONFIGS[name])
+    c.update(override)
+    return make_tables(c["n"], c["p"], c["g"], c["density"], SEED_BASE + int(name[-1]))
+
+
+def reference_resample_indices(n_pphmms: int, n_boot: int, seed: int, sort: bool = False) -> np.ndarray:
+    """(B, P) int64 resample indices drawn exactly as the reference draws them
+    (app/src/pl1_graphs.py:81-82, unsorted; app/src/virus_classification.py:295-296,
+    sorted) from numpy's legacy global MT19937 stream -- the reference itself never seeds
+    (SURVEY quirk Q4); seeding here only makes the bench repeatable."""
+    np.random.seed(seed)
+    out = np.empty((n_boot, n_pphmms), dtype=np.int64)
+    pool = list(range(n_pphmms))
+    for b in range(n_boot):
+        idx = np.random.choice(pool, n_pphmms, replace=True)
+        out[b] = np.sort(idx) if sort else idx
+    return out

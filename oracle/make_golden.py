@@ -1,0 +1,157 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (Mayne941/gravity2)
+imported from /root/reference.  Runs only in the build container (the GPU box has no
+/root/reference); the fixtures it writes are committed and are what pins the oracle.
+
+    python oracle/make_golden.py
+
+Cosmetic-only imports the container lacks (termcolor, alive_progress: oracle/stubs/;
+plotly, Bio, matplotlib: empty stand-ins created below) are stubbed; none of them is on
+the arithmetic path.
+"""
+import os
+import sys
+import tempfile
+import types
+import warnings
+from unittest import mock
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = os.environ.get("GRAVITY_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(HERE, "stubs"), REF, REPO]
+
+for name in ["plotly", "plotly.express", "Bio", "Bio.Phylo", "matplotlib", "matplotlib.pyplot",
+             "matplotlib.colors", "matplotlib.patches", "matplotlib.lines", "ete3"]:
+    if name not in sys.modules:
+        try:
+            __import__(name)
+        except Exception:
+            sys.modules[name] = mock.MagicMock()
+
+from app.utils.similarity_matrix_constructor import SimilarityMat_Constructor  # noqa: E402
+from app.utils.parallel_gom_sig_generator import generate_gom_sigs  # noqa: E402
+from app.utils.gomdb_constructor import GOMDB_Constructor  # noqa: E402
+from app.utils.dcor import dcor, cent_dist  # noqa: E402
+from app.utils.dist_mat_to_tree import DistMat2Tree  # noqa: E402
+from app.utils.shared_pphmm_graphs import shared_pphmm_ratio, shared_norm_pphmm_ratio  # noqa: E402
+
+from gravity2_b200.synth import make_tables  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def write_csvs(tmp, sig, loc):
+    """The two CSVs SimilarityMat_Constructor insists on, laid out as
+    app/src/pl1_graphs.py:307-319 writes them."""
+    n, p = sig.shape
+    names = [f"v{i}" for i in range(n)]
+    cols = [f"PPHMM {c}" for c in range(p)]
+    df = pd.DataFrame(sig, columns=cols)
+    df.insert(0, "Virus name", names)
+    f_sig = os.path.join(tmp, "sigs.csv")
+    df.to_csv(f_sig)
+    dl = pd.DataFrame(np.abs(loc), columns=cols)
+    dl.insert(0, "Virus name", names)
+    f_loc = os.path.join(tmp, "locs.csv")
+    dl.to_csv(f_loc, index=False)
+    return {"PphmmLocs": f_loc, "PphmmAndGomSigs": f_sig}
+
+
+def ref_gom_table(loc, db, ids):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.column_stack([generate_gom_sigs(g, loc, db) for g in ids])
+
+
+def main():
+    gold = {}
+    # --- known answers the reference itself holds
+    gold["dcor_kat"] = np.float64(dcor(np.matrix("1;2;3;4;5"), np.matrix("1;2;9;4;4")))
+    gold["cent_dist_123456"] = cent_dist(np.array([[1, 2], [3, 4], [5, 6]]))
+    fx_loc = np.array([[1, 0, 1], [0, 1, 0], [1, 1, 1]])
+    fx_db = {"GOM1": np.array([[1, 0, 1], [0, 1, 0], [1, 1, 1]]),
+             "GOM2": np.array([[0, 1, 0], [1, 0, 1], [0, 0, 0]])}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gold["gomfix_GOM1"] = np.array(generate_gom_sigs("GOM1", fx_loc, fx_db))
+        gold["gomfix_GOM2"] = np.array(generate_gom_sigs("GOM2", fx_loc, fx_db))
+    D3 = np.array([[0.0, 0.2, 0.4], [0.2, 0.0, 0.6], [0.4, 0.6, 0.0]])
+    gold["newick_3x3_single"] = np.array(DistMat2Tree(D3.copy(), ["A", "B", "C"], "single", False))
+
+    with tempfile.TemporaryDirectory() as tmp:
+        # --- small synthetic case A (sparse, PL1-like) and B (denser, with empty genome + duplicate)
+        for tag, (n, p, g, dens, seed) in {"A": (14, 60, 4, 0.25, 101), "B": (10, 33, 3, 0.6, 202)}.items():
+            t = make_tables(n, p, g, dens, seed)
+            sig, loc = t.sig, t.loc
+            if tag == "B":
+                sig[3] = 0.0; loc[3] = 0.0            # all-zero genome (Q5: S[i,i] = 0)
+                sig[7] = sig[2]; loc[7] = loc[2]      # duplicate genome (S = 1 off-diagonal)
+            fn = write_csvs(tmp, sig, loc)
+            db = GOMDB_Constructor(t.taxo, loc, t.gom_ids)
+            gom = ref_gom_table(loc, db, t.gom_ids)
+            gold[f"{tag}_sig"], gold[f"{tag}_loc"], gold[f"{tag}_gom"] = sig, loc, gom
+            gold[f"{tag}_taxo"] = t.taxo
+            gold[f"{tag}_gom_ids"] = np.array(t.gom_ids)
+            spr = np.random.default_rng(seed).random((n, n))
+            spr = (spr + spr.T) / 2
+            gold[f"{tag}_spr"] = spr
+            for scheme in ["P", "G", "L", "PG", "PL", "R", "RG", "PR"]:
+                for pw in ([1.0, 2.0] if scheme == "PG" else [1.0]):
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        S = SimilarityMat_Constructor(sig.copy(), gom, loc, spr.copy(), 0.0, 0, scheme, pw, fn)
+                    gold[f"{tag}_S_{scheme}_p{int(pw)}"] = np.array(S)
+            # threshold > 0 (weight == 0): idempotent in-place zeroing (Q1)
+            sig_thr = sig.copy()
+            S = SimilarityMat_Constructor(sig_thr, gom, loc, None, 0.0, 60, "PG", 1.0, fn)
+            gold[f"{tag}_S_PG_thr60"] = np.array(S)
+            gold[f"{tag}_sig_after_thr60"] = sig_thr
+            # presence/absence matrices (a14, a15) through the reference's CSV reader
+            order = list(range(n))
+            keep = [i for i in order if np.count_nonzero(sig[i])]     # a15 raises on empty genomes
+            gold[f"{tag}_shared"] = np.array(shared_pphmm_ratio(order, fn, None), dtype=np.int64)
+            gold[f"{tag}_shared_norm_keep"] = np.array(keep)
+            gold[f"{tag}_shared_norm"] = shared_norm_pphmm_ratio(keep, fn, None)
+            # --- bootstrap loop bodies with the reference's own RNG call (Q4)
+            np.random.seed(1234 + seed)
+            idx_pl1, D_pl1, idx_pl2, S_pl2 = [], [], [], []
+            for _ in range(3):
+                # PL1, app/src/pl1_graphs.py:81-107 (signature table doubles as location table, Q3)
+                idx = np.random.choice(list(range(p)), p, replace=True)
+                b_sig = sig[:, idx]; b_loc = sig[:, idx]
+                bdb = GOMDB_Constructor(t.taxo, b_loc, t.gom_ids)
+                bgom = ref_gom_table(b_loc, bdb, t.gom_ids)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    S = SimilarityMat_Constructor(b_sig, bgom, b_loc, None, 0.0, 0, "PG", 1.0, fn)
+                D = 1 - S; D[D < 0] = 0
+                idx_pl1.append(idx); D_pl1.append(D)
+            n_ref = n - 3
+            for _ in range(3):
+                # PL2, app/src/virus_classification.py:295-315 (sorted idx, real location table)
+                idx = sorted(np.random.choice(list(range(p)), p, replace=True))
+                b_sig = sig[:, idx]; b_loc = loc[:, idx]
+                bdb = GOMDB_Constructor(t.taxo[:n_ref], b_loc[:n_ref], t.gom_ids)
+                bgom = ref_gom_table(b_loc, bdb, t.gom_ids)
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    S = SimilarityMat_Constructor(b_sig, bgom, b_loc, None, 0.0, 0, "PG", 1.0, fn)
+                idx_pl2.append(np.array(idx)); S_pl2.append(np.array(S))
+            gold[f"{tag}_boot_seed"] = np.int64(1234 + seed)
+            gold[f"{tag}_pl1_idx"] = np.array(idx_pl1)
+            gold[f"{tag}_pl1_D"] = np.array(D_pl1)
+            gold[f"{tag}_pl2_nref"] = np.int64(n_ref)
+            gold[f"{tag}_pl2_idx"] = np.array(idx_pl2)
+            gold[f"{tag}_pl2_S"] = np.array(S_pl2)
+            D0 = 1 - gold[f"{tag}_S_PG_p1"]; D0[D0 < 0] = 0
+            gold[f"{tag}_newick_avg"] = np.array(DistMat2Tree(D0.copy(), [f"v{i}" for i in range(n)], "average", False))
+    np.savez_compressed(os.path.join(OUT, "reference_golden.npz"), **gold)
+    print("wrote", os.path.join(OUT, "reference_golden.npz"), len(gold), "arrays")
+
+
+if __name__ == "__main__":
+    main()
