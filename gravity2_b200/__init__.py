@@ -1,0 +1,13 @@
+"""gravity2_b200 -- B200-native (sm_100a) pairwise genome-similarity engine for GRAViTy-V2.
+
+Importing the package touches neither CUDA nor the shared library; both are bound on first use.
+"""
+from .dropin import (  # noqa: F401
+    SimilarityMat_Constructor, dist_mat_constructor, GOMDB_Constructor, GOMSignatureTable_Constructor,
+    generate_gom_sigs, dcor, shared_pphmm_ratio, shared_norm_pphmm_ratio, shared_norm_pphmm_ratio_from_array,
+    shared_pphmm_counts, binary_jaccard, bootstrap_distance_matrices, draw_resample_indices,
+    weights_from_indices, gom_membership,
+)
+from .engine import Engine, default_engine  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,478 @@
+// C ABI of libgravity_b200: context, host-pointer entry points, device-resident job.
+// Declarations and per-entry reference citations: include/gravity2_b200.h.
+#include "common.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "gom.h"
+
+int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n_pad, int64_t k_pad,
+                       int64_t tile_begin, int64_t tile_end, const float* w, int64_t nb, int ksplit,
+                       double* ws);
+int boot_mma_available();
+int boot_mma_launch(gv2_ctx* ctx, const float* tab, int64_t n, int64_t n_pad, int64_t k_pad,
+                    const float* w, int64_t nb, double* ws);
+
+static thread_local std::string g_create_error;
+
+int gv2_fail(gv2_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+extern "C" int gv2_version(void) { return 100; }
+
+extern "C" int gv2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int create_impl(int device, void* stream, bool own, gv2_ctx** out) {
+    if (!out) return gv2_fail(nullptr, GV2_ERR_ARG, "gv2_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return gv2_fail(nullptr, GV2_ERR_CUDA, "gv2_create: no CUDA device (%s); libgravity_b200 has no CPU fallback",
+                        e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return gv2_fail(nullptr, GV2_ERR_ARG, "gv2_create: device %d of %d", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return gv2_fail(nullptr, GV2_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return gv2_fail(nullptr, GV2_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return gv2_fail(nullptr, GV2_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                        device, prop.major, prop.minor);
+    gv2_ctx* c = new gv2_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (own) {
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete c; return gv2_fail(nullptr, GV2_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        c->own_stream = true;
+    } else {
+        c->stream = (cudaStream_t)stream;
+    }
+    *out = c;
+    return GV2_OK;
+}
+
+extern "C" int gv2_create(int device, gv2_ctx** out) { return create_impl(device, nullptr, true, out); }
+extern "C" int gv2_create_on_stream(int device, void* s, gv2_ctx** out) { return create_impl(device, s, false, out); }
+
+extern "C" void gv2_destroy(gv2_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* gv2_last_error(const gv2_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int gv2_synchronize(gv2_ctx* ctx) {
+    if (!ctx) return GV2_ERR_ARG;
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GV2_OK;
+}
+
+extern "C" uint64_t gv2_launch_count(const gv2_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------- helpers
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t b) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = b ? b : 1;
+        return cudaMalloc(&p, bytes);
+    }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+#define ALLOC(ctx, buf, bytes)                                                                   \
+    do {                                                                                         \
+        cudaError_t e__ = (buf).alloc(bytes);                                                    \
+        if (e__ != cudaSuccess)                                                                  \
+            return gv2_fail((ctx), GV2_ERR_NOMEM, "%s:%d device allocation of %.3f GB failed: %s", \
+                            __FILE__, __LINE__, (double)(bytes) / 1e9, cudaGetErrorString(e__));  \
+    } while (0)
+
+// host matrix (rows x cols doubles, stride ld) -> device, contiguous (ld = cols)
+static int upload_matrix(gv2_ctx* ctx, const double* h, int64_t rows, int64_t cols, int64_t ld, DevBuf& d) {
+    ALLOC(ctx, d, (size_t)rows * cols * sizeof(double));
+    if (rows == 0 || cols == 0) return GV2_OK;
+    GV2_CUDA(ctx, cudaMemcpy2DAsync(d.p, cols * sizeof(double), h, ld * sizeof(double), cols * sizeof(double), rows,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    return GV2_OK;
+}
+
+static int pick_ksplit(gv2_ctx* ctx, int64_t ntl, int64_t nb, int64_t k_pad) {
+    // enough CTAs for >= 2 waves at 2 CTAs/SM; never split below one fp32 slab
+    const int64_t want = 4LL * ctx->sm_count;
+    int64_t ks = (want + ntl * nb - 1) / std::max<int64_t>(1, ntl * nb);
+    const int64_t max_ks = std::max<int64_t>(1, k_pad / 1024);
+    return (int)std::max<int64_t>(1, std::min<int64_t>(ks, std::min<int64_t>(max_ks, 64)));
+}
+
+// ------------------------------------------------------------------------- device job
+struct gv2_job {
+    gv2_ctx* ctx = nullptr;
+    int64_t n = 0, p = 0, g = 0, n_pad = 0, p_pad = 0, g_pad = 0, ntiles = 0;
+    int scheme = GV2_SCHEME_PG, out_kind = GV2_OUT_DISTANCE;
+    double power = 1.0;
+    bool need_p = false, need_g = false;
+    DevBuf sig64, loc64;              // owned uploads (empty when the caller's tables are on the device)
+    const double* d_sig = nullptr;
+    const double* d_loc = nullptr;
+    DevBuf sigf, sig_rowsum, sig_nan;
+    GomDb* gom = nullptr;
+    DevBuf gom_base;                   // [n][g] float64 base GOM table (lazy)
+    bool have_gom_base = false;
+    // workspaces, grown on demand
+    DevBuf wsP, wsG, gomtab, gomf, gom_rowsum, gom_nan, wf, w_rowsum;
+    size_t device_bytes() const {
+        size_t b = sig64.bytes + loc64.bytes + sigf.bytes + sig_rowsum.bytes + sig_nan.bytes + gom_base.bytes +
+                   wsP.bytes + wsG.bytes + gomtab.bytes + gomf.bytes + gom_rowsum.bytes + gom_nan.bytes + wf.bytes + w_rowsum.bytes;
+        if (gom) b += gom->bytes;
+        return b;
+    }
+};
+
+static int ensure(gv2_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (b.p && b.bytes >= bytes) return GV2_OK;
+    ALLOC(ctx, b, bytes);
+    return GV2_OK;
+}
+
+extern "C" void gv2_job_destroy(gv2_job* job) {
+    if (!job) return;
+    cudaSetDevice(job->ctx->device);
+    cudaStreamSynchronize(job->ctx->stream);
+    gom_db_free(job->gom);
+    delete job;
+}
+
+extern "C" size_t gv2_job_device_bytes(const gv2_job* job) { return job ? job->device_bytes() : 0; }
+
+extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc, int tables_are_device,
+                              int64_t n, int64_t p, const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g,
+                              int scheme, double power, int out_kind, gv2_job** out) {
+    if (!ctx || !out || n < 0 || p < 0) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_job_create: bad arguments");
+    *out = nullptr;
+    if (scheme != GV2_SCHEME_P && scheme != GV2_SCHEME_G && scheme != GV2_SCHEME_PG)
+        return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "gv2_job_create: scheme %d (jobs cover P, G, PG)", scheme);
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    gv2_job* j = new gv2_job();
+    j->ctx = ctx; j->n = n; j->p = p; j->g = g; j->scheme = scheme; j->power = power; j->out_kind = out_kind;
+    j->need_p = scheme != GV2_SCHEME_G;
+    j->need_g = scheme != GV2_SCHEME_P;
+    j->n_pad = gv2_round_up(std::max<int64_t>(n, 1), GV2_TILE);
+    j->p_pad = gv2_round_up(std::max<int64_t>(p, 1), GV2_BK);
+    j->g_pad = gv2_round_up(std::max<int64_t>(g, 1), GV2_BK);
+    j->ntiles = gv2_num_tiles(n);
+    int rc = GV2_OK;
+    auto bail = [&](int code) { gv2_job_destroy(j); return code; };
+    if (j->need_p) {
+        if (!sig) return bail(gv2_fail(ctx, GV2_ERR_ARG, "gv2_job_create: scheme needs the signature table"));
+        if (tables_are_device) j->d_sig = sig;
+        else { if ((rc = upload_matrix(ctx, sig, n, p, p, j->sig64))) return bail(rc); j->d_sig = j->sig64.as<double>(); }
+        if ((rc = ensure(ctx, j->sigf, (size_t)j->n_pad * j->p_pad * sizeof(float)))) return bail(rc);
+        if ((rc = ensure(ctx, j->sig_rowsum, (size_t)n * sizeof(double)))) return bail(rc);
+        if ((rc = ensure(ctx, j->sig_nan, (size_t)n))) return bail(rc);
+        if ((rc = gv2_dev_prepare_table(ctx, j->d_sig, n, p, p, 0.0, 0, j->sigf.as<float>(), j->n_pad, j->p_pad,
+                                        j->sig_rowsum.as<double>(), j->sig_nan.as<uint8_t>()))) return bail(rc);
+    }
+    if (j->need_g) {
+        if (!loc || !gom_of_row || g <= 0) return bail(gv2_fail(ctx, GV2_ERR_ARG, "gv2_job_create: scheme needs loc, gom_of_row and g > 0"));
+        if (tables_are_device) j->d_loc = loc;
+        else if (loc == sig && j->need_p) j->d_loc = j->d_sig;          // PL1 quirk Q3: one upload
+        else { if ((rc = upload_matrix(ctx, loc, n, p, p, j->loc64))) return bail(rc); j->d_loc = j->loc64.as<double>(); }
+        if (n_gom_rows > n) return bail(gv2_fail(ctx, GV2_ERR_ARG, "gv2_job_create: n_gom_rows > n"));
+        std::vector<int32_t> mem_ptr(g + 1, 0);
+        std::vector<int64_t> mem_row;
+        for (int64_t r = 0; r < n_gom_rows; ++r) {
+            if (gom_of_row[r] >= g) return bail(gv2_fail(ctx, GV2_ERR_ARG, "gom_of_row[%lld] = %d >= g", (long long)r, gom_of_row[r]));
+            if (gom_of_row[r] >= 0) mem_ptr[gom_of_row[r] + 1]++;
+        }
+        for (int64_t k = 0; k < g; ++k) mem_ptr[k + 1] += mem_ptr[k];
+        mem_row.resize(mem_ptr[g]);
+        std::vector<int32_t> fill(mem_ptr.begin(), mem_ptr.end() - 1);
+        for (int64_t r = 0; r < n_gom_rows; ++r)
+            if (gom_of_row[r] >= 0) mem_row[fill[gom_of_row[r]]++] = r;
+        if ((rc = gom_db_build(ctx, j->d_loc, n, p, p, j->d_loc, p, mem_row.data(), mem_ptr.data(), g, 0, &j->gom))) return bail(rc);
+    }
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = j;
+    return GV2_OK;
+}
+
+// GOM table (fp64 [nb][n][g]) -> fp32 padded tables [nb][n_pad][g_pad] + row sums + NaN flags
+static int job_prepare_gom(gv2_job* j, const double* tab64, int64_t nb) {
+    gv2_ctx* ctx = j->ctx;
+    int rc;
+    if ((rc = ensure(ctx, j->gomf, (size_t)nb * j->n_pad * j->g_pad * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, j->gom_rowsum, (size_t)nb * j->n * sizeof(double)))) return rc;
+    if ((rc = ensure(ctx, j->gom_nan, (size_t)nb * j->n))) return rc;
+    for (int64_t b = 0; b < nb; ++b)
+        if ((rc = gv2_dev_prepare_table(ctx, tab64 + b * j->n * j->g, j->n, j->g, j->g, 0.0, 0,
+                                        j->gomf.as<float>() + b * j->n_pad * j->g_pad, j->n_pad, j->g_pad,
+                                        j->gom_rowsum.as<double>() + b * j->n, j->gom_nan.as<uint8_t>() + b * j->n)))
+            return rc;
+    return GV2_OK;
+}
+
+extern "C" int gv2_job_gom_table(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out) {
+    if (!job || !dev_out || nb <= 0) return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_gom_table: bad arguments");
+    if (!job->gom) return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_gom_table: job has no GOM database");
+    if (!dev_weights && nb != 1) return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_gom_table: nb must be 1 without weights");
+    GV2_CUDA(job->ctx, cudaSetDevice(job->ctx->device));
+    return gom_db_score(job->ctx, job->gom, dev_weights, nb, dev_out);
+}
+
+extern "C" int gv2_job_base(gv2_job* job, int64_t tile_begin, int64_t tile_end, int packed, double* dev_out) {
+    if (!job || !dev_out || tile_begin < 0 || tile_end < tile_begin || tile_end > job->ntiles)
+        return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_base: bad arguments");
+    gv2_ctx* ctx = job->ctx;
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t ntl = tile_end - tile_begin;
+    if (ntl == 0) return GV2_OK;
+    const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
+    int rc;
+    gv2_gj_component cp{}, cg{};
+    if (job->need_p) {
+        const int ks = pick_ksplit(ctx, ntl, 1, job->p_pad);
+        if ((rc = ensure(ctx, job->wsP, (size_t)ks * ntl * tile_elems * sizeof(double)))) return rc;
+        if ((rc = gj_min_sums_launch(ctx, job->sigf.as<float>(), 0, job->n_pad, job->p_pad, tile_begin, tile_end, nullptr, 1, ks,
+                                     job->wsP.as<double>()))) return rc;
+        cp.min_sums = job->wsP.as<double>(); cp.rowsums = job->sig_rowsum.as<double>(); cp.nanflags = job->sig_nan.as<uint8_t>();
+        cp.ksplit = ks;
+    }
+    if (job->need_g) {
+        if (!job->have_gom_base) {
+            if ((rc = ensure(ctx, job->gom_base, (size_t)job->n * job->g * sizeof(double)))) return rc;
+            if ((rc = gom_db_score(ctx, job->gom, nullptr, 1, job->gom_base.as<double>()))) return rc;
+            job->have_gom_base = true;
+        }
+        if ((rc = job_prepare_gom(job, job->gom_base.as<double>(), 1))) return rc;
+        if ((rc = ensure(ctx, job->wsG, (size_t)ntl * tile_elems * sizeof(double)))) return rc;
+        if ((rc = gj_min_sums_launch(ctx, job->gomf.as<float>(), 0, job->n_pad, job->g_pad, tile_begin, tile_end, nullptr, 1, 1,
+                                     job->wsG.as<double>()))) return rc;
+        cg.min_sums = job->wsG.as<double>(); cg.rowsums = job->gom_rowsum.as<double>(); cg.nanflags = job->gom_nan.as<uint8_t>();
+        cg.ksplit = 1;
+    }
+    return gv2_dev_gj_epilogue(ctx, job->n, tile_begin, tile_end, 1, &cp, &cg, nullptr, job->scheme, job->power,
+                               job->out_kind, packed, dev_out, 0);
+}
+
+extern "C" int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out) {
+    if (!job || !dev_weights || !dev_out || nb < 0)
+        return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates: bad arguments");
+    gv2_ctx* ctx = job->ctx;
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (nb == 0 || job->n == 0) return GV2_OK;
+    const int64_t n = job->n, p = job->p, g = job->g, ntl = job->ntiles;
+    const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
+    // replicates per pass: bounded by the pair-sum workspaces (8 B * N_pad^2/2 per replicate and component)
+    const size_t per_rep = ntl * tile_elems * sizeof(double) * ((job->need_p ? 1 : 0) + (job->need_g ? 1 : 0)) +
+                           (job->need_g ? (size_t)job->n_pad * job->g_pad * 4 + (size_t)n * g * 8 : 0);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t have = job->wsP.bytes + job->wsG.bytes + job->gomf.bytes + job->gomtab.bytes;
+    int64_t chunk = (int64_t)std::max<size_t>(1, std::min<size_t>((size_t)nb, (size_t)((free_b + have) * 0.5) / std::max<size_t>(1, per_rep)));
+    chunk = std::min<int64_t>(chunk, 512);
+    int rc;
+    for (int64_t b0 = 0; b0 < nb; b0 += chunk) {
+        const int64_t cb = std::min<int64_t>(chunk, nb - b0);
+        const int32_t* w = dev_weights + b0 * p;
+        gv2_gj_component cp{}, cg{};
+        if (job->need_p) {
+            if ((rc = ensure(ctx, job->wf, (size_t)cb * job->p_pad * sizeof(float)))) return rc;
+            if ((rc = ensure(ctx, job->w_rowsum, (size_t)cb * n * sizeof(double)))) return rc;
+            if ((rc = gv2_dev_weights_to_float(ctx, w, cb, p, job->p_pad, job->wf.as<float>()))) return rc;
+            if ((rc = gv2_dev_weighted_rowsums(ctx, job->sigf.as<float>(), n, job->p_pad, job->wf.as<float>(), cb,
+                                               job->w_rowsum.as<double>()))) return rc;
+            if ((rc = ensure(ctx, job->wsP, (size_t)cb * ntl * tile_elems * sizeof(double)))) return rc;
+            if (boot_mma_available() && cb >= 8) {
+                if ((rc = boot_mma_launch(ctx, job->sigf.as<float>(), n, job->n_pad, job->p_pad, job->wf.as<float>(), cb,
+                                          job->wsP.as<double>()))) return rc;
+            } else {
+                if ((rc = gj_min_sums_launch(ctx, job->sigf.as<float>(), 0, job->n_pad, job->p_pad, 0, ntl, job->wf.as<float>(), cb, 1,
+                                             job->wsP.as<double>()))) return rc;
+            }
+            cp.min_sums = job->wsP.as<double>(); cp.rowsums = job->w_rowsum.as<double>(); cp.nanflags = job->sig_nan.as<uint8_t>();
+            cp.ksplit = 1; cp.replicate_stride_sums = (int64_t)(ntl * tile_elems); cp.replicate_stride_rows = n;
+        }
+        if (job->need_g) {
+            if ((rc = ensure(ctx, job->gomtab, (size_t)cb * n * g * sizeof(double)))) return rc;
+            if ((rc = gom_db_score(ctx, job->gom, w, cb, job->gomtab.as<double>()))) return rc;
+            if ((rc = job_prepare_gom(job, job->gomtab.as<double>(), cb))) return rc;
+            if ((rc = ensure(ctx, job->wsG, (size_t)cb * ntl * tile_elems * sizeof(double)))) return rc;
+            if ((rc = gj_min_sums_launch(ctx, job->gomf.as<float>(), job->n_pad * job->g_pad, job->n_pad, job->g_pad, 0, ntl, nullptr, cb, 1,
+                                         job->wsG.as<double>()))) return rc;
+            cg.min_sums = job->wsG.as<double>(); cg.rowsums = job->gom_rowsum.as<double>(); cg.nanflags = job->gom_nan.as<uint8_t>();
+            cg.ksplit = 1; cg.replicate_stride_sums = (int64_t)(ntl * tile_elems); cg.replicate_stride_rows = n;
+            cg.replicate_stride_nan = n;
+        }
+        // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)
+        if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
+                                      dev_out + b0 * n * n, n * n))) return rc;
+    }
+    return GV2_OK;
+}
+
+// ------------------------------------------------------------------ host-pointer wrappers
+extern "C" int gv2_similarity_host(gv2_ctx* ctx, const double* sig, int64_t n, int64_t p, int64_t ld_sig,
+                                   const double* gom, int64_t g, int64_t ld_gom, const double* spr, int scheme,
+                                   double power, double threshold, int apply_threshold, int out_kind, double* out) {
+    if (!ctx || !out || n < 0) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_similarity_host: bad arguments");
+    if (scheme < GV2_SCHEME_P || scheme > GV2_SCHEME_PL) return gv2_fail(ctx, GV2_ERR_ARG, "unknown scheme %d", scheme);
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return GV2_OK;
+    const bool need_p = scheme == GV2_SCHEME_P || scheme == GV2_SCHEME_PG || scheme == GV2_SCHEME_PR || scheme == GV2_SCHEME_PL;
+    const bool need_g = scheme == GV2_SCHEME_G || scheme == GV2_SCHEME_PG || scheme == GV2_SCHEME_RG;
+    const bool need_r = scheme == GV2_SCHEME_R || scheme == GV2_SCHEME_RG || scheme == GV2_SCHEME_PR ||
+                        scheme == GV2_SCHEME_L || scheme == GV2_SCHEME_PL;
+    if ((need_p && !sig) || (need_g && !gom) || (need_r && !spr))
+        return gv2_fail(ctx, GV2_ERR_ARG, "gv2_similarity_host: scheme %d is missing an input table", scheme);
+    const int64_t n_pad = gv2_round_up(n, GV2_TILE), ntl = gv2_num_tiles(n);
+    const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
+    int rc;
+    DevBuf t64, tf, rs_p, nan_p, ws_p, g64, gf, rs_g, nan_g, ws_g, d_spr, d_out;
+    gv2_gj_component cp{}, cg{};
+    if (need_p) {
+        const int64_t p_pad = gv2_round_up(std::max<int64_t>(p, 1), GV2_BK);
+        if ((rc = upload_matrix(ctx, sig, n, p, ld_sig, t64))) return rc;
+        ALLOC(ctx, tf, (size_t)n_pad * p_pad * sizeof(float));
+        ALLOC(ctx, rs_p, (size_t)n * sizeof(double));
+        ALLOC(ctx, nan_p, (size_t)n);
+        if ((rc = gv2_dev_prepare_table(ctx, t64.as<double>(), n, p, p, threshold, apply_threshold, tf.as<float>(), n_pad, p_pad,
+                                        rs_p.as<double>(), nan_p.as<uint8_t>()))) return rc;
+        const int ks = pick_ksplit(ctx, ntl, 1, p_pad);
+        ALLOC(ctx, ws_p, (size_t)ks * ntl * tile_elems * sizeof(double));
+        if ((rc = gj_min_sums_launch(ctx, tf.as<float>(), 0, n_pad, p_pad, 0, ntl, nullptr, 1, ks, ws_p.as<double>()))) return rc;
+        cp.min_sums = ws_p.as<double>(); cp.rowsums = rs_p.as<double>(); cp.nanflags = nan_p.as<uint8_t>(); cp.ksplit = ks;
+    }
+    if (need_g) {
+        const int64_t g_pad = gv2_round_up(std::max<int64_t>(g, 1), GV2_BK);
+        if ((rc = upload_matrix(ctx, gom, n, g, ld_gom, g64))) return rc;
+        ALLOC(ctx, gf, (size_t)n_pad * g_pad * sizeof(float));
+        ALLOC(ctx, rs_g, (size_t)n * sizeof(double));
+        ALLOC(ctx, nan_g, (size_t)n);
+        if ((rc = gv2_dev_prepare_table(ctx, g64.as<double>(), n, g, g, 0.0, 0, gf.as<float>(), n_pad, g_pad, rs_g.as<double>(),
+                                        nan_g.as<uint8_t>()))) return rc;
+        ALLOC(ctx, ws_g, (size_t)ntl * tile_elems * sizeof(double));
+        if ((rc = gj_min_sums_launch(ctx, gf.as<float>(), 0, n_pad, g_pad, 0, ntl, nullptr, 1, 1, ws_g.as<double>()))) return rc;
+        cg.min_sums = ws_g.as<double>(); cg.rowsums = rs_g.as<double>(); cg.nanflags = nan_g.as<uint8_t>(); cg.ksplit = 1;
+    }
+    if (need_r && (rc = upload_matrix(ctx, spr, n, n, n, d_spr))) return rc;
+    ALLOC(ctx, d_out, (size_t)n * n * sizeof(double));
+    if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, 1, &cp, &cg, d_spr.as<double>(), scheme, power, out_kind, 0, d_out.as<double>(), 0))) return rc;
+    GV2_CUDA(ctx, cudaMemcpyAsync(out, d_out.p, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GV2_OK;
+}
+
+extern "C" int gv2_gom_table_host(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t ld_loc,
+                                  const double* gom_rows, int64_t ld_gom_rows, const int64_t* gom_offsets, int64_t g,
+                                  const int32_t* weights, int64_t nb, int flags, double* out) {
+    if (!ctx || !loc || !gom_offsets || !out || n < 0 || p < 0 || g < 0 || nb <= 0)
+        return gv2_fail(ctx, GV2_ERR_ARG, "gv2_gom_table_host: bad arguments");
+    if (!weights && nb != 1) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_gom_table_host: nb must be 1 without weights");
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0 || g == 0) return GV2_OK;
+    const int64_t M = gom_offsets[g];
+    if (M > 0 && !gom_rows) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_gom_table_host: gom_rows is NULL");
+    int rc;
+    DevBuf d_loc, d_rows, d_w, d_out;
+    if ((rc = upload_matrix(ctx, loc, n, p, ld_loc, d_loc))) return rc;
+    if ((rc = upload_matrix(ctx, gom_rows, M, p, ld_gom_rows, d_rows))) return rc;
+    std::vector<int32_t> mem_ptr(g + 1);
+    std::vector<int64_t> mem_row(M);
+    for (int64_t k = 0; k <= g; ++k) mem_ptr[k] = (int32_t)gom_offsets[k];
+    for (int64_t r = 0; r < M; ++r) mem_row[r] = r;
+    GomDb* db = nullptr;
+    if ((rc = gom_db_build(ctx, d_loc.as<double>(), n, p, p, d_rows.as<double>(), p, mem_row.data(), mem_ptr.data(), g, flags, &db))) return rc;
+    if (weights) {
+        ALLOC(ctx, d_w, (size_t)nb * p * sizeof(int32_t));
+        cudaError_t e = cudaMemcpyAsync(d_w.p, weights, (size_t)nb * p * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { gom_db_free(db); return gv2_fail(ctx, GV2_ERR_CUDA, "weights upload: %s", cudaGetErrorString(e)); }
+    }
+    cudaError_t e = d_out.alloc((size_t)nb * n * g * sizeof(double));
+    if (e != cudaSuccess) { gom_db_free(db); return gv2_fail(ctx, GV2_ERR_NOMEM, "gom table output: %s", cudaGetErrorString(e)); }
+    rc = gom_db_score(ctx, db, weights ? d_w.as<int32_t>() : nullptr, nb, d_out.as<double>());
+    if (rc == GV2_OK) {
+        e = cudaMemcpyAsync(out, d_out.p, (size_t)nb * n * g * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = gv2_fail(ctx, GV2_ERR_CUDA, "gom table download: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(ctx->stream);
+    gom_db_free(db);
+    return rc;
+}
+
+extern "C" int gv2_shared_counts_host(gv2_ctx* ctx, const double* tab, int64_t n, int64_t p, int64_t ld,
+                                      int32_t* inter, int32_t* nnz) {
+    if (!ctx || !tab || !inter || n < 0 || p < 0) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_shared_counts_host: bad arguments");
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return GV2_OK;
+    const int64_t n_pad = gv2_round_up(n, GV2_TILE);
+    const int64_t words = gv2_round_up(std::max<int64_t>(1, (p + 63) / 64), 16);
+    int rc;
+    DevBuf d_tab, d_bits, d_nnz, d_inter;
+    if ((rc = upload_matrix(ctx, tab, n, p, ld, d_tab))) return rc;
+    ALLOC(ctx, d_bits, (size_t)n_pad * words * 8);
+    ALLOC(ctx, d_nnz, (size_t)n * sizeof(int32_t));
+    ALLOC(ctx, d_inter, (size_t)n * n * sizeof(int32_t));
+    if ((rc = gv2_dev_pack_presence(ctx, d_tab.as<double>(), n, p, p, d_bits.as<uint64_t>(), n_pad, words, d_nnz.as<int32_t>()))) return rc;
+    if ((rc = gv2_dev_shared_counts(ctx, d_bits.as<uint64_t>(), n, n_pad, words, 0, gv2_num_tiles(n), d_inter.as<int32_t>()))) return rc;
+    GV2_CUDA(ctx, cudaMemcpyAsync(inter, d_inter.p, (size_t)n * n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nnz) GV2_CUDA(ctx, cudaMemcpyAsync(nnz, d_nnz.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GV2_OK;
+}
+
+extern "C" int gv2_bootstrap_host(gv2_ctx* ctx, const double* sig, const double* loc, int64_t n, int64_t p,
+                                  const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g, const int32_t* weights,
+                                  int64_t nb, int scheme, double power, int out_kind, double* out) {
+    if (!ctx || !weights || !out || nb < 0) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_bootstrap_host: bad arguments");
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (nb == 0 || n == 0) return GV2_OK;
+    gv2_job* job = nullptr;
+    int rc = gv2_job_create(ctx, sig, loc, 0, n, p, gom_of_row, n_gom_rows, g, scheme, power, out_kind, &job);
+    if (rc) return rc;
+    DevBuf d_w, d_out;
+    cudaError_t e = d_w.alloc((size_t)nb * p * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_w.p, weights, (size_t)nb * p * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { gv2_job_destroy(job); return gv2_fail(ctx, GV2_ERR_CUDA, "weights upload: %s", cudaGetErrorString(e)); }
+    // stream the replicates out in slabs so that the device never holds more than ~4 GB of output
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)((4ULL << 30) / std::max<size_t>(1, (size_t)n * n * 8))));
+    e = d_out.alloc((size_t)slab * n * n * sizeof(double));
+    if (e != cudaSuccess) { gv2_job_destroy(job); return gv2_fail(ctx, GV2_ERR_NOMEM, "bootstrap output slab: %s", cudaGetErrorString(e)); }
+    for (int64_t b0 = 0; b0 < nb && rc == GV2_OK; b0 += slab) {
+        const int64_t cb = std::min<int64_t>(slab, nb - b0);
+        rc = gv2_job_replicates(job, d_w.as<int32_t>() + b0 * p, cb, d_out.as<double>());
+        if (rc == GV2_OK) {
+            e = cudaMemcpyAsync(out + b0 * n * n, d_out.p, (size_t)cb * n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = gv2_fail(ctx, GV2_ERR_CUDA, "bootstrap download: %s", cudaGetErrorString(e));
+        }
+    }
+    gv2_job_destroy(job);
+    return rc;
+}

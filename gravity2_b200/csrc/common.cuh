@@ -1,0 +1,42 @@
+// Shared declarations for libgravity_b200 (sm_100a).  Internal header: the public C ABI
+// is include/gravity2_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/gravity2_b200.h"
+
+struct gv2_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    unsigned long long launches = 0;   // kernels launched through this context (bench: gpu_launches)
+};
+
+#define GV2_TILE 128          // genome-pair tile edge of the similarity kernels
+#define GV2_BK 32             // PPHMM columns staged per pipeline stage
+
+int gv2_fail(gv2_ctx* ctx, int code, const char* fmt, ...);
+
+#define GV2_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return gv2_fail((ctx), GV2_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,  \
+                            cudaGetErrorString(e__));                                        \
+    } while (0)
+
+#define GV2_LAUNCH_CHECK(ctx)                                                                \
+    do {                                                                                     \
+        (ctx)->launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess)                                                              \
+            return gv2_fail((ctx), GV2_ERR_CUDA, "%s:%d launch: %s", __FILE__, __LINE__,     \
+                            cudaGetErrorString(e__));                                        \
+    } while (0)
+
+static inline int64_t gv2_round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

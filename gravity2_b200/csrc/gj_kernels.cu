@@ -1,0 +1,500 @@
+// Generalised-Jaccard kernels (K1/K2/K3 of SURVEY.md §2.2) for sm_100a.
+//
+// Reference semantics: app/utils/similarity_matrix_constructor.py:167-177 computes, per
+// genome pair, sum(min(a,b)) / sum(max(a,b)) over full float64 rows.  Here the all-pairs
+// problem is a (min,+) "GEMM": 128x128 genome-pair tiles, PPHMM columns staged 32 at a
+// time through a 3-stage cp.async shared-memory ring, 8x8 register tile per thread,
+// one FMNMX (ALU pipe) + one FADD/FFMA (FMA pipe) per (pair, column) cell.
+//   sum(max) is never formed per cell: sum(max) = sum(a) + sum(b) - sum(min).
+// Precision: values are rounded once to fp32 (6e-8 relative), min is exact, accumulation
+// is fp32 within a slab of <= GJ_SLAB columns and each slab total is promoted to fp64 in
+// the pair-tile workspace (direct-min + slab promotion passes the 1e-6
+// gate; the sum|a-b| identity does not).
+#include "common.cuh"
+
+#include <math.h>
+
+#define GJ_THREADS 256
+#define GJ_STAGES 3
+#define GJ_LDS (GV2_BK + 4)          // padded row stride (floats): conflict-free LDS.128
+#define GJ_SLAB 1024                 // columns accumulated in fp32 before fp64 promotion
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// linear upper-triangular tile index -> (bi <= bj), nt = tiles per side
+__host__ __device__ inline void gv2_tile_coords(long long t, int nt, int* bi, int* bj) {
+    // row bi holds (nt - bi) tiles; offset(bi) = bi*nt - bi*(bi-1)/2
+    double disc = (2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t;
+    int r = (int)floor(((2.0 * nt + 1.0) - sqrt(disc)) * 0.5);
+    if (r < 0) r = 0;
+    while (r > 0 && (long long)r * nt - (long long)r * (r - 1) / 2 > t) --r;
+    while ((long long)(r + 1) * nt - (long long)(r + 1) * r / 2 <= t) ++r;
+    *bi = r;
+    *bj = r + (int)(t - ((long long)r * nt - (long long)r * (r - 1) / 2));
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: per-tile sum_c w_c * min(T[i,c], T[j,c])   (w == 1 when !WEIGHTED)
+// grid = (tiles in [tile_begin, tile_end), ksplit, nb);  ws[((b*ksplit+ks)*ntl + t)][128*128]
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(GJ_THREADS, 2)
+gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int kblocks_total,
+                   int nt, long long tile_begin, const float* __restrict__ wts, long long w_stride,
+                   double* __restrict__ ws) {
+    extern __shared__ __align__(16) float smem[];
+    float* sA = smem;                                         // [STAGES][128][GJ_LDS]
+    float* sB = sA + GJ_STAGES * GV2_TILE * GJ_LDS;           // [STAGES][128][GJ_LDS]
+    float* sW = sB + GJ_STAGES * GV2_TILE * GJ_LDS;           // [STAGES][32]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int ksplit = gridDim.y, ks = blockIdx.y, b = blockIdx.z;
+    const long long ntl = gridDim.x;
+    int bi, bj;
+    gv2_tile_coords(tile_begin + blockIdx.x, nt, &bi, &bj);
+
+    // this CTA's K range, in 32-column blocks
+    const int kb_per = (kblocks_total + ksplit - 1) / ksplit;
+    const int kb0 = ks * kb_per;
+    const int kb1 = min(kblocks_total, kb0 + kb_per);
+    const int nkb = max(0, kb1 - kb0);
+
+    tab += (size_t)b * tab_stride;                            // one table per replicate (GOM), or 0
+    const float* gA = tab + (size_t)bi * GV2_TILE * ld;
+    const float* gB = tab + (size_t)bj * GV2_TILE * ld;
+    const float* gW = WEIGHTED ? wts + (size_t)b * w_stride : nullptr;
+
+    auto load_stage = [&](int stage, int kb) {
+        const int k = kb * GV2_BK;
+        float* a = sA + stage * GV2_TILE * GJ_LDS;
+        float* bb = sB + stage * GV2_TILE * GJ_LDS;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            int q = tid + s * GJ_THREADS;
+            int row = q >> 3, cc = (q & 7) * 4;
+            cp_async16(a + row * GJ_LDS + cc, gA + (size_t)row * ld + k + cc);
+            cp_async16(bb + row * GJ_LDS + cc, gB + (size_t)row * ld + k + cc);
+        }
+        if (WEIGHTED && tid < 8) cp_async16(sW + stage * GV2_BK + tid * 4, gW + k + tid * 4);
+    };
+
+    float acc[8][8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) acc[m][n] = 0.f;
+
+    double* wtile = ws + (((size_t)b * ksplit + ks) * ntl + blockIdx.x) * (size_t)(GV2_TILE * GV2_TILE);
+
+    // promote the fp32 slab totals into the fp64 workspace (first slab stores, later ones add)
+    auto flush = [&](bool first) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int n = 0; n < 8; ++n) {
+                size_t o = (size_t)(ty + 16 * m) * GV2_TILE + (tx + 16 * n);
+                double v = (double)acc[m][n];
+                if (!first) v += wtile[o];
+                wtile[o] = v;
+                acc[m][n] = 0.f;
+            }
+    };
+
+#pragma unroll
+    for (int s = 0; s < GJ_STAGES - 1; ++s) {
+        if (s < nkb) load_stage(s, kb0 + s);
+        cp_async_commit();
+    }
+
+    bool first = true;
+    int in_slab = 0;
+    for (int it = 0; it < nkb; ++it) {
+        cp_async_wait<GJ_STAGES - 2>();
+        __syncthreads();
+        {   // prefetch stage it + STAGES-1 (its buffer was consumed at iteration it-1)
+            int nxt = it + GJ_STAGES - 1;
+            if (nxt < nkb) load_stage(nxt % GJ_STAGES, kb0 + nxt);
+            cp_async_commit();
+        }
+        const int stage = it % GJ_STAGES;
+        const float* a = sA + stage * GV2_TILE * GJ_LDS + ty * GJ_LDS;
+        const float* bb = sB + stage * GV2_TILE * GJ_LDS + tx * GJ_LDS;
+        const float* w = sW + stage * GV2_BK;
+#pragma unroll
+        for (int kg = 0; kg < GV2_BK / 4; ++kg) {
+            float4 bf[8];
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                bf[n] = *reinterpret_cast<const float4*>(bb + n * 16 * GJ_LDS + kg * 4);
+            float4 wv = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (WEIGHTED) wv = *reinterpret_cast<const float4*>(w + kg * 4);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                float4 af = *reinterpret_cast<const float4*>(a + m * 16 * GJ_LDS + kg * 4);
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    if (WEIGHTED) {
+                        acc[m][n] = fmaf(wv.x, fminf(af.x, bf[n].x), acc[m][n]);
+                        acc[m][n] = fmaf(wv.y, fminf(af.y, bf[n].y), acc[m][n]);
+                        acc[m][n] = fmaf(wv.z, fminf(af.z, bf[n].z), acc[m][n]);
+                        acc[m][n] = fmaf(wv.w, fminf(af.w, bf[n].w), acc[m][n]);
+                    } else {
+                        acc[m][n] += fminf(af.x, bf[n].x);
+                        acc[m][n] += fminf(af.y, bf[n].y);
+                        acc[m][n] += fminf(af.z, bf[n].z);
+                        acc[m][n] += fminf(af.w, bf[n].w);
+                    }
+                }
+            }
+        }
+        in_slab += GV2_BK;
+        if (in_slab >= GJ_SLAB) {
+            flush(first);
+            first = false;
+            in_slab = 0;
+        }
+    }
+    if (in_slab > 0 || first) flush(first);
+}
+
+// ---------------------------------------------------------------------------------------
+// table preparation: float64 (n x k, ld) -> zero-padded float32 (n_pad x k_pad), score
+// threshold `x < thr -> 0` (similarity_matrix_constructor.py:139-140 with weight == 0),
+// per-row fp64 sum of the fp32 values and NaN flag.  One block per destination row.
+__global__ void prepare_table_kernel(const double* __restrict__ src, long long n, long long k,
+                                     long long ld_src, double thr, int apply_thr,
+                                     float* __restrict__ dst, long long k_pad,
+                                     double* __restrict__ rowsum, unsigned char* __restrict__ nanflag) {
+    const long long r = blockIdx.x;
+    float* d = dst + r * k_pad;
+    double s = 0.0;
+    int has_nan = 0;
+    if (r < n) {
+        const double* p = src + r * ld_src;
+        for (long long c = threadIdx.x; c < k_pad; c += blockDim.x) {
+            float f = 0.f;
+            if (c < k) {
+                double v = p[c];
+                if (apply_thr && v < thr) v = 0.0;
+                f = (float)v;
+                if (isnan(v)) has_nan = 1;
+                s += (double)f;
+            }
+            d[c] = f;
+        }
+    } else {
+        for (long long c = threadIdx.x; c < k_pad; c += blockDim.x) d[c] = 0.f;
+    }
+    __shared__ double red[32];
+    __shared__ int rnan;
+    if (threadIdx.x == 0) rnan = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    if (has_nan) rnan = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && r < n) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        if (rowsum) rowsum[r] = t;
+        if (nanflag) nanflag[r] = (unsigned char)rnan;
+    }
+}
+
+// weighted row sums: out[b][i] = sum_c w[b][c] * T[i][c]  (fp64).  grid = (n, nb)
+__global__ void weighted_rowsum_kernel(const float* __restrict__ tab, long long k_pad,
+                                       const float* __restrict__ w, long long w_stride,
+                                       long long n, double* __restrict__ out) {
+    const long long r = blockIdx.x, b = blockIdx.y;
+    const float* t = tab + r * k_pad;
+    const float* ww = w + b * w_stride;
+    double s = 0.0;
+    for (long long c = threadIdx.x * 4; c < k_pad; c += blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(t + c);
+        float4 q = *reinterpret_cast<const float4*>(ww + c);
+        s += (double)v.x * q.x + (double)v.y * q.y + (double)v.z * q.z + (double)v.w * q.w;
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tt = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tt += red[i];
+        out[b * n + r] = tt;
+    }
+}
+
+// int32 column multiplicities -> fp32 weights, zero-padded to k_pad.  grid = (ceil(k_pad/256), nb)
+__global__ void weights_to_float_kernel(const int* __restrict__ w, long long k, long long k_pad,
+                                        float* __restrict__ out) {
+    long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long b = blockIdx.y;
+    if (c < k_pad) out[b * k_pad + c] = c < k ? (float)w[b * k + c] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 epilogue: NaN/negative clean, scheme combine, clamp, **p, optional 1-S, mirror.
+// similarity_matrix_constructor.py:201-226, pl1_graphs.py:52-53.
+// One block per 32x32 sub-block of a 128x128 tile: grid = (tiles*16, nb), block = (32, 8).
+struct GjComp {
+    const double* ws;        // [nb][ksplit][ntl][128*128] or null
+    const double* rowsum;    // [nb][n]
+    const unsigned char* nan;  // [nb][n] or null
+    int ksplit;
+    long long b_stride_ws;   // elements between replicates in ws (0 = shared by all replicates)
+    long long b_stride_row;  // elements between replicates in rowsum (0 = shared)
+    long long b_stride_nan;  // elements between replicates in nan (0 = shared)
+};
+
+__device__ __forceinline__ double gj_value(const GjComp& c, long long b, long long ntl,
+                                           long long t, int r, int cc, long long gi, long long gj) {
+    const double* w = c.ws + b * c.b_stride_ws + t * (long long)(GV2_TILE * GV2_TILE) + r * GV2_TILE + cc;
+    double smin = 0.0;
+    for (int ks = 0; ks < c.ksplit; ++ks) smin += w[(long long)ks * ntl * (GV2_TILE * GV2_TILE)];
+    const double* rs = c.rowsum + b * c.b_stride_row;
+    double si = rs[gi], sj = rs[gj];
+    if (gi == gj) smin = si;                       // diagonal: sum(min) == sum(a) exactly
+    double smax = si + sj - smin;
+    double v = (smax == 0.0) ? 0.0 : smin / smax;  // `if not sum(max) == 0 else 0`, :168
+    if (c.nan) {
+        const unsigned char* nf = c.nan + b * c.b_stride_nan;
+        if (nf[gi] | nf[gj]) v = nan("");
+    }
+    if (isnan(v) || v < 0.0) v = 0.0;              // :204-205
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+gj_epilogue_kernel(long long n, int nt, long long tile_begin, long long ntl, GjComp P, GjComp G,
+                   const double* __restrict__ spr, int scheme, double pw, int out_kind,
+                   int packed, double* __restrict__ out, long long out_b_stride) {
+    __shared__ double tr[32][33];
+    const long long t = blockIdx.x >> 4;
+    const int sub = blockIdx.x & 15, sr = sub >> 2, sc = sub & 3;
+    const long long b = blockIdx.y;
+    int bi, bj;
+    gv2_tile_coords(tile_begin + t, nt, &bi, &bj);
+    double* o = out + b * out_b_stride;
+    const int lx = threadIdx.x;
+    const bool mirror = !packed && (bi != bj || sr != sc);
+    if (!packed && bi == bj && sr > sc) return;     // lower sub-blocks of a diagonal tile
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy) {
+        const int ly = threadIdx.y + yy * 8;
+        const int r = sr * 32 + ly, c = sc * 32 + lx;
+        const long long gi = (long long)bi * GV2_TILE + r, gj = (long long)bj * GV2_TILE + c;
+        double s = 0.0;
+        if (gi < n && gj < n) {
+            double vp = 0.0, vg = 0.0, vr = 0.0;
+            if (scheme == GV2_SCHEME_P || scheme == GV2_SCHEME_PG || scheme == GV2_SCHEME_PR)
+                vp = gj_value(P, b, ntl, t, r, c, gi, gj);
+            if (scheme == GV2_SCHEME_G || scheme == GV2_SCHEME_PG || scheme == GV2_SCHEME_RG)
+                vg = gj_value(G, b, ntl, t, r, c, gi, gj);
+            if (scheme == GV2_SCHEME_PL) vp = gj_value(P, b, ntl, t, r, c, gi, gj);
+            if (scheme == GV2_SCHEME_R || scheme == GV2_SCHEME_RG || scheme == GV2_SCHEME_PR)
+                vr = spr[gi * n + gj];
+            if (scheme == GV2_SCHEME_L || scheme == GV2_SCHEME_PL) {   // aux = location dCor matrix
+                vr = spr[gi * n + gj];
+                if (isnan(vr) || vr < 0.0) vr = 0.0;                   // :201-205 cleans "L" too
+            }
+            switch (scheme) {
+                case GV2_SCHEME_P: s = vp; break;
+                case GV2_SCHEME_G: s = vg; break;
+                case GV2_SCHEME_PG: s = sqrt(vp * vg); break;     // (P*G)**0.5, :214
+                case GV2_SCHEME_R: s = vr; break;
+                case GV2_SCHEME_RG: s = sqrt(vr * vg); break;     // :220
+                case GV2_SCHEME_PR: s = sqrt(vr * vp); break;     // :222
+                case GV2_SCHEME_L: s = vr; break;                 // :212
+                case GV2_SCHEME_PL: s = vp * vr; break;           // :216
+            }
+            if (s < 0.0) s = 0.0;                                 // :224
+            if (pw != 1.0) s = pow(s, pw);                        // :226
+            if (out_kind == GV2_OUT_DISTANCE) {                   // pl1_graphs.py:52-53
+                s = 1.0 - s;
+                if (s < 0.0) s = 0.0;
+            }
+            if (packed) o[t * (long long)(GV2_TILE * GV2_TILE) + r * GV2_TILE + c] = s;
+            else o[gi * n + gj] = s;
+        } else if (packed) {
+            o[t * (long long)(GV2_TILE * GV2_TILE) + r * GV2_TILE + c] = 0.0;
+        }
+        tr[ly][lx] = s;
+    }
+    if (!mirror) return;
+    __syncthreads();
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy) {
+        const int ly = threadIdx.y + yy * 8;
+        // element (row = sc*32+ly of block bj, col = sr*32+lx of block bi) = value[lx][ly]
+        const long long gj = (long long)bj * GV2_TILE + sc * 32 + ly;
+        const long long gi = (long long)bi * GV2_TILE + sr * 32 + lx;
+        if (gi < n && gj < n) o[gj * n + gi] = tr[lx][ly];
+    }
+}
+
+// packed tiles [ntl][128*128] -> symmetric n x n (after an all-gather of tile blocks).
+__global__ void __launch_bounds__(256)
+unpack_tiles_kernel(long long n, int nt, long long tile_begin, const double* __restrict__ packed,
+                    double* __restrict__ out) {
+    __shared__ double tr[32][33];
+    const long long t = blockIdx.x >> 4;
+    const int sub = blockIdx.x & 15, sr = sub >> 2, sc = sub & 3;
+    int bi, bj;
+    gv2_tile_coords(tile_begin + t, nt, &bi, &bj);
+    if (bi == bj && sr > sc) return;
+    const int lx = threadIdx.x;
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy) {
+        const int ly = threadIdx.y + yy * 8;
+        const int r = sr * 32 + ly, c = sc * 32 + lx;
+        const long long gi = (long long)bi * GV2_TILE + r, gj = (long long)bj * GV2_TILE + c;
+        double s = packed[t * (long long)(GV2_TILE * GV2_TILE) + r * GV2_TILE + c];
+        if (gi < n && gj < n) out[gi * n + gj] = s;
+        tr[ly][lx] = s;
+    }
+    if (bi == bj && sr == sc) return;
+    __syncthreads();
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy) {
+        const int ly = threadIdx.y + yy * 8;
+        const long long gj = (long long)bj * GV2_TILE + sc * 32 + ly;
+        const long long gi = (long long)bi * GV2_TILE + sr * 32 + lx;
+        if (gi < n && gj < n) out[gj * n + gi] = tr[lx][ly];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers (C ABI; declared in include/gravity2_b200.h)
+static size_t gj_smem_bytes() {
+    return (size_t)(2 * GJ_STAGES * GV2_TILE * GJ_LDS + GJ_STAGES * GV2_BK) * sizeof(float);
+}
+
+extern "C" int64_t gv2_num_tiles(int64_t n) {
+    int64_t nt = (n + GV2_TILE - 1) / GV2_TILE;
+    return nt * (nt + 1) / 2;
+}
+
+extern "C" int gv2_dev_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k,
+                                     int64_t ld_src, double threshold, int apply_threshold,
+                                     float* dst, int64_t n_pad, int64_t k_pad, double* rowsum,
+                                     uint8_t* nanflag) {
+    if (!ctx || !src || !dst || n < 0 || k < 0 || n_pad < n || k_pad < k || (k_pad % GV2_BK) ||
+        (n_pad % GV2_TILE))
+        return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_prepare_table: bad arguments");
+    if (n_pad == 0) return GV2_OK;
+    prepare_table_kernel<<<(unsigned)n_pad, 256, 0, ctx->stream>>>(src, n, k, ld_src, threshold,
+                                                                    apply_threshold, dst, k_pad, rowsum, nanflag);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+extern "C" int gv2_dev_weights_to_float(gv2_ctx* ctx, const int32_t* w, int64_t nb, int64_t k,
+                                        int64_t k_pad, float* out) {
+    if (!ctx || !w || !out || nb <= 0) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_weights_to_float: bad arguments");
+    dim3 grid((unsigned)((k_pad + 255) / 256), (unsigned)nb);
+    weights_to_float_kernel<<<grid, 256, 0, ctx->stream>>>(w, k, k_pad, out);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+extern "C" int gv2_dev_weighted_rowsums(gv2_ctx* ctx, const float* tab, int64_t n, int64_t k_pad,
+                                        const float* w, int64_t nb, double* out) {
+    if (!ctx || !tab || !w || !out) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_weighted_rowsums: bad arguments");
+    if (n == 0 || nb == 0) return GV2_OK;
+    dim3 grid((unsigned)n, (unsigned)nb);
+    weighted_rowsum_kernel<<<grid, 256, 0, ctx->stream>>>(tab, k_pad, w, k_pad, n, out);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n_pad, int64_t k_pad,
+                       int64_t tile_begin, int64_t tile_end, const float* w, int64_t nb, int ksplit,
+                       double* ws) {
+    if (!ctx || !tab || !ws || nb <= 0 || ksplit <= 0 || tile_end < tile_begin || (k_pad % GV2_BK) ||
+        (n_pad % GV2_TILE))
+        return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_gj_min_sums: bad arguments");
+    const int64_t ntl = tile_end - tile_begin;
+    if (ntl == 0) return GV2_OK;
+    if (tile_end > gv2_num_tiles(n_pad)) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_gj_min_sums: tile range");
+    if (nb > 65535 || ksplit > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_gj_min_sums: nb/ksplit > 65535");
+    static bool attr_done = false;
+    size_t smem = gj_smem_bytes();
+    if (!attr_done) {
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)ntl, (unsigned)ksplit, (unsigned)nb);
+    const int nt = (int)(n_pad / GV2_TILE);
+    const int kblocks = (int)(k_pad / GV2_BK);
+    if (w)
+        gj_min_tile_kernel<true><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, w, k_pad, ws);
+    else
+        gj_min_tile_kernel<false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, nullptr, 0, ws);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+extern "C" int gv2_dev_gj_min_sums(gv2_ctx* ctx, const float* tab, int64_t n_pad, int64_t k_pad,
+                                   int64_t tile_begin, int64_t tile_end, const float* w,
+                                   int64_t nb, int ksplit, double* ws) {
+    if (!w && nb != 1) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_gj_min_sums: nb must be 1 without weights");
+    return gj_min_sums_launch(ctx, tab, 0, n_pad, k_pad, tile_begin, tile_end, w, nb, ksplit, ws);
+}
+
+static GjComp to_comp(const gv2_gj_component* c) {
+    GjComp r{};
+    if (c) {
+        r.ws = c->min_sums; r.rowsum = c->rowsums; r.nan = c->nanflags; r.ksplit = c->ksplit;
+        r.b_stride_ws = c->replicate_stride_sums; r.b_stride_row = c->replicate_stride_rows;
+        r.b_stride_nan = c->replicate_stride_nan;
+    }
+    return r;
+}
+
+extern "C" int gv2_dev_gj_epilogue(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_t tile_end,
+                                   int64_t nb, const gv2_gj_component* comp_p,
+                                   const gv2_gj_component* comp_g, const double* spr, int scheme,
+                                   double p, int out_kind, int packed, double* out,
+                                   int64_t out_replicate_stride) {
+    if (!ctx || !out || n < 0 || nb <= 0 || tile_end < tile_begin)
+        return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_gj_epilogue: bad arguments");
+    const bool need_p = scheme == GV2_SCHEME_P || scheme == GV2_SCHEME_PG || scheme == GV2_SCHEME_PR || scheme == GV2_SCHEME_PL;
+    const bool need_g = scheme == GV2_SCHEME_G || scheme == GV2_SCHEME_PG || scheme == GV2_SCHEME_RG;
+    const bool need_r = scheme == GV2_SCHEME_R || scheme == GV2_SCHEME_RG || scheme == GV2_SCHEME_PR ||
+                        scheme == GV2_SCHEME_L || scheme == GV2_SCHEME_PL;
+    if (scheme < GV2_SCHEME_P || scheme > GV2_SCHEME_PL)
+        return gv2_fail(ctx, GV2_ERR_ARG, "unknown similarity scheme %d", scheme);
+    if ((need_p && (!comp_p || !comp_p->min_sums || !comp_p->rowsums)) ||
+        (need_g && (!comp_g || !comp_g->min_sums || !comp_g->rowsums)) || (need_r && !spr))
+        return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_gj_epilogue: scheme %d is missing an input", scheme);
+    const int64_t ntl = tile_end - tile_begin;
+    if (ntl == 0 || n == 0) return GV2_OK;
+    const int nt = (int)((n + GV2_TILE - 1) / GV2_TILE);
+    dim3 grid((unsigned)(ntl * 16), (unsigned)nb), block(32, 8);
+    gj_epilogue_kernel<<<grid, block, 0, ctx->stream>>>(n, nt, tile_begin, ntl, to_comp(comp_p), to_comp(comp_g),
+                                                        spr, scheme, p, out_kind, packed, out, out_replicate_stride);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+extern "C" int gv2_dev_unpack_tiles(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_t tile_end,
+                                    const double* packed, double* out) {
+    if (!ctx || !packed || !out || tile_end < tile_begin) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_unpack_tiles: bad arguments");
+    const int64_t ntl = tile_end - tile_begin;
+    if (ntl == 0 || n == 0) return GV2_OK;
+    const int nt = (int)((n + GV2_TILE - 1) / GV2_TILE);
+    dim3 block(32, 8);
+    unpack_tiles_kernel<<<(unsigned)(ntl * 16), block, 0, ctx->stream>>>(n, nt, tile_begin, packed, out);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}

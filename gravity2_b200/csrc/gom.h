@@ -1,0 +1,33 @@
+// Device-side GOM database (internal).  See gom_kernels.cu.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+struct gv2_ctx;
+
+struct GomDb {
+    int64_t n = 0, p = 0, G = 0;
+    long long nnz = 0;          // non-zero location entries of the scored genomes
+    int npt = 0;                // sum over GOMs of |R_g|
+    int max_ng = 0, max_t = 0;
+    long long ilist_stride = 0, wave = 0;
+    size_t bytes = 0;
+    // genome CSR
+    long long* g_ptr = nullptr; int* g_col = nullptr; double* g_val = nullptr;
+    // GOM members and point sets
+    int* mem_ptr = nullptr; long long* mem_row = nullptr;
+    int* pt_ptr = nullptr; int* pt_col = nullptr; int* pos = nullptr;
+    long long* x_off = nullptr; long long* a_off = nullptr;
+    double* X = nullptr; double* nrm = nullptr; double* A = nullptr;
+    // per-chunk scratch (32 replicates)
+    double* wT = nullptr; double* arT = nullptr; double* sqT = nullptr; double* rT = nullptr;
+    double* gagg = nullptr; double* vagg = nullptr; int* ilist = nullptr;
+};
+
+int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t ld_loc,
+                 const double* rowtab, int64_t ld_row, const int64_t* mem_row_h,
+                 const int32_t* mem_ptr_h, int64_t G, int flags, GomDb** out);
+int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, double* out);
+void gom_db_free(GomDb* db);

@@ -1,0 +1,214 @@
+"""Drop-in replacements for the reference's hot-path functions (same names, argument order,
+argument meaning, return shapes/dtypes and error behaviour), computing on a B200 through
+libgravity_b200.  Import paths mirroring the reference's live under ``gravity2_b200.app.utils``.
+
+Reference (Mayne941/gravity2) interfaces replaced here:
+  SimilarityMat_Constructor        app/utils/similarity_matrix_constructor.py:7-226
+  GOMDB_Constructor                app/utils/gomdb_constructor.py:2-8
+  GOMSignatureTable_Constructor    app/utils/parallel_gom_sig_generator.py:10-28 (5-arg) and
+                                   app/utils/gom_signature_table_constructor.py:34-52 (4-arg)
+  generate_gom_sigs                app/utils/parallel_gom_sig_generator.py:30-37
+  dcor                             app/utils/dcor.py:34-62
+  shared_pphmm_ratio / shared_norm_pphmm_ratio   app/utils/shared_pphmm_graphs.py:59-97
+  bootstrap loop bodies            app/src/pl1_graphs.py:78-107, app/src/virus_classification.py:290-315
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Sequence
+
+import numpy as np
+
+from .engine import Engine, default_engine
+
+
+# ------------------------------------------------------------------------------ similarity
+def SimilarityMat_Constructor(PPHMMSignatureTable, GOMSignatureTable, PPHMMLocationTable, SPRSignatureTable,
+                              pphmm_neighbourhood_weight, pphmm_signature_score_threshold,
+                              SimilarityMeasurementScheme="PG", p=1.0, fnames=False, engine: Optional[Engine] = None):
+    """Similarity matrix for the given scheme and p: float64 (N, N), fresh array.
+
+    ``fnames`` is accepted and ignored: the reference re-reads two CSVs from it to build
+    neighbourhood index lists that have no effect unless ``pphmm_neighbourhood_weight != 0``
+    (SURVEY quirk Q2).  With a non-zero weight the reference's result depends on how often each
+    row has been touched by the pair loop (quirk Q1); that mode is not built and raises."""
+    if pphmm_neighbourhood_weight != 0:
+        raise NotImplementedError(
+            "PphmmNeighbourhoodWeight != 0 (in-place, visit-count dependent row scaling of "
+            "similarity_matrix_constructor.py:120-140) is not implemented on the B200 path")
+    scheme = SimilarityMeasurementScheme
+    eng = engine or default_engine()
+    thr = pphmm_signature_score_threshold
+    aux = None
+    if "R" in scheme:
+        aux = SPRSignatureTable
+    if "L" in scheme:
+        aux = eng.location_dcor_matrix(PPHMMLocationTable)
+    S = eng.similarity(PPHMMSignatureTable, GOMSignatureTable, aux, scheme, float(p), float(thr),
+                       apply_threshold=("P" in scheme), distance=False)
+    if "P" in scheme and isinstance(PPHMMSignatureTable, np.ndarray):
+        # the reference zeroes `row < threshold` in the CALLER's table (views, :116-140); keep that side effect
+        PPHMMSignatureTable[PPHMMSignatureTable < thr] = 0
+    return S
+
+
+def dist_mat_constructor(PPHMMSignatureTable, GOMSignatureTable, PPHMMLocationTable, SPRSignatureTable, payload,
+                         fnames=None, engine: Optional[Engine] = None):
+    """GRAViTyDendrogramAndHeatmapConstruction.dist_mat_constructor, app/src/pl1_graphs.py:40-54."""
+    SimMat = SimilarityMat_Constructor(PPHMMSignatureTable, GOMSignatureTable, PPHMMLocationTable, SPRSignatureTable,
+                                       payload["PphmmNeighbourhoodWeight"], payload["PphmmSigScoreThreshold"],
+                                       payload["SimilarityMeasurementScheme"], payload["p"], fnames, engine=engine)
+    DistMat = 1 - SimMat
+    DistMat[DistMat < 0] = 0
+    return DistMat
+
+
+# ------------------------------------------------------------------------------------ GOM
+def GOMDB_Constructor(TaxoGroupingList, PPHMMLocationTable, GOMIDList):
+    """GOM database: dict id -> member rows.  A host-side gather (numpy boolean mask)."""
+    GOMDb = {}
+    for id in GOMIDList:
+        GOMDb[id] = PPHMMLocationTable[TaxoGroupingList == id, :]
+    return GOMDb
+
+
+def _gom_rows(GOMDB, ids, p):
+    rows = [np.asarray(GOMDB[g], dtype=np.float64).reshape(-1, p) for g in ids]
+    offs = np.zeros(len(ids) + 1, dtype=np.int64)
+    offs[1:] = np.cumsum([r.shape[0] for r in rows])
+    cat = np.concatenate(rows, axis=0) if rows and offs[-1] > 0 else np.zeros((0, p))
+    return cat, offs
+
+
+def GOMSignatureTable_Constructor(PPHMMLocationTable, GOMDB, GOMIDList, payload=None, bootstrap=0,
+                                  engine: Optional[Engine] = None):
+    """(N, G) float64 GOM signature table, columns in GOMIDList order.  Accepts both reference
+    signatures (4-arg twin without ``payload``; ``payload['N_CPUs']`` is ignored)."""
+    if not isinstance(payload, (dict, type(None))):       # 4-arg twin: (loc, GOMDB, ids, bootstrap)
+        bootstrap, payload = payload, None
+    if bootstrap != 0:
+        print(f"- (Re-)Constructing GOM Signature Table, bootstrap iteration: {bootstrap+1}")
+    loc = np.asarray(PPHMMLocationTable, dtype=np.float64)
+    if len(GOMIDList) == 0:
+        return np.empty((len(loc), 0))
+    cat, offs = _gom_rows(GOMDB, list(GOMIDList), loc.shape[1])
+    return (engine or default_engine()).gom_table(loc, cat, offs)
+
+
+def generate_gom_sigs(GOM, PPHMMLocationTable, GOMDB, engine: Optional[Engine] = None):
+    """One GOM column as a list of floats."""
+    loc = np.asarray(PPHMMLocationTable, dtype=np.float64)
+    cat, offs = _gom_rows(GOMDB, [GOM], loc.shape[1])
+    return [float(x) for x in (engine or default_engine()).gom_table(loc, cat, offs)[:, 0]]
+
+
+def dcor(X, Y, engine: Optional[Engine] = None):
+    """Distance correlation of X (n, m) and Y (n, 1) -- KAT dcor([1..5],[1,2,9,4,4]) = 0.76267624241686649."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    assert X.shape[0] == Y.shape[0]
+    if Y.ndim != 2 or Y.shape[1] != 1:
+        raise NotImplementedError("device dcor takes Y of shape (n, 1), as every reference call site passes")
+    n = X.shape[0]
+    if n == 0:
+        return 0.0
+    rows = np.ascontiguousarray(X.reshape(n, -1).T)
+    out = (engine or default_engine()).gom_table(Y.reshape(1, n), rows, np.array([0, rows.shape[0]]), all_columns=True)
+    return float(out[0, 0])
+
+
+# ------------------------------------------------------------------------- presence / absence
+def _sig_array(fnames, label_order):
+    """get_sig_data, app/utils/shared_pphmm_graphs.py:16-21."""
+    import pandas as pd
+    df = pd.read_csv(fnames["PphmmAndGomSigs"], index_col=0)
+    df = df.iloc[:, 1:]
+    df = df.apply(pd.to_numeric)
+    return np.asarray(df.reindex(label_order))
+
+
+def shared_pphmm_counts(arr, engine: Optional[Engine] = None):
+    return (engine or default_engine()).shared_counts(arr)
+
+
+def shared_pphmm_ratio(label_order, fnames, labels, engine: Optional[Engine] = None):
+    """Matrix of PPHMM co-occurrence counts: list of lists of Python ints."""
+    inter, _ = shared_pphmm_counts(_sig_array(fnames, label_order), engine)
+    return inter.tolist()
+
+
+def shared_norm_pphmm_ratio_from_array(arr, engine: Optional[Engine] = None):
+    inter, nnz = shared_pphmm_counts(arr, engine)
+    mp = np.minimum(nnz[:, None], nnz[None, :]).astype(np.int64)
+    hits = inter.astype(np.int64)
+    lo, hi = np.minimum(hits, mp), np.maximum(hits, mp)
+    if (hi == 0).any():
+        raise ZeroDivisionError("division by zero")        # Python ints in the reference, :86
+    return (lo / hi).T.copy()
+
+
+def shared_norm_pphmm_ratio(label_order, fnames, labels, engine: Optional[Engine] = None):
+    """Normalised ratio of shared PPHMMs, float64 (N, N); 0/0 raises ZeroDivisionError as the reference."""
+    return shared_norm_pphmm_ratio_from_array(_sig_array(fnames, label_order), engine)
+
+
+def binary_jaccard(trait_table, engine: Optional[Engine] = None):
+    """PPHMM x PPHMM binary Jaccard of RefVirusAnnotator.sort_pphmm (app/src/ref_virus_annotator.py:148-158):
+    popcount(a & b) / popcount(a | b), NaN for two empty rows (no zero guard in the reference)."""
+    inter, nnz = shared_pphmm_counts(trait_table, engine)
+    union = nnz[:, None].astype(np.int64) + nnz[None, :] - inter
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return inter / union
+
+
+# ------------------------------------------------------------------------------ bootstrap
+def draw_resample_indices(n_pphmms: int, sort: bool = False):
+    """The reference's own draw from numpy's global legacy RNG (pl1_graphs.py:81-82; sorted in
+    virus_classification.py:295-296), keeping that stream in step with the reference's later draws."""
+    idx = np.random.choice(list(range(n_pphmms)), n_pphmms, replace=True)
+    return np.array(sorted(idx)) if sort else idx
+
+
+def weights_from_indices(idx, n_pphmms: int):
+    return np.bincount(np.asarray(idx, dtype=np.int64), minlength=n_pphmms).astype(np.int32)
+
+
+def gom_membership(TaxoGroupingList, GOMIDList, n_rows: Optional[int] = None):
+    """int32 GOM index per table row (-1 = not in any GOM), the device form of GOMDB_Constructor."""
+    taxo = np.asarray(TaxoGroupingList)
+    out = np.full(len(taxo) if n_rows is None else n_rows, -1, dtype=np.int32)
+    for k, g in enumerate(GOMIDList):
+        out[: len(taxo)][taxo == g] = k
+    return out
+
+
+def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, GOMIDList, payload,
+                                N_Bootstrap: Optional[int] = None, pipeline: str = "pl1", indices=None,
+                                batch: int = 64, distance: bool = True,
+                                engine: Optional[Engine] = None) -> Iterator[np.ndarray]:
+    """Yields one (N, N) float64 matrix per bootstrap replicate, in the reference's order.
+
+    pipeline="pl1": app/src/pl1_graphs.py:78-107 -- unsorted indices, and the bootstrapped SIGNATURE
+    table doubles as the location table; yields D.
+    pipeline="pl2": app/src/virus_classification.py:290-315 -- sorted indices, real location table,
+    GOMDB from the first len(TaxoGroupingList) rows.
+    ``indices`` (B, P) overrides the draw (e.g. Engine.philox_indices); by default indices are drawn
+    exactly as the reference draws them, replicate by replicate."""
+    eng = engine or default_engine()
+    sig = np.ascontiguousarray(PPHMMSignatureTable, dtype=np.float64)
+    n, p = sig.shape
+    nb = int(payload["N_Bootstrap"] if N_Bootstrap is None else N_Bootstrap)
+    scheme = payload["SimilarityMeasurementScheme"]
+    if payload.get("PphmmNeighbourhoodWeight", 0) != 0 or payload.get("PphmmSigScoreThreshold", 0) != 0:
+        raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
+    loc = sig if pipeline == "pl1" else np.ascontiguousarray(PPHMMLocationTable, dtype=np.float64)
+    gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
+    for b0 in range(0, nb, batch):
+        cb = min(batch, nb - b0)
+        if indices is None:
+            idx = [draw_resample_indices(p, sort=(pipeline == "pl2")) for _ in range(cb)]
+        else:
+            idx = indices[b0:b0 + cb]
+        w = np.stack([weights_from_indices(i, p) for i in idx])
+        out = eng.bootstrap(sig, loc, gor, len(GOMIDList), w, scheme, float(payload.get("p", 1.0)), distance=distance)
+        for k in range(cb):
+            yield out[k]

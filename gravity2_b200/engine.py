@@ -1,0 +1,164 @@
+"""Host-side engine: numpy in, numpy out, every computation through the C ABI on a B200.
+
+One ``Engine`` = one ``gv2_ctx`` (one CUDA device + stream).  The module-level
+``default_engine()`` is created lazily on first use, never at import time, so that a process
+that later forks ``multiprocessing.Pool`` workers (the reference does, upstream of this path:
+app/utils/parallel_sig_generator.py:51) has not initialised CUDA just by importing us.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterator, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import GravityNativeError, SCHEMES, OUT_DISTANCE, OUT_SIMILARITY  # noqa: F401
+
+
+def _f64(a, name) -> np.ndarray:
+    a = np.asarray(a)
+    if a.ndim != 2:
+        raise ValueError(f"{name} must be 2-D, got shape {a.shape}")
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, device: Optional[int] = None):
+        self.lib = _lib.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", os.environ.get("GRAVITY_B200_DEVICE", "0")))
+        h = C.c_void_p()
+        rc = self.lib.gv2_create(int(device), C.byref(h))
+        if rc != _lib.OK:
+            msg = self.lib.gv2_last_error(None)
+            raise GravityNativeError(rc, msg.decode() if msg else "?")
+        self.ctx = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.gv2_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.gv2_launch_count(self.ctx))
+
+    def synchronize(self):
+        _lib.check(self.ctx, self.lib.gv2_synchronize(self.ctx))
+
+    # ---------------------------------------------------------------- similarity (a1, a3-a7)
+    def similarity(self, sig, gom, aux, scheme: str = "PG", p: float = 1.0, threshold: float = 0.0,
+                   apply_threshold: bool = False, distance: bool = False) -> np.ndarray:
+        if scheme not in SCHEMES:
+            raise ValueError(f"unknown SimilarityMeasurementScheme {scheme!r}")
+        need_p = "P" in scheme
+        need_g = "G" in scheme
+        need_aux = "R" in scheme or "L" in scheme
+        sig = _f64(sig, "PPHMMSignatureTable") if need_p else None
+        gom = _f64(gom, "GOMSignatureTable") if need_g else None
+        aux = _f64(aux, "SPRSignatureTable / location dCor matrix") if need_aux else None
+        n = (sig if sig is not None else gom if gom is not None else aux).shape[0]
+        for a in (sig, gom, aux):
+            if a is not None and a.shape[0] != n:
+                raise ValueError("tables disagree on the number of genomes")
+        if aux is not None and aux.shape != (n, n):
+            raise ValueError(f"aux matrix must be ({n}, {n})")
+        out = np.empty((n, n), dtype=np.float64)
+        rc = self.lib.gv2_similarity_host(
+            self.ctx, _ptr(sig), n, 0 if sig is None else sig.shape[1], 0 if sig is None else sig.shape[1],
+            _ptr(gom), 0 if gom is None else gom.shape[1], 0 if gom is None else gom.shape[1], _ptr(aux),
+            SCHEMES[scheme], float(p), float(threshold), int(bool(apply_threshold)),
+            OUT_DISTANCE if distance else OUT_SIMILARITY, _ptr(out))
+        _lib.check(self.ctx, rc)
+        return out
+
+    # --------------------------------------------------------------------- GOM table (a11-a13)
+    def gom_table(self, loc, gom_rows, gom_offsets, weights=None, all_columns: bool = False) -> np.ndarray:
+        loc = _f64(loc, "PPHMMLocationTable")
+        n, p = loc.shape
+        offs = np.ascontiguousarray(gom_offsets, dtype=np.int64)
+        g = len(offs) - 1
+        gom_rows = _f64(gom_rows, "GOM rows") if offs[-1] > 0 else np.zeros((0, p))
+        if gom_rows.shape[1] != p or gom_rows.shape[0] != offs[-1]:
+            raise ValueError("GOM rows do not match the location table / offsets")
+        nb = 1
+        w = None
+        if weights is not None:
+            w = np.ascontiguousarray(weights, dtype=np.int32)
+            if w.ndim == 1:
+                w = w[None, :]
+            if w.shape[1] != p:
+                raise ValueError("weights must be (B, P)")
+            nb = w.shape[0]
+        out = np.zeros((nb, n, g), dtype=np.float64)
+        rc = self.lib.gv2_gom_table_host(self.ctx, _ptr(loc), n, p, p, _ptr(gom_rows), p, _ptr(offs), g, _ptr(w), nb,
+                                         _lib.GOM_ALL_COLUMNS if all_columns else 0, _ptr(out))
+        _lib.check(self.ctx, rc)
+        return out if weights is not None else out[0]
+
+    def location_dcor_matrix(self, loc) -> np.ndarray:
+        """Scheme "L": dcor of two genomes' location vectors over the union of their hits
+        (similarity_matrix_constructor.py:179-186) = GOM table with one single-member GOM per genome."""
+        loc = _f64(loc, "PPHMMLocationTable")
+        return self.gom_table(loc, loc, np.arange(loc.shape[0] + 1))
+
+    # ------------------------------------------------------------------ presence/absence (a14-a16)
+    def shared_counts(self, tab):
+        tab = _f64(tab, "signature table")
+        n, p = tab.shape
+        inter = np.empty((n, n), dtype=np.int32)
+        nnz = np.empty((n,), dtype=np.int32)
+        rc = self.lib.gv2_shared_counts_host(self.ctx, _ptr(tab), n, p, p, _ptr(inter), _ptr(nnz))
+        _lib.check(self.ctx, rc)
+        return inter, nnz
+
+    # ------------------------------------------------------------------------- bootstrap (a8, a9)
+    def bootstrap(self, sig, loc, gom_of_row, g: int, weights, scheme: str = "PG", p: float = 1.0,
+                  distance: bool = True) -> np.ndarray:
+        """All replicates at once: (B, N, N) float64.  ``gom_of_row[r]`` = GOM index of loc row r
+        (-1 = not a GOMDB member); ``weights`` (B, P) int32 = bincount of each resample index list."""
+        if scheme not in ("P", "G", "PG"):
+            raise NotImplementedError(f"batched bootstrap covers schemes P, G, PG (got {scheme!r})")
+        sig = _f64(sig, "PPHMMSignatureTable")
+        n, pp = sig.shape
+        same = loc is sig
+        loc = sig if same else (_f64(loc, "PPHMMLocationTable") if loc is not None else None)
+        w = np.ascontiguousarray(weights, dtype=np.int32)
+        if w.ndim == 1:
+            w = w[None, :]
+        nb = w.shape[0]
+        gor = None if gom_of_row is None else np.ascontiguousarray(gom_of_row, dtype=np.int32)
+        out = np.empty((nb, n, n), dtype=np.float64)
+        rc = self.lib.gv2_bootstrap_host(self.ctx, _ptr(sig), _ptr(loc), n, pp, _ptr(gor), 0 if gor is None else len(gor),
+                                         int(g), _ptr(w), nb, SCHEMES[scheme], float(p),
+                                         OUT_DISTANCE if distance else OUT_SIMILARITY, _ptr(out))
+        _lib.check(self.ctx, rc)
+        return out
+
+    def philox_indices(self, seed: int, n_boot: int, p: int) -> np.ndarray:
+        out = np.empty((n_boot, p), dtype=np.int64)
+        _lib.check(self.ctx, self.lib.gv2_philox_indices_host(self.ctx, C.c_uint64(seed), n_boot, p, _ptr(out)))
+        return out
+
+
+_default: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default
+    if _default is None:
+        _default = Engine()
+    return _default

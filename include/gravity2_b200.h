@@ -1,0 +1,192 @@
+/* libgravity_b200 -- C ABI of the B200 (sm_100a) pairwise genome-similarity engine.
+ *
+ * Drop-in boundary for the hot path of GRAViTy-V2 (Mayne941/gravity2): PPHMM / GOM
+ * signature tables -> generalised-Jaccard similarity matrices -> composite (PG) distance
+ * -> bootstrap replicate matrices, plus the GOM distance-correlation scoring and the
+ * presence/absence (popcount) matrices.  Citations are file:line in the reference checkout.
+ *
+ * Conventions
+ *   - plain C: pointers + int64 sizes; no C++ / torch types cross this boundary;
+ *   - every entry point returns int: GV2_OK (0) or a negative GV2_ERR_* code; the message is
+ *     read with gv2_last_error(ctx);
+ *   - "_host" entry points take HOST pointers owned by the caller (numpy arrays in the
+ *     reference's process) and return results in caller-owned host buffers;
+ *   - "gv2_dev_" entry points take DEVICE pointers on the context's device and enqueue work on
+ *     the context's stream without synchronising (the caller synchronises with gv2_synchronize
+ *     or its own stream);
+ *   - a context is single-caller (not re-entrant), like the reference's call sites
+ *     (SURVEY.md section 8b);
+ *   - there is NO CPU fallback: without a usable CUDA device gv2_create fails.
+ */
+#ifndef GRAVITY2_B200_H
+#define GRAVITY2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GV2_OK 0
+#define GV2_ERR_ARG (-1)
+#define GV2_ERR_CUDA (-2)
+#define GV2_ERR_NOMEM (-3)
+#define GV2_ERR_UNSUPPORTED (-4)
+#define GV2_ERR_ZERODIV (-5) /* shared_norm_pphmm_ratio 0/0, shared_pphmm_graphs.py:86 */
+
+/* SimilarityMeasurementScheme, similarity_matrix_constructor.py:207-222 */
+#define GV2_SCHEME_P 0
+#define GV2_SCHEME_G 1
+#define GV2_SCHEME_PG 2
+#define GV2_SCHEME_R 3
+#define GV2_SCHEME_RG 4
+#define GV2_SCHEME_PR 5
+#define GV2_SCHEME_L 6  /* `spr` then carries the location dCor matrix (gv2_gom_table_host, one GOM per genome) */
+#define GV2_SCHEME_PL 7
+
+#define GV2_OUT_SIMILARITY 0 /* SimilarityMat ** p, similarity_matrix_constructor.py:226 */
+#define GV2_OUT_DISTANCE 1   /* D = 1 - S; D[D<0] = 0, app/src/pl1_graphs.py:52-53 */
+
+#define GV2_TILE_EDGE 128 /* genome-pair tile edge; unit of multi-GPU sharding */
+
+typedef struct gv2_ctx gv2_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int gv2_version(void);
+int gv2_device_count(void);
+/* Binds to CUDA device `device` and creates a private stream.  Lazy: the first CUDA call in
+ * the process happens here, never at library load (fork safety). */
+int gv2_create(int device, gv2_ctx** out);
+/* Same, but enqueue on an existing cudaStream_t (e.g. torch's current stream). */
+int gv2_create_on_stream(int device, void* cuda_stream, gv2_ctx** out);
+void gv2_destroy(gv2_ctx* ctx);
+const char* gv2_last_error(const gv2_ctx* ctx); /* ctx may be NULL: last creation error */
+int gv2_synchronize(gv2_ctx* ctx);
+uint64_t gv2_launch_count(const gv2_ctx* ctx); /* kernels launched so far through ctx */
+
+/* ---- host-pointer entry points (what the reference-side binding calls) ----------------- */
+
+/* Replaces SimilarityMat_Constructor's pair loop + clean/combine/power for
+ * PphmmNeighbourhoodWeight == 0 (app/utils/similarity_matrix_constructor.py:112-226).
+ *   sig  [n][p] float64, row stride ld_sig   (NULL if the scheme has no "P")
+ *   gom  [n][g] float64, row stride ld_gom   (NULL if the scheme has no "G")
+ *   spr  [n][n] float64: SPRSignatureTable for R / RG / PR; the PPHMM-location dCor matrix
+ *        (:179-186, computed with gv2_gom_table_host) for L / PL; else NULL
+ *   apply_threshold != 0: entries `x < threshold` count as 0 (:139-140); the caller mirrors
+ *   that mutation onto its own array.
+ *   out  [n][n] float64, fresh symmetric matrix (S**p or D per out_kind). */
+int gv2_similarity_host(gv2_ctx* ctx, const double* sig, int64_t n, int64_t p, int64_t ld_sig,
+                        const double* gom, int64_t g, int64_t ld_gom, const double* spr,
+                        int scheme, double power, double threshold, int apply_threshold,
+                        int out_kind, double* out);
+
+/* Replaces GOMSignatureTable_Constructor / generate_gom_sigs
+ * (app/utils/parallel_gom_sig_generator.py:10-37, gom_signature_table_constructor.py:34-61).
+ *   loc       [n][p] float64 PPHMM location table of the genomes to score
+ *   gom_rows  [gom_offsets[g]][p] float64: the GOMDB members' location rows, GOM after GOM in
+ *             GOMIDList order; GOM k owns rows gom_offsets[k] .. gom_offsets[k+1]
+ *   weights   [nb][p] int32 column multiplicities (bootstrap resample as bincount of the
+ *             reference's index list) or NULL (nb = 1, all ones)
+ *   out       [nb][n][g] float64; NaN where the reference yields NaN (dcor.py:10).
+ * With one single-member GOM per genome (gom_rows = loc, gom_offsets = 0..n) the result is the
+ * PPHMM-location dCor matrix of scheme "L" (similarity_matrix_constructor.py:179-186). */
+int gv2_gom_table_host(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t ld_loc,
+                       const double* gom_rows, int64_t ld_gom_rows, const int64_t* gom_offsets,
+                       int64_t g, const int32_t* weights, int64_t nb, int flags, double* out);
+#define GV2_GOM_ALL_COLUMNS 1 /* flags: score over every column instead of the relevant set R
+                                 (plain dcor(X, Y) of app/utils/dcor.py:34-62) */
+
+/* Replaces shared_pphmm_ratio / the counts of shared_norm_pphmm_ratio
+ * (app/utils/shared_pphmm_graphs.py:59-97) and the binary Jaccard of
+ * RefVirusAnnotator.sort_pphmm (app/src/ref_virus_annotator.py:148-158): bit-packs
+ * `tab != 0` and counts co-present columns.
+ *   inter [n][n] int32 (popcount(a & b)), nnz [n] int32 (popcount(a)); bit-exact. */
+int gv2_shared_counts_host(gv2_ctx* ctx, const double* tab, int64_t n, int64_t p, int64_t ld,
+                           int32_t* inter, int32_t* nnz);
+
+/* Bootstrap replicate distance (or similarity) matrices: the loop bodies of
+ * app/src/pl1_graphs.py:78-107 and app/src/virus_classification.py:290-315 for all
+ * replicates [0, nb) in batched launches.
+ *   sig, loc   [n][p] float64 (PL1 passes the signature table as loc)
+ *   gom_of_row [n_gom_rows] int32: GOM index (0..g-1) of loc row r, or -1 if that row is not
+ *              a GOMDB member; only rows [0, n_gom_rows) can be members (PL2: the reference rows)
+ *   weights    [nb][p] int32 = bincount of each replicate's resample index list
+ *   out        [nb][n][n] float64 */
+int gv2_bootstrap_host(gv2_ctx* ctx, const double* sig, const double* loc, int64_t n, int64_t p,
+                       const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g,
+                       const int32_t* weights, int64_t nb, int scheme, double power,
+                       int out_kind, double* out);
+
+/* Counter-based (Philox4x32-10) resample indices, the device-RNG mode: out[b][k] in [0, p).
+ * The reference-identical mode draws the indices on the host with numpy's legacy MT19937
+ *  and passes their bincount as `weights`. */
+int gv2_philox_indices_host(gv2_ctx* ctx, uint64_t seed, int64_t nb, int64_t p, int64_t* out);
+int gv2_dev_philox_weights(gv2_ctx* ctx, uint64_t seed, int64_t b0, int64_t nb, int64_t p,
+                           int32_t* weights /* [nb][p] */);
+
+/* ---- device-resident job: tables stay in HBM across calls ------------------------------ */
+typedef struct gv2_job gv2_job;
+/* Uploads (or, with *_is_device != 0, reads in place) the float64 tables, converts them to the
+ * kernels' layouts and builds the GOM side structures.  loc / gom_of_row may be NULL when the
+ * scheme has no "G". */
+int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc, int tables_are_device,
+                   int64_t n, int64_t p, const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g,
+                   int scheme, double power, int out_kind, gv2_job** out);
+void gv2_job_destroy(gv2_job* job);
+/* Base (un-resampled) matrix for pair tiles [tile_begin, tile_end) of the upper triangle:
+ *   packed == 0: writes the tiles (and their mirrors) into dev_out [n][n];
+ *   packed != 0: dev_out is [tile_end-tile_begin][128*128] tile blocks (multi-GPU all-gather
+ *   payload; scatter with gv2_dev_unpack_tiles). */
+int gv2_job_base(gv2_job* job, int64_t tile_begin, int64_t tile_end, int packed, double* dev_out);
+/* Replicates [0, nb) given their device-resident weights; dev_out [nb][n][n]. */
+int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out);
+/* GOM signature table of the job's loc table under the given weights (NULL = base):
+ * dev_out [nb][n][g]. */
+int gv2_job_gom_table(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out);
+size_t gv2_job_device_bytes(const gv2_job* job);
+
+/* ---- device-pointer primitives ----------------------------------------------------------- */
+int64_t gv2_num_tiles(int64_t n); /* upper-triangular 128x128 tiles incl. diagonal */
+
+typedef struct {
+    const double* min_sums;        /* [nb][ksplit][tiles][128*128] from gv2_dev_gj_min_sums */
+    const double* rowsums;         /* [nb][n] sum_c w_c * x_c */
+    const uint8_t* nanflags;       /* [nb][n] row contains NaN, or NULL */
+    int32_t ksplit;
+    int64_t replicate_stride_sums; /* elements between replicates in min_sums (0 = shared) */
+    int64_t replicate_stride_rows; /* elements between replicates in rowsums (0 = shared) */
+    int64_t replicate_stride_nan;  /* elements between replicates in nanflags (0 = shared) */
+} gv2_gj_component;
+
+/* float64 [n][k] -> zero-padded float32 [n_pad][k_pad] (n_pad % 128 == 0, k_pad % 32 == 0),
+ * per-row sum and NaN flag. */
+int gv2_dev_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src,
+                          double threshold, int apply_threshold, float* dst, int64_t n_pad,
+                          int64_t k_pad, double* rowsum, uint8_t* nanflag);
+int gv2_dev_weights_to_float(gv2_ctx* ctx, const int32_t* w, int64_t nb, int64_t k, int64_t k_pad,
+                             float* out);
+int gv2_dev_weighted_rowsums(gv2_ctx* ctx, const float* tab, int64_t n, int64_t k_pad,
+                             const float* w, int64_t nb, double* out);
+/* K1: sum_c w_c * min(x_ic, x_jc) for pair tiles [tile_begin, tile_end), nb weight rows
+ * (w == NULL: nb must be 1, unweighted). */
+int gv2_dev_gj_min_sums(gv2_ctx* ctx, const float* tab, int64_t n_pad, int64_t k_pad,
+                        int64_t tile_begin, int64_t tile_end, const float* w, int64_t nb,
+                        int ksplit, double* ws);
+/* K3: clean / combine / clamp / power / (1 - S) / mirror. */
+int gv2_dev_gj_epilogue(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_t tile_end, int64_t nb,
+                        const gv2_gj_component* comp_p, const gv2_gj_component* comp_g,
+                        const double* spr, int scheme, double power, int out_kind, int packed,
+                        double* out, int64_t out_replicate_stride);
+int gv2_dev_unpack_tiles(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_t tile_end,
+                         const double* packed, double* out);
+/* K6: bit-pack `tab != 0` into [n_pad][words] uint64 rows; counts per pair tile range. */
+int gv2_dev_pack_presence(gv2_ctx* ctx, const double* tab, int64_t n, int64_t p, int64_t ld,
+                          uint64_t* bits, int64_t n_pad, int64_t words, int32_t* nnz);
+int gv2_dev_shared_counts(gv2_ctx* ctx, const uint64_t* bits, int64_t n, int64_t n_pad,
+                          int64_t words, int64_t tile_begin, int64_t tile_end, int32_t* inter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAVITY2_B200_H */

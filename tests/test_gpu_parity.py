@@ -1,0 +1,262 @@
+"""GPU parity tests (run with -m gpu on a B200): every call goes through the C ABI
+(libgravity_b200.so) and is compared with the CPU oracle / the reference's golden outputs.
+Tolerances: bit-exact for counts and indices; rel 1e-6 on score-based similarities
+(BASELINE.json north_star); the fp64 GOM/dCor path is held to 1e-9."""
+import os
+import tempfile
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import gravity_oracle as O
+from oracle import philox_oracle
+from gravity2_b200 import synth
+
+RTOL = 1e-6        # north_star tolerance for score-based similarities
+ATOL = 1e-12       # entries below this are compared absolutely
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import gravity2_b200
+    return gravity2_b200.default_engine()
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype == np.float64
+    err = np.abs(a - b)
+    ok = err <= atol + rtol * np.abs(b)
+    assert ok.all(), f"max rel err {np.max(err / np.maximum(np.abs(b), 1e-300)):.3e}, worst abs {err.max():.3e}"
+
+
+# ------------------------------------------------------------------ golden fixtures (reference outputs)
+@pytest.mark.parametrize("tag", ["A", "B"])
+@pytest.mark.parametrize("scheme,p", [("P", 1), ("G", 1), ("L", 1), ("PG", 1), ("PG", 2), ("PL", 1), ("R", 1), ("RG", 1), ("PR", 1)])
+def test_similarity_golden(golden, eng, tag, scheme, p):
+    import gravity2_b200 as G
+    sig, loc, gom, spr = (golden[f"{tag}_{k}"].copy() for k in ("sig", "loc", "gom", "spr"))
+    S = G.SimilarityMat_Constructor(sig, gom, loc, spr, 0.0, 0, scheme, float(p), fnames=None)
+    close(S, golden[f"{tag}_S_{scheme}_p{p}"])
+    assert np.array_equal(S, S.T)
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_threshold_golden(golden, eng, tag):
+    import gravity2_b200 as G
+    sig = golden[f"{tag}_sig"].copy()
+    S = G.SimilarityMat_Constructor(sig, golden[f"{tag}_gom"], golden[f"{tag}_loc"], None, 0.0, 60, "PG", 1.0)
+    close(S, golden[f"{tag}_S_PG_thr60"])
+    assert np.array_equal(sig, golden[f"{tag}_sig_after_thr60"])      # caller's table mutated like the reference
+
+
+def test_neighbourhood_weight_is_refused(golden):
+    import gravity2_b200 as G
+    with pytest.raises(NotImplementedError):
+        G.SimilarityMat_Constructor(golden["A_sig"], golden["A_gom"], golden["A_loc"], None, 0.1, 0, "PG", 1.0)
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_gom_table_golden(golden, eng, tag):
+    import gravity2_b200 as G
+    loc, taxo, ids = golden[f"{tag}_loc"], golden[f"{tag}_taxo"], list(golden[f"{tag}_gom_ids"])
+    db = G.GOMDB_Constructor(taxo, loc, ids)
+    tab = G.GOMSignatureTable_Constructor(loc, db, ids, {"N_CPUs": 1})
+    assert tab.shape == golden[f"{tag}_gom"].shape
+    close(tab, golden[f"{tag}_gom"], rtol=1e-9)
+    tab4 = G.GOMSignatureTable_Constructor(loc, db, ids, 0)           # 4-arg twin (quirk Q10)
+    assert np.array_equal(tab, tab4)
+
+
+def test_dcor_kat_and_fixture(golden, eng):
+    import gravity2_b200 as G
+    v = G.dcor(np.array([[1.], [2.], [3.], [4.], [5.]]), np.array([[1.], [2.], [9.], [4.], [4.]]))
+    assert v == pytest.approx(0.76267624241686649, rel=1e-12)
+    loc = np.array([[1, 0, 1], [0, 1, 0], [1, 1, 1]], dtype=float)
+    db = {"GOM1": np.array([[1, 0, 1], [0, 1, 0], [1, 1, 1]], dtype=float),
+          "GOM2": np.array([[0, 1, 0], [1, 0, 1], [0, 0, 0]], dtype=float)}
+    for g in db:
+        got = G.generate_gom_sigs(g, loc, db)
+        assert isinstance(got, list) and all(isinstance(x, float) for x in got)
+        assert np.allclose(got, golden[f"gomfix_{g}"], rtol=1e-12, atol=1e-15)
+    # edge cases: n_rel = 0, 1; all-zero GOM; identical vectors
+    z = np.zeros((1, 5))
+    assert G.generate_gom_sigs("g", z, {"g": np.zeros((2, 5))}) == [0.0]
+    one = np.array([[0., 3., 0., 0., 0.]])
+    assert G.generate_gom_sigs("g", one, {"g": np.zeros((2, 5))}) == [0.0]
+    x = np.array([[5., -2., 7., 0., 1.]])
+    assert G.generate_gom_sigs("g", x, {"g": x.copy()})[0] == pytest.approx(1.0, rel=1e-12)
+    assert G.generate_gom_sigs("g", x, {"g": np.zeros((0, 5))}) == [0.0]
+
+
+def test_dcor_multidim_random(eng):
+    import gravity2_b200 as G
+    rng = np.random.default_rng(5)
+    for n, m in [(2, 1), (7, 3), (40, 6), (129, 2)]:
+        X = rng.normal(size=(n, m)) * (rng.random((n, m)) < 0.7)
+        Y = rng.normal(size=(n, 1)) * (rng.random((n, 1)) < 0.7)
+        assert G.dcor(X, Y) == pytest.approx(O.dcor(X, Y), rel=1e-10, abs=1e-14)
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_presence_golden(golden, eng, tag):
+    import gravity2_b200 as G
+    import pandas as pd
+    sig = golden[f"{tag}_sig"]
+    n, p = sig.shape
+    with tempfile.TemporaryDirectory() as tmp:
+        df = pd.DataFrame(sig, columns=[f"PPHMM {c}" for c in range(p)])
+        df.insert(0, "Virus name", [f"v{i}" for i in range(n)])
+        f = os.path.join(tmp, "sigs.csv")
+        df.to_csv(f)                                                   # as app/src/pl1_graphs.py:307-315
+        fn = {"PphmmAndGomSigs": f}
+        got = G.shared_pphmm_ratio(list(range(n)), fn, None)
+        assert isinstance(got, list) and isinstance(got[0][0], int)
+        assert np.array_equal(np.array(got), golden[f"{tag}_shared"])
+        keep = list(golden[f"{tag}_shared_norm_keep"])
+        assert np.array_equal(G.shared_norm_pphmm_ratio(keep, fn, None), golden[f"{tag}_shared_norm"])
+        if len(keep) < n:
+            with pytest.raises(ZeroDivisionError):
+                G.shared_norm_pphmm_ratio(list(range(n)), fn, None)
+    bj = G.binary_jaccard(sig.T)
+    assert np.array_equal(bj, O.binary_gj(sig.T), equal_nan=True)
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_bootstrap_golden(golden, eng, tag):
+    """PL1 and PL2 loop bodies: reference index stream (bit-exact) and replicate matrices."""
+    import gravity2_b200 as G
+    sig, loc, taxo = golden[f"{tag}_sig"], golden[f"{tag}_loc"], golden[f"{tag}_taxo"]
+    ids = list(golden[f"{tag}_gom_ids"])
+    payload = {"N_Bootstrap": 3, "SimilarityMeasurementScheme": "PG", "p": 1.0,
+               "PphmmNeighbourhoodWeight": 0.0, "PphmmSigScoreThreshold": 0}
+    np.random.seed(int(golden[f"{tag}_boot_seed"]))
+    got = list(G.bootstrap_distance_matrices(sig, loc, taxo, ids, payload, pipeline="pl1"))
+    assert len(got) == 3
+    for r in range(3):
+        close(got[r], golden[f"{tag}_pl1_D"][r])
+    n_ref = int(golden[f"{tag}_pl2_nref"])
+    got = list(G.bootstrap_distance_matrices(sig, loc, taxo[:n_ref], ids, payload, pipeline="pl2", distance=False))
+    for r in range(3):
+        close(got[r], golden[f"{tag}_pl2_S"][r])
+    # the global numpy stream advanced exactly as in the reference run: next draw matches a fresh replay
+    nxt = np.random.randint(0, 1 << 30)
+    np.random.seed(int(golden[f"{tag}_boot_seed"]))
+    for _ in range(3):
+        O.bootstrap_indices(sig.shape[1])
+    for _ in range(3):
+        O.bootstrap_indices(sig.shape[1], sort=True)
+    assert nxt == np.random.randint(0, 1 << 30)
+
+
+# ------------------------------------------------------------------------ seeded synthetic tables vs oracle
+@pytest.mark.parametrize("n,p,g,dens", [(1, 1, 1, 1.0), (3, 5, 2, 1.0), (127, 31, 5, 0.5), (129, 33, 5, 0.3),
+                                        (300, 2049, 12, 0.05), (260, 4200, 9, 1.0)])
+def test_similarity_shapes_vs_oracle(eng, n, p, g, dens):
+    """ragged sizes around the 128-genome tile / 32-column block / 1024-column slab edges"""
+    t = synth.make_tables(n, p, g, dens, seed=7 + n)
+    gom = np.random.default_rng(n).random((n, g)) * (np.random.default_rng(n + 1).random((n, g)) < 0.8)
+    for scheme in ("P", "G", "PG"):
+        S = eng.similarity(t.sig, gom, None, scheme, 1.0)
+        ref = O.similarity_mat_fast(t.sig, gom, None, 0, scheme, 1.0)
+        close(S, ref)
+        assert np.array_equal(S, S.T)
+    D = eng.similarity(t.sig, gom, None, "PG", 1.0, distance=True)
+    close(D, O.dist_from_sim(O.similarity_mat_fast(t.sig, gom, None, 0, "PG", 1.0)), rtol=0, atol=1e-6)
+
+
+def test_similarity_nan_and_zero_rows(eng):
+    t = synth.make_tables(40, 200, 4, 0.2, seed=3)
+    gom = np.random.default_rng(0).random((40, 4))
+    gom[5, 2] = np.nan                     # dcor's sqrt of a negative sum (Q5): the whole row's G similarity -> 0
+    t.sig[7] = 0
+    gom[9] = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = O.similarity_mat(t.sig.copy(), gom, t.loc, None, 0.0, 0, "PG", 1.0)
+    S = eng.similarity(t.sig, gom, None, "PG", 1.0)
+    close(S, ref)
+    assert S[7, 7] == 0.0 and S[5, 5] == 0.0 and S[9, 9] == 0.0
+
+
+def test_cfg2_full_size_vs_oracle_and_dendrogram(eng):
+    """BASELINE config 2 shape: 1k genomes x 5k PPHMMs, PG, base matrix; plus identical UPGMA merges."""
+    t = synth.make_config("cfg2")
+    import gravity2_b200 as G
+    gor = G.gom_membership(t.taxo, t.gom_ids)
+    order = np.argsort(gor, kind="stable")
+    offs = np.concatenate([[0], np.cumsum(np.bincount(gor, minlength=len(t.gom_ids)))])
+    gom = eng.gom_table(t.loc, t.loc[order], offs)
+    # oracle GOM table on a row subsample (the reference's n^2 dcor is slow): 40 genomes x all GOMs
+    rows = np.arange(0, 1000, 25)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_gom = O.gom_table(t.loc[rows], O.gomdb(t.taxo, t.loc, t.gom_ids), t.gom_ids)
+    close(gom[rows], ref_gom, rtol=1e-9)
+    S = eng.similarity(t.sig, gom, None, "PG", 1.0)
+    ref = O.similarity_mat_fast(t.sig, gom, None, 0, "PG", 1.0)
+    close(S, ref)
+    assert np.all(np.diag(S) == 1.0)
+    Z1 = O.linkage_merges(O.dist_from_sim(S.copy()))
+    Z0 = O.linkage_merges(O.dist_from_sim(ref.copy()))
+    same = np.array_equal(Z1[:, :2], Z0[:, :2])
+    if not same:   # tie-aware: merges may swap only where heights tie within 1e-9
+        bad = np.where((Z1[:, :2] != Z0[:, :2]).any(axis=1))[0]
+        assert np.allclose(Z1[bad, 2], Z0[bad, 2], rtol=0, atol=1e-7), "dendrogram topology differs beyond ties"
+    assert np.allclose(Z1[:, 2], Z0[:, 2], rtol=0, atol=2e-6)
+
+
+def test_weighted_gom_and_bootstrap_vs_resampled_oracle(eng):
+    """column multiplicities == literal column resampling (PL2 body), N=60, P=400"""
+    import gravity2_b200 as G
+    t = synth.make_tables(60, 400, 5, 0.08, seed=11)
+    n_ref = 45
+    np.random.seed(99)
+    idx = [O.bootstrap_indices(400, sort=True) for _ in range(4)]
+    w = np.stack([O.weights_from_indices(i, 400) for i in idx])
+    gor = G.gom_membership(t.taxo[:n_ref], t.gom_ids)
+    S = eng.bootstrap(t.sig, t.loc, gor, len(t.gom_ids), w, "PG", 1.0, distance=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for r in range(4):
+            ref, _ = O.pl2_bootstrap_replicate(t.sig, t.loc, n_ref, t.taxo[:n_ref], t.gom_ids, idx[r])
+            close(S[r], ref)
+    # all-ones weights reproduce the base matrix
+    ones = np.ones((1, 400), dtype=np.int32)
+    S1 = eng.bootstrap(t.sig, t.loc, gor, len(t.gom_ids), ones, "PG", 1.0, distance=False)[0]
+    db = O.gomdb(t.taxo[:n_ref], t.loc[:n_ref], t.gom_ids)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        base = O.similarity_mat(t.sig.copy(), O.gom_table(t.loc, db, t.gom_ids), t.loc, None, 0.0, 0, "PG", 1.0)
+    close(S1, base)
+
+
+def test_bootstrap_many_replicates_p_scheme(eng):
+    """70 replicates (more than one 32-lane chunk), scheme P, against the weighted oracle"""
+    t = synth.make_tables(150, 700, 6, 0.1, seed=21)
+    rng = np.random.default_rng(4)
+    w = np.stack([np.bincount(rng.integers(0, 700, 700), minlength=700) for _ in range(70)]).astype(np.int32)
+    D = eng.bootstrap(t.sig, None, None, 0, w, "P", 1.0, distance=True)
+    for r in (0, 31, 32, 69):
+        ref = O.dist_from_sim(O.similarity_mat_fast(t.sig, None, None, 0, "P", 1.0, w=w[r]))
+        close(D[r], ref, rtol=0, atol=1e-6)
+
+
+def test_shared_counts_large_bit_exact(eng):
+    rng = np.random.default_rng(8)
+    for n, p in [(1, 1), (130, 65), (257, 3000), (300, 1025)]:
+        tab = rng.random((n, p)) * (rng.random((n, p)) < 0.1)
+        inter, nnz = eng.shared_counts(tab)
+        nz = (tab != 0).astype(np.int32)
+        assert np.array_equal(inter, nz @ nz.T)
+        assert np.array_equal(nnz, nz.sum(1))
+
+
+def test_philox_indices_bit_exact(eng):
+    for seed, nb, p in [(0, 2, 7), (0xDEADBEEFCAFEF00D, 3, 1001)]:
+        got = eng.philox_indices(seed, nb, p)
+        assert got.dtype == np.int64
+        assert np.array_equal(got, philox_oracle.philox_indices(seed, nb, p))
