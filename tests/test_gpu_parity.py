@@ -137,7 +137,9 @@ def test_bootstrap_golden(golden, eng, tag):
     got = list(G.bootstrap_distance_matrices(sig, loc, taxo, ids, payload, pipeline="pl1"))
     assert len(got) == 3
     for r in range(3):
-        close(got[r], golden[f"{tag}_pl1_D"][r])
+        # D = 1 - S: the 1e-6 relative bound on S is an absolute 1e-6 bound on D
+        close(got[r], golden[f"{tag}_pl1_D"][r], rtol=0, atol=1e-6)
+        assert np.all(np.diag(got[r])[np.diag(golden[f"{tag}_pl1_D"][r]) == 0] == 0)
     n_ref = int(golden[f"{tag}_pl2_nref"])
     got = list(G.bootstrap_distance_matrices(sig, loc, taxo[:n_ref], ids, payload, pipeline="pl2", distance=False))
     for r in range(3):
