@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgravity_b200.so")
+LIB_PATH = os.environ.get("GV2_LIB", os.path.join(_HERE, "libgravity_b200.so"))
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_ZERODIV = -1, -2, -3, -4, -5

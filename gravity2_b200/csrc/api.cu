@@ -14,8 +14,14 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
                        int64_t tile_begin, int64_t tile_end, const float* w, int64_t nb, int ksplit,
                        double* ws);
 int boot_mma_available();
-int boot_mma_launch(gv2_ctx* ctx, const float* tab, int64_t n, int64_t n_pad, int64_t k_pad,
-                    const float* w, int64_t nb, double* ws);
+int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n_pad, int64_t k_pad, int64_t tile_begin,
+                    int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* w8_scratch, int* overflow_flag,
+                    double* ws);
+size_t boot_mma_scratch_bytes(int64_t k_pad, int64_t nb);
+int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src, uint32_t* dst,
+                           int64_t n_pad, int64_t k_pad, double* quantum, int* usable);
+int boot_mma_rowsums(gv2_ctx* ctx, const uint32_t* tab, int64_t n, int64_t k, int64_t k_pad, const int32_t* w, int64_t nb,
+                     double quantum, double* out);
 
 static thread_local std::string g_create_error;
 
@@ -126,7 +132,7 @@ static int pick_ksplit(gv2_ctx* ctx, int64_t ntl, int64_t nb, int64_t k_pad) {
     // enough CTAs for >= 2 waves at 2 CTAs/SM; never split below one fp32 slab
     const int64_t want = 4LL * ctx->sm_count;
     int64_t ks = (want + ntl * nb - 1) / std::max<int64_t>(1, ntl * nb);
-    const int64_t max_ks = std::max<int64_t>(1, k_pad / 1024);
+    const int64_t max_ks = std::max<int64_t>(1, k_pad / 512);
     return (int)std::max<int64_t>(1, std::min<int64_t>(ks, std::min<int64_t>(max_ks, 64)));
 }
 
@@ -141,11 +147,14 @@ struct gv2_job {
     const double* d_sig = nullptr;
     const double* d_loc = nullptr;
     DevBuf sigf, sig_rowsum, sig_nan;
+    DevBuf sigfix;                     // 32-bit fixed-point signature table for the tensor-core path
+    double quantum = 0.0;
+    bool mma_ok = false;
     GomDb* gom = nullptr;
     DevBuf gom_base;                   // [n][g] float64 base GOM table (lazy)
     bool have_gom_base = false;
     // workspaces, grown on demand
-    DevBuf wsP, wsG, gomtab, gomf, gom_rowsum, gom_nan, wf, w_rowsum;
+    DevBuf wsP, wsG, gomtab, gomf, gom_rowsum, gom_nan, wf, w_rowsum, wbf16, mma_flag;
     size_t device_bytes() const {
         size_t b = sig64.bytes + loc64.bytes + sigf.bytes + sig_rowsum.bytes + sig_nan.bytes + gom_base.bytes +
                    wsP.bytes + wsG.bytes + gomtab.bytes + gomf.bytes + gom_rowsum.bytes + gom_nan.bytes + wf.bytes + w_rowsum.bytes;
@@ -183,7 +192,7 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
     j->need_p = scheme != GV2_SCHEME_G;
     j->need_g = scheme != GV2_SCHEME_P;
     j->n_pad = gv2_round_up(std::max<int64_t>(n, 1), GV2_TILE);
-    j->p_pad = gv2_round_up(std::max<int64_t>(p, 1), GV2_BK);
+    j->p_pad = gv2_round_up(std::max<int64_t>(p, 1), 128);   // 128: one tensor-core K chunk (4 x the 32-column block)
     j->g_pad = gv2_round_up(std::max<int64_t>(g, 1), GV2_BK);
     j->ntiles = gv2_num_tiles(n);
     int rc = GV2_OK;
@@ -197,6 +206,13 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
         if ((rc = ensure(ctx, j->sig_nan, (size_t)n))) return bail(rc);
         if ((rc = gv2_dev_prepare_table(ctx, j->d_sig, n, p, p, 0.0, 0, j->sigf.as<float>(), j->n_pad, j->p_pad,
                                         j->sig_rowsum.as<double>(), j->sig_nan.as<uint8_t>()))) return bail(rc);
+        if (boot_mma_available()) {
+            int usable = 0;
+            if ((rc = ensure(ctx, j->sigfix, (size_t)j->n_pad * j->p_pad * sizeof(uint32_t)))) return bail(rc);
+            if ((rc = boot_mma_prepare_table(ctx, j->d_sig, n, p, p, j->sigfix.as<uint32_t>(), j->n_pad, j->p_pad, &j->quantum,
+                                             &usable))) return bail(rc);
+            j->mma_ok = usable != 0;
+        }
     }
     if (j->need_g) {
         if (!loc || !gom_of_row || g <= 0) return bail(gv2_fail(ctx, GV2_ERR_ARG, "gv2_job_create: scheme needs loc, gom_of_row and g > 0"));
@@ -297,21 +313,31 @@ extern "C" int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int6
     int64_t chunk = (int64_t)std::max<size_t>(1, std::min<size_t>((size_t)nb, (size_t)((free_b + have) * 0.5) / std::max<size_t>(1, per_rep)));
     chunk = std::min<int64_t>(chunk, 512);
     int rc;
+    bool used_mma = false;
     for (int64_t b0 = 0; b0 < nb; b0 += chunk) {
         const int64_t cb = std::min<int64_t>(chunk, nb - b0);
         const int32_t* w = dev_weights + b0 * p;
         gv2_gj_component cp{}, cg{};
         if (job->need_p) {
-            if ((rc = ensure(ctx, job->wf, (size_t)cb * job->p_pad * sizeof(float)))) return rc;
             if ((rc = ensure(ctx, job->w_rowsum, (size_t)cb * n * sizeof(double)))) return rc;
-            if ((rc = gv2_dev_weights_to_float(ctx, w, cb, p, job->p_pad, job->wf.as<float>()))) return rc;
-            if ((rc = gv2_dev_weighted_rowsums(ctx, job->sigf.as<float>(), n, job->p_pad, job->wf.as<float>(), cb,
-                                               job->w_rowsum.as<double>()))) return rc;
             if ((rc = ensure(ctx, job->wsP, (size_t)cb * ntl * tile_elems * sizeof(double)))) return rc;
-            if (boot_mma_available() && cb >= 8) {
-                if ((rc = boot_mma_launch(ctx, job->sigf.as<float>(), n, job->n_pad, job->p_pad, job->wf.as<float>(), cb,
-                                          job->wsP.as<double>()))) return rc;
+            if (job->mma_ok && cb >= 8) {
+                // tensor-core path: exact integer contraction on the fixed-point table
+                if ((rc = ensure(ctx, job->wbf16, boot_mma_scratch_bytes(job->p_pad, cb)))) return rc;
+                if (!job->mma_flag.p) {
+                    if ((rc = ensure(ctx, job->mma_flag, sizeof(int)))) return rc;
+                    GV2_CUDA(ctx, cudaMemsetAsync(job->mma_flag.p, 0, sizeof(int), ctx->stream));
+                }
+                if ((rc = boot_mma_rowsums(ctx, job->sigfix.as<uint32_t>(), n, p, job->p_pad, w, cb, job->quantum,
+                                           job->w_rowsum.as<double>()))) return rc;
+                if ((rc = boot_mma_launch(ctx, job->sigfix.as<uint32_t>(), job->quantum, job->n_pad, job->p_pad, 0, ntl, w, p, cb,
+                                          job->wbf16.p, job->mma_flag.as<int>(), job->wsP.as<double>()))) return rc;
+                used_mma = true;
             } else {
+                if ((rc = ensure(ctx, job->wf, (size_t)cb * job->p_pad * sizeof(float)))) return rc;
+                if ((rc = gv2_dev_weights_to_float(ctx, w, cb, p, job->p_pad, job->wf.as<float>()))) return rc;
+                if ((rc = gv2_dev_weighted_rowsums(ctx, job->sigf.as<float>(), n, job->p_pad, job->wf.as<float>(), cb,
+                                                   job->w_rowsum.as<double>()))) return rc;
                 if ((rc = gj_min_sums_launch(ctx, job->sigf.as<float>(), 0, job->n_pad, job->p_pad, 0, ntl, job->wf.as<float>(), cb, 1,
                                              job->wsP.as<double>()))) return rc;
             }
@@ -332,6 +358,12 @@ extern "C" int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int6
         // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)
         if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
                                       dev_out + b0 * n * n, n * n))) return rc;
+    }
+    if (used_mma) {     // multiplicities above 255 do not fit the uint8 operand: refuse rather than wrap
+        int flag = 0;
+        GV2_CUDA(ctx, cudaMemcpyAsync(&flag, job->mma_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (flag) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a column multiplicity exceeds 255 (uint8 weights of the tensor-core path); set GV2_DISABLE_MMA=1");
     }
     return GV2_OK;
 }

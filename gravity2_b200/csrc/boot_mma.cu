@@ -1,7 +1,496 @@
-// Batched bootstrap on the 5th-generation tensor cores (tcgen05): placeholder until the kernel lands.
+// Batched bootstrap Jaccard on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// What it computes: for every genome pair (i <= j) and every replicate b of a block,
+//     S[b][i][j] = sum_c w[b][c] * min(T[i][c], T[j][c])
+// i.e. the numerator of the generalised Jaccard of a column-resampled signature table
+// (app/src/pl1_graphs.py:81-86 + app/utils/similarity_matrix_constructor.py:167): resampling P
+// columns with replacement == integer column multiplicities w = bincount(idx).
+//
+// Why tensor cores: min(T_i, T_j) is not a contraction, but once the vector m_ij[c] = min(..) is
+// formed, all replicates share it:  S[pair][b] = sum_c m_pair[c] * W[b][c]  is a GEMM with
+// M = pairs, N = replicates, K = PPHMM columns.  CUDA cores produce the A operand (the min tile),
+// the tensor cores do the pairs x replicates x columns contraction.
+//
+// Exactness: fp32 tensor-core accumulation truncates when it aligns small products to a large
+// accumulator (measured here: 2.5e-6 relative after only 130 accumulation steps with a bf16
+// hi/mid/lo split), so the contraction is done in INTEGERS instead.  The table is held as 32-bit
+// fixed point x_fix = rint(x * (2^32-1)/max(T)) (min commutes with the monotone map), the four
+// bytes of min(x_i, x_j) are four uint8 digit planes, the multiplicities are uint8, and
+// tcgen05.mma.kind::i8 accumulates each plane exactly in int32 (digit <= 255, sum_c w_c = P, so
+// |sum| <= 255 P << 2^31).  The planes are recombined in fp64: sum = q * sum_d 256^d * plane_d.
+// The only error is the input quantisation q/2 = max(T) * 2^-33 per element.
+//
+// CTA = 128 pairs (8 i-rows x 16 j-rows of one 128x128 genome tile) x N <= 128 replicates;
+// TMEM = 4 planes x 128 columns of int32.  One pipeline stage = 128 PPHMM columns.
+//   warps 0-7  producers: stream the 24 fixed-point table rows through a cp.async ring, form the
+//              u32 min, byte-transpose into the four K-major SWIZZLE_128B digit tiles; afterwards
+//              drain TMEM (epilogue)
+//   warp  8    TMA: W tile [N rows x 128 columns] uint8, SWIZZLE_128B, one elected thread
+//   warp  9    MMA issuer: 4 planes x 4 (K=32) tcgen05.mma per stage, one elected thread
 #include "common.cuh"
 
-int boot_mma_available() { return 0; }
-int boot_mma_launch(gv2_ctx* ctx, const float*, int64_t, int64_t, int64_t, const float*, int64_t, double*) {
-    return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "tcgen05 bootstrap kernel not built");
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+
+#define BM_PAIRS 128
+#define BM_KC 128                      // columns per pipeline stage (= one 128-byte swizzle row of uint8)
+#define BM_STAGES 2
+#define BM_PLANES 4                    // uint8 digit planes of the 32-bit fixed-point min
+#define BM_NMAX 128                    // replicates per CTA: BM_PLANES * BM_NMAX = 512 TMEM columns
+#define BM_TMEM_COLS 512
+#define BM_PRODUCERS 256               // threads
+#define BM_THREADS (BM_PRODUCERS + 64)
+#define BM_RING 3                      // table-row staging ring (chunks)
+#define BM_ROWS 24                     // 8 i-rows + 16 j-rows
+#define BM_A_BYTES (BM_PAIRS * BM_KC)                // 16 KB per plane
+#define BM_W_BYTES (BM_NMAX * BM_KC)                 // 16 KB
+#define BM_STAGE_BYTES (BM_PLANES * BM_A_BYTES + BM_W_BYTES) // 80 KB
+#define BM_RING_BYTES (BM_ROWS * BM_KC * 4)          // 12 KB per chunk
+#define BM_SMEM (BM_STAGES * BM_STAGE_BYTES + BM_RING * BM_RING_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+
+__host__ __device__ inline int bm_ws_index(int r, int c) { return ((((r >> 4) << 3) + (c >> 4)) << 8) + ((r & 15) << 4) + (c & 15); }
+
+__host__ __device__ inline void bm_tile_coords(long long t, int nt, int* bi, int* bj) {
+    double disc = (2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t;
+    int r = (int)floor(((2.0 * nt + 1.0) - sqrt(disc)) * 0.5);
+    if (r < 0) r = 0;
+    while (r > 0 && (long long)r * nt - (long long)r * (r - 1) / 2 > t) --r;
+    while ((long long)(r + 1) * nt - (long long)(r + 1) * r / 2 <= t) ++r;
+    *bi = r;
+    *bj = r + (int)(t - ((long long)r * nt - (long long)r * (r - 1) / 2));
+}
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address >> 4 in bits
+// [0,14), leading byte offset 0 (one swizzle atom along K), stride byte offset 1024 (8 rows x 128 B)
+// in bits [32,46), version 1 in bits [46,48), layout type 2 (SWIZZLE_128B) in bits [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor, kind::i8: D = S32 (bits [4,6) = 2), A = B = unsigned 8 bit (bits [7,10) =
+// [10,13) = 0), both K-major (bits 15, 16 = 0), N >> 3 in bits [17,23), M >> 4 in bits [24,29)
+__device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
+    return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, K = 32 uint8 per instruction
+__device__ __forceinline__ void umma_u8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 TMEM lanes (this warp's quarter) x 16 consecutive 32-bit columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem));
+}
+
+// 4x4 byte transpose: v[0..3] = four consecutive columns (u32 each) -> p[d] = byte d of each column,
+// column k in byte k (little endian = element order of the K-major uint8 tile).  8 PRMT.
+__device__ __forceinline__ void byte_planes(const uint32_t v0, const uint32_t v1, const uint32_t v2, const uint32_t v3,
+                                            uint32_t* p) {
+    const uint32_t t0 = __byte_perm(v0, v1, 0x5140);   // v0.b0 v1.b0 v0.b1 v1.b1
+    const uint32_t t1 = __byte_perm(v2, v3, 0x5140);
+    const uint32_t t2 = __byte_perm(v0, v1, 0x7362);   // v0.b2 v1.b2 v0.b3 v1.b3
+    const uint32_t t3 = __byte_perm(v2, v3, 0x7362);
+    p[0] = __byte_perm(t0, t1, 0x5410);
+    p[1] = __byte_perm(t0, t1, 0x7632);
+    p[2] = __byte_perm(t2, t3, 0x5410);
+    p[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+// ---------------------------------------------------------------------------------- kernel
+// grid = (128 sub-tiles, genome tiles in [tile_begin, tile_end), replicate blocks)
+__global__ void __launch_bounds__(BM_THREADS, 1)
+boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, long long tile_begin,
+                const __grid_constant__ CUtensorMap wmap, int nb_total, int nblk, long long ws_rep_stride,
+                double quantum, double* __restrict__ ws) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-B aligned
+    uint8_t* stage_base = smem;
+    uint32_t* ring = (uint32_t*)(smem + BM_STAGES * BM_STAGE_BYTES);
+    uint64_t* bars = (uint64_t*)(smem + BM_STAGES * BM_STAGE_BYTES + BM_RING * BM_RING_BYTES);
+    uint64_t* full = bars;                  // [BM_STAGES]
+    uint64_t* empty = bars + BM_STAGES;     // [BM_STAGES]
+    uint64_t* tmem_full = bars + 2 * BM_STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * BM_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = blockIdx.x, si = sub >> 3, sj = sub & 7;      // 16 i-groups of 8 rows, 8 j-groups of 16 rows
+    int bi, bj;
+    bm_tile_coords(tile_begin + blockIdx.y, nt, &bi, &bj);
+    if (bi == bj && si * 8 > sj * 16 + 15) return;                 // sub-tile entirely below the diagonal
+    const int rep0 = blockIdx.z * nblk;
+    const int nrep = min(nblk, nb_total - rep0);                   // valid replicates of this block
+    const int umma_n = nblk;                                       // = TMA box rows; padded W rows are zero
+
+    if (tid == 0) {
+        for (int s = 0; s < BM_STAGES; ++s) {
+            mbar_init(&full[s], BM_PRODUCERS + 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {   // TMEM: 4 digit planes x 128 int32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BM_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ============================ producers ============================
+        const uint32_t* gI = tab + (size_t)(bi * GV2_TILE + si * 8) * ld;
+        const uint32_t* gJ = tab + (size_t)(bj * GV2_TILE + sj * 16) * ld;
+        auto ring_load = [&](int kc) {
+            uint32_t* dst = ring + (kc % BM_RING) * (BM_ROWS * BM_KC);
+            for (int q = tid; q < BM_ROWS * 32; q += BM_PRODUCERS) {       // 24 rows x 32 pieces of 16 B
+                const int row = q >> 5, piece = q & 31;
+                const uint32_t* src = (row < 8 ? gI + (size_t)row * ld : gJ + (size_t)(row - 8) * ld) + (size_t)kc * BM_KC + piece * 4;
+                cp16(dst + row * BM_KC + piece * 4, src);
+            }
+        };
+        for (int s = 0; s < BM_RING - 1; ++s) {
+            if (s < kchunks) ring_load(s);
+            asm volatile("cp.async.commit_group;");
+        }
+        const int q = tid & 7;
+        for (int kc = 0; kc < kchunks; ++kc) {
+            const int st = kc % BM_STAGES;
+            const uint32_t ph = (kc / BM_STAGES) & 1;
+            asm volatile("cp.async.wait_group %0;" ::"n"(BM_RING - 2));
+            asm volatile("bar.sync 1, %0;" ::"n"(BM_PRODUCERS));             // chunk kc landed for every producer
+            if (kc + BM_RING - 1 < kchunks) ring_load(kc + BM_RING - 1);    // slot of chunk kc-1: free since the barrier
+            asm volatile("cp.async.commit_group;");
+            mbar_wait(&empty[st], ph ^ 1);                                   // MMA has drained this stage
+            const uint32_t* rg = ring + (kc % BM_RING) * (BM_ROWS * BM_KC);
+            uint8_t* a0 = stage_base + st * BM_STAGE_BYTES;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int m = (tid >> 3) + 32 * it;              // pair row of the A tiles
+                const int ii = m >> 4, jj = m & 15;
+                // K-major SWIZZLE_128B row: (m/8)*1024 + (m%8)*128, 16-byte piece x at (x ^ (m%8))*16
+                uint8_t* row = a0 + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    // this thread's 4 consecutive columns: 16-byte piece (c*8 + q) of the 128-column chunk
+                    const int col = (c * 8 + q) * 4;
+                    const uint4 x = *reinterpret_cast<const uint4*>(rg + ii * BM_KC + col);
+                    const uint4 y = *reinterpret_cast<const uint4*>(rg + (8 + jj) * BM_KC + col);
+                    uint32_t p[4];
+                    byte_planes(min(x.x, y.x), min(x.y, y.y), min(x.z, y.z), min(x.w, y.w), p);
+                    // columns col..col+3 are bytes col..col+3 of the uint8 row: piece col/16, word (col/4)%4
+                    const uint32_t off = (uint32_t)((((col >> 4) ^ (m & 7)) << 4) + (col & 12));
+#pragma unroll
+                    for (int d = 0; d < BM_PLANES; ++d) *reinterpret_cast<uint32_t*>(row + d * BM_A_BYTES + off) = p[d];
+                }
+            }
+            fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            mbar_arrive(&full[st]);
+        }
+        // ============================ epilogue ============================
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int lg = warp & 3, half = warp >> 2;          // TMEM lanes 32*lg.., replicate columns half*64..
+        const int m = lg * 32 + lane;
+        const int r = si * 8 + (m >> 4), c = sj * 16 + (m & 15);
+        double* out = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + bm_ws_index(r, c);
+        for (int cb = 0; cb < 4; ++cb) {
+            const int col0 = half * 64 + cb * 16;
+            if (col0 >= umma_n) break;
+            uint32_t v[BM_PLANES][16];
+#pragma unroll
+            for (int d = 0; d < BM_PLANES; ++d)
+                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * BM_NMAX + col0), v[d]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int rep = col0 + e;
+                // exact: each plane sum < 2^31, the combination < 2^55 only in its top 53 bits matter (<= 0.5 ulp)
+                const double sum = (double)(int)v[0][e] + 256.0 * (double)(int)v[1][e] + 65536.0 * (double)(int)v[2][e] +
+                                   16777216.0 * (double)(int)v[3][e];
+                if (rep < nrep) out[(size_t)(rep0 + rep) * ws_rep_stride] = sum * quantum;
+            }
+        }
+    } else if (warp == 8) {
+        // ============================ TMA: W tiles ============================
+        if (lane == 0) {
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int st = kc % BM_STAGES;
+                const uint32_t ph = (kc / BM_STAGES) & 1;
+                mbar_wait(&empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&full[st], (uint32_t)(umma_n * BM_KC));
+                tma_load_2d(stage_base + st * BM_STAGE_BYTES + BM_PLANES * BM_A_BYTES, &wmap, &full[st], kc * BM_KC, rep0);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ============================ MMA issuer ============================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(BM_PAIRS, umma_n);
+            for (int kc = 0; kc < kchunks; ++kc) {
+                const int st = kc % BM_STAGES;
+                const uint32_t ph = (kc / BM_STAGES) & 1;
+                mbar_wait(&full[st], ph);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(stage_base + st * BM_STAGE_BYTES);
+                const uint32_t w0 = a0 + BM_PLANES * BM_A_BYTES;
+#pragma unroll
+                for (int d = 0; d < BM_PLANES; ++d) {
+#pragma unroll
+                    for (int k = 0; k < BM_KC / 32; ++k) {
+                        const uint64_t da = umma_desc(a0 + d * BM_A_BYTES + k * 32);
+                        const uint64_t db = umma_desc(w0 + k * 32);
+                        umma_u8(tmem_base + (uint32_t)(d * BM_NMAX), da, db, idesc, (kc | k) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty[st]);                 // frees the stage when these MMAs have read it
+            }
+            umma_commit(tmem_full);                      // accumulators complete
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BM_TMEM_COLS));
+}
+
+// int32 multiplicities -> uint8 rows, zero padded: out [nb_pad][k_pad].  grid = (ceil(k_pad/256), nb_pad)
+__global__ void weights_to_u8_kernel(const int* __restrict__ w, long long nb, long long k, long long k_pad,
+                                     uint8_t* __restrict__ out, int* __restrict__ overflow) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (c >= k_pad) return;
+    int v = (b < nb && c < k) ? w[b * k + c] : 0;
+    if (v < 0 || v > 255) { atomicExch(overflow, 1); v = 0; }
+    out[b * k_pad + c] = (uint8_t)v;
+}
+
+// float64 table -> 32-bit fixed point, zero padded [n_pad][k_pad]; scale = (2^32-1)/max.  NaN and
+// negative entries become 0 (NaN rows are flagged by prepare_table; negatives disable this path).
+__global__ void table_to_fixed_kernel(const double* __restrict__ src, long long n, long long k, long long ld_src,
+                                      double scale, uint32_t* __restrict__ dst, long long k_pad) {
+    const long long r = blockIdx.x;
+    uint32_t* d = dst + r * k_pad;
+    for (long long c = threadIdx.x; c < k_pad; c += blockDim.x) {
+        uint32_t f = 0;
+        if (r < n && c < k) {
+            const double v = src[r * ld_src + c];
+            if (v > 0.0) f = (uint32_t)__double2ull_rn(fmin(v * scale, 4294967295.0));
+        }
+        d[c] = f;
+    }
+}
+
+// per-block max and "has negative" of a float64 table (ignoring NaN).  stats[0] = max bits (as ull of
+// the non-negative double), stats[1] = negative flag
+__global__ void table_stats_kernel(const double* __restrict__ src, long long n, long long k, long long ld_src,
+                                   unsigned long long* __restrict__ stats) {
+    const long long r = blockIdx.x;
+    double mx = 0.0;
+    int neg = 0;
+    for (long long c = threadIdx.x; c < k; c += blockDim.x) {
+        const double v = src[r * ld_src + c];
+        if (v > mx) mx = v;
+        if (v < 0.0) neg = 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        neg |= __shfl_xor_sync(0xffffffffu, neg, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&stats[0], (unsigned long long)__double_as_longlong(mx));   // order-preserving for non-negative doubles
+        if (neg) atomicExch(&stats[1], 1ull);
+    }
+}
+
+// fixed-point weighted row sums: out[b][i] = q * sum_c w[b][c] * x_fix[i][c]  (exact integer sum in fp64 range)
+// grid = (n, nb)
+__global__ void weighted_rowsum_fixed_kernel(const uint32_t* __restrict__ tab, long long k_pad, const int* __restrict__ w,
+                                             long long k, long long n, double quantum, double* __restrict__ out) {
+    const long long r = blockIdx.x, b = blockIdx.y;
+    const uint32_t* t = tab + r * k_pad;
+    const int* ww = w + b * k;
+    unsigned long long s = 0;
+    for (long long c = threadIdx.x; c < k; c += blockDim.x) s += (unsigned long long)t[c] * (unsigned long long)(unsigned)ww[c];
+    __shared__ unsigned long long red[32];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long tt = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tt += red[i];
+        out[b * n + r] = (double)tt * quantum;
+    }
+}
+
+// ---------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+int boot_mma_available() {
+    static int state = -1;
+    if (state < 0) {
+        const char* env = getenv("GV2_DISABLE_MMA");
+        state = (env && env[0] == '1') ? 0 : (get_encode() ? 1 : 0);
+    }
+    return state;
+}
+
+// Builds the fixed-point table.  Returns GV2_OK and *usable = 0 if the table has negative entries
+// (min does not commute with the unsigned fixed-point map then; the caller keeps the fp32 path).
+int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src, uint32_t* dst,
+                           int64_t n_pad, int64_t k_pad, double* quantum, int* usable) {
+    unsigned long long* stats = nullptr;
+    GV2_CUDA(ctx, cudaMalloc((void**)&stats, 2 * sizeof(unsigned long long)));
+    GV2_CUDA(ctx, cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (n > 0 && k > 0) {
+        table_stats_kernel<<<(unsigned)n, 256, 0, ctx->stream>>>(src, n, k, ld_src, stats);
+        ctx->launches++;
+    }
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(h, stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stats);
+    if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "table stats: %s", cudaGetErrorString(e));
+    double mx;
+    memcpy(&mx, &h[0], sizeof mx);
+    *usable = (h[1] == 0 && isfinite(mx)) ? 1 : 0;
+    const double scale = mx > 0.0 ? 4294967295.0 / mx : 0.0;
+    *quantum = mx > 0.0 ? mx / 4294967295.0 : 0.0;
+    if (!*usable) return GV2_OK;
+    table_to_fixed_kernel<<<(unsigned)n_pad, 256, 0, ctx->stream>>>(src, n, k, ld_src, scale, dst, k_pad);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+int boot_mma_rowsums(gv2_ctx* ctx, const uint32_t* tab, int64_t n, int64_t k, int64_t k_pad, const int32_t* w, int64_t nb,
+                     double quantum, double* out) {
+    if (n == 0 || nb == 0) return GV2_OK;
+    dim3 grid((unsigned)n, (unsigned)nb);
+    weighted_rowsum_fixed_kernel<<<grid, 256, 0, ctx->stream>>>(tab, k_pad, w, k, n, quantum, out);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+static void bm_blocks(int64_t nb, int64_t* nblocks, int64_t* nblk) {
+    *nblocks = (nb + BM_NMAX - 1) / BM_NMAX;
+    *nblk = ((nb + *nblocks - 1) / *nblocks + 15) / 16 * 16;
+}
+
+size_t boot_mma_scratch_bytes(int64_t k_pad, int64_t nb) {
+    int64_t nblocks, nblk;
+    bm_blocks(nb, &nblocks, &nblk);
+    return (size_t)(nblocks * nblk) * k_pad;
+}
+
+// tab: fixed point [n_pad][k_pad] (k_pad % 128 == 0); w: int32 [nb][k] multiplicities (device);
+// ws: fp64 [nb][ntl][128*128] in the gj_ws_index layout, tiles [tile_begin, tile_end)
+int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n_pad, int64_t k_pad, int64_t tile_begin,
+                    int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* w8_scratch, int* overflow_flag,
+                    double* ws) {
+    if (k_pad % BM_KC) return gv2_fail(ctx, GV2_ERR_ARG, "boot_mma_launch: k_pad %% 128 != 0");
+    const int64_t ntl = tile_end - tile_begin;
+    if (ntl <= 0 || nb <= 0) return GV2_OK;
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+    int64_t nblocks, nblk;
+    bm_blocks(nb, &nblocks, &nblk);
+    const int64_t nb_pad = nblocks * nblk;
+    uint8_t* wb = (uint8_t*)w8_scratch;                       // [nb_pad][k_pad]
+    dim3 gw((unsigned)((k_pad + 255) / 256), (unsigned)nb_pad);
+    weights_to_u8_kernel<<<gw, 256, 0, ctx->stream>>>(w, nb, k, k_pad, wb, overflow_flag);
+    GV2_LAUNCH_CHECK(ctx);
+    CUtensorMap map;
+    cuuint64_t dims[2] = {(cuuint64_t)k_pad, (cuuint64_t)nb_pad};
+    cuuint64_t strides[1] = {(cuuint64_t)k_pad};
+    cuuint32_t box[2] = {BM_KC, (cuuint32_t)nblk};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, wb, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return gv2_fail(ctx, GV2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        attr_done = true;
+    }
+    if (ntl > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "boot_mma_launch: more than 65535 genome tiles per launch");
+    dim3 grid(128, (unsigned)ntl, (unsigned)nblocks);
+    boot_mma_kernel<<<grid, BM_THREADS, BM_SMEM, ctx->stream>>>(tab, (int)k_pad, (int)(k_pad / BM_KC), (int)(n_pad / GV2_TILE),
+                                                                tile_begin, map, (int)nb, (int)nblk,
+                                                                (long long)ntl * GV2_TILE * GV2_TILE, quantum, ws);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
 }

@@ -14,10 +14,21 @@
 
 #include <math.h>
 
+#define GJ_PRAGMA_(x) _Pragma(#x)
+#define GJ_UNROLL(n) GJ_PRAGMA_(unroll n)
 #define GJ_THREADS 256
 #define GJ_STAGES 3
 #define GJ_LDS (GV2_BK + 4)          // padded row stride (floats): conflict-free LDS.128
-#define GJ_SLAB 1024                 // columns accumulated in fp32 before fp64 promotion
+#ifndef GJ_SLAB
+#define GJ_SLAB 128                  // columns accumulated in fp32 before fp64 promotion
+#endif
+#ifndef GJ_KG_UNROLL
+#define GJ_KG_UNROLL 2                // 4-column groups unrolled per loop trip (whole stage = 8 overflows the I-cache)
+#endif
+// Workspace tile layout: element (r, c) of a 128x128 pair tile lives at gj_ws_index(r, c), i.e. as
+// [r/16][c/16][r%16][c%16], so that the 256 threads of the tile kernel (thread (ty, tx) owns rows
+// ty+16m, columns tx+16n) read-modify-write 256 consecutive doubles per (m, n).
+__host__ __device__ inline int gj_ws_index(int r, int c) { return ((((r >> 4) << 3) + (c >> 4)) << 8) + ((r & 15) << 4) + (c & 15); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -100,10 +111,12 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
         for (int m = 0; m < 8; ++m)
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
-                size_t o = (size_t)(ty + 16 * m) * GV2_TILE + (tx + 16 * n);
-                double v = (double)acc[m][n];
-                if (!first) v += wtile[o];
-                wtile[o] = v;
+                size_t o = (size_t)((m * 8 + n) * 256 + tid);      // == gj_ws_index(ty + 16m, tx + 16n)
+                // first slab: plain store (no zero-init needed); later slabs: fire-and-forget RED.ADD.F64.
+                // Each address is only ever touched by this one thread, in program order, so the
+                // fp64 sum is formed in slab order and is deterministic.
+                if (first) wtile[o] = (double)acc[m][n];
+                else atomicAdd(&wtile[o], (double)acc[m][n]);
                 acc[m][n] = 0.f;
             }
     };
@@ -128,7 +141,7 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
         const float* a = sA + stage * GV2_TILE * GJ_LDS + ty * GJ_LDS;
         const float* bb = sB + stage * GV2_TILE * GJ_LDS + tx * GJ_LDS;
         const float* w = sW + stage * GV2_BK;
-#pragma unroll
+        GJ_UNROLL(GJ_KG_UNROLL)
         for (int kg = 0; kg < GV2_BK / 4; ++kg) {
             float4 bf[8];
 #pragma unroll
@@ -141,16 +154,23 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
                 float4 af = *reinterpret_cast<const float4*>(a + m * 16 * GJ_LDS + kg * 4);
 #pragma unroll
                 for (int n = 0; n < 8; ++n) {
+                    // 4 columns are summed as a tree before they touch the (large) accumulator: same
+                    // instruction count as a chain, a quarter of the accumulator roundings
                     if (WEIGHTED) {
+#ifdef GJ_W_TREE
+                        float s0 = fmaf(wv.x, fminf(af.x, bf[n].x), wv.y * fminf(af.y, bf[n].y));
+                        float s1 = fmaf(wv.z, fminf(af.z, bf[n].z), wv.w * fminf(af.w, bf[n].w));
+                        acc[m][n] += s0 + s1;
+#else
                         acc[m][n] = fmaf(wv.x, fminf(af.x, bf[n].x), acc[m][n]);
                         acc[m][n] = fmaf(wv.y, fminf(af.y, bf[n].y), acc[m][n]);
                         acc[m][n] = fmaf(wv.z, fminf(af.z, bf[n].z), acc[m][n]);
                         acc[m][n] = fmaf(wv.w, fminf(af.w, bf[n].w), acc[m][n]);
+#endif
                     } else {
-                        acc[m][n] += fminf(af.x, bf[n].x);
-                        acc[m][n] += fminf(af.y, bf[n].y);
-                        acc[m][n] += fminf(af.z, bf[n].z);
-                        acc[m][n] += fminf(af.w, bf[n].w);
+                        float s0 = fminf(af.x, bf[n].x) + fminf(af.y, bf[n].y);
+                        float s1 = fminf(af.z, bf[n].z) + fminf(af.w, bf[n].w);
+                        acc[m][n] += s0 + s1;
                     }
                 }
             }
@@ -257,7 +277,10 @@ struct GjComp {
 
 __device__ __forceinline__ double gj_value(const GjComp& c, long long b, long long ntl,
                                            long long t, int r, int cc, long long gi, long long gj) {
-    const double* w = c.ws + b * c.b_stride_ws + t * (long long)(GV2_TILE * GV2_TILE) + r * GV2_TILE + cc;
+    // diagonal tiles: always read the upper-triangle entry (the tensor-core path leaves sub-tiles that lie
+    // wholly below the diagonal unwritten; the value is symmetric)
+    if (gi > gj && gi - r == gj - cc) { int tmp = r; r = cc; cc = tmp; }
+    const double* w = c.ws + b * c.b_stride_ws + t * (long long)(GV2_TILE * GV2_TILE) + gj_ws_index(r, cc);
     double smin = 0.0;
     for (int ks = 0; ks < c.ksplit; ++ks) smin += w[(long long)ks * ntl * (GV2_TILE * GV2_TILE)];
     const double* rs = c.rowsum + b * c.b_stride_row;
