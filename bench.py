@@ -276,9 +276,9 @@ def main():
                     ck(lib.gv2_dev_unpack_tiles(ctx, n, a, b, C.c_void_p(d_gath[r * per].data_ptr()), C.c_void_p(d_base.data_ptr())))
         else:
             ck(lib.gv2_job_base(job, 0, ntiles, 0, C.c_void_p(d_base.data_ptr())))
-        for b0 in range(0, len(my_reps), ring):
-            cb = min(ring, len(my_reps) - b0)
-            ck(lib.gv2_job_replicates(job, C.c_void_p(d_w[b0].data_ptr()), cb, C.c_void_p(d_out.data_ptr())))
+        if my_reps:      # all of this rank's replicates in one call; results stream through the device ring
+            ck(lib.gv2_job_replicates_stream(job, C.c_void_p(d_w.data_ptr()), len(my_reps), C.c_void_p(d_out.data_ptr()), ring,
+                                             None, None, None))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -383,49 +383,52 @@ def measure_roofline(lib, ctx, ck, job, cfg, n, p, d_w, d_out, ring, stream, pea
 
 
 def measure_e2e(lib, ctx, ck, t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist, torch, steps):
-    """Whole job through the host-pointer entry points with numpy buffers: every step uploads the
-    tables and downloads the base matrix and every replicate matrix (one reusable host slab)."""
-    from gravity2_b200 import _lib
+    """Whole job through the package's public host API (what a pipeline_i / pipeline_ii call site uses):
+    numpy tables in host memory -> gravity2_b200.engine.Job (one H2D upload of the table per step) -> base
+    matrix as a numpy array -> every replicate matrix delivered in host memory (pinned ring, zero-copy
+    view) to a consumer that reads it.  H2D and D2H are inside the timed region, every step."""
+    import gravity2_b200
+    from gravity2_b200.engine import Job
+    eng = gravity2_b200.Engine(int(os.environ.get("LOCAL_RANK", "0")))
     sig = t.sig
-    order = np.argsort(gor, kind="stable")
-    order = order[gor[order] >= 0]
-    offs = np.concatenate([[0], np.cumsum(np.bincount(gor[gor >= 0], minlength=g))]).astype(np.int64)
-    slab = max(1, min(len(my_reps) or 1, int((4 << 30) // (n * n * 8))))
-    out = np.empty((slab, n, n))
-    base = np.empty((n, n))
-    gom = np.empty((1, n, g))
     w_mine = np.ascontiguousarray(weights[my_reps]) if my_reps else np.zeros((0, p), np.int32)
-    vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    acc = [0.0, 0]
+
+    def consume(b, m):              # the device->host read of the step's result: touch every delivered matrix
+        acc[0] += float(m[0, -1]) + float(m[-1, 0]) + float(m[n // 2, n // 3])
+        acc[1] += 1
 
     def job_once():
-        if rank == 0:
-            rows = np.ascontiguousarray(sig[order])
-            ck(lib.gv2_gom_table_host(ctx, vp(sig), n, p, p, vp(rows), p, vp(offs), g, None, 1, 0, vp(gom)))
-            ck(lib.gv2_similarity_host(ctx, vp(sig), n, p, p, vp(gom), g, g, None, _lib.SCHEMES["PG"], 1.0, 0.0, 0,
-                                       _lib.OUT_DISTANCE, vp(base)))
-        for b0 in range(0, len(my_reps), slab):
-            cb = min(slab, len(my_reps) - b0)
-            ck(lib.gv2_bootstrap_host(ctx, vp(sig), vp(sig), n, p, vp(gor), n, g, vp(w_mine[b0:]), cb, _lib.SCHEMES["PG"], 1.0,
-                                      _lib.OUT_DISTANCE, vp(out)))
+        job = Job(eng, sig, sig, gor, g, "PG", 1.0, distance=True)      # PL1: sig doubles as loc (Q3)
+        try:
+            if rank == 0:
+                consume(-1, job.base())
+            job.for_each_replicate(w_mine, consume)
+        finally:
+            job.close()
 
     job_once()          # warm-up
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
+    acc[1] = 0
     t0 = time.perf_counter()
     for _ in range(steps):
         job_once()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
+    assert acc[1] == steps * (len(my_reps) + (1 if rank == 0 else 0)), "consumer did not see every matrix"
     if dist is not None:
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-    n_slabs = (len(my_reps) + slab - 1) // slab
-    h2d = n * p * 8 * (2 + n_slabs) + n * g * 8 + weights.nbytes // max(1, world)
-    d2h = (1 + len(my_reps)) * n * n * 8 + n * g * 8
+    h2d = n * p * 8 + w_mine.nbytes + gor.nbytes
+    d2h = ((1 if rank == 0 else 0) + len(my_reps)) * n * n * 8
+    eng.close()
     return {"value": pairs * (1 + B) / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": dt * 1e3, "api": "gv2_gom_table_host + gv2_similarity_host + gv2_bootstrap_host (numpy buffers, pageable)"}
+            "ms_per_step": dt * 1e3,
+            "api": "gravity2_b200.engine.Job(sig, loc, ...).base() + .for_each_replicate(weights, consumer): numpy in, "
+                   "numpy views of a pinned host ring out (per-rank bytes)"}
 
 
 def measure_cpu_baseline(args, cfg):

@@ -56,6 +56,13 @@ PROTOTYPES = {
     "gv2_job_destroy": (None, [c_vp]),
     "gv2_job_base": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp]),
     "gv2_job_replicates": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "gv2_job_replicates_stream": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "gv2_dev_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),
+    "gv2_dev_free": (C.c_int, [c_vp, c_vp]),
+    "gv2_host_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),
+    "gv2_host_free": (C.c_int, [c_vp, c_vp]),
+    "gv2_memcpy_h2d": (C.c_int, [c_vp, c_vp, c_vp, C.c_size_t]),
+    "gv2_memcpy_d2h": (C.c_int, [c_vp, c_vp, c_vp, C.c_size_t]),
     "gv2_job_gom_table": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "gv2_job_device_bytes": (C.c_size_t, [c_vp]),
     "gv2_num_tiles": (c_i64, [c_i64]),
@@ -73,6 +80,9 @@ PROTOTYPES = {
 }
 
 _lib = None
+
+
+REPLICATE_CB = C.CFUNCTYPE(C.c_int, c_i64, c_vp, c_vp)      # gv2_replicate_cb
 
 
 class GravityNativeError(RuntimeError):

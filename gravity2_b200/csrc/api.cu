@@ -98,6 +98,47 @@ extern "C" int gv2_synchronize(gv2_ctx* ctx) {
 
 extern "C" uint64_t gv2_launch_count(const gv2_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// ---------------------------------------------------------- memory helpers for hosts without a CUDA binding
+extern "C" int gv2_dev_alloc(gv2_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_alloc: bad arguments");
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_NOMEM, "cudaMalloc(%.3f GB): %s", bytes / 1e9, cudaGetErrorString(e));
+    return GV2_OK;
+}
+extern "C" int gv2_dev_free(gv2_ctx* ctx, void* p) {
+    if (!ctx) return GV2_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+    return GV2_OK;
+}
+extern "C" int gv2_host_alloc(gv2_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_host_alloc: bad arguments");
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_NOMEM, "cudaMallocHost(%.3f GB): %s", bytes / 1e9, cudaGetErrorString(e));
+    return GV2_OK;
+}
+extern "C" int gv2_host_free(gv2_ctx* ctx, void* p) {
+    if (!ctx) return GV2_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaFreeHost(p);
+    return GV2_OK;
+}
+extern "C" int gv2_memcpy_h2d(gv2_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return GV2_ERR_ARG;
+    GV2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GV2_OK;
+}
+extern "C" int gv2_memcpy_d2h(gv2_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return GV2_ERR_ARG;
+    GV2_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GV2_OK;
+}
+
 // ------------------------------------------------------------------------------- helpers
 struct DevBuf {
     void* p = nullptr;
@@ -155,6 +196,8 @@ struct gv2_job {
     bool have_gom_base = false;
     // workspaces, grown on demand
     DevBuf wsP, wsG, gomtab, gomf, gom_rowsum, gom_nan, wf, w_rowsum, wbf16, mma_flag;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
     size_t device_bytes() const {
         size_t b = sig64.bytes + loc64.bytes + sigf.bytes + sig_rowsum.bytes + sig_nan.bytes + gom_base.bytes +
                    wsP.bytes + wsG.bytes + gomtab.bytes + gomf.bytes + gom_rowsum.bytes + gom_nan.bytes + wf.bytes + w_rowsum.bytes;
@@ -173,6 +216,11 @@ extern "C" void gv2_job_destroy(gv2_job* job) {
     if (!job) return;
     cudaSetDevice(job->ctx->device);
     cudaStreamSynchronize(job->ctx->stream);
+    if (job->copy_stream) {
+        cudaStreamSynchronize(job->copy_stream);
+        for (int h = 0; h < 2; ++h) { cudaEventDestroy(job->ev_ready[h]); cudaEventDestroy(job->ev_drained[h]); }
+        cudaStreamDestroy(job->copy_stream);
+    }
     gom_db_free(job->gom);
     delete job;
 }
@@ -296,69 +344,145 @@ extern "C" int gv2_job_base(gv2_job* job, int64_t tile_begin, int64_t tile_end, 
                                job->out_kind, packed, dev_out, 0);
 }
 
-extern "C" int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out) {
-    if (!job || !dev_weights || !dev_out || nb < 0)
-        return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates: bad arguments");
+// Replicates [0, nb): replicate b is written to ring slot (b % ring_len) of dev_ring [ring_len][n][n] and, when
+// host_out != NULL, copied to host_out[b] ([nb][n][n], pinned or pageable) on a second stream while the next
+// slots are being computed.  ring_len == nb keeps every replicate resident (gv2_job_replicates).
+//
+// Two nested batches: a SUPER-CHUNK of replicates shares one pass of the expensive per-table work (tensor-core
+// pair sums for up to 128 replicates per CTA, GOM scoring 32 replicates per warp); inside it, sub-chunks of at
+// most ring_len / 2 replicates run the cheap per-replicate tail (GOM Jaccard sums, epilogue) into one half of
+// the ring while the other half drains to the host.
+extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
+                                         int64_t ring_len, double* host_out, gv2_replicate_cb cb_fn, void* cb_user) {
+    if (!job || !dev_weights || !dev_ring || nb < 0 || ring_len <= 0 || (cb_fn && !host_out))
+        return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_stream: bad arguments");
+    if (cb_fn && ring_len < 2 && nb > 1)
+        return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_replicates_stream: callback mode needs ring_len >= 2");
     gv2_ctx* ctx = job->ctx;
     GV2_CUDA(ctx, cudaSetDevice(ctx->device));
     if (nb == 0 || job->n == 0) return GV2_OK;
     const int64_t n = job->n, p = job->p, g = job->g, ntl = job->ntiles;
     const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
-    // replicates per pass: bounded by the pair-sum workspaces (8 B * N_pad^2/2 per replicate and component)
-    const size_t per_rep = ntl * tile_elems * sizeof(double) * ((job->need_p ? 1 : 0) + (job->need_g ? 1 : 0)) +
-                           (job->need_g ? (size_t)job->n_pad * job->g_pad * 4 + (size_t)n * g * 8 : 0);
+    ring_len = std::min(ring_len, nb);
+    // sub-chunk: half the ring when results stream to the host (ping-pong), else the whole ring
+    const int64_t sub = (host_out && ring_len >= 2) ? ring_len / 2 : ring_len;
+    // super-chunk: bounded by the fp64 pair-sum workspace of the signature table (+ the GOM tables)
+    const size_t per_rep = (job->need_p ? ntl * tile_elems * sizeof(double) + (size_t)job->p_pad : 0) +
+                           (job->need_g ? (size_t)job->n_pad * job->g_pad * 4 + (size_t)n * g * 8 : 0) + (size_t)n * 8 * 2;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const size_t have = job->wsP.bytes + job->wsG.bytes + job->gomf.bytes + job->gomtab.bytes;
-    int64_t chunk = (int64_t)std::max<size_t>(1, std::min<size_t>((size_t)nb, (size_t)((free_b + have) * 0.5) / std::max<size_t>(1, per_rep)));
-    chunk = std::min<int64_t>(chunk, 512);
+    const size_t have = job->wsP.bytes + job->gomf.bytes + job->gomtab.bytes + job->wbf16.bytes;
+    const size_t sub_bytes = job->need_g ? (size_t)sub * ntl * tile_elems * sizeof(double) : 0;
+    const size_t avail = (size_t)((free_b + have) * 0.85);
+    int64_t super = (int64_t)((avail > sub_bytes ? avail - sub_bytes : 0) / std::max<size_t>(1, per_rep));
+    super = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(super, nb), 1024));
+    if (super >= 128) super = super / 128 * 128;            // whole 128-replicate tensor-core blocks
+    else if (super >= 32) super = super / 32 * 32;
+    if (!job->copy_stream) {
+        GV2_CUDA(ctx, cudaStreamCreateWithFlags(&job->copy_stream, cudaStreamNonBlocking));
+        for (int h = 0; h < 2; ++h) {
+            GV2_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_ready[h], cudaEventDisableTiming));
+            GV2_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_drained[h], cudaEventDisableTiming));
+        }
+    }
+    bool drained_pending[2] = {false, false};
+    int64_t pend_b0[2] = {0, 0}, pend_cb[2] = {0, 0}, pend_slot[2] = {0, 0};   // sub-chunk whose copy is in flight, per half
     int rc;
     bool used_mma = false;
-    for (int64_t b0 = 0; b0 < nb; b0 += chunk) {
-        const int64_t cb = std::min<int64_t>(chunk, nb - b0);
-        const int32_t* w = dev_weights + b0 * p;
+    int64_t slot = 0;     // next ring slot
+    int half = 0;
+    // callback mode: once the copy of a sub-chunk has landed in the host ring, hand its replicates to the consumer.
+    // Called AFTER the next sub-chunk has been enqueued, so the GPU computes while the consumer works.
+    auto deliver = [&](int h) -> int {
+        if (!cb_fn || !drained_pending[h]) return GV2_OK;
+        cudaError_t e = cudaEventSynchronize(job->ev_drained[h]);
+        if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "replicate copy: %s", cudaGetErrorString(e));
+        for (int64_t k = 0; k < pend_cb[h]; ++k)
+            if (cb_fn(pend_b0[h] + k, host_out + (pend_slot[h] + k) * n * n, cb_user) != 0)
+                return gv2_fail(ctx, GV2_ERR_ARG, "replicate callback asked to stop at replicate %lld", (long long)(pend_b0[h] + k));
+        drained_pending[h] = false;
+        return GV2_OK;
+    };
+    for (int64_t s0 = 0; s0 < nb; s0 += super) {
+        const int64_t sb = std::min<int64_t>(super, nb - s0);
+        const int32_t* w = dev_weights + s0 * p;
         gv2_gj_component cp{}, cg{};
         if (job->need_p) {
-            if ((rc = ensure(ctx, job->w_rowsum, (size_t)cb * n * sizeof(double)))) return rc;
-            if ((rc = ensure(ctx, job->wsP, (size_t)cb * ntl * tile_elems * sizeof(double)))) return rc;
-            if (job->mma_ok && cb >= 8) {
+            if ((rc = ensure(ctx, job->w_rowsum, (size_t)sb * n * sizeof(double)))) return rc;
+            if ((rc = ensure(ctx, job->wsP, (size_t)sb * ntl * tile_elems * sizeof(double)))) return rc;
+            if (job->mma_ok && sb >= 8) {
                 // tensor-core path: exact integer contraction on the fixed-point table
-                if ((rc = ensure(ctx, job->wbf16, boot_mma_scratch_bytes(job->p_pad, cb)))) return rc;
+                if ((rc = ensure(ctx, job->wbf16, boot_mma_scratch_bytes(job->p_pad, sb)))) return rc;
                 if (!job->mma_flag.p) {
                     if ((rc = ensure(ctx, job->mma_flag, sizeof(int)))) return rc;
                     GV2_CUDA(ctx, cudaMemsetAsync(job->mma_flag.p, 0, sizeof(int), ctx->stream));
                 }
-                if ((rc = boot_mma_rowsums(ctx, job->sigfix.as<uint32_t>(), n, p, job->p_pad, w, cb, job->quantum,
+                if ((rc = boot_mma_rowsums(ctx, job->sigfix.as<uint32_t>(), n, p, job->p_pad, w, sb, job->quantum,
                                            job->w_rowsum.as<double>()))) return rc;
-                if ((rc = boot_mma_launch(ctx, job->sigfix.as<uint32_t>(), job->quantum, job->n_pad, job->p_pad, 0, ntl, w, p, cb,
+                if ((rc = boot_mma_launch(ctx, job->sigfix.as<uint32_t>(), job->quantum, job->n_pad, job->p_pad, 0, ntl, w, p, sb,
                                           job->wbf16.p, job->mma_flag.as<int>(), job->wsP.as<double>()))) return rc;
                 used_mma = true;
             } else {
-                if ((rc = ensure(ctx, job->wf, (size_t)cb * job->p_pad * sizeof(float)))) return rc;
-                if ((rc = gv2_dev_weights_to_float(ctx, w, cb, p, job->p_pad, job->wf.as<float>()))) return rc;
-                if ((rc = gv2_dev_weighted_rowsums(ctx, job->sigf.as<float>(), n, job->p_pad, job->wf.as<float>(), cb,
+                if ((rc = ensure(ctx, job->wf, (size_t)sb * job->p_pad * sizeof(float)))) return rc;
+                if ((rc = gv2_dev_weights_to_float(ctx, w, sb, p, job->p_pad, job->wf.as<float>()))) return rc;
+                if ((rc = gv2_dev_weighted_rowsums(ctx, job->sigf.as<float>(), n, job->p_pad, job->wf.as<float>(), sb,
                                                    job->w_rowsum.as<double>()))) return rc;
-                if ((rc = gj_min_sums_launch(ctx, job->sigf.as<float>(), 0, job->n_pad, job->p_pad, 0, ntl, job->wf.as<float>(), cb, 1,
+                if ((rc = gj_min_sums_launch(ctx, job->sigf.as<float>(), 0, job->n_pad, job->p_pad, 0, ntl, job->wf.as<float>(), sb, 1,
                                              job->wsP.as<double>()))) return rc;
             }
-            cp.min_sums = job->wsP.as<double>(); cp.rowsums = job->w_rowsum.as<double>(); cp.nanflags = job->sig_nan.as<uint8_t>();
-            cp.ksplit = 1; cp.replicate_stride_sums = (int64_t)(ntl * tile_elems); cp.replicate_stride_rows = n;
         }
         if (job->need_g) {
-            if ((rc = ensure(ctx, job->gomtab, (size_t)cb * n * g * sizeof(double)))) return rc;
-            if ((rc = gom_db_score(ctx, job->gom, w, cb, job->gomtab.as<double>()))) return rc;
-            if ((rc = job_prepare_gom(job, job->gomtab.as<double>(), cb))) return rc;
-            if ((rc = ensure(ctx, job->wsG, (size_t)cb * ntl * tile_elems * sizeof(double)))) return rc;
-            if ((rc = gj_min_sums_launch(ctx, job->gomf.as<float>(), job->n_pad * job->g_pad, job->n_pad, job->g_pad, 0, ntl, nullptr, cb, 1,
-                                         job->wsG.as<double>()))) return rc;
-            cg.min_sums = job->wsG.as<double>(); cg.rowsums = job->gom_rowsum.as<double>(); cg.nanflags = job->gom_nan.as<uint8_t>();
-            cg.ksplit = 1; cg.replicate_stride_sums = (int64_t)(ntl * tile_elems); cg.replicate_stride_rows = n;
-            cg.replicate_stride_nan = n;
+            if ((rc = ensure(ctx, job->gomtab, (size_t)sb * n * g * sizeof(double)))) return rc;
+            if ((rc = gom_db_score(ctx, job->gom, w, sb, job->gomtab.as<double>()))) return rc;
+            if ((rc = job_prepare_gom(job, job->gomtab.as<double>(), sb))) return rc;
         }
-        // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)
-        if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
-                                      dev_out + b0 * n * n, n * n))) return rc;
+        for (int64_t c0 = 0; c0 < sb; c0 += sub) {
+            int64_t cb = std::min<int64_t>(sub, sb - c0);
+            if (slot + cb > ring_len) slot = 0;                            // sub-chunks never wrap inside the ring
+            if (host_out && ring_len >= 2) { slot = half * sub; }
+            if (cb_fn) {
+                if ((rc = deliver(half))) return rc;                       // consumer is done with these host slots too
+            } else if (drained_pending[half]) {                            // the copy that last read these slots is done
+                GV2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, job->ev_drained[half], 0));
+                drained_pending[half] = false;
+            }
+            if (job->need_p) {
+                cp.min_sums = job->wsP.as<double>() + (size_t)c0 * ntl * tile_elems;
+                cp.rowsums = job->w_rowsum.as<double>() + c0 * n; cp.nanflags = job->sig_nan.as<uint8_t>();
+                cp.ksplit = 1; cp.replicate_stride_sums = (int64_t)(ntl * tile_elems); cp.replicate_stride_rows = n;
+            }
+            if (job->need_g) {
+                if ((rc = ensure(ctx, job->wsG, (size_t)cb * ntl * tile_elems * sizeof(double)))) return rc;
+                if ((rc = gj_min_sums_launch(ctx, job->gomf.as<float>() + (size_t)c0 * job->n_pad * job->g_pad, job->n_pad * job->g_pad,
+                                             job->n_pad, job->g_pad, 0, ntl, nullptr, cb, 1, job->wsG.as<double>()))) return rc;
+                cg.min_sums = job->wsG.as<double>(); cg.rowsums = job->gom_rowsum.as<double>() + c0 * n;
+                cg.nanflags = job->gom_nan.as<uint8_t>() + c0 * n;
+                cg.ksplit = 1; cg.replicate_stride_sums = (int64_t)(ntl * tile_elems); cg.replicate_stride_rows = n;
+                cg.replicate_stride_nan = n;
+            }
+            // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)
+            if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
+                                          dev_ring + slot * n * n, n * n))) return rc;
+            if (host_out) {
+                GV2_CUDA(ctx, cudaEventRecord(job->ev_ready[half], ctx->stream));
+                GV2_CUDA(ctx, cudaStreamWaitEvent(job->copy_stream, job->ev_ready[half], 0));
+                double* hdst = cb_fn ? host_out + slot * n * n : host_out + (s0 + c0) * n * n;   // host ring vs linear output
+                GV2_CUDA(ctx, cudaMemcpyAsync(hdst, dev_ring + slot * n * n, (size_t)cb * n * n * sizeof(double),
+                                              cudaMemcpyDeviceToHost, job->copy_stream));
+                GV2_CUDA(ctx, cudaEventRecord(job->ev_drained[half], job->copy_stream));
+                drained_pending[half] = true;
+                pend_b0[half] = s0 + c0; pend_cb[half] = cb; pend_slot[half] = slot;
+                half ^= 1;
+                if (cb_fn && (rc = deliver(half))) return rc;              // previous sub-chunk, while this one runs
+            }
+            slot += cb;
+        }
     }
+    if (cb_fn) {
+        if ((rc = deliver(half))) return rc;
+        if ((rc = deliver(half ^ 1))) return rc;
+    }
+    if (host_out) GV2_CUDA(ctx, cudaStreamSynchronize(job->copy_stream));
     if (used_mma) {     // multiplicities above 255 do not fit the uint8 operand: refuse rather than wrap
         int flag = 0;
         GV2_CUDA(ctx, cudaMemcpyAsync(&flag, job->mma_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -366,6 +490,12 @@ extern "C" int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int6
         if (flag) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a column multiplicity exceeds 255 (uint8 weights of the tensor-core path); set GV2_DISABLE_MMA=1");
     }
     return GV2_OK;
+}
+
+extern "C" int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out) {
+    if (nb < 0) return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates: bad arguments");
+    if (nb == 0) return GV2_OK;
+    return gv2_job_replicates_stream(job, dev_weights, nb, dev_out, nb, nullptr, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------ host-pointer wrappers
@@ -492,18 +622,14 @@ extern "C" int gv2_bootstrap_host(gv2_ctx* ctx, const double* sig, const double*
     cudaError_t e = d_w.alloc((size_t)nb * p * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_w.p, weights, (size_t)nb * p * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { gv2_job_destroy(job); return gv2_fail(ctx, GV2_ERR_CUDA, "weights upload: %s", cudaGetErrorString(e)); }
-    // stream the replicates out in slabs so that the device never holds more than ~4 GB of output
-    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(nb, (int64_t)((4ULL << 30) / std::max<size_t>(1, (size_t)n * n * 8))));
-    e = d_out.alloc((size_t)slab * n * n * sizeof(double));
-    if (e != cudaSuccess) { gv2_job_destroy(job); return gv2_fail(ctx, GV2_ERR_NOMEM, "bootstrap output slab: %s", cudaGetErrorString(e)); }
-    for (int64_t b0 = 0; b0 < nb && rc == GV2_OK; b0 += slab) {
-        const int64_t cb = std::min<int64_t>(slab, nb - b0);
-        rc = gv2_job_replicates(job, d_w.as<int32_t>() + b0 * p, cb, d_out.as<double>());
-        if (rc == GV2_OK) {
-            e = cudaMemcpyAsync(out + b0 * n * n, d_out.p, (size_t)cb * n * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) rc = gv2_fail(ctx, GV2_ERR_CUDA, "bootstrap download: %s", cudaGetErrorString(e));
-        }
+    // replicates stream through a device ring of at most ~8 GB (two halves: one computing, one draining)
+    const int64_t ring_len = std::max<int64_t>(2, std::min<int64_t>(nb, (int64_t)((8ULL << 30) / std::max<size_t>(1, (size_t)n * n * 8))));
+    e = d_out.alloc((size_t)std::min<int64_t>(ring_len, nb) * n * n * sizeof(double));
+    if (e != cudaSuccess) { gv2_job_destroy(job); return gv2_fail(ctx, GV2_ERR_NOMEM, "bootstrap output ring: %s", cudaGetErrorString(e)); }
+    rc = gv2_job_replicates_stream(job, d_w.as<int32_t>(), nb, d_out.as<double>(), ring_len, out, nullptr, nullptr);
+    if (rc == GV2_OK) {
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = gv2_fail(ctx, GV2_ERR_CUDA, "bootstrap: %s", cudaGetErrorString(e));
     }
     gv2_job_destroy(job);
     return rc;

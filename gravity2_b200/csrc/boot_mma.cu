@@ -39,7 +39,7 @@
 #define BM_PLANES 4                    // uint8 digit planes of the 32-bit fixed-point min
 #define BM_NMAX 128                    // replicates per CTA: BM_PLANES * BM_NMAX = 512 TMEM columns
 #define BM_TMEM_COLS 512
-#define BM_PRODUCERS 256               // threads
+#define BM_PRODUCERS 512               // producer threads (16 warps: two pair rows per thread and stage)
 #define BM_THREADS (BM_PRODUCERS + 64)
 #define BM_RING 3                      // table-row staging ring (chunks)
 #define BM_ROWS 24                     // 8 i-rows + 16 j-rows
@@ -163,7 +163,9 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
                 const __grid_constant__ CUtensorMap wmap, int nb_total, int nblk, long long ws_rep_stride,
                 double quantum, double* __restrict__ ws) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B: 1024-B aligned
+    // SWIZZLE_128B needs 1024-B alignment; offsetting the array (not casting through uintptr_t) keeps the
+    // pointers provably shared, so the producers get LDS/STS instead of generic LD/ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* stage_base = smem;
     uint32_t* ring = (uint32_t*)(smem + BM_STAGES * BM_STAGE_BYTES);
     uint64_t* bars = (uint64_t*)(smem + BM_STAGES * BM_STAGE_BYTES + BM_RING * BM_RING_BYTES);
@@ -198,7 +200,7 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < BM_PRODUCERS / 32) {
         // ============================ producers ============================
         const uint32_t* gI = tab + (size_t)(bi * GV2_TILE + si * 8) * ld;
         const uint32_t* gJ = tab + (size_t)(bj * GV2_TILE + sj * 16) * ld;
@@ -214,7 +216,7 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
             if (s < kchunks) ring_load(s);
             asm volatile("cp.async.commit_group;");
         }
-        const int q = tid & 7;
+        static_assert(BM_PRODUCERS == 512 && BM_PAIRS == 128 && BM_KC == 128, "producer mapping: 16 warps x (2 x 4 pairs), 32 lanes x 4 columns");
         for (int kc = 0; kc < kchunks; ++kc) {
             const int st = kc % BM_STAGES;
             const uint32_t ph = (kc / BM_STAGES) & 1;
@@ -225,24 +227,30 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
             mbar_wait(&empty[st], ph ^ 1);                                   // MMA has drained this stage
             const uint32_t* rg = ring + (kc % BM_RING) * (BM_ROWS * BM_KC);
             uint8_t* a0 = stage_base + st * BM_STAGE_BYTES;
+            // Warp w owns a 2 x 4 block of pairs (i-rows 2*(w/4)+{0,1}, j-rows 4*(w%4)+{0..3}); lane = one group of
+            // four consecutive columns.  Per stage a thread loads 2 x-pieces + 4 y-pieces (6 LDS.128 for 8 pairs:
+            // the shared-memory data pipe, shared with the tensor core's operand reads, is this kernel's bound)
+            // and a warp's 32 STS.32 to one A row cover its 128 bytes exactly once under the XOR swizzle.
+            const int ii0 = (warp >> 2) * 2, jj0 = (warp & 3) * 4;
+            const int col = lane * 4;
+            uint4 x[2], y[4];
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int m = (tid >> 3) + 32 * it;              // pair row of the A tiles
-                const int ii = m >> 4, jj = m & 15;
-                // K-major SWIZZLE_128B row: (m/8)*1024 + (m%8)*128, 16-byte piece x at (x ^ (m%8))*16
-                uint8_t* row = a0 + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u;
+            for (int a = 0; a < 2; ++a) x[a] = *reinterpret_cast<const uint4*>(rg + (ii0 + a) * BM_KC + col);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    // this thread's 4 consecutive columns: 16-byte piece (c*8 + q) of the 128-column chunk
-                    const int col = (c * 8 + q) * 4;
-                    const uint4 x = *reinterpret_cast<const uint4*>(rg + ii * BM_KC + col);
-                    const uint4 y = *reinterpret_cast<const uint4*>(rg + (8 + jj) * BM_KC + col);
+            for (int b = 0; b < 4; ++b) y[b] = *reinterpret_cast<const uint4*>(rg + (8 + jj0 + b) * BM_KC + col);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int m = (ii0 + a) * 16 + jj0 + b;                 // pair row of the A tiles
                     uint32_t p[4];
-                    byte_planes(min(x.x, y.x), min(x.y, y.y), min(x.z, y.z), min(x.w, y.w), p);
-                    // columns col..col+3 are bytes col..col+3 of the uint8 row: piece col/16, word (col/4)%4
-                    const uint32_t off = (uint32_t)((((col >> 4) ^ (m & 7)) << 4) + (col & 12));
+                    byte_planes(min(x[a].x, y[b].x), min(x[a].y, y[b].y), min(x[a].z, y[b].z), min(x[a].w, y[b].w), p);
+                    // K-major SWIZZLE_128B: row m at (m/8)*1024 + (m%8)*128; columns col..col+3 are bytes col..col+3:
+                    // 16-byte piece col/16 (XOR m%8), word (col/4)%4
+                    uint8_t* dst = a0 + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u +
+                                   (uint32_t)((((col >> 4) ^ (m & 7)) << 4) + (col & 12));
 #pragma unroll
-                    for (int d = 0; d < BM_PLANES; ++d) *reinterpret_cast<uint32_t*>(row + d * BM_A_BYTES + off) = p[d];
+                    for (int d = 0; d < BM_PLANES; ++d) *reinterpret_cast<uint32_t*>(dst + d * BM_A_BYTES) = p[d];
                 }
             }
             fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor-core (async) proxy
@@ -251,12 +259,14 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
         // ============================ epilogue ============================
         mbar_wait(tmem_full, 0);
         tc_fence_after();
-        const int lg = warp & 3, half = warp >> 2;          // TMEM lanes 32*lg.., replicate columns half*64..
+        constexpr int kColGroups = BM_PRODUCERS / 128;      // warps sharing a TMEM lane quarter split the columns
+        constexpr int kColsPerGroup = BM_NMAX / kColGroups;
+        const int lg = warp & 3, half = warp >> 2;          // TMEM lanes 32*lg.., replicate columns half*kColsPerGroup..
         const int m = lg * 32 + lane;
         const int r = si * 8 + (m >> 4), c = sj * 16 + (m & 15);
         double* out = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + bm_ws_index(r, c);
-        for (int cb = 0; cb < 4; ++cb) {
-            const int col0 = half * 64 + cb * 16;
+        for (int cb = 0; cb < kColsPerGroup / 16; ++cb) {
+            const int col0 = half * kColsPerGroup + cb * 16;
             if (col0 >= umma_n) break;
             uint32_t v[BM_PLANES][16];
 #pragma unroll
@@ -272,7 +282,7 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
                 if (rep < nrep) out[(size_t)(rep0 + rep) * ws_rep_stride] = sum * quantum;
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == BM_PRODUCERS / 32) {
         // ============================ TMA: W tiles ============================
         if (lane == 0) {
             for (int kc = 0; kc < kchunks; ++kc) {

@@ -183,7 +183,7 @@ def gom_membership(TaxoGroupingList, GOMIDList, n_rows: Optional[int] = None):
 
 def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, GOMIDList, payload,
                                 N_Bootstrap: Optional[int] = None, pipeline: str = "pl1", indices=None,
-                                batch: int = 64, distance: bool = True,
+                                batch: int = 256, distance: bool = True,
                                 engine: Optional[Engine] = None) -> Iterator[np.ndarray]:
     """Yields one (N, N) float64 matrix per bootstrap replicate, in the reference's order.
 
@@ -192,7 +192,10 @@ def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGro
     pipeline="pl2": app/src/virus_classification.py:290-315 -- sorted indices, real location table,
     GOMDB from the first len(TaxoGroupingList) rows.
     ``indices`` (B, P) overrides the draw (e.g. Engine.philox_indices); by default indices are drawn
-    exactly as the reference draws them, replicate by replicate."""
+    exactly as the reference draws them, replicate by replicate.
+    Each yielded matrix is a zero-copy view into a pinned host ring: it is valid until the next one is
+    requested (copy it to keep it), which is how the reference's loop uses it (tree, then discard)."""
+    from .engine import Job
     eng = engine or default_engine()
     sig = np.ascontiguousarray(PPHMMSignatureTable, dtype=np.float64)
     n, p = sig.shape
@@ -202,13 +205,18 @@ def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGro
         raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
     loc = sig if pipeline == "pl1" else np.ascontiguousarray(PPHMMLocationTable, dtype=np.float64)
     gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
-    for b0 in range(0, nb, batch):
-        cb = min(batch, nb - b0)
-        if indices is None:
-            idx = [draw_resample_indices(p, sort=(pipeline == "pl2")) for _ in range(cb)]
-        else:
-            idx = indices[b0:b0 + cb]
-        w = np.stack([weights_from_indices(i, p) for i in idx])
-        out = eng.bootstrap(sig, loc, gor, len(GOMIDList), w, scheme, float(payload.get("p", 1.0)), distance=distance)
-        for k in range(cb):
-            yield out[k]
+    job = Job(eng, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance=distance)
+    try:
+        # tables are uploaded once; replicates go through in batches big enough to fill the tensor-core
+        # blocks (128 replicates per CTA) and the 32-replicate lanes of the GOM kernels
+        for b0 in range(0, nb, batch):
+            cb = min(batch, nb - b0)
+            if indices is None:
+                idx = [draw_resample_indices(p, sort=(pipeline == "pl2")) for _ in range(cb)]
+            else:
+                idx = indices[b0:b0 + cb]
+            w = np.stack([weights_from_indices(i, p) for i in idx])
+            for m in job.replicates(w):
+                yield m
+    finally:
+        job.close()

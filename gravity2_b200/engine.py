@@ -40,9 +40,30 @@ class Engine:
             raise GravityNativeError(rc, msg.decode() if msg else "?")
         self.ctx = h
         self.device = int(device)
+        self._ring = (C.c_void_p(), C.c_void_p(), 0)       # cached (device ring, pinned host ring, bytes)
+
+    def ring(self, nbytes: int):
+        """Device + page-locked host staging rings, cached across jobs (pinning memory is slow)."""
+        dev, host, have = self._ring
+        if have >= nbytes:
+            return dev, host
+        self._free_ring()
+        dev, host = C.c_void_p(), C.c_void_p()
+        _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, nbytes, C.byref(dev)))
+        _lib.check(self.ctx, self.lib.gv2_host_alloc(self.ctx, nbytes, C.byref(host)))
+        self._ring = (dev, host, nbytes)
+        return dev, host
+
+    def _free_ring(self):
+        dev, host, have = self._ring
+        if have:
+            self.lib.gv2_dev_free(self.ctx, dev)
+            self.lib.gv2_host_free(self.ctx, host)
+        self._ring = (C.c_void_p(), C.c_void_p(), 0)
 
     def close(self):
         if getattr(self, "ctx", None):
+            self._free_ring()
             self.lib.gv2_destroy(self.ctx)
             self.ctx = None
 
@@ -152,6 +173,132 @@ class Engine:
         out = np.empty((n_boot, p), dtype=np.int64)
         _lib.check(self.ctx, self.lib.gv2_philox_indices_host(self.ctx, C.c_uint64(seed), n_boot, p, _ptr(out)))
         return out
+
+
+class Job:
+    """Device-resident tables (gv2_job): upload once, then the base matrix and any number of bootstrap
+    replicates.  Replicates stream through a device ring and a pinned host ring; each one is handed to
+    the consumer as a zero-copy (N, N) float64 view that is valid until the consumer asks for the next."""
+
+    def __init__(self, eng: Engine, sig, loc, gom_of_row, g: int, scheme: str = "PG", p: float = 1.0,
+                 distance: bool = True, ring_bytes: int = 1 << 30):
+        if scheme not in ("P", "G", "PG"):
+            raise NotImplementedError(f"device jobs cover schemes P, G, PG (got {scheme!r})")
+        self.eng, self.lib, self.ctx = eng, eng.lib, eng.ctx
+        sig = _f64(sig, "PPHMMSignatureTable")
+        self.n, self.p = sig.shape
+        loc_arr = sig if (loc is sig or loc is None) else _f64(loc, "PPHMMLocationTable")
+        gor = None if gom_of_row is None else np.ascontiguousarray(gom_of_row, dtype=np.int32)
+        self.job = C.c_void_p()
+        # the same host pointer for sig and loc (PL1, quirk Q3) is uploaded once by the library
+        _lib.check(self.ctx, self.lib.gv2_job_create(
+            self.ctx, _ptr(sig), _ptr(loc_arr if "G" in scheme else None), 0, self.n, self.p, _ptr(gor),
+            0 if gor is None else len(gor), int(g), SCHEMES[scheme], float(p),
+            OUT_DISTANCE if distance else OUT_SIMILARITY, C.byref(self.job)))
+        self.ntiles = int(self.lib.gv2_num_tiles(self.n))
+        mat = max(1, self.n * self.n * 8)
+        self.ring_len = max(2, int(ring_bytes // mat))       # two halves: one computing, one draining
+
+    def close(self):
+        if getattr(self, "job", None):
+            self.lib.gv2_job_destroy(self.job)
+            self.job = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def base(self) -> np.ndarray:
+        n = self.n
+        d = C.c_void_p()
+        _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, n * n * 8, C.byref(d)))
+        try:
+            _lib.check(self.ctx, self.lib.gv2_job_base(self.job, 0, self.ntiles, 0, d))
+            out = np.empty((n, n))
+            _lib.check(self.ctx, self.lib.gv2_memcpy_d2h(self.ctx, _ptr(out), d, n * n * 8))
+        finally:
+            self.lib.gv2_dev_free(self.ctx, d)
+        return out
+
+    def for_each_replicate(self, weights, fn) -> None:
+        """fn(b, matrix) for every replicate in order; matrix is a zero-copy view into the pinned ring."""
+        w = np.ascontiguousarray(weights, dtype=np.int32)
+        if w.ndim == 1:
+            w = w[None, :]
+        nb = w.shape[0]
+        if nb == 0:
+            return
+        if w.shape[1] != self.p:
+            raise ValueError("weights must be (B, P)")
+        n = self.n
+        ring_len = max(2, min(self.ring_len, nb))
+        dev_ring, host_ring = self.eng.ring(ring_len * n * n * 8)
+        d_w = C.c_void_p()
+        _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, w.nbytes, C.byref(d_w)))
+        err = []
+
+        def _cb(b, ptr, _user):
+            try:
+                buf = (C.c_double * (n * n)).from_address(ptr)
+                fn(int(b), np.frombuffer(buf, dtype=np.float64).reshape(n, n))
+                return 0
+            except BaseException as e:      # never let an exception cross the C frame
+                err.append(e)
+                return 1
+
+        cb = _lib.REPLICATE_CB(_cb)
+        try:
+            _lib.check(self.ctx, self.lib.gv2_memcpy_h2d(self.ctx, d_w, _ptr(w), w.nbytes))
+            rc = self.lib.gv2_job_replicates_stream(self.job, d_w, nb, dev_ring, ring_len, host_ring,
+                                                    C.cast(cb, C.c_void_p), None)
+            if err:
+                raise err[0]
+            _lib.check(self.ctx, rc)
+        finally:
+            self.lib.gv2_dev_free(self.ctx, d_w)
+
+    def replicates(self, weights) -> Iterator[np.ndarray]:
+        """Generator form of for_each_replicate: the native call runs on a worker thread and hands each
+        matrix over without copying; the GPU keeps computing ahead while the consumer holds a matrix."""
+        import queue
+        import threading
+        q: "queue.Queue" = queue.Queue(maxsize=1)
+        done = threading.Event()
+        stop = []
+
+        def hand_over(b, m):
+            if stop:
+                raise StopIteration
+            done.clear()
+            q.put((b, m))
+            done.wait()                 # consumer has moved on: the ring slot may be reused
+
+        def run():
+            try:
+                self.for_each_replicate(weights, hand_over)
+                q.put(None)
+            except StopIteration:
+                q.put(None)
+            except BaseException as e:
+                q.put(e)
+
+        t = threading.Thread(target=run, daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield item[1]
+                done.set()
+        finally:
+            stop.append(True)
+            done.set()
+            t.join()
 
 
 _default: Optional[Engine] = None

@@ -65,6 +65,14 @@ const char* gv2_last_error(const gv2_ctx* ctx); /* ctx may be NULL: last creatio
 int gv2_synchronize(gv2_ctx* ctx);
 uint64_t gv2_launch_count(const gv2_ctx* ctx); /* kernels launched so far through ctx */
 
+/* device / pinned-host memory for hosts without their own CUDA binding (ctypes, cgo, JNI ...) */
+int gv2_dev_alloc(gv2_ctx* ctx, size_t bytes, void** out);
+int gv2_dev_free(gv2_ctx* ctx, void* ptr);
+int gv2_host_alloc(gv2_ctx* ctx, size_t bytes, void** out); /* page-locked */
+int gv2_host_free(gv2_ctx* ctx, void* ptr);
+int gv2_memcpy_h2d(gv2_ctx* ctx, void* dst, const void* src, size_t bytes); /* synchronous */
+int gv2_memcpy_d2h(gv2_ctx* ctx, void* dst, const void* src, size_t bytes);
+
 /* ---- host-pointer entry points (what the reference-side binding calls) ----------------- */
 
 /* Replaces SimilarityMat_Constructor's pair loop + clean/combine/power for
@@ -127,6 +135,7 @@ int gv2_dev_philox_weights(gv2_ctx* ctx, uint64_t seed, int64_t b0, int64_t nb, 
 
 /* ---- device-resident job: tables stay in HBM across calls ------------------------------ */
 typedef struct gv2_job gv2_job;
+typedef int (*gv2_replicate_cb)(int64_t replicate, const double* matrix /* [n][n] host */, void* user);
 /* Uploads (or, with *_is_device != 0, reads in place) the float64 tables, converts them to the
  * kernels' layouts and builds the GOM side structures.  loc / gom_of_row may be NULL when the
  * scheme has no "G". */
@@ -141,6 +150,15 @@ void gv2_job_destroy(gv2_job* job);
 int gv2_job_base(gv2_job* job, int64_t tile_begin, int64_t tile_end, int packed, double* dev_out);
 /* Replicates [0, nb) given their device-resident weights; dev_out [nb][n][n]. */
 int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out);
+/* Streaming form: replicate b goes to slot (b % ring_len) of dev_ring [ring_len][n][n]; with host_out != NULL
+ * ([nb][n][n] host memory, ideally pinned) every replicate is also copied out on a second stream while the
+ * next ones are computed, so the device never holds more than ring_len matrices.
+ * callback == NULL: host_out is linear, replicate b lands in host_out[b].
+ * callback != NULL: host_out is a HOST RING [ring_len][n][n]; as soon as replicate b is in host memory the
+ * library calls callback(b, matrix, user) on the calling thread (in replicate order) while the GPU already
+ * computes the next sub-chunk; the matrix is valid until the callback returns; non-zero return stops. */
+int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
+                              int64_t ring_len, double* host_out, gv2_replicate_cb callback, void* user);
 /* GOM signature table of the job's loc table under the given weights (NULL = base):
  * dev_out [nb][n][g]. */
 int gv2_job_gom_table(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out);

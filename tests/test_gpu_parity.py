@@ -134,14 +134,15 @@ def test_bootstrap_golden(golden, eng, tag):
     payload = {"N_Bootstrap": 3, "SimilarityMeasurementScheme": "PG", "p": 1.0,
                "PphmmNeighbourhoodWeight": 0.0, "PphmmSigScoreThreshold": 0}
     np.random.seed(int(golden[f"{tag}_boot_seed"]))
-    got = list(G.bootstrap_distance_matrices(sig, loc, taxo, ids, payload, pipeline="pl1"))
+    # each yielded matrix is a view into the pinned host ring, valid until the next is requested: copy to keep
+    got = [m.copy() for m in G.bootstrap_distance_matrices(sig, loc, taxo, ids, payload, pipeline="pl1")]
     assert len(got) == 3
     for r in range(3):
         # D = 1 - S: the 1e-6 relative bound on S is an absolute 1e-6 bound on D
         close(got[r], golden[f"{tag}_pl1_D"][r], rtol=0, atol=1e-6)
         assert np.all(np.diag(got[r])[np.diag(golden[f"{tag}_pl1_D"][r]) == 0] == 0)
     n_ref = int(golden[f"{tag}_pl2_nref"])
-    got = list(G.bootstrap_distance_matrices(sig, loc, taxo[:n_ref], ids, payload, pipeline="pl2", distance=False))
+    got = [m.copy() for m in G.bootstrap_distance_matrices(sig, loc, taxo[:n_ref], ids, payload, pipeline="pl2", distance=False)]
     for r in range(3):
         close(got[r], golden[f"{tag}_pl2_S"][r])
     # the global numpy stream advanced exactly as in the reference run: next draw matches a fresh replay
@@ -262,3 +263,51 @@ def test_philox_indices_bit_exact(eng):
         got = eng.philox_indices(seed, nb, p)
         assert got.dtype == np.int64
         assert np.array_equal(got, philox_oracle.philox_indices(seed, nb, p))
+
+
+def test_streaming_job_matches_batch_and_oracle(eng):
+    """Job: tables uploaded once, 150 PG replicates streamed through the rings (tensor-core blocks of
+    128 + a remainder, ring ping-pong, callback hand-over) == the all-at-once entry point == oracle."""
+    import gravity2_b200 as G
+    from gravity2_b200.engine import Job
+    t = synth.make_tables(140, 900, 6, 0.06, seed=31)
+    rng = np.random.default_rng(9)
+    w = np.stack([np.bincount(rng.integers(0, 900, 900), minlength=900) for _ in range(150)]).astype(np.int32)
+    gor = G.gom_membership(t.taxo, t.gom_ids)
+    job = Job(eng, t.sig, t.sig, gor, len(t.gom_ids), "PG", 1.0, distance=True, ring_bytes=7 * 140 * 140 * 8)
+    seen = {}
+    job.for_each_replicate(w, lambda b, m: seen.__setitem__(b, m.copy()))
+    assert sorted(seen) == list(range(150))
+    gen = [m.copy() for m in job.replicates(w[:5])]
+    base = job.base()
+    job.close()
+    allatonce = eng.bootstrap(t.sig, t.sig, gor, len(t.gom_ids), w, "PG", 1.0, distance=True)
+    for b in range(150):
+        assert np.array_equal(seen[b], allatonce[b])
+    for b in range(5):      # 5 replicates run on the fp32 CUDA-core kernel, 150 on the tensor cores
+        close(gen[b], allatonce[b], rtol=0, atol=1e-6)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for b in (0, 77, 149):
+            idx = np.repeat(np.arange(900), w[b])
+            ref = O.pl1_bootstrap_replicate(t.sig, t.taxo, t.gom_ids, idx)
+            close(seen[b], ref, rtol=0, atol=1e-6)
+        db = O.gomdb(t.taxo, t.sig, t.gom_ids)          # PL1: signature table doubles as location table
+        ref0 = O.dist_from_sim(O.similarity_mat(t.sig.copy(), O.gom_table(t.sig, db, t.gom_ids), t.sig, None, 0.0, 0, "PG", 1.0))
+    close(base, ref0, rtol=0, atol=1e-6)
+
+
+def test_tensor_core_path_is_exact_integer_arithmetic(eng):
+    """scheme P replicates through tcgen05 (>= 8 replicates): error is the 2^-33 input quantisation only"""
+    t = synth.make_tables(200, 1500, 5, 0.3, seed=41)
+    rng = np.random.default_rng(2)
+    w = np.stack([np.bincount(rng.integers(0, 1500, 1500), minlength=1500) for _ in range(24)]).astype(np.int32)
+    S = eng.bootstrap(t.sig, None, None, 0, w, "P", 1.0, distance=False)
+    for b in (0, 23):
+        ref = O.similarity_mat_fast(t.sig, None, None, 0, "P", 1.0, w=w[b])
+        close(S[b], ref, rtol=2e-8)
+        assert np.array_equal(S[b], S[b].T) and np.all(np.diag(S[b]) == 1.0)
+    # duplicate genomes: exactly 1.0 off the diagonal (integer sums cancel exactly)
+    t.sig[10] = t.sig[3]
+    S = eng.bootstrap(t.sig, None, None, 0, w[:8], "P", 1.0, distance=False)
+    assert np.all(S[:, 3, 10] == 1.0)
