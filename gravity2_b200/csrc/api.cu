@@ -20,8 +20,7 @@ int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n
 size_t boot_mma_scratch_bytes(int64_t k_pad, int64_t nb);
 int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src, uint32_t* dst,
                            int64_t n_pad, int64_t k_pad, double* quantum, int* usable);
-int boot_mma_rowsums(gv2_ctx* ctx, const uint32_t* tab, int64_t n, int64_t k, int64_t k_pad, const int32_t* w, int64_t nb,
-                     double quantum, double* out);
+int boot_mma_rowsums(gv2_ctx* ctx, const double* ws, int64_t ntl, int64_t n, int64_t nb, double* out);
 
 static thread_local std::string g_create_error;
 
@@ -417,10 +416,9 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
                     if ((rc = ensure(ctx, job->mma_flag, sizeof(int)))) return rc;
                     GV2_CUDA(ctx, cudaMemsetAsync(job->mma_flag.p, 0, sizeof(int), ctx->stream));
                 }
-                if ((rc = boot_mma_rowsums(ctx, job->sigfix.as<uint32_t>(), n, p, job->p_pad, w, sb, job->quantum,
-                                           job->w_rowsum.as<double>()))) return rc;
                 if ((rc = boot_mma_launch(ctx, job->sigfix.as<uint32_t>(), job->quantum, job->n_pad, job->p_pad, 0, ntl, w, p, sb,
                                           job->wbf16.p, job->mma_flag.as<int>(), job->wsP.as<double>()))) return rc;
+                if ((rc = boot_mma_rowsums(ctx, job->wsP.as<double>(), ntl, n, sb, job->w_rowsum.as<double>()))) return rc;
                 used_mma = true;
             } else {
                 if ((rc = ensure(ctx, job->wf, (size_t)sb * job->p_pad * sizeof(float)))) return rc;

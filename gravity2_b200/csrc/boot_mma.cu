@@ -373,24 +373,17 @@ __global__ void table_stats_kernel(const double* __restrict__ src, long long n, 
     }
 }
 
-// fixed-point weighted row sums: out[b][i] = q * sum_c w[b][c] * x_fix[i][c]  (exact integer sum in fp64 range)
-// grid = (n, nb)
-__global__ void weighted_rowsum_fixed_kernel(const uint32_t* __restrict__ tab, long long k_pad, const int* __restrict__ w,
-                                             long long k, long long n, double quantum, double* __restrict__ out) {
-    const long long r = blockIdx.x, b = blockIdx.y;
-    const uint32_t* t = tab + r * k_pad;
-    const int* ww = w + b * k;
-    unsigned long long s = 0;
-    for (long long c = threadIdx.x; c < k; c += blockDim.x) s += (unsigned long long)t[c] * (unsigned long long)(unsigned)ww[c];
-    __shared__ unsigned long long red[32];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long tt = 0;
-        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tt += red[i];
-        out[b * n + r] = (double)tt * quantum;
-    }
+// Weighted row sums sum_c w[b][c] * x[i][c] are the diagonal pairs (i, i) of the contraction itself
+// (min(x, x) = x), so they are read back from the pair-sum workspace: exact, and identical to what the
+// off-diagonal sums are built from.  grid = (ceil(n/256), nb)
+__global__ void diag_rowsums_kernel(const double* __restrict__ ws, long long ws_rep_stride, int nt, long long n,
+                                    double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (i >= n) return;
+    const long long bi = i / GV2_TILE;
+    const int r = (int)(i % GV2_TILE);
+    const long long t = bi * nt - bi * (bi - 1) / 2;          // linear index of diagonal tile (bi, bi)
+    out[b * n + i] = ws[b * ws_rep_stride + t * (GV2_TILE * GV2_TILE) + bm_ws_index(r, r)];
 }
 
 // ---------------------------------------------------------------------------------- host
@@ -446,11 +439,12 @@ int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k
     return GV2_OK;
 }
 
-int boot_mma_rowsums(gv2_ctx* ctx, const uint32_t* tab, int64_t n, int64_t k, int64_t k_pad, const int32_t* w, int64_t nb,
-                     double quantum, double* out) {
+// ws must hold ALL tiles [0, ntiles) of every replicate (tile_begin == 0)
+int boot_mma_rowsums(gv2_ctx* ctx, const double* ws, int64_t ntl, int64_t n, int64_t nb, double* out) {
     if (n == 0 || nb == 0) return GV2_OK;
-    dim3 grid((unsigned)n, (unsigned)nb);
-    weighted_rowsum_fixed_kernel<<<grid, 256, 0, ctx->stream>>>(tab, k_pad, w, k, n, quantum, out);
+    const int nt = (int)((n + GV2_TILE - 1) / GV2_TILE);
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)nb);
+    diag_rowsums_kernel<<<grid, 256, 0, ctx->stream>>>(ws, (long long)ntl * GV2_TILE * GV2_TILE, nt, n, out);
     GV2_LAUNCH_CHECK(ctx);
     return GV2_OK;
 }

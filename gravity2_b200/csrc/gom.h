@@ -12,7 +12,7 @@ struct GomDb {
     long long nnz = 0;          // non-zero location entries of the scored genomes
     int npt = 0;                // sum over GOMs of |R_g|
     int max_ng = 0, max_t = 0;
-    long long ilist_stride = 0, wave = 0;
+    size_t vg_smem = 0, va_smem = 0;
     size_t bytes = 0;
     // genome CSR
     long long* g_ptr = nullptr; int* g_col = nullptr; double* g_val = nullptr;
@@ -23,7 +23,9 @@ struct GomDb {
     double* X = nullptr; double* nrm = nullptr; double* A = nullptr;
     // per-chunk scratch (32 replicates)
     double* wT = nullptr; double* arT = nullptr; double* sqT = nullptr; double* rT = nullptr;
-    double* gagg = nullptr; double* vagg = nullptr; int* ilist = nullptr;
+    double* gagg = nullptr; double* vagg = nullptr;
+    unsigned char* wT8 = nullptr; double* wG = nullptr; int* flag = nullptr;   // uint8 weights, per-GOM gathered weights, flags
+    long long* heavy_list = nullptr;   // (genome, GOM) pairs whose intersection list overflows the light kernel
 };
 
 int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t ld_loc,

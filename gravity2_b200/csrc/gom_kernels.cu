@@ -139,37 +139,61 @@ __global__ void gom_dist_cache_kernel(const int* __restrict__ pt_ptr, const int*
     if (k < ng && l < ng) A[a_off[g] + (long long)k * ng + l] = sqrt(acc);
 }
 
-// wT[c][b] = (double) w[b0 + b][c] for b < nb, else 0.   grid = ceil(P*NBC/256)
+// wT[c][b] = (double) w[b0 + b][c] for b < nb, else 0; wT8 the same as uint8 (staged in shared memory by the
+// scoring kernels; multiplicities above 255 raise *overflow).   grid = ceil(P*NBC/256)
 __global__ void weights_transpose_kernel(const int* __restrict__ w, long long p, int nb,
-                                         double* __restrict__ wT) {
+                                         double* __restrict__ wT, unsigned char* __restrict__ wT8,
+                                         int* __restrict__ overflow) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p * NBC) return;
     const long long c = i / NBC;
     const int b = (int)(i % NBC);
-    wT[i] = (w == nullptr) ? (b < nb ? 1.0 : 0.0) : (b < nb ? (double)w[(long long)b * p + c] : 0.0);
+    const int v = (w == nullptr) ? (b < nb ? 1 : 0) : (b < nb ? w[(long long)b * p + c] : 0);
+    if (v < 0 || v > 255) atomicExch(overflow, 1);
+    wT[i] = (double)v;
+    wT8[i] = (unsigned char)v;
 }
 
-// GA: arT[pt][b] = sum_l w_l A[k][l],  sqT[pt][b] = sum_l w_l A[k][l]^2.
-// grid = (ceil(max_ng/8), G), block = (32 b, 8 k)
-__global__ void gom_rowsums_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_col,
-                                   const long long* __restrict__ a_off, const double* __restrict__ A,
-                                   const double* __restrict__ wT, double* __restrict__ arT,
-                                   double* __restrict__ sqT) {
+// per-GOM gathered weights: wG[pt][b] = wT[pt_col[pt]][b]   grid = ceil(npt*NBC/256)
+__global__ void gom_gather_weights_kernel(const int* __restrict__ pt_col, long long npt,
+                                          const double* __restrict__ wT, double* __restrict__ wG) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npt * NBC) return;
+    wG[i] = wT[(long long)pt_col[i / NBC] * NBC + (i % NBC)];
+}
+
+// GA: arT[pt][b] = sum_l w_l A[k][l],  sqT[pt][b] = sum_l w_l A[k][l]^2  (a batched GEMV per GOM).
+// grid = (ceil(max_ng/32), G), block = (32 b, 8): each thread owns 4 rows k for its replicate lane, so one
+// coalesced weight load feeds 8 fp64 FMAs.
+__global__ void __launch_bounds__(256)
+gom_rowsums_kernel(const int* __restrict__ pt_ptr, const long long* __restrict__ a_off,
+                   const double* __restrict__ A, const double* __restrict__ wG,
+                   double* __restrict__ arT, double* __restrict__ sqT) {
     const int g = blockIdx.y;
     const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
-    const int k = blockIdx.x * 8 + threadIdx.y;
-    if (k >= ng) return;
+    const int k0 = blockIdx.x * 32 + threadIdx.y * 4;
+    if (k0 >= ng) return;
     const int b = threadIdx.x;
-    const double* a = A + a_off[g] + (long long)k * ng;
-    double s1 = 0.0, s2 = 0.0;
+    const double* a = A + a_off[g];
+    const double* w = wG + (long long)p0 * NBC + b;
+    const int kk[4] = {k0, min(k0 + 1, ng - 1), min(k0 + 2, ng - 1), min(k0 + 3, ng - 1)};
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+#pragma unroll 4
     for (int l = 0; l < ng; ++l) {
-        const double w = wT[(long long)pt_col[p0 + l] * NBC + b];
-        const double d = a[l];
-        s1 = fma(w, d, s1);
-        s2 = fma(w * d, d, s2);
+        const double wv = w[(long long)l * NBC];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const double d = a[(long long)kk[r] * ng + l];
+            s1[r] = fma(wv, d, s1[r]);
+            s2[r] = fma(wv * d, d, s2[r]);
+        }
     }
-    arT[(long long)(p0 + k) * NBC + b] = s1;
-    sqT[(long long)(p0 + k) * NBC + b] = s2;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (k0 + r < ng) {
+            arT[(long long)(p0 + k0 + r) * NBC + b] = s1[r];
+            sqT[(long long)(p0 + k0 + r) * NBC + b] = s2[r];
+        }
 }
 
 // GB: per-GOM aggregates, lane = replicate.  gagg[g][q][b], q in 0..GAGG-1.  grid = G, block = 32
@@ -197,22 +221,33 @@ __global__ void gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int*
 }
 
 // VA: per-genome weighted row sums r_c = sum_{d in R_v} w_d |y_c - y_d| and aggregates.
-// One block per genome; threadIdx.x = replicate lane, threadIdx.y strides over the genome's hits.
+// One block per genome; threadIdx.x = replicate lane, threadIdx.y strides over the genome's hits.  The genome's
+// hit values and its uint8 weights [t][32] are staged in shared memory (dynamic: t * 40 bytes).
 #define VAGG 7   // t, Y1, Y2, Ys, RR1, RR2, RY
 __global__ void genome_rowsums_kernel(const long long* __restrict__ ptr, const int* __restrict__ col,
-                                      const double* __restrict__ val, const double* __restrict__ wT,
+                                      const double* __restrict__ val, const unsigned char* __restrict__ wT8,
                                       double* __restrict__ rT, double* __restrict__ vagg) {
+    extern __shared__ __align__(16) unsigned char va_smem[];
     const long long v = blockIdx.x;
     const long long o = ptr[v];
     const int t = (int)(ptr[v + 1] - o);
-    const int b = threadIdx.x, ny = blockDim.y;
+    double* sy = reinterpret_cast<double*>(va_smem);                 // [t]
+    unsigned char* sw = va_smem + (size_t)((t + 1) & ~1) * 8;         // [t][32]
+    const int b = threadIdx.x, ny = blockDim.y, tid = threadIdx.y * 32 + threadIdx.x;
+    for (int d = tid; d < t; d += 32 * ny) sy[d] = val[o + d];
+    for (int i = tid; i < t * 8; i += 32 * ny) {                      // 4 weight bytes per thread and trip
+        const int d = i >> 3, q = i & 7;
+        reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + d] * NBC)[q];
+    }
+    __syncthreads();
     double T = 0, Y1 = 0, Y2 = 0, Ys = 0, RR1 = 0, RR2 = 0, RY = 0;
     for (int c = threadIdx.y; c < t; c += ny) {
-        const double yc = val[o + c];
+        const double yc = sy[c];
         double r = 0.0;
-        for (int d = 0; d < t; ++d) r = fma(wT[(long long)col[o + d] * NBC + b], fabs(yc - val[o + d]), r);
+#pragma unroll 4
+        for (int d = 0; d < t; ++d) r = fma((double)sw[d * NBC + b], fabs(yc - sy[d]), r);
         rT[(o + c) * NBC + b] = r;
-        const double w = wT[(long long)col[o + c] * NBC + b], ay = fabs(yc);
+        const double w = (double)sw[c * NBC + b], ay = fabs(yc);
         T += w;
         Y1 = fma(w, ay, Y1);
         Y2 = fma(w * yc, yc, Y2);
@@ -227,95 +262,70 @@ __global__ void genome_rowsums_kernel(const long long* __restrict__ ptr, const i
     __syncthreads();
     if (threadIdx.y == 0) {
         for (int i = 0; i < VAGG; ++i) {
-            double s = 0.0;
-            for (int y = 0; y < ny; ++y) s += red[y][i][b];
-            vagg[(v * VAGG + i) * NBC + b] = s;
+            double sm = 0.0;
+            for (int y = 0; y < ny; ++y) sm += red[y][i][b];
+            vagg[(v * VAGG + i) * NBC + b] = sm;
         }
     }
 }
 
-// VG: one warp per (genome, GOM); lane = replicate.
-// out[b][v][g].  grid = ceil(n*G / warps_per_block)
-__global__ void __launch_bounds__(128)
-gom_score_kernel(long long n, int G, long long p, const long long* __restrict__ ptr,
-                 const int* __restrict__ col, const double* __restrict__ val,
-                 const int* __restrict__ pt_ptr, const int* __restrict__ pos,
-                 const double* __restrict__ nrm, const long long* __restrict__ a_off,
-                 const double* __restrict__ A, const double* __restrict__ wT,
-                 const double* __restrict__ arT, const double* __restrict__ rT,
-                 const double* __restrict__ gagg, const double* __restrict__ vagg, int nb,
-                 double* __restrict__ out, int* __restrict__ ilist, long long ilist_stride,
-                 long long w_base, long long w_end) {
-    const int lane = threadIdx.x & 31;
-    const long long wrel = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long wid = w_base + wrel;
-    if (wid >= w_end) return;
-    // GOM-major order keeps one GOM's distance cache hot in L2 while all genomes are scored
-    const int g = (int)(wid / n);
-    const long long v = wid % n;
-    const long long o = ptr[v];
-    const int t = (int)(ptr[v + 1] - o);
-    const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
-    const int* posg = pos + (long long)g * p;
-    const double* Ag = A + a_off[g];
+// VG: score (genome, GOM) pairs; lane = replicate.  out[b][v][g].
+// The intersection list I0 = R_v & R_g (replicate independent) is staged in shared memory: y, |X| norm, GOM
+// point index, genome hit index and the 32 uint8 weights of each entry (56 bytes), so that the |I|^2 pair
+// loop reads shared memory plus one L2-resident distance-cache entry per iteration.
+//   light kernel: one WARP per pair, room for VG_LIGHT_CAP entries (the handful of PPHMMs a genome shares with
+//                 a foreign taxon) -> full occupancy; longer lists are appended to a work list instead;
+//   heavy kernel: one BLOCK per listed pair (a genome against its own taxon: |I| ~ all of its hits), the four
+//                 warps split the outer loop of the pair sums and reduce through shared memory.
+#define VG_ENTRY_BYTES 56
+#define VG_LIGHT_CAP 64
+#define VG_NSUM 12
 
-    // intersection list I0 = R_v & R_g (replicate independent): entries (hit index, point index)
-    int* il = ilist + wrel * ilist_stride;   // [2 * t] scratch in global memory
-    int ni = 0;
-    for (int c0 = 0; c0 < t; c0 += 32) {
-        const int c = c0 + lane;
-        int k = -1;
-        if (c < t) k = posg[col[o + c]];
-        const unsigned m = __ballot_sync(0xffffffffu, k >= 0);
-        if (k >= 0) {
-            const int w = ni + __popc(m & ((1u << lane) - 1u));
-            il[2 * w] = c;
-            il[2 * w + 1] = k;
-        }
-        ni += __popc(m);
-    }
-    __syncwarp();
+struct VgSums { double v[VG_NSUM]; };   // SW S_ar S_nrm S_r S_y C_arr C_ary C_nr C_ny Q1 Q2 Q3
 
-    const int b = lane;
-    double SW = 0, S_ar = 0, S_nrm = 0, S_r = 0, S_y = 0, C_arr = 0, C_ary = 0, C_nr = 0, C_ny = 0;
-    double Q1 = 0, Q2 = 0, Q3 = 0;
-    for (int a = 0; a < ni; ++a) {
-        const int c = il[2 * a], k = il[2 * a + 1];
-        const double yc = val[o + c], ayc = fabs(yc);
-        const double wc = wT[(long long)col[o + c] * NBC + b];
+__device__ __forceinline__ void vg_accumulate(int a_begin, int a_step, int ni, int b, const double* __restrict__ sy,
+                                              const double* __restrict__ sn, const int* __restrict__ sk,
+                                              const int* __restrict__ sc, const unsigned char* __restrict__ sw,
+                                              const double* __restrict__ Ag, int ng, int p0, long long o,
+                                              const double* __restrict__ arT, const double* __restrict__ rT, VgSums& S) {
+    for (int a = a_begin; a < ni; a += a_step) {
+        const int k = sk[a];
+        const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
+        const double wc = (double)sw[a * NBC + b];
         const double ar = arT[(long long)(p0 + k) * NBC + b];
-        const double nr = nrm[p0 + k];
-        const double r = rT[(o + c) * NBC + b];
-        SW += wc;
-        S_ar = fma(wc, ar, S_ar);
-        S_nrm = fma(wc, nr, S_nrm);
-        S_r = fma(wc, r, S_r);
-        S_y = fma(wc, ayc, S_y);
-        C_arr = fma(wc * ar, r, C_arr);
-        C_ary = fma(wc * ar, ayc, C_ary);
-        C_nr = fma(wc * nr, r, C_nr);
-        C_ny = fma(wc * nr, ayc, C_ny);
+        const double r = rT[(o + sc[a]) * NBC + b];
+        S.v[0] += wc;
+        S.v[1] = fma(wc, ar, S.v[1]);
+        S.v[2] = fma(wc, nr, S.v[2]);
+        S.v[3] = fma(wc, r, S.v[3]);
+        S.v[4] = fma(wc, ayc, S.v[4]);
+        S.v[5] = fma(wc * ar, r, S.v[5]);
+        S.v[6] = fma(wc * ar, ayc, S.v[6]);
+        S.v[7] = fma(wc * nr, r, S.v[7]);
+        S.v[8] = fma(wc * nr, ayc, S.v[8]);
         const double* arow = Ag + (long long)k * ng;
         double q1 = 0, q2 = 0, q3 = 0;
+#pragma unroll 8
         for (int e = 0; e < a; ++e) {           // unordered pairs e < a, doubled below
-            const int d = il[2 * e], l = il[2 * e + 1];
-            const double yd = val[o + d];
-            const double wd = wT[(long long)col[o + d] * NBC + b];
-            const double dist = arow[l];
+            const double yd = sy[e];
+            const double wd = (double)sw[e * NBC + b];
+            const double dist = arow[sk[e]];
             const double dy = fabs(yc - yd);
             q1 = fma(wd * dist, dy, q1);
             q2 = fma(wd * dist, ayc + fabs(yd), q2);
-            q3 = fma(wd * (nr + nrm[p0 + l]), dy, q3);
+            q3 = fma(wd * (nr + sn[e]), dy, q3);
         }
-        Q1 = fma(2.0 * wc, q1, Q1);
-        Q2 = fma(wc, q2, Q2);
-        Q3 = fma(wc, q3, Q3);
+        S.v[9] = fma(2.0 * wc, q1, S.v[9]);
+        S.v[10] = fma(wc, q2, S.v[10]);
+        S.v[11] = fma(wc, q3, S.v[11]);
     }
-    if (b >= nb) return;
-    const double* ga = gagg + (long long)g * GAGG * NBC + b;
+}
+
+__device__ __forceinline__ double vg_finish(const VgSums& S, const double* __restrict__ ga, const double* __restrict__ va) {
+    const double SW = S.v[0], S_ar = S.v[1], S_nrm = S.v[2], S_r = S.v[3], S_y = S.v[4], C_arr = S.v[5], C_ary = S.v[6],
+                 C_nr = S.v[7], C_ny = S.v[8], Q1 = S.v[9], Q2 = S.v[10], Q3 = S.v[11];
     const double n_g = ga[0], N1 = ga[NBC], N2 = ga[2 * NBC], AR1 = ga[3 * NBC], AR2 = ga[4 * NBC],
                  ARN = ga[5 * NBC], SAA = ga[6 * NBC];
-    const double* va = vagg + v * VAGG * NBC + b;
     const double T = va[0], Y1 = va[NBC], Y2 = va[2 * NBC], Ys = va[3 * NBC], RR1 = va[4 * NBC],
                  RR2 = va[5 * NBC], RY = va[6 * NBC];
     const double e = T - SW, z = n_g - SW, nn = n_g + e;
@@ -339,7 +349,133 @@ gom_score_kernel(long long n, int G, long long p, const long long* __restrict__ 
         const double dvB = sqrt(sBB / (nn * nn));
         if (dvA > 0.0 && dvB > 0.0) res = dcov / sqrt(dvA * dvB);
     }
-    out[((long long)b * n + v) * G + g] = res;
+    return res;
+}
+
+// scan the genome's hits against the GOM's column set (one warp, column order preserved); entries beyond
+// `cap` are counted but not stored
+__device__ __forceinline__ int vg_scan(int lane, int t, long long o, const int* __restrict__ col,
+                                       const double* __restrict__ val, const int* __restrict__ posg,
+                                       const double* __restrict__ nrm, int p0, int cap, double* sy, double* sn, int* sk, int* sc) {
+    int ni = 0;
+    for (int c0 = 0; c0 < t; c0 += 32) {
+        const int c = c0 + lane;
+        int k = -1;
+        if (c < t) k = posg[col[o + c]];
+        const unsigned m = __ballot_sync(0xffffffffu, k >= 0);
+        if (k >= 0) {
+            const int w = ni + __popc(m & ((1u << lane) - 1u));
+            if (w < cap) {
+                sy[w] = val[o + c];
+                sn[w] = nrm[p0 + k];
+                sk[w] = k;
+                sc[w] = c;
+            }
+        }
+        ni += __popc(m);
+    }
+    return ni;
+}
+
+__global__ void __launch_bounds__(128)
+gom_score_light_kernel(long long n, int G, long long p, const long long* __restrict__ ptr,
+                       const int* __restrict__ col, const double* __restrict__ val,
+                       const int* __restrict__ pt_ptr, const int* __restrict__ pos,
+                       const double* __restrict__ nrm, const long long* __restrict__ a_off,
+                       const double* __restrict__ A, const unsigned char* __restrict__ wT8,
+                       const double* __restrict__ arT, const double* __restrict__ rT,
+                       const double* __restrict__ gagg, const double* __restrict__ vagg, int nb,
+                       double* __restrict__ out, long long* __restrict__ heavy_list, int* __restrict__ heavy_count) {
+    __shared__ __align__(16) unsigned char smem[4 * VG_LIGHT_CAP * VG_ENTRY_BYTES];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long wid = (long long)blockIdx.x * 4 + wib;
+    if (wid >= n * G) return;
+    // GOM-major order keeps one GOM's distance cache hot in L2 while all genomes are scored
+    const int g = (int)(wid / n);
+    const long long v = wid % n;
+    const long long o = ptr[v];
+    const int t = (int)(ptr[v + 1] - o);
+    const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
+    unsigned char* base = smem + wib * VG_LIGHT_CAP * VG_ENTRY_BYTES;
+    double* sy = reinterpret_cast<double*>(base);
+    double* sn = sy + VG_LIGHT_CAP;
+    int* sk = reinterpret_cast<int*>(sn + VG_LIGHT_CAP);
+    int* sc = sk + VG_LIGHT_CAP;
+    unsigned char* sw = reinterpret_cast<unsigned char*>(sc + VG_LIGHT_CAP);
+    const int ni = vg_scan(lane, t, o, col, val, pos + (long long)g * p, nrm, p0, VG_LIGHT_CAP, sy, sn, sk, sc);
+    if (ni > VG_LIGHT_CAP) {
+        if (lane == 0) heavy_list[atomicAdd(heavy_count, 1)] = wid;
+        return;
+    }
+    __syncwarp();
+    for (int i = lane; i < ni * 8; i += 32)                             // weights: 4 bytes per lane and trip
+        reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + sc[i >> 3]] * NBC)[i & 7];
+    __syncwarp();
+    VgSums S;
+#pragma unroll
+    for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
+    vg_accumulate(0, 1, ni, lane, sy, sn, sk, sc, sw, A + a_off[g], ng, p0, o, arT, rT, S);
+    if (lane < nb)
+        out[((long long)lane * n + v) * G + g] = vg_finish(S, gagg + (long long)g * GAGG * NBC + lane, vagg + v * VAGG * NBC + lane);
+}
+
+// persistent blocks over the heavy list; dynamic shared memory: cap * 56 bytes + reduction scratch
+__global__ void __launch_bounds__(128)
+gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long long* __restrict__ ptr,
+                       const int* __restrict__ col, const double* __restrict__ val,
+                       const int* __restrict__ pt_ptr, const int* __restrict__ pos,
+                       const double* __restrict__ nrm, const long long* __restrict__ a_off,
+                       const double* __restrict__ A, const unsigned char* __restrict__ wT8,
+                       const double* __restrict__ arT, const double* __restrict__ rT,
+                       const double* __restrict__ gagg, const double* __restrict__ vagg, int nb,
+                       double* __restrict__ out, const long long* __restrict__ heavy_list,
+                       const int* __restrict__ heavy_count) {
+    extern __shared__ __align__(16) unsigned char vg_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int cap = (max_t + 1) & ~1;
+    double* sy = reinterpret_cast<double*>(vg_smem);
+    double* sn = sy + cap;
+    int* sk = reinterpret_cast<int*>(sn + cap);
+    int* sc = sk + cap;
+    unsigned char* sw = reinterpret_cast<unsigned char*>(sc + cap);
+    double* red = reinterpret_cast<double*>(vg_smem + (size_t)cap * VG_ENTRY_BYTES);   // [3][VG_NSUM][32]
+    __shared__ int s_ni;
+    const int total = *heavy_count;
+    for (int it = blockIdx.x; it < total; it += gridDim.x) {
+        const long long wid = heavy_list[it];
+        const int g = (int)(wid / n);
+        const long long v = wid % n;
+        const long long o = ptr[v];
+        const int t = (int)(ptr[v + 1] - o);
+        const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
+        __syncthreads();                                                // previous pair fully consumed
+        if (wib == 0) {
+            const int ni = vg_scan(lane, t, o, col, val, pos + (long long)g * p, nrm, p0, cap, sy, sn, sk, sc);
+            if (lane == 0) s_ni = ni;
+        }
+        __syncthreads();
+        const int ni = s_ni;
+        for (int i = threadIdx.x; i < ni * 8; i += 128)
+            reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + sc[i >> 3]] * NBC)[i & 7];
+        __syncthreads();
+        VgSums S;
+#pragma unroll
+        for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
+        // outer index a costs ~a inner trips: warps take a = 4j + (wib ^ (j & 3)) so that all four finish together
+        vg_accumulate(wib, 4, ni, lane, sy, sn, sk, sc, sw, A + a_off[g], ng, p0, o, arT, rT, S);
+        if (wib > 0) {
+#pragma unroll
+            for (int i = 0; i < VG_NSUM; ++i) red[((wib - 1) * VG_NSUM + i) * 32 + lane] = S.v[i];
+        }
+        __syncthreads();
+        if (wib == 0) {
+#pragma unroll
+            for (int i = 0; i < VG_NSUM; ++i)
+                S.v[i] += red[(0 * VG_NSUM + i) * 32 + lane] + red[(1 * VG_NSUM + i) * 32 + lane] + red[(2 * VG_NSUM + i) * 32 + lane];
+            if (lane < nb)
+                out[((long long)lane * n + v) * G + g] = vg_finish(S, gagg + (long long)g * GAGG * NBC + lane, vagg + v * VAGG * NBC + lane);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -364,7 +500,7 @@ void gom_db_free(GomDb* db) {
     cudaFree(db->mem_ptr); cudaFree(db->mem_row); cudaFree(db->pt_ptr); cudaFree(db->pt_col);
     cudaFree(db->pos); cudaFree(db->x_off); cudaFree(db->a_off); cudaFree(db->X); cudaFree(db->nrm);
     cudaFree(db->A); cudaFree(db->wT); cudaFree(db->arT); cudaFree(db->sqT); cudaFree(db->rT);
-    cudaFree(db->gagg); cudaFree(db->vagg); cudaFree(db->ilist);
+    cudaFree(db->gagg); cudaFree(db->vagg); cudaFree(db->wT8); cudaFree(db->wG); cudaFree(db->flag); cudaFree(db->heavy_list);
     delete db;
 }
 
@@ -486,12 +622,22 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
         for (int64_t v = 0; v < n; ++v) max_t = std::max<int>(max_t, (int)(ptr_h[v + 1] - ptr_h[v]));
     }
     db->max_t = max_t;
-    db->ilist_stride = 2LL * max_t;
-    // scored in waves of `wave` (genome, GOM) warps so that the scratch stays bounded
-    long long total_w = n * G;
-    long long cap = (long long)(1ULL << 30) / (sizeof(int) * (db->ilist_stride ? db->ilist_stride : 1));
-    db->wave = std::max<long long>(128, std::min<long long>(total_w, cap));
-    CK(dalloc(&db->ilist, (size_t)db->wave * db->ilist_stride, &db->bytes));
+    CK(dalloc(&db->wT8, p * NBC, &db->bytes));
+    CK(dalloc(&db->wG, (size_t)db->npt * NBC, &db->bytes));
+    CK(dalloc(&db->flag, 2, &db->bytes));          // [0] weight overflow, [1] heavy-list length
+    CK(cudaMemsetAsync(db->flag, 0, 2 * sizeof(int), st));
+    // shared-memory staging of the scoring kernels: 56 bytes per genome hit and warp
+    CK(dalloc(&db->heavy_list, (size_t)std::max<long long>(1, n * G), &db->bytes));
+    const size_t vg_smem = (size_t)((max_t + 1) & ~1) * VG_ENTRY_BYTES + 3 * VG_NSUM * 32 * sizeof(double);
+    const size_t va_smem = (size_t)((max_t + 1) & ~1) * 8 + (size_t)max_t * NBC + 16;
+    if (vg_smem > 200 * 1024 || va_smem > 200 * 1024) {
+        gom_db_free(db);
+        return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a genome has %d location hits; the GOM scoring kernels stage at most %d per genome "
+                        "in shared memory", max_t, (int)(190 * 1024 / VG_ENTRY_BYTES));
+    }
+    db->vg_smem = vg_smem; db->va_smem = va_smem;
+    CK(cudaFuncSetAttribute(gom_score_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(vg_smem, 1024)));
+    CK(cudaFuncSetAttribute(genome_rowsums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(va_smem, 1024)));
     CK(cudaStreamSynchronize(st));
     cudaFree(flag); cudaFree(scan);
     CK(cudaGetLastError());
@@ -508,31 +654,42 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
         const int cb = (int)std::min<int64_t>(NBC, nb - b0);
         if (p) {
             weights_transpose_kernel<<<(unsigned)((p * NBC + 255) / 256), 256, 0, st>>>(
-                weights ? weights + b0 * p : nullptr, p, cb, db->wT);
+                weights ? weights + b0 * p : nullptr, p, cb, db->wT, db->wT8, db->flag);
             ctx->launches++;
         }
         if (db->max_ng) {
-            dim3 g1((unsigned)((db->max_ng + 7) / 8), (unsigned)G), b1(32, 8);
-            gom_rowsums_kernel<<<g1, b1, 0, st>>>(db->pt_ptr, db->pt_col, db->a_off, db->A, db->wT, db->arT, db->sqT);
+            gom_gather_weights_kernel<<<(unsigned)(((long long)db->npt * NBC + 255) / 256), 256, 0, st>>>(db->pt_col, db->npt, db->wT, db->wG);
+            ctx->launches++;
+            dim3 g1((unsigned)((db->max_ng + 31) / 32), (unsigned)G), b1(32, 8);
+            gom_rowsums_kernel<<<g1, b1, 0, st>>>(db->pt_ptr, db->a_off, db->A, db->wG, db->arT, db->sqT);
             ctx->launches++;
         }
         gom_aggregates_kernel<<<(unsigned)G, 32, 0, st>>>(db->pt_ptr, db->pt_col, db->nrm, db->wT, db->arT, db->sqT, db->gagg);
         ctx->launches++;
         dim3 bv(32, 8);
-        genome_rowsums_kernel<<<(unsigned)n, bv, 0, st>>>(db->g_ptr, db->g_col, db->g_val, db->wT, db->rT, db->vagg);
+        genome_rowsums_kernel<<<(unsigned)n, bv, db->va_smem, st>>>(db->g_ptr, db->g_col, db->g_val, db->wT8, db->rT, db->vagg);
         ctx->launches++;
-        // score in waves; a wave covers a contiguous range of the GOM-major (g, v) index
-        const long long total_w = n * G;
-        for (long long w0 = 0; w0 < total_w; w0 += db->wave) {
-            const long long wn = std::min<long long>(db->wave, total_w - w0);
-            gom_score_kernel<<<(unsigned)((wn + 3) / 4), 128, 0, st>>>(
-                n, (int)G, p, db->g_ptr, db->g_col, db->g_val, db->pt_ptr, db->pos, db->nrm, db->a_off,
-                db->A, db->wT, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G,
-                db->ilist, db->ilist_stride, w0, w0 + wn);
+        {
+            const long long total_w = n * G;
+            cudaMemsetAsync(db->flag + 1, 0, sizeof(int), st);          // heavy-list counter
+            gom_score_light_kernel<<<(unsigned)((total_w + 3) / 4), 128, 0, st>>>(
+                n, (int)G, p, db->g_ptr, db->g_col, db->g_val, db->pt_ptr, db->pos, db->nrm, db->a_off, db->A,
+                db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G, db->heavy_list, db->flag + 1);
+            ctx->launches++;
+            gom_score_heavy_kernel<<<(unsigned)(ctx->sm_count * 8), 128, db->vg_smem, st>>>(
+                n, (int)G, p, db->max_t, db->g_ptr, db->g_col, db->g_val, db->pt_ptr, db->pos, db->nrm, db->a_off, db->A,
+                db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G, db->heavy_list, db->flag + 1);
             ctx->launches++;
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "gom_db_score: %s", cudaGetErrorString(e));
+    }
+    if (weights) {      // multiplicities are staged as uint8 in shared memory: refuse anything above 255
+        int flag = 0;
+        cudaError_t e = cudaMemcpyAsync(&flag, db->flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "gom_db_score: %s", cudaGetErrorString(e));
+        if (flag) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a column multiplicity exceeds 255 (uint8 weights of the GOM kernels)");
     }
     return GV2_OK;
 }
