@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--config", default=os.environ.get("GV2_BENCH_CONFIG", "cfg2"))
+    ap.add_argument("--config", default=os.environ.get("GV2_BENCH_CONFIG", "cfg3"))
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--boot", type=int, default=None, help="override the number of bootstrap replicates")
     ap.add_argument("--seed", type=int, default=20241019)
@@ -222,9 +222,10 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gravity2_b200 import _lib, gom_membership
+    from gravity2_b200 import _lib, gom_membership, sharding
 
-    steps = args.steps if args.steps is not None else 5
+    big = cfg["n"] * cfg["n"] * (1 + cfg["b"]) > 2e10          # cfg3-sized jobs: a step takes seconds
+    steps = args.steps if args.steps is not None else (3 if big else 5)
     warmup = args.warmup if args.warmup is not None else 3
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -253,15 +254,14 @@ def main():
     gor_p = gor.ctypes.data_as(C.c_void_p)
     ck(lib.gv2_job_create(ctx, C.c_void_p(d_sig.data_ptr()), C.c_void_p(d_sig.data_ptr()), 1, n, p, gor_p, n, g,
                           _lib.SCHEMES["PG"], 1.0, _lib.OUT_DISTANCE, C.byref(job)))
-    my_reps = list(range(rank, B, world))
+    my_reps = sharding.replicate_indices(B, rank, world)
     d_w = torch.from_numpy(np.ascontiguousarray(weights[my_reps])).cuda() if my_reps else None
     ntiles = int(lib.gv2_num_tiles(n))
-    per = (ntiles + world - 1) // world
-    t0_, t1_ = min(ntiles, rank * per), min(ntiles, (rank + 1) * per)
+    per = sharding.tiles_per_rank(ntiles, world)
+    t0_, t1_ = sharding.tile_range(ntiles, rank, world)
     tile_elems = _lib.TILE * _lib.TILE
     d_base = torch.empty((n, n), dtype=torch.float64, device="cuda")
     d_pack = torch.zeros((per, tile_elems), dtype=torch.float64, device="cuda") if world > 1 else None
-    d_gath = torch.empty((world * per, tile_elems), dtype=torch.float64, device="cuda") if world > 1 else None
     # replicate output ring: as many replicates as fit in ~8 GB
     ring = max(1, min(len(my_reps) or 1, int((8 << 30) // (n * n * 8))))
     d_out = torch.empty((ring, n, n), dtype=torch.float64, device="cuda")
@@ -269,9 +269,9 @@ def main():
     def step():
         if world > 1:
             ck(lib.gv2_job_base(job, t0_, t1_, 1, C.c_void_p(d_pack.data_ptr())))
-            dist.all_gather_into_tensor(d_gath, d_pack)
+            d_gath = sharding.all_gather_tiles(d_pack, world)
             for r in range(world):
-                a, b = min(ntiles, r * per), min(ntiles, (r + 1) * per)
+                a, b = sharding.tile_range(ntiles, r, world)
                 if b > a:
                     ck(lib.gv2_dev_unpack_tiles(ctx, n, a, b, C.c_void_p(d_gath[r * per].data_ptr()), C.c_void_p(d_base.data_ptr())))
         else:
@@ -295,6 +295,7 @@ def main():
     l0 = int(lib.gv2_launch_count(ctx))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    lib.gv2_timing_enable(ctx, 1)           # CUDA events around every launch of the dominant kernel, same stream
     e0.record(stream)
     for _ in range(steps):
         step()
@@ -302,6 +303,9 @@ def main():
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = int(lib.gv2_launch_count(ctx)) - l0
+    k_ms, k_n = C.c_double(0.0), C.c_int64(0)
+    ck(lib.gv2_timing_read(ctx, C.byref(k_ms), C.byref(k_n)))
+    lib.gv2_timing_enable(ctx, 0)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -318,7 +322,7 @@ def main():
     e2e = None
     peaks, peak_kind = load_peaks()
     if rank == 0:
-        roofline = measure_roofline(lib, ctx, ck, job, cfg, n, p, d_w, d_out, ring, stream, peaks, peak_kind, torch)
+        roofline = make_roofline(k_ms.value, k_n.value, steps, n, p, len(my_reps), ms, peaks, peak_kind)
     # ---- end to end through the host-pointer C ABI
     if not args.no_e2e:
         e2e = measure_e2e(lib, ctx, ck, t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist if world > 1 else None, torch,
@@ -327,7 +331,8 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32 min / f32 slab sums promoted to f64 (GOM dCor in f64)", "data": "synthetic",
+                "dtype": "u32 fixed-point min -> u8 digit planes x u8 multiplicities -> int32 (exact), f64 epilogue; GOM dCor f64; base matrix f32 min / f64 slab sums",
+                "data": "synthetic",
                 "config": workload_config(args, cfg, world), "clocks": clocks, "gpu_launches": launches,
                 "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
@@ -335,51 +340,30 @@ def main():
         dist.destroy_process_group()
 
 
-def measure_roofline(lib, ctx, ck, job, cfg, n, p, d_w, d_out, ring, stream, peaks, peak_kind, torch):
-    """The dominant kernel of the step is the weighted PPHMM Jaccard reduction of the replicates.
-    It is FP32/ALU-pipe bound, not HBM bound: issue slots = 2 per (pair, column, replicate)
-    cell (FMNMX + FFMA) -> peak = 148 SM x 128 lanes x sm_max_mhz / 2 cells/s.  Reported as TFLOP/s
-    with 2 "flops" per cell so that bound == "tensor"-style compute; achieved HBM GB/s is in `hbm`."""
-    from gravity2_b200 import _lib
-    if d_w is None:
+def make_roofline(kernel_ms, kernel_launches, steps, n, p, nrep, region_ms, peaks, peak_kind):
+    """Dominant kernel = boot_mma_kernel (tcgen05.mma.kind::i8): pairs x replicates x columns contraction of the
+    four uint8 digit planes of min(x_i, x_j) with the uint8 multiplicities.  Its durations are CUDA-event times
+    taken inside the timed region on the launching stream (gv2_timing_*).
+      algorithmic ops per launch = pairs * P * replicates * 4 planes * 2 (multiply + add)      [DESIGN.md section 4]
+      peak = 2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 tensor throughput on sm_100a is twice
+             bf16; the driver measures bf16 only) -- the sustained figure, since the kernel runs inside a long step
+    """
+    if kernel_launches == 0 or kernel_ms <= 0:
         return None
-    n_pad = (n + 127) // 128 * 128
-    p_pad = (p + 31) // 32 * 32
-    cb = min(ring, d_w.shape[0])
-    job_only_p = C.c_void_p()
-    # time gv2_job_replicates of a P-only job: weights->float, row sums, the tile kernel, epilogue;
-    # the tile kernel's own time is taken from its share in the committed ncu launch list.
-    ntiles = int(lib.gv2_num_tiles(n))
-    wf = torch.empty((cb, p_pad), dtype=torch.float32, device="cuda")
-    ws = torch.empty((cb, ntiles, 128 * 128), dtype=torch.float64, device="cuda")
-    tab = torch.zeros((n_pad, p_pad), dtype=torch.float32, device="cuda")
-    ck(lib.gv2_dev_weights_to_float(ctx, C.c_void_p(d_w.data_ptr()), cb, p, p_pad, C.c_void_p(wf.data_ptr())))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
-    for _ in range(2):
-        ck(lib.gv2_dev_gj_min_sums(ctx, C.c_void_p(tab.data_ptr()), n_pad, p_pad, 0, ntiles, C.c_void_p(wf.data_ptr()), cb, 1,
-                                   C.c_void_p(ws.data_ptr())))
-    torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(reps):
-        ck(lib.gv2_dev_gj_min_sums(ctx, C.c_void_p(tab.data_ptr()), n_pad, p_pad, 0, ntiles, C.c_void_p(wf.data_ptr()), cb, 1,
-                                   C.c_void_p(ws.data_ptr())))
-    e1.record(stream)
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3 / reps
-    cells = float(ntiles) * 128 * 128 * p_pad * cb          # cells the launch really processes (full tiles)
-    algo_cells = float(n * (n + 1) // 2) * p * cb            # algorithmic cells (upper triangle, true P)
-    sm_mhz = peaks.get("sm_max_mhz", 1965.0)
-    peak_cells = 148 * 128 * sm_mhz * 1e6 / 2.0
-    algo_bytes = cb * (n_pad * p_pad * 4.0 + ntiles * 128 * 128 * 8.0)
-    return {"kernel": "gj_min_tile_kernel<true> (weighted min-plus tile reduction)", "bound": "tensor",
-            "achieved": 2 * algo_cells / sec / 1e12, "peak": 2 * peak_cells / 1e12, "unit": "TFLOP/s",
-            "frac": algo_cells / sec / peak_cells, "traffic": None,
-            "note": "bound is the FP32/ALU issue pipe (2 instr per cell: FMNMX+FFMA; peak = 148*128*sm_max_mhz/2 cells/s), "
-                    "not HBM and not the tensor pipe; 'TFLOP/s' counts 2 ops per (pair,column,replicate) cell",
-            "launch_ms": sec * 1e3, "replicates_per_launch": cb, "cells_processed_incl_padding": cells,
-            "hbm": {"achieved": algo_bytes / sec / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                    "frac": algo_bytes / sec / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_kind": peak_kind}}
+    pairs = n * (n + 1) // 2
+    ops_per_step = float(pairs) * p * nrep * 4 * 2
+    sec_per_step = kernel_ms * 1e-3 / steps
+    bf16 = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0))
+    peak = 2.0 * bf16
+    achieved = ops_per_step / sec_per_step / 1e12
+    return {"kernel": "boot_mma_kernel (tcgen05.mma kind::i8, 4 uint8 digit planes, TMA-fed multiplicities, TMEM int32 accumulators)",
+            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_kind": f"{peak_kind}: 2 x bf16_tflops_sustained ({bf16}) = dense int8 TOP/s",
+            "launches_per_step": kernel_launches / steps, "avg_launch_ms": kernel_ms / kernel_launches,
+            "share_of_step": kernel_ms / region_ms,
+            "note": "ops are int8 multiply-adds counted as 2 ops ('TFLOP/s' = TOP/s); the kernel is bound by the SM's shared-memory "
+                    "data pipe shared by the operand reads of UTCIMMA and the producers' LDS/STS (DESIGN.md section 4), not by HBM: "
+                    "tables and multiplicities are L2-resident"}
 
 
 def measure_e2e(lib, ctx, ck, t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist, torch, steps):

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "gv2_last_error": (C.c_char_p, [c_vp]),
     "gv2_synchronize": (C.c_int, [c_vp]),
     "gv2_launch_count": (C.c_uint64, [c_vp]),
+    "gv2_timing_enable": (C.c_int, [c_vp, C.c_int]),
+    "gv2_timing_read": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(c_i64)]),
     "gv2_similarity_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, c_vp]),
     "gv2_gom_table_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,

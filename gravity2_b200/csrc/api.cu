@@ -97,6 +97,29 @@ extern "C" int gv2_synchronize(gv2_ctx* ctx) {
 
 extern "C" uint64_t gv2_launch_count(const gv2_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int gv2_timing_enable(gv2_ctx* ctx, int on) {
+    if (!ctx) return GV2_ERR_ARG;
+    ctx->timing = on != 0;
+    return GV2_OK;
+}
+
+extern "C" int gv2_timing_read(gv2_ctx* ctx, double* total_ms, int64_t* launches) {
+    if (!ctx || !total_ms || !launches) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_timing_read: bad arguments");
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double t = 0.0;
+    for (auto& pr : ctx->timed) {
+        float ms = 0.f;
+        GV2_CUDA(ctx, cudaEventElapsedTime(&ms, pr.first, pr.second));
+        t += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    *total_ms = t;
+    *launches = (int64_t)ctx->timed.size();
+    ctx->timed.clear();
+    return GV2_OK;
+}
+
 // ---------------------------------------------------------- memory helpers for hosts without a CUDA binding
 extern "C" int gv2_dev_alloc(gv2_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_alloc: bad arguments");

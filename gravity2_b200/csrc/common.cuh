@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/gravity2_b200.h"
 
@@ -15,6 +17,9 @@ struct gv2_ctx {
     bool own_stream = false;
     std::string err;
     unsigned long long launches = 0;   // kernels launched through this context (bench: gpu_launches)
+    // optional CUDA-event timing of the dominant kernel (gv2_timing_enable / gv2_timing_read)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
 };
 
 #define GV2_TILE 128          // genome-pair tile edge of the similarity kernels

@@ -64,6 +64,10 @@ void gv2_destroy(gv2_ctx* ctx);
 const char* gv2_last_error(const gv2_ctx* ctx); /* ctx may be NULL: last creation error */
 int gv2_synchronize(gv2_ctx* ctx);
 uint64_t gv2_launch_count(const gv2_ctx* ctx); /* kernels launched so far through ctx */
+/* CUDA-event timing of the dominant kernel (the tensor-core replicate contraction), on the context's stream:
+ * enable, run, then read the summed duration and launch count (reading synchronises and resets). */
+int gv2_timing_enable(gv2_ctx* ctx, int on);
+int gv2_timing_read(gv2_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* device / pinned-host memory for hosts without their own CUDA binding (ctypes, cgo, JNI ...) */
 int gv2_dev_alloc(gv2_ctx* ctx, size_t bytes, void** out);
