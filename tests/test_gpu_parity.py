@@ -311,3 +311,90 @@ def test_tensor_core_path_is_exact_integer_arithmetic(eng):
     t.sig[10] = t.sig[3]
     S = eng.bootstrap(t.sig, None, None, 0, w[:8], "P", 1.0, distance=False)
     assert np.all(S[:, 3, 10] == 1.0)
+
+
+def test_device_primitives_packed_tiles_roundtrip(eng):
+    """C-ABI device-pointer primitives (what the multi-GPU path uses): prepare -> min sums for two tile ranges ->
+    packed epilogue -> unpack == the one-shot host entry point."""
+    import ctypes as C
+    import torch
+    from gravity2_b200 import _lib
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    assert lib.gv2_create_on_stream(0, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.byref(ctx)) == 0
+    t = synth.make_tables(300, 777, 4, 0.2, seed=77)
+    n, p = t.sig.shape
+    n_pad, p_pad = 384, 800
+    ntl = int(lib.gv2_num_tiles(n))
+    assert ntl == 6
+    d_sig = torch.from_numpy(t.sig).cuda()
+    tab = torch.empty((n_pad, p_pad), dtype=torch.float32, device="cuda")
+    rs = torch.empty(n, dtype=torch.float64, device="cuda")
+    nanf = torch.empty(n, dtype=torch.uint8, device="cuda")
+    vp = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+    assert lib.gv2_dev_prepare_table(ctx, vp(d_sig), n, p, p, 0.0, 0, vp(tab), n_pad, p_pad, vp(rs), vp(nanf)) == 0
+    out = torch.full((n, n), -1.0, dtype=torch.float64, device="cuda")
+    for (a, b) in [(0, 4), (4, 6)]:
+        ws = torch.empty((b - a, 128 * 128), dtype=torch.float64, device="cuda")
+        packed = torch.empty((b - a, 128 * 128), dtype=torch.float64, device="cuda")
+        assert lib.gv2_dev_gj_min_sums(ctx, vp(tab), n_pad, p_pad, a, b, None, 1, 1, vp(ws)) == 0
+        comp = _lib.GjComponent(min_sums=ws.data_ptr(), rowsums=rs.data_ptr(), nanflags=nanf.data_ptr(), ksplit=1)
+        assert lib.gv2_dev_gj_epilogue(ctx, n, a, b, 1, C.byref(comp), None, None, _lib.SCHEMES["P"], 1.0,
+                                       _lib.OUT_SIMILARITY, 1, vp(packed), 0) == 0, lib.gv2_last_error(ctx)
+        assert lib.gv2_dev_unpack_tiles(ctx, n, a, b, vp(packed), vp(out)) == 0
+    torch.cuda.synchronize()
+    ref = eng.similarity(t.sig, None, None, "P", 1.0)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    lib.gv2_destroy(ctx)
+
+
+def test_error_paths(eng):
+    import gravity2_b200 as G
+    with pytest.raises(ValueError):
+        eng.similarity(np.ones((3, 4)), np.ones((2, 2)), None, "PG")
+    with pytest.raises(ValueError):
+        eng.similarity(np.ones((3, 4)), None, None, "XX")
+    with pytest.raises(G.engine.GravityNativeError):           # multiplicity > 255 is refused, never wrapped
+        w = np.zeros((8, 40), dtype=np.int32); w[:, 0] = 300
+        eng.bootstrap(np.random.default_rng(0).random((5, 40)), None, None, 0, w, "P")
+    assert G.GOMSignatureTable_Constructor(np.zeros((4, 6)), {}, [], {"N_CPUs": 1}).shape == (4, 0)
+    S = eng.similarity(np.zeros((0, 5)), None, None, "P")
+    assert S.shape == (0, 0)
+
+
+def test_full_size_properties_cfg3(eng):
+    """BASELINE config 3 size (10k genomes x 30k PPHMMs): size-independent properties + spot checks against the
+    reference expression on sampled pairs (the oracle cannot run the full matrix in seconds)."""
+    t = synth.make_tables(10000, 30000, 200, 0.01, seed=synth.SEED_BASE + 3)
+    sig = t.sig
+    sig[9001] = sig[17]                                   # duplicate genome
+    sig[9002] = 0.0                                       # empty genome
+    S = eng.similarity(sig, None, None, "P", 1.0)
+    assert S.shape == (10000, 10000) and np.array_equal(S, S.T)
+    d = np.diag(S)
+    assert d[9002] == 0.0 and np.all(np.delete(d, 9002) == 1.0)
+    assert S.min() >= 0.0 and S.max() <= 1.0 + 1e-12
+    assert abs(S[17, 9001] - 1.0) < 1e-6 and np.all(S[9002] == 0.0)
+    rng = np.random.default_rng(0)
+    for i, j in rng.integers(0, 10000, (200, 2)):
+        ref = O._gj(sig[i], sig[j])
+        assert abs(S[i, j] - ref) <= 1e-6 * abs(ref) + 1e-12
+    # tensor-core replicates at full size: all-ones multiplicities reproduce the base matrix; exact 1.0 for duplicates
+    w = np.ones((8, 30000), dtype=np.int32)
+    w[1:] = np.stack([np.bincount(rng.integers(0, 30000, 30000), minlength=30000) for _ in range(7)])
+    from gravity2_b200.engine import Job
+    job = Job(eng, sig, None, None, 0, "P", 1.0, distance=False)
+    seen = {}
+
+    def take(b, m):
+        seen[b] = (m[:64, :].copy(), float(m[17, 9001]), float(m[9002, 9002]), bool(np.array_equal(m[:300, 5000:5300], m[5000:5300, :300].T)))
+    job.for_each_replicate(w, take)
+    job.close()
+    assert sorted(seen) == list(range(8))
+    assert np.allclose(seen[0][0], S[:64], rtol=1e-6, atol=1e-12)
+    for b in range(8):
+        assert seen[b][1] == 1.0 and seen[b][2] == 0.0 and seen[b][3]
+    i, j = 3, 4711
+    ww = w[5].astype(np.float64)
+    ref = np.sum(np.minimum(sig[i], sig[j]) * ww) / np.sum(np.maximum(sig[i], sig[j]) * ww)
+    assert abs(seen[5][0][i, j] - ref) <= 1e-6 * ref + 1e-12
