@@ -20,13 +20,16 @@
 // |sum| <= 255 P << 2^31).  The planes are recombined in fp64: sum = q * sum_d 256^d * plane_d.
 // The only error is the input quantisation q/2 = max(T) * 2^-33 per element.
 //
-// CTA = 128 pairs (8 i-rows x 16 j-rows of one 128x128 genome tile) x N <= 128 replicates;
-// TMEM = 4 planes x 128 columns of int32.  One pipeline stage = 128 PPHMM columns.
-//   warps 0-7  producers: stream the 24 fixed-point table rows through a cp.async ring, form the
+// CTA = 128 pairs (8 i-rows x 16 j-rows of one 128x128 genome tile) x N <= 256 replicates x TWO digit planes;
+// TMEM = 2 planes x 256 columns of int32 (all 512).  The four planes take two launches (low half-word, then
+// high half-word, which adds 65536 x its sums to the workspace): the wider N amortises the A-operand reads of
+// the tensor core and the producers' shared-memory traffic over twice the replicates (the SM's shared-memory
+// data pipe, not the tensor pipe, is what bounds this kernel).  One pipeline stage = 128 PPHMM columns.
+//   warps 0-15 producers: stream the 24 fixed-point table rows through a cp.async ring, form the
 //              u32 min, byte-transpose into the four K-major SWIZZLE_128B digit tiles; afterwards
 //              drain TMEM (epilogue)
-//   warp  8    TMA: W tile [N rows x 128 columns] uint8, SWIZZLE_128B, one elected thread
-//   warp  9    MMA issuer: 4 planes x 4 (K=32) tcgen05.mma per stage, one elected thread
+//   warp 16    TMA: W tile [N rows x 128 columns] uint8, SWIZZLE_128B, one elected thread
+//   warp 17    MMA issuer: 2 planes x 4 (K=32) tcgen05.mma (M128 N256) per stage, one elected thread
 #include "common.cuh"
 
 #include <cuda.h>
@@ -36,16 +39,16 @@
 #define BM_PAIRS 128
 #define BM_KC 128                      // columns per pipeline stage (= one 128-byte swizzle row of uint8)
 #define BM_STAGES 2
-#define BM_PLANES 4                    // uint8 digit planes of the 32-bit fixed-point min
-#define BM_NMAX 128                    // replicates per CTA: BM_PLANES * BM_NMAX = 512 TMEM columns
+#define BM_PLANES 2                    // uint8 digit planes per pass (two passes cover the 32-bit fixed-point min)
+#define BM_NMAX 256                    // replicates per CTA: BM_PLANES * BM_NMAX = 512 TMEM columns
 #define BM_TMEM_COLS 512
 #define BM_PRODUCERS 512               // producer threads (16 warps: two pair rows per thread and stage)
 #define BM_THREADS (BM_PRODUCERS + 64)
 #define BM_RING 3                      // table-row staging ring (chunks)
 #define BM_ROWS 24                     // 8 i-rows + 16 j-rows
 #define BM_A_BYTES (BM_PAIRS * BM_KC)                // 16 KB per plane
-#define BM_W_BYTES (BM_NMAX * BM_KC)                 // 16 KB
-#define BM_STAGE_BYTES (BM_PLANES * BM_A_BYTES + BM_W_BYTES) // 80 KB
+#define BM_W_BYTES (BM_NMAX * BM_KC)                 // 32 KB
+#define BM_STAGE_BYTES (BM_PLANES * BM_A_BYTES + BM_W_BYTES) // 64 KB
 #define BM_RING_BYTES (BM_ROWS * BM_KC * 4)          // 12 KB per chunk
 #define BM_SMEM (BM_STAGES * BM_STAGE_BYTES + BM_RING * BM_RING_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 
@@ -142,22 +145,21 @@ __device__ __forceinline__ void cp16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem));
 }
 
-// 4x4 byte transpose: v[0..3] = four consecutive columns (u32 each) -> p[d] = byte d of each column,
-// column k in byte k (little endian = element order of the K-major uint8 tile).  8 PRMT.
+// byte transpose of one half-word: v0..v3 = four consecutive columns (u32 each) -> p[0] = the low bytes,
+// p[1] = the high bytes of the selected half-word (HI: bytes 2,3; else bytes 0,1), column k in byte k
+// (little endian = element order of the K-major uint8 tile).  4 PRMT.
+template <bool HI>
 __device__ __forceinline__ void byte_planes(const uint32_t v0, const uint32_t v1, const uint32_t v2, const uint32_t v3,
                                             uint32_t* p) {
-    const uint32_t t0 = __byte_perm(v0, v1, 0x5140);   // v0.b0 v1.b0 v0.b1 v1.b1
-    const uint32_t t1 = __byte_perm(v2, v3, 0x5140);
-    const uint32_t t2 = __byte_perm(v0, v1, 0x7362);   // v0.b2 v1.b2 v0.b3 v1.b3
-    const uint32_t t3 = __byte_perm(v2, v3, 0x7362);
+    const uint32_t t0 = __byte_perm(v0, v1, HI ? 0x7362 : 0x5140);   // v0.bA v1.bA v0.bB v1.bB
+    const uint32_t t1 = __byte_perm(v2, v3, HI ? 0x7362 : 0x5140);
     p[0] = __byte_perm(t0, t1, 0x5410);
     p[1] = __byte_perm(t0, t1, 0x7632);
-    p[2] = __byte_perm(t2, t3, 0x5410);
-    p[3] = __byte_perm(t2, t3, 0x7632);
 }
 
 // ---------------------------------------------------------------------------------- kernel
 // grid = (128 sub-tiles, genome tiles in [tile_begin, tile_end), replicate blocks)
+template <bool HI>
 __global__ void __launch_bounds__(BM_THREADS, 1)
 boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, long long tile_begin,
                 const __grid_constant__ CUtensorMap wmap, int nb_total, int nblk, long long ws_rep_stride,
@@ -191,7 +193,7 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) {   // TMEM: 4 digit planes x 128 int32 columns
+    if (warp == 0) {   // TMEM: 2 digit planes x 256 int32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BM_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -243,8 +245,8 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const int m = (ii0 + a) * 16 + jj0 + b;                 // pair row of the A tiles
-                    uint32_t p[4];
-                    byte_planes(min(x[a].x, y[b].x), min(x[a].y, y[b].y), min(x[a].z, y[b].z), min(x[a].w, y[b].w), p);
+                    uint32_t p[BM_PLANES];
+                    byte_planes<HI>(min(x[a].x, y[b].x), min(x[a].y, y[b].y), min(x[a].z, y[b].z), min(x[a].w, y[b].w), p);
                     // K-major SWIZZLE_128B: row m at (m/8)*1024 + (m%8)*128; columns col..col+3 are bytes col..col+3:
                     // 16-byte piece col/16 (XOR m%8), word (col/4)%4
                     uint8_t* dst = a0 + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u +
@@ -276,10 +278,14 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
                 const int rep = col0 + e;
-                // exact: each plane sum < 2^31, the combination < 2^55 only in its top 53 bits matter (<= 0.5 ulp)
-                const double sum = (double)(int)v[0][e] + 256.0 * (double)(int)v[1][e] + 65536.0 * (double)(int)v[2][e] +
-                                   16777216.0 * (double)(int)v[3][e];
-                if (rep < nrep) out[(size_t)(rep0 + rep) * ws_rep_stride] = sum * quantum;
+                // exact integers: each plane sum < 2^31; the low pass stores, the high pass adds 65536 x its sums
+                // (a second launch on the same stream: plain read-modify-write, deterministic)
+                const double sum = (double)(int)v[0][e] + 256.0 * (double)(int)v[1][e];
+                if (rep < nrep) {
+                    double* o = out + (size_t)(rep0 + rep) * ws_rep_stride;
+                    if (HI) *o += sum * 65536.0 * quantum;
+                    else *o = sum * quantum;
+                }
             }
         }
     } else if (warp == BM_PRODUCERS / 32) {
@@ -487,7 +493,8 @@ int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n
     if (r != CUDA_SUCCESS) return gv2_fail(ctx, GV2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     static bool attr_done = false;
     if (!attr_done) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
         attr_done = true;
     }
     if (ntl > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "boot_mma_launch: more than 65535 genome tiles per launch");
@@ -498,9 +505,14 @@ int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n
         GV2_CUDA(ctx, cudaEventCreate(&ev1));
         GV2_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    boot_mma_kernel<<<grid, BM_THREADS, BM_SMEM, ctx->stream>>>(tab, (int)k_pad, (int)(k_pad / BM_KC), (int)(n_pad / GV2_TILE),
-                                                                tile_begin, map, (int)nb, (int)nblk,
-                                                                (long long)ntl * GV2_TILE * GV2_TILE, quantum, ws);
+    // low half-word (digit planes 0, 1) stores, high half-word (planes 2, 3) accumulates on top
+    boot_mma_kernel<false><<<grid, BM_THREADS, BM_SMEM, ctx->stream>>>(tab, (int)k_pad, (int)(k_pad / BM_KC), (int)(n_pad / GV2_TILE),
+                                                                       tile_begin, map, (int)nb, (int)nblk,
+                                                                       (long long)ntl * GV2_TILE * GV2_TILE, quantum, ws);
+    GV2_LAUNCH_CHECK(ctx);
+    boot_mma_kernel<true><<<grid, BM_THREADS, BM_SMEM, ctx->stream>>>(tab, (int)k_pad, (int)(k_pad / BM_KC), (int)(n_pad / GV2_TILE),
+                                                                      tile_begin, map, (int)nb, (int)nblk,
+                                                                      (long long)ntl * GV2_TILE * GV2_TILE, quantum, ws);
     GV2_LAUNCH_CHECK(ctx);
     if (ctx->timing) {
         GV2_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
