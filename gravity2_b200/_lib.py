@@ -46,6 +46,7 @@ PROTOTYPES = {
     "gv2_timing_read": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(c_i64)]),
     "gv2_similarity_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, c_vp]),
+    "gv2_similarity_nbhd_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, C.c_double, C.c_double, c_vp, c_vp]),
     "gv2_gom_table_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
                                      C.c_int, c_vp]),
     "gv2_shared_counts_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),

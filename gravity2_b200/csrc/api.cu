@@ -398,9 +398,11 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
     const size_t avail = (size_t)((free_b + have) * 0.85);
     int64_t super = (int64_t)((avail > sub_bytes ? avail - sub_bytes : 0) / std::max<size_t>(1, per_rep));
     super = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(super, nb), 1024));
-    if (super >= 256) super = super / 256 * 256;            // whole 256-replicate tensor-core blocks
-    else if (super >= 128) super = super / 128 * 128;
-    else if (super >= 32) super = super / 32 * 32;
+    if (super < nb) {                                       // several super-chunks: whole tensor-core / GOM lane blocks
+        if (super >= 256) super = super / 256 * 256;
+        else if (super >= 128) super = super / 128 * 128;
+        else if (super >= 32) super = super / 32 * 32;
+    }
     if (!job->copy_stream) {
         GV2_CUDA(ctx, cudaStreamCreateWithFlags(&job->copy_stream, cudaStreamNonBlocking));
         for (int h = 0; h < 2; ++h) {

@@ -27,14 +27,13 @@ def SimilarityMat_Constructor(PPHMMSignatureTable, GOMSignatureTable, PPHMMLocat
                               SimilarityMeasurementScheme="PG", p=1.0, fnames=False, engine: Optional[Engine] = None):
     """Similarity matrix for the given scheme and p: float64 (N, N), fresh array.
 
-    ``fnames`` is accepted and ignored: the reference re-reads two CSVs from it to build
-    neighbourhood index lists that have no effect unless ``pphmm_neighbourhood_weight != 0``
-    (SURVEY quirk Q2).  With a non-zero weight the reference's result depends on how often each
-    row has been touched by the pair loop (quirk Q1); that mode is not built and raises."""
-    if pphmm_neighbourhood_weight != 0:
-        raise NotImplementedError(
-            "PphmmNeighbourhoodWeight != 0 (in-place, visit-count dependent row scaling of "
-            "similarity_matrix_constructor.py:120-140) is not implemented on the B200 path")
+    ``pphmm_neighbourhood_weight == 0`` (the default and every shipped payload): ``fnames`` is not read --
+    the reference re-reads two CSVs from it to build neighbourhood index lists that then have no effect
+    (SURVEY quirk Q2).  With a non-zero weight the lists are built from ``fnames`` exactly as the
+    reference builds them and its visit-count dependent in-place row scaling (quirk Q1) is reproduced: at
+    pair (i, j >= i) row i has been scaled j + 2 times and row j i + 1 times, and the caller's table is
+    left scaled N + 1 times, so that a following call (e.g. the next bootstrap) starts where the
+    reference's would."""
     scheme = SimilarityMeasurementScheme
     eng = engine or default_engine()
     thr = pphmm_signature_score_threshold
@@ -43,6 +42,30 @@ def SimilarityMat_Constructor(PPHMMSignatureTable, GOMSignatureTable, PPHMMLocat
         aux = SPRSignatureTable
     if "L" in scheme:
         aux = eng.location_dcor_matrix(PPHMMLocationTable)
+    if pphmm_neighbourhood_weight != 0 and "P" in scheme:
+        from . import neighbourhood as nbhd
+        if not fnames:
+            raise ValueError("PphmmNeighbourhoodWeight != 0 needs fnames['PphmmLocs'] and fnames['PphmmAndGomSigs']")
+        cls = nbhd.neighbourhood_classes(*nbhd.read_neighbourhood_csvs(fnames))
+        n = PPHMMSignatureTable.shape[0]
+        if cls.shape != PPHMMSignatureTable.shape:
+            raise IndexError(f"neighbourhood indices from the CSVs ({cls.shape}) do not fit the signature table "
+                             f"{PPHMMSignatureTable.shape}")
+        # cleaned GJ_P (times the R / L factor of PR / PL), then the ordinary combine with GJ_P in the aux slot:
+        # P -> R, PG -> RG; PR = (R * P) ** 0.5 and PL = P * L go through R with the product as aux
+        if scheme in ("PR", "PL"):
+            # L is cleaned like P (:201-205) before the product; R is taken as is
+            mul = np.asarray(aux, dtype=np.float64)
+            if scheme == "PL":
+                mul = np.where(np.isnan(mul) | (mul < 0), 0.0, mul)
+            gjp = eng.similarity_neighbourhood(PPHMMSignatureTable, cls, pphmm_neighbourhood_weight, thr, mul)
+            S = eng.similarity(None, None, gjp, "R", float(p) * (0.5 if scheme == "PR" else 1.0))
+        else:
+            gjp = eng.similarity_neighbourhood(PPHMMSignatureTable, cls, pphmm_neighbourhood_weight, thr)
+            S = eng.similarity(None, GOMSignatureTable, gjp, {"P": "R", "PG": "RG"}[scheme], float(p))
+        if isinstance(PPHMMSignatureTable, np.ndarray):
+            nbhd.apply_in_place(PPHMMSignatureTable, cls, pphmm_neighbourhood_weight, thr, n + 1)
+        return S
     S = eng.similarity(PPHMMSignatureTable, GOMSignatureTable, aux, scheme, float(p), float(thr),
                        apply_threshold=("P" in scheme), distance=False)
     if "P" in scheme and isinstance(PPHMMSignatureTable, np.ndarray):

@@ -106,6 +106,23 @@ class Engine:
         _lib.check(self.ctx, rc)
         return out
 
+    def similarity_neighbourhood(self, sig, cls, weight: float, threshold: float, mul=None) -> np.ndarray:
+        """Cleaned PPHMM generalised-Jaccard matrix of the PphmmNeighbourhoodWeight != 0 mode
+        (similarity_matrix_constructor.py:112-169 with the visit-count dependent row scaling, quirk Q1)."""
+        sig = _f64(sig, "PPHMMSignatureTable")
+        n, p = sig.shape
+        cls = np.ascontiguousarray(cls, dtype=np.uint8)
+        if cls.shape != (n, p):
+            raise ValueError("neighbourhood class table must match the signature table")
+        mul = None if mul is None else _f64(mul, "multiplier matrix")
+        if mul is not None and mul.shape != (n, n):
+            raise ValueError(f"multiplier matrix must be ({n}, {n})")
+        out = np.empty((n, n), dtype=np.float64)
+        rc = self.lib.gv2_similarity_nbhd_host(self.ctx, _ptr(sig), n, p, p, _ptr(cls), float(weight), float(threshold),
+                                               _ptr(mul), _ptr(out))
+        _lib.check(self.ctx, rc)
+        return out
+
     # --------------------------------------------------------------------- GOM table (a11-a13)
     def gom_table(self, loc, gom_rows, gom_offsets, weights=None, all_columns: bool = False) -> np.ndarray:
         loc = _f64(loc, "PPHMMLocationTable")

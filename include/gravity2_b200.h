@@ -93,6 +93,20 @@ int gv2_similarity_host(gv2_ctx* ctx, const double* sig, int64_t n, int64_t p, i
                         int scheme, double power, double threshold, int apply_threshold,
                         int out_kind, double* out);
 
+/* PphmmNeighbourhoodWeight != 0 parity mode of the same function (:112-169 with the in-place, visit-count
+ * dependent row scaling of :120-140): the cleaned (:201-205) PPHMM generalised-Jaccard
+ * matrix in which, at pair (i, j >= i), row i has been through j + 2 and row j through i + 1 applications of
+ * "negative-list entries x (1 - weight), positive-list entries x (1 + weight), then x < threshold -> 0".
+ *   cls [n][p] uint8 (dense, row stride p): bit 0 = column on the genome's negative list, bit 1 = on its
+ *       positive list (the lists of :79-110, built host-side from the two CSVs by the binding);
+ *   mul [n][n] float64 or NULL: element-wise factor applied to the cleaned matrix (SPR / location dCor
+ *       matrix of schemes PR / PL);
+ *   out [n][n] float64.  The caller combines it through gv2_similarity_host (as `spr`, schemes R / RG) and
+ *   mirrors the reference's N + 1 applications onto its own table. */
+int gv2_similarity_nbhd_host(gv2_ctx* ctx, const double* sig, int64_t n, int64_t p, int64_t ld_sig,
+                             const uint8_t* cls, double weight, double threshold, const double* mul,
+                             double* out);
+
 /* Replaces GOMSignatureTable_Constructor / generate_gom_sigs
  * (app/utils/parallel_gom_sig_generator.py:10-37, gom_signature_table_constructor.py:34-61).
  *   loc       [n][p] float64 PPHMM location table of the genomes to score

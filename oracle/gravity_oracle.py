@@ -22,7 +22,7 @@ import numpy as np
 
 __all__ = [
     "cent_dist", "dcov", "dvar", "dcor", "gomdb", "generate_gom_sigs", "gom_table",
-    "similarity_mat", "similarity_mat_fast", "gj_pair_sums", "dist_from_sim",
+    "similarity_mat", "similarity_mat_fast", "neighbourhood_index_lists", "gj_pair_sums", "dist_from_sim",
     "shared_pphmm_ratio", "shared_norm_pphmm_ratio", "binary_gj", "bootstrap_indices",
     "pl1_bootstrap_replicate", "pl2_bootstrap_replicate", "weights_from_indices",
     "weighted_gj", "weighted_dcor", "dist_mat_to_tree", "linkage_merges",
@@ -129,28 +129,90 @@ def _gj(a: np.ndarray, b: np.ndarray) -> float:
         return np.sum(np.minimum(a, b)) / mx if not mx == 0 else 0
 
 
+def neighbourhood_index_lists(loc_csv: np.ndarray, sig_csv: np.ndarray):
+    """The CSV preprocessing of SimilarityMat_Constructor,
+    app/utils/similarity_matrix_constructor.py:19-110, restated loop for loop.
+
+    ``loc_csv``: numeric block of ``fnames["PphmmLocs"]`` (``iloc[:, 1:]``, :20-22);
+    ``sig_csv``: numeric block of ``fnames["PphmmAndGomSigs"]`` (``iloc[:, 2:]``, :29-31).
+    Returns ``(neg, pos)``: dict genome row -> list of ORIGINAL column numbers whose entry is
+    multiplied by (1 - w) / (1 + w) every time the pair loop touches that row (:120-133)."""
+    import pandas as pd
+    trim = pd.DataFrame(np.asarray(loc_csv, dtype=np.float64)).replace(0, np.nan)      # :24
+    means = trim.mean().to_list()                                                      # :25
+    means_indices = np.argsort(means)                                                  # :26
+    sig_nan = np.array(pd.DataFrame(np.asarray(sig_csv, dtype=np.float64)).replace(0, np.nan))   # :32
+    all_dists = []
+    for row in sig_nan:                                                                # :35-39
+        dists = []
+        for i in range(row.shape[0]):
+            dists.append(round(np.abs(row[i] - means[i]), 4) if not row[i] == np.nan else 0)
+        all_dists.append(dists)
+    distance_arr = np.nan_to_num(np.array(all_dists).T[means_indices].T, 0)            # :41
+    neighbourhoods = {}
+    for row_idx, row in enumerate(distance_arr):                                       # :45-77 (AMP_SINGLETONS = True)
+        neighbourhood = 0
+        for prof_idx, prof in enumerate(row):
+            if prof_idx == 0:
+                continue
+            if prof != 0:
+                neighbourhood += 1
+                if prof_idx == len(row) - 1:
+                    neighbourhoods.setdefault(row_idx, {}).update(
+                        {prof_idx - neighbourhood: [neighbourhood + 1, row[prof_idx - neighbourhood:prof_idx]]})
+            else:
+                if neighbourhood == 0:
+                    continue
+                neighbourhoods.setdefault(row_idx, {}).update(
+                    {prof_idx - neighbourhood: [neighbourhood + 1, row[prof_idx - neighbourhood - 1:prof_idx]]})
+                neighbourhood = 0
+    neg_sorted, pos_sorted = {}, {}
+    for row_key, row in neighbourhoods.items():                                        # :79-95 (MIN_NEIGH_SIZE = 5)
+        for nei_key, nei in row.items():
+            if nei[0] < 5:
+                continue
+            neg_sorted.setdefault(row_key, [])
+            idxs = [i + nei_key for i in range(len(nei[1]))]
+            pos_sorted.setdefault(row_key, [])
+            pos_sorted[row_key] = pos_sorted[row_key] + [np.argmax(nei[1]) + nei_key]
+            del idxs[np.argmax(nei[1])]
+            neg_sorted[row_key] = neg_sorted[row_key] + idxs
+    reversed_ = np.argsort(means_indices)                                              # :98-110
+    neg = {r: [int(np.where(reversed_ == prof)[0][0]) for prof in row] for r, row in neg_sorted.items()}
+    pos = {r: [int(np.where(reversed_ == prof)[0][0]) for prof in row] for r, row in pos_sorted.items()}
+    return neg, pos
+
+
 def similarity_mat(sig, gom, loc, spr, neighbourhood_weight=0.0, score_threshold=0,
-                   scheme="PG", p=1.0) -> np.ndarray:
+                   scheme="PG", p=1.0, neighbourhoods=None) -> np.ndarray:
     """SimilarityMat_Constructor pair loop + clean/combine/power,
     app/utils/similarity_matrix_constructor.py:112-226.
 
-    Restated for ``neighbourhood_weight == 0`` (the default, api_classes.py:135, and every
-    shipped payload): then the CSV preprocessing :19-110 has no effect on the result
-    (quirk Q2) and the in-place row mutation :126-140 reduces to the idempotent threshold
-    ``row[row < thr] = 0`` (quirk Q1), which is applied to the CALLER'S array as the
-    reference does."""
-    if neighbourhood_weight != 0:
-        raise NotImplementedError("oracle restates the PphmmNeighbourhoodWeight == 0 path only")
+    With ``neighbourhood_weight == 0`` (the default, api_classes.py:135, and every shipped
+    payload) the CSV preprocessing :19-110 has no effect on the result (quirk Q2) and the
+    in-place row mutation :126-140 reduces to the idempotent threshold ``row[row < thr] = 0``
+    (quirk Q1).  With a non-zero weight pass ``neighbourhoods = neighbourhood_index_lists(..)``:
+    the rows are then scaled IN PLACE every time the pair loop touches them, exactly as the
+    reference does (the caller's ``sig`` is left mutated, and the result depends on it)."""
+    if neighbourhood_weight != 0 and neighbourhoods is None:
+        raise ValueError("neighbourhood_weight != 0 needs the index lists of neighbourhood_index_lists()")
+    neg, pos = neighbourhoods if neighbourhoods is not None else ({}, {})
     N = sig.shape[0] if sig is not None else gom.shape[0]
     p = float(p)
     P_mat = np.zeros((N, N))
     G_mat = np.zeros((N, N))
     L_mat = np.zeros((N, N))
+    NEG_WEIGHT = 1 - neighbourhood_weight
+    POS_WEIGHT = 1 + neighbourhood_weight
     for i in range(N):
         for j in range(i, N):
             if "P" in scheme:
                 si = sig[i]
                 sj = sig[j]
+                for r, row in ((i, si), (j, sj)):                                      # :126-137
+                    if r in neg:
+                        row[neg[r]] = row[neg[r]] * NEG_WEIGHT
+                        row[pos[r]] = row[pos[r]] * POS_WEIGHT
                 si[si < score_threshold] = 0
                 sj[sj < score_threshold] = 0
                 P_mat[i, j] = _gj(si, sj)

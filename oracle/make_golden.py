@@ -153,5 +153,46 @@ def main():
     print("wrote", os.path.join(OUT, "reference_golden.npz"), len(gold), "arrays")
 
 
+def main_neighbourhood():
+    """PphmmNeighbourhoodWeight != 0: the unmodified reference on
+    tables with runs of >= 4 consecutive hits in location order, one of them reaching the last column."""
+    gold = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, (n, p, g, dens, seed) in {"C": (12, 48, 3, 0.55, 303), "D": (9, 40, 3, 0.35, 404)}.items():
+            t = make_tables(n, p, g, dens, seed)
+            sig, loc = t.sig, t.loc
+            # naive location table of the CSV: |loc|, increasing with the column number so that the location
+            # order is (mostly) the column order and hit runs survive the sort; the last column sorts last
+            rng = np.random.default_rng(seed)
+            naive = np.where(sig != 0, (np.arange(p)[None, :] * 100.0 + rng.integers(1, 90, (n, p))), 0.0)
+            sig[1, -6:] = [55.5, 80.1, 20.2, 90.3, 10.4, 70.7]       # run that reaches the last column
+            naive[1, -6:] = (np.arange(p)[-6:] * 100.0 + 7)
+            sig[2, :5] = [30.0, 45.0, 60.0, 75.0, 15.0]              # run starting at the (skipped) first column
+            naive[2, :5] = (np.arange(5) * 100.0 + 3)
+            sig[2, 5] = 0.0; naive[2, 5] = 0.0
+            if tag == "D":
+                sig[4] = 0.0; naive[4] = 0.0                         # all-zero genome
+            fn = write_csvs(tmp, sig, naive)
+            db = GOMDB_Constructor(t.taxo, loc, t.gom_ids)
+            gom = ref_gom_table(loc, db, t.gom_ids)
+            gold[f"{tag}_sig"], gold[f"{tag}_naive_loc"], gold[f"{tag}_gom"] = sig.copy(), naive, gom
+            for k, (w, thr, scheme, pw) in enumerate([(0.05, 0, "P", 1.0), (0.05, 30, "PG", 1.0), (0.3, 12.5, "PG", 2.0)]):
+                s_in = sig.copy()
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    S = SimilarityMat_Constructor(s_in, gom, loc, None, w, thr, scheme, pw, fn)
+                    S2 = SimilarityMat_Constructor(s_in, gom, loc, None, w, thr, scheme, pw, fn)   # second call starts from the mutated table
+                gold[f"{tag}_case{k}"] = np.array([w, thr, pw])
+                gold[f"{tag}_case{k}_scheme"] = np.array(scheme)
+                gold[f"{tag}_case{k}_S"] = np.array(S)
+                gold[f"{tag}_case{k}_S_second_call"] = np.array(S2)
+                gold[f"{tag}_case{k}_sig_after_two_calls"] = s_in
+    np.savez_compressed(os.path.join(OUT, "reference_golden_neighbourhood.npz"), **gold)
+    print("wrote reference_golden_neighbourhood.npz", len(gold), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "neighbourhood":
+        main_neighbourhood()
+    else:
+        main()

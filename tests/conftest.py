@@ -17,3 +17,27 @@ def pytest_configure(config):
 def golden():
     path = os.path.join(REPO, "tests", "golden", "reference_golden.npz")
     return dict(np.load(path, allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def golden_nbhd():
+    """PphmmNeighbourhoodWeight != 0 outputs of the unmodified reference (oracle/make_golden.py neighbourhood)."""
+    path = os.path.join(REPO, "tests", "golden", "reference_golden_neighbourhood.npz")
+    return dict(np.load(path, allow_pickle=False))
+
+
+def write_reference_csvs(tmp, sig, naive_loc):
+    """The two CSVs SimilarityMat_Constructor reads, laid out as app/src/pl1_graphs.py:307-319 writes them."""
+    import pandas as pd
+    n, p = sig.shape
+    names = [f"v{i}" for i in range(n)]
+    cols = [f"PPHMM {c}" for c in range(p)]
+    df = pd.DataFrame(sig, columns=cols)
+    df.insert(0, "Virus name", names)
+    f_sig = os.path.join(tmp, "sigs.csv")
+    df.to_csv(f_sig)
+    dl = pd.DataFrame(np.abs(naive_loc), columns=cols)
+    dl.insert(0, "Virus name", names)
+    f_loc = os.path.join(tmp, "locs.csv")
+    dl.to_csv(f_loc, index=False)
+    return {"PphmmLocs": f_loc, "PphmmAndGomSigs": f_sig}

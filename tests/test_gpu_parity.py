@@ -53,10 +53,50 @@ def test_threshold_golden(golden, eng, tag):
     assert np.array_equal(sig, golden[f"{tag}_sig_after_thr60"])      # caller's table mutated like the reference
 
 
-def test_neighbourhood_weight_is_refused(golden):
+@pytest.mark.parametrize("tag", ["C", "D"])
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_neighbourhood_weight_golden(golden_nbhd, eng, tag, case):
+    """PphmmNeighbourhoodWeight != 0: the reference's visit-count dependent in-place row scaling (quirk Q1),
+    two consecutive calls on the same (mutated) table, against the unmodified reference's outputs."""
     import gravity2_b200 as G
-    with pytest.raises(NotImplementedError):
-        G.SimilarityMat_Constructor(golden["A_sig"], golden["A_gom"], golden["A_loc"], None, 0.1, 0, "PG", 1.0)
+    from conftest import write_reference_csvs
+    g = golden_nbhd
+    w, thr, pw = g[f"{tag}_case{case}"]
+    scheme = str(g[f"{tag}_case{case}_scheme"])
+    sig = g[f"{tag}_sig"].copy()
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = write_reference_csvs(tmp, g[f"{tag}_sig"], g[f"{tag}_naive_loc"])
+        S = G.SimilarityMat_Constructor(sig, g[f"{tag}_gom"], None, None, w, thr, scheme, pw, fn)
+        S2 = G.SimilarityMat_Constructor(sig, g[f"{tag}_gom"], None, None, w, thr, scheme, pw, fn)
+    close(S, g[f"{tag}_case{case}_S"])
+    close(S2, g[f"{tag}_case{case}_S_second_call"])
+    assert np.array_equal(S, S.T)
+    assert np.array_equal(sig, g[f"{tag}_case{case}_sig_after_two_calls"])    # caller's table left as the reference leaves it
+
+
+@pytest.mark.parametrize("scheme", ["P", "PG", "PR", "PL"])
+def test_neighbourhood_weight_vs_oracle(eng, scheme):
+    """Larger seeded table, every scheme with a P component, against the loop restatement."""
+    import gravity2_b200 as G
+    from conftest import write_reference_csvs
+    t = synth.make_tables(45, 160, 4, 0.45, seed=77)
+    rng = np.random.default_rng(5)
+    naive = np.where(t.sig != 0, np.arange(160)[None, :] * 50.0 + rng.integers(1, 40, t.sig.shape), 0.0)
+    spr = rng.random((45, 45)); spr = (spr + spr.T) / 2
+    db = O.gomdb(t.taxo, t.loc, t.gom_ids)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gom = O.gom_table(t.loc, db, t.gom_ids)
+        nb = O.neighbourhood_index_lists(naive, t.sig)
+        assert len(nb[0]) > 10
+        s_ref = t.sig.copy()
+        ref = O.similarity_mat(s_ref, gom, t.loc, spr.copy(), 0.1, 25, scheme, 1.5, neighbourhoods=nb)
+    s_dev = t.sig.copy()
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = write_reference_csvs(tmp, t.sig, naive)
+        S = G.SimilarityMat_Constructor(s_dev, gom, t.loc, spr.copy(), 0.1, 25, scheme, 1.5, fn)
+    close(S, ref)
+    assert np.array_equal(s_dev, s_ref)
 
 
 @pytest.mark.parametrize("tag", ["A", "B"])

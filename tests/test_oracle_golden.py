@@ -139,3 +139,63 @@ def test_newick_average_matches_reference(golden, tag):
     D = O.dist_from_sim(S.copy())
     n = len(D)
     assert O.dist_mat_to_tree(D, [f"v{i}" for i in range(n)], "average") == str(golden[f"{tag}_newick_avg"])
+
+
+# ------------------------------------------------- PphmmNeighbourhoodWeight != 0
+@pytest.mark.parametrize("tag", ["C", "D"])
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_neighbourhood_mode_oracle_is_the_reference(golden_nbhd, tag, case):
+    g = golden_nbhd
+    w, thr, pw = g[f"{tag}_case{case}"]
+    scheme = str(g[f"{tag}_case{case}_scheme"])
+    nb = O.neighbourhood_index_lists(g[f"{tag}_naive_loc"], g[f"{tag}_sig"])
+    assert nb[0], "fixture must contain neighbourhoods"
+    sig = g[f"{tag}_sig"].copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        S = O.similarity_mat(sig, g[f"{tag}_gom"], None, None, w, thr, scheme, pw, neighbourhoods=nb)
+        S2 = O.similarity_mat(sig, g[f"{tag}_gom"], None, None, w, thr, scheme, pw, neighbourhoods=nb)
+    assert np.array_equal(S, g[f"{tag}_case{case}_S"])
+    assert np.array_equal(S2, g[f"{tag}_case{case}_S_second_call"])           # starts from the mutated table
+    assert np.array_equal(sig, g[f"{tag}_case{case}_sig_after_two_calls"])
+    assert not np.array_equal(S, S2)
+
+
+@pytest.mark.parametrize("tag", ["C", "D"])
+def test_neighbourhood_host_logic(golden_nbhd, tag):
+    """gravity2_b200.neighbourhood (array formulation) == the loop restatement == the reference."""
+    from gravity2_b200 import neighbourhood as NB
+    g = golden_nbhd
+    neg, pos = O.neighbourhood_index_lists(g[f"{tag}_naive_loc"], g[f"{tag}_sig"])
+    ref = np.zeros(g[f"{tag}_sig"].shape, dtype=np.uint8)
+    for r, cols in neg.items():
+        ref[r, cols] |= NB.NEG
+    for r, cols in pos.items():
+        ref[r, cols] |= NB.POS
+    cls = NB.neighbourhood_classes(g[f"{tag}_naive_loc"], g[f"{tag}_sig"])
+    assert np.array_equal(cls, ref)
+    for case in range(3):
+        w, thr, _ = g[f"{tag}_case{case}"]
+        sig = g[f"{tag}_sig"].copy()
+        n = len(sig)
+        NB.apply_in_place(sig, cls, w, thr, n + 1)
+        NB.apply_in_place(sig, cls, w, thr, n + 1)
+        assert np.array_equal(sig, g[f"{tag}_case{case}_sig_after_two_calls"])
+
+
+def test_neighbourhood_host_logic_random():
+    from gravity2_b200 import neighbourhood as NB
+    rng = np.random.default_rng(7)
+    for _ in range(120):
+        n, p = int(rng.integers(1, 8)), int(rng.integers(1, 30))
+        sig = np.where(rng.random((n, p)) < rng.random(), np.round(rng.gamma(2, 60, (n, p)), 1), 0.0)
+        loc = np.where(sig != 0, rng.integers(1, 5, (n, p)) * 1.0, 0.0)
+        if rng.random() < 0.3:
+            loc[:, rng.integers(0, p)] = 0          # never-hit column: NaN mean, sorts last
+        neg, pos = O.neighbourhood_index_lists(loc, sig)
+        ref = np.zeros((n, p), dtype=np.uint8)
+        for r, cols in neg.items():
+            ref[r, cols] |= NB.NEG
+        for r, cols in pos.items():
+            ref[r, cols] |= NB.POS
+        assert np.array_equal(NB.neighbourhood_classes(loc, sig), ref)
