@@ -39,18 +39,18 @@
 #define BM_PAIRS 128
 #define BM_KC 128                      // columns per pipeline stage (= one 128-byte swizzle row of uint8)
 #define BM_STAGES 2
-// NP = uint8 digit planes per pass: 2 (two passes, N <= 256: the wide-N variant) or 4 (one pass, N <= 128: used
-// when a call brings at most 128 replicates, e.g. 1000 replicates sharded over 8 GPUs).  NP * NMAX = 512 TMEM columns.
+#define BM_PLANES 2                    // uint8 digit planes per pass (two passes cover the 32-bit fixed-point min)
+#define BM_NMAX 256                    // replicates per CTA: BM_PLANES * BM_NMAX = 512 TMEM columns
 #define BM_TMEM_COLS 512
-#define BM_NMAX_OF(NP) (BM_TMEM_COLS / (NP))
 #define BM_PRODUCERS 512               // producer threads (16 warps: two pair rows per thread and stage)
 #define BM_THREADS (BM_PRODUCERS + 64)
 #define BM_RING 3                      // table-row staging ring (chunks)
 #define BM_ROWS 24                     // 8 i-rows + 16 j-rows
 #define BM_A_BYTES (BM_PAIRS * BM_KC)                // 16 KB per plane
-#define BM_STAGE_BYTES_OF(NP) ((NP) * BM_A_BYTES + BM_NMAX_OF(NP) * BM_KC)   // NP=2: 64 KB, NP=4: 80 KB
+#define BM_W_BYTES (BM_NMAX * BM_KC)                 // 32 KB
+#define BM_STAGE_BYTES (BM_PLANES * BM_A_BYTES + BM_W_BYTES) // 64 KB
 #define BM_RING_BYTES (BM_ROWS * BM_KC * 4)          // 12 KB per chunk
-#define BM_SMEM_OF(NP) (BM_STAGES * BM_STAGE_BYTES_OF(NP) + BM_RING * BM_RING_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define BM_SMEM (BM_STAGES * BM_STAGE_BYTES + BM_RING * BM_RING_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 
 __host__ __device__ inline int bm_ws_index(int r, int c) { return ((((r >> 4) << 3) + (c >> 4)) << 8) + ((r & 15) << 4) + (c & 15); }
 
@@ -148,32 +148,22 @@ __device__ __forceinline__ void cp16(void* smem, const void* gmem) {
 // byte transpose of one half-word: v0..v3 = four consecutive columns (u32 each) -> p[0] = the low bytes,
 // p[1] = the high bytes of the selected half-word (HI: bytes 2,3; else bytes 0,1), column k in byte k
 // (little endian = element order of the K-major uint8 tile).  4 PRMT.
-template <int NP, bool HI>
+template <bool HI>
 __device__ __forceinline__ void byte_planes(const uint32_t v0, const uint32_t v1, const uint32_t v2, const uint32_t v3,
                                             uint32_t* p) {
-    if (NP == 2) {
-        const uint32_t t0 = __byte_perm(v0, v1, HI ? 0x7362 : 0x5140);   // v0.bA v1.bA v0.bB v1.bB
-        const uint32_t t1 = __byte_perm(v2, v3, HI ? 0x7362 : 0x5140);
-        p[0] = __byte_perm(t0, t1, 0x5410);
-        p[1] = __byte_perm(t0, t1, 0x7632);
-    } else {                                                             // all four bytes: 8 PRMT
-        const uint32_t t0 = __byte_perm(v0, v1, 0x5140), t1 = __byte_perm(v2, v3, 0x5140);
-        const uint32_t t2 = __byte_perm(v0, v1, 0x7362), t3 = __byte_perm(v2, v3, 0x7362);
-        p[0] = __byte_perm(t0, t1, 0x5410);
-        p[1] = __byte_perm(t0, t1, 0x7632);
-        p[NP - 2] = __byte_perm(t2, t3, 0x5410);
-        p[NP - 1] = __byte_perm(t2, t3, 0x7632);
-    }
+    const uint32_t t0 = __byte_perm(v0, v1, HI ? 0x7362 : 0x5140);   // v0.bA v1.bA v0.bB v1.bB
+    const uint32_t t1 = __byte_perm(v2, v3, HI ? 0x7362 : 0x5140);
+    p[0] = __byte_perm(t0, t1, 0x5410);
+    p[1] = __byte_perm(t0, t1, 0x7632);
 }
 
 // ---------------------------------------------------------------------------------- kernel
 // grid = (128 sub-tiles, genome tiles in [tile_begin, tile_end), replicate blocks)
-template <int NP, bool HI>
+template <bool HI>
 __global__ void __launch_bounds__(BM_THREADS, 1)
 boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, long long tile_begin,
                 const __grid_constant__ CUtensorMap wmap, int nb_total, int nblk, long long ws_rep_stride,
                 double quantum, double* __restrict__ ws) {
-    constexpr int BM_PLANES = NP, BM_NMAX = BM_NMAX_OF(NP), BM_STAGE_BYTES = BM_STAGE_BYTES_OF(NP);
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B needs 1024-B alignment; offsetting the array (not casting through uintptr_t) keeps the
     // pointers provably shared, so the producers get LDS/STS instead of generic LD/ST
@@ -203,7 +193,7 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) {   // TMEM: NP digit planes x 512/NP int32 columns
+    if (warp == 0) {   // TMEM: 2 digit planes x 256 int32 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BM_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -256,7 +246,7 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
                 for (int b = 0; b < 4; ++b) {
                     const int m = (ii0 + a) * 16 + jj0 + b;                 // pair row of the A tiles
                     uint32_t p[BM_PLANES];
-                    byte_planes<NP, HI>(min(x[a].x, y[b].x), min(x[a].y, y[b].y), min(x[a].z, y[b].z), min(x[a].w, y[b].w), p);
+                    byte_planes<HI>(min(x[a].x, y[b].x), min(x[a].y, y[b].y), min(x[a].z, y[b].z), min(x[a].w, y[b].w), p);
                     // K-major SWIZZLE_128B: row m at (m/8)*1024 + (m%8)*128; columns col..col+3 are bytes col..col+3:
                     // 16-byte piece col/16 (XOR m%8), word (col/4)%4
                     uint8_t* dst = a0 + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u +
@@ -290,8 +280,7 @@ boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, l
                 const int rep = col0 + e;
                 // exact integers: each plane sum < 2^31; the low pass stores, the high pass adds 65536 x its sums
                 // (a second launch on the same stream: plain read-modify-write, deterministic)
-                double sum = (double)(int)v[0][e] + 256.0 * (double)(int)v[1][e];
-                if (NP == 4) sum += 65536.0 * (double)(int)v[NP - 2][e] + 16777216.0 * (double)(int)v[NP - 1][e];
+                const double sum = (double)(int)v[0][e] + 256.0 * (double)(int)v[1][e];
                 if (rep < nrep) {
                     double* o = out + (size_t)(rep0 + rep) * ws_rep_stride;
                     if (HI) *o += sum * 65536.0 * quantum;
@@ -466,10 +455,7 @@ int boot_mma_rowsums(gv2_ctx* ctx, const double* ws, int64_t ntl, int64_t n, int
     return GV2_OK;
 }
 
-// one pass over four planes when everything fits 128 replicates, else two passes over two planes with N <= 256
-static int bm_planes(int64_t nb) { return nb <= BM_NMAX_OF(4) ? 4 : 2; }
 static void bm_blocks(int64_t nb, int64_t* nblocks, int64_t* nblk) {
-    const int64_t BM_NMAX = BM_NMAX_OF(bm_planes(nb));
     *nblocks = (nb + BM_NMAX - 1) / BM_NMAX;
     *nblk = ((nb + *nblocks - 1) / *nblocks + 15) / 16 * 16;
 }
@@ -507,9 +493,8 @@ int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n
     if (r != CUDA_SUCCESS) return gv2_fail(ctx, GV2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     static bool attr_done = false;
     if (!attr_done) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM_OF(2)));
-        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM_OF(2)));
-        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM_OF(4)));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
         attr_done = true;
     }
     if (ntl > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "boot_mma_launch: more than 65535 genome tiles per launch");
@@ -520,21 +505,15 @@ int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n
         GV2_CUDA(ctx, cudaEventCreate(&ev1));
         GV2_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
-    const int kchunks = (int)(k_pad / BM_KC), ntside = (int)(n_pad / GV2_TILE);
-    const long long rep_stride = (long long)ntl * GV2_TILE * GV2_TILE;
-    if (bm_planes(nb) == 4) {
-        boot_mma_kernel<4, false><<<grid, BM_THREADS, BM_SMEM_OF(4), ctx->stream>>>(tab, (int)k_pad, kchunks, ntside, tile_begin, map,
-                                                                                    (int)nb, (int)nblk, rep_stride, quantum, ws);
-        GV2_LAUNCH_CHECK(ctx);
-    } else {
-        // low half-word (digit planes 0, 1) stores, high half-word (planes 2, 3) accumulates on top
-        boot_mma_kernel<2, false><<<grid, BM_THREADS, BM_SMEM_OF(2), ctx->stream>>>(tab, (int)k_pad, kchunks, ntside, tile_begin, map,
-                                                                                    (int)nb, (int)nblk, rep_stride, quantum, ws);
-        GV2_LAUNCH_CHECK(ctx);
-        boot_mma_kernel<2, true><<<grid, BM_THREADS, BM_SMEM_OF(2), ctx->stream>>>(tab, (int)k_pad, kchunks, ntside, tile_begin, map,
-                                                                                   (int)nb, (int)nblk, rep_stride, quantum, ws);
-        GV2_LAUNCH_CHECK(ctx);
-    }
+    // low half-word (digit planes 0, 1) stores, high half-word (planes 2, 3) accumulates on top
+    boot_mma_kernel<false><<<grid, BM_THREADS, BM_SMEM, ctx->stream>>>(tab, (int)k_pad, (int)(k_pad / BM_KC), (int)(n_pad / GV2_TILE),
+                                                                       tile_begin, map, (int)nb, (int)nblk,
+                                                                       (long long)ntl * GV2_TILE * GV2_TILE, quantum, ws);
+    GV2_LAUNCH_CHECK(ctx);
+    boot_mma_kernel<true><<<grid, BM_THREADS, BM_SMEM, ctx->stream>>>(tab, (int)k_pad, (int)(k_pad / BM_KC), (int)(n_pad / GV2_TILE),
+                                                                      tile_begin, map, (int)nb, (int)nblk,
+                                                                      (long long)ntl * GV2_TILE * GV2_TILE, quantum, ws);
+    GV2_LAUNCH_CHECK(ctx);
     if (ctx->timing) {
         GV2_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
         ctx->timed.emplace_back(ev0, ev1);
