@@ -2,7 +2,9 @@
 // Declarations and per-entry reference citations: include/gravity2_b200.h.
 #include "common.cuh"
 
+#include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,14 +15,29 @@
 int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n_pad, int64_t k_pad,
                        int64_t tile_begin, int64_t tile_end, const float* w, int64_t nb, int ksplit,
                        double* ws);
+int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k_pad, int64_t nb,
+                    const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
+                    double* ws, double* out, int64_t out_replicate_stride);
 int boot_mma_available();
 int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n_pad, int64_t k_pad, int64_t tile_begin,
                     int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* w8_scratch, int* overflow_flag,
                     double* ws);
 size_t boot_mma_scratch_bytes(int64_t k_pad, int64_t nb);
+int boot_table_stats(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src, double* max_value, int* has_negative);
 int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src, uint32_t* dst,
-                           int64_t n_pad, int64_t k_pad, double* quantum, int* usable);
+                           int64_t n_pad, int64_t k_pad, double max_value, double* quantum);
 int boot_mma_rowsums(gv2_ctx* ctx, const double* ws, int64_t ntl, int64_t n, int64_t nb, double* out);
+struct BootSparse;
+int boot_sparse_build(gv2_ctx* ctx, const double* tab, int64_t n, int64_t k, int64_t ld, int64_t n_pad, int64_t k_pad,
+                      double max_value, BootSparse** out);
+void boot_sparse_free(BootSparse* s);
+size_t boot_sparse_bytes(const BootSparse* s);
+long long boot_sparse_nnz(const BootSparse* s);
+unsigned long long boot_sparse_cells(const BootSparse* s);
+size_t boot_sparse_scratch_bytes(int64_t k_pad, int64_t nb);
+int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t k_pad, int64_t tile_begin,
+                       int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* wT_scratch, int* overflow_flag,
+                       double* ws);
 
 static thread_local std::string g_create_error;
 
@@ -166,6 +183,7 @@ struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     ~DevBuf() { if (p) cudaFree(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
     cudaError_t alloc(size_t b) {
         if (p) { cudaFree(p); p = nullptr; }
         bytes = b ? b : 1;
@@ -213,6 +231,7 @@ struct gv2_job {
     DevBuf sigfix;                     // 32-bit fixed-point signature table for the tensor-core path
     double quantum = 0.0;
     bool mma_ok = false;
+    BootSparse* sparse = nullptr;      // CSR of the fixed-point table when the sparse replicate path is chosen
     GomDb* gom = nullptr;
     DevBuf gom_base;                   // [n][g] float64 base GOM table (lazy)
     bool have_gom_base = false;
@@ -224,6 +243,7 @@ struct gv2_job {
         size_t b = sig64.bytes + loc64.bytes + sigf.bytes + sig_rowsum.bytes + sig_nan.bytes + gom_base.bytes +
                    wsP.bytes + wsG.bytes + gomtab.bytes + gomf.bytes + gom_rowsum.bytes + gom_nan.bytes + wf.bytes + w_rowsum.bytes;
         if (gom) b += gom->bytes;
+        b += sigfix.bytes + wbf16.bytes + boot_sparse_bytes(sparse);
         return b;
     }
 };
@@ -244,6 +264,7 @@ extern "C" void gv2_job_destroy(gv2_job* job) {
         cudaStreamDestroy(job->copy_stream);
     }
     gom_db_free(job->gom);
+    boot_sparse_free(job->sparse);
     delete job;
 }
 
@@ -276,12 +297,35 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
         if ((rc = ensure(ctx, j->sig_nan, (size_t)n))) return bail(rc);
         if ((rc = gv2_dev_prepare_table(ctx, j->d_sig, n, p, p, 0.0, 0, j->sigf.as<float>(), j->n_pad, j->p_pad,
                                         j->sig_rowsum.as<double>(), j->sig_nan.as<uint8_t>()))) return bail(rc);
-        if (boot_mma_available()) {
-            int usable = 0;
-            if ((rc = ensure(ctx, j->sigfix, (size_t)j->n_pad * j->p_pad * sizeof(uint32_t)))) return bail(rc);
-            if ((rc = boot_mma_prepare_table(ctx, j->d_sig, n, p, p, j->sigfix.as<uint32_t>(), j->n_pad, j->p_pad, &j->quantum,
-                                             &usable))) return bail(rc);
-            j->mma_ok = usable != 0;
+        {
+            // Replicate path.  Two exact integer paths on a fixed-point image of the table (both need a non-negative
+            // table): the CSR walk (work ~ co-present columns; real tables are ~99 % zeros) and the dense tensor-core
+            // contraction; else the fp32 tile kernel.  GV2_BOOT_PATH = sparse | mma | fp32 overrides the cost model.
+            double mx = 0.0;
+            int neg = 0;
+            if ((rc = boot_table_stats(ctx, j->d_sig, n, p, p, &mx, &neg))) return bail(rc);
+            const bool usable = !neg && isfinite(mx);
+            const char* path = getenv("GV2_BOOT_PATH");
+            const bool want_fp32 = path && !strcmp(path, "fp32");
+            const bool can_mma = boot_mma_available() != 0;
+            if (usable && !want_fp32) {
+                if ((rc = boot_sparse_build(ctx, j->d_sig, n, p, p, j->n_pad, j->p_pad, mx, &j->sparse))) return bail(rc);
+                // cost model (measured rates): the CSR walk does `cells` multiply-adds per
+                // replicate at ~1/75 of the per-cell rate of the dense tensor-core contraction
+                const double dense_cells = 0.5 * (double)j->n_pad * (double)(j->n_pad + 1) * (double)j->p_pad;
+                bool sparse_wins = (double)boot_sparse_cells(j->sparse) * 75.0 < dense_cells;
+                if (path && !strcmp(path, "sparse")) sparse_wins = true;
+                if (path && !strcmp(path, "mma")) sparse_wins = false;
+                if (!can_mma) sparse_wins = true;                        // both exact; never fall to fp32 needlessly
+                if (!sparse_wins) {
+                    boot_sparse_free(j->sparse);
+                    j->sparse = nullptr;
+                    if ((rc = ensure(ctx, j->sigfix, (size_t)j->n_pad * j->p_pad * sizeof(uint32_t)))) return bail(rc);
+                    if ((rc = boot_mma_prepare_table(ctx, j->d_sig, n, p, p, j->sigfix.as<uint32_t>(), j->n_pad, j->p_pad, mx,
+                                                     &j->quantum))) return bail(rc);
+                    j->mma_ok = true;
+                }
+            }
         }
     }
     if (j->need_g) {
@@ -435,15 +479,21 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
         if (job->need_p) {
             if ((rc = ensure(ctx, job->w_rowsum, (size_t)sb * n * sizeof(double)))) return rc;
             if ((rc = ensure(ctx, job->wsP, (size_t)sb * ntl * tile_elems * sizeof(double)))) return rc;
-            if (job->mma_ok && sb >= 8) {
-                // tensor-core path: exact integer contraction on the fixed-point table
-                if ((rc = ensure(ctx, job->wbf16, boot_mma_scratch_bytes(job->p_pad, sb)))) return rc;
+            if (job->sparse || (job->mma_ok && sb >= 8)) {
+                // exact integer paths on the fixed-point table: CSR walk (sparse tables) or tensor-core contraction
+                const size_t scratch = job->sparse ? boot_sparse_scratch_bytes(job->p_pad, sb) : boot_mma_scratch_bytes(job->p_pad, sb);
+                if ((rc = ensure(ctx, job->wbf16, scratch))) return rc;
                 if (!job->mma_flag.p) {
                     if ((rc = ensure(ctx, job->mma_flag, sizeof(int)))) return rc;
                     GV2_CUDA(ctx, cudaMemsetAsync(job->mma_flag.p, 0, sizeof(int), ctx->stream));
                 }
-                if ((rc = boot_mma_launch(ctx, job->sigfix.as<uint32_t>(), job->quantum, job->n_pad, job->p_pad, 0, ntl, w, p, sb,
-                                          job->wbf16.p, job->mma_flag.as<int>(), job->wsP.as<double>()))) return rc;
+                if (job->sparse)
+                    rc = boot_sparse_launch(ctx, job->sparse, job->n_pad, job->p_pad, 0, ntl, w, p, sb, job->wbf16.p,
+                                            job->mma_flag.as<int>(), job->wsP.as<double>());
+                else
+                    rc = boot_mma_launch(ctx, job->sigfix.as<uint32_t>(), job->quantum, job->n_pad, job->p_pad, 0, ntl, w, p, sb,
+                                         job->wbf16.p, job->mma_flag.as<int>(), job->wsP.as<double>());
+                if (rc) return rc;
                 if ((rc = boot_mma_rowsums(ctx, job->wsP.as<double>(), ntl, n, sb, job->w_rowsum.as<double>()))) return rc;
                 used_mma = true;
             } else {
@@ -476,17 +526,18 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
                 cp.ksplit = 1; cp.replicate_stride_sums = (int64_t)(ntl * tile_elems); cp.replicate_stride_rows = n;
             }
             if (job->need_g) {
-                if ((rc = ensure(ctx, job->wsG, (size_t)cb * ntl * tile_elems * sizeof(double)))) return rc;
-                if ((rc = gj_min_sums_launch(ctx, job->gomf.as<float>() + (size_t)c0 * job->n_pad * job->g_pad, job->n_pad * job->g_pad,
-                                             job->n_pad, job->g_pad, 0, ntl, nullptr, cb, 1, job->wsG.as<double>()))) return rc;
-                cg.min_sums = job->wsG.as<double>(); cg.rowsums = job->gom_rowsum.as<double>() + c0 * n;
-                cg.nanflags = job->gom_nan.as<uint8_t>() + c0 * n;
-                cg.ksplit = 1; cg.replicate_stride_sums = (int64_t)(ntl * tile_elems); cg.replicate_stride_rows = n;
-                cg.replicate_stride_nan = n;
+                // GOM Jaccard sums and the epilogue in one kernel: the GOM pair sums never go through HBM
+                cg.rowsums = job->gom_rowsum.as<double>() + c0 * n; cg.nanflags = job->gom_nan.as<uint8_t>() + c0 * n;
+                cg.ksplit = 1; cg.replicate_stride_rows = n; cg.replicate_stride_nan = n;
+                if ((rc = ensure(ctx, job->wsG, (size_t)(job->g_pad > 128 ? cb : 1) * ntl * tile_elems * sizeof(double)))) return rc;
+                if ((rc = gj_fused_launch(ctx, job->gomf.as<float>() + (size_t)c0 * job->n_pad * job->g_pad, job->n_pad * job->g_pad, n,
+                                          job->n_pad, job->g_pad, cb, job->need_p ? &cp : nullptr, &cg, job->scheme, job->power,
+                                          job->out_kind, job->wsG.as<double>(), dev_ring + slot * n * n, n * n))) return rc;
+            } else {
+                // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)
+                if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
+                                              dev_ring + slot * n * n, n * n))) return rc;
             }
-            // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)
-            if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
-                                          dev_ring + slot * n * n, n * n))) return rc;
             if (host_out) {
                 GV2_CUDA(ctx, cudaEventRecord(job->ev_ready[half], ctx->stream));
                 GV2_CUDA(ctx, cudaStreamWaitEvent(job->copy_stream, job->ev_ready[half], 0));
@@ -511,7 +562,8 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
         int flag = 0;
         GV2_CUDA(ctx, cudaMemcpyAsync(&flag, job->mma_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (flag) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a column multiplicity exceeds 255 (uint8 weights of the tensor-core path); set GV2_DISABLE_MMA=1");
+        if (flag) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "%s (limits of the exact integer replicate paths); set GV2_BOOT_PATH=fp32",
+                                  flag == 2 ? "a replicate's column multiplicities sum to more than 65536" : "a column multiplicity exceeds 255");
     }
     return GV2_OK;
 }

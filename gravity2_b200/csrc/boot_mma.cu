@@ -418,10 +418,9 @@ int boot_mma_available() {
     return state;
 }
 
-// Builds the fixed-point table.  Returns GV2_OK and *usable = 0 if the table has negative entries
-// (min does not commute with the unsigned fixed-point map then; the caller keeps the fp32 path).
-int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src, uint32_t* dst,
-                           int64_t n_pad, int64_t k_pad, double* quantum, int* usable) {
+// Largest entry (ignoring NaN) and "has a negative entry" of a float64 table.  The exact integer replicate paths
+// need a non-negative table: min does not commute with the unsigned fixed-point map otherwise.
+int boot_table_stats(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src, double* max_value, int* has_negative) {
     unsigned long long* stats = nullptr;
     GV2_CUDA(ctx, cudaMalloc((void**)&stats, 2 * sizeof(unsigned long long)));
     GV2_CUDA(ctx, cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
@@ -434,12 +433,16 @@ int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(stats);
     if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "table stats: %s", cudaGetErrorString(e));
-    double mx;
-    memcpy(&mx, &h[0], sizeof mx);
-    *usable = (h[1] == 0 && isfinite(mx)) ? 1 : 0;
-    const double scale = mx > 0.0 ? 4294967295.0 / mx : 0.0;
-    *quantum = mx > 0.0 ? mx / 4294967295.0 : 0.0;
-    if (!*usable) return GV2_OK;
+    memcpy(max_value, &h[0], sizeof(double));
+    *has_negative = h[1] != 0;
+    return GV2_OK;
+}
+
+// Builds the 32-bit fixed-point table of the tensor-core path: x -> rint(x * (2^32 - 1) / max_value), zero padded.
+int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k, int64_t ld_src, uint32_t* dst,
+                           int64_t n_pad, int64_t k_pad, double max_value, double* quantum) {
+    const double scale = max_value > 0.0 ? 4294967295.0 / max_value : 0.0;
+    *quantum = max_value > 0.0 ? max_value / 4294967295.0 : 0.0;
     table_to_fixed_kernel<<<(unsigned)n_pad, 256, 0, ctx->stream>>>(src, n, k, ld_src, scale, dst, k_pad);
     GV2_LAUNCH_CHECK(ctx);
     return GV2_OK;

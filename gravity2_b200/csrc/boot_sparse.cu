@@ -1,0 +1,506 @@
+// Batched bootstrap Jaccard numerators on SPARSE signature tables (work ~ co-present PPHMMs), sm_100a.
+//
+// Same contract as boot_mma.cu: for every genome pair (i <= j) and every replicate b
+//     S[b][i][j] = sum_c w[b][c] * min(T[i][c], T[j][c])
+// (app/src/pl1_graphs.py:81-86 + app/utils/similarity_matrix_constructor.py:167, multiplicities
+// w = bincount(idx)), written to the same fp64 pair-sum workspace.
+//
+// Real signature tables are ~99 % zeros (a genome hits a few hundred of 30 000 PPHMMs), and
+// min(T[i][c], T[j][c]) is zero unless BOTH genomes hit c.  So per pair only the co-present columns
+// matter: ~4 on average at the 1 % density of the BASELINE configs, against 30 000 columns in the
+// dense contraction.  The kernel walks CSR rows.
+//
+// Exact and deterministic: values are 48-bit fixed point f = rint(x * 2^48 (1 - 2^-30) / max(T)) (a
+// monotone map, so min commutes), held as a 32-bit high and a 16-bit low limb; the multiplicities are
+// uint8; sum_c w_c * hi_c accumulates in 64-bit and sum_c w_c * lo_c in 32-bit integers (the launch
+// checks sum_c w_c <= 2^(32-16)), so the sums do not depend on the order the lists are built in.  The
+// only error is the input quantisation max(T) * 2^-49 per element (~1e-15 relative on S).
+//
+//   CTA  = one 16 x 16 block of a 128 x 128 genome-pair tile x up to 1024 replicates.
+//   build  : the 16 j-rows are scattered into a shared-memory table mask[c] = bit set of the j-rows
+//            that hit column c (uint16 per column, 60 KB for 30 000 columns); their column lists are
+//            copied to shared memory;
+//   match  : the entries of all 16 i-rows, one per thread: mask[c] names the j-rows sharing the
+//            column (usually none).  Hits are counted per pair, the 256 pair lists are laid out back
+//            to back in a pool by a block scan, and a second pass writes (column, min value), the j
+//            value found by binary search in the shared-memory copy of the row.  If the pool would
+//            overflow, the batch of i-rows is halved (down to a slice of one row);
+//   reduce : the threads become replicate lanes (one replicate each): for every list entry one byte of the
+//            transposed multiplicities wT[c][replicate], one IMAD.WIDE and one IMAD; the 16 pairs of an
+//            i-row accumulate in registers and leave as one whole 128-byte line of the workspace (the
+//            replicates' workspaces are 0.4 GB apart: partial lines would be evicted half written).
+// The row sums sum_c w_c x_ic are the diagonal pairs, exactly as in the tensor-core path.
+#include "common.cuh"
+
+#include <cub/cub.cuh>
+
+#define BS_THREADS 256
+#define BS_WIN 32768                    // columns per mask window (uint16 masks: <= 64 KB)
+#define BS_JCAP 256                     // j-row columns kept in shared memory (longer rows: tail searched in global memory)
+#define BS_POOL 2048                    // list entries per match pass (a 125-entry slice of one row can never overflow it)
+#define BS_LO_BITS 16
+static inline size_t bs_smem_bytes(int kwin) {
+    return (size_t)kwin * 2 + 16 * BS_JCAP * 4 + BS_POOL * 8 + (256 + 256 + 260 + 16) * sizeof(int);
+}
+
+__host__ __device__ inline void bs_tile_coords(long long t, int nt, int* bi, int* bj) {
+    double disc = (2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t;
+    int r = (int)floor(((2.0 * nt + 1.0) - sqrt(disc)) * 0.5);
+    if (r < 0) r = 0;
+    while (r > 0 && (long long)r * nt - (long long)r * (r - 1) / 2 > t) --r;
+    while ((long long)(r + 1) * nt - (long long)(r + 1) * r / 2 <= t) ++r;
+    *bi = r;
+    *bj = r + (int)(t - ((long long)r * nt - (long long)r * (r - 1) / 2));
+}
+
+struct BsCsr {
+    const long long* ptr;     // [n_pad + 1]
+    const int* col;           // [nnz] ascending within a row
+    const uint32_t* hi;       // [nnz] bits 47..16 of the 48-bit fixed-point value
+    const uint16_t* lo;       // [nnz] bits 15..0
+};
+
+// position of column c in a sorted row whose first `slen` columns are in shared memory, the rest in global memory
+__device__ __forceinline__ int bs_find(const int* scol, int slen, const int* gcol, int len, int c) {
+    int lo = 0, hi = slen - 1;
+    const int* col = scol;
+    int off = 0;
+    if (slen == 0 || c > scol[slen - 1]) { col = gcol + slen; off = slen; hi = len - slen - 1; }
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (col[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    return off + lo;
+}
+
+// grid = (64 sub-blocks, genome tiles in [tile_begin, tile_end), replicate blocks of RL)
+// RL = replicate lanes per slot (one replicate per lane), PP = 256 / RL slots sharing the i-rows of a batch
+template <int RL>
+__global__ void __launch_bounds__(BS_THREADS, 2)
+boot_sparse_kernel(BsCsr csr, int nt, long long tile_begin, const uint8_t* __restrict__ wT, long long w_ld, int kwin, int nwin,
+                   int nb_total, long long ws_rep_stride, double quantum, double* __restrict__ ws) {
+    constexpr int PP = BS_THREADS / RL;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t* mask32 = (uint32_t*)smem;                              // [kwin / 2]: two uint16 j-row masks per word
+    int* jcol = (int*)(smem + (size_t)kwin * 2);                     // [16][BS_JCAP]
+    uint2* pool = (uint2*)(jcol + 16 * BS_JCAP);                     // [BS_POOL] (window column | lo << 16, hi)
+    int* cnt = (int*)(pool + BS_POOL);                               // [256] hits per pair of the batch
+    int* fillc = cnt + 256;                                          // [256]
+    int* base = fillc + 256;                                         // [257] list offsets (multiples of 4)
+    int* jlen = base + 260;                                          // [16] j-row lengths
+    __shared__ typename cub::BlockScan<int, BS_THREADS>::TempStorage scan_tmp;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = blockIdx.x, si = sub >> 3, sj = sub & 7;
+    int bi, bj;
+    bs_tile_coords(tile_begin + blockIdx.y, nt, &bi, &bj);
+    if (bi == bj && si > sj) return;                                 // block entirely below the diagonal
+    const bool diag_block = bi == bj && si == sj;
+    const int slot = tid / RL, rl = tid % RL;
+    const int rep0 = blockIdx.z * RL + rl;                           // this lane's replicate
+    const long long rowI0 = (long long)bi * GV2_TILE + si * 16, rowJ0 = (long long)bj * GV2_TILE + sj * 16;
+    double* wsblk = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + (size_t)(((si << 3) + sj) << 8);
+    const double q_hi = quantum * 65536.0;
+
+    for (int win = 0; win < nwin; ++win) {
+        const int c_lo = win * BS_WIN;
+        // ---- build: j-row masks of this column window (+ the shared-memory copy of the column lists)
+        __syncthreads();
+        for (int q = tid; q < kwin / 2; q += BS_THREADS) mask32[q] = 0u;
+        __syncthreads();
+        for (int h = 0; h < 2; ++h) {
+            const int jj = warp + 8 * h;
+            const long long j0 = csr.ptr[rowJ0 + jj], j1 = csr.ptr[rowJ0 + jj + 1];
+            if (lane == 0) jlen[jj] = (int)(j1 - j0);
+            for (long long e = j0 + lane; e < j1; e += 32) {
+                const int c = csr.col[e];
+                if (e - j0 < BS_JCAP) jcol[jj * BS_JCAP + (int)(e - j0)] = c;
+                const int cw = c - c_lo;
+                if ((unsigned)cw < (unsigned)kwin) atomicOr(&mask32[cw >> 1], 1u << (jj + 16 * (cw & 1)));
+            }
+        }
+        __syncthreads();
+
+        // ---- batches of i-rows [ra, rb); a single row may be sliced further to entries [cs0, cs1)
+        int ra = 0, batch = 16;
+        long long cs0 = -1, cs1 = -1;                                  // slice of row ra (cs0 < 0: whole rows)
+        bool row_started = false;                                      // an earlier slice of row ra has been stored
+        while (ra < 16) {
+            const int rb = cs0 >= 0 ? ra + 1 : min(16, ra + batch);
+            const int nrows = rb - ra;
+            cnt[tid] = 0;
+            fillc[tid] = 0;
+            __syncthreads();
+            for (int r = 0; r < nrows; ++r) {
+                const int ii = ra + r;
+                long long e0 = csr.ptr[rowI0 + ii], e1 = csr.ptr[rowI0 + ii + 1];
+                if (cs0 >= 0) { e0 = cs0; e1 = cs1; }
+                const unsigned keep = diag_block ? (0xffffu << ii) & 0xffffu : 0xffffu;   // pairs below the diagonal are never read
+                for (long long e = e0 + tid; e < e1; e += BS_THREADS) {
+                    const int cw = csr.col[e] - c_lo;
+                    if ((unsigned)cw < (unsigned)kwin) {
+                        unsigned m = (mask32[cw >> 1] >> (16 * (cw & 1))) & keep;
+                        while (m) { const int jj = __ffs(m) - 1; m &= m - 1; atomicAdd(&cnt[r * 16 + jj], 1); }
+                    }
+                }
+            }
+            __syncthreads();
+            {
+                const int padded = tid < nrows * 16 ? (cnt[tid] + 3) & ~3 : 0;
+                int off, total;
+                cub::BlockScan<int, BS_THREADS>(scan_tmp).ExclusiveSum(padded, off, total);
+                base[tid] = off;
+                if (tid == 0) base[256] = total;
+            }
+            __syncthreads();
+            if (base[256] > BS_POOL) {                                 // uniform decision: shrink the batch and retry
+                if (nrows > 1) batch = nrows / 2;
+                else {
+                    if (cs0 < 0) { cs0 = csr.ptr[rowI0 + ra]; cs1 = csr.ptr[rowI0 + ra + 1]; }
+                    cs1 = cs0 + (cs1 - cs0) / 2;
+                }
+                __syncthreads();
+                continue;
+            }
+            for (int r = 0; r < nrows; ++r) {
+                const int ii = ra + r;
+                long long e0 = csr.ptr[rowI0 + ii], e1 = csr.ptr[rowI0 + ii + 1];
+                if (cs0 >= 0) { e0 = cs0; e1 = cs1; }
+                const unsigned keep = diag_block ? (0xffffu << ii) & 0xffffu : 0xffffu;
+                for (long long e = e0 + tid; e < e1; e += BS_THREADS) {
+                    const int c = csr.col[e];
+                    const int cw = c - c_lo;
+                    if ((unsigned)cw < (unsigned)kwin) {
+                        unsigned m = (mask32[cw >> 1] >> (16 * (cw & 1))) & keep;
+                        if (m) {
+                            const unsigned long long fi = ((unsigned long long)csr.hi[e] << BS_LO_BITS) | csr.lo[e];
+                            while (m) {
+                                const int jj = __ffs(m) - 1;
+                                m &= m - 1;
+                                const long long j0 = csr.ptr[rowJ0 + jj];
+                                const int pos = bs_find(jcol + jj * BS_JCAP, min(jlen[jj], BS_JCAP), csr.col + j0, jlen[jj], c);
+                                const unsigned long long fj = ((unsigned long long)csr.hi[j0 + pos] << BS_LO_BITS) | csr.lo[j0 + pos];
+                                const unsigned long long f = min(fi, fj);
+                                const int q = r * 16 + jj;
+                                pool[base[q] + atomicAdd(&fillc[q], 1)] =
+                                    make_uint2((uint32_t)cw | ((uint32_t)(f & 0xffffu) << 16), (uint32_t)(f >> BS_LO_BITS));
+                            }
+                        }
+                    }
+                }
+            }
+            // pad every list to a multiple of 4 entries with (column 0, value 0): the reduce loop runs 4 entries a step
+            if (tid < nrows * 16) {
+                const int end = tid + 1 < 256 ? base[tid + 1] : base[256];
+                for (int k = base[tid] + cnt[tid]; k < end; ++k) pool[k] = make_uint2(0u, 0u);
+            }
+            __syncthreads();
+            // ---- reduce: lane = one replicate, slot s takes i-rows s, s + PP, ... of the batch; per i-row the 16 lists
+            // are walked 4 entries a step (one byte of the transposed multiplicities per entry) into 16 accumulator
+            // pairs, then the 16 sums leave as one whole 128-byte line of the replicate's workspace
+            const bool first = win == 0 && !row_started;
+            const uint8_t* wTl = wT + (size_t)c_lo * w_ld + rep0;       // this lane's column of the window's multiplicities
+            const uint32_t wld32 = (uint32_t)w_ld;                     // window columns x row stride < 2^32 (checked at launch)
+            for (int r = slot; r < nrows; r += PP) {
+                unsigned long long ahi[16];
+                uint32_t alo[16];
+                const int beg = base[r * 16], end = r * 16 + 16 < 256 ? base[r * 16 + 16] : base[256];
+                // the multiplicity bytes of step e + 4 are in flight while step e multiplies; the entries themselves are
+                // re-read from shared memory (two LDS.128 a step) rather than carried in registers
+                uint32_t wb[4];
+                if (beg < end) {
+                    const uint4 p0 = *reinterpret_cast<const uint4*>(pool + beg), p1 = *reinterpret_cast<const uint4*>(pool + beg + 2);
+                    wb[0] = __ldg(wTl + (p0.x & 0xffffu) * wld32);
+                    wb[1] = __ldg(wTl + (p0.z & 0xffffu) * wld32);
+                    wb[2] = __ldg(wTl + (p1.x & 0xffffu) * wld32);
+                    wb[3] = __ldg(wTl + (p1.z & 0xffffu) * wld32);
+                }
+                int e = beg;
+#pragma unroll
+                for (int a = 0; a < 16; ++a) {
+                    const int ne = r * 16 + a + 1 < 256 ? base[r * 16 + a + 1] : base[256];
+                    unsigned long long h = 0ull;
+                    uint32_t l = 0u;
+                    for (; e < ne; e += 4) {                           // lists are padded: a whole step belongs to one pair
+                        const uint32_t w0 = wb[0], w1 = wb[1], w2 = wb[2], w3 = wb[3];
+                        if (e + 4 < end) {
+                            const uint4 n0 = *reinterpret_cast<const uint4*>(pool + e + 4), n1 = *reinterpret_cast<const uint4*>(pool + e + 6);
+                            wb[0] = __ldg(wTl + (n0.x & 0xffffu) * wld32);
+                            wb[1] = __ldg(wTl + (n0.z & 0xffffu) * wld32);
+                            wb[2] = __ldg(wTl + (n1.x & 0xffffu) * wld32);
+                            wb[3] = __ldg(wTl + (n1.z & 0xffffu) * wld32);
+                        }
+                        const uint4 c0 = *reinterpret_cast<const uint4*>(pool + e), c1 = *reinterpret_cast<const uint4*>(pool + e + 2);
+                        h += (unsigned long long)c0.y * w0;
+                        h += (unsigned long long)c0.w * w1;
+                        h += (unsigned long long)c1.y * w2;
+                        h += (unsigned long long)c1.w * w3;
+                        l += (c0.x >> 16) * w0 + (c0.z >> 16) * w1 + (c1.x >> 16) * w2 + (c1.z >> 16) * w3;
+                    }
+                    ahi[a] = h;
+                    alo[a] = l;
+                }
+                // exact integers -> fp64; the first pass over a row stores, later ones (row slices, further column
+                // windows) add: same thread, program order, deterministic
+                if ((first || beg < end) && rep0 < nb_total) {
+                    double* o = wsblk + (size_t)rep0 * ws_rep_stride + ((ra + r) << 4);
+#pragma unroll
+                    for (int a = 0; a < 16; a += 2) {
+                        double v0 = (double)ahi[a] * q_hi + (double)alo[a] * quantum;
+                        double v1 = (double)ahi[a + 1] * q_hi + (double)alo[a + 1] * quantum;
+                        if (!first) {
+                            const double2 p = *reinterpret_cast<const double2*>(o + a);
+                            v0 += p.x; v1 += p.y;
+                        }
+                        *reinterpret_cast<double2*>(o + a) = make_double2(v0, v1);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- advance
+            if (cs0 >= 0 && cs1 < csr.ptr[rowI0 + ra + 1]) {            // more slices of this row
+                cs0 = cs1;
+                cs1 = csr.ptr[rowI0 + ra + 1];
+                row_started = true;
+            } else {
+                ra = rb;
+                batch = 16 - ra;
+                cs0 = cs1 = -1;
+                row_started = false;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- CSR of the fixed-point table
+// entries: x > 0 (NaN rows are flagged separately by prepare_table; negative tables do not come here)
+__device__ __forceinline__ unsigned long long bs_fixed48(double x, double scale) {
+    return x > 0.0 ? (unsigned long long)__double2ull_rn(fmin(x * scale, 281474976710655.0)) : 0ull;
+}
+
+__global__ void bs_count_kernel(const double* __restrict__ tab, long long n, long long k, long long ld, double scale,
+                                long long* __restrict__ cnt) {
+    const long long r = blockIdx.x;
+    int c = 0;
+    if (r < n) {
+        const double* row = tab + r * ld;
+        for (long long q = threadIdx.x; q < k; q += blockDim.x) c += (bs_fixed48(row[q], scale) != 0ull);
+    }
+    __shared__ int red[8];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        cnt[r] = t;
+    }
+}
+
+// one warp per row, ballot compaction keeps the columns ascending.  grid = ceil(n / 8), block = 256
+__global__ void bs_fill_kernel(const double* __restrict__ tab, long long n, long long k, long long ld, double scale,
+                               const long long* __restrict__ ptr, int* __restrict__ col, uint32_t* __restrict__ hi,
+                               uint16_t* __restrict__ lo) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const double* row = tab + r * ld;
+    long long o = ptr[r];
+    for (long long k0 = 0; k0 < k; k0 += 32) {
+        const unsigned long long f = (k0 + lane < k) ? bs_fixed48(row[k0 + lane], scale) : 0ull;
+        const unsigned hit = __ballot_sync(0xffffffffu, f != 0ull);
+        if (f) {
+            const long long d = o + __popc(hit & ((1u << lane) - 1));
+            col[d] = (int)(k0 + lane);
+            hi[d] = (uint32_t)(f >> BS_LO_BITS);
+            lo[d] = (uint16_t)(f & 0xffffu);
+        }
+        o += __popc(hit);
+    }
+}
+
+// per-column hit counts (postings lengths): sum_c cnt_c (cnt_c + 1) / 2 = total co-present (pair, column) cells
+__global__ void bs_colcount_kernel(const int* __restrict__ col, long long nnz, int* __restrict__ colcnt) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&colcnt[col[e]], 1);
+}
+__global__ void bs_cells_kernel(const int* __restrict__ colcnt, long long k, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < k; c += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long v = (unsigned long long)colcnt[c];
+        s += v * (v + 1) / 2;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// int32 multiplicities [nb][k] -> transposed uint8 [k_pad][w_ld] (zero padded).  32 x 32 tiles through shared memory.
+__global__ void bs_weights_transpose_kernel(const int* __restrict__ w, long long nb, long long k, long long k_pad,
+                                            long long w_ld, uint8_t* __restrict__ out, int* __restrict__ overflow) {
+    __shared__ uint8_t t[32][33];
+    const long long c0 = (long long)blockIdx.x * 32, b0 = (long long)blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const long long b = b0 + y, c = c0 + threadIdx.x;
+        int v = (b < nb && c < k) ? w[b * k + c] : 0;
+        if (v < 0 || v > 255) { atomicExch(overflow, 1); v = 0; }
+        t[y][threadIdx.x] = (uint8_t)v;
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const long long c = c0 + y, b = b0 + threadIdx.x;
+        if (c < k_pad && b < w_ld) out[c * w_ld + b] = t[threadIdx.x][y];
+    }
+}
+
+// sum_c w[b][c] must stay <= 2^(32 - BS_LO_BITS): the low limbs accumulate in 32 bits.  grid = nb
+__global__ void bs_wsum_check_kernel(const int* __restrict__ w, long long k, int* __restrict__ overflow) {
+    const int* row = w + (long long)blockIdx.x * k;
+    long long s = 0;
+    for (long long c = threadIdx.x; c < k; c += blockDim.x) s += row[c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ long long red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        if (t > (1ll << (32 - BS_LO_BITS))) atomicExch(overflow, 2);
+    }
+}
+
+// ---------------------------------------------------------------------------------- host
+struct BootSparse {
+    long long* ptr = nullptr;
+    int* col = nullptr;
+    uint32_t* hi = nullptr;
+    uint16_t* lo = nullptr;
+    long long nnz = 0;
+    unsigned long long cells = 0;     // co-present (pair incl. diagonal, column) cells
+    double quantum = 0.0;             // value of one unit of the 48-bit fixed point
+    size_t bytes = 0;
+};
+
+void boot_sparse_free(BootSparse* s) {
+    if (!s) return;
+    cudaFree(s->ptr); cudaFree(s->col); cudaFree(s->hi); cudaFree(s->lo);
+    delete s;
+}
+
+size_t boot_sparse_bytes(const BootSparse* s) { return s ? s->bytes : 0; }
+long long boot_sparse_nnz(const BootSparse* s) { return s ? s->nnz : 0; }
+unsigned long long boot_sparse_cells(const BootSparse* s) { return s ? s->cells : 0; }
+
+// CSR (48-bit fixed point) of the float64 table [n][k] (row stride ld), padded with empty rows to n_pad;
+// max_value = largest entry of the table (> 0, finite; the caller has checked there are no negative entries)
+int boot_sparse_build(gv2_ctx* ctx, const double* tab, int64_t n, int64_t k, int64_t ld, int64_t n_pad, int64_t k_pad,
+                      double max_value, BootSparse** out) {
+    *out = nullptr;
+    BootSparse* s = new BootSparse();
+    long long* cnt = nullptr;
+    int* colcnt = nullptr;
+    unsigned long long* cells = nullptr;
+    void* tmp = nullptr;
+    auto fail = [&](cudaError_t e, const char* what) {
+        cudaFree(cnt); cudaFree(colcnt); cudaFree(cells); cudaFree(tmp);
+        boot_sparse_free(s);
+        return gv2_fail(ctx, e == cudaErrorMemoryAllocation ? GV2_ERR_NOMEM : GV2_ERR_CUDA, "boot_sparse_build (%s): %s", what, cudaGetErrorString(e));
+    };
+    // x -> rint(x * scale) < 2^48: the (1 - 2^-30) keeps the largest entry below 2^48 after rounding
+    const double scale = max_value > 0.0 ? 281474976710656.0 * (1.0 - 9.313225746154785e-10) / max_value : 0.0;
+    s->quantum = scale > 0.0 ? 1.0 / scale : 0.0;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&cnt, (size_t)(n_pad + 1) * sizeof(long long))) != cudaSuccess) return fail(e, "counts");
+    if ((e = cudaMalloc((void**)&s->ptr, (size_t)(n_pad + 1) * sizeof(long long))) != cudaSuccess) return fail(e, "row pointers");
+    if ((e = cudaMemsetAsync(cnt, 0, (size_t)(n_pad + 1) * sizeof(long long), ctx->stream)) != cudaSuccess) return fail(e, "memset");
+    bs_count_kernel<<<(unsigned)n_pad, 256, 0, ctx->stream>>>(tab, n, k, ld, scale, cnt);
+    ctx->launches++;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, s->ptr, (int)(n_pad + 1), ctx->stream);
+    if ((e = cudaMalloc(&tmp, tb ? tb : 1)) != cudaSuccess) return fail(e, "scan scratch");
+    cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, s->ptr, (int)(n_pad + 1), ctx->stream);
+    ctx->launches++;
+    if ((e = cudaMemcpyAsync(&s->nnz, s->ptr + n_pad, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return fail(e, "nnz");
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "scan");
+    const size_t nz = (size_t)std::max<long long>(1, s->nnz);
+    if ((e = cudaMalloc((void**)&s->col, nz * sizeof(int))) != cudaSuccess) return fail(e, "columns");
+    if ((e = cudaMalloc((void**)&s->hi, nz * sizeof(uint32_t))) != cudaSuccess) return fail(e, "values");
+    if ((e = cudaMalloc((void**)&s->lo, nz * sizeof(uint16_t))) != cudaSuccess) return fail(e, "values");
+    if (n > 0) {
+        bs_fill_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(tab, n, k, ld, scale, s->ptr, s->col, s->hi, s->lo);
+        ctx->launches++;
+    }
+    if ((e = cudaMalloc((void**)&colcnt, (size_t)k_pad * sizeof(int))) != cudaSuccess) return fail(e, "column counts");
+    if ((e = cudaMalloc((void**)&cells, sizeof(unsigned long long))) != cudaSuccess) return fail(e, "cells");
+    cudaMemsetAsync(colcnt, 0, (size_t)k_pad * sizeof(int), ctx->stream);
+    cudaMemsetAsync(cells, 0, sizeof(unsigned long long), ctx->stream);
+    if (s->nnz) {
+        bs_colcount_kernel<<<(unsigned)std::min<long long>(4096, (s->nnz + 255) / 256), 256, 0, ctx->stream>>>(s->col, s->nnz, colcnt);
+        ctx->launches++;
+    }
+    bs_cells_kernel<<<(unsigned)std::min<long long>(1024, (k_pad + 255) / 256), 256, 0, ctx->stream>>>(colcnt, k_pad, cells);
+    ctx->launches++;
+    if ((e = cudaMemcpyAsync(&s->cells, cells, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return fail(e, "cells");
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "column statistics");
+    cudaFree(cnt); cudaFree(colcnt); cudaFree(cells); cudaFree(tmp);
+    s->bytes = (size_t)(n_pad + 1) * sizeof(long long) + nz * (sizeof(int) + sizeof(uint32_t) + sizeof(uint16_t));
+    *out = s;
+    return GV2_OK;
+}
+
+static int bs_lanes(int64_t nb) { return nb <= 64 ? 64 : nb <= 128 ? 128 : 256; }
+static int64_t bs_wld(int64_t nb) {
+    const int64_t per = bs_lanes(nb);
+    return (nb + per - 1) / per * per;
+}
+size_t boot_sparse_scratch_bytes(int64_t k_pad, int64_t nb) { return (size_t)k_pad * bs_wld(nb); }
+
+// ws: fp64 [nb][ntl][128*128] (gj_ws_index layout), tiles [tile_begin, tile_end); w: int32 [nb][k] (device).
+// *overflow_flag is set to 1 when a multiplicity exceeds 255 and to 2 when a replicate's multiplicities sum to
+// more than 65536 (neither can happen for a bootstrap resample of k <= 65536 columns).
+int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t k_pad, int64_t tile_begin,
+                       int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* wT_scratch, int* overflow_flag,
+                       double* ws) {
+    const int64_t ntl = tile_end - tile_begin;
+    if (ntl <= 0 || nb <= 0) return GV2_OK;
+    if (ntl > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "boot_sparse_launch: more than 65535 genome tiles per launch");
+    const int rl = bs_lanes(nb);
+    const int64_t w_ld = bs_wld(nb);
+    uint8_t* wT = (uint8_t*)wT_scratch;
+    dim3 gt((unsigned)((k_pad + 31) / 32), (unsigned)((w_ld + 31) / 32)), bt(32, 8);
+    bs_weights_transpose_kernel<<<gt, bt, 0, ctx->stream>>>(w, nb, k, k_pad, w_ld, wT, overflow_flag);
+    GV2_LAUNCH_CHECK(ctx);
+    bs_wsum_check_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(w, k, overflow_flag);
+    GV2_LAUNCH_CHECK(ctx);
+    static bool attr_done = false;
+    if (!attr_done) {
+        const int mx = (int)bs_smem_bytes(BS_WIN);
+        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+        attr_done = true;
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ctx->timing) {
+        GV2_CUDA(ctx, cudaEventCreate(&ev0));
+        GV2_CUDA(ctx, cudaEventCreate(&ev1));
+        GV2_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    BsCsr csr{s->ptr, s->col, s->hi, s->lo};
+    const int nt = (int)(n_pad / GV2_TILE), nwin = (int)((k_pad + BS_WIN - 1) / BS_WIN);
+    const int kwin = (int)std::min<int64_t>(k_pad, BS_WIN);            // k_pad is a multiple of 128
+    const size_t smem = bs_smem_bytes(kwin);
+    const long long rep_stride = (long long)ntl * GV2_TILE * GV2_TILE;
+    dim3 grid(64, (unsigned)ntl, (unsigned)(w_ld / rl));
+    if (rl == 64)
+        boot_sparse_kernel<64><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, ws);
+    else if (rl == 128)
+        boot_sparse_kernel<128><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, ws);
+    else
+        boot_sparse_kernel<256><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, ws);
+    GV2_LAUNCH_CHECK(ctx);
+    if (ctx->timing) {
+        GV2_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+        ctx->timed.emplace_back(ev0, ev1);
+    }
+    return GV2_OK;
+}

@@ -52,14 +52,69 @@ __host__ __device__ inline void gv2_tile_coords(long long t, int nt, int* bi, in
     *bj = r + (int)(t - ((long long)r * nt - (long long)r * (r - 1) / 2));
 }
 
+struct GjComp {
+    const double* ws;        // [nb][ksplit][ntl][128*128] or null
+    const double* rowsum;    // [nb][n]
+    const unsigned char* nan;  // [nb][n] or null
+    int ksplit;
+    long long b_stride_ws;   // elements between replicates in ws (0 = shared by all replicates)
+    long long b_stride_row;  // elements between replicates in rowsum (0 = shared)
+    long long b_stride_nan;  // elements between replicates in nan (0 = shared)
+};
+
+// Fused tail of the replicate path: the tile kernel that forms the GOM-signature pair sums also does the epilogue
+// (clean / combine with the PPHMM component / clamp / power / 1 - S / mirror), so the GOM pair sums never travel
+// through HBM and the separate epilogue pass disappears.
+struct GjFuse {
+    GjComp P;                // PPHMM component (pair sums from the replicate kernels), ws == null for scheme G
+    const double* g_rowsum;  // [nb][n] row sums of this kernel's own table
+    const unsigned char* g_nan;
+    long long g_stride_row, g_stride_nan;
+    long long n;
+    int scheme, out_kind;
+    double pw;
+    double* out;             // [nb][n][n]
+    long long out_b_stride;
+};
+#define GJ_STAGE_LD 129      // doubles per staged row of the mirror transpose (64 x 129 x 8 B = 66 KB of the idle ring)
+
+// 1/sqrt(x) and 1/x to full double precision without the branchy library routines: fp32 seed (22 good bits) and three
+// Newton steps in fp64.  x must be positive and inside the fp32 range (pair sums and their products are; the callers
+// send anything else to the library routine).
+__device__ __forceinline__ double gj_rsqrt(double x) {
+    double r = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    r = r * fma(-hx * r, r, 1.5);
+    r = r * fma(-hx * r, r, 1.5);
+    r = r * fma(-hx * r, r, 1.5);
+    return r;
+}
+__device__ __forceinline__ double gj_rcp(double x) {
+    double r = (double)(1.0f / (float)x);
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    return r;
+}
+__device__ __forceinline__ bool gj_fast_range(double x) { return x > 1e-30 && x < 1e30; }
+
+__device__ __forceinline__ double gj_ratio(double smin, double si, double sj, bool diag, bool isnan_row) {
+    if (diag) smin = si;                           // diagonal: sum(min) == sum(a) exactly
+    const double smax = si + sj - smin;
+    double v = (smax == 0.0) ? 0.0 : smin / smax;  // `if not sum(max) == 0 else 0`, similarity_matrix_constructor.py:168
+    if (isnan_row) v = nan("");
+    if (isnan(v) || v < 0.0) v = 0.0;              // :204-205
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: per-tile sum_c w_c * min(T[i,c], T[j,c])   (w == 1 when !WEIGHTED)
 // grid = (tiles in [tile_begin, tile_end), ksplit, nb);  ws[((b*ksplit+ks)*ntl + t)][128*128]
-template <bool WEIGHTED>
+template <bool WEIGHTED, bool FUSED>
 __global__ void __launch_bounds__(GJ_THREADS, 2)
 gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int kblocks_total,
                    int nt, long long tile_begin, const float* __restrict__ wts, long long w_stride,
-                   double* __restrict__ ws) {
+                   double* __restrict__ ws, const GjFuse fz) {
     extern __shared__ __align__(16) float smem[];
     float* sA = smem;                                         // [STAGES][128][GJ_LDS]
     float* sB = sA + GJ_STAGES * GV2_TILE * GJ_LDS;           // [STAGES][128][GJ_LDS]
@@ -116,6 +171,7 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
                 // Each address is only ever touched by this one thread, in program order, so the
                 // fp64 sum is formed in slab order and is deterministic.
                 if (first) wtile[o] = (double)acc[m][n];
+                else if (FUSED) wtile[o] += (double)acc[m][n];         // read back below by this same thread: no RED
                 else atomicAdd(&wtile[o], (double)acc[m][n]);
                 acc[m][n] = 0.f;
             }
@@ -176,13 +232,106 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
             }
         }
         in_slab += GV2_BK;
-        if (in_slab >= GJ_SLAB) {
+        if (in_slab >= GJ_SLAB && !(FUSED && it + 1 == nkb)) {   // fused: the last slab stays in registers
             flush(first);
             first = false;
             in_slab = 0;
         }
     }
-    if (in_slab > 0 || first) flush(first);
+    if (!FUSED) {
+        if (in_slab > 0 || first) flush(first);
+        return;
+    }
+    // ------------------------------------------------------------------ fused epilogue (ksplit == 1)
+    cp_async_wait<0>();
+    const long long n = fz.n;
+    const double* g_rs = fz.g_rowsum + b * fz.g_stride_row;
+    const unsigned char* g_nf = fz.g_nan ? fz.g_nan + b * fz.g_stride_nan : nullptr;
+    const bool has_p = fz.P.ws != nullptr;
+    const double* p_ws = has_p ? fz.P.ws + b * fz.P.b_stride_ws + (long long)blockIdx.x * (GV2_TILE * GV2_TILE) : nullptr;
+    const double* p_rs = has_p ? fz.P.rowsum + b * fz.P.b_stride_row : nullptr;
+    const unsigned char* p_nf = (has_p && fz.P.nan) ? fz.P.nan + b * fz.P.b_stride_nan : nullptr;
+    double* o = fz.out + b * fz.out_b_stride;
+    double* stage = reinterpret_cast<double*>(smem);                 // [64][GJ_STAGE_LD]
+    double gsj[8], psj[8];
+    bool nanj_g[8], nanj_p[8];
+#pragma unroll
+    for (int nn = 0; nn < 8; ++nn) {
+        const long long gj = (long long)bj * GV2_TILE + tx + 16 * nn;
+        const bool ok = gj < n;
+        gsj[nn] = ok ? g_rs[gj] : 0.0;
+        psj[nn] = (ok && has_p) ? p_rs[gj] : 0.0;
+        nanj_g[nn] = ok && g_nf && g_nf[gj];
+        nanj_p[nn] = ok && p_nf && p_nf[gj];
+    }
+    for (int half = 0; half < 2; ++half) {
+        __syncthreads();                                             // ring (first half) / previous stage contents are dead
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) {
+            const int m = half * 4 + mm;
+            const int r = ty + 16 * m;
+            const long long gi = (long long)bi * GV2_TILE + r;
+            const bool oki = gi < n;
+            const double gsi = oki ? g_rs[gi] : 0.0, psi = (oki && has_p) ? p_rs[gi] : 0.0;
+            const bool gnan_i = oki && g_nf && g_nf[gi], pnan_i = oki && p_nf && p_nf[gi];
+            // all of this row's loads first (16 independent 8-byte loads in flight), then the arithmetic
+            double gprev[8], pv[8];
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) {
+                const int c = tx + 16 * nn;
+                gprev[nn] = first ? 0.0 : wtile[(size_t)((m * 8 + nn) * 256 + tid)];
+                // diagonal tiles: the replicate kernels leave the entries below the diagonal unwritten
+                const int rr = (bi == bj && r > c) ? c : r, cc = (bi == bj && r > c) ? r : c;
+                pv[nn] = has_p ? p_ws[gj_ws_index(rr, cc)] : 0.0;
+            }
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) {
+                const int c = tx + 16 * nn;
+                const long long gj = (long long)bj * GV2_TILE + c;
+                double sv = 0.0;
+                if (oki && gj < n) {
+                    // GJ = sum(min) / sum(max), 0 when sum(max) == 0 (:168), NaN and negatives cleaned to 0 (:204-205), then
+                    // (P * G) ** 0.5 (:214) -- as ONE reciprocal square root: sqrt(Np Ng / (Dp Dg)) = |Np Ng| rsqrt(Np Ng Dp Dg)
+                    const bool diag = gi == gj;
+                    const double ng = diag ? gsi : gprev[nn] + (double)acc[m][nn];      // diagonal: sum(min) == sum(a) exactly
+                    const double dg = gsi + gsj[nn] - ng;
+                    bool zero = gnan_i || nanj_g[nn] || dg == 0.0 || ((ng < 0.0) != (dg < 0.0));
+                    double num = ng, den = dg;
+                    if (has_p) {
+                        const double np_ = diag ? psi : pv[nn];
+                        const double dp = psi + psj[nn] - np_;
+                        zero = zero || pnan_i || nanj_p[nn] || dp == 0.0 || ((np_ < 0.0) != (dp < 0.0));
+                        num *= np_;
+                        den *= dp;
+                    }
+                    if (zero || num == 0.0) sv = 0.0;
+                    else if (num == den) sv = 1.0;                   // diagonal, duplicate genomes: exactly 1
+                    else if (has_p) {
+                        const double x = num * den;
+                        sv = fabs(num) * (gj_fast_range(x) ? gj_rsqrt(x) : rsqrt(x));
+                    } else {
+                        sv = num * (gj_fast_range(den) ? gj_rcp(den) : 1.0 / den);
+                    }
+                    if (sv < 0.0) sv = 0.0;                          // :224
+                    if (fz.pw != 1.0) sv = pow(sv, fz.pw);           // :226
+                    if (fz.out_kind == GV2_OUT_DISTANCE) {           // pl1_graphs.py:52-53
+                        sv = 1.0 - sv;
+                        if (sv < 0.0) sv = 0.0;
+                    }
+                    o[gi * n + gj] = sv;
+                }
+                stage[(ty + 16 * mm) * GJ_STAGE_LD + c] = sv;
+            }
+        }
+        if (bi == bj) continue;                                      // diagonal tiles hold both triangles already
+        __syncthreads();
+        // mirror: row (bj*128 + c), columns bi*128 + 64*half + [0, 64): 64 consecutive doubles per staged column
+        for (int q = tid; q < 64 * GV2_TILE; q += GJ_THREADS) {
+            const int c = q >> 6, rl = q & 63;
+            const long long gj = (long long)bj * GV2_TILE + c, gi = (long long)bi * GV2_TILE + half * 64 + rl;
+            if (gi < n && gj < n) o[gj * n + gi] = stage[rl * GJ_STAGE_LD + c];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -265,16 +414,6 @@ __global__ void weights_to_float_kernel(const int* __restrict__ w, long long k, 
 // K3 epilogue: NaN/negative clean, scheme combine, clamp, **p, optional 1-S, mirror.
 // similarity_matrix_constructor.py:201-226, pl1_graphs.py:52-53.
 // One block per 32x32 sub-block of a 128x128 tile: grid = (tiles*16, nb), block = (32, 8).
-struct GjComp {
-    const double* ws;        // [nb][ksplit][ntl][128*128] or null
-    const double* rowsum;    // [nb][n]
-    const unsigned char* nan;  // [nb][n] or null
-    int ksplit;
-    long long b_stride_ws;   // elements between replicates in ws (0 = shared by all replicates)
-    long long b_stride_row;  // elements between replicates in rowsum (0 = shared)
-    long long b_stride_nan;  // elements between replicates in nan (0 = shared)
-};
-
 __device__ __forceinline__ double gj_value(const GjComp& c, long long b, long long ntl,
                                            long long t, int r, int cc, long long gi, long long gj) {
     // diagonal tiles: always read the upper-triangle entry (the tensor-core path leaves sub-tiles that lie
@@ -452,17 +591,49 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
     static bool attr_done = false;
     size_t smem = gj_smem_bytes();
     if (!attr_done) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     dim3 grid((unsigned)ntl, (unsigned)ksplit, (unsigned)nb);
     const int nt = (int)(n_pad / GV2_TILE);
     const int kblocks = (int)(k_pad / GV2_BK);
     if (w)
-        gj_min_tile_kernel<true><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, w, k_pad, ws);
+        gj_min_tile_kernel<true, false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, w, k_pad, ws, GjFuse{});
     else
-        gj_min_tile_kernel<false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, nullptr, 0, ws);
+        gj_min_tile_kernel<false, false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, nullptr, 0, ws, GjFuse{});
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+static GjComp to_comp(const gv2_gj_component* c);
+
+// Fused GOM pair sums + epilogue for replicates [0, nb): one table per replicate (tab_stride), all tiles [0, ntl),
+// schemes G and PG.  ws: scratch [nb][ntl][128*128] for the slab promotion (touched only when k_pad > GJ_SLAB).
+int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k_pad, int64_t nb,
+                    const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
+                    double* ws, double* out, int64_t out_replicate_stride) {
+    if (scheme != GV2_SCHEME_G && scheme != GV2_SCHEME_PG) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: scheme %d", scheme);
+    if (!tab || !comp_g || !comp_g->rowsums || !out || (scheme == GV2_SCHEME_PG && (!comp_p || !comp_p->min_sums || !comp_p->rowsums || comp_p->ksplit != 1)))
+        return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: bad arguments");
+    const int64_t ntl = gv2_num_tiles(n);
+    if (ntl == 0 || nb <= 0) return GV2_OK;
+    if (nb > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: nb > 65535");
+    static bool attr_done = false;
+    const size_t smem = gj_smem_bytes();
+    if (!attr_done) {
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    GjFuse fz{};
+    if (scheme == GV2_SCHEME_PG) fz.P = to_comp(comp_p);
+    fz.g_rowsum = comp_g->rowsums; fz.g_nan = comp_g->nanflags;
+    fz.g_stride_row = comp_g->replicate_stride_rows; fz.g_stride_nan = comp_g->replicate_stride_nan;
+    fz.n = n; fz.scheme = scheme; fz.out_kind = out_kind; fz.pw = power; fz.out = out; fz.out_b_stride = out_replicate_stride;
+    dim3 grid((unsigned)ntl, 1, (unsigned)nb);
+    gj_min_tile_kernel<false, true><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, (int)(k_pad / GV2_BK), (int)(n_pad / GV2_TILE),
+                                                                             0, nullptr, 0, ws, fz);
     GV2_LAUNCH_CHECK(ctx);
     return GV2_OK;
 }

@@ -353,6 +353,37 @@ def test_tensor_core_path_is_exact_integer_arithmetic(eng):
     assert np.all(S[:, 3, 10] == 1.0)
 
 
+@pytest.mark.parametrize("n,p,dens,nb", [(150, 700, 0.1, 5), (200, 1500, 0.6, 24), (131, 40000, 0.02, 300),
+                                         (40, 3000, 1.0, 9), (300, 900, 0.03, 600)])
+def test_replicate_paths_agree(eng, monkeypatch, n, p, dens, nb):
+    """The three replicate paths (CSR walk of sparse tables, tensor-core contraction, fp32 tile kernel) against the
+    weighted oracle and each other.  Rows longer than one 256-entry segment, a table wider than one 32768-column
+    window, empty and duplicate genomes, diagonal blocks, and all three replicate-lane configurations."""
+    t = synth.make_tables(n, p, 5, dens, seed=n + nb)
+    t.sig[7] = 0.0
+    t.sig[n - 1] = t.sig[2]
+    rng = np.random.default_rng(nb)
+    w = np.stack([np.bincount(rng.integers(0, p, p), minlength=p) for _ in range(nb)]).astype(np.int32)
+    out = {}
+    for path in ("sparse", "mma", "fp32"):
+        monkeypatch.setenv("GV2_BOOT_PATH", path)
+        out[path] = eng.bootstrap(t.sig, None, None, 0, w, "P", 1.0, distance=False)
+    monkeypatch.delenv("GV2_BOOT_PATH")
+    for b in sorted({0, nb // 2, nb - 1}):
+        ref = O.similarity_mat_fast(t.sig, None, None, 0, "P", 1.0, w=w[b])
+        close(out["sparse"][b], ref, rtol=1e-12)                         # 48-bit fixed point, exact integer sums
+        close(out["mma"][b], ref)                                            # 32-bit fixed point: max(T) * 2^-33 per element
+        close(out["fp32"][b], ref)
+    # duplicate genomes: the integer sums cancel exactly unless a dense row had to be sliced or the table spans two
+    # column windows (partial sums then meet in fp64)
+    dup = out["sparse"][:, 2, n - 1]
+    assert np.all(dup == 1.0) if dens <= 0.1 and p <= 32768 else np.all(np.abs(dup - 1.0) <= 2e-15)
+    bad = np.argwhere(out["sparse"][:, 7, :] != 0.0)
+    assert len(bad) == 0, f"empty genome: similarity must be exactly 0; first offenders (replicate, j): {bad[:5].tolist()}"
+    for b in (0, nb - 1):
+        assert np.array_equal(out["sparse"][b], out["sparse"][b].T)
+
+
 def test_device_primitives_packed_tiles_roundtrip(eng):
     """C-ABI device-pointer primitives (what the multi-GPU path uses): prepare -> min sums for two tile ranges ->
     packed epilogue -> unpack == the one-shot host entry point."""
