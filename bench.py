@@ -303,9 +303,14 @@ def main():
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = int(lib.gv2_launch_count(ctx)) - l0
-    k_ms, k_n = C.c_double(0.0), C.c_int64(0)
-    ck(lib.gv2_timing_read(ctx, C.byref(k_ms), C.byref(k_n)))
+    times = {}
+    for name, kind in (("pairs", _lib.TIME_PAIRSUMS), ("tail", _lib.TIME_TAIL), ("gom", _lib.TIME_GOM)):
+        k_ms, k_n = C.c_double(0.0), C.c_int64(0)
+        ck(lib.gv2_timing_read_kind(ctx, kind, C.byref(k_ms), C.byref(k_n)))
+        times[name] = (k_ms.value, k_n.value)
     lib.gv2_timing_enable(ctx, 0)
+    path = _lib.PATH_NAMES.get(int(lib.gv2_job_replicate_path(job)), "?")
+    cells = int(lib.gv2_job_copresent_cells(job))
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -322,7 +327,7 @@ def main():
     e2e = None
     peaks, peak_kind = load_peaks()
     if rank == 0:
-        roofline = make_roofline(k_ms.value, k_n.value, steps, n, p, len(my_reps), ms, peaks, peak_kind)
+        roofline = make_roofline(times, path, cells, steps, n, p, g, len(my_reps), ms, peaks, peak_kind)
     # ---- end to end through the host-pointer C ABI
     if not args.no_e2e:
         e2e = measure_e2e(lib, ctx, ck, t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist if world > 1 else None, torch,
@@ -331,7 +336,10 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "u32 fixed-point min -> u8 digit planes x u8 multiplicities -> int32 (exact), f64 epilogue; GOM dCor f64; base matrix f32 min / f64 slab sums",
+                "dtype": {"sparse": "48-bit fixed-point min x u8 multiplicities -> int64 (exact)",
+                          "mma": "u32 fixed-point min -> u8 digit planes x u8 multiplicities -> int32 (exact)",
+                          "fp32": "f32 min, f32 slab sums -> f64"}.get(path, path) +
+                         "; GOM Jaccard f32 min / f32 64-column slabs -> f64; GOM dCor f64; epilogue f64",
                 "data": "synthetic",
                 "config": workload_config(args, cfg, world), "clocks": clocks, "gpu_launches": launches,
                 "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline}
@@ -340,30 +348,69 @@ def main():
         dist.destroy_process_group()
 
 
-def make_roofline(kernel_ms, kernel_launches, steps, n, p, nrep, region_ms, peaks, peak_kind):
-    """Dominant kernel = boot_mma_kernel (tcgen05.mma.kind::i8): pairs x replicates x columns contraction of the
-    four uint8 digit planes of min(x_i, x_j) with the uint8 multiplicities.  Its durations are CUDA-event times
-    taken inside the timed region on the launching stream (gv2_timing_*).
-      algorithmic ops per launch = pairs * P * replicates * 4 planes * 2 (multiply + add)      [DESIGN.md section 4]
-      peak = 2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 tensor throughput on sm_100a is twice
-             bf16; the driver measures bf16 only) -- the sustained figure, since the kernel runs inside a long step
-    """
-    if kernel_launches == 0 or kernel_ms <= 0:
-        return None
+def make_roofline(times, path, cells, steps, n, p, g, nrep, region_ms, peaks, peak_kind):
+    """Roofline of the dominant kernel (largest share of the timed region) + a line for every timed kernel group.
+    Durations are CUDA-event times taken inside the timed region on the launching stream (gv2_timing_read_kind).
+    Algorithmic work per step, pairs = N(N+1)/2:
+      tail  (gj_fused_kernel, one launch per sub-chunk of replicates): per replicate it READS the PPHMM pair sums
+            (8 B x pairs) and the fp32 GOM table (4 N G) and WRITES the N x N float64 matrix (8 N^2); its arithmetic is
+            pairs x G cells of the (min, +) semiring at 2 issue slots per cell (FMNMX on the ALU pipe + FADD): bounded by
+            the FP32/ALU issue rate, not by HBM -- both fractions are reported;
+      pairs (replicate pair sums): tensor-core path: pairs x P x replicates x 4 planes x 2 ops against 2 x the measured
+            bf16 rate; sparse path: WRITES 8 B x pairs x replicates of workspace (+ CSR and multiplicities, small);
+      gom   (GOM dCor scoring, 5 kernels per 32-replicate chunk): N x G scores per replicate, reported as scores/s."""
     pairs = n * (n + 1) // 2
-    ops_per_step = float(pairs) * p * nrep * 4 * 2
-    sec_per_step = kernel_ms * 1e-3 / steps
-    bf16 = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0))
-    peak = 2.0 * bf16
-    achieved = ops_per_step / sec_per_step / 1e12
-    return {"kernel": "boot_mma_kernel (tcgen05.mma kind::i8, 4 uint8 digit planes, TMA-fed multiplicities, TMEM int32 accumulators)",
-            "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "peak_kind": f"{peak_kind}: 2 x bf16_tflops_sustained ({bf16}) = dense int8 TOP/s",
-            "launches_per_step": kernel_launches / steps, "avg_launch_ms": kernel_ms / kernel_launches,
-            "share_of_step": kernel_ms / region_ms,
-            "note": "ops are int8 multiply-adds counted as 2 ops ('TFLOP/s' = TOP/s); the kernel is bound by the SM's shared-memory "
-                    "data pipe shared by the operand reads of UTCIMMA and the producers' LDS/STS (DESIGN.md section 4), not by HBM: "
-                    "tables and multiplicities are L2-resident"}
+    hbm = peaks.get("hbm_gbs", 6550.0)
+    sm_mhz = peaks.get("sm_max_mhz", 1965.0)
+    fp32_issue = 148 * 128 * sm_mhz * 1e6                 # thread-instructions/s over all SMSPs
+    lines = {}
+    ms, cnt = times["tail"]
+    if cnt:
+        sec = ms * 1e-3 / steps
+        bytes_step = nrep * (8.0 * pairs + 8.0 * n * n + 4.0 * n * g)
+        slots = nrep * float(pairs) * g * 2
+        lines["tail"] = {"kernel": "gj_fused_kernel (GOM-signature (min,+) pair sums on 128x64 tiles + clean/combine/clamp/1-S/mirror epilogue)",
+                         "bound": "hbm", "achieved": bytes_step / sec / 1e9, "peak": hbm, "unit": "GB/s",
+                         "frac": bytes_step / sec / 1e9 / hbm, "traffic": None,
+                         "pipe": {"bound": "fp32/alu issue (2 slots per cell: FMNMX + FADD)", "achieved": slots / sec, "peak": fp32_issue,
+                                  "unit": "thread-instr/s", "frac": slots / sec / fp32_issue},
+                         "launches_per_step": cnt / steps, "avg_launch_ms": ms / cnt, "share_of_step": ms / region_ms,
+                         "note": "compute bound by design: the G-column min/+ reduction costs 2 issue slots per (pair, GOM) cell; the HBM "
+                                 "fraction is what is left of the N x N float64 write + pair-sum read per replicate"}
+    ms, cnt = times["pairs"]
+    if cnt:
+        sec = ms * 1e-3 / steps
+        if path == "mma":
+            bf16 = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0))
+            ops = float(pairs) * p * nrep * 4 * 2
+            lines["pairs"] = {"kernel": "boot_mma_kernel (tcgen05.mma kind::i8, uint8 digit planes x uint8 multiplicities, TMEM int32 accumulators)",
+                              "bound": "tensor", "achieved": ops / sec / 1e12, "peak": 2.0 * bf16, "unit": "TFLOP/s",
+                              "frac": ops / sec / 1e12 / (2.0 * bf16), "traffic": None,
+                              "peak_kind": f"{peak_kind}: 2 x bf16_tflops_sustained ({bf16}) = dense int8 TOP/s"}
+        else:
+            bytes_step = 8.0 * pairs * nrep
+            lines["pairs"] = {"kernel": f"replicate pair sums, path {path} (boot_sparse_kernel: CSR walk, 48-bit fixed point, exact integer sums)"
+                              if path == "sparse" else f"replicate pair sums, path {path}",
+                              "bound": "hbm", "achieved": bytes_step / sec / 1e9, "peak": hbm, "unit": "GB/s",
+                              "frac": bytes_step / sec / 1e9 / hbm, "traffic": None,
+                              "copresent_cells": int(cells), "cell_replicates_per_s": cells * nrep / sec if cells else None,
+                              "note": "latency bound on the L2 reads of the transposed multiplicities (one byte per list entry and replicate); "
+                                      "algorithmic bytes = the fp64 pair-sum workspace it writes"}
+        lines["pairs"].update({"launches_per_step": cnt / steps, "avg_launch_ms": ms / cnt, "share_of_step": ms / region_ms})
+    ms, cnt = times["gom"]
+    if cnt:
+        sec = ms * 1e-3 / steps
+        lines["gom"] = {"kernel": "GOM dCor scoring (gom_rowsums / genome_rowsums / gom_aggregates / gom_score_light / gom_score_heavy)",
+                        "bound": "latency / L2 (fp64)", "achieved": float(n) * g * nrep / sec, "unit": "dCor scores/s",
+                        "launches_per_step": cnt / steps, "avg_launch_ms": ms / cnt, "share_of_step": ms / region_ms}
+    if not lines:
+        return None
+    dominant = max((k for k in lines if k != "gom"), key=lambda k: lines[k]["share_of_step"], default=None)
+    out = dict(lines[dominant]) if dominant else {}
+    out["peak_kind"] = out.get("peak_kind", f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs / sm_max_mhz)")
+    out["kernels"] = {k: {kk: v[kk] for kk in ("kernel", "share_of_step", "avg_launch_ms", "launches_per_step", "frac") if kk in v}
+                      for k, v in lines.items()}
+    return out
 
 
 def measure_e2e(lib, ctx, ck, t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist, torch, steps):

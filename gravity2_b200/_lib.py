@@ -17,6 +17,8 @@ SCHEMES = {"P": 0, "G": 1, "PG": 2, "R": 3, "RG": 4, "PR": 5, "L": 6, "PL": 7}
 OUT_SIMILARITY, OUT_DISTANCE = 0, 1
 TILE = 128
 GOM_ALL_COLUMNS = 1
+TIME_PAIRSUMS, TIME_TAIL, TIME_GOM = 0, 1, 2
+PATH_NAMES = {0: "none", 1: "fp32", 2: "mma", 3: "sparse"}
 
 c_i64 = C.c_int64
 c_dp = C.POINTER(C.c_double)
@@ -44,6 +46,9 @@ PROTOTYPES = {
     "gv2_launch_count": (C.c_uint64, [c_vp]),
     "gv2_timing_enable": (C.c_int, [c_vp, C.c_int]),
     "gv2_timing_read": (C.c_int, [c_vp, C.POINTER(C.c_double), C.POINTER(c_i64)]),
+    "gv2_timing_read_kind": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(c_i64)]),
+    "gv2_job_replicate_path": (C.c_int, [c_vp]),
+    "gv2_job_copresent_cells": (C.c_uint64, [c_vp]),
     "gv2_similarity_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, c_vp]),
     "gv2_similarity_nbhd_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, C.c_double, C.c_double, c_vp, c_vp]),

@@ -17,7 +17,7 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
                        double* ws);
 int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k_pad, int64_t nb,
                     const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
-                    double* ws, double* out, int64_t out_replicate_stride);
+                    double* out, int64_t out_replicate_stride);
 int boot_mma_available();
 int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n_pad, int64_t k_pad, int64_t tile_begin,
                     int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* w8_scratch, int* overflow_flag,
@@ -120,21 +120,30 @@ extern "C" int gv2_timing_enable(gv2_ctx* ctx, int on) {
     return GV2_OK;
 }
 
-extern "C" int gv2_timing_read(gv2_ctx* ctx, double* total_ms, int64_t* launches) {
-    if (!ctx || !total_ms || !launches) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_timing_read: bad arguments");
+// Summed duration and number of timed launch groups of one kind since the last read of that kind (synchronises).
+extern "C" int gv2_timing_read_kind(gv2_ctx* ctx, int kind, double* total_ms, int64_t* launches) {
+    if (!ctx || !total_ms || !launches) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_timing_read_kind: bad arguments");
     GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     double t = 0.0;
-    for (auto& pr : ctx->timed) {
+    int64_t cnt = 0;
+    std::vector<gv2_ctx::Timed> keep;
+    for (auto& e : ctx->timed) {
+        if (e.kind != kind) { keep.push_back(e); continue; }
         float ms = 0.f;
-        GV2_CUDA(ctx, cudaEventElapsedTime(&ms, pr.first, pr.second));
+        GV2_CUDA(ctx, cudaEventElapsedTime(&ms, e.a, e.b));
         t += ms;
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+        ++cnt;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
     }
+    ctx->timed.swap(keep);
     *total_ms = t;
-    *launches = (int64_t)ctx->timed.size();
-    ctx->timed.clear();
+    *launches = cnt;
     return GV2_OK;
+}
+
+extern "C" int gv2_timing_read(gv2_ctx* ctx, double* total_ms, int64_t* launches) {
+    return gv2_timing_read_kind(ctx, GV2_TIME_PAIRSUMS, total_ms, launches);
 }
 
 // ---------------------------------------------------------- memory helpers for hosts without a CUDA binding
@@ -269,6 +278,14 @@ extern "C" void gv2_job_destroy(gv2_job* job) {
 }
 
 extern "C" size_t gv2_job_device_bytes(const gv2_job* job) { return job ? job->device_bytes() : 0; }
+
+// Which replicate pair-sum path the job's cost model chose (GV2_PATH_*), and the number of co-present
+// (genome pair incl. diagonal, PPHMM column) cells of its signature table (0 when no CSR was built).
+extern "C" int gv2_job_replicate_path(const gv2_job* job) {
+    if (!job || !job->need_p) return GV2_PATH_NONE;
+    return job->sparse ? GV2_PATH_SPARSE : job->mma_ok ? GV2_PATH_MMA : GV2_PATH_FP32;
+}
+extern "C" uint64_t gv2_job_copresent_cells(const gv2_job* job) { return job ? boot_sparse_cells(job->sparse) : 0; }
 
 extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc, int tables_are_device,
                               int64_t n, int64_t p, const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g,
@@ -438,7 +455,7 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const size_t have = job->wsP.bytes + job->gomf.bytes + job->gomtab.bytes + job->wbf16.bytes;
-    const size_t sub_bytes = job->need_g ? (size_t)sub * ntl * tile_elems * sizeof(double) : 0;
+    const size_t sub_bytes = 0;     // the fused tail keeps the GOM pair sums in registers: no per-sub-chunk workspace
     const size_t avail = (size_t)((free_b + have) * 0.85);
     int64_t super = (int64_t)((avail > sub_bytes ? avail - sub_bytes : 0) / std::max<size_t>(1, per_rep));
     super = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(super, nb), 1024));
@@ -529,10 +546,9 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
                 // GOM Jaccard sums and the epilogue in one kernel: the GOM pair sums never go through HBM
                 cg.rowsums = job->gom_rowsum.as<double>() + c0 * n; cg.nanflags = job->gom_nan.as<uint8_t>() + c0 * n;
                 cg.ksplit = 1; cg.replicate_stride_rows = n; cg.replicate_stride_nan = n;
-                if ((rc = ensure(ctx, job->wsG, (size_t)(job->g_pad > 128 ? cb : 1) * ntl * tile_elems * sizeof(double)))) return rc;
                 if ((rc = gj_fused_launch(ctx, job->gomf.as<float>() + (size_t)c0 * job->n_pad * job->g_pad, job->n_pad * job->g_pad, n,
                                           job->n_pad, job->g_pad, cb, job->need_p ? &cp : nullptr, &cg, job->scheme, job->power,
-                                          job->out_kind, job->wsG.as<double>(), dev_ring + slot * n * n, n * n))) return rc;
+                                          job->out_kind, dev_ring + slot * n * n, n * n))) return rc;
             } else {
                 // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)
                 if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,

@@ -502,12 +502,8 @@ int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n
     }
     if (ntl > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "boot_mma_launch: more than 65535 genome tiles per launch");
     dim3 grid(128, (unsigned)ntl, (unsigned)nblocks);
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (ctx->timing) {
-        GV2_CUDA(ctx, cudaEventCreate(&ev0));
-        GV2_CUDA(ctx, cudaEventCreate(&ev1));
-        GV2_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
-    }
+    Gv2Timer timer(ctx, GV2_TIME_PAIRSUMS);
+    timer.begin();
     // low half-word (digit planes 0, 1) stores, high half-word (planes 2, 3) accumulates on top
     boot_mma_kernel<false><<<grid, BM_THREADS, BM_SMEM, ctx->stream>>>(tab, (int)k_pad, (int)(k_pad / BM_KC), (int)(n_pad / GV2_TILE),
                                                                        tile_begin, map, (int)nb, (int)nblk,
@@ -517,9 +513,6 @@ int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n
                                                                       tile_begin, map, (int)nb, (int)nblk,
                                                                       (long long)ntl * GV2_TILE * GV2_TILE, quantum, ws);
     GV2_LAUNCH_CHECK(ctx);
-    if (ctx->timing) {
-        GV2_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
-        ctx->timed.emplace_back(ev0, ev1);
-    }
+    timer.end();
     return GV2_OK;
 }

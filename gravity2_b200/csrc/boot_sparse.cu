@@ -479,12 +479,8 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
         GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         attr_done = true;
     }
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (ctx->timing) {
-        GV2_CUDA(ctx, cudaEventCreate(&ev0));
-        GV2_CUDA(ctx, cudaEventCreate(&ev1));
-        GV2_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
-    }
+    Gv2Timer timer(ctx, GV2_TIME_PAIRSUMS);
+    timer.begin();
     BsCsr csr{s->ptr, s->col, s->hi, s->lo};
     const int nt = (int)(n_pad / GV2_TILE), nwin = (int)((k_pad + BS_WIN - 1) / BS_WIN);
     const int kwin = (int)std::min<int64_t>(k_pad, BS_WIN);            // k_pad is a multiple of 128
@@ -498,9 +494,6 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     else
         boot_sparse_kernel<256><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, ws);
     GV2_LAUNCH_CHECK(ctx);
-    if (ctx->timing) {
-        GV2_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
-        ctx->timed.emplace_back(ev0, ev1);
-    }
+    timer.end();
     return GV2_OK;
 }

@@ -17,9 +17,34 @@ struct gv2_ctx {
     bool own_stream = false;
     std::string err;
     unsigned long long launches = 0;   // kernels launched through this context (bench: gpu_launches)
-    // optional CUDA-event timing of the dominant kernel (gv2_timing_enable / gv2_timing_read)
+    // optional CUDA-event timing of the hot kernels by group (gv2_timing_enable / gv2_timing_read_kind)
     bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+    struct Timed { cudaEvent_t a, b; int kind; };
+    std::vector<Timed> timed;
+};
+
+// kernel groups of the event timing (include/gravity2_b200.h: GV2_TIME_*)
+#define GV2_TIME_PAIRSUMS 0   // replicate pair-sum kernel (CSR walk / tensor-core contraction)
+#define GV2_TIME_TAIL 1       // fused GOM Jaccard + epilogue
+#define GV2_TIME_GOM 2        // GOM dCor scoring kernels of one replicate chunk
+
+// RAII-free helper: t.begin() before the launches, t.end() after; no-ops unless timing is enabled
+struct Gv2Timer {
+    gv2_ctx* ctx;
+    int kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Gv2Timer(gv2_ctx* c, int k) : ctx(c), kind(k) {}
+    void begin() {
+        if (!ctx->timing) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; return; }
+        cudaEventRecord(a, ctx->stream);
+    }
+    void end() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->timed.push_back({a, b, kind});
+        a = b = nullptr;
+    }
 };
 
 #define GV2_TILE 128          // genome-pair tile edge of the similarity kernels

@@ -76,7 +76,7 @@ struct GjFuse {
     double* out;             // [nb][n][n]
     long long out_b_stride;
 };
-#define GJ_STAGE_LD 129      // doubles per staged row of the mirror transpose (64 x 129 x 8 B = 66 KB of the idle ring)
+#define GJ_STAGE_LD 129      // doubles per staged column of the mirror transpose (64 x 129 x 8 B = 66 KB of the idle ring)
 
 // 1/sqrt(x) and 1/x to full double precision without the branchy library routines: fp32 seed (22 good bits) and three
 // Newton steps in fp64.  x must be positive and inside the fp32 range (pair sums and their products are; the callers
@@ -110,11 +110,11 @@ __device__ __forceinline__ double gj_ratio(double smin, double si, double sj, bo
 // ---------------------------------------------------------------------------------------
 // K1: per-tile sum_c w_c * min(T[i,c], T[j,c])   (w == 1 when !WEIGHTED)
 // grid = (tiles in [tile_begin, tile_end), ksplit, nb);  ws[((b*ksplit+ks)*ntl + t)][128*128]
-template <bool WEIGHTED, bool FUSED>
+template <bool WEIGHTED>
 __global__ void __launch_bounds__(GJ_THREADS, 2)
 gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int kblocks_total,
                    int nt, long long tile_begin, const float* __restrict__ wts, long long w_stride,
-                   double* __restrict__ ws, const GjFuse fz) {
+                   double* __restrict__ ws) {
     extern __shared__ __align__(16) float smem[];
     float* sA = smem;                                         // [STAGES][128][GJ_LDS]
     float* sB = sA + GJ_STAGES * GV2_TILE * GJ_LDS;           // [STAGES][128][GJ_LDS]
@@ -171,7 +171,6 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
                 // Each address is only ever touched by this one thread, in program order, so the
                 // fp64 sum is formed in slab order and is deterministic.
                 if (first) wtile[o] = (double)acc[m][n];
-                else if (FUSED) wtile[o] += (double)acc[m][n];         // read back below by this same thread: no RED
                 else atomicAdd(&wtile[o], (double)acc[m][n]);
                 acc[m][n] = 0.f;
             }
@@ -232,105 +231,180 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
             }
         }
         in_slab += GV2_BK;
-        if (in_slab >= GJ_SLAB && !(FUSED && it + 1 == nkb)) {   // fused: the last slab stays in registers
+        if (in_slab >= GJ_SLAB) {
             flush(first);
             first = false;
             in_slab = 0;
         }
     }
-    if (!FUSED) {
-        if (in_slab > 0 || first) flush(first);
-        return;
+    if (in_slab > 0 || first) flush(first);
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused tail of the replicate path: GOM-signature pair sums (K1 arithmetic on a 128 x 64 pair tile) + the whole
+// epilogue (clean / combine with the PPHMM component / clamp / power / 1 - S / mirror) in one kernel, so the GOM
+// pair sums never travel through HBM and the separate epilogue pass over the PPHMM workspace disappears.
+//   grid = (2 * tiles, 1, replicates): CTA (t, half) owns rows [0,128) x columns [64 half, 64 half + 64) of tile t;
+//   thread (ty, tx) owns rows ty + 16 m (m < 8), columns 64 half + tx + 16 n (n < 4): 32 fp32 slab accumulators
+//   promoted every GF_SLAB columns into 32 fp64 running sums that stay in registers.
+#define GF_STAGES 3
+#define GF_SLAB 64
+#define GF_STAGE_FLOATS ((GV2_TILE + 64) * GJ_LDS)
+static size_t gf_smem_bytes() { return (size_t)GF_STAGES * GF_STAGE_FLOATS * sizeof(float); }
+
+__global__ void __launch_bounds__(GJ_THREADS, 2)
+gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int nkb, int nt, const GjFuse fz) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const long long t = blockIdx.x >> 1;
+    const int half = blockIdx.x & 1;
+    const long long b = blockIdx.z;
+    int bi, bj;
+    gv2_tile_coords(t, nt, &bi, &bj);
+    tab += (size_t)b * tab_stride;                            // one GOM table per replicate
+    const float* gA = tab + (size_t)bi * GV2_TILE * ld;
+    const float* gB = tab + ((size_t)bj * GV2_TILE + half * 64) * ld;
+
+    auto load_stage = [&](int stage, int kb) {
+        const int k = kb * GV2_BK;
+        float* a = smem + stage * GF_STAGE_FLOATS;
+        float* bb = a + GV2_TILE * GJ_LDS;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const int q = tid + s * GJ_THREADS, row = q >> 3, cc = (q & 7) * 4;
+            cp_async16(a + row * GJ_LDS + cc, gA + (size_t)row * ld + k + cc);
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int q = tid + s * GJ_THREADS, row = q >> 3, cc = (q & 7) * 4;
+            cp_async16(bb + row * GJ_LDS + cc, gB + (size_t)row * ld + k + cc);
+        }
+    };
+
+    float acc[8][4];
+    double sum[8][4];
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { acc[m][n] = 0.f; sum[m][n] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < GF_STAGES - 1; ++s) {
+        if (s < nkb) load_stage(s, s);
+        cp_async_commit();
     }
-    // ------------------------------------------------------------------ fused epilogue (ksplit == 1)
+    int in_slab = 0;
+    for (int it = 0; it < nkb; ++it) {
+        cp_async_wait<GF_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nxt = it + GF_STAGES - 1;
+            if (nxt < nkb) load_stage(nxt % GF_STAGES, nxt);
+            cp_async_commit();
+        }
+        const float* a = smem + (it % GF_STAGES) * GF_STAGE_FLOATS + ty * GJ_LDS;
+        const float* bb = smem + (it % GF_STAGES) * GF_STAGE_FLOATS + (GV2_TILE + tx) * GJ_LDS;
+#pragma unroll 2
+        for (int kg = 0; kg < GV2_BK / 4; ++kg) {
+            float4 bf[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) bf[n] = *reinterpret_cast<const float4*>(bb + n * 16 * GJ_LDS + kg * 4);
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                const float4 af = *reinterpret_cast<const float4*>(a + m * 16 * GJ_LDS + kg * 4);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const float s0 = fminf(af.x, bf[n].x) + fminf(af.y, bf[n].y);
+                    const float s1 = fminf(af.z, bf[n].z) + fminf(af.w, bf[n].w);
+                    acc[m][n] += s0 + s1;
+                }
+            }
+        }
+        in_slab += GV2_BK;
+        if (in_slab >= GF_SLAB || it + 1 == nkb) {            // fp32 slab totals -> fp64 running sums (registers)
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+#pragma unroll
+                for (int n = 0; n < 4; ++n) { sum[m][n] += (double)acc[m][n]; acc[m][n] = 0.f; }
+            in_slab = 0;
+        }
+    }
     cp_async_wait<0>();
+
+    // ------------------------------------------------------------------ epilogue
     const long long n = fz.n;
+    const double qnan = nan("");
     const double* g_rs = fz.g_rowsum + b * fz.g_stride_row;
     const unsigned char* g_nf = fz.g_nan ? fz.g_nan + b * fz.g_stride_nan : nullptr;
     const bool has_p = fz.P.ws != nullptr;
-    const double* p_ws = has_p ? fz.P.ws + b * fz.P.b_stride_ws + (long long)blockIdx.x * (GV2_TILE * GV2_TILE) : nullptr;
+    const double* p_ws = has_p ? fz.P.ws + b * fz.P.b_stride_ws + t * (long long)(GV2_TILE * GV2_TILE) : nullptr;
     const double* p_rs = has_p ? fz.P.rowsum + b * fz.P.b_stride_row : nullptr;
     const unsigned char* p_nf = (has_p && fz.P.nan) ? fz.P.nan + b * fz.P.b_stride_nan : nullptr;
     double* o = fz.out + b * fz.out_b_stride;
-    double* stage = reinterpret_cast<double*>(smem);                 // [64][GJ_STAGE_LD]
-    double gsj[8], psj[8];
-    bool nanj_g[8], nanj_p[8];
+    double* stage = reinterpret_cast<double*>(smem);                 // [64 columns][GJ_STAGE_LD]: the mirror transpose
+    const bool powered = fz.pw != 1.0, as_distance = fz.out_kind == GV2_OUT_DISTANCE;
+    // row sums of the partner genomes; a genome with a NaN entry gets NaN sums, which the `> 0` tests below turn into 0
+    double gsj[4], psj[4];
 #pragma unroll
-    for (int nn = 0; nn < 8; ++nn) {
-        const long long gj = (long long)bj * GV2_TILE + tx + 16 * nn;
+    for (int nn = 0; nn < 4; ++nn) {
+        const long long gj = (long long)bj * GV2_TILE + half * 64 + tx + 16 * nn;
         const bool ok = gj < n;
-        gsj[nn] = ok ? g_rs[gj] : 0.0;
-        psj[nn] = (ok && has_p) ? p_rs[gj] : 0.0;
-        nanj_g[nn] = ok && g_nf && g_nf[gj];
-        nanj_p[nn] = ok && p_nf && p_nf[gj];
+        gsj[nn] = ok ? ((g_nf && g_nf[gj]) ? qnan : g_rs[gj]) : 0.0;
+        psj[nn] = (ok && has_p) ? ((p_nf && p_nf[gj]) ? qnan : p_rs[gj]) : 0.0;
     }
-    for (int half = 0; half < 2; ++half) {
-        __syncthreads();                                             // ring (first half) / previous stage contents are dead
+    __syncthreads();                                                 // the ring is dead: reuse it as the transpose stage
 #pragma unroll
-        for (int mm = 0; mm < 4; ++mm) {
-            const int m = half * 4 + mm;
-            const int r = ty + 16 * m;
-            const long long gi = (long long)bi * GV2_TILE + r;
-            const bool oki = gi < n;
-            const double gsi = oki ? g_rs[gi] : 0.0, psi = (oki && has_p) ? p_rs[gi] : 0.0;
-            const bool gnan_i = oki && g_nf && g_nf[gi], pnan_i = oki && p_nf && p_nf[gi];
-            // all of this row's loads first (16 independent 8-byte loads in flight), then the arithmetic
-            double gprev[8], pv[8];
+    for (int m = 0; m < 8; ++m) {
+        const int r = ty + 16 * m;
+        const long long gi = (long long)bi * GV2_TILE + r;
+        const bool oki = gi < n;
+        const double gsi = oki ? ((g_nf && g_nf[gi]) ? qnan : g_rs[gi]) : 0.0;
+        const double psi = (oki && has_p) ? ((p_nf && p_nf[gi]) ? qnan : p_rs[gi]) : 0.0;
+        double pv[4];
 #pragma unroll
-            for (int nn = 0; nn < 8; ++nn) {
-                const int c = tx + 16 * nn;
-                gprev[nn] = first ? 0.0 : wtile[(size_t)((m * 8 + nn) * 256 + tid)];
-                // diagonal tiles: the replicate kernels leave the entries below the diagonal unwritten
-                const int rr = (bi == bj && r > c) ? c : r, cc = (bi == bj && r > c) ? r : c;
-                pv[nn] = has_p ? p_ws[gj_ws_index(rr, cc)] : 0.0;
-            }
-#pragma unroll
-            for (int nn = 0; nn < 8; ++nn) {
-                const int c = tx + 16 * nn;
-                const long long gj = (long long)bj * GV2_TILE + c;
-                double sv = 0.0;
-                if (oki && gj < n) {
-                    // GJ = sum(min) / sum(max), 0 when sum(max) == 0 (:168), NaN and negatives cleaned to 0 (:204-205), then
-                    // (P * G) ** 0.5 (:214) -- as ONE reciprocal square root: sqrt(Np Ng / (Dp Dg)) = |Np Ng| rsqrt(Np Ng Dp Dg)
-                    const bool diag = gi == gj;
-                    const double ng = diag ? gsi : gprev[nn] + (double)acc[m][nn];      // diagonal: sum(min) == sum(a) exactly
-                    const double dg = gsi + gsj[nn] - ng;
-                    bool zero = gnan_i || nanj_g[nn] || dg == 0.0 || ((ng < 0.0) != (dg < 0.0));
-                    double num = ng, den = dg;
-                    if (has_p) {
-                        const double np_ = diag ? psi : pv[nn];
-                        const double dp = psi + psj[nn] - np_;
-                        zero = zero || pnan_i || nanj_p[nn] || dp == 0.0 || ((np_ < 0.0) != (dp < 0.0));
-                        num *= np_;
-                        den *= dp;
-                    }
-                    if (zero || num == 0.0) sv = 0.0;
-                    else if (num == den) sv = 1.0;                   // diagonal, duplicate genomes: exactly 1
-                    else if (has_p) {
-                        const double x = num * den;
-                        sv = fabs(num) * (gj_fast_range(x) ? gj_rsqrt(x) : rsqrt(x));
-                    } else {
-                        sv = num * (gj_fast_range(den) ? gj_rcp(den) : 1.0 / den);
-                    }
-                    if (sv < 0.0) sv = 0.0;                          // :224
-                    if (fz.pw != 1.0) sv = pow(sv, fz.pw);           // :226
-                    if (fz.out_kind == GV2_OUT_DISTANCE) {           // pl1_graphs.py:52-53
-                        sv = 1.0 - sv;
-                        if (sv < 0.0) sv = 0.0;
-                    }
-                    o[gi * n + gj] = sv;
-                }
-                stage[(ty + 16 * mm) * GJ_STAGE_LD + c] = sv;
-            }
+        for (int nn = 0; nn < 4; ++nn) {
+            const int c = half * 64 + tx + 16 * nn;
+            // diagonal tiles: the replicate kernels leave the entries below the diagonal unwritten
+            const int rr = (bi == bj && r > c) ? c : r, cc = (bi == bj && r > c) ? r : c;
+            pv[nn] = has_p ? p_ws[gj_ws_index(rr, cc)] : 0.0;
         }
-        if (bi == bj) continue;                                      // diagonal tiles hold both triangles already
-        __syncthreads();
-        // mirror: row (bj*128 + c), columns bi*128 + 64*half + [0, 64): 64 consecutive doubles per staged column
-        for (int q = tid; q < 64 * GV2_TILE; q += GJ_THREADS) {
-            const int c = q >> 6, rl = q & 63;
-            const long long gj = (long long)bj * GV2_TILE + c, gi = (long long)bi * GV2_TILE + half * 64 + rl;
-            if (gi < n && gj < n) o[gj * n + gi] = stage[rl * GJ_STAGE_LD + c];
+#pragma unroll
+        for (int nn = 0; nn < 4; ++nn) {
+            const int cl = tx + 16 * nn;
+            const long long gj = (long long)bj * GV2_TILE + half * 64 + cl;
+            // GJ = sum(min) / sum(max), 0 when sum(max) == 0 (:168), NaN and negatives cleaned to 0 (:204-205), then
+            // (P * G) ** 0.5 (:214) as ONE reciprocal square root: sqrt(Np Ng / (Dp Dg)) = Np Ng rsqrt(Np Ng Dp Dg).
+            // N D > 0 says: sum(max) != 0, ratio positive, nothing NaN.
+            const bool diag = gi == gj;
+            const double ng = diag ? gsi : sum[m][nn];                 // diagonal: sum(min) == sum(a) exactly
+            const double dg = gsi + gsj[nn] - ng;
+            const double ag = ng * dg;
+            double sv;
+            if (has_p) {
+                const double np_ = diag ? psi : pv[nn];
+                const double dp = psi + psj[nn] - np_;
+                const double ap = np_ * dp;
+                const double num = np_ * ng, den = dp * dg, x = ag * ap;
+                sv = (num == den) ? 1.0 : fabs(num) * (gj_fast_range(x) ? gj_rsqrt(x) : rsqrt(x));   // == : diagonal, duplicates
+                if (!(ag > 0.0 && ap > 0.0)) sv = 0.0;
+            } else {
+                sv = (ng == dg) ? 1.0 : fabs(ng) * (gj_fast_range(fabs(dg)) ? gj_rcp(fabs(dg)) : 1.0 / fabs(dg));
+                if (!(ag > 0.0)) sv = 0.0;
+            }
+            if (powered) sv = pow(sv, fz.pw);                        // :226 (sv >= 0 already, :224)
+            if (as_distance) sv = fmax(1.0 - sv, 0.0);               // pl1_graphs.py:52-53
+            if (oki && gj < n) o[gi * n + gj] = sv;
+            stage[cl * GJ_STAGE_LD + r] = sv;
         }
+    }
+    if (bi == bj) return;                                            // diagonal tiles hold both triangles already
+    __syncthreads();
+    // mirror: rows bj*128 + 64 half + [0, 64), columns bi*128 + [0, 128): 128 consecutive doubles per staged row
+    for (int q = tid; q < 64 * GV2_TILE; q += GJ_THREADS) {
+        const int cl = q >> 7, r = q & 127;
+        const long long gj = (long long)bj * GV2_TILE + half * 64 + cl, gi = (long long)bi * GV2_TILE + r;
+        if (gi < n && gj < n) o[gj * n + gi] = stage[cl * GJ_STAGE_LD + r];
     }
 }
 
@@ -591,39 +665,39 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
     static bool attr_done = false;
     size_t smem = gj_smem_bytes();
     if (!attr_done) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     dim3 grid((unsigned)ntl, (unsigned)ksplit, (unsigned)nb);
     const int nt = (int)(n_pad / GV2_TILE);
     const int kblocks = (int)(k_pad / GV2_BK);
     if (w)
-        gj_min_tile_kernel<true, false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, w, k_pad, ws, GjFuse{});
+        gj_min_tile_kernel<true><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, w, k_pad, ws);
     else
-        gj_min_tile_kernel<false, false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, nullptr, 0, ws, GjFuse{});
+        gj_min_tile_kernel<false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, kblocks, nt, tile_begin, nullptr, 0, ws);
     GV2_LAUNCH_CHECK(ctx);
     return GV2_OK;
 }
 
 static GjComp to_comp(const gv2_gj_component* c);
 
-// Fused GOM pair sums + epilogue for replicates [0, nb): one table per replicate (tab_stride), all tiles [0, ntl),
-// schemes G and PG.  ws: scratch [nb][ntl][128*128] for the slab promotion (touched only when k_pad > GJ_SLAB).
+// Fused GOM pair sums + epilogue for replicates [0, nb): one table per replicate (tab_stride), all tiles, schemes G and PG.
 int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k_pad, int64_t nb,
                     const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
-                    double* ws, double* out, int64_t out_replicate_stride) {
+                    double* out, int64_t out_replicate_stride) {
     if (scheme != GV2_SCHEME_G && scheme != GV2_SCHEME_PG) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: scheme %d", scheme);
-    if (!tab || !comp_g || !comp_g->rowsums || !out || (scheme == GV2_SCHEME_PG && (!comp_p || !comp_p->min_sums || !comp_p->rowsums || comp_p->ksplit != 1)))
+    if (!tab || !comp_g || !comp_g->rowsums || !out || (k_pad % GV2_BK) || (n_pad % GV2_TILE) ||
+        (scheme == GV2_SCHEME_PG && (!comp_p || !comp_p->min_sums || !comp_p->rowsums || comp_p->ksplit != 1)))
         return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: bad arguments");
     const int64_t ntl = gv2_num_tiles(n);
     if (ntl == 0 || nb <= 0) return GV2_OK;
     if (nb > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: nb > 65535");
     static bool attr_done = false;
-    const size_t smem = gj_smem_bytes();
+    const size_t smem = gf_smem_bytes();
+    static_assert(GF_STAGES * GF_STAGE_FLOATS * sizeof(float) >= 64 * GJ_STAGE_LD * sizeof(double), "transpose stage must fit the ring");
     if (!attr_done) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     GjFuse fz{};
@@ -631,10 +705,12 @@ int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t 
     fz.g_rowsum = comp_g->rowsums; fz.g_nan = comp_g->nanflags;
     fz.g_stride_row = comp_g->replicate_stride_rows; fz.g_stride_nan = comp_g->replicate_stride_nan;
     fz.n = n; fz.scheme = scheme; fz.out_kind = out_kind; fz.pw = power; fz.out = out; fz.out_b_stride = out_replicate_stride;
-    dim3 grid((unsigned)ntl, 1, (unsigned)nb);
-    gj_min_tile_kernel<false, true><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, (int)(k_pad / GV2_BK), (int)(n_pad / GV2_TILE),
-                                                                             0, nullptr, 0, ws, fz);
+    dim3 grid((unsigned)(2 * ntl), 1, (unsigned)nb);
+    Gv2Timer timer(ctx, GV2_TIME_TAIL);
+    timer.begin();
+    gj_fused_kernel<<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, (int)(k_pad / GV2_BK), (int)(n_pad / GV2_TILE), fz);
     GV2_LAUNCH_CHECK(ctx);
+    timer.end();
     return GV2_OK;
 }
 

@@ -1,5 +1,6 @@
 // Device-side GOM database (internal).  See gom_kernels.cu.
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
@@ -26,6 +27,11 @@ struct GomDb {
     double* gagg = nullptr; double* vagg = nullptr;
     unsigned char* wT8 = nullptr; double* wG = nullptr; int* flag = nullptr;   // uint8 weights, per-GOM gathered weights, flags
     long long* heavy_list = nullptr;   // (genome, GOM) pairs whose intersection list overflows the light kernel
+    int n_heavy = 0;
+    // replicate-independent intersection lists I0 = R_v & R_g of every (GOM, genome) pair, built once per database:
+    // entries [is_ptr[g*n+v], is_ptr[g*n+v+1]) of is_ent, each (GOM point index k, genome hit index c)
+    long long* is_ptr = nullptr;
+    int2* is_ent = nullptr;
 };
 
 int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t ld_loc,

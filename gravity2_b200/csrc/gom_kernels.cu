@@ -377,6 +377,56 @@ __device__ __forceinline__ int vg_scan(int lane, int t, long long o, const int* 
     return ni;
 }
 
+// Intersection lists, built once per database (they do not depend on the replicate): one warp per (GOM, genome)
+// pair counts / writes the genome's hits that fall in the GOM's column set, column order preserved.
+// FILL == false: cnt[wid] = |I0|;  FILL == true: entries written at is_ptr[wid].  grid = ceil(n*G/8), block = 256
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+gom_isect_kernel(long long n, int G, long long p, const long long* __restrict__ ptr, const int* __restrict__ col,
+                 const int* __restrict__ pos, long long* __restrict__ cnt, const long long* __restrict__ is_ptr,
+                 int2* __restrict__ is_ent) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (wid >= n * G) return;
+    const int g = (int)(wid / n);
+    const long long v = wid % n;
+    const long long o = ptr[v];
+    const int t = (int)(ptr[v + 1] - o);
+    const int* posg = pos + (long long)g * p;
+    long long w0 = FILL ? is_ptr[wid] : 0;
+    int ni = 0;
+    for (int c0 = 0; c0 < t; c0 += 32) {
+        const int c = c0 + lane;
+        int k = -1;
+        if (c < t) k = posg[col[o + c]];
+        const unsigned m = __ballot_sync(0xffffffffu, k >= 0);
+        if (FILL && k >= 0) is_ent[w0 + ni + __popc(m & ((1u << lane) - 1u))] = make_int2(k, c);
+        ni += __popc(m);
+    }
+    if (!FILL && lane == 0) cnt[wid] = ni;
+}
+
+// work list of the heavy kernel: pairs whose list does not fit the light kernel's shared-memory slots
+__global__ void gom_heavy_list_kernel(long long total, const long long* __restrict__ is_ptr, int cap,
+                                      long long* __restrict__ heavy_list, int* __restrict__ heavy_count) {
+    const long long wid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wid >= total) return;
+    if (is_ptr[wid + 1] - is_ptr[wid] > cap) heavy_list[atomicAdd(heavy_count, 1)] = wid;
+}
+
+// load a precomputed intersection list into the staging arrays (threads tid, tid + nthreads, ...)
+__device__ __forceinline__ void vg_load(int tid, int nthreads, int ni, const int2* __restrict__ ent, long long o,
+                                        const double* __restrict__ val, const double* __restrict__ nrm, int p0,
+                                        double* sy, double* sn, int* sk, int* sc) {
+    for (int a = tid; a < ni; a += nthreads) {
+        const int2 e = ent[a];
+        sy[a] = val[o + e.y];
+        sn[a] = nrm[p0 + e.x];
+        sk[a] = e.x;
+        sc[a] = e.y;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 gom_score_light_kernel(long long n, int G, long long p, const long long* __restrict__ ptr,
                        const int* __restrict__ col, const double* __restrict__ val,
@@ -385,7 +435,7 @@ gom_score_light_kernel(long long n, int G, long long p, const long long* __restr
                        const double* __restrict__ A, const unsigned char* __restrict__ wT8,
                        const double* __restrict__ arT, const double* __restrict__ rT,
                        const double* __restrict__ gagg, const double* __restrict__ vagg, int nb,
-                       double* __restrict__ out, long long* __restrict__ heavy_list, int* __restrict__ heavy_count) {
+                       double* __restrict__ out, const long long* __restrict__ is_ptr, const int2* __restrict__ is_ent) {
     __shared__ __align__(16) unsigned char smem[4 * VG_LIGHT_CAP * VG_ENTRY_BYTES];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * 4 + wib;
@@ -402,11 +452,10 @@ gom_score_light_kernel(long long n, int G, long long p, const long long* __restr
     int* sk = reinterpret_cast<int*>(sn + VG_LIGHT_CAP);
     int* sc = sk + VG_LIGHT_CAP;
     unsigned char* sw = reinterpret_cast<unsigned char*>(sc + VG_LIGHT_CAP);
-    const int ni = vg_scan(lane, t, o, col, val, pos + (long long)g * p, nrm, p0, VG_LIGHT_CAP, sy, sn, sk, sc);
-    if (ni > VG_LIGHT_CAP) {
-        if (lane == 0) heavy_list[atomicAdd(heavy_count, 1)] = wid;
-        return;
-    }
+    const long long e0 = is_ptr[wid];
+    const int ni = (int)(is_ptr[wid + 1] - e0);
+    if (ni > VG_LIGHT_CAP) return;                                      // on the heavy kernel's work list
+    vg_load(lane, 32, ni, is_ent + e0, o, val, nrm, p0, sy, sn, sk, sc);
     __syncwarp();
     for (int i = lane; i < ni * 8; i += 32)                             // weights: 4 bytes per lane and trip
         reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + sc[i >> 3]] * NBC)[i & 7];
@@ -429,7 +478,7 @@ gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long lo
                        const double* __restrict__ arT, const double* __restrict__ rT,
                        const double* __restrict__ gagg, const double* __restrict__ vagg, int nb,
                        double* __restrict__ out, const long long* __restrict__ heavy_list,
-                       const int* __restrict__ heavy_count) {
+                       int total, const long long* __restrict__ is_ptr, const int2* __restrict__ is_ent) {
     extern __shared__ __align__(16) unsigned char vg_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int cap = (max_t + 1) & ~1;
@@ -439,8 +488,6 @@ gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long lo
     int* sc = sk + cap;
     unsigned char* sw = reinterpret_cast<unsigned char*>(sc + cap);
     double* red = reinterpret_cast<double*>(vg_smem + (size_t)cap * VG_ENTRY_BYTES);   // [3][VG_NSUM][32]
-    __shared__ int s_ni;
-    const int total = *heavy_count;
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
         const long long wid = heavy_list[it];
         const int g = (int)(wid / n);
@@ -449,12 +496,10 @@ gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long lo
         const int t = (int)(ptr[v + 1] - o);
         const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
         __syncthreads();                                                // previous pair fully consumed
-        if (wib == 0) {
-            const int ni = vg_scan(lane, t, o, col, val, pos + (long long)g * p, nrm, p0, cap, sy, sn, sk, sc);
-            if (lane == 0) s_ni = ni;
-        }
+        const long long e0 = is_ptr[wid];
+        const int ni = (int)(is_ptr[wid + 1] - e0);
+        vg_load(threadIdx.x, 128, ni, is_ent + e0, o, val, nrm, p0, sy, sn, sk, sc);
         __syncthreads();
-        const int ni = s_ni;
         for (int i = threadIdx.x; i < ni * 8; i += 128)
             reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + sc[i >> 3]] * NBC)[i & 7];
         __syncthreads();
@@ -501,6 +546,7 @@ void gom_db_free(GomDb* db) {
     cudaFree(db->pos); cudaFree(db->x_off); cudaFree(db->a_off); cudaFree(db->X); cudaFree(db->nrm);
     cudaFree(db->A); cudaFree(db->wT); cudaFree(db->arT); cudaFree(db->sqT); cudaFree(db->rT);
     cudaFree(db->gagg); cudaFree(db->vagg); cudaFree(db->wT8); cudaFree(db->wG); cudaFree(db->flag); cudaFree(db->heavy_list);
+    cudaFree(db->is_ptr); cudaFree(db->is_ent);
     delete db;
 }
 
@@ -627,7 +673,37 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
     CK(dalloc(&db->flag, 2, &db->bytes));          // [0] weight overflow, [1] heavy-list length
     CK(cudaMemsetAsync(db->flag, 0, 2 * sizeof(int), st));
     // shared-memory staging of the scoring kernels: 56 bytes per genome hit and warp
-    CK(dalloc(&db->heavy_list, (size_t)std::max<long long>(1, n * G), &db->bytes));
+    // ---- intersection lists + the heavy kernel's work list (replicate independent)
+    {
+        const long long total_w = n * G;
+        long long* icnt = nullptr;
+        CK(dalloc(&icnt, total_w + 1, nullptr));
+        CK(dalloc(&db->is_ptr, total_w + 1, &db->bytes));
+        CK(cudaMemsetAsync(icnt, 0, (size_t)(total_w + 1) * sizeof(long long), st));
+        if (total_w) {
+            gom_isect_kernel<false><<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->pos, icnt, nullptr, nullptr);
+            ctx->launches++;
+        }
+        void* tmp = nullptr; size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, icnt, db->is_ptr, (int)(total_w + 1), st);
+        CK(cudaMalloc(&tmp, tb ? tb : 1));
+        cub::DeviceScan::ExclusiveSum(tmp, tb, icnt, db->is_ptr, (int)(total_w + 1), st);
+        ctx->launches++;
+        long long n_ent = 0;
+        CK(cudaMemcpyAsync(&n_ent, db->is_ptr + total_w, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        cudaFree(tmp); cudaFree(icnt);
+        CK(dalloc(&db->is_ent, (size_t)std::max<long long>(1, n_ent), &db->bytes));
+        CK(dalloc(&db->heavy_list, (size_t)std::max<long long>(1, total_w), &db->bytes));
+        if (total_w) {
+            gom_isect_kernel<true><<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->pos, nullptr, db->is_ptr, db->is_ent);
+            ctx->launches++;
+            gom_heavy_list_kernel<<<(unsigned)((total_w + 255) / 256), 256, 0, st>>>(total_w, db->is_ptr, VG_LIGHT_CAP, db->heavy_list, db->flag + 1);
+            ctx->launches++;
+            CK(cudaMemcpyAsync(&db->n_heavy, db->flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+    }
     const size_t vg_smem = (size_t)((max_t + 1) & ~1) * VG_ENTRY_BYTES + 3 * VG_NSUM * 32 * sizeof(double);
     const size_t va_smem = (size_t)((max_t + 1) & ~1) * 8 + (size_t)max_t * NBC + 16;
     if (vg_smem > 200 * 1024 || va_smem > 200 * 1024) {
@@ -652,6 +728,8 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
     if (n == 0 || G == 0) return GV2_OK;
     for (int64_t b0 = 0; b0 < nb; b0 += NBC) {
         const int cb = (int)std::min<int64_t>(NBC, nb - b0);
+        Gv2Timer timer(ctx, GV2_TIME_GOM);
+        timer.begin();
         if (p) {
             weights_transpose_kernel<<<(unsigned)((p * NBC + 255) / 256), 256, 0, st>>>(
                 weights ? weights + b0 * p : nullptr, p, cb, db->wT, db->wT8, db->flag);
@@ -671,16 +749,19 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
         ctx->launches++;
         {
             const long long total_w = n * G;
-            cudaMemsetAsync(db->flag + 1, 0, sizeof(int), st);          // heavy-list counter
             gom_score_light_kernel<<<(unsigned)((total_w + 3) / 4), 128, 0, st>>>(
                 n, (int)G, p, db->g_ptr, db->g_col, db->g_val, db->pt_ptr, db->pos, db->nrm, db->a_off, db->A,
-                db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G, db->heavy_list, db->flag + 1);
+                db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G, db->is_ptr, db->is_ent);
             ctx->launches++;
-            gom_score_heavy_kernel<<<(unsigned)(ctx->sm_count * 8), 128, db->vg_smem, st>>>(
-                n, (int)G, p, db->max_t, db->g_ptr, db->g_col, db->g_val, db->pt_ptr, db->pos, db->nrm, db->a_off, db->A,
-                db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G, db->heavy_list, db->flag + 1);
-            ctx->launches++;
+            if (db->n_heavy) {
+                gom_score_heavy_kernel<<<(unsigned)std::min<long long>(db->n_heavy, ctx->sm_count * 8), 128, db->vg_smem, st>>>(
+                    n, (int)G, p, db->max_t, db->g_ptr, db->g_col, db->g_val, db->pt_ptr, db->pos, db->nrm, db->a_off, db->A,
+                    db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G, db->heavy_list, db->n_heavy,
+                    db->is_ptr, db->is_ent);
+                ctx->launches++;
+            }
         }
+        timer.end();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "gom_db_score: %s", cudaGetErrorString(e));
     }

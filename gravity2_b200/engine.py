@@ -198,7 +198,7 @@ class Job:
     the consumer as a zero-copy (N, N) float64 view that is valid until the consumer asks for the next."""
 
     def __init__(self, eng: Engine, sig, loc, gom_of_row, g: int, scheme: str = "PG", p: float = 1.0,
-                 distance: bool = True, ring_bytes: int = 1 << 30):
+                 distance: bool = True, ring_bytes: int = 8 << 30):
         if scheme not in ("P", "G", "PG"):
             raise NotImplementedError(f"device jobs cover schemes P, G, PG (got {scheme!r})")
         self.eng, self.lib, self.ctx = eng, eng.lib, eng.ctx

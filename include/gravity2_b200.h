@@ -64,10 +64,14 @@ void gv2_destroy(gv2_ctx* ctx);
 const char* gv2_last_error(const gv2_ctx* ctx); /* ctx may be NULL: last creation error */
 int gv2_synchronize(gv2_ctx* ctx);
 uint64_t gv2_launch_count(const gv2_ctx* ctx); /* kernels launched so far through ctx */
-/* CUDA-event timing of the dominant kernel (the tensor-core replicate contraction), on the context's stream:
- * enable, run, then read the summed duration and launch count (reading synchronises and resets). */
+/* CUDA-event timing of the hot kernels, on the context's stream, by group: enable, run, then read the summed
+ * duration and the number of timed launch groups of one kind (reading synchronises and resets that kind). */
+#define GV2_TIME_PAIRSUMS 0 /* replicate pair sums: CSR walk (sparse tables) or tensor-core contraction */
+#define GV2_TIME_TAIL 1     /* fused GOM Jaccard + epilogue kernel */
+#define GV2_TIME_GOM 2      /* GOM dCor scoring kernels of one 32-replicate chunk */
 int gv2_timing_enable(gv2_ctx* ctx, int on);
-int gv2_timing_read(gv2_ctx* ctx, double* total_ms, int64_t* launches);
+int gv2_timing_read_kind(gv2_ctx* ctx, int kind, double* total_ms, int64_t* launches);
+int gv2_timing_read(gv2_ctx* ctx, double* total_ms, int64_t* launches); /* = kind GV2_TIME_PAIRSUMS */
 
 /* device / pinned-host memory for hosts without their own CUDA binding (ctypes, cgo, JNI ...) */
 int gv2_dev_alloc(gv2_ctx* ctx, size_t bytes, void** out);
@@ -181,6 +185,15 @@ int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t 
  * dev_out [nb][n][g]. */
 int gv2_job_gom_table(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out);
 size_t gv2_job_device_bytes(const gv2_job* job);
+/* Replicate pair-sum path chosen for the job's signature table: exact integer arithmetic on a fixed-point image
+ * (CSR walk of sparse tables / tensor-core contraction of dense ones) or the fp32 tile kernel (tables with negative
+ * entries).  The environment variable GV2_BOOT_PATH = sparse | mma | fp32 overrides the cost model. */
+#define GV2_PATH_NONE 0
+#define GV2_PATH_FP32 1
+#define GV2_PATH_MMA 2
+#define GV2_PATH_SPARSE 3
+int gv2_job_replicate_path(const gv2_job* job);
+uint64_t gv2_job_copresent_cells(const gv2_job* job); /* sum over column c of cnt_c (cnt_c + 1) / 2 */
 
 /* ---- device-pointer primitives ----------------------------------------------------------- */
 int64_t gv2_num_tiles(int64_t n); /* upper-triangular 128x128 tiles incl. diagonal */
