@@ -278,7 +278,8 @@ __global__ void genome_rowsums_kernel(const long long* __restrict__ ptr, const i
 //   heavy kernel: one BLOCK per listed pair (a genome against its own taxon: |I| ~ all of its hits), the four
 //                 warps split the outer loop of the pair sums and reduce through shared memory.
 #define VG_ENTRY_BYTES 56
-#define VG_LIGHT_CAP 64
+#define VG_LIGHT_CAP 32
+#define VG_LIGHT_BYTES (VG_LIGHT_CAP * VG_ENTRY_BYTES + VG_LIGHT_CAP * (VG_LIGHT_CAP - 1) / 2 * 8)   // entries + distance triangle
 #define VG_NSUM 12
 
 struct VgSums { double v[VG_NSUM]; };   // SW S_ar S_nrm S_r S_y C_arr C_ary C_nr C_ny Q1 Q2 Q3
@@ -436,7 +437,7 @@ gom_score_light_kernel(long long n, int G, long long p, const long long* __restr
                        const double* __restrict__ arT, const double* __restrict__ rT,
                        const double* __restrict__ gagg, const double* __restrict__ vagg, int nb,
                        double* __restrict__ out, const long long* __restrict__ is_ptr, const int2* __restrict__ is_ent) {
-    __shared__ __align__(16) unsigned char smem[4 * VG_LIGHT_CAP * VG_ENTRY_BYTES];
+    __shared__ __align__(16) unsigned char smem[4 * VG_LIGHT_BYTES];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * 4 + wib;
     if (wid >= n * G) return;
@@ -444,12 +445,12 @@ gom_score_light_kernel(long long n, int G, long long p, const long long* __restr
     const int g = (int)(wid / n);
     const long long v = wid % n;
     const long long o = ptr[v];
-    const int t = (int)(ptr[v + 1] - o);
     const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
-    unsigned char* base = smem + wib * VG_LIGHT_CAP * VG_ENTRY_BYTES;
+    unsigned char* base = smem + wib * VG_LIGHT_BYTES;
     double* sy = reinterpret_cast<double*>(base);
     double* sn = sy + VG_LIGHT_CAP;
-    int* sk = reinterpret_cast<int*>(sn + VG_LIGHT_CAP);
+    double* sd = sn + VG_LIGHT_CAP;                                      // [a (a - 1) / 2 + e], e < a: |X_a - X_e|
+    int* sk = reinterpret_cast<int*>(sd + VG_LIGHT_CAP * (VG_LIGHT_CAP - 1) / 2);
     int* sc = sk + VG_LIGHT_CAP;
     unsigned char* sw = reinterpret_cast<unsigned char*>(sc + VG_LIGHT_CAP);
     const long long e0 = is_ptr[wid];
@@ -459,11 +460,53 @@ gom_score_light_kernel(long long n, int G, long long p, const long long* __restr
     __syncwarp();
     for (int i = lane; i < ni * 8; i += 32)                             // weights: 4 bytes per lane and trip
         reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + sc[i >> 3]] * NBC)[i & 7];
+    // the ni (ni - 1) / 2 distance-cache entries the pair sums need, gathered by all lanes at once: every load is
+    // independent, so the warp pays one L2 latency instead of one per entry
+    const double* Ag = A + a_off[g];
+    const int npair = ni * (ni - 1) / 2;
+    for (int q = lane; q < npair; q += 32) {
+        int a = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
+        while (a * (a - 1) / 2 > q) --a;
+        while ((a + 1) * a / 2 <= q) ++a;
+        const int e = q - a * (a - 1) / 2;
+        sd[q] = Ag[(long long)sk[a] * ng + sk[e]];
+    }
     __syncwarp();
     VgSums S;
 #pragma unroll
     for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
-    vg_accumulate(0, 1, ni, lane, sy, sn, sk, sc, sw, A + a_off[g], ng, p0, o, arT, rT, S);
+    const int b = lane;
+    for (int a = 0; a < ni; ++a) {
+        const int k = sk[a];
+        const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
+        const double wc = (double)sw[a * NBC + b];
+        const double ar = arT[(long long)(p0 + k) * NBC + b];
+        const double r = rT[(o + sc[a]) * NBC + b];
+        S.v[0] += wc;
+        S.v[1] = fma(wc, ar, S.v[1]);
+        S.v[2] = fma(wc, nr, S.v[2]);
+        S.v[3] = fma(wc, r, S.v[3]);
+        S.v[4] = fma(wc, ayc, S.v[4]);
+        S.v[5] = fma(wc * ar, r, S.v[5]);
+        S.v[6] = fma(wc * ar, ayc, S.v[6]);
+        S.v[7] = fma(wc * nr, r, S.v[7]);
+        S.v[8] = fma(wc * nr, ayc, S.v[8]);
+        const double* drow = sd + a * (a - 1) / 2;
+        double q1 = 0, q2 = 0, q3 = 0;
+#pragma unroll 4
+        for (int e = 0; e < a; ++e) {           // unordered pairs e < a, doubled below
+            const double yd = sy[e];
+            const double wd = (double)sw[e * NBC + b];
+            const double dist = drow[e];
+            const double dy = fabs(yc - yd);
+            q1 = fma(wd * dist, dy, q1);
+            q2 = fma(wd * dist, ayc + fabs(yd), q2);
+            q3 = fma(wd * (nr + sn[e]), dy, q3);
+        }
+        S.v[9] = fma(2.0 * wc, q1, S.v[9]);
+        S.v[10] = fma(wc, q2, S.v[10]);
+        S.v[11] = fma(wc, q3, S.v[11]);
+    }
     if (lane < nb)
         out[((long long)lane * n + v) * G + g] = vg_finish(S, gagg + (long long)g * GAGG * NBC + lane, vagg + v * VAGG * NBC + lane);
 }
