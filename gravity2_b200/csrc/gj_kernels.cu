@@ -78,25 +78,27 @@ struct GjFuse {
 };
 #define GJ_STAGE_LD 129      // doubles per staged column of the mirror transpose (64 x 129 x 8 B = 66 KB of the idle ring)
 
-// 1/sqrt(x) and 1/x to full double precision without the branchy library routines: fp32 seed (22 good bits) and three
-// Newton steps in fp64.  x must be positive and inside the fp32 range (pair sums and their products are; the callers
-// send anything else to the library routine).
+// 1/sqrt(x) and 1/x to full double precision without the branchy library routines: fp32 seed (22 good bits) and two
+// Newton steps in fp64 (44, then 88 bits).  x > 0; values outside the fp32 range are first scaled by an even power
+// of two (selects, no branch), so the whole thing is straight-line code.
 __device__ __forceinline__ double gj_rsqrt(double x) {
+    const bool tiny = x < 1e-30, huge = x > 1e30;
+    x *= tiny ? 0x1p+200 : (huge ? 0x1p-200 : 1.0);
     double r = (double)rsqrtf((float)x);
     const double hx = 0.5 * x;
     r = r * fma(-hx * r, r, 1.5);
     r = r * fma(-hx * r, r, 1.5);
-    r = r * fma(-hx * r, r, 1.5);
-    return r;
+    return r * (tiny ? 0x1p+100 : (huge ? 0x1p-100 : 1.0));
 }
 __device__ __forceinline__ double gj_rcp(double x) {
-    double r = (double)(1.0f / (float)x);
+    const bool tiny = x < 1e-30, huge = x > 1e30;
+    const double sc = tiny ? 0x1p+200 : (huge ? 0x1p-200 : 1.0);
+    x *= sc;
+    double r = (double)__frcp_rn((float)x);
     r = r * fma(-x, r, 2.0);
     r = r * fma(-x, r, 2.0);
-    r = r * fma(-x, r, 2.0);
-    return r;
+    return r * sc;
 }
-__device__ __forceinline__ bool gj_fast_range(double x) { return x > 1e-30 && x < 1e30; }
 
 __device__ __forceinline__ double gj_ratio(double smin, double si, double sj, bool diag, bool isnan_row) {
     if (diag) smin = si;                           // diagonal: sum(min) == sum(a) exactly
@@ -386,10 +388,10 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
                 const double dp = psi + psj[nn] - np_;
                 const double ap = np_ * dp;
                 const double num = np_ * ng, den = dp * dg, x = ag * ap;
-                sv = (num == den) ? 1.0 : fabs(num) * (gj_fast_range(x) ? gj_rsqrt(x) : rsqrt(x));   // == : diagonal, duplicates
+                sv = (num == den) ? 1.0 : fabs(num) * gj_rsqrt(x);   // == : diagonal, duplicate genomes
                 if (!(ag > 0.0 && ap > 0.0)) sv = 0.0;
             } else {
-                sv = (ng == dg) ? 1.0 : fabs(ng) * (gj_fast_range(fabs(dg)) ? gj_rcp(fabs(dg)) : 1.0 / fabs(dg));
+                sv = (ng == dg) ? 1.0 : fabs(ng) * gj_rcp(fabs(dg));
                 if (!(ag > 0.0)) sv = 0.0;
             }
             if (powered) sv = pow(sv, fz.pw);                        // :226 (sv >= 0 already, :224)

@@ -476,36 +476,47 @@ gom_score_light_kernel(long long n, int G, long long p, const long long* __restr
 #pragma unroll
     for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
     const int b = lane;
-    for (int a = 0; a < ni; ++a) {
-        const int k = sk[a];
-        const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
-        const double wc = (double)sw[a * NBC + b];
-        const double ar = arT[(long long)(p0 + k) * NBC + b];
-        const double r = rT[(o + sc[a]) * NBC + b];
-        S.v[0] += wc;
-        S.v[1] = fma(wc, ar, S.v[1]);
-        S.v[2] = fma(wc, nr, S.v[2]);
-        S.v[3] = fma(wc, r, S.v[3]);
-        S.v[4] = fma(wc, ayc, S.v[4]);
-        S.v[5] = fma(wc * ar, r, S.v[5]);
-        S.v[6] = fma(wc * ar, ayc, S.v[6]);
-        S.v[7] = fma(wc * nr, r, S.v[7]);
-        S.v[8] = fma(wc * nr, ayc, S.v[8]);
-        const double* drow = sd + a * (a - 1) / 2;
-        double q1 = 0, q2 = 0, q3 = 0;
-#pragma unroll 4
-        for (int e = 0; e < a; ++e) {           // unordered pairs e < a, doubled below
-            const double yd = sy[e];
-            const double wd = (double)sw[e * NBC + b];
-            const double dist = drow[e];
-            const double dy = fabs(yc - yd);
-            q1 = fma(wd * dist, dy, q1);
-            q2 = fma(wd * dist, ayc + fabs(yd), q2);
-            q3 = fma(wd * (nr + sn[e]), dy, q3);
+    for (int a0 = 0; a0 < ni; a0 += 4) {
+        // the per-replicate row sums of four list entries at a time: eight independent loads in flight
+        double ar4[4], r4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = min(a0 + u, ni - 1);
+            ar4[u] = arT[(long long)(p0 + sk[a]) * NBC + b];
+            r4[u] = rT[(o + sc[a]) * NBC + b];
         }
-        S.v[9] = fma(2.0 * wc, q1, S.v[9]);
-        S.v[10] = fma(wc, q2, S.v[10]);
-        S.v[11] = fma(wc, q3, S.v[11]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int a = a0 + u;
+            if (a >= ni) break;
+            const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
+            const double wc = (double)sw[a * NBC + b];
+            const double ar = ar4[u], r = r4[u];
+            S.v[0] += wc;
+            S.v[1] = fma(wc, ar, S.v[1]);
+            S.v[2] = fma(wc, nr, S.v[2]);
+            S.v[3] = fma(wc, r, S.v[3]);
+            S.v[4] = fma(wc, ayc, S.v[4]);
+            S.v[5] = fma(wc * ar, r, S.v[5]);
+            S.v[6] = fma(wc * ar, ayc, S.v[6]);
+            S.v[7] = fma(wc * nr, r, S.v[7]);
+            S.v[8] = fma(wc * nr, ayc, S.v[8]);
+            const double* drow = sd + a * (a - 1) / 2;
+            double q1 = 0, q2 = 0, q3 = 0;
+#pragma unroll 4
+            for (int e = 0; e < a; ++e) {           // unordered pairs e < a, doubled below
+                const double yd = sy[e];
+                const double wd = (double)sw[e * NBC + b];
+                const double dist = drow[e];
+                const double dy = fabs(yc - yd);
+                q1 = fma(wd * dist, dy, q1);
+                q2 = fma(wd * dist, ayc + fabs(yd), q2);
+                q3 = fma(wd * (nr + sn[e]), dy, q3);
+            }
+            S.v[9] = fma(2.0 * wc, q1, S.v[9]);
+            S.v[10] = fma(wc, q2, S.v[10]);
+            S.v[11] = fma(wc, q3, S.v[11]);
+        }
     }
     if (lane < nb)
         out[((long long)lane * n + v) * G + g] = vg_finish(S, gagg + (long long)g * GAGG * NBC + lane, vagg + v * VAGG * NBC + lane);
