@@ -460,8 +460,10 @@ gom_score_light_kernel(long long n, int G, long long p, const long long* __restr
     __syncwarp();
     for (int i = lane; i < ni * 8; i += 32)                             // weights: 4 bytes per lane and trip
         reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + sc[i >> 3]] * NBC)[i & 7];
-    // the ni (ni - 1) / 2 distance-cache entries the pair sums need, gathered by all lanes at once: every load is
-    // independent, so the warp pays one L2 latency instead of one per entry
+    // The three pair sums of the expansion enter S_ab only as Q1 - 2 Q2 - 2 Q3 = sum_{a>e} w_a w_e M_ae with the
+    // replicate-independent M_ae = 2 [ d_ae (|y_a - y_e| - |y_a| - |y_e|) - (|X_a| + |X_e|) |y_a - y_e| ], d_ae the
+    // distance-cache entry.  Lanes-as-entries build the M triangle once per pair (every load independent: one L2
+    // latency for the whole gather); lanes-as-replicates then need one FMA per entry.
     const double* Ag = A + a_off[g];
     const int npair = ni * (ni - 1) / 2;
     for (int q = lane; q < npair; q += 32) {
@@ -469,54 +471,38 @@ gom_score_light_kernel(long long n, int G, long long p, const long long* __restr
         while (a * (a - 1) / 2 > q) --a;
         while ((a + 1) * a / 2 <= q) ++a;
         const int e = q - a * (a - 1) / 2;
-        sd[q] = Ag[(long long)sk[a] * ng + sk[e]];
+        const double dist = Ag[(long long)sk[a] * ng + sk[e]];
+        const double ya = sy[a], ye = sy[e], dy = fabs(ya - ye);
+        sd[q] = 2.0 * (dist * (dy - fabs(ya) - fabs(ye)) - (sn[a] + sn[e]) * dy);
     }
     __syncwarp();
     VgSums S;
 #pragma unroll
     for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
     const int b = lane;
-    for (int a0 = 0; a0 < ni; a0 += 4) {
-        // the per-replicate row sums of four list entries at a time: eight independent loads in flight
-        double ar4[4], r4[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int a = min(a0 + u, ni - 1);
-            ar4[u] = arT[(long long)(p0 + sk[a]) * NBC + b];
-            r4[u] = rT[(o + sc[a]) * NBC + b];
+    for (int a = 0; a < ni; ++a) {
+        const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
+        const double wc = (double)sw[a * NBC + b];
+        const double ar = arT[(long long)(p0 + sk[a]) * NBC + b];
+        const double r = rT[(o + sc[a]) * NBC + b];
+        S.v[0] += wc;
+        S.v[1] = fma(wc, ar, S.v[1]);
+        S.v[2] = fma(wc, nr, S.v[2]);
+        S.v[3] = fma(wc, r, S.v[3]);
+        S.v[4] = fma(wc, ayc, S.v[4]);
+        S.v[5] = fma(wc * ar, r, S.v[5]);
+        S.v[6] = fma(wc * ar, ayc, S.v[6]);
+        S.v[7] = fma(wc * nr, r, S.v[7]);
+        S.v[8] = fma(wc * nr, ayc, S.v[8]);
+        const double* mrow = sd + a * (a - 1) / 2;
+        double q0 = 0.0, q1 = 0.0;
+        int e = 0;
+        for (; e + 1 < a; e += 2) {             // unordered pairs e < a
+            q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+            q1 = fma((double)sw[(e + 1) * NBC + b], mrow[e + 1], q1);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int a = a0 + u;
-            if (a >= ni) break;
-            const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
-            const double wc = (double)sw[a * NBC + b];
-            const double ar = ar4[u], r = r4[u];
-            S.v[0] += wc;
-            S.v[1] = fma(wc, ar, S.v[1]);
-            S.v[2] = fma(wc, nr, S.v[2]);
-            S.v[3] = fma(wc, r, S.v[3]);
-            S.v[4] = fma(wc, ayc, S.v[4]);
-            S.v[5] = fma(wc * ar, r, S.v[5]);
-            S.v[6] = fma(wc * ar, ayc, S.v[6]);
-            S.v[7] = fma(wc * nr, r, S.v[7]);
-            S.v[8] = fma(wc * nr, ayc, S.v[8]);
-            const double* drow = sd + a * (a - 1) / 2;
-            double q1 = 0, q2 = 0, q3 = 0;
-#pragma unroll 4
-            for (int e = 0; e < a; ++e) {           // unordered pairs e < a, doubled below
-                const double yd = sy[e];
-                const double wd = (double)sw[e * NBC + b];
-                const double dist = drow[e];
-                const double dy = fabs(yc - yd);
-                q1 = fma(wd * dist, dy, q1);
-                q2 = fma(wd * dist, ayc + fabs(yd), q2);
-                q3 = fma(wd * (nr + sn[e]), dy, q3);
-            }
-            S.v[9] = fma(2.0 * wc, q1, S.v[9]);
-            S.v[10] = fma(wc, q2, S.v[10]);
-            S.v[11] = fma(wc, q3, S.v[11]);
-        }
+        if (e < a) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+        S.v[9] = fma(wc, q0 + q1, S.v[9]);      // enters vg_finish as Q1 (Q2 = Q3 = 0)
     }
     if (lane < nb)
         out[((long long)lane * n + v) * G + g] = vg_finish(S, gagg + (long long)g * GAGG * NBC + lane, vagg + v * VAGG * NBC + lane);
@@ -542,6 +528,7 @@ gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long lo
     int* sc = sk + cap;
     unsigned char* sw = reinterpret_cast<unsigned char*>(sc + cap);
     double* red = reinterpret_cast<double*>(vg_smem + (size_t)cap * VG_ENTRY_BYTES);   // [3][VG_NSUM][32]
+    double* mrows = red + 3 * VG_NSUM * 32;                                             // [4][cap]
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
         const long long wid = heavy_list[it];
         const int g = (int)(wid / n);
@@ -560,8 +547,49 @@ gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long lo
         VgSums S;
 #pragma unroll
         for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
-        // outer index a costs ~a inner trips: warps take a = 4j + (wib ^ (j & 3)) so that all four finish together
-        vg_accumulate(wib, 4, ni, lane, sy, sn, sk, sc, sw, A + a_off[g], ng, p0, o, arT, rT, S);
+        // The four warps split the outer index a (cost ~ a inner trips): a = wib, wib + 4, ...  Per a, lanes-as-entries
+        // build the replicate-independent row M_a. (see the light kernel) in the warp's shared-memory row with
+        // independent distance-cache loads, then lanes-as-replicates take one FMA per entry.
+        {
+            const double* Ag = A + a_off[g];
+            double* mrow = mrows + wib * cap;
+            const int b = lane;
+            for (int a = wib; a < ni; a += 4) {
+                const int k = sk[a];
+                const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
+                const double* arow = Ag + (long long)k * ng;
+#pragma unroll 4
+                for (int e = lane; e < a; e += 32) {
+                    const double dist = arow[sk[e]];
+                    const double ye = sy[e], dy = fabs(yc - ye);
+                    mrow[e] = 2.0 * (dist * (dy - ayc - fabs(ye)) - (nr + sn[e]) * dy);
+                }
+                const double wc = (double)sw[a * NBC + b];
+                const double ar = arT[(long long)(p0 + k) * NBC + b];
+                const double r = rT[(o + sc[a]) * NBC + b];
+                S.v[0] += wc;
+                S.v[1] = fma(wc, ar, S.v[1]);
+                S.v[2] = fma(wc, nr, S.v[2]);
+                S.v[3] = fma(wc, r, S.v[3]);
+                S.v[4] = fma(wc, ayc, S.v[4]);
+                S.v[5] = fma(wc * ar, r, S.v[5]);
+                S.v[6] = fma(wc * ar, ayc, S.v[6]);
+                S.v[7] = fma(wc * nr, r, S.v[7]);
+                S.v[8] = fma(wc * nr, ayc, S.v[8]);
+                __syncwarp();
+                double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+                int e = 0;
+                for (; e + 3 < a; e += 4) {
+                    q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+                    q1 = fma((double)sw[(e + 1) * NBC + b], mrow[e + 1], q1);
+                    q2 = fma((double)sw[(e + 2) * NBC + b], mrow[e + 2], q2);
+                    q3 = fma((double)sw[(e + 3) * NBC + b], mrow[e + 3], q3);
+                }
+                for (; e < a; ++e) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+                S.v[9] = fma(wc, (q0 + q1) + (q2 + q3), S.v[9]);       // enters vg_finish as Q1 (Q2 = Q3 = 0)
+                __syncwarp();                                           // the row is rewritten for the next a
+            }
+        }
         if (wib > 0) {
 #pragma unroll
             for (int i = 0; i < VG_NSUM; ++i) red[((wib - 1) * VG_NSUM + i) * 32 + lane] = S.v[i];
@@ -758,7 +786,7 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
             CK(cudaStreamSynchronize(st));
         }
     }
-    const size_t vg_smem = (size_t)((max_t + 1) & ~1) * VG_ENTRY_BYTES + 3 * VG_NSUM * 32 * sizeof(double);
+    const size_t vg_smem = (size_t)((max_t + 1) & ~1) * (VG_ENTRY_BYTES + 4 * sizeof(double)) + 3 * VG_NSUM * 32 * sizeof(double);
     const size_t va_smem = (size_t)((max_t + 1) & ~1) * 8 + (size_t)max_t * NBC + 16;
     if (vg_smem > 200 * 1024 || va_smem > 200 * 1024) {
         gom_db_free(db);
