@@ -229,6 +229,8 @@ def main():
     warmup = args.warmup if args.warmup is not None else 3
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # its banner goes to stdout, ahead of the JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = _lib.load()
     stream = torch.cuda.current_stream()
