@@ -331,16 +331,20 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
                 // replicate at ~1/75 of the per-cell rate of the dense tensor-core contraction
                 const double dense_cells = 0.5 * (double)j->n_pad * (double)(j->n_pad + 1) * (double)j->p_pad;
                 bool sparse_wins = (double)boot_sparse_cells(j->sparse) * 75.0 < dense_cells;
+                if (!can_mma) sparse_wins = true;                        // both exact; never fall to fp32 needlessly
+                // a resample of P columns has multiplicities summing to P; the low limbs of the sparse path sum in 32 bits
+                if (p > 65536) sparse_wins = false;
                 if (path && !strcmp(path, "sparse")) sparse_wins = true;
                 if (path && !strcmp(path, "mma")) sparse_wins = false;
-                if (!can_mma) sparse_wins = true;                        // both exact; never fall to fp32 needlessly
                 if (!sparse_wins) {
                     boot_sparse_free(j->sparse);
                     j->sparse = nullptr;
-                    if ((rc = ensure(ctx, j->sigfix, (size_t)j->n_pad * j->p_pad * sizeof(uint32_t)))) return bail(rc);
-                    if ((rc = boot_mma_prepare_table(ctx, j->d_sig, n, p, p, j->sigfix.as<uint32_t>(), j->n_pad, j->p_pad, mx,
-                                                     &j->quantum))) return bail(rc);
-                    j->mma_ok = true;
+                    if (can_mma) {
+                        if ((rc = ensure(ctx, j->sigfix, (size_t)j->n_pad * j->p_pad * sizeof(uint32_t)))) return bail(rc);
+                        if ((rc = boot_mma_prepare_table(ctx, j->d_sig, n, p, p, j->sigfix.as<uint32_t>(), j->n_pad, j->p_pad, mx,
+                                                         &j->quantum))) return bail(rc);
+                        j->mma_ok = true;
+                    }
                 }
             }
         }

@@ -13,10 +13,11 @@ struct GomDb {
     long long nnz = 0;          // non-zero location entries of the scored genomes
     int npt = 0;                // sum over GOMs of |R_g|
     int max_ng = 0, max_t = 0;
-    size_t vg_smem = 0, va_smem = 0;
+    size_t vg_smem = 0;
     size_t bytes = 0;
     // genome CSR
     long long* g_ptr = nullptr; int* g_col = nullptr; double* g_val = nullptr;
+    int* g_ord = nullptr;       // per genome: its hit indices ordered by location value (replicate independent)
     // GOM members and point sets
     int* mem_ptr = nullptr; long long* mem_row = nullptr;
     int* pt_ptr = nullptr; int* pt_col = nullptr; int* pos = nullptr;

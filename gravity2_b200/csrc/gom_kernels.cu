@@ -220,34 +220,56 @@ __global__ void gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int*
     o[4 * NBC] = AR2; o[5 * NBC] = ARN; o[6 * NBC] = SAA;
 }
 
-// VA: per-genome weighted row sums r_c = sum_{d in R_v} w_d |y_c - y_d| and aggregates.
-// One block per genome; threadIdx.x = replicate lane, threadIdx.y strides over the genome's hits.  The genome's
-// hit values and its uint8 weights [t][32] are staged in shared memory (dynamic: t * 40 bytes).
-#define VAGG 7   // t, Y1, Y2, Ys, RR1, RR2, RY
-__global__ void genome_rowsums_kernel(const long long* __restrict__ ptr, const int* __restrict__ col,
-                                      const double* __restrict__ val, const unsigned char* __restrict__ wT8,
-                                      double* __restrict__ rT, double* __restrict__ vagg) {
-    extern __shared__ __align__(16) unsigned char va_smem[];
-    const long long v = blockIdx.x;
+#define VAGG 7   // t, Y1, Y2, Ys, RR1, RR2, RY: per-genome aggregates of the weighted row sums r_c = sum_d w_d |y_c - y_d|
+// Order of a genome's hits by location value (ties by hit index), by rank counting: ord[o + rank] = hit index.
+// Built once per database.  grid = n, block = 128; the values are staged in shared memory (dynamic: t * 8 bytes).
+__global__ void genome_order_kernel(const long long* __restrict__ ptr, const double* __restrict__ val, int* __restrict__ ord) {
+    extern __shared__ __align__(16) unsigned char vo_smem[];
+    double* sy = reinterpret_cast<double*>(vo_smem);
+    const long long o = ptr[blockIdx.x];
+    const int t = (int)(ptr[blockIdx.x + 1] - o);
+    for (int d = threadIdx.x; d < t; d += blockDim.x) sy[d] = val[o + d];
+    __syncthreads();
+    for (int c = threadIdx.x; c < t; c += blockDim.x) {
+        const double yc = sy[c];
+        const bool nc = yc != yc;                  // NaN sorts last (a total order keeps the permutation valid)
+        int rank = 0;
+        for (int d = 0; d < t; ++d) {
+            const double yd = sy[d];
+            const bool nd = yd != yd;
+            rank += (!nd && nc) || (nd == nc && (yd < yc || ((yd == yc || nc) && d < c)));
+        }
+        ord[o + rank] = c;
+    }
+}
+
+// VA by prefix sums: with the hits in location order, r_c = sum_d w_d |y_c - y_d| = y_c (W_<c - W_>c) - (S_<c - S_>c),
+// W / S the running sums of w and w y -- t steps per genome and replicate instead of t^2.  One warp per genome,
+// lane = replicate.  grid = ceil(n / 4), block = 128
+__global__ void __launch_bounds__(128)
+genome_rowsums_sorted_kernel(long long n, const long long* __restrict__ ptr, const int* __restrict__ col,
+                             const double* __restrict__ val, const int* __restrict__ ord,
+                             const unsigned char* __restrict__ wT8, double* __restrict__ rT, double* __restrict__ vagg) {
+    const long long v = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int b = threadIdx.x & 31;
+    if (v >= n) return;
     const long long o = ptr[v];
     const int t = (int)(ptr[v + 1] - o);
-    double* sy = reinterpret_cast<double*>(va_smem);                 // [t]
-    unsigned char* sw = va_smem + (size_t)((t + 1) & ~1) * 8;         // [t][32]
-    const int b = threadIdx.x, ny = blockDim.y, tid = threadIdx.y * 32 + threadIdx.x;
-    for (int d = tid; d < t; d += 32 * ny) sy[d] = val[o + d];
-    for (int i = tid; i < t * 8; i += 32 * ny) {                      // 4 weight bytes per thread and trip
-        const int d = i >> 3, q = i & 7;
-        reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + d] * NBC)[q];
+    double Wtot = 0.0, Stot = 0.0;
+    for (int c = 0; c < t; ++c) {
+        const double w = (double)wT8[(long long)col[o + c] * NBC + b];
+        Wtot += w;
+        Stot = fma(w, val[o + c], Stot);
     }
-    __syncthreads();
+    double Wlt = 0.0, Slt = 0.0;
     double T = 0, Y1 = 0, Y2 = 0, Ys = 0, RR1 = 0, RR2 = 0, RY = 0;
-    for (int c = threadIdx.y; c < t; c += ny) {
-        const double yc = sy[c];
-        double r = 0.0;
-#pragma unroll 4
-        for (int d = 0; d < t; ++d) r = fma((double)sw[d * NBC + b], fabs(yc - sy[d]), r);
+    for (int k = 0; k < t; ++k) {
+        const int c = ord[o + k];
+        const double yc = val[o + c], ay = fabs(yc);
+        const double w = (double)wT8[(long long)col[o + c] * NBC + b];
+        // hits tied with y_c contribute |y_c - y_d| = 0 on either side, so "before / after in the order" is enough
+        const double r = yc * (2.0 * Wlt + w - Wtot) - (2.0 * Slt + w * yc - Stot);
         rT[(o + c) * NBC + b] = r;
-        const double w = (double)sw[c * NBC + b], ay = fabs(yc);
         T += w;
         Y1 = fma(w, ay, Y1);
         Y2 = fma(w * yc, yc, Y2);
@@ -255,18 +277,11 @@ __global__ void genome_rowsums_kernel(const long long* __restrict__ ptr, const i
         RR1 = fma(w, r, RR1);
         RR2 = fma(w * r, r, RR2);
         RY = fma(w * r, ay, RY);
+        Wlt += w;
+        Slt = fma(w, yc, Slt);
     }
-    __shared__ double red[8][VAGG][NBC];
-    double q[VAGG] = {T, Y1, Y2, Ys, RR1, RR2, RY};
-    for (int i = 0; i < VAGG; ++i) red[threadIdx.y][i][b] = q[i];
-    __syncthreads();
-    if (threadIdx.y == 0) {
-        for (int i = 0; i < VAGG; ++i) {
-            double sm = 0.0;
-            for (int y = 0; y < ny; ++y) sm += red[y][i][b];
-            vagg[(v * VAGG + i) * NBC + b] = sm;
-        }
-    }
+    double* q = vagg + v * VAGG * NBC + b;
+    q[0 * NBC] = T; q[1 * NBC] = Y1; q[2 * NBC] = Y2; q[3 * NBC] = Ys; q[4 * NBC] = RR1; q[5 * NBC] = RR2; q[6 * NBC] = RY;
 }
 
 // VG: score (genome, GOM) pairs; lane = replicate.  out[b][v][g].
@@ -283,44 +298,6 @@ __global__ void genome_rowsums_kernel(const long long* __restrict__ ptr, const i
 #define VG_NSUM 12
 
 struct VgSums { double v[VG_NSUM]; };   // SW S_ar S_nrm S_r S_y C_arr C_ary C_nr C_ny Q1 Q2 Q3
-
-__device__ __forceinline__ void vg_accumulate(int a_begin, int a_step, int ni, int b, const double* __restrict__ sy,
-                                              const double* __restrict__ sn, const int* __restrict__ sk,
-                                              const int* __restrict__ sc, const unsigned char* __restrict__ sw,
-                                              const double* __restrict__ Ag, int ng, int p0, long long o,
-                                              const double* __restrict__ arT, const double* __restrict__ rT, VgSums& S) {
-    for (int a = a_begin; a < ni; a += a_step) {
-        const int k = sk[a];
-        const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
-        const double wc = (double)sw[a * NBC + b];
-        const double ar = arT[(long long)(p0 + k) * NBC + b];
-        const double r = rT[(o + sc[a]) * NBC + b];
-        S.v[0] += wc;
-        S.v[1] = fma(wc, ar, S.v[1]);
-        S.v[2] = fma(wc, nr, S.v[2]);
-        S.v[3] = fma(wc, r, S.v[3]);
-        S.v[4] = fma(wc, ayc, S.v[4]);
-        S.v[5] = fma(wc * ar, r, S.v[5]);
-        S.v[6] = fma(wc * ar, ayc, S.v[6]);
-        S.v[7] = fma(wc * nr, r, S.v[7]);
-        S.v[8] = fma(wc * nr, ayc, S.v[8]);
-        const double* arow = Ag + (long long)k * ng;
-        double q1 = 0, q2 = 0, q3 = 0;
-#pragma unroll 8
-        for (int e = 0; e < a; ++e) {           // unordered pairs e < a, doubled below
-            const double yd = sy[e];
-            const double wd = (double)sw[e * NBC + b];
-            const double dist = arow[sk[e]];
-            const double dy = fabs(yc - yd);
-            q1 = fma(wd * dist, dy, q1);
-            q2 = fma(wd * dist, ayc + fabs(yd), q2);
-            q3 = fma(wd * (nr + sn[e]), dy, q3);
-        }
-        S.v[9] = fma(2.0 * wc, q1, S.v[9]);
-        S.v[10] = fma(wc, q2, S.v[10]);
-        S.v[11] = fma(wc, q3, S.v[11]);
-    }
-}
 
 __device__ __forceinline__ double vg_finish(const VgSums& S, const double* __restrict__ ga, const double* __restrict__ va) {
     const double SW = S.v[0], S_ar = S.v[1], S_nrm = S.v[2], S_r = S.v[3], S_y = S.v[4], C_arr = S.v[5], C_ary = S.v[6],
@@ -351,31 +328,6 @@ __device__ __forceinline__ double vg_finish(const VgSums& S, const double* __res
         if (dvA > 0.0 && dvB > 0.0) res = dcov / sqrt(dvA * dvB);
     }
     return res;
-}
-
-// scan the genome's hits against the GOM's column set (one warp, column order preserved); entries beyond
-// `cap` are counted but not stored
-__device__ __forceinline__ int vg_scan(int lane, int t, long long o, const int* __restrict__ col,
-                                       const double* __restrict__ val, const int* __restrict__ posg,
-                                       const double* __restrict__ nrm, int p0, int cap, double* sy, double* sn, int* sk, int* sc) {
-    int ni = 0;
-    for (int c0 = 0; c0 < t; c0 += 32) {
-        const int c = c0 + lane;
-        int k = -1;
-        if (c < t) k = posg[col[o + c]];
-        const unsigned m = __ballot_sync(0xffffffffu, k >= 0);
-        if (k >= 0) {
-            const int w = ni + __popc(m & ((1u << lane) - 1u));
-            if (w < cap) {
-                sy[w] = val[o + c];
-                sn[w] = nrm[p0 + k];
-                sk[w] = k;
-                sc[w] = c;
-            }
-        }
-        ni += __popc(m);
-    }
-    return ni;
 }
 
 // Intersection lists, built once per database (they do not depend on the replicate): one warp per (GOM, genome)
@@ -623,7 +575,7 @@ static cudaError_t dalloc(T** p, size_t count, size_t* total) {
 
 void gom_db_free(GomDb* db) {
     if (!db) return;
-    cudaFree(db->g_ptr); cudaFree(db->g_col); cudaFree(db->g_val);
+    cudaFree(db->g_ptr); cudaFree(db->g_col); cudaFree(db->g_val); cudaFree(db->g_ord);
     cudaFree(db->mem_ptr); cudaFree(db->mem_row); cudaFree(db->pt_ptr); cudaFree(db->pt_col);
     cudaFree(db->pos); cudaFree(db->x_off); cudaFree(db->a_off); cudaFree(db->X); cudaFree(db->nrm);
     cudaFree(db->A); cudaFree(db->wT); cudaFree(db->arT); cudaFree(db->sqT); cudaFree(db->rT);
@@ -750,6 +702,14 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
         for (int64_t v = 0; v < n; ++v) max_t = std::max<int>(max_t, (int)(ptr_h[v + 1] - ptr_h[v]));
     }
     db->max_t = max_t;
+    CK(dalloc(&db->g_ord, db->nnz, &db->bytes));
+    if (n && max_t) {
+        const size_t vo = (size_t)max_t * 8;
+        if (vo > 200 * 1024) { gom_db_free(db); return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a genome has %d location hits", max_t); }
+        CK(cudaFuncSetAttribute(genome_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(vo, 1024)));
+        genome_order_kernel<<<(unsigned)n, 128, vo, st>>>(db->g_ptr, db->g_val, db->g_ord);
+        ctx->launches++;
+    }
     CK(dalloc(&db->wT8, p * NBC, &db->bytes));
     CK(dalloc(&db->wG, (size_t)db->npt * NBC, &db->bytes));
     CK(dalloc(&db->flag, 2, &db->bytes));          // [0] weight overflow, [1] heavy-list length
@@ -787,15 +747,13 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
         }
     }
     const size_t vg_smem = (size_t)((max_t + 1) & ~1) * (VG_ENTRY_BYTES + 4 * sizeof(double)) + 3 * VG_NSUM * 32 * sizeof(double);
-    const size_t va_smem = (size_t)((max_t + 1) & ~1) * 8 + (size_t)max_t * NBC + 16;
-    if (vg_smem > 200 * 1024 || va_smem > 200 * 1024) {
+    if (vg_smem > 200 * 1024) {
         gom_db_free(db);
         return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a genome has %d location hits; the GOM scoring kernels stage at most %d per genome "
                         "in shared memory", max_t, (int)(190 * 1024 / VG_ENTRY_BYTES));
     }
-    db->vg_smem = vg_smem; db->va_smem = va_smem;
+    db->vg_smem = vg_smem;
     CK(cudaFuncSetAttribute(gom_score_heavy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(vg_smem, 1024)));
-    CK(cudaFuncSetAttribute(genome_rowsums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(va_smem, 1024)));
     CK(cudaStreamSynchronize(st));
     cudaFree(flag); cudaFree(scan);
     CK(cudaGetLastError());
@@ -826,8 +784,7 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
         }
         gom_aggregates_kernel<<<(unsigned)G, 32, 0, st>>>(db->pt_ptr, db->pt_col, db->nrm, db->wT, db->arT, db->sqT, db->gagg);
         ctx->launches++;
-        dim3 bv(32, 8);
-        genome_rowsums_kernel<<<(unsigned)n, bv, db->va_smem, st>>>(db->g_ptr, db->g_col, db->g_val, db->wT8, db->rT, db->vagg);
+        genome_rowsums_sorted_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(n, db->g_ptr, db->g_col, db->g_val, db->g_ord, db->wT8, db->rT, db->vagg);
         ctx->launches++;
         {
             const long long total_w = n * G;
