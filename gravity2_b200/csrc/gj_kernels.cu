@@ -716,6 +716,14 @@ int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t 
     return GV2_OK;
 }
 
+extern "C" int gv2_dev_gj_fused(gv2_ctx* ctx, const float* tab, int64_t tab_replicate_stride, int64_t n, int64_t n_pad,
+                                int64_t k_pad, int64_t nb, const gv2_gj_component* comp_p, const gv2_gj_component* comp_g,
+                                int scheme, double p, int out_kind, double* out, int64_t out_replicate_stride) {
+    if (!ctx) return GV2_ERR_ARG;
+    return gj_fused_launch(ctx, tab, tab_replicate_stride, n, n_pad, k_pad, nb, comp_p, comp_g, scheme, p, out_kind, out,
+                           out_replicate_stride);
+}
+
 extern "C" int gv2_dev_gj_min_sums(gv2_ctx* ctx, const float* tab, int64_t n_pad, int64_t k_pad,
                                    int64_t tile_begin, int64_t tile_end, const float* w,
                                    int64_t nb, int ksplit, double* ws) {

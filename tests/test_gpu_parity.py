@@ -419,6 +419,69 @@ def test_device_primitives_packed_tiles_roundtrip(eng):
     lib.gv2_destroy(ctx)
 
 
+@pytest.mark.parametrize("scheme,pw,kind", [("PG", 1.0, "D"), ("PG", 2.0, "S"), ("G", 1.0, "S"), ("G", 0.5, "D")])
+def test_fused_tail_equals_separate_kernels(eng, scheme, pw, kind):
+    """gv2_dev_gj_fused (pair sums in registers + epilogue) against gv2_dev_gj_min_sums + gv2_dev_gj_epilogue on the same
+    device tables: two replicate tables of 232 columns (two 128-column slabs in the separate path), a genome with a NaN
+    entry in each component, an all-zero genome, a duplicate genome; n not a multiple of 64."""
+    import ctypes as C
+    import torch
+    from gravity2_b200 import _lib
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    assert lib.gv2_create_on_stream(0, C.c_void_p(torch.cuda.current_stream().cuda_stream), C.byref(ctx)) == 0
+    vp = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+    rng = np.random.default_rng(11)
+    n, p, g, nb = 301, 500, 232, 2
+    n_pad, p_pad, g_pad = 384, 512, 256
+    ntl = int(lib.gv2_num_tiles(n))
+    sig = synth.make_tables(n, p, 4, 0.2, seed=5).sig
+    sig[9] = 0.0; sig[40] = sig[3]; sig[17, 5] = np.nan
+    gom = rng.random((nb, n, g)) * (rng.random((nb, n, g)) < 0.7)
+    gom[:, 9] = 0.0; gom[:, 40] = gom[:, 3]; gom[1, 23, 7] = np.nan
+    out_kind = _lib.OUT_DISTANCE if kind == "D" else _lib.OUT_SIMILARITY
+
+    def prep(a64, k, k_pad):
+        d = torch.from_numpy(np.ascontiguousarray(a64)).cuda()
+        tab = torch.empty((n_pad, k_pad), dtype=torch.float32, device="cuda")
+        rs = torch.empty(n, dtype=torch.float64, device="cuda")
+        nf = torch.empty(n, dtype=torch.uint8, device="cuda")
+        assert lib.gv2_dev_prepare_table(ctx, vp(d), n, k, k, 0.0, 0, vp(tab), n_pad, k_pad, vp(rs), vp(nf)) == 0
+        return tab, rs, nf
+
+    ptab, prs, pnf = prep(sig, p, p_pad)
+    wsp = torch.empty((ntl, 128 * 128), dtype=torch.float64, device="cuda")
+    assert lib.gv2_dev_gj_min_sums(ctx, vp(ptab), n_pad, p_pad, 0, ntl, None, 1, 1, vp(wsp)) == 0
+    cp = _lib.GjComponent(min_sums=wsp.data_ptr(), rowsums=prs.data_ptr(), nanflags=pnf.data_ptr(), ksplit=1)
+    gtabs = torch.empty((nb, n_pad, g_pad), dtype=torch.float32, device="cuda")
+    grs = torch.empty((nb, n), dtype=torch.float64, device="cuda")
+    gnf = torch.empty((nb, n), dtype=torch.uint8, device="cuda")
+    sep = torch.empty((nb, n, n), dtype=torch.float64, device="cuda")
+    for b in range(nb):
+        tab, rs, nf = prep(gom[b], g, g_pad)
+        gtabs[b], grs[b], gnf[b] = tab, rs, nf
+        wsg = torch.empty((ntl, 128 * 128), dtype=torch.float64, device="cuda")
+        assert lib.gv2_dev_gj_min_sums(ctx, vp(tab), n_pad, g_pad, 0, ntl, None, 1, 1, vp(wsg)) == 0
+        cg = _lib.GjComponent(min_sums=wsg.data_ptr(), rowsums=rs.data_ptr(), nanflags=nf.data_ptr(), ksplit=1)
+        assert lib.gv2_dev_gj_epilogue(ctx, n, 0, ntl, 1, C.byref(cp), C.byref(cg), None, _lib.SCHEMES[scheme], pw, out_kind, 0,
+                                       vp(sep[b]), 0) == 0, lib.gv2_last_error(ctx)
+    fused = torch.full((nb, n, n), -7.0, dtype=torch.float64, device="cuda")
+    cgf = _lib.GjComponent(min_sums=None, rowsums=grs.data_ptr(), nanflags=gnf.data_ptr(), ksplit=1,
+                           replicate_stride_rows=n, replicate_stride_nan=n)
+    assert lib.gv2_dev_gj_fused(ctx, vp(gtabs), n_pad * g_pad, n, n_pad, g_pad, nb, C.byref(cp) if scheme == "PG" else None,
+                                C.byref(cgf), _lib.SCHEMES[scheme], pw, out_kind, vp(fused), n * n) == 0, lib.gv2_last_error(ctx)
+    torch.cuda.synchronize()
+    a, b = fused.cpu().numpy(), sep.cpu().numpy()
+    assert np.array_equal(a, np.transpose(a, (0, 2, 1)))
+    # same fp32 cell arithmetic; slabs of 64 (fused) against 128 columns and one rsqrt against two divisions + sqrt
+    assert np.abs(a - b).max() <= 2e-7
+    zero_row = 1.0 if kind == "D" else 0.0
+    assert np.all(a[:, 9, :] == zero_row) and np.all(a[:, 17, :] == zero_row if scheme == "PG" else True) and np.all(a[1, 23, :] == zero_row)
+    # duplicate genomes: 1 up to the fp32 slab rounding of the tile kernels (the job's integer pair sums give exactly 1)
+    assert np.all(np.abs(a[:, 3, 40] - (0.0 if kind == "D" else 1.0)) <= 2e-7)
+    lib.gv2_destroy(ctx)
+
+
 def test_error_paths(eng):
     import gravity2_b200 as G
     with pytest.raises(ValueError):

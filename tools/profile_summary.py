@@ -1,0 +1,74 @@
+"""Turn ncu outputs into the committed summaries under profiles/.
+
+  python tools/profile_summary.py launches <ncu --csv launch list> <out.csv> "<command line>"
+  python tools/profile_summary.py full <report.ncu-rep> <out.csv>          (needs ncu on PATH; one row block per kernel)
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+
+
+def launches(src, dst, cmd):
+    rows = list(csv.reader(open(src)))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr = rows[start]
+    ci = {h: i for i, h in enumerate(hdr)}
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[start + 1:]:
+        if len(r) < len(hdr) or r[ci["Metric Name"]] != "gpu__time_duration.sum":
+            continue
+        k = r[ci["Kernel Name"]].split("(")[0].replace("void ", "")
+        v = float(r[ci["Metric Value"]].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[ci["Metric Unit"]], 1e-6)
+        agg[k][0] += 1
+        agg[k][1] += v
+    tot = sum(v[1] for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list summary -- `{cmd}`\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES, not absolutes).\n")
+        f.write(f"# total kernel time {tot:.1f} ms over {sum(v[0] for v in agg.values())} launches (warm-up + timed step + job set-up)\n")
+        f.write("kernel,launches,total_ms,share\n")
+        for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
+            f.write(f"{k[:70]},{v[0]},{v[1]:.3f},{v[1] / tot:.4f}\n")
+
+
+def full(rep, dst):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full --clock-control none, {rep.split('/')[-1]}: selected metrics per captured launch\n")
+        for vals in rows[2:]:
+            d = dict(zip(hdr, vals))
+            u = dict(zip(hdr, units))
+            f.write(f"kernel,{d.get('Kernel Name', '?')[:90].replace(',', ';')}\n")
+            f.write(f"grid,{d.get('Grid Size', '').replace(',', ' ')},block,{d.get('Block Size', '').replace(',', ' ')}\n")
+            for k in KEYS:
+                if k in d:
+                    f.write(f"{k},{d[k]},{u.get(k, '')}\n")
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        full(sys.argv[2], sys.argv[3])
