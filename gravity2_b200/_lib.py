@@ -52,6 +52,9 @@ PROTOTYPES = {
     "gv2_similarity_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp, C.c_int,
                                       C.c_double, C.c_double, C.c_int, C.c_int, c_vp]),
     "gv2_similarity_nbhd_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, C.c_double, C.c_double, c_vp, c_vp]),
+    "gv2_linkage_host": (C.c_int, [c_vp, c_vp, c_i64, C.c_char_p, c_vp]),
+    "gv2_newick_from_linkage": (C.c_int, [c_vp, c_i64, C.POINTER(C.c_char_p), c_vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "gv2_job_replicates_newick": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, C.c_char_p, C.POINTER(C.c_char_p), c_vp, c_vp]),
     "gv2_gom_table_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64,
                                      C.c_int, c_vp]),
     "gv2_shared_counts_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
@@ -93,6 +96,7 @@ _lib = None
 
 
 REPLICATE_CB = C.CFUNCTYPE(C.c_int, c_i64, c_vp, c_vp)      # gv2_replicate_cb
+NEWICK_CB = C.CFUNCTYPE(C.c_int, c_i64, c_vp, C.c_size_t, c_vp)   # gv2_newick_cb
 
 
 class GravityNativeError(RuntimeError):

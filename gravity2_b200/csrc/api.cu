@@ -39,6 +39,11 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
                        int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* wT_scratch, int* overflow_flag,
                        double* ws);
 
+int lk_launch(gv2_ctx* ctx, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, int* dev_chain, double* dev_Zraw);
+void lk_finalize_host(const double* raw, int64_t n, double* Z);
+extern "C" int gv2_newick_from_linkage(const double* Z, int64_t n, const char* const* leaf_names, char* out, size_t out_cap,
+                                       size_t* out_len);
+
 static thread_local std::string g_create_error;
 
 int gv2_fail(gv2_ctx* ctx, int code, const char* fmt, ...) {
@@ -439,8 +444,70 @@ extern "C" int gv2_job_base(gv2_job* job, int64_t tile_begin, int64_t tile_end, 
 // pair sums for up to 128 replicates per CTA, GOM scoring 32 replicates per warp); inside it, sub-chunks of at
 // most ring_len / 2 replicates run the cheap per-replicate tail (GOM Jaccard sums, epilogue) into one half of
 // the ring while the other half drains to the host.
-extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
-                                         int64_t ring_len, double* host_out, gv2_replicate_cb cb_fn, void* cb_user) {
+// Device-side consumer of a sub-chunk of replicate matrices: UPGMA on the ring slots, linkage rows to the host,
+// Newick strings to the caller (gv2_job_replicates_newick).  Two buffers: the host finishes sub-chunk k - 1 (sort,
+// relabel, print) while the GPU works on sub-chunk k.
+struct TreeSink {
+    gv2_ctx* ctx = nullptr;
+    int64_t n = 0, cap = 0;
+    const char* const* names = nullptr;
+    gv2_newick_cb cb = nullptr;
+    void* user = nullptr;
+    int* chain = nullptr;
+    double* zdev[2] = {nullptr, nullptr};
+    double* zhost[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int64_t pend_b0[2] = {0, 0}, pend_cnt[2] = {0, 0};
+    int cur = 0;
+    std::vector<double> Z;
+    std::string text;
+    ~TreeSink() {
+        cudaFree(chain);
+        for (int h = 0; h < 2; ++h) { cudaFree(zdev[h]); cudaFreeHost(zhost[h]); if (ev[h]) cudaEventDestroy(ev[h]); }
+    }
+    int init(gv2_ctx* c, int64_t n_, int64_t cap_) {
+        ctx = c; n = n_; cap = cap_;
+        const size_t zb = (size_t)cap * std::max<int64_t>(1, n - 1) * 4 * sizeof(double);
+        GV2_CUDA(ctx, cudaMalloc((void**)&chain, (size_t)cap * std::max<int64_t>(1, n) * sizeof(int)));
+        for (int h = 0; h < 2; ++h) {
+            GV2_CUDA(ctx, cudaMalloc((void**)&zdev[h], zb));
+            GV2_CUDA(ctx, cudaMallocHost((void**)&zhost[h], zb));
+            GV2_CUDA(ctx, cudaEventCreateWithFlags(&ev[h], cudaEventDisableTiming));
+        }
+        Z.resize((size_t)std::max<int64_t>(1, n - 1) * 4);
+        return GV2_OK;
+    }
+    // matrices of replicates [b0, b0 + cnt) are in dev[0 .. cnt) (stride n*n): cluster them, fetch the rows
+    int enqueue(double* dev, int64_t b0, int64_t cnt) {
+        int rc = lk_launch(ctx, dev, n * n, n, cnt, chain, zdev[cur]);
+        if (rc) return rc;
+        if (n > 1)
+            GV2_CUDA(ctx, cudaMemcpyAsync(zhost[cur], zdev[cur], (size_t)cnt * (n - 1) * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        GV2_CUDA(ctx, cudaEventRecord(ev[cur], ctx->stream));
+        pend_b0[cur] = b0; pend_cnt[cur] = cnt;
+        cur ^= 1;
+        return GV2_OK;
+    }
+    int drain(int h) {
+        if (pend_cnt[h] == 0) return GV2_OK;
+        cudaError_t e = cudaEventSynchronize(ev[h]);
+        if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "linkage rows: %s", cudaGetErrorString(e));
+        for (int64_t k = 0; k < pend_cnt[h]; ++k) {
+            if (n > 1) lk_finalize_host(zhost[h] + (size_t)k * (n - 1) * 4, n, Z.data());
+            size_t len = 0;
+            gv2_newick_from_linkage(Z.data(), n, names, nullptr, 0, &len);
+            text.resize(len + 1);
+            gv2_newick_from_linkage(Z.data(), n, names, &text[0], len + 1, &len);
+            if (cb(pend_b0[h] + k, text.c_str(), len, user) != 0)
+                return gv2_fail(ctx, GV2_ERR_ARG, "tree callback asked to stop at replicate %lld", (long long)(pend_b0[h] + k));
+        }
+        pend_cnt[h] = 0;
+        return GV2_OK;
+    }
+};
+
+static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring, int64_t ring_len,
+                           double* host_out, gv2_replicate_cb cb_fn, void* cb_user, TreeSink* sink) {
     if (!job || !dev_weights || !dev_ring || nb < 0 || ring_len <= 0 || (cb_fn && !host_out))
         return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_stream: bad arguments");
     if (cb_fn && ring_len < 2 && nb > 1)
@@ -452,7 +519,7 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
     const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
     ring_len = std::min(ring_len, nb);
     // sub-chunk: half the ring when results stream to the host (ping-pong), else the whole ring
-    const int64_t sub = (host_out && ring_len >= 2) ? ring_len / 2 : ring_len;
+    const int64_t sub = (!sink && host_out && ring_len >= 2) ? ring_len / 2 : ring_len;
     // super-chunk: bounded by the fp64 pair-sum workspace of the signature table (+ the GOM tables)
     const size_t per_rep = (job->need_p ? ntl * tile_elems * sizeof(double) + (size_t)job->p_pad : 0) +
                            (job->need_g ? (size_t)job->n_pad * job->g_pad * 4 + (size_t)n * g * 8 : 0) + (size_t)n * 8 * 2;
@@ -558,6 +625,10 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
                 if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
                                               dev_ring + slot * n * n, n * n))) return rc;
             }
+            if (sink) {     // cluster this sub-chunk on the device; meanwhile finish the previous one on the host
+                if ((rc = sink->enqueue(dev_ring + slot * n * n, s0 + c0, cb))) return rc;
+                if ((rc = sink->drain(sink->cur))) return rc;
+            }
             if (host_out) {
                 GV2_CUDA(ctx, cudaEventRecord(job->ev_ready[half], ctx->stream));
                 GV2_CUDA(ctx, cudaStreamWaitEvent(job->copy_stream, job->ev_ready[half], 0));
@@ -577,6 +648,10 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
         if ((rc = deliver(half))) return rc;
         if ((rc = deliver(half ^ 1))) return rc;
     }
+    if (sink) {
+        if ((rc = sink->drain(sink->cur))) return rc;
+        if ((rc = sink->drain(sink->cur ^ 1))) return rc;
+    }
     if (host_out) GV2_CUDA(ctx, cudaStreamSynchronize(job->copy_stream));
     if (used_mma) {     // multiplicities above 255 do not fit the uint8 operand: refuse rather than wrap
         int flag = 0;
@@ -586,6 +661,29 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
                                   flag == 2 ? "a replicate's column multiplicities sum to more than 65536" : "a column multiplicity exceeds 255");
     }
     return GV2_OK;
+}
+
+extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
+                                         int64_t ring_len, double* host_out, gv2_replicate_cb cb_fn, void* cb_user) {
+    return replicates_impl(job, dev_weights, nb, dev_ring, ring_len, host_out, cb_fn, cb_user, nullptr);
+}
+
+// The bootstrap loops keep only the dendrogram of a replicate (app/src/pl1_graphs.py:108-117): replicate distance
+// matrices are clustered where they are (UPGMA, device) and only their Newick strings reach the caller, in replicate
+// order.  dev_ring [ring_len][n][n] is scratch: ring_len matrices are clustered concurrently (one CTA each).
+extern "C" int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring, int64_t ring_len,
+                                         const char* method, const char* const* leaf_names, gv2_newick_cb cb, void* user) {
+    if (!job || !leaf_names || !cb) return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_newick: bad arguments");
+    if (!method || strcmp(method, "average"))
+        return gv2_fail(job->ctx, GV2_ERR_UNSUPPORTED, "gv2_job_replicates_newick: linkage method '%s' (built: average)", method ? method : "");
+    if (job->out_kind != GV2_OUT_DISTANCE) return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_replicates_newick: the job must produce distances");
+    if (nb <= 0 || job->n == 0) return GV2_OK;
+    GV2_CUDA(job->ctx, cudaSetDevice(job->ctx->device));
+    TreeSink sink;
+    int rc = sink.init(job->ctx, job->n, std::min<int64_t>(ring_len, nb));
+    if (rc) return rc;
+    sink.names = leaf_names; sink.cb = cb; sink.user = user;
+    return replicates_impl(job, dev_weights, nb, dev_ring, ring_len, nullptr, nullptr, nullptr, &sink);
 }
 
 extern "C" int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out) {

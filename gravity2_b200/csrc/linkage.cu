@@ -1,0 +1,300 @@
+// Batched UPGMA dendrograms on the device + Newick strings on the host.
+//
+// Reference: DistMat2Tree, app/utils/dist_mat_to_tree.py:5-21 -- the distance matrix is zero-clamped, its upper
+// triangle is handed to scipy.cluster.hierarchy.linkage(method) (scipy is a third-party dependency of the
+// reference, pinned scipy==1.14.0 in requirements.txt:4; its published algorithm for method "average" is the
+// nearest-neighbour chain of scipy/cluster/_hierarchy.pyx `nn_chain`, restated here), to_tree() turns the linkage
+// matrix into nodes and GetNewick (app/utils/get_newick.py:1-13) prints them.  The bootstrap loops
+// (app/src/pl1_graphs.py:108-117, app/src/virus_classification.py:316-330) do this once per replicate and keep
+// only the Newick line, so with the clustering on the device a replicate's 0.8 GB distance matrix never has to
+// leave HBM: 320 KB of linkage rows do.
+//
+// nn_chain, as scipy runs it (the order of every comparison decides how ties fall, and real distance matrices
+// are full of exact ties at D = 1):
+//   chain: a stack of clusters, each the nearest neighbour of the one below.  With an empty chain start at the
+//   lowest-numbered live cluster.  For the top x: y = argmin_i D[x][i] over live i != x, scanning i upwards with a
+//   strict `<`, starting from the previous chain element as the incumbent (so it wins ties).  If y is that previous
+//   element the two are mutual nearest neighbours: merge; else push y.
+//   merge (x < y after a swap): row k = (x, y, D[x][y], |x| + |y|); x dies, y becomes the union,
+//   D[i][y] = (|x| D[i][x] + |y| D[i][y]) / (|x| + |y|) for every live i (three separately rounded operations).
+//   Afterwards the rows are stably sorted by distance and relabelled with a union-find (host, below).
+//
+// One CTA per matrix (the algorithm is a chain of ~3n dependent row scans: parallelism comes from clustering
+// many replicates at once); the matrix is the full symmetric n x n float64 block the fused tail wrote, so a row
+// scan is one contiguous 8n-byte read; it is updated in place (row y contiguous, column y scattered).
+#include "common.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#define LK_THREADS 1024
+
+struct LkBest { double d; int i; };
+
+__device__ __forceinline__ LkBest lk_min(LkBest a, LkBest b) {
+    // smaller distance; on equal distances the lower index (what an upward scan with a strict `<` keeps)
+    if (b.d < a.d || (b.d == a.d && b.i < a.i)) return b;
+    return a;
+}
+
+// grid = matrices, block = LK_THREADS; dynamic shared memory: n ints (cluster sizes)
+// D: [nb][n][n] float64, destroyed; chain: [nb][n] int scratch; Zraw: [nb][n-1][4] float64 in merge order
+__global__ void __launch_bounds__(LK_THREADS, 1)
+lk_nn_chain_average_kernel(double* __restrict__ Dall, long long d_stride, int n, int* __restrict__ chain_all,
+                           double* __restrict__ Zall) {
+    extern __shared__ int lk_size[];
+    __shared__ LkBest s_warp[LK_THREADS / 32];
+    __shared__ int s_x, s_y, s_len, s_merge, s_first;
+    __shared__ double s_min;
+    double* D = Dall + (size_t)blockIdx.x * d_stride;
+    int* chain = chain_all + (size_t)blockIdx.x * n;
+    double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += LK_THREADS) lk_size[i] = 1;
+    if (tid == 0) { s_len = 0; s_first = 0; }
+    __syncthreads();
+    for (int k = 0; k < n - 1; ++k) {
+        if (tid == 0 && s_len == 0) {
+            int f = s_first;
+            while (lk_size[f] == 0) ++f;              // lowest-numbered live cluster (dead ones never come back)
+            s_first = f;
+            chain[0] = f;
+            s_len = 1;
+        }
+        __syncthreads();
+        // grow the chain until its two top elements are mutual nearest neighbours
+        while (true) {
+            const int len = s_len;
+            const int x = chain[len - 1];
+            const int prev = len > 1 ? chain[len - 2] : -1;
+            const double* row = D + (size_t)x * n;
+            LkBest best{INFINITY, 0x7fffffff};
+            for (int i = tid; i < n; i += LK_THREADS) {
+                if (lk_size[i] == 0 || i == x) continue;
+                const double d = row[i];
+                if (d < best.d) { best.d = d; best.i = i; }      // ascending i per thread: first minimum kept
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                LkBest other;
+                other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+                other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+                best = lk_min(best, other);
+            }
+            if (lane == 0) s_warp[warp] = best;
+            __syncthreads();
+            if (warp == 0) {
+                best = s_warp[lane];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    LkBest other;
+                    other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+                    other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+                    best = lk_min(best, other);
+                }
+                if (lane == 0) {
+                    // the previous chain element is the incumbent: a scanned cluster replaces it only if strictly closer
+                    int y = best.i;
+                    double cur = best.d;
+                    if (prev >= 0) {
+                        const double dp = row[prev];
+                        if (!(best.d < dp)) { y = prev; cur = dp; }
+                    } else if (best.i == 0x7fffffff) {
+                        y = 0;                        // every distance NaN: scipy keeps its stale y; unreachable for cleaned matrices
+                    }
+                    if (prev >= 0 && y == prev) {
+                        s_merge = 1;
+                    } else {
+                        s_merge = 0;
+                        chain[len] = y;
+                        s_len = len + 1;
+                    }
+                    s_x = x; s_y = y; s_min = cur;
+                }
+            }
+            __syncthreads();
+            if (s_merge) break;
+        }
+        // merge the two top elements
+        int x = s_x, y = s_y;
+        if (x > y) { const int t = x; x = y; y = t; }
+        const int nx = lk_size[x], ny = lk_size[y];
+        const double dmin = s_min;
+        __syncthreads();                              // everyone has read the sizes and s_* before they change
+        if (tid == 0) {
+            Z[(size_t)k * 4 + 0] = (double)x;
+            Z[(size_t)k * 4 + 1] = (double)y;
+            Z[(size_t)k * 4 + 2] = dmin;
+            Z[(size_t)k * 4 + 3] = (double)(nx + ny);
+            lk_size[x] = 0;
+            lk_size[y] = nx + ny;
+            s_len -= 2;
+        }
+        __syncthreads();
+        const double* rx = D + (size_t)x * n;
+        double* ry = D + (size_t)y * n;
+        const double fx = (double)nx, fy = (double)ny, fs = (double)(nx + ny);
+        for (int i = tid; i < n; i += LK_THREADS) {
+            if (lk_size[i] == 0 || i == y) continue;
+            // (size_x * d_xi + size_y * d_yi) / (size_x + size_y): three roundings, no FMA contraction
+            const double v = __ddiv_rn(__dadd_rn(__dmul_rn(fx, rx[i]), __dmul_rn(fy, ry[i])), fs);
+            ry[i] = v;
+            D[(size_t)i * n + y] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// scipy clusters the UPPER triangle of the matrix it is given (dist_mat_to_tree.py:9): mirror it down, so that an
+// asymmetric input behaves as in the reference.  grid = (ceil(n/32), ceil(n/8)), block = (32, 8)
+__global__ void lk_mirror_upper_kernel(double* __restrict__ D, long long n) {
+    const long long j = (long long)blockIdx.x * 32 + threadIdx.x, i = (long long)blockIdx.y * 8 + threadIdx.y;
+    if (i < n && j < n && j > i) D[j * n + i] = D[i * n + j];
+}
+
+// ---------------------------------------------------------------------------------- host: sort, relabel, Newick
+// Rows in merge order -> scipy's linkage matrix: stable sort by distance, then union-find labels
+// (scipy/cluster/_hierarchy.pyx: nn_chain tail + label()).
+static void lk_finalize(const double* raw, int64_t n, double* Z) {
+    const int64_t m = n - 1;
+    std::vector<int64_t> order(m);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return raw[a * 4 + 2] < raw[b * 4 + 2]; });
+    std::vector<int64_t> parent(2 * n - 1), size(2 * n - 1, 1);
+    std::iota(parent.begin(), parent.end(), 0);
+    int64_t next = n;
+    auto find = [&](int64_t x) {
+        int64_t p = x;
+        while (parent[x] != x) x = parent[x];
+        while (parent[p] != x) { const int64_t q = parent[p]; parent[p] = x; p = q; }
+        return x;
+    };
+    for (int64_t i = 0; i < m; ++i) {
+        const double* r = raw + order[i] * 4;
+        const int64_t xr = find((int64_t)r[0]), yr = find((int64_t)r[1]);
+        Z[i * 4 + 0] = (double)std::min(xr, yr);
+        Z[i * 4 + 1] = (double)std::max(xr, yr);
+        Z[i * 4 + 2] = r[2];
+        parent[xr] = next; parent[yr] = next;
+        size[next] = size[xr] + size[yr];
+        Z[i * 4 + 3] = (double)size[next];
+        ++next;
+    }
+}
+
+// GetNewick(to_tree(Z), "", root.dist, names), app/utils/get_newick.py:1-13: children are printed right first, every
+// branch length is "%f" of (parent height - node height), the root closes with ");".  Iterative (the reference recurses).
+static void lk_newick(const double* Z, int64_t n, const char* const* names, std::string& out) {
+    out.clear();
+    if (n <= 0) return;
+    char buf[64];
+    if (n == 1) {                                     // to_tree of an empty linkage is the single leaf; its parent height is its own
+        out += names[0];
+        snprintf(buf, sizeof buf, ":%f", 0.0);
+        out += buf;
+        return;
+    }
+    struct Frame { int64_t node; double parent; int stage; };
+    std::vector<Frame> st;
+    const int64_t root = 2 * n - 2;
+    auto height = [&](int64_t v) { return v < n ? 0.0 : Z[(v - n) * 4 + 2]; };
+    st.push_back({root, height(root), 0});
+    while (!st.empty()) {
+        Frame& f = st.back();
+        if (f.node < n) {
+            out += names[f.node];
+            snprintf(buf, sizeof buf, ":%f", f.parent - 0.0);
+            out += buf;
+            st.pop_back();
+            continue;
+        }
+        const int64_t k = f.node - n;
+        const double h = Z[k * 4 + 2];
+        if (f.stage == 0) {
+            out += '(';
+            f.stage = 1;
+            st.push_back({(int64_t)Z[k * 4 + 1], h, 0});      // right child first
+        } else if (f.stage == 1) {
+            out += ',';
+            f.stage = 2;
+            st.push_back({(int64_t)Z[k * 4 + 0], h, 0});
+        } else {
+            if (f.node == root) out += ");";
+            else {
+                snprintf(buf, sizeof buf, "):%f", f.parent - h);
+                out += buf;
+            }
+            st.pop_back();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- entry points
+static int lk_method(const char* method) { return method && !strcmp(method, "average") ? 0 : -1; }
+
+size_t lk_smem_bytes(int64_t n) { return (size_t)n * sizeof(int); }
+
+// dev_D [nb][n][n] (stride d_stride elements) is clustered in place (destroyed); dev_chain [nb][n] ints;
+// dev_Zraw [nb][n-1][4] receives the merge-ordered rows.  Enqueued on the context's stream.
+int lk_launch(gv2_ctx* ctx, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, int* dev_chain, double* dev_Zraw) {
+    if (n <= 1 || nb <= 0) return GV2_OK;
+    const size_t smem = lk_smem_bytes(n);
+    if (smem > 200 * 1024) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage keeps the cluster sizes in shared memory: n = %lld > 51200", (long long)n);
+    static size_t attr = 0;
+    if (smem > attr) {
+        GV2_CUDA(ctx, cudaFuncSetAttribute(lk_nn_chain_average_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        attr = smem;
+    }
+    lk_nn_chain_average_kernel<<<(unsigned)nb, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_chain, dev_Zraw);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+void lk_finalize_host(const double* raw, int64_t n, double* Z) { lk_finalize(raw, n, Z); }
+
+extern "C" int gv2_newick_from_linkage(const double* Z, int64_t n, const char* const* leaf_names, char* out, size_t out_cap,
+                                       size_t* out_len) {
+    if (!Z && n > 1) return GV2_ERR_ARG;
+    if (!leaf_names || !out_len) return GV2_ERR_ARG;
+    std::string s;
+    lk_newick(Z, n, leaf_names, s);
+    *out_len = s.size();
+    if (out && out_cap > s.size()) memcpy(out, s.c_str(), s.size() + 1);
+    else if (out) return GV2_ERR_NOMEM;
+    return GV2_OK;
+}
+
+extern "C" int gv2_linkage_host(gv2_ctx* ctx, const double* dist, int64_t n, const char* method, double* Z) {
+    if (!ctx || !dist || !Z || n < 1) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_linkage_host: bad arguments");
+    if (lk_method(method) != 0) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "gv2_linkage_host: method '%s' (built: average)", method ? method : "");
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 1) return GV2_OK;
+    double *d_D = nullptr, *d_Z = nullptr;
+    int* d_chain = nullptr;
+    auto cleanup = [&]() { cudaFree(d_D); cudaFree(d_Z); cudaFree(d_chain); };
+    cudaError_t e = cudaMalloc((void**)&d_D, (size_t)n * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_Z, (size_t)(n - 1) * 4 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_chain, (size_t)n * sizeof(int));
+    if (e != cudaSuccess) { cleanup(); return gv2_fail(ctx, GV2_ERR_NOMEM, "gv2_linkage_host: %s", cudaGetErrorString(e)); }
+    e = cudaMemcpyAsync(d_D, dist, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    int rc = GV2_OK;
+    if (e == cudaSuccess) {
+        lk_mirror_upper_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n + 7) / 8)), dim3(32, 8), 0, ctx->stream>>>(d_D, n);
+        ctx->launches++;
+        rc = lk_launch(ctx, d_D, n * n, n, 1, d_chain, d_Z);
+    }
+    std::vector<double> raw((size_t)(n - 1) * 4);
+    if (e == cudaSuccess && rc == GV2_OK) e = cudaMemcpyAsync(raw.data(), d_Z, raw.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && rc == GV2_OK) e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (rc) return rc;
+    if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "gv2_linkage_host: %s", cudaGetErrorString(e));
+    lk_finalize(raw.data(), n, Z);
+    return GV2_OK;
+}

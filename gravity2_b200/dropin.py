@@ -183,6 +183,59 @@ def binary_jaccard(trait_table, engine: Optional[Engine] = None):
         return inter / union
 
 
+# ------------------------------------------------------------------------------ dendrograms
+def DistMat2Tree(DistMat, LeafList, Dendrogram_LinkageMethod, do_logscale=False, engine: Optional[Engine] = None):
+    """app/utils/dist_mat_to_tree.py:5-21: Newick string of the UPGMA dendrogram of a distance matrix.  The clustering
+    (scipy ``linkage`` of the upper triangle) runs on the device, to_tree + GetNewick natively on the host.  Like the
+    reference, negative entries of the caller's matrix are zeroed in place.  Built for method "average" (the default of
+    every shipped payload); other methods raise."""
+    if Dendrogram_LinkageMethod != "average":
+        raise NotImplementedError(f"device linkage is built for method 'average' (got {Dendrogram_LinkageMethod!r})")
+    eng = engine or default_engine()
+    DistMat[DistMat < 0] = 0
+    D = np.asarray(DistMat, dtype=np.float64)
+    if do_logscale:
+        D = 10 ** D
+    return eng.newick(eng.linkage(D, "average"), LeafList)
+
+
+def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, GOMIDList, payload, LeafList,
+                     N_Bootstrap: Optional[int] = None, pipeline: str = "pl1", indices=None, batch: int = 512,
+                     engine: Optional[Engine] = None) -> Iterator[str]:
+    """One Newick line per bootstrap replicate, in the reference's order: the loop bodies of
+    app/src/pl1_graphs.py:78-117 (resample, GOM rebuild, distance matrix, DistMat2Tree) with everything up to the
+    dendrogram on the device -- the 8 N^2 bytes of a replicate's distance matrix never cross PCIe.  Arguments as
+    ``bootstrap_distance_matrices``; ``LeafList`` are the tree labels (TaxoLabelList)."""
+    from .engine import Job
+    eng = engine or default_engine()
+    sig = np.ascontiguousarray(PPHMMSignatureTable, dtype=np.float64)
+    n, p = sig.shape
+    nb = int(payload["N_Bootstrap"] if N_Bootstrap is None else N_Bootstrap)
+    scheme = payload["SimilarityMeasurementScheme"]
+    method = payload.get("Dendrogram_LinkageMethod", "average")
+    if payload.get("PphmmNeighbourhoodWeight", 0) != 0 or payload.get("PphmmSigScoreThreshold", 0) != 0:
+        raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
+    if method != "average":
+        raise NotImplementedError(f"device linkage is built for method 'average' (got {method!r})")
+    loc = sig if pipeline == "pl1" else np.ascontiguousarray(PPHMMLocationTable, dtype=np.float64)
+    gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
+    job = Job(eng, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance=True)
+    try:
+        for b0 in range(0, nb, batch):
+            cb = min(batch, nb - b0)
+            if indices is None:
+                idx = [draw_resample_indices(p, sort=(pipeline == "pl2")) for _ in range(cb)]
+            else:
+                idx = indices[b0:b0 + cb]
+            w = np.stack([weights_from_indices(i, p) for i in idx])
+            out = []
+            job.for_each_tree(w, LeafList, lambda b, s: out.append(s), method)
+            for s in out:
+                yield s
+    finally:
+        job.close()
+
+
 # ------------------------------------------------------------------------------ bootstrap
 def draw_resample_indices(n_pphmms: int, sort: bool = False):
     """The reference's own draw from numpy's global legacy RNG (pl1_graphs.py:81-82; sorted in

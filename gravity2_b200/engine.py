@@ -186,6 +186,31 @@ class Engine:
         _lib.check(self.ctx, rc)
         return out
 
+    # ------------------------------------------------------------------ dendrograms
+    def linkage(self, dist, method: str = "average") -> np.ndarray:
+        """scipy.cluster.hierarchy.linkage(dist[np.triu_indices_from(dist, k=1)], method) on the device: float64 (n-1, 4)."""
+        d = _f64(dist, "distance matrix")
+        n = d.shape[0]
+        if d.shape != (n, n):
+            raise ValueError("distance matrix must be square")
+        Z = np.empty((max(n - 1, 0), 4), dtype=np.float64)
+        _lib.check(self.ctx, self.lib.gv2_linkage_host(self.ctx, _ptr(d), n, method.encode(), _ptr(Z)))
+        return Z
+
+    def newick(self, Z, leaf_names) -> str:
+        """GetNewick(to_tree(Z), "", root.dist, leaf_names), app/utils/get_newick.py:1-13 (host, native)."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        n = Z.shape[0] + 1
+        names = [str(x).encode() for x in leaf_names]
+        if len(names) < n:
+            raise IndexError("fewer leaf names than leaves")
+        arr = (C.c_char_p * len(names))(*names)
+        ln = C.c_size_t(0)
+        _lib.check(self.ctx, self.lib.gv2_newick_from_linkage(_ptr(Z), n, arr, None, 0, C.byref(ln)))
+        buf = C.create_string_buffer(ln.value + 1)
+        _lib.check(self.ctx, self.lib.gv2_newick_from_linkage(_ptr(Z), n, arr, buf, ln.value + 1, C.byref(ln)))
+        return buf.value.decode()
+
     def philox_indices(self, seed: int, n_boot: int, p: int) -> np.ndarray:
         out = np.empty((n_boot, p), dtype=np.int64)
         _lib.check(self.ctx, self.lib.gv2_philox_indices_host(self.ctx, C.c_uint64(seed), n_boot, p, _ptr(out)))
@@ -275,6 +300,56 @@ class Job:
             _lib.check(self.ctx, rc)
         finally:
             self.lib.gv2_dev_free(self.ctx, d_w)
+
+    def for_each_tree(self, weights, leaf_names, fn, method: str = "average", ring_bytes: Optional[int] = None) -> None:
+        """fn(b, newick) for every replicate in order: the replicate's distance matrix is clustered on the device
+        (UPGMA) and printed as DistMat2Tree prints it; the matrices never leave HBM.  ``ring_bytes`` of device memory
+        hold the matrices being clustered concurrently (one CTA each; default: up to 128 matrices or 55 % of the
+        free memory)."""
+        w = np.ascontiguousarray(weights, dtype=np.int32)
+        if w.ndim == 1:
+            w = w[None, :]
+        nb = w.shape[0]
+        if nb == 0:
+            return
+        if w.shape[1] != self.p:
+            raise ValueError("weights must be (B, P)")
+        n = self.n
+        names = [str(x).encode() for x in leaf_names]
+        if len(names) < n:
+            raise IndexError("fewer leaf names than genomes")
+        arr = (C.c_char_p * len(names))(*names)
+        mat = max(1, n * n * 8)
+        if ring_bytes is None:
+            import torch
+            free_b = torch.cuda.mem_get_info(self.eng.device)[0] if torch.cuda.is_available() else 16 << 30
+            ring_bytes = int(0.55 * free_b)
+        ring_len = max(1, min(nb, 128, int(ring_bytes // mat)))
+        dev_ring, d_w = C.c_void_p(), C.c_void_p()
+        _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, ring_len * mat, C.byref(dev_ring)))
+        err = []
+
+        def _cb(b, ptr, ln, _user):
+            try:
+                fn(int(b), C.string_at(ptr, ln).decode())
+                return 0
+            except BaseException as e:      # never let an exception cross the C frame
+                err.append(e)
+                return 1
+
+        cb = _lib.NEWICK_CB(_cb)
+        try:
+            _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, w.nbytes, C.byref(d_w)))
+            _lib.check(self.ctx, self.lib.gv2_memcpy_h2d(self.ctx, d_w, _ptr(w), w.nbytes))
+            rc = self.lib.gv2_job_replicates_newick(self.job, d_w, nb, dev_ring, ring_len, method.encode(), arr,
+                                                    C.cast(cb, C.c_void_p), None)
+            if err:
+                raise err[0]
+            _lib.check(self.ctx, rc)
+        finally:
+            if d_w:
+                self.lib.gv2_dev_free(self.ctx, d_w)
+            self.lib.gv2_dev_free(self.ctx, dev_ring)
 
     def replicates(self, weights) -> Iterator[np.ndarray]:
         """Generator form of for_each_replicate: the native call runs on a worker thread and hands each

@@ -127,6 +127,14 @@ int gv2_gom_table_host(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, in
 #define GV2_GOM_ALL_COLUMNS 1 /* flags: score over every column instead of the relevant set R
                                  (plain dcor(X, Y) of app/utils/dcor.py:34-62) */
 
+/* Replaces the clustering of DistMat2Tree (app/utils/dist_mat_to_tree.py:7-12): scipy.cluster.hierarchy.linkage of the
+ * upper triangle of `dist` [n][n] (host), method "average"; Z [n-1][4] float64 as scipy returns it (sorted, relabelled). */
+int gv2_linkage_host(gv2_ctx* ctx, const double* dist, int64_t n, const char* method, double* Z);
+/* to_tree + GetNewick (app/utils/get_newick.py:1-13) of a linkage matrix: host only, no context.  *out_len = length
+ * without the terminator; with out == NULL only the length is returned. */
+int gv2_newick_from_linkage(const double* Z, int64_t n, const char* const* leaf_names, char* out, size_t out_cap,
+                            size_t* out_len);
+
 /* Replaces shared_pphmm_ratio / the counts of shared_norm_pphmm_ratio
  * (app/utils/shared_pphmm_graphs.py:59-97) and the binary Jaccard of
  * RefVirusAnnotator.sort_pphmm (app/src/ref_virus_annotator.py:148-158): bit-packs
@@ -181,6 +189,15 @@ int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, dou
  * computes the next sub-chunk; the matrix is valid until the callback returns; non-zero return stops. */
 int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
                               int64_t ring_len, double* host_out, gv2_replicate_cb callback, void* user);
+/* Replicate dendrograms without shipping the matrices: each replicate's distance matrix is
+ * clustered on the device (UPGMA = scipy.cluster.hierarchy.linkage(..., "average"), nearest-neighbour chain with scipy's
+ * tie order) and printed as DistMat2Tree + GetNewick print it (app/utils/dist_mat_to_tree.py:5-21,
+ * app/utils/get_newick.py:1-13); callback(b, newick, length, user) runs on the calling thread in replicate order.
+ * The job must have been created with GV2_OUT_DISTANCE.  dev_ring [ring_len][n][n] is scratch. */
+typedef int (*gv2_newick_cb)(int64_t replicate, const char* newick, size_t length, void* user);
+int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
+                              int64_t ring_len, const char* method, const char* const* leaf_names,
+                              gv2_newick_cb callback, void* user);
 /* GOM signature table of the job's loc table under the given weights (NULL = base):
  * dev_out [nb][n][g]. */
 int gv2_job_gom_table(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out);

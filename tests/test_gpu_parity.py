@@ -482,6 +482,65 @@ def test_fused_tail_equals_separate_kernels(eng, scheme, pw, kind):
     lib.gv2_destroy(ctx)
 
 
+# ------------------------------------------------------------------------ dendrograms
+@pytest.mark.parametrize("n,kind", [(2, "random"), (3, "ties"), (17, "ties"), (130, "random"), (513, "ties"), (1500, "blocks")])
+def test_device_linkage_equals_scipy(eng, n, kind):
+    """UPGMA on the device == scipy.cluster.hierarchy.linkage(method="average") row for row, bit for bit: heights from the
+    same three rounded operations, ties resolved in scipy's nearest-neighbour-chain order."""
+    from scipy.cluster.hierarchy import linkage
+    rng = np.random.default_rng(n)
+    if kind == "random":
+        D = rng.random((n, n))
+    elif kind == "ties":
+        D = rng.integers(1, 6, (n, n)) / 5.0                       # five distinct distances: ties everywhere
+    else:                                                          # block structure like a taxon table: many exact 1.0
+        grp = rng.integers(0, 12, n)
+        D = np.where(grp[:, None] == grp[None, :], np.round(rng.random((n, n)) * 0.6, 3), 1.0)
+    D = np.triu(D, 1)
+    D = D + D.T
+    Z = eng.linkage(D)
+    ref = linkage(D[np.triu_indices_from(D, k=1)], method="average")
+    assert Z.shape == ref.shape and np.array_equal(Z, ref)
+    # an asymmetric matrix is clustered by its upper triangle, as the reference does
+    A = D + np.tril(rng.random((n, n)), -1)
+    assert np.array_equal(eng.linkage(A), ref)
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_dist_mat_to_tree_golden(golden, eng, tag):
+    """DistMat2Tree drop-in against the Newick string the unmodified reference printed for the same similarity matrix."""
+    import gravity2_b200 as G
+    S = golden[f"{tag}_S_PG_p1"]
+    D = 1 - S
+    D[D < 0] = 0
+    names = [f"v{i}" for i in range(len(S))]
+    assert G.DistMat2Tree(D.copy(), names, "average", False) == str(golden[f"{tag}_newick_avg"])
+    # negative entries of the caller's matrix are zeroed in place, as dist_mat_to_tree.py:7 does
+    Dn = D.copy()
+    Dn[D == 0] = -0.5
+    assert G.DistMat2Tree(Dn, names, "average", False) == str(golden[f"{tag}_newick_avg"]) and np.array_equal(Dn, D)
+    with pytest.raises(NotImplementedError):
+        G.DistMat2Tree(D, names, "single", False)
+
+
+def test_bootstrap_newick_equals_matrices_then_scipy(eng):
+    """The device tree path (matrices clustered in HBM, only Newick lines returned) against the matrix path of the same
+    engine followed by the reference's own DistMat2Tree (oracle: scipy linkage + GetNewick), replicate by replicate."""
+    import gravity2_b200 as G
+    t = synth.make_tables(180, 900, 6, 0.04, seed=31)
+    payload = {"N_Bootstrap": 5, "SimilarityMeasurementScheme": "PG", "p": 1.0, "Dendrogram_LinkageMethod": "average",
+               "PphmmNeighbourhoodWeight": 0.0, "PphmmSigScoreThreshold": 0}
+    names = [f"{x}_{i}" for i, x in enumerate(t.taxo)]
+    np.random.seed(77)
+    mats = [m.copy() for m in G.bootstrap_distance_matrices(t.sig, None, t.taxo, t.gom_ids, payload, pipeline="pl1")]
+    np.random.seed(77)
+    trees = list(G.bootstrap_newick(t.sig, None, t.taxo, t.gom_ids, payload, names, pipeline="pl1"))
+    assert len(trees) == 5
+    for D, tree in zip(mats, trees):
+        assert tree == O.dist_mat_to_tree(D, names, "average", False)
+        assert tree.count(",") == len(names) - 1 and tree.endswith(");")
+
+
 def test_error_paths(eng):
     import gravity2_b200 as G
     with pytest.raises(ValueError):

@@ -84,3 +84,42 @@ def test_philox_oracle_known_answers():
     from oracle.philox_oracle import philox4x32_10
     assert philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
     assert philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+
+
+def test_native_newick_matches_the_reference_printer(golden):
+    """gv2_newick_from_linkage (host only: no GPU needed) == to_tree + GetNewick (app/utils/get_newick.py:1-13) on scipy
+    linkage matrices, including the reference's own golden (test/utils/test_dist_mat_to_tree.py:17 uses method single;
+    the printer does not care) and the reference-produced Newick of the synthetic fixtures."""
+    import ctypes as C
+    from scipy.cluster.hierarchy import linkage
+    from gravity2_b200 import _lib
+    from oracle import gravity_oracle as O
+    lib = _lib.load()
+
+    def native(Z, names):
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        n = Z.shape[0] + 1
+        arr = (C.c_char_p * n)(*[s.encode() for s in names])
+        ln = C.c_size_t(0)
+        assert lib.gv2_newick_from_linkage(Z.ctypes.data_as(C.c_void_p), n, arr, None, 0, C.byref(ln)) == 0
+        buf = C.create_string_buffer(ln.value + 1)
+        assert lib.gv2_newick_from_linkage(Z.ctypes.data_as(C.c_void_p), n, arr, buf, ln.value + 1, C.byref(ln)) == 0
+        return buf.value.decode()
+
+    D3 = np.array([[0.0, 0.2, 0.4], [0.2, 0.0, 0.6], [0.4, 0.6, 0.0]])
+    Z = linkage(D3[np.triu_indices_from(D3, k=1)], method="single")
+    assert native(Z, ["A", "B", "C"]) == str(golden["newick_3x3_single"])
+    rng = np.random.default_rng(3)
+    for n in (2, 3, 7, 40, 300):
+        X = rng.random((n, 4))
+        D = np.round(np.sqrt(((X[:, None] - X[None]) ** 2).sum(-1)), 2)      # rounded: plenty of exact ties
+        names = [f"v{i}|x" for i in range(n)]
+        Z = linkage(D[np.triu_indices_from(D, k=1)], method="average")
+        assert native(Z, names) == O.dist_mat_to_tree(D.copy(), names, "average", False)
+    for tag in ("A", "B"):
+        S = golden[f"{tag}_S_PG_p1"]
+        D0 = 1 - S
+        D0[D0 < 0] = 0
+        names = [f"v{i}" for i in range(len(S))]
+        Z = linkage(D0[np.triu_indices_from(D0, k=1)], method="average")
+        assert native(Z, names) == str(golden[f"{tag}_newick_avg"])
