@@ -10,9 +10,10 @@ rebuilt per replicate, as app/src/pl1_graphs.py:78-107 does).  pairs/s = N(N+1)/
 
   value : inputs resident in HBM, outputs written to HBM (device-timed, CUDA events on the
           stream the kernels run on, max over ranks)
-  e2e   : the same job through the host-pointer C ABI (gv2_similarity_host / gv2_gom_table_host /
-          gv2_bootstrap_host) with numpy tables in host memory: H2D of the tables and D2H of every
-          replicate matrix inside the timed region
+  e2e   : the same job through the public host API (gravity2_b200.engine.Job) with numpy tables in host
+          memory: H2D of the tables and D2H of every replicate matrix inside the timed region
+  e2e_trees : the same job with the bootstrap loops' real product as the result: one Newick string per
+          replicate, the distance matrices clustered on the device (UPGMA) and never shipped
   --impl reference : the reference's numpy pair expressions and dcor-based GOM scoring (CPU oracle
           port of app/utils/similarity_matrix_constructor.py:167-177 and
           parallel_gom_sig_generator.py:30-37) on all host cores, on a bounded row sample.
@@ -334,6 +335,9 @@ def main():
     if not args.no_e2e:
         e2e = measure_e2e(lib, ctx, ck, t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist if world > 1 else None, torch,
                           steps=max(1, min(steps, 2)))
+    e2e_trees = None
+    if not args.no_e2e and B > 0:
+        e2e_trees = measure_e2e_trees(t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist if world > 1 else None, torch)
     lib.gv2_job_destroy(job)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -344,7 +348,7 @@ def main():
                          "; GOM Jaccard f32 min / f32 64-column slabs -> f64; GOM dCor f64; epilogue f64",
                 "data": "synthetic",
                 "config": workload_config(args, cfg, world), "clocks": clocks, "gpu_launches": launches,
-                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "e2e": e2e, "e2e_trees": e2e_trees, "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -462,6 +466,53 @@ def measure_e2e(lib, ctx, ck, t, gor, weights, my_reps, n, p, g, B, pairs, world
             "ms_per_step": dt * 1e3,
             "api": "gravity2_b200.engine.Job(sig, loc, ...).base() + .for_each_replicate(weights, consumer): numpy in, "
                    "numpy views of a pinned host ring out (per-rank bytes)"}
+
+
+def measure_e2e_trees(t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist, torch):
+    """The same job with the bootstrap loops' real product as the result (app/src/pl1_graphs.py:108-117 keeps only the
+    dendrogram of a replicate): numpy tables in -> Job.for_each_tree -> one Newick string per replicate out, the distance
+    matrices clustered in HBM (device UPGMA, scipy's nn_chain average linkage bit for bit) and never shipped.  H2D of the
+    tables and D2H of the linkage rows inside the timed region.  One step (the job takes seconds)."""
+    import gravity2_b200
+    from gravity2_b200.engine import Job
+    eng = gravity2_b200.Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    names = [f"{x}_{i}" for i, x in enumerate(t.taxo)]
+    w_mine = np.ascontiguousarray(weights[my_reps]) if my_reps else np.zeros((0, p), np.int32)
+    acc = [0, 0]
+
+    def consume(b, s):
+        acc[0] += len(s)
+        acc[1] += 1
+
+    def job_once():
+        job = Job(eng, t.sig, t.sig, gor, g, "PG", 1.0, distance=True)
+        try:
+            if rank == 0:
+                consume(-1, gravity2_b200.DistMat2Tree(job.base(), names, "average", False, engine=eng))
+            job.for_each_tree(w_mine, names, consume)
+        finally:
+            job.close()
+
+    job_once()          # warm-up
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    acc[1] = 0
+    t0 = time.perf_counter()
+    job_once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert acc[1] == len(my_reps) + (1 if rank == 0 else 0), "consumer did not see every tree"
+    if dist is not None:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    eng.close()
+    return {"value": pairs * (1 + B) / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(n * p * 8 + w_mine.nbytes + gor.nbytes + (n * n * 8 if rank == 0 else 0)),
+            "d2h_bytes_per_step": int(len(my_reps) * (n - 1) * 32 + (n * n * 8 + (n - 1) * 32 if rank == 0 else 0)),
+            "api": "gravity2_b200.engine.Job(sig, loc, ...).for_each_tree(weights, leaf_names, consumer) + DistMat2Tree(base): numpy in, "
+                   "one Newick string per replicate out (UPGMA on the device; per-rank bytes)"}
 
 
 def measure_cpu_baseline(args, cfg):

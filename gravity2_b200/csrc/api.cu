@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "gom.h"
@@ -39,10 +40,9 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
                        int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* wT_scratch, int* overflow_flag,
                        double* ws);
 
-int lk_launch(gv2_ctx* ctx, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, int* dev_chain, double* dev_Zraw);
+int lk_launch(gv2_ctx* ctx, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw);
 void lk_finalize_host(const double* raw, int64_t n, double* Z);
-extern "C" int gv2_newick_from_linkage(const double* Z, int64_t n, const char* const* leaf_names, char* out, size_t out_cap,
-                                       size_t* out_len);
+void lk_newick_host(const double* Z, int64_t n, const char* const* names, std::string& out);
 
 static thread_local std::string g_create_error;
 
@@ -284,6 +284,13 @@ extern "C" void gv2_job_destroy(gv2_job* job) {
 
 extern "C" size_t gv2_job_device_bytes(const gv2_job* job) { return job ? job->device_bytes() : 0; }
 
+extern "C" int gv2_mem_info(gv2_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
+    if (!ctx || !free_bytes || !total_bytes) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_mem_info: bad arguments");
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    GV2_CUDA(ctx, cudaMemGetInfo(free_bytes, total_bytes));
+    return GV2_OK;
+}
+
 // Which replicate pair-sum path the job's cost model chose (GV2_PATH_*), and the number of co-present
 // (genome pair incl. diagonal, PPHMM column) cells of its signature table (0 when no CSR was built).
 extern "C" int gv2_job_replicate_path(const gv2_job* job) {
@@ -453,33 +460,28 @@ struct TreeSink {
     const char* const* names = nullptr;
     gv2_newick_cb cb = nullptr;
     void* user = nullptr;
-    int* chain = nullptr;
     double* zdev[2] = {nullptr, nullptr};
     double* zhost[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     int64_t pend_b0[2] = {0, 0}, pend_cnt[2] = {0, 0};
     int cur = 0;
-    std::vector<double> Z;
-    std::string text;
+    std::vector<std::string> texts;
     ~TreeSink() {
-        cudaFree(chain);
         for (int h = 0; h < 2; ++h) { cudaFree(zdev[h]); cudaFreeHost(zhost[h]); if (ev[h]) cudaEventDestroy(ev[h]); }
     }
     int init(gv2_ctx* c, int64_t n_, int64_t cap_) {
         ctx = c; n = n_; cap = cap_;
         const size_t zb = (size_t)cap * std::max<int64_t>(1, n - 1) * 4 * sizeof(double);
-        GV2_CUDA(ctx, cudaMalloc((void**)&chain, (size_t)cap * std::max<int64_t>(1, n) * sizeof(int)));
         for (int h = 0; h < 2; ++h) {
             GV2_CUDA(ctx, cudaMalloc((void**)&zdev[h], zb));
             GV2_CUDA(ctx, cudaMallocHost((void**)&zhost[h], zb));
             GV2_CUDA(ctx, cudaEventCreateWithFlags(&ev[h], cudaEventDisableTiming));
         }
-        Z.resize((size_t)std::max<int64_t>(1, n - 1) * 4);
         return GV2_OK;
     }
     // matrices of replicates [b0, b0 + cnt) are in dev[0 .. cnt) (stride n*n): cluster them, fetch the rows
     int enqueue(double* dev, int64_t b0, int64_t cnt) {
-        int rc = lk_launch(ctx, dev, n * n, n, cnt, chain, zdev[cur]);
+        int rc = lk_launch(ctx, dev, n * n, n, cnt, zdev[cur]);
         if (rc) return rc;
         if (n > 1)
             GV2_CUDA(ctx, cudaMemcpyAsync(zhost[cur], zdev[cur], (size_t)cnt * (n - 1) * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -492,16 +494,26 @@ struct TreeSink {
         if (pend_cnt[h] == 0) return GV2_OK;
         cudaError_t e = cudaEventSynchronize(ev[h]);
         if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "linkage rows: %s", cudaGetErrorString(e));
-        for (int64_t k = 0; k < pend_cnt[h]; ++k) {
-            if (n > 1) lk_finalize_host(zhost[h] + (size_t)k * (n - 1) * 4, n, Z.data());
-            size_t len = 0;
-            gv2_newick_from_linkage(Z.data(), n, names, nullptr, 0, &len);
-            text.resize(len + 1);
-            gv2_newick_from_linkage(Z.data(), n, names, &text[0], len + 1, &len);
-            if (cb(pend_b0[h] + k, text.c_str(), len, user) != 0)
-                return gv2_fail(ctx, GV2_ERR_ARG, "tree callback asked to stop at replicate %lld", (long long)(pend_b0[h] + k));
-        }
+        // sort + relabel + print the sub-chunk's trees on a few host threads (~5 ms of work per 10 000-leaf tree), then
+        // hand them over in replicate order on the calling thread
+        const int64_t cnt = pend_cnt[h];
+        texts.resize((size_t)cnt);
+        const int nthreads = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(cnt, 8), (int64_t)std::thread::hardware_concurrency()));
+        auto work = [&](int t) {
+            std::vector<double> Zl((size_t)std::max<int64_t>(1, n - 1) * 4);
+            for (int64_t k = t; k < cnt; k += nthreads) {
+                if (n > 1) lk_finalize_host(zhost[h] + (size_t)k * (n - 1) * 4, n, Zl.data());
+                lk_newick_host(Zl.data(), n, names, texts[(size_t)k]);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
         pend_cnt[h] = 0;
+        for (int64_t k = 0; k < cnt; ++k)
+            if (cb(pend_b0[h] + k, texts[(size_t)k].c_str(), texts[(size_t)k].size(), user) != 0)
+                return gv2_fail(ctx, GV2_ERR_ARG, "tree callback asked to stop at replicate %lld", (long long)(pend_b0[h] + k));
         return GV2_OK;
     }
 };

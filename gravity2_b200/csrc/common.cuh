@@ -23,10 +23,7 @@ struct gv2_ctx {
     std::vector<Timed> timed;
 };
 
-// kernel groups of the event timing (include/gravity2_b200.h: GV2_TIME_*)
-#define GV2_TIME_PAIRSUMS 0   // replicate pair-sum kernel (CSR walk / tensor-core contraction)
-#define GV2_TIME_TAIL 1       // fused GOM Jaccard + epilogue
-#define GV2_TIME_GOM 2        // GOM dCor scoring kernels of one replicate chunk
+// kernel groups of the event timing: GV2_TIME_* in include/gravity2_b200.h
 
 // RAII-free helper: t.begin() before the launches, t.end() after; no-ops unless timing is enabled
 struct Gv2Timer {

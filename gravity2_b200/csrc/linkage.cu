@@ -43,17 +43,16 @@ __device__ __forceinline__ LkBest lk_min(LkBest a, LkBest b) {
     return a;
 }
 
-// grid = matrices, block = LK_THREADS; dynamic shared memory: n ints (cluster sizes)
-// D: [nb][n][n] float64, destroyed; chain: [nb][n] int scratch; Zraw: [nb][n-1][4] float64 in merge order
+// grid = matrices, block = LK_THREADS; dynamic shared memory: 2 n ints (cluster sizes, the chain)
+// D: [nb][n][n] float64, destroyed; Zraw: [nb][n-1][4] float64 in merge order
 __global__ void __launch_bounds__(LK_THREADS, 1)
-lk_nn_chain_average_kernel(double* __restrict__ Dall, long long d_stride, int n, int* __restrict__ chain_all,
-                           double* __restrict__ Zall) {
+lk_nn_chain_average_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
     extern __shared__ int lk_size[];
     __shared__ LkBest s_warp[LK_THREADS / 32];
     __shared__ int s_x, s_y, s_len, s_merge, s_first;
-    __shared__ double s_min;
+    __shared__ double s_min, s_dp;
     double* D = Dall + (size_t)blockIdx.x * d_stride;
-    int* chain = chain_all + (size_t)blockIdx.x * n;
+    int* chain = lk_size + n;
     double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n; i += LK_THREADS) lk_size[i] = 1;
@@ -78,6 +77,7 @@ lk_nn_chain_average_kernel(double* __restrict__ Dall, long long d_stride, int n,
             for (int i = tid; i < n; i += LK_THREADS) {
                 if (lk_size[i] == 0 || i == x) continue;
                 const double d = row[i];
+                if (i == prev) s_dp = d;                         // the incumbent's distance, for the final comparison
                 if (d < best.d) { best.d = d; best.i = i; }      // ascending i per thread: first minimum kept
             }
 #pragma unroll
@@ -103,7 +103,7 @@ lk_nn_chain_average_kernel(double* __restrict__ Dall, long long d_stride, int n,
                     int y = best.i;
                     double cur = best.d;
                     if (prev >= 0) {
-                        const double dp = row[prev];
+                        const double dp = s_dp;
                         if (!(best.d < dp)) { y = prev; cur = dp; }
                     } else if (best.i == 0x7fffffff) {
                         y = 0;                        // every distance NaN: scipy keeps its stale y; unreachable for cleaned matrices
@@ -238,25 +238,29 @@ static void lk_newick(const double* Z, int64_t n, const char* const* names, std:
 // ---------------------------------------------------------------------------------- entry points
 static int lk_method(const char* method) { return method && !strcmp(method, "average") ? 0 : -1; }
 
-size_t lk_smem_bytes(int64_t n) { return (size_t)n * sizeof(int); }
+size_t lk_smem_bytes(int64_t n) { return (size_t)n * 2 * sizeof(int); }
 
-// dev_D [nb][n][n] (stride d_stride elements) is clustered in place (destroyed); dev_chain [nb][n] ints;
-// dev_Zraw [nb][n-1][4] receives the merge-ordered rows.  Enqueued on the context's stream.
-int lk_launch(gv2_ctx* ctx, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, int* dev_chain, double* dev_Zraw) {
+// dev_D [nb][n][n] (stride d_stride elements) is clustered in place (destroyed); dev_Zraw [nb][n-1][4] receives the
+// merge-ordered rows.  Enqueued on the context's stream.
+int lk_launch(gv2_ctx* ctx, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw) {
     if (n <= 1 || nb <= 0) return GV2_OK;
     const size_t smem = lk_smem_bytes(n);
-    if (smem > 200 * 1024) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage keeps the cluster sizes in shared memory: n = %lld > 51200", (long long)n);
+    if (smem > 200 * 1024) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage keeps the cluster sizes and the chain in shared memory: n = %lld > 25600", (long long)n);
     static size_t attr = 0;
     if (smem > attr) {
         GV2_CUDA(ctx, cudaFuncSetAttribute(lk_nn_chain_average_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         attr = smem;
     }
-    lk_nn_chain_average_kernel<<<(unsigned)nb, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_chain, dev_Zraw);
+    Gv2Timer timer(ctx, GV2_TIME_LINKAGE);
+    timer.begin();
+    lk_nn_chain_average_kernel<<<(unsigned)nb, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
     GV2_LAUNCH_CHECK(ctx);
+    timer.end();
     return GV2_OK;
 }
 
 void lk_finalize_host(const double* raw, int64_t n, double* Z) { lk_finalize(raw, n, Z); }
+void lk_newick_host(const double* Z, int64_t n, const char* const* names, std::string& out) { lk_newick(Z, n, names, out); }
 
 extern "C" int gv2_newick_from_linkage(const double* Z, int64_t n, const char* const* leaf_names, char* out, size_t out_cap,
                                        size_t* out_len) {
@@ -276,18 +280,16 @@ extern "C" int gv2_linkage_host(gv2_ctx* ctx, const double* dist, int64_t n, con
     GV2_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n == 1) return GV2_OK;
     double *d_D = nullptr, *d_Z = nullptr;
-    int* d_chain = nullptr;
-    auto cleanup = [&]() { cudaFree(d_D); cudaFree(d_Z); cudaFree(d_chain); };
+    auto cleanup = [&]() { cudaFree(d_D); cudaFree(d_Z); };
     cudaError_t e = cudaMalloc((void**)&d_D, (size_t)n * n * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_Z, (size_t)(n - 1) * 4 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&d_chain, (size_t)n * sizeof(int));
     if (e != cudaSuccess) { cleanup(); return gv2_fail(ctx, GV2_ERR_NOMEM, "gv2_linkage_host: %s", cudaGetErrorString(e)); }
     e = cudaMemcpyAsync(d_D, dist, (size_t)n * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     int rc = GV2_OK;
     if (e == cudaSuccess) {
         lk_mirror_upper_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n + 7) / 8)), dim3(32, 8), 0, ctx->stream>>>(d_D, n);
         ctx->launches++;
-        rc = lk_launch(ctx, d_D, n * n, n, 1, d_chain, d_Z);
+        rc = lk_launch(ctx, d_D, n * n, n, 1, d_Z);
     }
     std::vector<double> raw((size_t)(n - 1) * 4);
     if (e == cudaSuccess && rc == GV2_OK) e = cudaMemcpyAsync(raw.data(), d_Z, raw.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);

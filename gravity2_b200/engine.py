@@ -304,7 +304,7 @@ class Job:
     def for_each_tree(self, weights, leaf_names, fn, method: str = "average", ring_bytes: Optional[int] = None) -> None:
         """fn(b, newick) for every replicate in order: the replicate's distance matrix is clustered on the device
         (UPGMA) and printed as DistMat2Tree prints it; the matrices never leave HBM.  ``ring_bytes`` of device memory
-        hold the matrices being clustered concurrently (one CTA each; default: up to 128 matrices or 55 % of the
+        hold the matrices being clustered concurrently (one CTA each; default: up to 128 matrices or 62 % of the
         free memory)."""
         w = np.ascontiguousarray(weights, dtype=np.int32)
         if w.ndim == 1:
@@ -321,9 +321,9 @@ class Job:
         arr = (C.c_char_p * len(names))(*names)
         mat = max(1, n * n * 8)
         if ring_bytes is None:
-            import torch
-            free_b = torch.cuda.mem_get_info(self.eng.device)[0] if torch.cuda.is_available() else 16 << 30
-            ring_bytes = int(0.55 * free_b)
+            free_b, total_b = C.c_size_t(0), C.c_size_t(0)
+            _lib.check(self.ctx, self.lib.gv2_mem_info(self.ctx, C.byref(free_b), C.byref(total_b)))
+            ring_bytes = int(0.62 * free_b.value)
         ring_len = max(1, min(nb, 128, int(ring_bytes // mat)))
         dev_ring, d_w = C.c_void_p(), C.c_void_p()
         _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, ring_len * mat, C.byref(dev_ring)))

@@ -69,6 +69,7 @@ uint64_t gv2_launch_count(const gv2_ctx* ctx); /* kernels launched so far throug
 #define GV2_TIME_PAIRSUMS 0 /* replicate pair sums: CSR walk (sparse tables) or tensor-core contraction */
 #define GV2_TIME_TAIL 1     /* fused GOM Jaccard + epilogue kernel */
 #define GV2_TIME_GOM 2      /* GOM dCor scoring kernels of one 32-replicate chunk */
+#define GV2_TIME_LINKAGE 3  /* device UPGMA of one sub-chunk of replicate matrices */
 int gv2_timing_enable(gv2_ctx* ctx, int on);
 int gv2_timing_read_kind(gv2_ctx* ctx, int kind, double* total_ms, int64_t* launches);
 int gv2_timing_read(gv2_ctx* ctx, double* total_ms, int64_t* launches); /* = kind GV2_TIME_PAIRSUMS */
@@ -80,6 +81,7 @@ int gv2_host_alloc(gv2_ctx* ctx, size_t bytes, void** out); /* page-locked */
 int gv2_host_free(gv2_ctx* ctx, void* ptr);
 int gv2_memcpy_h2d(gv2_ctx* ctx, void* dst, const void* src, size_t bytes); /* synchronous */
 int gv2_memcpy_d2h(gv2_ctx* ctx, void* dst, const void* src, size_t bytes);
+int gv2_mem_info(gv2_ctx* ctx, size_t* free_bytes, size_t* total_bytes); /* cudaMemGetInfo of the context's device */
 
 /* ---- host-pointer entry points (what the reference-side binding calls) ----------------- */
 
