@@ -40,7 +40,8 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
                        int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* wT_scratch, int* overflow_flag,
                        double* ws);
 
-int lk_launch(gv2_ctx* ctx, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw);
+int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw);
+int lk_method(const char* method);
 void lk_finalize_host(const double* raw, int64_t n, double* Z);
 void lk_newick_host(const double* Z, int64_t n, const char* const* names, std::string& out);
 
@@ -457,6 +458,7 @@ extern "C" int gv2_job_base(gv2_job* job, int64_t tile_begin, int64_t tile_end, 
 struct TreeSink {
     gv2_ctx* ctx = nullptr;
     int64_t n = 0, cap = 0;
+    int method = 0;
     const char* const* names = nullptr;
     gv2_newick_cb cb = nullptr;
     void* user = nullptr;
@@ -481,7 +483,7 @@ struct TreeSink {
     }
     // matrices of replicates [b0, b0 + cnt) are in dev[0 .. cnt) (stride n*n): cluster them, fetch the rows
     int enqueue(double* dev, int64_t b0, int64_t cnt) {
-        int rc = lk_launch(ctx, dev, n * n, n, cnt, zdev[cur]);
+        int rc = lk_launch(ctx, method, dev, n * n, n, cnt, zdev[cur]);
         if (rc) return rc;
         if (n > 1)
             GV2_CUDA(ctx, cudaMemcpyAsync(zhost[cur], zdev[cur], (size_t)cnt * (n - 1) * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -686,15 +688,16 @@ extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weight
 extern "C" int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring, int64_t ring_len,
                                          const char* method, const char* const* leaf_names, gv2_newick_cb cb, void* user) {
     if (!job || !leaf_names || !cb) return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_newick: bad arguments");
-    if (!method || strcmp(method, "average"))
-        return gv2_fail(job->ctx, GV2_ERR_UNSUPPORTED, "gv2_job_replicates_newick: linkage method '%s' (built: average)", method ? method : "");
+    const int mth = lk_method(method);
+    if (mth < 0)
+        return gv2_fail(job->ctx, GV2_ERR_UNSUPPORTED, "gv2_job_replicates_newick: linkage method '%s' (built: average, complete, weighted, ward, single)", method ? method : "");
     if (job->out_kind != GV2_OUT_DISTANCE) return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_replicates_newick: the job must produce distances");
     if (nb <= 0 || job->n == 0) return GV2_OK;
     GV2_CUDA(job->ctx, cudaSetDevice(job->ctx->device));
     TreeSink sink;
     int rc = sink.init(job->ctx, job->n, std::min<int64_t>(ring_len, nb));
     if (rc) return rc;
-    sink.names = leaf_names; sink.cb = cb; sink.user = user;
+    sink.names = leaf_names; sink.cb = cb; sink.user = user; sink.method = mth;
     return replicates_impl(job, dev_weights, nb, dev_ring, ring_len, nullptr, nullptr, nullptr, &sink);
 }
 

@@ -3,7 +3,9 @@
 // Reference: DistMat2Tree, app/utils/dist_mat_to_tree.py:5-21 -- the distance matrix is zero-clamped, its upper
 // triangle is handed to scipy.cluster.hierarchy.linkage(method) (scipy is a third-party dependency of the
 // reference, pinned scipy==1.14.0 in requirements.txt:4; its published algorithm for method "average" is the
-// nearest-neighbour chain of scipy/cluster/_hierarchy.pyx `nn_chain`, restated here), to_tree() turns the linkage
+// nearest-neighbour chain of scipy/cluster/_hierarchy.pyx `nn_chain` -- also behind complete, weighted and ward -- and
+// for "single" `mst_single_linkage`, restated here (the test suite holds the same loops in Python, pinned bit for
+// bit to the installed scipy), to_tree() turns the linkage
 // matrix into nodes and GetNewick (app/utils/get_newick.py:1-13) prints them.  The bootstrap loops
 // (app/src/pl1_graphs.py:108-117, app/src/virus_classification.py:316-330) do this once per replicate and keep
 // only the Newick line, so with the clustering on the device a replicate's 0.8 GB distance matrix never has to
@@ -45,8 +47,30 @@ __device__ __forceinline__ LkBest lk_min(LkBest a, LkBest b) {
 
 // grid = matrices, block = LK_THREADS; dynamic shared memory: 2 n ints (cluster sizes, the chain)
 // D: [nb][n][n] float64, destroyed; Zraw: [nb][n-1][4] float64 in merge order
+// linkage_methods[...] of scipy/cluster/_hierarchy_distance_update.pxi; every operation rounded on its own (the host
+// builds of scipy do not contract to FMA), so the heights are bit-identical
+#define LK_AVERAGE 0
+#define LK_COMPLETE 1
+#define LK_WEIGHTED 2
+#define LK_WARD 3
+#define LK_SINGLE 4
+template <int METHOD>
+__device__ __forceinline__ double lk_new_dist(double d_xi, double d_yi, double d_xy, int nx, int ny, int ni) {
+    if (METHOD == LK_AVERAGE)
+        return __ddiv_rn(__dadd_rn(__dmul_rn((double)nx, d_xi), __dmul_rn((double)ny, d_yi)), (double)(nx + ny));
+    if (METHOD == LK_COMPLETE) return d_xi > d_yi ? d_xi : d_yi;
+    if (METHOD == LK_WEIGHTED) return __dmul_rn(0.5, __dadd_rn(d_xi, d_yi));
+    // ward: t = 1 / (nx + ny + ni); sqrt((ni + nx) t d_xi^2 + (ni + ny) t d_yi^2 - ni t d_xy^2), products left to right
+    const double t = __ddiv_rn(1.0, (double)(nx + ny + ni));
+    const double a = __dmul_rn(__dmul_rn(__dmul_rn((double)(ni + nx), t), d_xi), d_xi);
+    const double b = __dmul_rn(__dmul_rn(__dmul_rn((double)(ni + ny), t), d_yi), d_yi);
+    const double c = __dmul_rn(__dmul_rn(__dmul_rn((double)ni, t), d_xy), d_xy);
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), -c));
+}
+
+template <int METHOD>
 __global__ void __launch_bounds__(LK_THREADS, 1)
-lk_nn_chain_average_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
+lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
     extern __shared__ int lk_size[];
     __shared__ LkBest s_warp[LK_THREADS / 32];
     __shared__ int s_x, s_y, s_len, s_merge, s_first;
@@ -139,15 +163,74 @@ lk_nn_chain_average_kernel(double* __restrict__ Dall, long long d_stride, int n,
         __syncthreads();
         const double* rx = D + (size_t)x * n;
         double* ry = D + (size_t)y * n;
-        const double fx = (double)nx, fy = (double)ny, fs = (double)(nx + ny);
         for (int i = tid; i < n; i += LK_THREADS) {
-            if (lk_size[i] == 0 || i == y) continue;
-            // (size_x * d_xi + size_y * d_yi) / (size_x + size_y): three roundings, no FMA contraction
-            const double v = __ddiv_rn(__dadd_rn(__dmul_rn(fx, rx[i]), __dmul_rn(fy, ry[i])), fs);
+            const int ni = lk_size[i];
+            if (ni == 0 || i == y) continue;
+            const double v = lk_new_dist<METHOD>(rx[i], ry[i], dmin, nx, ny, ni);
             ry[i] = v;
             D[(size_t)i * n + y] = v;
         }
         __syncthreads();
+    }
+}
+
+// Method "single": mst_single_linkage of scipy/cluster/_hierarchy.pyx -- Prim's minimum spanning tree from node 0; per
+// step the row of the newest tree node lowers the running distances of the others, the closest (lowest index on
+// ties: upward scan, strict `<`) joins.  Dynamic shared memory: n ints (merged flags) + n doubles (running distances).
+__global__ void __launch_bounds__(LK_THREADS, 1)
+lk_mst_single_kernel(const double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
+    extern __shared__ int lk_size[];
+    __shared__ LkBest s_warp[LK_THREADS / 32];
+    __shared__ LkBest s_best;
+    int* merged = lk_size;
+    double* dmin = reinterpret_cast<double*>(lk_size + ((n + 1) & ~1));
+    const double* D = Dall + (size_t)blockIdx.x * d_stride;
+    double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += LK_THREADS) { merged[i] = 0; dmin[i] = INFINITY; }
+    __syncthreads();
+    int x = 0;
+    for (int k = 0; k < n - 1; ++k) {
+        if (tid == 0) merged[x] = 1;
+        __syncthreads();
+        const double* row = D + (size_t)x * n;
+        LkBest best{INFINITY, 0x7fffffff};
+        for (int i = tid; i < n; i += LK_THREADS) {
+            if (merged[i]) continue;
+            const double d = row[i];
+            double m = dmin[i];
+            if (m > d) { m = d; dmin[i] = d; }
+            if (m < best.d) { best.d = m; best.i = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            LkBest other;
+            other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+            other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+            best = lk_min(best, other);
+        }
+        if (lane == 0) s_warp[warp] = best;
+        __syncthreads();
+        if (warp == 0) {
+            best = s_warp[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                LkBest other;
+                other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+                other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+                best = lk_min(best, other);
+            }
+            if (lane == 0) {
+                if (best.i == 0x7fffffff) best.i = 0;     // all NaN / infinite: scipy keeps its stale y; unreachable for cleaned matrices
+                s_best = best;
+                Z[(size_t)k * 4 + 0] = (double)x;
+                Z[(size_t)k * 4 + 1] = (double)best.i;
+                Z[(size_t)k * 4 + 2] = best.d;
+                Z[(size_t)k * 4 + 3] = 0.0;               // sizes come from the relabelling pass
+            }
+        }
+        __syncthreads();
+        x = s_best.i;
     }
 }
 
@@ -236,24 +319,52 @@ static void lk_newick(const double* Z, int64_t n, const char* const* names, std:
 }
 
 // ---------------------------------------------------------------------------------- entry points
-static int lk_method(const char* method) { return method && !strcmp(method, "average") ? 0 : -1; }
+int lk_method(const char* method) {
+    if (!method) return -1;
+    if (!strcmp(method, "average")) return LK_AVERAGE;
+    if (!strcmp(method, "complete")) return LK_COMPLETE;
+    if (!strcmp(method, "weighted")) return LK_WEIGHTED;
+    if (!strcmp(method, "ward")) return LK_WARD;
+    if (!strcmp(method, "single")) return LK_SINGLE;
+    return -1;      // centroid / median (scipy's fast_linkage) are not built
+}
 
-size_t lk_smem_bytes(int64_t n) { return (size_t)n * 2 * sizeof(int); }
+size_t lk_smem_bytes(int64_t n, int method) {
+    return method == LK_SINGLE ? (size_t)((n + 1) & ~1) * sizeof(int) + (size_t)n * sizeof(double) : (size_t)n * 2 * sizeof(int);
+}
 
 // dev_D [nb][n][n] (stride d_stride elements) is clustered in place (destroyed); dev_Zraw [nb][n-1][4] receives the
 // merge-ordered rows.  Enqueued on the context's stream.
-int lk_launch(gv2_ctx* ctx, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw) {
+int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw) {
     if (n <= 1 || nb <= 0) return GV2_OK;
-    const size_t smem = lk_smem_bytes(n);
-    if (smem > 200 * 1024) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage keeps the cluster sizes and the chain in shared memory: n = %lld > 25600", (long long)n);
-    static size_t attr = 0;
-    if (smem > attr) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(lk_nn_chain_average_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-        attr = smem;
+    if (method < 0 || method > LK_SINGLE) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage: methods average, complete, weighted, ward, single");
+    const size_t smem = lk_smem_bytes(n, method);
+    if (smem > 200 * 1024)
+        return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage keeps its per-cluster state in shared memory: n = %lld needs %zu bytes", (long long)n, smem);
+    static size_t attr[LK_SINGLE + 1] = {0, 0, 0, 0, 0};
+    if (smem > attr[method]) {
+        const int sz = (int)std::max<size_t>(smem, 1024);
+        cudaError_t e = cudaSuccess;
+        switch (method) {
+            case LK_AVERAGE: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_AVERAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
+            case LK_COMPLETE: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_COMPLETE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
+            case LK_WEIGHTED: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
+            case LK_WARD: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
+            default: e = cudaFuncSetAttribute(lk_mst_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
+        }
+        GV2_CUDA(ctx, e);
+        attr[method] = smem;
     }
     Gv2Timer timer(ctx, GV2_TIME_LINKAGE);
     timer.begin();
-    lk_nn_chain_average_kernel<<<(unsigned)nb, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+    const unsigned g = (unsigned)nb;
+    switch (method) {
+        case LK_AVERAGE: lk_nn_chain_kernel<LK_AVERAGE><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+        case LK_COMPLETE: lk_nn_chain_kernel<LK_COMPLETE><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+        case LK_WEIGHTED: lk_nn_chain_kernel<LK_WEIGHTED><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+        case LK_WARD: lk_nn_chain_kernel<LK_WARD><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+        default: lk_mst_single_kernel<<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+    }
     GV2_LAUNCH_CHECK(ctx);
     timer.end();
     return GV2_OK;
@@ -276,7 +387,8 @@ extern "C" int gv2_newick_from_linkage(const double* Z, int64_t n, const char* c
 
 extern "C" int gv2_linkage_host(gv2_ctx* ctx, const double* dist, int64_t n, const char* method, double* Z) {
     if (!ctx || !dist || !Z || n < 1) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_linkage_host: bad arguments");
-    if (lk_method(method) != 0) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "gv2_linkage_host: method '%s' (built: average)", method ? method : "");
+    const int mth = lk_method(method);
+    if (mth < 0) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "gv2_linkage_host: method '%s' (built: average, complete, weighted, ward, single)", method ? method : "");
     GV2_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n == 1) return GV2_OK;
     double *d_D = nullptr, *d_Z = nullptr;
@@ -289,7 +401,7 @@ extern "C" int gv2_linkage_host(gv2_ctx* ctx, const double* dist, int64_t n, con
     if (e == cudaSuccess) {
         lk_mirror_upper_kernel<<<dim3((unsigned)((n + 31) / 32), (unsigned)((n + 7) / 8)), dim3(32, 8), 0, ctx->stream>>>(d_D, n);
         ctx->launches++;
-        rc = lk_launch(ctx, d_D, n * n, n, 1, d_Z);
+        rc = lk_launch(ctx, mth, d_D, n * n, n, 1, d_Z);
     }
     std::vector<double> raw((size_t)(n - 1) * 4);
     if (e == cudaSuccess && rc == GV2_OK) e = cudaMemcpyAsync(raw.data(), d_Z, raw.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);

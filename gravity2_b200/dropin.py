@@ -184,19 +184,23 @@ def binary_jaccard(trait_table, engine: Optional[Engine] = None):
 
 
 # ------------------------------------------------------------------------------ dendrograms
+LINKAGE_METHODS = ("average", "complete", "weighted", "ward", "single")
+
+
 def DistMat2Tree(DistMat, LeafList, Dendrogram_LinkageMethod, do_logscale=False, engine: Optional[Engine] = None):
     """app/utils/dist_mat_to_tree.py:5-21: Newick string of the UPGMA dendrogram of a distance matrix.  The clustering
     (scipy ``linkage`` of the upper triangle) runs on the device, to_tree + GetNewick natively on the host.  Like the
-    reference, negative entries of the caller's matrix are zeroed in place.  Built for method "average" (the default of
-    every shipped payload); other methods raise."""
-    if Dendrogram_LinkageMethod != "average":
-        raise NotImplementedError(f"device linkage is built for method 'average' (got {Dendrogram_LinkageMethod!r})")
+    reference, negative entries of the caller's matrix are zeroed in place.  Built for scipy's nearest-neighbour-chain
+    methods (average -- the default of every shipped payload --, complete, weighted, ward) and single; centroid and
+    median raise."""
+    if Dendrogram_LinkageMethod not in LINKAGE_METHODS:
+        raise NotImplementedError(f"device linkage is built for methods {LINKAGE_METHODS} (got {Dendrogram_LinkageMethod!r})")
     eng = engine or default_engine()
     DistMat[DistMat < 0] = 0
     D = np.asarray(DistMat, dtype=np.float64)
     if do_logscale:
         D = 10 ** D
-    return eng.newick(eng.linkage(D, "average"), LeafList)
+    return eng.newick(eng.linkage(D, Dendrogram_LinkageMethod), LeafList)
 
 
 def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, GOMIDList, payload, LeafList,
@@ -215,8 +219,8 @@ def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, 
     method = payload.get("Dendrogram_LinkageMethod", "average")
     if payload.get("PphmmNeighbourhoodWeight", 0) != 0 or payload.get("PphmmSigScoreThreshold", 0) != 0:
         raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
-    if method != "average":
-        raise NotImplementedError(f"device linkage is built for method 'average' (got {method!r})")
+    if method not in LINKAGE_METHODS:
+        raise NotImplementedError(f"device linkage is built for methods {LINKAGE_METHODS} (got {method!r})")
     loc = sig if pipeline == "pl1" else np.ascontiguousarray(PPHMMLocationTable, dtype=np.float64)
     gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
     job = Job(eng, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance=True)

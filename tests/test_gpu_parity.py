@@ -483,10 +483,11 @@ def test_fused_tail_equals_separate_kernels(eng, scheme, pw, kind):
 
 
 # ------------------------------------------------------------------------ dendrograms
+@pytest.mark.parametrize("method", ["average", "complete", "weighted", "ward", "single"])
 @pytest.mark.parametrize("n,kind", [(2, "random"), (3, "ties"), (17, "ties"), (130, "random"), (513, "ties"), (1500, "blocks")])
-def test_device_linkage_equals_scipy(eng, n, kind):
-    """UPGMA on the device == scipy.cluster.hierarchy.linkage(method="average") row for row, bit for bit: heights from the
-    same three rounded operations, ties resolved in scipy's nearest-neighbour-chain order."""
+def test_device_linkage_equals_scipy(eng, n, kind, method):
+    """Device linkage == scipy.cluster.hierarchy.linkage(method) row for row, bit for bit: heights from the same
+    separately rounded operations, ties resolved in the order scipy's nn_chain / mst_single_linkage resolve them."""
     from scipy.cluster.hierarchy import linkage
     rng = np.random.default_rng(n)
     if kind == "random":
@@ -498,12 +499,12 @@ def test_device_linkage_equals_scipy(eng, n, kind):
         D = np.where(grp[:, None] == grp[None, :], np.round(rng.random((n, n)) * 0.6, 3), 1.0)
     D = np.triu(D, 1)
     D = D + D.T
-    Z = eng.linkage(D)
-    ref = linkage(D[np.triu_indices_from(D, k=1)], method="average")
+    Z = eng.linkage(D, method)
+    ref = linkage(D[np.triu_indices_from(D, k=1)], method=method)
     assert Z.shape == ref.shape and np.array_equal(Z, ref)
     # an asymmetric matrix is clustered by its upper triangle, as the reference does
     A = D + np.tril(rng.random((n, n)), -1)
-    assert np.array_equal(eng.linkage(A), ref)
+    assert np.array_equal(eng.linkage(A, method), ref)
 
 
 @pytest.mark.parametrize("tag", ["A", "B"])
@@ -519,8 +520,9 @@ def test_dist_mat_to_tree_golden(golden, eng, tag):
     Dn = D.copy()
     Dn[D == 0] = -0.5
     assert G.DistMat2Tree(Dn, names, "average", False) == str(golden[f"{tag}_newick_avg"]) and np.array_equal(Dn, D)
+    assert G.DistMat2Tree(D.copy(), names, "complete", True) == O.dist_mat_to_tree(D.copy(), names, "complete", True)
     with pytest.raises(NotImplementedError):
-        G.DistMat2Tree(D, names, "single", False)
+        G.DistMat2Tree(D, names, "centroid", False)
 
 
 def test_bootstrap_newick_equals_matrices_then_scipy(eng):

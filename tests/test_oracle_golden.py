@@ -199,3 +199,20 @@ def test_neighbourhood_host_logic_random():
         for r, cols in pos.items():
             ref[r, cols] |= NB.POS
         assert np.array_equal(NB.neighbourhood_classes(loc, sig), ref)
+
+
+# ------------------------------------------------- scipy's linkage, restated (third-party arithmetic on the tree step)
+@pytest.mark.parametrize("method", ["average", "complete", "weighted", "ward", "single"])
+def test_linkage_restatement_is_scipy(method):
+    """oracle/linkage_oracle.py (nn_chain / mst_single_linkage / label of scipy/cluster/_hierarchy.pyx, loop for loop) ==
+    the installed scipy, bit for bit, on matrices with and without exact ties."""
+    from scipy.cluster.hierarchy import linkage
+    from oracle import linkage_oracle as L
+    rng = np.random.default_rng(5)
+    for trial in range(8):
+        n = int(rng.integers(2, 50))
+        D = rng.integers(1, 6, (n, n)) / 5.0 if trial % 2 else rng.random((n, n))
+        D = np.triu(D, 1)
+        D = D + D.T
+        dl = D[np.triu_indices_from(D, k=1)]
+        assert np.array_equal(L.linkage(dl, method), linkage(dl, method=method))
