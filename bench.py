@@ -178,7 +178,7 @@ def run_reference(args, cfg):
             "config": workload_config(args, cfg, 1),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cfg, world):
@@ -191,7 +191,23 @@ def workload_config(args, cfg, world):
 
 
 # -------------------------------------------------------------------------------- our arm
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything else the run prints (library banners such as
+    NCCL's version line, warnings) was redirected to stderr by main()."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                              # fd 1 -> stderr for native libraries and child processes
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
@@ -331,14 +347,17 @@ def main():
     peaks, peak_kind = load_peaks()
     if rank == 0:
         roofline = make_roofline(times, path, cells, steps, n, p, g, len(my_reps), ms, peaks, peak_kind)
-    # ---- end to end through the host-pointer C ABI
+    # ---- end to end through the public host API: release the device-resident job first (its workspaces hold ~100 GB)
+    lib.gv2_job_destroy(job)
+    job = None
+    del d_out, d_base, d_sig
+    torch.cuda.empty_cache()
     if not args.no_e2e:
         e2e = measure_e2e(lib, ctx, ck, t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist if world > 1 else None, torch,
                           steps=max(1, min(steps, 2)))
     e2e_trees = None
     if not args.no_e2e and B > 0:
         e2e_trees = measure_e2e_trees(t, gor, weights, my_reps, n, p, g, B, pairs, world, rank, dist if world > 1 else None, torch)
-    lib.gv2_job_destroy(job)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -349,7 +368,7 @@ def main():
                 "data": "synthetic",
                 "config": workload_config(args, cfg, world), "clocks": clocks, "gpu_launches": launches,
                 "e2e": e2e, "e2e_trees": e2e_trees, "roofline": roofline, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -377,7 +396,10 @@ def make_roofline(times, path, cells, steps, n, p, g, nrep, region_ms, peaks, pe
         slots = nrep * float(pairs) * g * 2
         lines["tail"] = {"kernel": "gj_fused_kernel (GOM-signature (min,+) pair sums on 128x64 tiles + clean/combine/clamp/1-S/mirror epilogue)",
                          "bound": "hbm", "achieved": bytes_step / sec / 1e9, "peak": hbm, "unit": "GB/s",
-                         "frac": bytes_step / sec / 1e9 / hbm, "traffic": None,
+                         "frac": bytes_step / sec / 1e9 / hbm,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch (10 replicates at cfg3), ncu --set full,
+                         # profiles/r01_top_kernels_ncu_full.csv; algorithmic bytes of the same launch: 1.21e10
+                         "traffic": 1.2472e10 if (n, g, round(nrep / max(cnt / steps, 1))) == (10000, 200, 10) else None,
                          "pipe": {"bound": "fp32/alu issue (2 slots per cell: FMNMX + FADD)", "achieved": slots / sec, "peak": fp32_issue,
                                   "unit": "thread-instr/s", "frac": slots / sec / fp32_issue},
                          "launches_per_step": cnt / steps, "avg_launch_ms": ms / cnt, "share_of_step": ms / region_ms,

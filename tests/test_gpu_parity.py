@@ -589,6 +589,12 @@ def test_full_size_properties_cfg3(eng):
     assert np.allclose(seen[0][0], S[:64], rtol=1e-6, atol=1e-12)
     for b in range(8):
         assert seen[b][1] == 1.0 and seen[b][2] == 0.0 and seen[b][3]
+    # device UPGMA at full size: the base distance matrix (10 000 leaves, thousands of exact ties at D = 1) against scipy
+    from scipy.cluster.hierarchy import linkage
+    D = 1.0 - S
+    D[D < 0] = 0
+    Zd = eng.linkage(D, "average")
+    assert np.array_equal(Zd, linkage(D[np.triu_indices_from(D, k=1)], method="average"))
     i, j = 3, 4711
     ww = w[5].astype(np.float64)
     ref = np.sum(np.minimum(sig[i], sig[j]) * ww) / np.sum(np.maximum(sig[i], sig[j]) * ww)
