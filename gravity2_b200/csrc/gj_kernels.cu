@@ -14,6 +14,8 @@
 
 #include <math.h>
 
+#include <type_traits>
+
 #define GJ_PRAGMA_(x) _Pragma(#x)
 #define GJ_UNROLL(n) GJ_PRAGMA_(unroll n)
 #define GJ_THREADS 256
@@ -356,50 +358,63 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
         psj[nn] = (ok && has_p) ? ((p_nf && p_nf[gj]) ? qnan : p_rs[gj]) : 0.0;
     }
     __syncthreads();                                                 // the ring is dead: reuse it as the transpose stage
+    // Two instances of the same loop body: interior off-diagonal tiles (all but ~2 n/128 of them) need no bounds tests,
+    // no diagonal special case and no index swap, which removes about a third of the epilogue's instructions.
+    auto rows = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        double* orow = o + ((long long)bi * GV2_TILE + ty) * n + (long long)bj * GV2_TILE + half * 64 + tx;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const int r = ty + 16 * m;
-        const long long gi = (long long)bi * GV2_TILE + r;
-        const bool oki = gi < n;
-        const double gsi = oki ? ((g_nf && g_nf[gi]) ? qnan : g_rs[gi]) : 0.0;
-        const double psi = (oki && has_p) ? ((p_nf && p_nf[gi]) ? qnan : p_rs[gi]) : 0.0;
-        double pv[4];
+        for (int m = 0; m < 8; ++m) {
+            const int r = ty + 16 * m;
+            const long long gi = (long long)bi * GV2_TILE + r;
+            const bool oki = FAST || gi < n;
+            const double gsi = oki ? ((g_nf && g_nf[gi]) ? qnan : g_rs[gi]) : 0.0;
+            const double psi = (oki && has_p) ? ((p_nf && p_nf[gi]) ? qnan : p_rs[gi]) : 0.0;
+            double pv[4];
 #pragma unroll
-        for (int nn = 0; nn < 4; ++nn) {
-            const int c = half * 64 + tx + 16 * nn;
-            // diagonal tiles: the replicate kernels leave the entries below the diagonal unwritten
-            const int rr = (bi == bj && r > c) ? c : r, cc = (bi == bj && r > c) ? r : c;
-            pv[nn] = has_p ? p_ws[gj_ws_index(rr, cc)] : 0.0;
-        }
-#pragma unroll
-        for (int nn = 0; nn < 4; ++nn) {
-            const int cl = tx + 16 * nn;
-            const long long gj = (long long)bj * GV2_TILE + half * 64 + cl;
-            // GJ = sum(min) / sum(max), 0 when sum(max) == 0 (:168), NaN and negatives cleaned to 0 (:204-205), then
-            // (P * G) ** 0.5 (:214) as ONE reciprocal square root: sqrt(Np Ng / (Dp Dg)) = Np Ng rsqrt(Np Ng Dp Dg).
-            // N D > 0 says: sum(max) != 0, ratio positive, nothing NaN.
-            const bool diag = gi == gj;
-            const double ng = diag ? gsi : sum[m][nn];                 // diagonal: sum(min) == sum(a) exactly
-            const double dg = gsi + gsj[nn] - ng;
-            const double ag = ng * dg;
-            double sv;
-            if (has_p) {
-                const double np_ = diag ? psi : pv[nn];
-                const double dp = psi + psj[nn] - np_;
-                const double ap = np_ * dp;
-                const double num = np_ * ng, den = dp * dg, x = ag * ap;
-                sv = (num == den) ? 1.0 : fabs(num) * gj_rsqrt(x);   // == : diagonal, duplicate genomes
-                if (!(ag > 0.0 && ap > 0.0)) sv = 0.0;
-            } else {
-                sv = (ng == dg) ? 1.0 : fabs(ng) * gj_rcp(fabs(dg));
-                if (!(ag > 0.0)) sv = 0.0;
+            for (int nn = 0; nn < 4; ++nn) {
+                if (FAST) {
+                    pv[nn] = has_p ? p_ws[(size_t)((m * 8 + half * 4 + nn) * 256 + tid)] : 0.0;   // == gj_ws_index(r, c)
+                } else {
+                    const int c = half * 64 + tx + 16 * nn;
+                    // diagonal tiles: the replicate kernels leave the entries below the diagonal unwritten
+                    const int rr = (bi == bj && r > c) ? c : r, cc = (bi == bj && r > c) ? r : c;
+                    pv[nn] = has_p ? p_ws[gj_ws_index(rr, cc)] : 0.0;
+                }
             }
-            if (powered) sv = pow(sv, fz.pw);                        // :226 (sv >= 0 already, :224)
-            if (as_distance) sv = fmax(1.0 - sv, 0.0);               // pl1_graphs.py:52-53
-            if (oki && gj < n) o[gi * n + gj] = sv;
-            stage[cl * GJ_STAGE_LD + r] = sv;
+#pragma unroll
+            for (int nn = 0; nn < 4; ++nn) {
+                const int cl = tx + 16 * nn;
+                const long long gj = (long long)bj * GV2_TILE + half * 64 + cl;
+                // GJ = sum(min) / sum(max), 0 when sum(max) == 0 (:168), NaN and negatives cleaned to 0 (:204-205), then
+                // (P * G) ** 0.5 (:214) as ONE reciprocal square root: sqrt(Np Ng / (Dp Dg)) = Np Ng rsqrt(Np Ng Dp Dg).
+                // N D > 0 says: sum(max) != 0, ratio positive, nothing NaN.
+                const bool diag = !FAST && gi == gj;
+                const double ng = diag ? gsi : sum[m][nn];             // diagonal: sum(min) == sum(a) exactly
+                const double dg = gsi + gsj[nn] - ng;
+                const double ag = ng * dg;
+                double sv;
+                if (has_p) {
+                    const double np_ = diag ? psi : pv[nn];
+                    const double dp = psi + psj[nn] - np_;
+                    const double ap = np_ * dp;
+                    const double num = np_ * ng, den = dp * dg, x = ag * ap;
+                    sv = (num == den) ? 1.0 : fabs(num) * gj_rsqrt(x);   // == : diagonal, duplicate genomes
+                    if (!(ag > 0.0 && ap > 0.0)) sv = 0.0;
+                } else {
+                    sv = (ng == dg) ? 1.0 : fabs(ng) * gj_rcp(fabs(dg));
+                    if (!(ag > 0.0)) sv = 0.0;
+                }
+                if (powered) sv = pow(sv, fz.pw);                    // :226 (sv >= 0 already, :224)
+                if (as_distance) sv = fmax(1.0 - sv, 0.0);           // pl1_graphs.py:52-53
+                if (FAST || (oki && gj < n)) orow[(long long)(16 * m) * n + 16 * nn] = sv;
+                stage[cl * GJ_STAGE_LD + r] = sv;
+            }
         }
-    }
+    };
+    const bool interior = bi != bj && ((long long)bi + 1) * GV2_TILE <= n && (long long)bj * GV2_TILE + half * 64 + 64 <= n;
+    if (interior) rows(std::true_type{});
+    else rows(std::false_type{});
     if (bi == bj) return;                                            // diagonal tiles hold both triangles already
     __syncthreads();
     // mirror: rows bj*128 + 64 half + [0, 64), columns bi*128 + [0, 128): 128 consecutive doubles per staged row
