@@ -86,7 +86,7 @@ PROTOTYPES = {
     "gv2_dev_gj_epilogue": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_i64, C.POINTER(GjComponent),
                                       C.POINTER(GjComponent), c_vp, C.c_int, C.c_double, C.c_int, C.c_int, c_vp,
                                       c_i64]),
-    "gv2_dev_gj_fused": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, C.POINTER(GjComponent), C.POINTER(GjComponent),
+    "gv2_dev_gj_fused": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, C.POINTER(GjComponent), C.POINTER(GjComponent),
                                    C.c_int, C.c_double, C.c_int, c_vp, c_i64]),
     "gv2_dev_unpack_tiles": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gv2_dev_pack_presence": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_vp]),

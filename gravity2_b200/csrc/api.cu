@@ -16,7 +16,7 @@
 int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n_pad, int64_t k_pad,
                        int64_t tile_begin, int64_t tile_end, const float* w, int64_t nb, int ksplit,
                        double* ws);
-int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k_pad, int64_t nb,
+int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k, int64_t k_pad, int64_t nb,
                     const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
                     double* out, int64_t out_replicate_stride);
 int boot_mma_available();
@@ -632,7 +632,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 cg.rowsums = job->gom_rowsum.as<double>() + c0 * n; cg.nanflags = job->gom_nan.as<uint8_t>() + c0 * n;
                 cg.ksplit = 1; cg.replicate_stride_rows = n; cg.replicate_stride_nan = n;
                 if ((rc = gj_fused_launch(ctx, job->gomf.as<float>() + (size_t)c0 * job->n_pad * job->g_pad, job->n_pad * job->g_pad, n,
-                                          job->n_pad, job->g_pad, cb, job->need_p ? &cp : nullptr, &cg, job->scheme, job->power,
+                                          job->n_pad, g, job->g_pad, cb, job->need_p ? &cp : nullptr, &cg, job->scheme, job->power,
                                           job->out_kind, dev_ring + slot * n * n, n * n))) return rc;
             } else {
                 // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)

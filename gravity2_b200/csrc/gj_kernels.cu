@@ -257,7 +257,7 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
 static size_t gf_smem_bytes() { return (size_t)GF_STAGES * GF_STAGE_FLOATS * sizeof(float); }
 
 __global__ void __launch_bounds__(GJ_THREADS, 2)
-gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int nkb, int nt, const GjFuse fz) {
+gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int nkb, int k_groups, int nt, const GjFuse fz) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -309,8 +309,10 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
         }
         const float* a = smem + (it % GF_STAGES) * GF_STAGE_FLOATS + ty * GJ_LDS;
         const float* bb = smem + (it % GF_STAGES) * GF_STAGE_FLOATS + (GV2_TILE + tx) * GJ_LDS;
+        // the zero padding beyond the last real column (G = 200 is padded to 224) contributes nothing: skip its 4-column groups
+        const int nkg = min(GV2_BK / 4, k_groups - it * (GV2_BK / 4));
 #pragma unroll 2
-        for (int kg = 0; kg < GV2_BK / 4; ++kg) {
+        for (int kg = 0; kg < nkg; ++kg) {
             float4 bf[4];
 #pragma unroll
             for (int n = 0; n < 4; ++n) bf[n] = *reinterpret_cast<const float4*>(bb + n * 16 * GJ_LDS + kg * 4);
@@ -700,11 +702,11 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
 static GjComp to_comp(const gv2_gj_component* c);
 
 // Fused GOM pair sums + epilogue for replicates [0, nb): one table per replicate (tab_stride), all tiles, schemes G and PG.
-int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k_pad, int64_t nb,
+int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k, int64_t k_pad, int64_t nb,
                     const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
                     double* out, int64_t out_replicate_stride) {
     if (scheme != GV2_SCHEME_G && scheme != GV2_SCHEME_PG) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: scheme %d", scheme);
-    if (!tab || !comp_g || !comp_g->rowsums || !out || (k_pad % GV2_BK) || (n_pad % GV2_TILE) ||
+    if (!tab || !comp_g || !comp_g->rowsums || !out || (k_pad % GV2_BK) || (n_pad % GV2_TILE) || k < 0 || k > k_pad ||
         (scheme == GV2_SCHEME_PG && (!comp_p || !comp_p->min_sums || !comp_p->rowsums || comp_p->ksplit != 1)))
         return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: bad arguments");
     const int64_t ntl = gv2_num_tiles(n);
@@ -725,17 +727,20 @@ int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t 
     dim3 grid((unsigned)(2 * ntl), 1, (unsigned)nb);
     Gv2Timer timer(ctx, GV2_TIME_TAIL);
     timer.begin();
-    gj_fused_kernel<<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, (int)(k_pad / GV2_BK), (int)(n_pad / GV2_TILE), fz);
+    const int k_groups = (int)((k + 3) / 4);                     // 4-column groups that hold real columns
+    const int nkb = (int)((k + GV2_BK - 1) / GV2_BK);            // stages that hold real columns
+    gj_fused_kernel<<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, nkb, k_groups, (int)(n_pad / GV2_TILE), fz);
     GV2_LAUNCH_CHECK(ctx);
     timer.end();
     return GV2_OK;
 }
 
 extern "C" int gv2_dev_gj_fused(gv2_ctx* ctx, const float* tab, int64_t tab_replicate_stride, int64_t n, int64_t n_pad,
-                                int64_t k_pad, int64_t nb, const gv2_gj_component* comp_p, const gv2_gj_component* comp_g,
-                                int scheme, double p, int out_kind, double* out, int64_t out_replicate_stride) {
+                                int64_t k, int64_t k_pad, int64_t nb, const gv2_gj_component* comp_p,
+                                const gv2_gj_component* comp_g, int scheme, double p, int out_kind, double* out,
+                                int64_t out_replicate_stride) {
     if (!ctx) return GV2_ERR_ARG;
-    return gj_fused_launch(ctx, tab, tab_replicate_stride, n, n_pad, k_pad, nb, comp_p, comp_g, scheme, p, out_kind, out,
+    return gj_fused_launch(ctx, tab, tab_replicate_stride, n, n_pad, k, k_pad, nb, comp_p, comp_g, scheme, p, out_kind, out,
                            out_replicate_stride);
 }
 

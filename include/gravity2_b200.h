@@ -249,13 +249,14 @@ int gv2_dev_gj_epilogue(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_t til
                         const double* spr, int scheme, double power, int out_kind, int packed,
                         double* out, int64_t out_replicate_stride);
 /* K1 + K3 in one kernel for the per-replicate tail (schemes G and PG, all tiles): pair sums of the fp32 table(s)
- * `tab` (one [n_pad][k_pad] table per replicate, tab_replicate_stride elements apart; the GOM signature tables)
+ * `tab` (one [n_pad][k_pad] table per replicate, k real columns, tab_replicate_stride elements apart; the GOM signature tables)
  * are formed in registers and combined at once with the PPHMM component comp_p (its min_sums from
  * gv2_dev_gj_min_sums / the replicate kernels, ksplit == 1; NULL for scheme G); comp_g carries only the row sums and
  * NaN flags of `tab`.  out [nb][n][n], symmetric. */
 int gv2_dev_gj_fused(gv2_ctx* ctx, const float* tab, int64_t tab_replicate_stride, int64_t n, int64_t n_pad,
-                     int64_t k_pad, int64_t nb, const gv2_gj_component* comp_p, const gv2_gj_component* comp_g,
-                     int scheme, double p, int out_kind, double* out, int64_t out_replicate_stride);
+                     int64_t k, int64_t k_pad, int64_t nb, const gv2_gj_component* comp_p,
+                     const gv2_gj_component* comp_g, int scheme, double p, int out_kind, double* out,
+                     int64_t out_replicate_stride);
 int gv2_dev_unpack_tiles(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_t tile_end,
                          const double* packed, double* out);
 /* K6: bit-pack `tab != 0` into [n_pad][words] uint64 rows; counts per pair tile range. */

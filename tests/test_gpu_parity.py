@@ -468,7 +468,7 @@ def test_fused_tail_equals_separate_kernels(eng, scheme, pw, kind):
     fused = torch.full((nb, n, n), -7.0, dtype=torch.float64, device="cuda")
     cgf = _lib.GjComponent(min_sums=None, rowsums=grs.data_ptr(), nanflags=gnf.data_ptr(), ksplit=1,
                            replicate_stride_rows=n, replicate_stride_nan=n)
-    assert lib.gv2_dev_gj_fused(ctx, vp(gtabs), n_pad * g_pad, n, n_pad, g_pad, nb, C.byref(cp) if scheme == "PG" else None,
+    assert lib.gv2_dev_gj_fused(ctx, vp(gtabs), n_pad * g_pad, n, n_pad, g, g_pad, nb, C.byref(cp) if scheme == "PG" else None,
                                 C.byref(cgf), _lib.SCHEMES[scheme], pw, out_kind, vp(fused), n * n) == 0, lib.gv2_last_error(ctx)
     torch.cuda.synchronize()
     a, b = fused.cpu().numpy(), sep.cpu().numpy()
