@@ -31,6 +31,7 @@ int boot_mma_rowsums(gv2_ctx* ctx, const double* ws, int64_t ntl, int64_t n, int
 struct BootSparse;
 int boot_sparse_build(gv2_ctx* ctx, const double* tab, int64_t n, int64_t k, int64_t ld, int64_t n_pad, int64_t k_pad,
                       double max_value, BootSparse** out);
+int boot_sparse_build_lists(gv2_ctx* ctx, BootSparse* s, size_t budget);
 void boot_sparse_free(BootSparse* s);
 size_t boot_sparse_bytes(const BootSparse* s);
 long long boot_sparse_nnz(const BootSparse* s);
@@ -349,6 +350,12 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
                 if (p > 65536) sparse_wins = false;
                 if (path && !strcmp(path, "sparse")) sparse_wins = true;
                 if (path && !strcmp(path, "mma")) sparse_wins = false;
+                if (sparse_wins) {
+                    // the match phase is replicate independent: write the pair lists once if they fit a tenth of the memory
+                    size_t free_b = 0, total_b = 0;
+                    cudaMemGetInfo(&free_b, &total_b);
+                    if ((rc = boot_sparse_build_lists(ctx, j->sparse, free_b / 10))) return bail(rc);
+                }
                 if (!sparse_wins) {
                     boot_sparse_free(j->sparse);
                     j->sparse = nullptr;

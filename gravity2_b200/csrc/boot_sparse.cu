@@ -272,6 +272,184 @@ boot_sparse_kernel(BsCsr csr, int nt, long long tile_begin, const uint8_t* __res
     }
 }
 
+// ---------------------------------------------------------------------------------- precomputed pair lists
+// The match phase does not depend on the replicate, so for tables whose lists fit in memory (cfg3: 2.2e8 entries,
+// 2.4 GB) it runs ONCE per job: the co-present (column, min value) lists of every genome pair are written to global
+// memory, and the per-launch kernel only streams them.  Without the 60 KB mask the streaming kernel holds three CTAs
+// per SM instead of two and has no barriers at all.
+//   rows:   one per (16 x 16 block, i-row): rowptr[row] = first entry; pend[row][jj] = end of pair (i, jj)'s list
+//           relative to rowptr[row] (lists back to back, each padded to a multiple of 4 entries with zero entries)
+//   entry:  x = column | low limb << 16 (needs k_pad <= 65536), y = high limb
+struct BsLists {
+    long long* rowptr = nullptr;   // [nrows + 1]
+    uint32_t* pend = nullptr;      // [nrows][16]
+    uint2* ent = nullptr;          // [rowptr[nrows]]
+    long long nrows = 0, nent = 0;
+    size_t bytes = 0;
+};
+
+#define BS_LIST_SMEM(KP) ((size_t)(KP) * 2 + 16 * BS_JCAP * 4 + (256 + 256 + 16) * sizeof(int))
+
+// FILL == false: pend (cumulative, padded) and rowtot per row.  FILL == true: entries at rowptr.  grid = (64, tiles)
+template <bool FILL>
+__global__ void __launch_bounds__(BS_THREADS, 1)
+bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowtot, const long long* __restrict__ rowptr,
+                      uint32_t* __restrict__ pend, uint2* __restrict__ ent) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t* mask32 = (uint32_t*)smem;                              // [k_pad / 2]
+    int* jcol = (int*)(smem + (size_t)k_pad * 2);                    // [16][BS_JCAP]
+    int* cnt = jcol + 16 * BS_JCAP;                                  // [256]
+    int* fillc = cnt + 256;                                          // [256]
+    int* jlen = fillc + 256;                                         // [16]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = blockIdx.x, si = sub >> 3, sj = sub & 7;
+    int bi, bj;
+    bs_tile_coords(blockIdx.y, nt, &bi, &bj);
+    const long long row0 = ((long long)blockIdx.y * 64 + sub) * 16;
+    if (bi == bj && si > sj) {                                       // block entirely below the diagonal: empty rows
+        if (!FILL && tid < 16) rowtot[row0 + tid] = 0;
+        if (!FILL) pend[row0 * 16 + tid] = 0;
+        return;
+    }
+    const bool diag_block = bi == bj && si == sj;
+    const long long rowI0 = (long long)bi * GV2_TILE + si * 16, rowJ0 = (long long)bj * GV2_TILE + sj * 16;
+    for (int q = tid; q < k_pad / 2; q += BS_THREADS) mask32[q] = 0u;
+    cnt[tid] = 0;
+    fillc[tid] = 0;
+    __syncthreads();
+    for (int h = 0; h < 2; ++h) {
+        const int jj = warp + 8 * h;
+        const long long j0 = csr.ptr[rowJ0 + jj], j1 = csr.ptr[rowJ0 + jj + 1];
+        if (lane == 0) jlen[jj] = (int)(j1 - j0);
+        for (long long e = j0 + lane; e < j1; e += 32) {
+            const int c = csr.col[e];
+            if (e - j0 < BS_JCAP) jcol[jj * BS_JCAP + (int)(e - j0)] = c;
+            atomicOr(&mask32[c >> 1], 1u << (jj + 16 * (c & 1)));
+        }
+    }
+    __syncthreads();
+    for (int ii = 0; ii < 16; ++ii) {
+        const long long e0 = csr.ptr[rowI0 + ii], e1 = csr.ptr[rowI0 + ii + 1];
+        const unsigned keep = diag_block ? (0xffffu << ii) & 0xffffu : 0xffffu;   // pairs below the diagonal are never read
+        const long long rbase = FILL ? rowptr[row0 + ii] : 0;
+        for (long long e = e0 + tid; e < e1; e += BS_THREADS) {
+            const int c = csr.col[e];
+            unsigned m = (mask32[c >> 1] >> (16 * (c & 1))) & keep;
+            if (!m) continue;
+            if (!FILL) {
+                while (m) { const int jj = __ffs(m) - 1; m &= m - 1; atomicAdd(&cnt[ii * 16 + jj], 1); }
+            } else {
+                const unsigned long long fi = ((unsigned long long)csr.hi[e] << BS_LO_BITS) | csr.lo[e];
+                while (m) {
+                    const int jj = __ffs(m) - 1;
+                    m &= m - 1;
+                    const long long j0 = csr.ptr[rowJ0 + jj];
+                    const int pos = bs_find(jcol + jj * BS_JCAP, min(jlen[jj], BS_JCAP), csr.col + j0, jlen[jj], c);
+                    const unsigned long long fj = ((unsigned long long)csr.hi[j0 + pos] << BS_LO_BITS) | csr.lo[j0 + pos];
+                    const unsigned long long f = min(fi, fj);
+                    const int q = ii * 16 + jj;
+                    const long long at = rbase + (jj ? pend[(row0 + ii) * 16 + jj - 1] : 0u) + atomicAdd(&fillc[q], 1);
+                    ent[at] = make_uint2((uint32_t)c | ((uint32_t)(f & 0xffffu) << 16), (uint32_t)(f >> BS_LO_BITS));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!FILL) {
+        // thread (ii, jj): padded cumulative end of its pair's list within the row (16-wide inclusive scan by shuffles)
+        const int ii = tid >> 4, jj = tid & 15;
+        int v = (cnt[tid] + 3) & ~3;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, v, o, 16);
+            if (jj >= o) v += u;
+        }
+        pend[(row0 + ii) * 16 + jj] = (uint32_t)v;
+        if (jj == 15) rowtot[row0 + ii] = v;
+    } else {
+        // zero entries up to the padded end of every list
+        const int ii = tid >> 4, jj = tid & 15;
+        const long long rbase = rowptr[row0 + ii];
+        const uint32_t beg = jj ? pend[(row0 + ii) * 16 + jj - 1] : 0u, end = pend[(row0 + ii) * 16 + jj];
+        for (uint32_t k = beg + (uint32_t)fillc[tid]; k < end; ++k) ent[rbase + k] = make_uint2(0u, 0u);
+    }
+}
+
+// Streams the precomputed lists: lane = replicate, slot s takes i-rows s, s + PP, ... of the block.
+// grid = (64 sub-blocks, tiles, replicate blocks of RL)
+template <int RL>
+__global__ void __launch_bounds__(BS_THREADS, 3)
+boot_sparse_lists_kernel(const long long* __restrict__ rowptr, const uint32_t* __restrict__ pend, const uint2* __restrict__ ent,
+                         int nt, const uint8_t* __restrict__ wT, long long w_ld, int nb_total, long long ws_rep_stride,
+                         double quantum, double* __restrict__ ws) {
+    constexpr int PP = BS_THREADS / RL;
+    const int tid = threadIdx.x;
+    const int sub = blockIdx.x, si = sub >> 3, sj = sub & 7;
+    int bi, bj;
+    bs_tile_coords(blockIdx.y, nt, &bi, &bj);
+    if (bi == bj && si > sj) return;
+    const int slot = tid / RL, rl = tid % RL;
+    const int rep0 = blockIdx.z * RL + rl;
+    const long long row0 = ((long long)blockIdx.y * 64 + sub) * 16;
+    double* wsblk = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + (size_t)(((si << 3) + sj) << 8);
+    const double q_hi = quantum * 65536.0;
+    const uint8_t* wTl = wT + rep0;
+    const uint32_t wld32 = (uint32_t)w_ld;
+    for (int r = slot; r < 16; r += PP) {
+        const uint2* list = ent + rowptr[row0 + r];
+        const uint4* pe4 = reinterpret_cast<const uint4*>(pend + (row0 + r) * 16);
+        uint32_t pe[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = __ldg(pe4 + q);
+            pe[4 * q] = v.x; pe[4 * q + 1] = v.y; pe[4 * q + 2] = v.z; pe[4 * q + 3] = v.w;
+        }
+        const uint32_t end = pe[15];
+        unsigned long long ahi[16];
+        uint32_t alo[16];
+        uint32_t wb[4];
+        if (end) {
+            const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(list)), p1 = __ldg(reinterpret_cast<const uint4*>(list + 2));
+            wb[0] = __ldg(wTl + (p0.x & 0xffffu) * wld32);
+            wb[1] = __ldg(wTl + (p0.z & 0xffffu) * wld32);
+            wb[2] = __ldg(wTl + (p1.x & 0xffffu) * wld32);
+            wb[3] = __ldg(wTl + (p1.z & 0xffffu) * wld32);
+        }
+        uint32_t e = 0;
+#pragma unroll
+        for (int a = 0; a < 16; ++a) {
+            const uint32_t ne = pe[a];
+            unsigned long long h = 0ull;
+            uint32_t l = 0u;
+            for (; e < ne; e += 4) {                                   // lists are padded: a whole step belongs to one pair
+                const uint32_t w0 = wb[0], w1 = wb[1], w2 = wb[2], w3 = wb[3];
+                const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(list + e)), c1 = __ldg(reinterpret_cast<const uint4*>(list + e + 2));
+                if (e + 4 < end) {
+                    const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(list + e + 4)), n1 = __ldg(reinterpret_cast<const uint4*>(list + e + 6));
+                    wb[0] = __ldg(wTl + (n0.x & 0xffffu) * wld32);
+                    wb[1] = __ldg(wTl + (n0.z & 0xffffu) * wld32);
+                    wb[2] = __ldg(wTl + (n1.x & 0xffffu) * wld32);
+                    wb[3] = __ldg(wTl + (n1.z & 0xffffu) * wld32);
+                }
+                h += (unsigned long long)c0.y * w0;
+                h += (unsigned long long)c0.w * w1;
+                h += (unsigned long long)c1.y * w2;
+                h += (unsigned long long)c1.w * w3;
+                l += (c0.x >> 16) * w0 + (c0.z >> 16) * w1 + (c1.x >> 16) * w2 + (c1.z >> 16) * w3;
+            }
+            ahi[a] = h;
+            alo[a] = l;
+        }
+        if (rep0 < nb_total) {
+            double* o = wsblk + (size_t)rep0 * ws_rep_stride + (r << 4);
+#pragma unroll
+            for (int a = 0; a < 16; a += 2)
+                *reinterpret_cast<double2*>(o + a) = make_double2((double)ahi[a] * q_hi + (double)alo[a] * quantum,
+                                                                  (double)ahi[a + 1] * q_hi + (double)alo[a + 1] * quantum);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------- CSR of the fixed-point table
 // entries: x > 0 (NaN rows are flagged separately by prepare_table; negative tables do not come here)
 __device__ __forceinline__ unsigned long long bs_fixed48(double x, double scale) {
@@ -378,11 +556,14 @@ struct BootSparse {
     unsigned long long cells = 0;     // co-present (pair incl. diagonal, column) cells
     double quantum = 0.0;             // value of one unit of the 48-bit fixed point
     size_t bytes = 0;
+    BsLists lists;                    // precomputed pair lists (rowptr == nullptr: match on the fly)
+    int64_t n_pad = 0, k_pad = 0;
 };
 
 void boot_sparse_free(BootSparse* s) {
     if (!s) return;
     cudaFree(s->ptr); cudaFree(s->col); cudaFree(s->hi); cudaFree(s->lo);
+    cudaFree(s->lists.rowptr); cudaFree(s->lists.pend); cudaFree(s->lists.ent);
     delete s;
 }
 
@@ -443,7 +624,62 @@ int boot_sparse_build(gv2_ctx* ctx, const double* tab, int64_t n, int64_t k, int
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "column statistics");
     cudaFree(cnt); cudaFree(colcnt); cudaFree(cells); cudaFree(tmp);
     s->bytes = (size_t)(n_pad + 1) * sizeof(long long) + nz * (sizeof(int) + sizeof(uint32_t) + sizeof(uint16_t));
+    s->n_pad = n_pad; s->k_pad = k_pad;
     *out = s;
+    return GV2_OK;
+}
+
+// Pair lists for all tiles: two passes (count, fill) around one scan.  Skipped (the launch then matches on the fly) when
+// the table is wider than 65536 columns, the lists would take more than `budget` bytes, or GV2_SPARSE_LISTS=0.
+int boot_sparse_build_lists(gv2_ctx* ctx, BootSparse* s, size_t budget) {
+    const char* env = getenv("GV2_SPARSE_LISTS");
+    if (env && env[0] == '0') return GV2_OK;
+    const int64_t n_pad = s->n_pad, k_pad = s->k_pad;
+    if (k_pad > 65536 || BS_LIST_SMEM(k_pad) > 200 * 1024) return GV2_OK;
+    const int64_t nt = n_pad / GV2_TILE, ntl = nt * (nt + 1) / 2;
+    if (ntl > 65535) return GV2_OK;
+    // padded entries <= co-present cells + 3 per pair; a cheap upper bound decides before anything is allocated
+    const double upper = ((double)s->cells + 1.5 * 0.5 * (double)n_pad * (double)n_pad) * 8.0 + (double)ntl * 64 * 16 * 72.0;
+    if (upper > (double)budget) return GV2_OK;
+    BsLists L;
+    L.nrows = ntl * 64 * 16;
+    long long* rowtot = nullptr;
+    void* tmp = nullptr;
+    auto fail = [&](cudaError_t e, const char* what) {
+        cudaFree(rowtot); cudaFree(tmp); cudaFree(L.rowptr); cudaFree(L.pend); cudaFree(L.ent);
+        return gv2_fail(ctx, e == cudaErrorMemoryAllocation ? GV2_ERR_NOMEM : GV2_ERR_CUDA, "boot_sparse_build_lists (%s): %s", what, cudaGetErrorString(e));
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&rowtot, (size_t)(L.nrows + 1) * sizeof(long long))) != cudaSuccess) return fail(e, "row totals");
+    if ((e = cudaMalloc((void**)&L.rowptr, (size_t)(L.nrows + 1) * sizeof(long long))) != cudaSuccess) return fail(e, "row pointers");
+    if ((e = cudaMalloc((void**)&L.pend, (size_t)L.nrows * 16 * sizeof(uint32_t))) != cudaSuccess) return fail(e, "pair ends");
+    if ((e = cudaMemsetAsync(rowtot + L.nrows, 0, sizeof(long long), ctx->stream)) != cudaSuccess) return fail(e, "memset");
+    const size_t smem = BS_LIST_SMEM(k_pad);
+    if ((e = cudaFuncSetAttribute(bs_lists_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return fail(e, "attr");
+    if ((e = cudaFuncSetAttribute(bs_lists_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return fail(e, "attr");
+    BsCsr csr{s->ptr, s->col, s->hi, s->lo};
+    dim3 grid(64, (unsigned)ntl);
+    bs_lists_build_kernel<false><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, (int)nt, (int)k_pad, rowtot, nullptr, L.pend, nullptr);
+    ctx->launches++;
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, rowtot, L.rowptr, (int)(L.nrows + 1), ctx->stream);
+    if ((e = cudaMalloc(&tmp, tb ? tb : 1)) != cudaSuccess) return fail(e, "scan scratch");
+    cub::DeviceScan::ExclusiveSum(tmp, tb, rowtot, L.rowptr, (int)(L.nrows + 1), ctx->stream);
+    ctx->launches++;
+    if ((e = cudaMemcpyAsync(&L.nent, L.rowptr + L.nrows, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return fail(e, "total");
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "count pass");
+    if ((double)L.nent * 8.0 > (double)budget) {        // cannot happen given the bound above; kept as a guard
+        cudaFree(rowtot); cudaFree(tmp); cudaFree(L.rowptr); cudaFree(L.pend);
+        return GV2_OK;
+    }
+    if ((e = cudaMalloc((void**)&L.ent, (size_t)std::max<long long>(1, L.nent) * sizeof(uint2))) != cudaSuccess) return fail(e, "entries");
+    bs_lists_build_kernel<true><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, (int)nt, (int)k_pad, nullptr, L.rowptr, L.pend, L.ent);
+    ctx->launches++;
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "fill pass");
+    cudaFree(rowtot); cudaFree(tmp);
+    L.bytes = (size_t)(L.nrows + 1) * 8 + (size_t)L.nrows * 64 + (size_t)std::max<long long>(1, L.nent) * 8;
+    s->lists = L;
+    s->bytes += L.bytes;
     return GV2_OK;
 }
 
@@ -481,6 +717,21 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     }
     Gv2Timer timer(ctx, GV2_TIME_PAIRSUMS);
     timer.begin();
+    const long long rep_stride_l = (long long)ntl * GV2_TILE * GV2_TILE;
+    if (s->lists.rowptr && tile_begin == 0 && ntl == (n_pad / GV2_TILE) * (n_pad / GV2_TILE + 1) / 2) {
+        const BsLists& L = s->lists;
+        dim3 gl(64, (unsigned)ntl, (unsigned)(w_ld / rl));
+        const int ntt = (int)(n_pad / GV2_TILE);
+        if (rl == 64)
+            boot_sparse_lists_kernel<64><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+        else if (rl == 128)
+            boot_sparse_lists_kernel<128><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+        else
+            boot_sparse_lists_kernel<256><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+        GV2_LAUNCH_CHECK(ctx);
+        timer.end();
+        return GV2_OK;
+    }
     BsCsr csr{s->ptr, s->col, s->hi, s->lo};
     const int nt = (int)(n_pad / GV2_TILE), nwin = (int)((k_pad + BS_WIN - 1) / BS_WIN);
     const int kwin = (int)std::min<int64_t>(k_pad, BS_WIN);            // k_pad is a multiple of 128
