@@ -375,10 +375,26 @@ bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowt
     }
 }
 
-// Streams the precomputed lists: lane = replicate, slot s takes i-rows s, s + PP, ... of the block.
-// grid = (64 sub-blocks, tiles, replicate blocks of RL)
+// Streams the precomputed lists.  Lane = FOUR replicates (one 4-byte load of the transposed multiplicities per entry
+// serves four multiply-adds: the kernel is bound by the number of global-memory instructions, `lg_throttle`), slot s
+// takes i-rows s, s + PP, ... of the block and walks the row's 16 lists in four groups of four pairs; 4 pairs x 4
+// replicates of accumulators per thread, results leave as whole 32-byte sectors.
+// grid = (64 sub-blocks, tiles, replicate blocks of 4 RL)
+#define BSL_MAC(A, E, W)                                                       \
+    do {                                                                       \
+        const uint32_t l16_ = (E).x >> 16;                                     \
+        hi[A][0] += (unsigned long long)(E).y * ((W) & 0xffu);                \
+        hi[A][1] += (unsigned long long)(E).y * (((W) >> 8) & 0xffu);         \
+        hi[A][2] += (unsigned long long)(E).y * (((W) >> 16) & 0xffu);        \
+        hi[A][3] += (unsigned long long)(E).y * ((W) >> 24);                  \
+        lo[A][0] += l16_ * ((W) & 0xffu);                                      \
+        lo[A][1] += l16_ * (((W) >> 8) & 0xffu);                               \
+        lo[A][2] += l16_ * (((W) >> 16) & 0xffu);                              \
+        lo[A][3] += l16_ * ((W) >> 24);                                        \
+    } while (0)
+
 template <int RL>
-__global__ void __launch_bounds__(BS_THREADS, 3)
+__global__ void __launch_bounds__(BS_THREADS, 2)
 boot_sparse_lists_kernel(const long long* __restrict__ rowptr, const uint32_t* __restrict__ pend, const uint2* __restrict__ ent,
                          int nt, const uint8_t* __restrict__ wT, long long w_ld, int nb_total, long long ws_rep_stride,
                          double quantum, double* __restrict__ ws) {
@@ -389,7 +405,7 @@ boot_sparse_lists_kernel(const long long* __restrict__ rowptr, const uint32_t* _
     bs_tile_coords(blockIdx.y, nt, &bi, &bj);
     if (bi == bj && si > sj) return;
     const int slot = tid / RL, rl = tid % RL;
-    const int rep0 = blockIdx.z * RL + rl;
+    const int rep0 = blockIdx.z * (4 * RL) + 4 * rl;                 // this lane's first replicate
     const long long row0 = ((long long)blockIdx.y * 64 + sub) * 16;
     double* wsblk = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + (size_t)(((si << 3) + sj) << 8);
     const double q_hi = quantum * 65536.0;
@@ -398,54 +414,56 @@ boot_sparse_lists_kernel(const long long* __restrict__ rowptr, const uint32_t* _
     for (int r = slot; r < 16; r += PP) {
         const uint2* list = ent + rowptr[row0 + r];
         const uint4* pe4 = reinterpret_cast<const uint4*>(pend + (row0 + r) * 16);
-        uint32_t pe[16];
+        uint32_t beg = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint4 v = __ldg(pe4 + q);
-            pe[4 * q] = v.x; pe[4 * q + 1] = v.y; pe[4 * q + 2] = v.z; pe[4 * q + 3] = v.w;
-        }
-        const uint32_t end = pe[15];
-        unsigned long long ahi[16];
-        uint32_t alo[16];
-        uint32_t wb[4];
-        if (end) {
-            const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(list)), p1 = __ldg(reinterpret_cast<const uint4*>(list + 2));
-            wb[0] = __ldg(wTl + (p0.x & 0xffffu) * wld32);
-            wb[1] = __ldg(wTl + (p0.z & 0xffffu) * wld32);
-            wb[2] = __ldg(wTl + (p1.x & 0xffffu) * wld32);
-            wb[3] = __ldg(wTl + (p1.z & 0xffffu) * wld32);
-        }
-        uint32_t e = 0;
+        for (int g = 0; g < 4; ++g) {
+            const uint4 pe = __ldg(pe4 + g);                         // ends of the group's four lists
+            const uint32_t end = pe.w;
+            unsigned long long hi[4][4];
+            uint32_t lo[4][4];
 #pragma unroll
-        for (int a = 0; a < 16; ++a) {
-            const uint32_t ne = pe[a];
-            unsigned long long h = 0ull;
-            uint32_t l = 0u;
-            for (; e < ne; e += 4) {                                   // lists are padded: a whole step belongs to one pair
-                const uint32_t w0 = wb[0], w1 = wb[1], w2 = wb[2], w3 = wb[3];
-                const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(list + e)), c1 = __ldg(reinterpret_cast<const uint4*>(list + e + 2));
-                if (e + 4 < end) {
-                    const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(list + e + 4)), n1 = __ldg(reinterpret_cast<const uint4*>(list + e + 6));
-                    wb[0] = __ldg(wTl + (n0.x & 0xffffu) * wld32);
-                    wb[1] = __ldg(wTl + (n0.z & 0xffffu) * wld32);
-                    wb[2] = __ldg(wTl + (n1.x & 0xffffu) * wld32);
-                    wb[3] = __ldg(wTl + (n1.z & 0xffffu) * wld32);
-                }
-                h += (unsigned long long)c0.y * w0;
-                h += (unsigned long long)c0.w * w1;
-                h += (unsigned long long)c1.y * w2;
-                h += (unsigned long long)c1.w * w3;
-                l += (c0.x >> 16) * w0 + (c0.z >> 16) * w1 + (c1.x >> 16) * w2 + (c1.z >> 16) * w3;
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { hi[a][k] = 0ull; lo[a][k] = 0u; }
+            uint32_t w4[4];
+            uint32_t e = beg;
+            if (e < end) {
+                const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(list + e)), p1 = __ldg(reinterpret_cast<const uint4*>(list + e + 2));
+                w4[0] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (p0.x & 0xffffu) * wld32));
+                w4[1] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (p0.z & 0xffffu) * wld32));
+                w4[2] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (p1.x & 0xffffu) * wld32));
+                w4[3] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (p1.z & 0xffffu) * wld32));
             }
-            ahi[a] = h;
-            alo[a] = l;
-        }
-        if (rep0 < nb_total) {
-            double* o = wsblk + (size_t)rep0 * ws_rep_stride + (r << 4);
 #pragma unroll
-            for (int a = 0; a < 16; a += 2)
-                *reinterpret_cast<double2*>(o + a) = make_double2((double)ahi[a] * q_hi + (double)alo[a] * quantum,
-                                                                  (double)ahi[a + 1] * q_hi + (double)alo[a + 1] * quantum);
+            for (int a = 0; a < 4; ++a) {
+                const uint32_t ne = a == 0 ? pe.x : a == 1 ? pe.y : a == 2 ? pe.z : pe.w;
+                for (; e < ne; e += 4) {                               // lists are padded: a whole step belongs to one pair
+                    const uint32_t w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
+                    const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(list + e)), c1 = __ldg(reinterpret_cast<const uint4*>(list + e + 2));
+                    if (e + 4 < end) {
+                        const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(list + e + 4)), n1 = __ldg(reinterpret_cast<const uint4*>(list + e + 6));
+                        w4[0] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (n0.x & 0xffffu) * wld32));
+                        w4[1] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (n0.z & 0xffffu) * wld32));
+                        w4[2] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (n1.x & 0xffffu) * wld32));
+                        w4[3] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (n1.z & 0xffffu) * wld32));
+                    }
+                    const uint2 e0 = make_uint2(c0.x, c0.y), e1 = make_uint2(c0.z, c0.w), e2 = make_uint2(c1.x, c1.y), e3 = make_uint2(c1.z, c1.w);
+                    BSL_MAC(a, e0, w0);
+                    BSL_MAC(a, e1, w1);
+                    BSL_MAC(a, e2, w2);
+                    BSL_MAC(a, e3, w3);
+                }
+            }
+            beg = end;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (rep0 + k >= nb_total) break;
+                double* o = wsblk + (size_t)(rep0 + k) * ws_rep_stride + (r << 4) + 4 * g;
+                *reinterpret_cast<double2*>(o) = make_double2((double)hi[0][k] * q_hi + (double)lo[0][k] * quantum,
+                                                              (double)hi[1][k] * q_hi + (double)lo[1][k] * quantum);
+                *reinterpret_cast<double2*>(o + 2) = make_double2((double)hi[2][k] * q_hi + (double)lo[2][k] * quantum,
+                                                                  (double)hi[3][k] * q_hi + (double)lo[3][k] * quantum);
+            }
         }
     }
 }
@@ -688,7 +706,13 @@ static int64_t bs_wld(int64_t nb) {
     const int64_t per = bs_lanes(nb);
     return (nb + per - 1) / per * per;
 }
-size_t boot_sparse_scratch_bytes(int64_t k_pad, int64_t nb) { return (size_t)k_pad * bs_wld(nb); }
+// the streaming (precomputed lists) kernel: four replicates per lane
+static int bsl_lanes(int64_t nb) { return nb <= 256 ? 64 : nb <= 512 ? 128 : 256; }
+static int64_t bsl_wld(int64_t nb) {
+    const int64_t per = 4 * bsl_lanes(nb);
+    return (nb + per - 1) / per * per;
+}
+size_t boot_sparse_scratch_bytes(int64_t k_pad, int64_t nb) { return (size_t)k_pad * std::max(bs_wld(nb), bsl_wld(nb)); }
 
 // ws: fp64 [nb][ntl][128*128] (gj_ws_index layout), tiles [tile_begin, tile_end); w: int32 [nb][k] (device).
 // *overflow_flag is set to 1 when a multiplicity exceeds 255 and to 2 when a replicate's multiplicities sum to
@@ -699,8 +723,9 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     const int64_t ntl = tile_end - tile_begin;
     if (ntl <= 0 || nb <= 0) return GV2_OK;
     if (ntl > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "boot_sparse_launch: more than 65535 genome tiles per launch");
-    const int rl = bs_lanes(nb);
-    const int64_t w_ld = bs_wld(nb);
+    const bool use_lists = s->lists.rowptr && tile_begin == 0 && ntl == (n_pad / GV2_TILE) * (n_pad / GV2_TILE + 1) / 2;
+    const int rl = use_lists ? bsl_lanes(nb) : bs_lanes(nb);
+    const int64_t w_ld = use_lists ? bsl_wld(nb) : bs_wld(nb);
     uint8_t* wT = (uint8_t*)wT_scratch;
     dim3 gt((unsigned)((k_pad + 31) / 32), (unsigned)((w_ld + 31) / 32)), bt(32, 8);
     bs_weights_transpose_kernel<<<gt, bt, 0, ctx->stream>>>(w, nb, k, k_pad, w_ld, wT, overflow_flag);
@@ -718,9 +743,9 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     Gv2Timer timer(ctx, GV2_TIME_PAIRSUMS);
     timer.begin();
     const long long rep_stride_l = (long long)ntl * GV2_TILE * GV2_TILE;
-    if (s->lists.rowptr && tile_begin == 0 && ntl == (n_pad / GV2_TILE) * (n_pad / GV2_TILE + 1) / 2) {
+    if (use_lists) {
         const BsLists& L = s->lists;
-        dim3 gl(64, (unsigned)ntl, (unsigned)(w_ld / rl));
+        dim3 gl(64, (unsigned)ntl, (unsigned)(w_ld / (4 * rl)));
         const int ntt = (int)(n_pad / GV2_TILE);
         if (rl == 64)
             boot_sparse_lists_kernel<64><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);

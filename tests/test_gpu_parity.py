@@ -368,7 +368,16 @@ def test_replicate_paths_agree(eng, monkeypatch, n, p, dens, nb):
     for path in ("sparse", "mma", "fp32"):
         monkeypatch.setenv("GV2_BOOT_PATH", path)
         out[path] = eng.bootstrap(t.sig, None, None, 0, w, "P", 1.0, distance=False)
+    # the sparse path with its pair lists matched on the fly inside the kernel instead of precomputed: the same integers
+    monkeypatch.setenv("GV2_BOOT_PATH", "sparse")
+    monkeypatch.setenv("GV2_SPARSE_LISTS", "0")
+    on_the_fly = eng.bootstrap(t.sig, None, None, 0, w, "P", 1.0, distance=False)
+    monkeypatch.delenv("GV2_SPARSE_LISTS")
     monkeypatch.delenv("GV2_BOOT_PATH")
+    if p <= 32768 and dens <= 0.1:
+        assert np.array_equal(on_the_fly, out["sparse"])
+    else:               # row slices / column windows of the on-the-fly kernel meet in fp64
+        assert np.allclose(on_the_fly, out["sparse"], rtol=1e-14, atol=0)
     for b in sorted({0, nb // 2, nb - 1}):
         ref = O.similarity_mat_fast(t.sig, None, None, 0, "P", 1.0, w=w[b])
         close(out["sparse"][b], ref, rtol=1e-12)                         # 48-bit fixed point, exact integer sums
