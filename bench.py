@@ -399,7 +399,7 @@ def make_roofline(times, path, cells, steps, n, p, g, nrep, region_ms, peaks, pe
                          "frac": bytes_step / sec / 1e9 / hbm,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch (10 replicates at cfg3), ncu --set full,
                          # profiles/r01_top_kernels_ncu_full.csv; algorithmic bytes of the same launch: 1.21e10
-                         "traffic": 1.2472e10 if (n, g, round(nrep / max(cnt / steps, 1))) == (10000, 200, 10) else None,
+                         "traffic": 1.2491e10 if (n, g, round(nrep / max(cnt / steps, 1))) == (10000, 200, 10) else None,
                          "pipe": {"bound": "fp32/alu issue (2 slots per cell: FMNMX + FADD)", "achieved": slots / sec, "peak": fp32_issue,
                                   "unit": "thread-instr/s", "frac": slots / sec / fp32_issue},
                          "launches_per_step": cnt / steps, "avg_launch_ms": ms / cnt, "share_of_step": ms / region_ms,
