@@ -552,6 +552,28 @@ def test_bootstrap_newick_equals_matrices_then_scipy(eng):
         assert tree.count(",") == len(names) - 1 and tree.endswith(");")
 
 
+@pytest.mark.parametrize("n,method", [(1, "average"), (2, "average"), (5, "ward"), (70, "single")])
+def test_bootstrap_newick_small_and_pl2(eng, n, method):
+    """Tree path edge cases: one and two genomes, PL2 (sorted indices, real location table, GOMDB from the reference rows
+    only), the other linkage methods -- always against the matrix path of the same engine + the reference's tree code."""
+    import gravity2_b200 as G
+    t = synth.make_tables(n, 120, min(3, n), 0.3, seed=n)
+    n_ref = max(1, n - 2)
+    payload = {"N_Bootstrap": 3, "SimilarityMeasurementScheme": "PG", "p": 1.0, "Dendrogram_LinkageMethod": method,
+               "PphmmNeighbourhoodWeight": 0.0, "PphmmSigScoreThreshold": 0}
+    names = [f"g{i}" for i in range(n)]
+    np.random.seed(5)
+    mats = [m.copy() for m in G.bootstrap_distance_matrices(t.sig, t.loc, t.taxo[:n_ref], t.gom_ids, payload, pipeline="pl2")]
+    np.random.seed(5)
+    trees = list(G.bootstrap_newick(t.sig, t.loc, t.taxo[:n_ref], t.gom_ids, payload, names, pipeline="pl2"))
+    assert len(trees) == 3
+    for D, tree in zip(mats, trees):
+        if n == 1:
+            assert tree == "g0:0.000000"            # scipy refuses an empty distance list; the single leaf is printed
+        else:
+            assert tree == O.dist_mat_to_tree(D, names, method, False)
+
+
 def test_error_paths(eng):
     import gravity2_b200 as G
     with pytest.raises(ValueError):
