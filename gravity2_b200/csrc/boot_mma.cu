@@ -494,11 +494,10 @@ int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n
     CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, wb, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return gv2_fail(ctx, GV2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!(ctx->smem_attr_done & GV2_ATTR_MMA)) {
         GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
         GV2_CUDA(ctx, cudaFuncSetAttribute(boot_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
-        attr_done = true;
+        ctx->smem_attr_done |= GV2_ATTR_MMA;
     }
     if (ntl > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "boot_mma_launch: more than 65535 genome tiles per launch");
     dim3 grid(128, (unsigned)ntl, (unsigned)nblocks);

@@ -665,7 +665,11 @@ int boot_sparse_build_lists(gv2_ctx* ctx, BootSparse* s, size_t budget) {
     void* tmp = nullptr;
     auto fail = [&](cudaError_t e, const char* what) {
         cudaFree(rowtot); cudaFree(tmp); cudaFree(L.rowptr); cudaFree(L.pend); cudaFree(L.ent);
-        return gv2_fail(ctx, e == cudaErrorMemoryAllocation ? GV2_ERR_NOMEM : GV2_ERR_CUDA, "boot_sparse_build_lists (%s): %s", what, cudaGetErrorString(e));
+        if (e == cudaErrorMemoryAllocation) {       // the lists are an optimisation: without them every launch matches on the fly
+            cudaGetLastError();
+            return GV2_OK;
+        }
+        return gv2_fail(ctx, GV2_ERR_CUDA, "boot_sparse_build_lists (%s): %s", what, cudaGetErrorString(e));
     };
     cudaError_t e;
     if ((e = cudaMalloc((void**)&rowtot, (size_t)(L.nrows + 1) * sizeof(long long))) != cudaSuccess) return fail(e, "row totals");
@@ -732,13 +736,12 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     GV2_LAUNCH_CHECK(ctx);
     bs_wsum_check_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(w, k, overflow_flag);
     GV2_LAUNCH_CHECK(ctx);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!(ctx->smem_attr_done & GV2_ATTR_SPARSE)) {
         const int mx = (int)bs_smem_bytes(BS_WIN);
         GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
         GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-        attr_done = true;
+        ctx->smem_attr_done |= GV2_ATTR_SPARSE;
     }
     Gv2Timer timer(ctx, GV2_TIME_PAIRSUMS);
     timer.begin();

@@ -17,6 +17,9 @@ struct gv2_ctx {
     bool own_stream = false;
     std::string err;
     unsigned long long launches = 0;   // kernels launched through this context (bench: gpu_launches)
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember per context what has been raised
+    unsigned smem_attr_done = 0;       // bit per launcher (GV2_ATTR_*)
+    size_t lk_smem_attr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // optional CUDA-event timing of the hot kernels by group (gv2_timing_enable / gv2_timing_read_kind)
     bool timing = false;
     struct Timed { cudaEvent_t a, b; int kind; };
@@ -43,6 +46,12 @@ struct Gv2Timer {
         a = b = nullptr;
     }
 };
+
+#define GV2_ATTR_GJ 1u
+#define GV2_ATTR_FUSED 2u
+#define GV2_ATTR_MMA 4u
+#define GV2_ATTR_SPARSE 8u
+#define GV2_ATTR_POPC 16u
 
 #define GV2_TILE 128          // genome-pair tile edge of the similarity kernels
 #define GV2_BK 32             // PPHMM columns staged per pipeline stage

@@ -681,12 +681,11 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
     if (ntl == 0) return GV2_OK;
     if (tile_end > gv2_num_tiles(n_pad)) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_gj_min_sums: tile range");
     if (nb > 65535 || ksplit > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_gj_min_sums: nb/ksplit > 65535");
-    static bool attr_done = false;
     size_t smem = gj_smem_bytes();
-    if (!attr_done) {
+    if (!(ctx->smem_attr_done & GV2_ATTR_GJ)) {
         GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GV2_CUDA(ctx, cudaFuncSetAttribute(gj_min_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        ctx->smem_attr_done |= GV2_ATTR_GJ;
     }
     dim3 grid((unsigned)ntl, (unsigned)ksplit, (unsigned)nb);
     const int nt = (int)(n_pad / GV2_TILE);
@@ -712,12 +711,11 @@ int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t 
     const int64_t ntl = gv2_num_tiles(n);
     if (ntl == 0 || nb <= 0) return GV2_OK;
     if (nb > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: nb > 65535");
-    static bool attr_done = false;
     const size_t smem = gf_smem_bytes();
     static_assert(GF_STAGES * GF_STAGE_FLOATS * sizeof(float) >= 64 * GJ_STAGE_LD * sizeof(double), "transpose stage must fit the ring");
-    if (!attr_done) {
+    if (!(ctx->smem_attr_done & GV2_ATTR_FUSED)) {
         GV2_CUDA(ctx, cudaFuncSetAttribute(gj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        ctx->smem_attr_done |= GV2_ATTR_FUSED;
     }
     GjFuse fz{};
     if (scheme == GV2_SCHEME_PG) fz.P = to_comp(comp_p);

@@ -341,7 +341,7 @@ int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t
     const size_t smem = lk_smem_bytes(n, method);
     if (smem > 200 * 1024)
         return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage keeps its per-cluster state in shared memory: n = %lld needs %zu bytes", (long long)n, smem);
-    static size_t attr[LK_SINGLE + 1] = {0, 0, 0, 0, 0};
+    size_t* attr = ctx->lk_smem_attr;
     if (smem > attr[method]) {
         const int sz = (int)std::max<size_t>(smem, 1024);
         cudaError_t e = cudaSuccess;

@@ -140,11 +140,10 @@ extern "C" int gv2_dev_shared_counts(gv2_ctx* ctx, const uint64_t* bits, int64_t
         return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_shared_counts: bad arguments");
     const int64_t ntl = tile_end - tile_begin;
     if (ntl == 0) return GV2_OK;
-    static bool attr_done = false;
     const size_t smem = (size_t)2 * PC_STAGES * GV2_TILE * PC_LDS * sizeof(unsigned);
-    if (!attr_done) {
+    if (!(ctx->smem_attr_done & GV2_ATTR_POPC)) {
         GV2_CUDA(ctx, cudaFuncSetAttribute(shared_count_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        ctx->smem_attr_done |= GV2_ATTR_POPC;
     }
     shared_count_tile_kernel<<<(unsigned)ntl, PC_THREADS, smem, ctx->stream>>>(
         (const unsigned*)bits, (int)(2 * words), (int)(2 * words / PC_BK), (int)(n_pad / GV2_TILE), tile_begin, n, inter);
