@@ -162,38 +162,61 @@ __global__ void gom_gather_weights_kernel(const int* __restrict__ pt_col, long l
     wG[i] = wT[(long long)pt_col[i / NBC] * NBC + (i % NBC)];
 }
 
-// GA: arT[pt][b] = sum_l w_l A[k][l],  sqT[pt][b] = sum_l w_l A[k][l]^2  (a batched GEMV per GOM).
-// grid = (ceil(max_ng/32), G), block = (32 b, 8): each thread owns 4 rows k for its replicate lane, so one
-// coalesced weight load feeds 8 fp64 FMAs.
+// GA: arT[pt][b] = sum_l w_l A[k][l],  sqT[pt][b] = sum_l w_l A[k][l]^2  (per GOM a [ng x ng] x [ng x 32] product).
+// grid = (ceil(max_ng/64), G), block = (32 b, 8): the block owns 64 rows k, a thread 8 of them for its replicate lane.
+// 32 columns l at a time go through shared memory (A tile 64 x 32 read as whole 256-byte row segments, weight tile
+// 32 x 32), so the inner loop is one conflict-free LDS of the weight and eight broadcast LDS of the distances per
+// 16 FMAs instead of global loads; the sums run over l in ascending order exactly as before.
+#define GA_ROWS 64
+#define GA_LC 32
 __global__ void __launch_bounds__(256)
 gom_rowsums_kernel(const int* __restrict__ pt_ptr, const long long* __restrict__ a_off,
                    const double* __restrict__ A, const double* __restrict__ wG,
                    double* __restrict__ arT, double* __restrict__ sqT) {
+    __shared__ double sA[GA_ROWS][GA_LC + 1];
+    __shared__ double sW[GA_LC][NBC];
     const int g = blockIdx.y;
     const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
-    const int k0 = blockIdx.x * 32 + threadIdx.y * 4;
-    if (k0 >= ng) return;
-    const int b = threadIdx.x;
+    const int kb = blockIdx.x * GA_ROWS;
+    if (kb >= ng) return;
+    const int b = threadIdx.x, ty = threadIdx.y;
     const double* a = A + a_off[g];
-    const double* w = wG + (long long)p0 * NBC + b;
-    const int kk[4] = {k0, min(k0 + 1, ng - 1), min(k0 + 2, ng - 1), min(k0 + 3, ng - 1)};
-    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-#pragma unroll 4
-    for (int l = 0; l < ng; ++l) {
-        const double wv = w[(long long)l * NBC];
+    const double* w = wG + (long long)p0 * NBC;
+    double s1[8], s2[8];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const double d = a[(long long)kk[r] * ng + l];
-            s1[r] = fma(wv, d, s1[r]);
-            s2[r] = fma(wv * d, d, s2[r]);
+    for (int r = 0; r < 8; ++r) { s1[r] = 0.0; s2[r] = 0.0; }
+    for (int l0 = 0; l0 < ng; l0 += GA_LC) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int row = ty * 8 + r, k = min(kb + row, ng - 1), l = l0 + b;
+            sA[row][b] = l < ng ? a[(long long)k * ng + l] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < GA_LC / 8; ++q) {
+            const int l = ty + 8 * q;
+            sW[l][b] = l0 + l < ng ? w[(long long)(l0 + l) * NBC + b] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int l = 0; l < GA_LC; ++l) {
+            const double wv = sW[l][b];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double d = sA[ty * 8 + r][l];
+                s1[r] = fma(wv, d, s1[r]);
+                s2[r] = fma(wv * d, d, s2[r]);
+            }
         }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-        if (k0 + r < ng) {
-            arT[(long long)(p0 + k0 + r) * NBC + b] = s1[r];
-            sqT[(long long)(p0 + k0 + r) * NBC + b] = s2[r];
+    for (int r = 0; r < 8; ++r) {
+        const int k = kb + ty * 8 + r;
+        if (k < ng) {
+            arT[(long long)(p0 + k) * NBC + b] = s1[r];
+            sqT[(long long)(p0 + k) * NBC + b] = s2[r];
         }
+    }
 }
 
 // GB: per-GOM aggregates, lane = replicate.  gagg[g][q][b], q in 0..GAGG-1.  grid = G, block = 32
@@ -778,7 +801,7 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
         if (db->max_ng) {
             gom_gather_weights_kernel<<<(unsigned)(((long long)db->npt * NBC + 255) / 256), 256, 0, st>>>(db->pt_col, db->npt, db->wT, db->wG);
             ctx->launches++;
-            dim3 g1((unsigned)((db->max_ng + 31) / 32), (unsigned)G), b1(32, 8);
+            dim3 g1((unsigned)((db->max_ng + GA_ROWS - 1) / GA_ROWS), (unsigned)G), b1(32, 8);
             gom_rowsums_kernel<<<g1, b1, 0, st>>>(db->pt_ptr, db->a_off, db->A, db->wG, db->arT, db->sqT);
             ctx->launches++;
         }
