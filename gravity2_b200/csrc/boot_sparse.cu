@@ -16,19 +16,25 @@
 // checks sum_c w_c <= 2^(32-16)), so the sums do not depend on the order the lists are built in.  The
 // only error is the input quantisation max(T) * 2^-49 per element (~1e-15 relative on S).
 //
-//   CTA  = one 16 x 16 block of a 128 x 128 genome-pair tile x up to 1024 replicates.
+// Two kernels share the match logic (a 16 x 16 block of a 128 x 128 genome-pair tile per CTA):
 //   build  : the 16 j-rows are scattered into a shared-memory table mask[c] = bit set of the j-rows
 //            that hit column c (uint16 per column, 60 KB for 30 000 columns); their column lists are
 //            copied to shared memory;
 //   match  : the entries of all 16 i-rows, one per thread: mask[c] names the j-rows sharing the
-//            column (usually none).  Hits are counted per pair, the 256 pair lists are laid out back
-//            to back in a pool by a block scan, and a second pass writes (column, min value), the j
-//            value found by binary search in the shared-memory copy of the row.  If the pool would
-//            overflow, the batch of i-rows is halved (down to a slice of one row);
-//   reduce : the threads become replicate lanes (one replicate each): for every list entry one byte of the
-//            transposed multiplicities wT[c][replicate], one IMAD.WIDE and one IMAD; the 16 pairs of an
-//            i-row accumulate in registers and leave as one whole 128-byte line of the workspace (the
-//            replicates' workspaces are 0.4 GB apart: partial lines would be evicted half written).
+//            column (usually none).  Hits are counted per pair, the pair lists are laid out back to
+//            back (each padded to 4 entries), and a second pass writes (column, min value), the j value
+//            found by binary search in the shared-memory copy of the row;
+//   reduce : the threads become replicate lanes: per list entry a load of the transposed multiplicities
+//            wT[c][replicates], IMAD.WIDE (high limb) and IMAD (low limb) into integer accumulators.
+// * bs_lists_build_kernel + boot_sparse_lists_kernel (the default): the match does not depend on the
+//   replicate, so it runs ONCE per job into global memory (2.4 GB of lists at the 10k x 30k config); the
+//   per-launch kernel only streams the lists: no shared memory, no barriers, four replicates per lane
+//   (one 4-byte multiplicity load serves four multiply-adds), 4 pairs x 4 replicates of accumulators per
+//   thread, results leave as whole 32-byte sectors.
+// * boot_sparse_kernel (lists too large for a tenth of the memory, or more than 65 536 columns): match
+//   on the fly inside every launch, pool of 2048 entries in shared memory (a batch of i-rows that would
+//   overflow it is halved, down to a slice of one row), column windows of 32 768, one replicate per lane,
+//   the 16 pairs of an i-row leave as one whole 128-byte line.
 // The row sums sum_c w_c x_ic are the diagonal pairs, exactly as in the tensor-core path.
 #include "common.cuh"
 
