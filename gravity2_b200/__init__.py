@@ -6,7 +6,7 @@ from .dropin import (  # noqa: F401
     SimilarityMat_Constructor, dist_mat_constructor, GOMDB_Constructor, GOMSignatureTable_Constructor,
     generate_gom_sigs, dcor, shared_pphmm_ratio, shared_norm_pphmm_ratio, shared_norm_pphmm_ratio_from_array,
     shared_pphmm_counts, binary_jaccard, bootstrap_distance_matrices, draw_resample_indices,
-    weights_from_indices, gom_membership, DistMat2Tree, bootstrap_newick,
+    weights_from_indices, gom_membership, DistMat2Tree, bootstrap_newick, sort_pphmm_distances, sort_pphmm_tree,
 )
 from .engine import Engine, default_engine  # noqa: F401
 

@@ -17,7 +17,7 @@ SCHEMES = {"P": 0, "G": 1, "PG": 2, "R": 3, "RG": 4, "PR": 5, "L": 6, "PL": 7}
 OUT_SIMILARITY, OUT_DISTANCE = 0, 1
 TILE = 128
 GOM_ALL_COLUMNS = 1
-TIME_PAIRSUMS, TIME_TAIL, TIME_GOM, TIME_LINKAGE = 0, 1, 2, 3
+TIME_PAIRSUMS, TIME_TAIL, TIME_GOM, TIME_LINKAGE, TIME_BASE = 0, 1, 2, 3, 4
 PATH_NAMES = {0: "none", 1: "fp32", 2: "mma", 3: "sparse"}
 
 c_i64 = C.c_int64
@@ -77,6 +77,10 @@ PROTOTYPES = {
     "gv2_mem_info": (C.c_int, [c_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "gv2_job_gom_table": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "gv2_job_device_bytes": (C.c_size_t, [c_vp]),
+    "gv2_job_gom_stats": (C.c_int, [c_vp, C.POINTER(c_i64)]),
+    "gv2_dev_shared_counts_packed": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
+    "gv2_dev_unpack_tiles_i32": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "gv2_dev_popc_peak": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_double)]),
     "gv2_num_tiles": (c_i64, [c_i64]),
     "gv2_dev_prepare_table": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_int, c_vp, c_i64, c_i64,
                                         c_vp, c_vp]),

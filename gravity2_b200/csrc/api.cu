@@ -244,6 +244,8 @@ struct gv2_job {
     const double* d_sig = nullptr;
     const double* d_loc = nullptr;
     DevBuf sigf, sig_rowsum, sig_nan;
+    DevBuf nan_cells, rep_nan;         // (row, column) of every NaN entry of the signature table; per-replicate row flags
+    int64_t n_nan_cells = 0;
     DevBuf sigfix;                     // 32-bit fixed-point signature table for the tensor-core path
     double quantum = 0.0;
     bool mma_ok = false;
@@ -301,6 +303,77 @@ extern "C" int gv2_job_replicate_path(const gv2_job* job) {
 }
 extern "C" uint64_t gv2_job_copresent_cells(const gv2_job* job) { return job ? boot_sparse_cells(job->sparse) : 0; }
 
+
+// ---- multiplicity validation, done ONCE per call before anything is computed or delivered: the uint8 operands of the
+// replicate kernels hold 0..255 (flag 1), the 32-bit low-limb sums of the sparse path need sum_c w_c <= 65536 (flag 2).
+__global__ void weights_validate_kernel(const int* __restrict__ w, long long k, int* __restrict__ flag) {
+    const int* row = w + (long long)blockIdx.x * k;
+    long long s = 0;
+    int bad = 0;
+    for (long long c = threadIdx.x; c < k; c += blockDim.x) {
+        const int v = row[c];
+        bad |= (v < 0 || v > 255);
+        s += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    __shared__ long long red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    if (bad) atomicOr(flag, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        if (t > 65536) atomicOr(flag, 2);
+    }
+}
+
+// ---- NaN entries of the signature table.  In the reference a NaN at (i, c) turns row i of a replicate's matrix into
+// zeros only when column c was drawn (np.minimum propagates it through the resampled row, :167-168, cleaned at :204);
+// the fixed-point / fp32 images hold 0 there, and a per-replicate row flag carries the NaN.
+__global__ void nan_cells_kernel(const double* __restrict__ src, long long n, long long k, long long ld, int2* __restrict__ out,
+                                 int cap, int* __restrict__ count) {
+    const long long r = blockIdx.x;
+    for (long long c = threadIdx.x; c < k; c += blockDim.x)
+        if (isnan(src[r * ld + c])) {
+            const int at = atomicAdd(count, 1);
+            if (at < cap) out[at] = make_int2((int)r, (int)c);
+        }
+}
+__global__ void rep_nan_kernel(const int2* __restrict__ cells, int ncells, const int* __restrict__ w, long long k, long long n,
+                               long long nb, unsigned char* __restrict__ flags) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)ncells * nb) return;
+    const long long b = i / ncells;
+    const int2 cell = cells[i % ncells];
+    if (w[b * k + cell.y] > 0) flags[b * n + cell.x] = 1;
+}
+
+static int job_collect_nan_cells(gv2_job* j) {
+    gv2_ctx* ctx = j->ctx;
+    j->n_nan_cells = 0;
+    if (j->n == 0 || j->p == 0) return GV2_OK;
+    std::vector<uint8_t> rowflag((size_t)j->n);
+    GV2_CUDA(ctx, cudaMemcpyAsync(rowflag.data(), j->sig_nan.p, (size_t)j->n, cudaMemcpyDeviceToHost, ctx->stream));
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!std::any_of(rowflag.begin(), rowflag.end(), [](uint8_t f) { return f != 0; })) return GV2_OK;
+    DevBuf cnt;
+    ALLOC(ctx, cnt, sizeof(int));
+    int have = 0, cap = 0;
+    for (int pass = 0; pass < 2; ++pass) {          // count, then fill
+        GV2_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, sizeof(int), ctx->stream));
+        nan_cells_kernel<<<(unsigned)j->n, 256, 0, ctx->stream>>>(j->d_sig, j->n, j->p, j->p, j->nan_cells.as<int2>(), cap, cnt.as<int>());
+        GV2_LAUNCH_CHECK(ctx);
+        GV2_CUDA(ctx, cudaMemcpyAsync(&have, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pass == 0) { cap = have; ALLOC(ctx, j->nan_cells, (size_t)std::max(1, cap) * sizeof(int2)); }
+    }
+    j->n_nan_cells = have;
+    return GV2_OK;
+}
+
 extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc, int tables_are_device,
                               int64_t n, int64_t p, const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g,
                               int scheme, double power, int out_kind, gv2_job** out) {
@@ -326,8 +399,11 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
         if ((rc = ensure(ctx, j->sigf, (size_t)j->n_pad * j->p_pad * sizeof(float)))) return bail(rc);
         if ((rc = ensure(ctx, j->sig_rowsum, (size_t)n * sizeof(double)))) return bail(rc);
         if ((rc = ensure(ctx, j->sig_nan, (size_t)n))) return bail(rc);
-        if ((rc = gv2_dev_prepare_table(ctx, j->d_sig, n, p, p, 0.0, 0, j->sigf.as<float>(), j->n_pad, j->p_pad,
+        // `row[row < thr] = 0` runs on every call of the reference, thr == 0 included (similarity_matrix_constructor.py:139-140):
+        // negative scores count as absent in the Jaccard sums.  The location side (d_loc) stays as it is.
+        if ((rc = gv2_dev_prepare_table(ctx, j->d_sig, n, p, p, 0.0, 1, j->sigf.as<float>(), j->n_pad, j->p_pad,
                                         j->sig_rowsum.as<double>(), j->sig_nan.as<uint8_t>()))) return bail(rc);
+        if ((rc = job_collect_nan_cells(j))) return bail(rc);
         {
             // Replicate path.  Two exact integer paths on a fixed-point image of the table (both need a non-negative
             // table): the CSR walk (work ~ co-present columns; real tables are ~99 % zeros) and the dense tensor-core
@@ -335,7 +411,8 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
             double mx = 0.0;
             int neg = 0;
             if ((rc = boot_table_stats(ctx, j->d_sig, n, p, p, &mx, &neg))) return bail(rc);
-            const bool usable = !neg && isfinite(mx);
+            (void)neg;                                   // negative entries are zeroed by the threshold: x <= 0 -> 0 in both images
+            const bool usable = isfinite(mx);
             const char* path = getenv("GV2_BOOT_PATH");
             const bool want_fp32 = path && !strcmp(path, "fp32");
             const bool can_mma = boot_mma_available() != 0;
@@ -387,6 +464,7 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
         for (int64_t r = 0; r < n_gom_rows; ++r)
             if (gom_of_row[r] >= 0) mem_row[fill[gom_of_row[r]]++] = r;
         if ((rc = gom_db_build(ctx, j->d_loc, n, p, p, j->d_loc, p, mem_row.data(), mem_ptr.data(), g, 0, &j->gom))) return bail(rc);
+        j->gom->weights_validated = true;          // replicates_impl / gv2_job_gom_table check the multiplicities before launching
     }
     GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *out = j;
@@ -412,15 +490,46 @@ extern "C" int gv2_job_gom_table(gv2_job* job, const int32_t* dev_weights, int64
     if (!job || !dev_out || nb <= 0) return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_gom_table: bad arguments");
     if (!job->gom) return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_gom_table: job has no GOM database");
     if (!dev_weights && nb != 1) return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_gom_table: nb must be 1 without weights");
-    GV2_CUDA(job->ctx, cudaSetDevice(job->ctx->device));
-    return gom_db_score(job->ctx, job->gom, dev_weights, nb, dev_out);
+    gv2_ctx* ctx = job->ctx;
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (dev_weights) {
+        if (!job->mma_flag.p) ALLOC(ctx, job->mma_flag, sizeof(int));
+        int flag = 0;
+        GV2_CUDA(ctx, cudaMemsetAsync(job->mma_flag.p, 0, sizeof(int), ctx->stream));
+        weights_validate_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(dev_weights, job->p, job->mma_flag.as<int>());
+        GV2_LAUNCH_CHECK(ctx);
+        GV2_CUDA(ctx, cudaMemcpyAsync(&flag, job->mma_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (flag & 1) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a column multiplicity is outside 0..255 (uint8 weights of the GOM kernels)");
+    }
+    return gom_db_score(ctx, job->gom, dev_weights, nb, dev_out);
 }
+
+extern "C" int gv2_job_gom_stats(const gv2_job* job, int64_t* stats) {
+    if (!job || !stats) return GV2_ERR_ARG;
+    for (int i = 0; i < 8; ++i) stats[i] = 0;
+    if (const GomDb* db = job->gom) {
+        stats[0] = db->npt; stats[1] = db->sum_ng2; stats[2] = db->nnz; stats[3] = db->n_heavy;
+        stats[4] = db->n_isect; stats[5] = db->n_mentries; stats[6] = db->max_ng; stats[7] = db->max_t;
+    }
+    return GV2_OK;
+}
+
+static int job_base_impl(gv2_job* job, int64_t tile_begin, int64_t tile_end, int packed, double* dev_out);
 
 extern "C" int gv2_job_base(gv2_job* job, int64_t tile_begin, int64_t tile_end, int packed, double* dev_out) {
     if (!job || !dev_out || tile_begin < 0 || tile_end < tile_begin || tile_end > job->ntiles)
         return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_base: bad arguments");
+    GV2_CUDA(job->ctx, cudaSetDevice(job->ctx->device));
+    Gv2Timer timer(job->ctx, GV2_TIME_BASE);
+    timer.begin();
+    const int rc = job_base_impl(job, tile_begin, tile_end, packed, dev_out);
+    timer.end();
+    return rc;
+}
+
+static int job_base_impl(gv2_job* job, int64_t tile_begin, int64_t tile_end, int packed, double* dev_out) {
     gv2_ctx* ctx = job->ctx;
-    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t ntl = tile_end - tile_begin;
     if (ntl == 0) return GV2_OK;
     const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
@@ -531,11 +640,25 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                            double* host_out, gv2_replicate_cb cb_fn, void* cb_user, TreeSink* sink) {
     if (!job || !dev_weights || !dev_ring || nb < 0 || ring_len <= 0 || (cb_fn && !host_out))
         return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_stream: bad arguments");
-    if (cb_fn && ring_len < 2 && nb > 1)
-        return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_replicates_stream: callback mode needs ring_len >= 2");
+    // host delivery ping-pongs two halves of the ring (one computing, one draining): a single slot cannot do that
+    if (host_out && ring_len < 2 && nb > 1)
+        return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_replicates_stream: host delivery of more than one replicate needs ring_len >= 2");
     gv2_ctx* ctx = job->ctx;
     GV2_CUDA(ctx, cudaSetDevice(ctx->device));
     if (nb == 0 || job->n == 0) return GV2_OK;
+    {   // multiplicities are checked before the first launch, so nothing wrong is ever delivered; the flag starts clean per call
+        if (!job->mma_flag.p) ALLOC(ctx, job->mma_flag, sizeof(int));
+        int flag = 0;
+        GV2_CUDA(ctx, cudaMemsetAsync(job->mma_flag.p, 0, sizeof(int), ctx->stream));
+        weights_validate_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(dev_weights, job->p, job->mma_flag.as<int>());
+        GV2_LAUNCH_CHECK(ctx);
+        GV2_CUDA(ctx, cudaMemcpyAsync(&flag, job->mma_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (flag & 1)
+            return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a column multiplicity is outside 0..255 (uint8 operands of the replicate kernels)");
+        if ((flag & 2) && job->sparse)
+            return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a replicate's column multiplicities sum to more than 65536 (limit of the exact sparse path); set GV2_BOOT_PATH=fp32");
+    }
     const int64_t n = job->n, p = job->p, g = job->g, ntl = job->ntiles;
     const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
     ring_len = std::min(ring_len, nb);
@@ -592,10 +715,6 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 // exact integer paths on the fixed-point table: CSR walk (sparse tables) or tensor-core contraction
                 const size_t scratch = job->sparse ? boot_sparse_scratch_bytes(job->p_pad, sb) : boot_mma_scratch_bytes(job->p_pad, sb);
                 if ((rc = ensure(ctx, job->wbf16, scratch))) return rc;
-                if (!job->mma_flag.p) {
-                    if ((rc = ensure(ctx, job->mma_flag, sizeof(int)))) return rc;
-                    GV2_CUDA(ctx, cudaMemsetAsync(job->mma_flag.p, 0, sizeof(int), ctx->stream));
-                }
                 if (job->sparse)
                     rc = boot_sparse_launch(ctx, job->sparse, job->n_pad, job->p_pad, 0, ntl, w, p, sb, job->wbf16.p,
                                             job->mma_flag.as<int>(), job->wsP.as<double>());
@@ -614,15 +733,28 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                                              job->wsP.as<double>()))) return rc;
             }
         }
+        if (job->need_p && job->n_nan_cells > 0) {      // NaN entries zero a row only in the replicates that drew their column
+            if ((rc = ensure(ctx, job->rep_nan, (size_t)sb * n))) return rc;
+            GV2_CUDA(ctx, cudaMemsetAsync(job->rep_nan.p, 0, (size_t)sb * n, ctx->stream));
+            const long long work = (long long)job->n_nan_cells * sb;
+            rep_nan_kernel<<<(unsigned)((work + 255) / 256), 256, 0, ctx->stream>>>(job->nan_cells.as<int2>(), (int)job->n_nan_cells, w, p, n, sb,
+                                                                                   job->rep_nan.as<unsigned char>());
+            GV2_LAUNCH_CHECK(ctx);
+        }
         if (job->need_g) {
             if ((rc = ensure(ctx, job->gomtab, (size_t)sb * n * g * sizeof(double)))) return rc;
             if ((rc = gom_db_score(ctx, job->gom, w, sb, job->gomtab.as<double>()))) return rc;
             if ((rc = job_prepare_gom(job, job->gomtab.as<double>(), sb))) return rc;
         }
-        for (int64_t c0 = 0; c0 < sb; c0 += sub) {
+        for (int64_t c0 = 0; c0 < sb;) {
             int64_t cb = std::min<int64_t>(sub, sb - c0);
-            if (slot + cb > ring_len) slot = 0;                            // sub-chunks never wrap inside the ring
-            if (host_out && ring_len >= 2) { slot = half * sub; }
+            if (!host_out && !sink) {                                      // device-only: replicate b lives in slot b % ring_len
+                slot = (s0 + c0) % ring_len;
+                cb = std::min<int64_t>(cb, ring_len - slot);
+            } else {
+                if (slot + cb > ring_len) slot = 0;                        // sub-chunks never wrap inside the ring
+                if (host_out && ring_len >= 2) { slot = half * sub; }
+            }
             if (cb_fn) {
                 if ((rc = deliver(half))) return rc;                       // consumer is done with these host slots too
             } else if (drained_pending[half]) {                            // the copy that last read these slots is done
@@ -631,7 +763,9 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
             }
             if (job->need_p) {
                 cp.min_sums = job->wsP.as<double>() + (size_t)c0 * ntl * tile_elems;
-                cp.rowsums = job->w_rowsum.as<double>() + c0 * n; cp.nanflags = job->sig_nan.as<uint8_t>();
+                cp.rowsums = job->w_rowsum.as<double>() + c0 * n;
+                cp.nanflags = job->n_nan_cells > 0 ? job->rep_nan.as<uint8_t>() + c0 * n : nullptr;
+                cp.replicate_stride_nan = job->n_nan_cells > 0 ? n : 0;
                 cp.ksplit = 1; cp.replicate_stride_sums = (int64_t)(ntl * tile_elems); cp.replicate_stride_rows = n;
             }
             if (job->need_g) {
@@ -642,7 +776,6 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                                           job->n_pad, g, job->g_pad, cb, job->need_p ? &cp : nullptr, &cg, job->scheme, job->power,
                                           job->out_kind, dev_ring + slot * n * n, n * n))) return rc;
             } else {
-                // (NaN flags of the signature table are replicate independent: replicate_stride_nan stays 0)
                 if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
                                               dev_ring + slot * n * n, n * n))) return rc;
             }
@@ -663,6 +796,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 if (cb_fn && (rc = deliver(half))) return rc;              // previous sub-chunk, while this one runs
             }
             slot += cb;
+            c0 += cb;
         }
     }
     if (cb_fn) {
@@ -674,13 +808,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
         if ((rc = sink->drain(sink->cur ^ 1))) return rc;
     }
     if (host_out) GV2_CUDA(ctx, cudaStreamSynchronize(job->copy_stream));
-    if (used_mma) {     // multiplicities above 255 do not fit the uint8 operand: refuse rather than wrap
-        int flag = 0;
-        GV2_CUDA(ctx, cudaMemcpyAsync(&flag, job->mma_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (flag) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "%s (limits of the exact integer replicate paths); set GV2_BOOT_PATH=fp32",
-                                  flag == 2 ? "a replicate's column multiplicities sum to more than 65536" : "a column multiplicity exceeds 255");
-    }
+    (void)used_mma;
     return GV2_OK;
 }
 
@@ -813,11 +941,22 @@ extern "C" int gv2_shared_counts_host(gv2_ctx* ctx, const double* tab, int64_t n
     const int64_t words = gv2_round_up(std::max<int64_t>(1, (p + 63) / 64), 16);
     int rc;
     DevBuf d_tab, d_bits, d_nnz, d_inter;
-    if ((rc = upload_matrix(ctx, tab, n, p, ld, d_tab))) return rc;
     ALLOC(ctx, d_bits, (size_t)n_pad * words * 8);
     ALLOC(ctx, d_nnz, (size_t)n * sizeof(int32_t));
     ALLOC(ctx, d_inter, (size_t)n * n * sizeof(int32_t));
-    if ((rc = gv2_dev_pack_presence(ctx, d_tab.as<double>(), n, p, p, d_bits.as<uint64_t>(), n_pad, words, d_nnz.as<int32_t>()))) return rc;
+    {   // the float64 table only passes through: row chunks of ~1 GB are uploaded and bit-packed one after the other
+        // (the packed table is 1/64 of it), so a 50 000 x 30 000 table never needs its 12 GB resident
+        const int64_t rows = std::max<int64_t>(GV2_TILE, ((int64_t)(1LL << 30) / std::max<int64_t>(8, p * 8)) / GV2_TILE * GV2_TILE);
+        ALLOC(ctx, d_tab, (size_t)std::min<int64_t>(rows, n) * p * sizeof(double));
+        for (int64_t r0 = 0; r0 < n; r0 += rows) {
+            const int64_t rc_rows = std::min<int64_t>(rows, n - r0);
+            GV2_CUDA(ctx, cudaMemcpy2DAsync(d_tab.p, p * sizeof(double), tab + r0 * ld, ld * sizeof(double), p * sizeof(double), rc_rows,
+                                            cudaMemcpyHostToDevice, ctx->stream));
+            const int64_t pad_rows = r0 + rc_rows == n ? n_pad - r0 : rc_rows;
+            if ((rc = gv2_dev_pack_presence(ctx, d_tab.as<double>(), rc_rows, p, p, d_bits.as<uint64_t>() + (size_t)r0 * words, pad_rows, words,
+                                            d_nnz.as<int32_t>() + r0))) return rc;
+        }
+    }
     if ((rc = gv2_dev_shared_counts(ctx, d_bits.as<uint64_t>(), n, n_pad, words, 0, gv2_num_tiles(n), d_inter.as<int32_t>()))) return rc;
     GV2_CUDA(ctx, cudaMemcpyAsync(inter, d_inter.p, (size_t)n * n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (nnz) GV2_CUDA(ctx, cudaMemcpyAsync(nnz, d_nnz.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -732,7 +732,6 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
                        double* ws) {
     const int64_t ntl = tile_end - tile_begin;
     if (ntl <= 0 || nb <= 0) return GV2_OK;
-    if (ntl > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "boot_sparse_launch: more than 65535 genome tiles per launch");
     const bool use_lists = s->lists.rowptr && tile_begin == 0 && ntl == (n_pad / GV2_TILE) * (n_pad / GV2_TILE + 1) / 2;
     const int rl = use_lists ? bsl_lanes(nb) : bs_lanes(nb);
     const int64_t w_ld = use_lists ? bsl_wld(nb) : bs_wld(nb);
@@ -771,14 +770,19 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     const int kwin = (int)std::min<int64_t>(k_pad, BS_WIN);            // k_pad is a multiple of 128
     const size_t smem = bs_smem_bytes(kwin);
     const long long rep_stride = (long long)ntl * GV2_TILE * GV2_TILE;
-    dim3 grid(64, (unsigned)ntl, (unsigned)(w_ld / rl));
-    if (rl == 64)
-        boot_sparse_kernel<64><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, ws);
-    else if (rl == 128)
-        boot_sparse_kernel<128><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, ws);
-    else
-        boot_sparse_kernel<256><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, ws);
-    GV2_LAUNCH_CHECK(ctx);
+    // grid.y holds at most 65535 tiles: larger tile ranges (n > 46 000 genomes) go in several launches
+    for (int64_t t0 = 0; t0 < ntl; t0 += 65535) {
+        const int64_t tc = std::min<int64_t>(65535, ntl - t0);
+        dim3 grid(64, (unsigned)tc, (unsigned)(w_ld / rl));
+        double* wsc = ws + (size_t)t0 * (GV2_TILE * GV2_TILE);
+        if (rl == 64)
+            boot_sparse_kernel<64><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin + t0, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, wsc);
+        else if (rl == 128)
+            boot_sparse_kernel<128><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin + t0, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, wsc);
+        else
+            boot_sparse_kernel<256><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, nt, tile_begin + t0, wT, w_ld, kwin, nwin, (int)nb, rep_stride, s->quantum, wsc);
+        GV2_LAUNCH_CHECK(ctx);
+    }
     timer.end();
     return GV2_OK;
 }

@@ -446,8 +446,9 @@ __global__ void prepare_table_kernel(const double* __restrict__ src, long long n
             if (c < k) {
                 double v = p[c];
                 if (apply_thr && v < thr) v = 0.0;
+                // a NaN entry is carried by the row flag (per replicate where the table is resampled); the image holds 0
+                if (isnan(v)) { has_nan = 1; v = 0.0; }
                 f = (float)v;
-                if (isnan(v)) has_nan = 1;
                 s += (double)f;
             }
             d[c] = f;

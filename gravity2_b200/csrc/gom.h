@@ -13,6 +13,9 @@ struct GomDb {
     long long nnz = 0;          // non-zero location entries of the scored genomes
     int npt = 0;                // sum over GOMs of |R_g|
     int max_ng = 0, max_t = 0;
+    long long sum_ng2 = 0;      // sum over GOMs of |R_g|^2 (entries of the distance caches)
+    long long n_isect = 0;      // entries of all intersection lists
+    long long n_mentries = 0;   // sum over (GOM, genome) pairs of |I| (|I| - 1) / 2
     size_t vg_smem = 0;
     size_t bytes = 0;
     // genome CSR
@@ -29,6 +32,7 @@ struct GomDb {
     unsigned char* wT8 = nullptr; double* wG = nullptr; int* flag = nullptr;   // uint8 weights, per-GOM gathered weights, flags
     long long* heavy_list = nullptr;   // (genome, GOM) pairs whose intersection list overflows the light kernel
     int n_heavy = 0;
+    bool weights_validated = false;    // the caller has checked 0 <= w <= 255 for every call (device jobs): no flag read-back per call
     // replicate-independent intersection lists I0 = R_v & R_g of every (GOM, genome) pair, built once per database:
     // entries [is_ptr[g*n+v], is_ptr[g*n+v+1]) of is_ent, each (GOM point index k, genome hit index c)
     long long* is_ptr = nullptr;

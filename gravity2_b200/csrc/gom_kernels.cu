@@ -243,7 +243,7 @@ __global__ void gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int*
     o[4 * NBC] = AR2; o[5 * NBC] = ARN; o[6 * NBC] = SAA;
 }
 
-#define VAGG 7   // t, Y1, Y2, Ys, RR1, RR2, RY: per-genome aggregates of the weighted row sums r_c = sum_d w_d |y_c - y_d|
+#define VAGG 8   // t, Y1, Y2, Ys, RR1, RR2, RY, YC (1 = all drawn hits share one location value): per-genome aggregates of the weighted row sums r_c = sum_d w_d |y_c - y_d|
 // Order of a genome's hits by location value (ties by hit index), by rank counting: ord[o + rank] = hit index.
 // Built once per database.  grid = n, block = 128; the values are staged in shared memory (dynamic: t * 8 bytes).
 __global__ void genome_order_kernel(const long long* __restrict__ ptr, const double* __restrict__ val, int* __restrict__ ord) {
@@ -286,10 +286,17 @@ genome_rowsums_sorted_kernel(long long n, const long long* __restrict__ ptr, con
     }
     double Wlt = 0.0, Slt = 0.0;
     double T = 0, Y1 = 0, Y2 = 0, Ys = 0, RR1 = 0, RR2 = 0, RY = 0;
+    double ylo = 0.0, yhi = 0.0;
+    bool seen = false, yconst = true;
     for (int k = 0; k < t; ++k) {
         const int c = ord[o + k];
         const double yc = val[o + c], ay = fabs(yc);
         const double w = (double)wT8[(long long)col[o + c] * NBC + b];
+        if (w > 0.0) {                              // hits come in location order: first and last drawn value bracket the rest
+            if (!seen) { ylo = yc; seen = true; }
+            yhi = yc;
+            yconst = ylo == yhi;
+        }
         // hits tied with y_c contribute |y_c - y_d| = 0 on either side, so "before / after in the order" is enough
         const double r = yc * (2.0 * Wlt + w - Wtot) - (2.0 * Slt + w * yc - Stot);
         rT[(o + c) * NBC + b] = r;
@@ -305,6 +312,7 @@ genome_rowsums_sorted_kernel(long long n, const long long* __restrict__ ptr, con
     }
     double* q = vagg + v * VAGG * NBC + b;
     q[0 * NBC] = T; q[1 * NBC] = Y1; q[2 * NBC] = Y2; q[3 * NBC] = Ys; q[4 * NBC] = RR1; q[5 * NBC] = RR2; q[6 * NBC] = RY;
+    q[7 * NBC] = yconst ? 1.0 : 0.0;
 }
 
 // VG: score (genome, GOM) pairs; lane = replicate.  out[b][v][g].
@@ -331,7 +339,11 @@ __device__ __forceinline__ double vg_finish(const VgSums& S, const double* __res
                  RR2 = va[5 * NBC], RY = va[6 * NBC];
     const double e = T - SW, z = n_g - SW, nn = n_g + e;
     double res = 0.0;
-    if (nn > 0.0) {
+    // Exactly degenerate Y: no zero-valued point (z == 0; the counts are small integers, exact) and every drawn hit at one
+    // location value.  The reference's centred matrix is then exactly 0 and it returns 0.0 (dcor.py:54-60); the un-centred
+    // expansion below would leave rounding noise in sBB instead.  (A degenerate X leaves exact zeros in every term.)
+    const bool y_degenerate = z == 0.0 && va[7 * NBC] != 0.0;
+    if (nn > 0.0 && !y_degenerate) {
         const double Sab = 2.0 * (C_ary - Q2) + 2.0 * (N1 - S_nrm) * (Y1 - S_y) + Q1 + 2.0 * (C_nr - Q3);
         const double cross = ((AR1 - S_ar) + e * (N1 - S_nrm)) * Y1 +
                              (C_arr + z * C_ary + e * C_nr + e * z * C_ny) +
@@ -388,6 +400,17 @@ __global__ void gom_heavy_list_kernel(long long total, const long long* __restri
     const long long wid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (wid >= total) return;
     if (is_ptr[wid + 1] - is_ptr[wid] > cap) heavy_list[atomicAdd(heavy_count, 1)] = wid;
+}
+
+// sum over pairs of |I| (|I| - 1) / 2: the pair-sum terms one replicate costs (roofline bookkeeping)
+__global__ void gom_mentries_kernel(long long total, const long long* __restrict__ is_ptr, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0;
+    for (long long wid = (long long)blockIdx.x * blockDim.x + threadIdx.x; wid < total; wid += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long ni = (unsigned long long)(is_ptr[wid + 1] - is_ptr[wid]);
+        s += ni * (ni - (ni ? 1 : 0)) / 2;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
 // load a precomputed intersection list into the staging arrays (threads tid, tid + nthreads, ...)
@@ -680,6 +703,7 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
         if (ng > max_ng) max_ng = (int)ng;
     }
     db->max_ng = max_ng;
+    db->sum_ng2 = a_off_h[G];
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     const size_t need = (size_t)(a_off_h[G] + x_off_h[G]) * sizeof(double);
@@ -766,7 +790,17 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
             gom_heavy_list_kernel<<<(unsigned)((total_w + 255) / 256), 256, 0, st>>>(total_w, db->is_ptr, VG_LIGHT_CAP, db->heavy_list, db->flag + 1);
             ctx->launches++;
             CK(cudaMemcpyAsync(&db->n_heavy, db->flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            unsigned long long* d_me = nullptr;
+            CK(dalloc(&d_me, 1, nullptr));
+            CK(cudaMemsetAsync(d_me, 0, sizeof(unsigned long long), st));
+            gom_mentries_kernel<<<(unsigned)std::min<long long>(2048, (total_w + 255) / 256), 256, 0, st>>>(total_w, db->is_ptr, d_me);
+            ctx->launches++;
+            unsigned long long me = 0;
+            CK(cudaMemcpyAsync(&me, d_me, sizeof me, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            cudaFree(d_me);
+            db->n_mentries = (long long)me;
+            db->n_isect = n_ent;
         }
     }
     const size_t vg_smem = (size_t)((max_t + 1) & ~1) * (VG_ENTRY_BYTES + 4 * sizeof(double)) + 3 * VG_NSUM * 32 * sizeof(double);
@@ -789,6 +823,10 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
     cudaStream_t st = ctx->stream;
     const int64_t n = db->n, p = db->p, G = db->G;
     if (n == 0 || G == 0) return GV2_OK;
+    if (weights && !db->weights_validated) {       // the flag starts clean per call (jobs validate up front instead)
+        cudaError_t e0 = cudaMemsetAsync(db->flag, 0, sizeof(int), st);
+        if (e0 != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "gom_db_score: %s", cudaGetErrorString(e0));
+    }
     for (int64_t b0 = 0; b0 < nb; b0 += NBC) {
         const int cb = (int)std::min<int64_t>(NBC, nb - b0);
         Gv2Timer timer(ctx, GV2_TIME_GOM);
@@ -827,7 +865,7 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "gom_db_score: %s", cudaGetErrorString(e));
     }
-    if (weights) {      // multiplicities are staged as uint8 in shared memory: refuse anything above 255
+    if (weights && !db->weights_validated) {      // multiplicities are staged as uint8 in shared memory: refuse anything above 255
         int flag = 0;
         cudaError_t e = cudaMemcpyAsync(&flag, db->flag, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);

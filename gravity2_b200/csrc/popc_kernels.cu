@@ -8,6 +8,8 @@
 // kernel.  Integer arithmetic throughout: results are bit-exact.
 #include "common.cuh"
 
+#include <algorithm>
+
 #define PC_THREADS 256
 #define PC_BK 32                  // 32-bit words per stage (1024 PPHMM columns)
 #define PC_LDS (PC_BK + 4)
@@ -50,6 +52,9 @@ __global__ void pack_presence_kernel(const double* __restrict__ tab, long long n
     }
 }
 
+// PACKED == false: counts (and their mirrors) go into inter [n][n];  PACKED == true: inter is [tiles][128*128] row-major
+// tile blocks (multi-GPU all-gather payload; scatter with unpack_tiles_i32_kernel)
+template <bool PACKED>
 __global__ void __launch_bounds__(PC_THREADS, 2)
 shared_count_tile_kernel(const unsigned* __restrict__ bits, int ld, int kblocks, int nt, long long tile_begin,
                          long long n, int* __restrict__ inter) {
@@ -110,17 +115,110 @@ shared_count_tile_kernel(const unsigned* __restrict__ bits, int ld, int kblocks,
             }
         }
     }
+    if (PACKED) {
+        int* o = inter + (size_t)blockIdx.x * (GV2_TILE * GV2_TILE);
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int nn = 0; nn < 8; ++nn) o[(ty + 16 * m) * GV2_TILE + tx + 16 * nn] = acc[m][nn];
+        return;
+    }
+    // direct rows: 16 consecutive ints per (m, nn); mirror through shared memory (the stage ring is dead) so that the
+    // transposed tile also leaves as whole 64-byte runs instead of one 4-byte store per 4 n bytes
+    __syncthreads();
+    int* tr = reinterpret_cast<int*>(psm);                           // [128][129]
 #pragma unroll
     for (int m = 0; m < 8; ++m)
 #pragma unroll
         for (int nn = 0; nn < 8; ++nn) {
-            long long gi = (long long)bi * GV2_TILE + ty + 16 * m;
-            long long gj = (long long)bj * GV2_TILE + tx + 16 * nn;
-            if (gi < n && gj < n) {
-                inter[gi * n + gj] = acc[m][nn];
-                inter[gj * n + gi] = acc[m][nn];
-            }
+            const int r = ty + 16 * m, c = tx + 16 * nn;
+            const long long gi = (long long)bi * GV2_TILE + r, gj = (long long)bj * GV2_TILE + c;
+            if (gi < n && gj < n) inter[gi * n + gj] = acc[m][nn];
+            tr[c * 129 + r] = acc[m][nn];
         }
+    if (bi == bj) return;                                            // diagonal tiles hold both triangles already
+    __syncthreads();
+    for (int q = tid; q < GV2_TILE * GV2_TILE; q += PC_THREADS) {
+        const int c = q >> 7, r = q & 127;
+        const long long gi = (long long)bi * GV2_TILE + r, gj = (long long)bj * GV2_TILE + c;
+        if (gi < n && gj < n) inter[gj * n + gi] = tr[c * 129 + r];
+    }
+}
+
+// packed int32 tiles [ntl][128*128] -> symmetric n x n.  grid = tiles * 16, block (32, 8)
+__global__ void __launch_bounds__(256)
+unpack_tiles_i32_kernel(long long n, int nt, long long tile_begin, const int* __restrict__ packed, int* __restrict__ out) {
+    __shared__ int tr[32][33];
+    const long long t = blockIdx.x >> 4;
+    const int sub = blockIdx.x & 15, sr = sub >> 2, sc = sub & 3;
+    int bi, bj;
+    pc_tile_coords(tile_begin + t, nt, &bi, &bj);
+    const int lx = threadIdx.x;
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy) {
+        const int ly = threadIdx.y + yy * 8;
+        const int r = sr * 32 + ly, c = sc * 32 + lx;
+        const long long gi = (long long)bi * GV2_TILE + r, gj = (long long)bj * GV2_TILE + c;
+        const int v = packed[t * (long long)(GV2_TILE * GV2_TILE) + r * GV2_TILE + c];
+        if (gi < n && gj < n) out[gi * n + gj] = v;
+        tr[ly][lx] = v;
+    }
+    if (bi == bj) return;
+    __syncthreads();
+#pragma unroll
+    for (int yy = 0; yy < 4; ++yy) {
+        const int ly = threadIdx.y + yy * 8;
+        const long long gj = (long long)bj * GV2_TILE + sc * 32 + ly;
+        const long long gi = (long long)bi * GV2_TILE + sr * 32 + lx;
+        if (gi < n && gj < n) out[gj * n + gi] = tr[lx][ly];
+    }
+}
+
+// POPC-pipe peak of this device, measured: register-resident LOP3 + POPC + IADD chains (8 independent per thread), no
+// memory traffic.  The roofline denominator of the presence / absence path (SURVEY.md section 8d asks for a micro-benchmark
+// instead of the programming guide's table figure).
+__global__ void __launch_bounds__(256)
+popc_peak_kernel(int iters, unsigned seed, unsigned* __restrict__ sink) {
+    unsigned a[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = seed * (threadIdx.x + 1 + 977 * k) + blockIdx.x; acc[k] = 0; }
+    unsigned m = seed | 0x55aa55aau;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            acc[k] += __popc(a[k] & m);
+            a[k] += acc[k];                      // keeps the AND operand changing: nothing hoists out of the loop
+        }
+        m = (m << 1) | (m >> 31);
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    if (s == 0x12345u) sink[0] = s;
+}
+
+static int pc_launch(gv2_ctx* ctx, const uint64_t* bits, int64_t n, int64_t n_pad, int64_t words, int64_t tile_begin,
+                     int64_t tile_end, int packed, int32_t* out) {
+    const int64_t ntl = tile_end - tile_begin;
+    if (ntl == 0) return GV2_OK;
+    // stage ring, reused as the [128][129] int transpose of the mirror
+    const size_t smem = std::max((size_t)2 * PC_STAGES * GV2_TILE * PC_LDS * sizeof(unsigned), (size_t)GV2_TILE * 129 * sizeof(int));
+    if (!(ctx->smem_attr_done & GV2_ATTR_POPC)) {
+        GV2_CUDA(ctx, cudaFuncSetAttribute(shared_count_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(shared_count_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->smem_attr_done |= GV2_ATTR_POPC;
+    }
+    const int nt = (int)(n_pad / GV2_TILE), ld = (int)(2 * words), kb = (int)(2 * words / PC_BK);
+    for (int64_t t0 = 0; t0 < ntl; t0 += 1 << 30) {                  // grid.x holds 2^31 - 1 blocks
+        const int64_t tc = std::min<int64_t>(1 << 30, ntl - t0);
+        if (packed)
+            shared_count_tile_kernel<true><<<(unsigned)tc, PC_THREADS, smem, ctx->stream>>>((const unsigned*)bits, ld, kb, nt, tile_begin + t0, n,
+                                                                                          out + t0 * (GV2_TILE * GV2_TILE));
+        else
+            shared_count_tile_kernel<false><<<(unsigned)tc, PC_THREADS, smem, ctx->stream>>>((const unsigned*)bits, ld, kb, nt, tile_begin + t0, n, out);
+        GV2_LAUNCH_CHECK(ctx);
+    }
+    return GV2_OK;
 }
 
 extern "C" int gv2_dev_pack_presence(gv2_ctx* ctx, const double* tab, int64_t n, int64_t p, int64_t ld,
@@ -140,13 +238,52 @@ extern "C" int gv2_dev_shared_counts(gv2_ctx* ctx, const uint64_t* bits, int64_t
         return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_shared_counts: bad arguments");
     const int64_t ntl = tile_end - tile_begin;
     if (ntl == 0) return GV2_OK;
-    const size_t smem = (size_t)2 * PC_STAGES * GV2_TILE * PC_LDS * sizeof(unsigned);
-    if (!(ctx->smem_attr_done & GV2_ATTR_POPC)) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(shared_count_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ctx->smem_attr_done |= GV2_ATTR_POPC;
+    return pc_launch(ctx, bits, n, n_pad, words, tile_begin, tile_end, 0, inter);
+}
+
+extern "C" int gv2_dev_shared_counts_packed(gv2_ctx* ctx, const uint64_t* bits, int64_t n, int64_t n_pad, int64_t words,
+                                            int64_t tile_begin, int64_t tile_end, int32_t* packed) {
+    if (!ctx || !bits || !packed || tile_end < tile_begin || (n_pad % GV2_TILE) || ((2 * words) % PC_BK))
+        return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_shared_counts_packed: bad arguments");
+    return pc_launch(ctx, bits, n, n_pad, words, tile_begin, tile_end, 1, packed);
+}
+
+extern "C" int gv2_dev_unpack_tiles_i32(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_t tile_end, const int32_t* packed,
+                                        int32_t* out) {
+    if (!ctx || !packed || !out || tile_end < tile_begin) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_unpack_tiles_i32: bad arguments");
+    const int64_t ntl = tile_end - tile_begin;
+    if (ntl == 0 || n == 0) return GV2_OK;
+    dim3 block(32, 8);
+    for (int64_t t0 = 0; t0 < ntl; t0 += 1 << 20) {                  // grid.x limit: 2^31 - 1 blocks of 16 per tile
+        const int64_t tc = std::min<int64_t>(1 << 20, ntl - t0);
+        unpack_tiles_i32_kernel<<<(unsigned)(tc * 16), block, 0, ctx->stream>>>(n, (int)((n + GV2_TILE - 1) / GV2_TILE), tile_begin + t0,
+                                                                                 packed + t0 * (GV2_TILE * GV2_TILE), out);
+        GV2_LAUNCH_CHECK(ctx);
     }
-    shared_count_tile_kernel<<<(unsigned)ntl, PC_THREADS, smem, ctx->stream>>>(
-        (const unsigned*)bits, (int)(2 * words), (int)(2 * words / PC_BK), (int)(n_pad / GV2_TILE), tile_begin, n, inter);
-    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
+extern "C" int gv2_dev_popc_peak(gv2_ctx* ctx, int iters, double* popc_per_s) {
+    if (!ctx || !popc_per_s || iters <= 0) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_dev_popc_peak: bad arguments");
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned* sink = nullptr;
+    GV2_CUDA(ctx, cudaMalloc((void**)&sink, sizeof(unsigned)));
+    cudaEvent_t a, b;
+    GV2_CUDA(ctx, cudaEventCreate(&a));
+    GV2_CUDA(ctx, cudaEventCreate(&b));
+    const unsigned blocks = (unsigned)ctx->sm_count * 8;             // 8 CTAs of 256 threads per SM: every SMSP saturated
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {                              // first pass warms up; best of the rest
+        cudaEventRecord(a, ctx->stream);
+        popc_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(iters, 0x9e3779b9u + rep, sink);
+        cudaEventRecord(b, ctx->stream);
+        ctx->launches++;
+        GV2_CUDA(ctx, cudaEventSynchronize(b));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    *popc_per_s = (double)blocks * 256.0 * 8.0 * iters / (best * 1e-3);
     return GV2_OK;
 }

@@ -183,6 +183,24 @@ def binary_jaccard(trait_table, engine: Optional[Engine] = None):
         return inter / union
 
 
+def sort_pphmm_distances(PPHMMSignatureTable, engine: Optional[Engine] = None):
+    """The matrix RefVirusAnnotator.sort_pphmm hands to DistMat2Tree (app/src/ref_virus_annotator.py:143-165):
+    ``1 - SimMat_traits`` of the 0/1 transposed signature table, (P, P) float64, NaN where both PPHMMs are empty."""
+    trait = np.ascontiguousarray(np.asarray(PPHMMSignatureTable, dtype=np.float64).T)
+    return 1 - binary_jaccard(trait, engine)
+
+
+def sort_pphmm_tree(PPHMMSignatureTable, do_logscale=False, engine: Optional[Engine] = None):
+    """Newick string of the PPHMM dendrogram of sort_pphmm (:162-165): average linkage, leaves named 0..P-1.  The
+    caller ladderizes it and reads the leaf order as the reference does (:167-170, Bio.Phylo)."""
+    D = sort_pphmm_distances(PPHMMSignatureTable, engine)
+    if not np.isfinite(D).all():
+        # scipy's linkage refuses non-finite distances, so the reference fails here too (empty PPHMM columns are
+        # removed upstream, remove_singleton_pphmm)
+        raise ValueError("The condensed distance matrix must contain only finite values.")
+    return DistMat2Tree(D, list(range(D.shape[0])), "average", do_logscale, engine=engine)
+
+
 # ------------------------------------------------------------------------------ dendrograms
 LINKAGE_METHODS = ("average", "complete", "weighted", "ward", "single")
 

@@ -229,6 +229,7 @@ class Job:
         self.eng, self.lib, self.ctx = eng, eng.lib, eng.ctx
         sig = _f64(sig, "PPHMMSignatureTable")
         self.n, self.p = sig.shape
+        self.g = int(g)
         loc_arr = sig if (loc is sig or loc is None) else _f64(loc, "PPHMMLocationTable")
         gor = None if gom_of_row is None else np.ascontiguousarray(gom_of_row, dtype=np.int32)
         self.job = C.c_void_p()
@@ -263,6 +264,36 @@ class Job:
         finally:
             self.lib.gv2_dev_free(self.ctx, d)
         return out
+
+    def gom_table(self, weights=None) -> np.ndarray:
+        """GOM signature table(s) of the job's location table: (N, G) for the un-resampled table, (B, N, G) for
+        column multiplicities ``weights`` (B, P) -- what GOMSignatureTable_Constructor returns on ``loc[:, idx]``."""
+        n = self.n
+        g = self.g
+        w = None
+        nb = 1
+        if weights is not None:
+            w = np.ascontiguousarray(weights, dtype=np.int32)
+            if w.ndim == 1:
+                w = w[None, :]
+            if w.shape[1] != self.p:
+                raise ValueError("weights must be (B, P)")
+            nb = w.shape[0]
+        out = np.empty((nb, n, g), dtype=np.float64)
+        d_out, d_w = C.c_void_p(), C.c_void_p()
+        _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, max(out.nbytes, 8), C.byref(d_out)))
+        try:
+            if w is not None:
+                _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, w.nbytes, C.byref(d_w)))
+                _lib.check(self.ctx, self.lib.gv2_memcpy_h2d(self.ctx, d_w, _ptr(w), w.nbytes))
+            _lib.check(self.ctx, self.lib.gv2_job_gom_table(self.job, d_w if w is not None else None, nb, d_out))
+            if out.nbytes:
+                _lib.check(self.ctx, self.lib.gv2_memcpy_d2h(self.ctx, _ptr(out), d_out, out.nbytes))
+        finally:
+            if d_w:
+                self.lib.gv2_dev_free(self.ctx, d_w)
+            self.lib.gv2_dev_free(self.ctx, d_out)
+        return out if weights is not None else out[0]
 
     def for_each_replicate(self, weights, fn) -> None:
         """fn(b, matrix) for every replicate in order; matrix is a zero-copy view into the pinned ring."""

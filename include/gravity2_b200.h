@@ -70,6 +70,7 @@ uint64_t gv2_launch_count(const gv2_ctx* ctx); /* kernels launched so far throug
 #define GV2_TIME_TAIL 1     /* fused GOM Jaccard + epilogue kernel */
 #define GV2_TIME_GOM 2      /* GOM dCor scoring kernels of one 32-replicate chunk */
 #define GV2_TIME_LINKAGE 3  /* device UPGMA of one sub-chunk of replicate matrices */
+#define GV2_TIME_BASE 4     /* one gv2_job_base call (un-resampled matrix) */
 int gv2_timing_enable(gv2_ctx* ctx, int on);
 int gv2_timing_read_kind(gv2_ctx* ctx, int kind, double* total_ms, int64_t* launches);
 int gv2_timing_read(gv2_ctx* ctx, double* total_ms, int64_t* launches); /* = kind GV2_TIME_PAIRSUMS */
@@ -183,9 +184,10 @@ void gv2_job_destroy(gv2_job* job);
 int gv2_job_base(gv2_job* job, int64_t tile_begin, int64_t tile_end, int packed, double* dev_out);
 /* Replicates [0, nb) given their device-resident weights; dev_out [nb][n][n]. */
 int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out);
-/* Streaming form: replicate b goes to slot (b % ring_len) of dev_ring [ring_len][n][n]; with host_out != NULL
- * ([nb][n][n] host memory, ideally pinned) every replicate is also copied out on a second stream while the
- * next ones are computed, so the device never holds more than ring_len matrices.
+/* Streaming form.  host_out == NULL (device-only): replicate b goes to slot (b % ring_len) of dev_ring [ring_len][n][n],
+ * so after the call the last ring_len replicates are resident.  With host_out != NULL ([nb][n][n] host memory, ideally
+ * pinned) the ring is used as two halves (one computing, one draining; ring_len >= 2) and every replicate is also copied
+ * out on a second stream while the next ones are computed, so the device never holds more than ring_len matrices.
  * callback == NULL: host_out is linear, replicate b lands in host_out[b].
  * callback != NULL: host_out is a HOST RING [ring_len][n][n]; as soon as replicate b is in host memory the
  * library calls callback(b, matrix, user) on the calling thread (in replicate order) while the GPU already
@@ -206,6 +208,10 @@ int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weights, int64_t 
  * dev_out [nb][n][g]. */
 int gv2_job_gom_table(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out);
 size_t gv2_job_device_bytes(const gv2_job* job);
+/* Sizes of the job's GOM database (roofline bookkeeping): stats[0] = sum_g |R_g| (GOM points), [1] = sum_g |R_g|^2
+ * (distance-cache entries), [2] = non-zero location entries, [3] = (genome, GOM) pairs on the heavy list, [4] = entries of the
+ * intersection lists, [5] = sum over pairs of |I| (|I| - 1) / 2 (pair-sum terms per replicate), [6] = max |R_g|, [7] = max hits. */
+int gv2_job_gom_stats(const gv2_job* job, int64_t* stats /* [8] */);
 /* Replicate pair-sum path chosen for the job's signature table: exact integer arithmetic on a fixed-point image
  * (CSR walk of sparse tables / tensor-core contraction of dense ones) or the fp32 tile kernel (tables with negative
  * entries).  The environment variable GV2_BOOT_PATH = sparse | mma | fp32 overrides the cost model. */
@@ -264,6 +270,15 @@ int gv2_dev_pack_presence(gv2_ctx* ctx, const double* tab, int64_t n, int64_t p,
                           uint64_t* bits, int64_t n_pad, int64_t words, int32_t* nnz);
 int gv2_dev_shared_counts(gv2_ctx* ctx, const uint64_t* bits, int64_t n, int64_t n_pad,
                           int64_t words, int64_t tile_begin, int64_t tile_end, int32_t* inter);
+/* Same counts as [tile_end - tile_begin][128*128] int32 tile blocks (multi-GPU all-gather payload) and their scatter
+ * (+ mirror) into inter [n][n]. */
+int gv2_dev_shared_counts_packed(gv2_ctx* ctx, const uint64_t* bits, int64_t n, int64_t n_pad, int64_t words,
+                                 int64_t tile_begin, int64_t tile_end, int32_t* packed);
+int gv2_dev_unpack_tiles_i32(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_t tile_end, const int32_t* packed,
+                             int32_t* out);
+/* POPC-pipe peak of the context's device, measured (register-resident AND + POPC + add chains on every SM):
+ * the roofline denominator of the presence / absence path. */
+int gv2_dev_popc_peak(gv2_ctx* ctx, int iters, double* popc_per_s);
 
 #ifdef __cplusplus
 }

@@ -191,8 +191,77 @@ def main_neighbourhood():
     print("wrote reference_golden_neighbourhood.npz", len(gold), "arrays")
 
 
+class _AutoMock:
+    """meta-path finder: any module under these prefixes that the container lacks becomes a MagicMock (none is on the
+    arithmetic path: sequence IO, plotting, shell wrappers)"""
+    PREFIXES = ("Bio", "ete3", "plotly", "matplotlib", "dendropy", "seaborn")
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        if name.split(".")[0] in self.PREFIXES:
+            return importlib.machinery.ModuleSpec(name, self)
+        return None
+
+    def create_module(self, spec):
+        m = mock.MagicMock()
+        m.__path__ = []
+        m.__name__ = spec.name
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+def main_sort_pphmm():
+    """a16: the PPHMM x PPHMM binary Jaccard of RefVirusAnnotator.sort_pphmm (app/src/ref_virus_annotator.py:143-158).
+    The UNMODIFIED method runs on a stand-in `self` holding only the signature table; the DistMat2Tree call that follows
+    the similarity loop (:162) is intercepted to capture `1 - SimMat_traits`, then the method is left (the rest rebuilds
+    HH-suite databases with shell commands)."""
+    for k in [k for k in sys.modules if k.split(".")[0] in _AutoMock.PREFIXES]:
+        del sys.modules[k]
+    sys.meta_path.insert(0, _AutoMock())
+    import app.src.ref_virus_annotator as rva
+
+    class _Captured(Exception):
+        pass
+
+    gold = {}
+    for tag, (n, p, dens, seed, empty_col) in {"E": (23, 40, 0.25, 505, False), "F": (17, 33, 0.15, 606, True)}.items():
+        t = make_tables(n, p, 3, dens, seed)
+        sig = t.sig
+        if empty_col:
+            sig[:, 5] = 0.0                      # two empty PPHMM columns: 0/0 -> NaN (the reference has no zero guard)
+            sig[:, 20] = 0.0
+        else:
+            for c in np.where((sig != 0).sum(0) == 0)[0]:
+                sig[c % n, c] = 12.5             # no empty column: linkage needs finite distances
+        box = {}
+
+        def fake_tree(DistMat, LeafList, Dendrogram_LinkageMethod, do_logscale):
+            box["D"] = np.array(DistMat)
+            box["leaves"] = list(LeafList)
+            raise _Captured()
+
+        me = types.SimpleNamespace(PPHMMSignatureTable=sig.copy(), payload={"LogscaleDendrogram": False})
+        with mock.patch.object(rva, "DistMat2Tree", fake_tree), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                rva.RefVirusAnnotator.sort_pphmm(me)
+            except _Captured:
+                pass
+        gold[f"{tag}_sig"] = sig
+        gold[f"{tag}_traits_D"] = box["D"]                       # 1 - SimMat_traits, (P, P), NaN for empty-vs-anything
+        assert box["leaves"] == list(range(p))
+        if not empty_col:
+            gold[f"{tag}_traits_newick"] = np.array(DistMat2Tree(box["D"].copy(), box["leaves"], "average", False))
+    np.savez_compressed(os.path.join(OUT, "reference_golden_sort_pphmm.npz"), **gold)
+    print("wrote reference_golden_sort_pphmm.npz", len(gold), "arrays")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "neighbourhood":
         main_neighbourhood()
+    elif len(sys.argv) > 1 and sys.argv[1] == "sort_pphmm":
+        main_sort_pphmm()
     else:
         main()

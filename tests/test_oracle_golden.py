@@ -216,3 +216,25 @@ def test_linkage_restatement_is_scipy(method):
         D = D + D.T
         dl = D[np.triu_indices_from(D, k=1)]
         assert np.array_equal(L.linkage(dl, method), linkage(dl, method=method))
+
+
+# ------------------------------------------------------------------ a16: sort_pphmm binary Jaccard (reference golden)
+@pytest.mark.parametrize("tag", ["E", "F"])
+def test_binary_gj_equals_reference_sort_pphmm(tag):
+    """oracle.binary_gj restates app/src/ref_virus_annotator.py:148-158; the golden is what the UNMODIFIED
+    RefVirusAnnotator.sort_pphmm handed to DistMat2Tree (oracle/make_golden.py sort_pphmm)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden_sort_pphmm.npz")
+    g = dict(np.load(path, allow_pickle=False))
+    D = 1 - O.binary_gj(g[f"{tag}_sig"].T)
+    ref = g[f"{tag}_traits_D"]
+    assert D.shape == ref.shape
+    assert np.array_equal(np.isnan(D), np.isnan(ref))
+    assert np.array_equal(np.nan_to_num(D, nan=-1.0), np.nan_to_num(ref, nan=-1.0))      # bit for bit
+    if tag == "F":
+        empty = (g["F_sig"] != 0).sum(axis=0) == 0                                        # empty vs empty column: 0/0
+        assert empty[5] and empty[20] and np.array_equal(np.isnan(ref), np.outer(empty, empty))
+        assert ref[5, 0] == 1.0                                                           # empty vs non-empty: 0/n = 0
+    else:
+        leaves = list(range(D.shape[0]))
+        assert O.dist_mat_to_tree(D.copy(), leaves, "average", False) == str(g["E_traits_newick"])
