@@ -18,7 +18,10 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
                        double* ws);
 int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k, int64_t k_pad, int64_t nb,
                     const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
-                    double* out, int64_t out_replicate_stride);
+                    double* out, int64_t out_replicate_stride, int fixed);
+int gom_quantize_launch(gv2_ctx* ctx, const double* tab64, int64_t n, int64_t g, int64_t nb, unsigned* dst, int64_t n_pad, int64_t g_pad,
+                        double* rowsum, uint8_t* nanflag, unsigned long long* scratch);
+
 int boot_mma_available();
 int boot_mma_launch(gv2_ctx* ctx, const uint32_t* tab, double quantum, int64_t n_pad, int64_t k_pad, int64_t tile_begin,
                     int64_t tile_end, const int32_t* w, int64_t k, int64_t nb, void* w8_scratch, int* overflow_flag,
@@ -29,6 +32,8 @@ int boot_mma_prepare_table(gv2_ctx* ctx, const double* src, int64_t n, int64_t k
                            int64_t n_pad, int64_t k_pad, double max_value, double* quantum);
 int boot_mma_rowsums(gv2_ctx* ctx, const double* ws, int64_t ntl, int64_t n, int64_t nb, double* out);
 struct BootSparse;
+int boot_sparse_has_lists(const BootSparse* s);
+int boot_sparse_rowsums(gv2_ctx* ctx, const BootSparse* s, int64_t n, double* out);
 int boot_sparse_build(gv2_ctx* ctx, const double* tab, int64_t n, int64_t k, int64_t ld, int64_t n_pad, int64_t k_pad,
                       double max_value, BootSparse** out);
 int boot_sparse_build_lists(gv2_ctx* ctx, BootSparse* s, size_t budget);
@@ -254,7 +259,8 @@ struct gv2_job {
     DevBuf gom_base;                   // [n][g] float64 base GOM table (lazy)
     bool have_gom_base = false;
     // workspaces, grown on demand
-    DevBuf wsP, wsG, gomtab, gomf, gom_rowsum, gom_nan, wf, w_rowsum, wbf16, mma_flag;
+    DevBuf wsP, wsG, gomtab, gomf, gom_rowsum, gom_nan, gom_qmax, wf, w_rowsum, wbf16, mma_flag;
+    DevBuf ones_w, sig_rowsum_fix;     // all-ones multiplicities and fixed-point row sums: the base matrix through the sparse path
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
     size_t device_bytes() const {
@@ -471,13 +477,19 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
     return GV2_OK;
 }
 
-// GOM table (fp64 [nb][n][g]) -> fp32 padded tables [nb][n_pad][g_pad] + row sums + NaN flags
-static int job_prepare_gom(gv2_job* j, const double* tab64, int64_t nb) {
+// GOM table (fp64 [nb][n][g]) -> padded tables [nb][n_pad][g_pad] + row sums + NaN flags: unsigned fixed point for the
+// replicates' fused tail (fixed != 0, one launch for all nb tables), fp32 for the base matrix's tile kernel
+static int job_prepare_gom(gv2_job* j, const double* tab64, int64_t nb, int fixed) {
     gv2_ctx* ctx = j->ctx;
     int rc;
     if ((rc = ensure(ctx, j->gomf, (size_t)nb * j->n_pad * j->g_pad * sizeof(float)))) return rc;
     if ((rc = ensure(ctx, j->gom_rowsum, (size_t)nb * j->n * sizeof(double)))) return rc;
     if ((rc = ensure(ctx, j->gom_nan, (size_t)nb * j->n))) return rc;
+    if (fixed) {
+        if ((rc = ensure(ctx, j->gom_qmax, sizeof(unsigned long long)))) return rc;
+        return gom_quantize_launch(ctx, tab64, j->n, j->g, nb, j->gomf.as<unsigned>(), j->n_pad, j->g_pad, j->gom_rowsum.as<double>(),
+                                   j->gom_nan.as<uint8_t>(), j->gom_qmax.as<unsigned long long>());
+    }
     for (int64_t b = 0; b < nb; ++b)
         if ((rc = gv2_dev_prepare_table(ctx, tab64 + b * j->n * j->g, j->n, j->g, j->g, 0.0, 0,
                                         j->gomf.as<float>() + b * j->n_pad * j->g_pad, j->n_pad, j->g_pad,
@@ -535,7 +547,25 @@ static int job_base_impl(gv2_job* job, int64_t tile_begin, int64_t tile_end, int
     const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
     int rc;
     gv2_gj_component cp{}, cg{};
-    if (job->need_p) {
+    if (job->need_p && boot_sparse_has_lists(job->sparse)) {
+        // sparse tables: the un-resampled matrix is the all-ones replicate of the exact list path (work ~ co-present cells,
+        // not pairs x P); row sums of the same fixed-point image, so that duplicate genomes come out at exactly 1
+        if (!job->ones_w.p) {
+            std::vector<int32_t> ones((size_t)std::max<int64_t>(1, job->p), 1);
+            if ((rc = ensure(ctx, job->ones_w, ones.size() * sizeof(int32_t)))) return rc;
+            GV2_CUDA(ctx, cudaMemcpyAsync(job->ones_w.p, ones.data(), ones.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+            GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if ((rc = ensure(ctx, job->sig_rowsum_fix, (size_t)std::max<int64_t>(1, job->n) * sizeof(double)))) return rc;
+            if ((rc = boot_sparse_rowsums(ctx, job->sparse, job->n, job->sig_rowsum_fix.as<double>()))) return rc;
+        }
+        if ((rc = ensure(ctx, job->wsP, (size_t)ntl * tile_elems * sizeof(double)))) return rc;
+        if ((rc = ensure(ctx, job->wbf16, boot_sparse_scratch_bytes(job->p_pad, 1)))) return rc;
+        if (!job->mma_flag.p) ALLOC(ctx, job->mma_flag, sizeof(int));
+        if ((rc = boot_sparse_launch(ctx, job->sparse, job->n_pad, job->p_pad, tile_begin, tile_end, job->ones_w.as<int32_t>(), job->p, 1,
+                                     job->wbf16.p, job->mma_flag.as<int>(), job->wsP.as<double>()))) return rc;
+        cp.min_sums = job->wsP.as<double>(); cp.rowsums = job->sig_rowsum_fix.as<double>(); cp.nanflags = job->sig_nan.as<uint8_t>();
+        cp.ksplit = 1;
+    } else if (job->need_p) {
         const int ks = pick_ksplit(ctx, ntl, 1, job->p_pad);
         if ((rc = ensure(ctx, job->wsP, (size_t)ks * ntl * tile_elems * sizeof(double)))) return rc;
         if ((rc = gj_min_sums_launch(ctx, job->sigf.as<float>(), 0, job->n_pad, job->p_pad, tile_begin, tile_end, nullptr, 1, ks,
@@ -549,7 +579,7 @@ static int job_base_impl(gv2_job* job, int64_t tile_begin, int64_t tile_end, int
             if ((rc = gom_db_score(ctx, job->gom, nullptr, 1, job->gom_base.as<double>()))) return rc;
             job->have_gom_base = true;
         }
-        if ((rc = job_prepare_gom(job, job->gom_base.as<double>(), 1))) return rc;
+        if ((rc = job_prepare_gom(job, job->gom_base.as<double>(), 1, 0))) return rc;
         if ((rc = ensure(ctx, job->wsG, (size_t)ntl * tile_elems * sizeof(double)))) return rc;
         if ((rc = gj_min_sums_launch(ctx, job->gomf.as<float>(), 0, job->n_pad, job->g_pad, tile_begin, tile_end, nullptr, 1, 1,
                                      job->wsG.as<double>()))) return rc;
@@ -744,7 +774,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
         if (job->need_g) {
             if ((rc = ensure(ctx, job->gomtab, (size_t)sb * n * g * sizeof(double)))) return rc;
             if ((rc = gom_db_score(ctx, job->gom, w, sb, job->gomtab.as<double>()))) return rc;
-            if ((rc = job_prepare_gom(job, job->gomtab.as<double>(), sb))) return rc;
+            if ((rc = job_prepare_gom(job, job->gomtab.as<double>(), sb, 1))) return rc;
         }
         for (int64_t c0 = 0; c0 < sb;) {
             int64_t cb = std::min<int64_t>(sub, sb - c0);
@@ -774,7 +804,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 cg.ksplit = 1; cg.replicate_stride_rows = n; cg.replicate_stride_nan = n;
                 if ((rc = gj_fused_launch(ctx, job->gomf.as<float>() + (size_t)c0 * job->n_pad * job->g_pad, job->n_pad * job->g_pad, n,
                                           job->n_pad, g, job->g_pad, cb, job->need_p ? &cp : nullptr, &cg, job->scheme, job->power,
-                                          job->out_kind, dev_ring + slot * n * n, n * n))) return rc;
+                                          job->out_kind, dev_ring + slot * n * n, n * n, 1))) return rc;
             } else {
                 if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
                                               dev_ring + slot * n * n, n * n))) return rc;

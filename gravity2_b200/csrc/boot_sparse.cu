@@ -59,6 +59,12 @@ __host__ __device__ inline void bs_tile_coords(long long t, int nt, int* bi, int
     *bj = r + (int)(t - ((long long)r * nt - (long long)r * (r - 1) / 2));
 }
 
+// exact integer limb sums -> fp64, with explicitly rounded operations so that every kernel (on-the-fly, streaming, row sums)
+// produces the same bits from the same integers (duplicate genomes: pair sum == row sum exactly)
+__device__ __forceinline__ double bs_to_double(unsigned long long hi, unsigned long long lo, double q_hi, double quantum) {
+    return __fma_rn((double)hi, q_hi, __dmul_rn((double)lo, quantum));
+}
+
 struct BsCsr {
     const long long* ptr;     // [n_pad + 1]
     const int* col;           // [nnz] ascending within a row
@@ -252,8 +258,8 @@ boot_sparse_kernel(BsCsr csr, int nt, long long tile_begin, const uint8_t* __res
                     double* o = wsblk + (size_t)rep0 * ws_rep_stride + ((ra + r) << 4);
 #pragma unroll
                     for (int a = 0; a < 16; a += 2) {
-                        double v0 = (double)ahi[a] * q_hi + (double)alo[a] * quantum;
-                        double v1 = (double)ahi[a + 1] * q_hi + (double)alo[a + 1] * quantum;
+                        double v0 = bs_to_double(ahi[a], alo[a], q_hi, quantum);
+                        double v1 = bs_to_double(ahi[a + 1], alo[a + 1], q_hi, quantum);
                         if (!first) {
                             const double2 p = *reinterpret_cast<const double2*>(o + a);
                             v0 += p.x; v1 += p.y;
@@ -285,11 +291,12 @@ boot_sparse_kernel(BsCsr csr, int nt, long long tile_begin, const uint8_t* __res
 // per SM instead of two and has no barriers at all.
 //   rows:   one per (16 x 16 block, i-row): rowptr[row] = first entry; pend[row][jj] = end of pair (i, jj)'s list
 //           relative to rowptr[row] (lists back to back, each padded to a multiple of 4 entries with zero entries)
-//   entry:  x = column | low limb << 16 (needs k_pad <= 65536), y = high limb
+//   entries: 8 bytes each, stored as planar GROUPS of four (32 bytes): uint16 column x 4 (needs k_pad <= 65536), then
+//           byte k (k = 0..5) of the four 48-bit values as one 32-bit word each
 struct BsLists {
-    long long* rowptr = nullptr;   // [nrows + 1]
+    long long* rowptr = nullptr;   // [nrows + 1], in entries (multiples of 4)
     uint32_t* pend = nullptr;      // [nrows][16]
-    uint2* ent = nullptr;          // [rowptr[nrows]]
+    uint8_t* ent = nullptr;        // [rowptr[nrows] * 8]
     long long nrows = 0, nent = 0;
     size_t bytes = 0;
 };
@@ -300,7 +307,7 @@ struct BsLists {
 template <bool FILL>
 __global__ void __launch_bounds__(BS_THREADS, 1)
 bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowtot, const long long* __restrict__ rowptr,
-                      uint32_t* __restrict__ pend, uint2* __restrict__ ent) {
+                      uint32_t* __restrict__ pend, uint8_t* __restrict__ ent) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t* mask32 = (uint32_t*)smem;                              // [k_pad / 2]
     int* jcol = (int*)(smem + (size_t)k_pad * 2);                    // [16][BS_JCAP]
@@ -355,7 +362,13 @@ bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowt
                     const unsigned long long f = min(fi, fj);
                     const int q = ii * 16 + jj;
                     const long long at = rbase + (jj ? pend[(row0 + ii) * 16 + jj - 1] : 0u) + atomicAdd(&fillc[q], 1);
-                    ent[at] = make_uint2((uint32_t)c | ((uint32_t)(f & 0xffffu) << 16), (uint32_t)(f >> BS_LO_BITS));
+                    // planar group of four entries (32 bytes): four uint16 columns, then six words holding byte k of the
+                    // four 48-bit values (the operand layout of the dp4a in the streaming kernel)
+                    uint8_t* gp = ent + (at >> 2) * 32;
+                    const int slot = (int)(at & 3);
+                    reinterpret_cast<uint16_t*>(gp)[slot] = (uint16_t)c;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) gp[8 + 4 * k + slot] = (uint8_t)(f >> (8 * k));
                 }
             }
         }
@@ -372,106 +385,188 @@ bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowt
         }
         pend[(row0 + ii) * 16 + jj] = (uint32_t)v;
         if (jj == 15) rowtot[row0 + ii] = v;
-    } else {
-        // zero entries up to the padded end of every list
-        const int ii = tid >> 4, jj = tid & 15;
-        const long long rbase = rowptr[row0 + ii];
-        const uint32_t beg = jj ? pend[(row0 + ii) * 16 + jj - 1] : 0u, end = pend[(row0 + ii) * 16 + jj];
-        for (uint32_t k = beg + (uint32_t)fillc[tid]; k < end; ++k) ent[rbase + k] = make_uint2(0u, 0u);
     }
+    // (FILL: the entry buffer was zeroed before the launch, so the padding of every list is already (column 0, value 0))
 }
 
-// Streams the precomputed lists.  Lane = FOUR replicates (one 4-byte load of the transposed multiplicities per entry
-// serves four multiply-adds: the kernel is bound by the number of global-memory instructions, `lg_throttle`), slot s
-// takes i-rows s, s + PP, ... of the block and walks the row's 16 lists in four groups of four pairs; 4 pairs x 4
-// replicates of accumulators per thread, results leave as whole 32-byte sectors.
-// grid = (64 sub-blocks, tiles, replicate blocks of 4 RL)
-#define BSL_MAC(A, E, W)                                                       \
-    do {                                                                       \
-        const uint32_t l16_ = (E).x >> 16;                                     \
-        hi[A][0] += (unsigned long long)(E).y * ((W) & 0xffu);                \
-        hi[A][1] += (unsigned long long)(E).y * (((W) >> 8) & 0xffu);         \
-        hi[A][2] += (unsigned long long)(E).y * (((W) >> 16) & 0xffu);        \
-        hi[A][3] += (unsigned long long)(E).y * ((W) >> 24);                  \
-        lo[A][0] += l16_ * ((W) & 0xffu);                                      \
-        lo[A][1] += l16_ * (((W) >> 8) & 0xffu);                               \
-        lo[A][2] += l16_ * (((W) >> 16) & 0xffu);                              \
-        lo[A][3] += l16_ * ((W) >> 24);                                        \
-    } while (0)
+// Streams the precomputed lists: S[b][i][j] = sum over the pair's list of value x multiplicity, for 128 replicates per
+// warp (lane = four replicates).  Everything the arithmetic waits for arrives asynchronously, per warp, with no block
+// barrier anywhere:
+//   lists    cp.async (LDGSTS) 8 bytes per lane, chunks of four groups (16 entries, 128 bytes), two chunks ahead;
+//   weights  per entry the 128 multiplicity bytes of the warp's replicates, gathered by column from the transposed
+//            table wT[c][replicate] with cp.async 16 bytes per lane (eight lanes per entry, four entries per
+//            instruction), one chunk ahead -- the dependent list -> column -> multiplicity chain of the previous
+//            kernel (two L2 latencies per step and warp) is off the critical path;
+//   math     per group of four entries: the 4 x 4 multiplicity bytes are transposed in registers (8 PRMT) and each of the
+//            six value-byte planes is one dp4a per replicate (24 dp4a for 16 products); plane sums stay in 32-bit integers
+//            (<= 255 * sum_c w_c <= 2^24) and are recombined into the same high / low limbs as before, so the results are
+//            bit-identical to the on-the-fly kernel's.
+// A warp owns 16 / RG consecutive i-rows of a 16 x 16 pair block (their lists are contiguous) for its 128 replicates;
+// block = RW replicate warps x RG row groups (RW * RG = 8).  grid = (64 sub-blocks, tiles, replicate blocks of 128 RW)
+#define BSS_CH 4                                     // groups per chunk
+#define BSS_LIST_BYTES (BSS_CH * 32)                 // 128
+#define BSS_W_BYTES (BSS_CH * 4 * 128)               // 2048
+#define BSS_WARP_BYTES (3 * BSS_LIST_BYTES + 2 * BSS_W_BYTES)
 
-template <int RL>
+__device__ __forceinline__ void bss_cp_async8(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void bss_cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void bss_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void bss_wait2() { asm volatile("cp.async.wait_group 2;\n" ::: "memory"); }
+__device__ __forceinline__ void bss_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+
+template <int RW>
 __global__ void __launch_bounds__(BS_THREADS, 2)
-boot_sparse_lists_kernel(const long long* __restrict__ rowptr, const uint32_t* __restrict__ pend, const uint2* __restrict__ ent,
-                         int nt, const uint8_t* __restrict__ wT, long long w_ld, int nb_total, long long ws_rep_stride,
-                         double quantum, double* __restrict__ ws) {
-    constexpr int PP = BS_THREADS / RL;
-    const int tid = threadIdx.x;
+boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* __restrict__ pend, const uint8_t* __restrict__ ent,
+                          int nt, long long tile_begin, const uint8_t* __restrict__ wT, long long w_ld, int nb_total,
+                          long long ws_rep_stride, double quantum, double* __restrict__ ws) {
+    constexpr int RG = 8 / RW;                       // row groups per block
+    constexpr int NR = 16 / RG;                      // i-rows per warp
+    __shared__ __align__(16) uint8_t smem[8 * BSS_WARP_BYTES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rw = warp % RW, rg = warp / RW;
     const int sub = blockIdx.x, si = sub >> 3, sj = sub & 7;
     int bi, bj;
-    bs_tile_coords(blockIdx.y, nt, &bi, &bj);
-    if (bi == bj && si > sj) return;
-    const int slot = tid / RL, rl = tid % RL;
-    const int rep0 = blockIdx.z * (4 * RL) + 4 * rl;                 // this lane's first replicate
-    const long long row0 = ((long long)blockIdx.y * 64 + sub) * 16;
+    bs_tile_coords(tile_begin + blockIdx.y, nt, &bi, &bj);
+    if (bi == bj && si > sj) return;                 // block entirely below the diagonal (never read)
+    uint8_t* lbuf = smem + warp * BSS_WARP_BYTES;    // three list chunks
+    uint8_t* wbuf = lbuf + 3 * BSS_LIST_BYTES;       // two chunks of multiplicities: [entry][128 replicates]
+    const long long row_first = ((tile_begin + blockIdx.y) * 64 + sub) * 16 + rg * NR;
+    const long long e_begin = rowptr[row_first];
+    const int ngroups = (int)((rowptr[row_first + NR] - e_begin) >> 2);
+    const uint8_t* gsrc = ent + e_begin * 8;
+    const long long repw = ((long long)blockIdx.z * RW + rw) * 128;      // first replicate of this warp
+    const int rep0 = (int)repw + 4 * lane;                               // first replicate of this lane
+    const uint8_t* wsrc = wT + repw + 16 * (lane & 7);
+    const int esub = lane >> 3;                      // entry of a group this lane gathers for
     double* wsblk = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + (size_t)(((si << 3) + sj) << 8);
     const double q_hi = quantum * 65536.0;
-    const uint8_t* wTl = wT + rep0;
-    const uint32_t wld32 = (uint32_t)w_ld;
-    for (int r = slot; r < 16; r += PP) {
-        const uint2* list = ent + rowptr[row0 + r];
-        const uint4* pe4 = reinterpret_cast<const uint4*>(pend + (row0 + r) * 16);
-        uint32_t beg = 0;
+    const int nchunks = (ngroups + BSS_CH - 1) / BSS_CH;
+
+    auto issue_list = [&](int c) {
+        if (lane < 16 && c * BSS_CH + (lane >> 2) < ngroups)
+            bss_cp_async8(lbuf + (c % 3) * BSS_LIST_BYTES + 8 * lane, gsrc + (size_t)c * BSS_LIST_BYTES + 8 * lane);
+        bss_commit();
+    };
+    auto issue_weights = [&](int c) {
+        const uint8_t* ls = lbuf + (c % 3) * BSS_LIST_BYTES;
+        uint8_t* wd = wbuf + (c & 1) * BSS_W_BYTES + esub * 128 + 16 * (lane & 7);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const uint4 pe = __ldg(pe4 + g);                         // ends of the group's four lists
-            const uint32_t end = pe.w;
-            unsigned long long hi[4][4];
-            uint32_t lo[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { hi[a][k] = 0ull; lo[a][k] = 0u; }
-            uint32_t w4[4];
-            uint32_t e = beg;
-            if (e < end) {
-                const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(list + e)), p1 = __ldg(reinterpret_cast<const uint4*>(list + e + 2));
-                w4[0] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (p0.x & 0xffffu) * wld32));
-                w4[1] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (p0.z & 0xffffu) * wld32));
-                w4[2] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (p1.x & 0xffffu) * wld32));
-                w4[3] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (p1.z & 0xffffu) * wld32));
+        for (int k = 0; k < BSS_CH; ++k)
+            if (c * BSS_CH + k < ngroups) {
+                const unsigned col = *reinterpret_cast<const uint16_t*>(ls + 32 * k + 2 * esub);
+                bss_cp_async16(wd + k * 512, wsrc + (size_t)col * (size_t)w_ld);
             }
+        bss_commit();
+    };
+
+    // pair bookkeeping: pair f = row * 16 + j of the warp's NR rows ends (in groups, relative to the warp's stream) at
+    // ends[f >> 5] of lane f & 31 -- loaded once, so that no global load sits on the flush path
+    constexpr int NE = NR >= 2 ? NR / 2 : 1;
+    int ends[NE];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const uint32_t ne = a == 0 ? pe.x : a == 1 ? pe.y : a == 2 ? pe.z : pe.w;
-                for (; e < ne; e += 4) {                               // lists are padded: a whole step belongs to one pair
-                    const uint32_t w0 = w4[0], w1 = w4[1], w2 = w4[2], w3 = w4[3];
-                    const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(list + e)), c1 = __ldg(reinterpret_cast<const uint4*>(list + e + 2));
-                    if (e + 4 < end) {
-                        const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(list + e + 4)), n1 = __ldg(reinterpret_cast<const uint4*>(list + e + 6));
-                        w4[0] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (n0.x & 0xffffu) * wld32));
-                        w4[1] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (n0.z & 0xffffu) * wld32));
-                        w4[2] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (n1.x & 0xffffu) * wld32));
-                        w4[3] = __ldg(reinterpret_cast<const uint32_t*>(wTl + (n1.z & 0xffffu) * wld32));
-                    }
-                    const uint2 e0 = make_uint2(c0.x, c0.y), e1 = make_uint2(c0.z, c0.w), e2 = make_uint2(c1.x, c1.y), e3 = make_uint2(c1.z, c1.w);
-                    BSL_MAC(a, e0, w0);
-                    BSL_MAC(a, e1, w1);
-                    BSL_MAC(a, e2, w2);
-                    BSL_MAC(a, e3, w3);
+    for (int q = 0; q < NE; ++q) {
+        const int f = 32 * q + lane;
+        const long long rr = row_first + (f >> 4);
+        ends[q] = f < NR * 16 ? (int)((rowptr[rr] - e_begin) >> 2) + (int)(pend[rr * 16 + (f & 15)] >> 2) : 0x7fffffff;
+    }
+    auto end_of = [&](int f) -> int {
+        int v = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < NE; ++q) {
+            const int u = __shfl_sync(0xffffffffu, ends[q], f & 31);
+            if ((f >> 5) == q) v = u;
+        }
+        return v;
+    };
+    int pf = 0;                                      // current pair of the warp: row = pf >> 4, j = pf & 15
+    int pair_end = end_of(0);
+    unsigned acc[6][4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[k][r] = 0u;
+    double res[4][4];                                // [pair & 3][replicate]: four pairs leave as whole 32-byte sectors
+    auto flush_pair = [&]() {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            // planes 2..5 are the high 32-bit limb, planes 0..1 the low 16-bit limb of the 48-bit values
+            unsigned long long hi = (unsigned long long)acc[2][r] + ((unsigned long long)acc[3][r] << 8) +
+                                    ((unsigned long long)acc[4][r] << 16) + ((unsigned long long)acc[5][r] << 24);
+            const unsigned lo = acc[0][r] + (acc[1][r] << 8);            // <= 255 * 65536 * 257 < 2^32
+            const double v = bs_to_double(hi, lo, q_hi, quantum);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if ((pf & 3) == q) res[q][r] = v;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[k][r] = 0u;
+        }
+        if ((pf & 3) == 3) {
+            const int ii = rg * NR + (pf >> 4);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (rep0 + r < nb_total) {
+                    double* o = wsblk + (size_t)(rep0 + r) * ws_rep_stride + (ii << 4) + (pf & 12);
+                    *reinterpret_cast<double2*>(o) = make_double2(res[0][r], res[1][r]);
+                    *reinterpret_cast<double2*>(o + 2) = make_double2(res[2][r], res[3][r]);
                 }
             }
-            beg = end;
+        }
+        ++pf;
+        pair_end = pf < NR * 16 ? end_of(pf) : 0x7fffffff;
+    };
+
+    if (nchunks > 0) {
+        issue_list(0);
+        issue_list(1);
+        bss_wait1();
+        __syncwarp();
+        issue_weights(0);
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        issue_list(c + 2);
+        bss_wait2();                                 // list chunk c + 1 has landed
+        __syncwarp();
+        issue_weights(c + 1);
+        bss_wait2();                                 // multiplicities of chunk c have landed
+        __syncwarp();
+        const uint8_t* ls = lbuf + (c % 3) * BSS_LIST_BYTES;
+        const uint8_t* wl = wbuf + (c & 1) * BSS_W_BYTES + 4 * lane;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (rep0 + k >= nb_total) break;
-                double* o = wsblk + (size_t)(rep0 + k) * ws_rep_stride + (r << 4) + 4 * g;
-                *reinterpret_cast<double2*>(o) = make_double2((double)hi[0][k] * q_hi + (double)lo[0][k] * quantum,
-                                                              (double)hi[1][k] * q_hi + (double)lo[1][k] * quantum);
-                *reinterpret_cast<double2*>(o + 2) = make_double2((double)hi[2][k] * q_hi + (double)lo[2][k] * quantum,
-                                                                  (double)hi[3][k] * q_hi + (double)lo[3][k] * quantum);
+        for (int k = 0; k < BSS_CH; ++k) {
+            const int g = c * BSS_CH + k;
+            if (g >= ngroups) break;
+            while (g >= pair_end) flush_pair();      // warp-uniform: lists are padded, a group belongs to one pair
+            const uint4 A = *reinterpret_cast<const uint4*>(ls + 32 * k);         // columns (x, y), planes 0, 1
+            const uint4 B = *reinterpret_cast<const uint4*>(ls + 32 * k + 16);    // planes 2..5
+            const unsigned x0 = *reinterpret_cast<const unsigned*>(wl + (4 * k + 0) * 128);
+            const unsigned x1 = *reinterpret_cast<const unsigned*>(wl + (4 * k + 1) * 128);
+            const unsigned x2 = *reinterpret_cast<const unsigned*>(wl + (4 * k + 2) * 128);
+            const unsigned x3 = *reinterpret_cast<const unsigned*>(wl + (4 * k + 3) * 128);
+            // 4 x 4 byte transpose: y[r] = multiplicities of the four entries for replicate r of this lane
+            const unsigned t0 = __byte_perm(x0, x1, 0x5140), t1 = __byte_perm(x2, x3, 0x5140);
+            const unsigned t2 = __byte_perm(x0, x1, 0x7362), t3 = __byte_perm(x2, x3, 0x7362);
+            unsigned y[4];
+            y[0] = __byte_perm(t0, t1, 0x5410); y[1] = __byte_perm(t0, t1, 0x7632);
+            y[2] = __byte_perm(t2, t3, 0x5410); y[3] = __byte_perm(t2, t3, 0x7632);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[0][r] = __dp4a(A.z, y[r], acc[0][r]);
+                acc[1][r] = __dp4a(A.w, y[r], acc[1][r]);
+                acc[2][r] = __dp4a(B.x, y[r], acc[2][r]);
+                acc[3][r] = __dp4a(B.y, y[r], acc[3][r]);
+                acc[4][r] = __dp4a(B.z, y[r], acc[4][r]);
+                acc[5][r] = __dp4a(B.w, y[r], acc[5][r]);
             }
         }
+        __syncwarp();                                // every lane is done with the slots the next iteration overwrites
     }
+    while (pf < NR * 16) flush_pair();               // the remaining (possibly empty) pairs of the warp's rows
 }
 
 // ---------------------------------------------------------------------------------- CSR of the fixed-point table
@@ -570,6 +665,21 @@ __global__ void bs_wsum_check_kernel(const int* __restrict__ w, long long k, int
     }
 }
 
+// Row sums sum_c x_ic of the fixed-point image = the diagonal pair sums under all-ones multiplicities, from the CSR:
+// one warp per row.  grid = ceil(n / 8), block = 256
+__global__ void bs_rowsums_kernel(BsCsr csr, long long n, double quantum, double* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    unsigned long long hi = 0ull, lo = 0ull;
+    for (long long e = csr.ptr[r] + lane; e < csr.ptr[r + 1]; e += 32) { hi += csr.hi[e]; lo += csr.lo[e]; }
+    for (int o = 16; o > 0; o >>= 1) {
+        hi += __shfl_xor_sync(0xffffffffu, hi, o);
+        lo += __shfl_xor_sync(0xffffffffu, lo, o);
+    }
+    if (lane == 0) out[r] = bs_to_double(hi, lo, quantum * 65536.0, quantum);
+}
+
 // ---------------------------------------------------------------------------------- host
 struct BootSparse {
     long long* ptr = nullptr;
@@ -592,6 +702,14 @@ void boot_sparse_free(BootSparse* s) {
 }
 
 size_t boot_sparse_bytes(const BootSparse* s) { return s ? s->bytes : 0; }
+int boot_sparse_has_lists(const BootSparse* s) { return s && s->lists.rowptr ? 1 : 0; }
+int boot_sparse_rowsums(gv2_ctx* ctx, const BootSparse* s, int64_t n, double* out) {
+    if (n == 0) return GV2_OK;
+    BsCsr csr{s->ptr, s->col, s->hi, s->lo};
+    bs_rowsums_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(csr, n, s->quantum, out);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
 long long boot_sparse_nnz(const BootSparse* s) { return s ? s->nnz : 0; }
 unsigned long long boot_sparse_cells(const BootSparse* s) { return s ? s->cells : 0; }
 
@@ -700,7 +818,8 @@ int boot_sparse_build_lists(gv2_ctx* ctx, BootSparse* s, size_t budget) {
         cudaFree(rowtot); cudaFree(tmp); cudaFree(L.rowptr); cudaFree(L.pend);
         return GV2_OK;
     }
-    if ((e = cudaMalloc((void**)&L.ent, (size_t)std::max<long long>(1, L.nent) * sizeof(uint2))) != cudaSuccess) return fail(e, "entries");
+    if ((e = cudaMalloc((void**)&L.ent, (size_t)std::max<long long>(4, L.nent) * 8)) != cudaSuccess) return fail(e, "entries");
+    if ((e = cudaMemsetAsync(L.ent, 0, (size_t)std::max<long long>(4, L.nent) * 8, ctx->stream)) != cudaSuccess) return fail(e, "entries");
     bs_lists_build_kernel<true><<<grid, BS_THREADS, smem, ctx->stream>>>(csr, (int)nt, (int)k_pad, nullptr, L.rowptr, L.pend, L.ent);
     ctx->launches++;
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return fail(e, "fill pass");
@@ -717,9 +836,10 @@ static int64_t bs_wld(int64_t nb) {
     return (nb + per - 1) / per * per;
 }
 // the streaming (precomputed lists) kernel: four replicates per lane
-static int bsl_lanes(int64_t nb) { return nb <= 256 ? 64 : nb <= 512 ? 128 : 256; }
+// the streaming (precomputed lists) kernel: RW warps of 128 replicates per block
+static int bss_rw(int64_t nb) { return nb <= 128 ? 1 : nb <= 256 ? 2 : nb <= 512 ? 4 : 8; }
 static int64_t bsl_wld(int64_t nb) {
-    const int64_t per = 4 * bsl_lanes(nb);
+    const int64_t per = 128 * bss_rw(nb);
     return (nb + per - 1) / per * per;
 }
 size_t boot_sparse_scratch_bytes(int64_t k_pad, int64_t nb) { return (size_t)k_pad * std::max(bs_wld(nb), bsl_wld(nb)); }
@@ -732,14 +852,12 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
                        double* ws) {
     const int64_t ntl = tile_end - tile_begin;
     if (ntl <= 0 || nb <= 0) return GV2_OK;
-    const bool use_lists = s->lists.rowptr && tile_begin == 0 && ntl == (n_pad / GV2_TILE) * (n_pad / GV2_TILE + 1) / 2;
-    const int rl = use_lists ? bsl_lanes(nb) : bs_lanes(nb);
+    const bool use_lists = s->lists.rowptr != nullptr;
+    const int rl = bs_lanes(nb);
     const int64_t w_ld = use_lists ? bsl_wld(nb) : bs_wld(nb);
     uint8_t* wT = (uint8_t*)wT_scratch;
     dim3 gt((unsigned)((k_pad + 31) / 32), (unsigned)((w_ld + 31) / 32)), bt(32, 8);
     bs_weights_transpose_kernel<<<gt, bt, 0, ctx->stream>>>(w, nb, k, k_pad, w_ld, wT, overflow_flag);
-    GV2_LAUNCH_CHECK(ctx);
-    bs_wsum_check_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(w, k, overflow_flag);
     GV2_LAUNCH_CHECK(ctx);
     if (!(ctx->smem_attr_done & GV2_ATTR_SPARSE)) {
         const int mx = (int)bs_smem_bytes(BS_WIN);
@@ -751,16 +869,19 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     Gv2Timer timer(ctx, GV2_TIME_PAIRSUMS);
     timer.begin();
     const long long rep_stride_l = (long long)ntl * GV2_TILE * GV2_TILE;
-    if (use_lists) {
+    if (use_lists) {                                 // (the lists exist only when all tiles fit one grid: ntl <= 65535)
         const BsLists& L = s->lists;
-        dim3 gl(64, (unsigned)ntl, (unsigned)(w_ld / (4 * rl)));
+        const int rwp = bss_rw(nb);
+        dim3 gl(64, (unsigned)ntl, (unsigned)(w_ld / (128 * rwp)));
         const int ntt = (int)(n_pad / GV2_TILE);
-        if (rl == 64)
-            boot_sparse_lists_kernel<64><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
-        else if (rl == 128)
-            boot_sparse_lists_kernel<128><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+        if (rwp == 1)
+            boot_sparse_stream_kernel<1><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+        else if (rwp == 2)
+            boot_sparse_stream_kernel<2><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+        else if (rwp == 4)
+            boot_sparse_stream_kernel<4><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
         else
-            boot_sparse_lists_kernel<256><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+            boot_sparse_stream_kernel<8><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
         GV2_LAUNCH_CHECK(ctx);
         timer.end();
         return GV2_OK;

@@ -102,6 +102,10 @@ __device__ __forceinline__ double gj_rcp(double x) {
     return r * sc;
 }
 
+__device__ __forceinline__ void gj_mad1(unsigned& acc, unsigned m, unsigned one) {
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(m), "r"(one));
+}
+
 __device__ __forceinline__ double gj_ratio(double smin, double si, double sj, bool diag, bool isnan_row) {
     if (diag) smin = si;                           // diagonal: sum(min) == sum(a) exactly
     const double smax = si + sj - smin;
@@ -256,8 +260,15 @@ gj_min_tile_kernel(const float* __restrict__ tab, long long tab_stride, int ld, 
 #define GF_STAGE_FLOATS ((GV2_TILE + 64) * GJ_LDS)
 static size_t gf_smem_bytes() { return (size_t)GF_STAGES * GF_STAGE_FLOATS * sizeof(float); }
 
+// FIXED == false: fp32 table, fp32 slab sums promoted to fp64 (any table).  FIXED == true: the table holds unsigned fixed-point
+// integers whose row sums fit 32 bits (the job's GOM signature tables, values in [0, 1] scaled by 2^s): integer min + integer
+// add are exact, so there is no slab promotion, no fp64 running sum -- 64 registers less per thread, which pays for loading
+// all 32 PPHMM pair sums of the thread in one batch -- and duplicate genomes give exactly S = 1.  The add is written as a
+// multiply-add by `one` (a kernel argument equal to 1) so that it issues on the FMA pipe (IMAD) while the min issues on the ALU
+// pipe: one instruction per pipe and cell, as in the fp32 variant (FMNMX + FADD).
+template <bool FIXED>
 __global__ void __launch_bounds__(GJ_THREADS, 2)
-gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int nkb, int k_groups, int nt, const GjFuse fz) {
+gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int nkb, int k_groups, int nt, const GjFuse fz, unsigned one) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
@@ -287,16 +298,28 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
     };
 
     float acc[8][4];
+    unsigned iacc[8][4];
     double sum[8][4];
 #pragma unroll
     for (int m = 0; m < 8; ++m)
 #pragma unroll
-        for (int n = 0; n < 4; ++n) { acc[m][n] = 0.f; sum[m][n] = 0.0; }
+        for (int n = 0; n < 4; ++n) { acc[m][n] = 0.f; iacc[m][n] = 0u; sum[m][n] = 0.0; }
 
 #pragma unroll
     for (int s = 0; s < GF_STAGES - 1; ++s) {
         if (s < nkb) load_stage(s, s);
         cp_async_commit();
+    }
+    if (fz.P.ws != nullptr) {
+        // the 64 KB of PPHMM pair sums this CTA reads in its epilogue: pull them into L2 now, under the main loop
+        // (element (r, c) of the tile is at [r/16][c/16][r%16][c%16]: per r/16 the CTA's half is 8 KB contiguous)
+        const double* pw = fz.P.ws + b * fz.P.b_stride_ws + t * (long long)(GV2_TILE * GV2_TILE);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int line = tid + q * GJ_THREADS;                    // 512 lines of 128 bytes
+            const double* a = pw + (size_t)(line >> 6) * 2048 + (size_t)half * 1024 + (size_t)(line & 63) * 16;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
     }
     int in_slab = 0;
     for (int it = 0; it < nkb; ++it) {
@@ -321,14 +344,25 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
                 const float4 af = *reinterpret_cast<const float4*>(a + m * 16 * GJ_LDS + kg * 4);
 #pragma unroll
                 for (int n = 0; n < 4; ++n) {
-                    const float s0 = fminf(af.x, bf[n].x) + fminf(af.y, bf[n].y);
-                    const float s1 = fminf(af.z, bf[n].z) + fminf(af.w, bf[n].w);
-                    acc[m][n] += s0 + s1;
+                    if (FIXED) {
+                        // one min (ALU pipe) + one multiply-add by 1 (FMA pipe) per cell; written as PTX so that the four
+                        // adds are not re-associated into 3-input integer adds, which issue on the ALU pipe as well
+                        unsigned v = iacc[m][n];
+                        gj_mad1(v, min(__float_as_uint(af.x), __float_as_uint(bf[n].x)), one);
+                        gj_mad1(v, min(__float_as_uint(af.y), __float_as_uint(bf[n].y)), one);
+                        gj_mad1(v, min(__float_as_uint(af.z), __float_as_uint(bf[n].z)), one);
+                        gj_mad1(v, min(__float_as_uint(af.w), __float_as_uint(bf[n].w)), one);
+                        iacc[m][n] = v;
+                    } else {
+                        const float s0 = fminf(af.x, bf[n].x) + fminf(af.y, bf[n].y);
+                        const float s1 = fminf(af.z, bf[n].z) + fminf(af.w, bf[n].w);
+                        acc[m][n] += s0 + s1;
+                    }
                 }
             }
         }
         in_slab += GV2_BK;
-        if (in_slab >= GF_SLAB || it + 1 == nkb) {            // fp32 slab totals -> fp64 running sums (registers)
+        if (!FIXED && (in_slab >= GF_SLAB || it + 1 == nkb)) {            // fp32 slab totals -> fp64 running sums (registers)
 #pragma unroll
             for (int m = 0; m < 8; ++m)
 #pragma unroll
@@ -365,8 +399,17 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
     auto rows = [&](auto fast_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
         double* orow = o + ((long long)bi * GV2_TILE + ty) * n + (long long)bj * GV2_TILE + half * 64 + tx;
+        // FIXED frees the registers of the fp64 running sums: all 32 pair sums of the thread are requested at once (one
+        // memory latency for the whole epilogue instead of one per row group)
+        double pall[FIXED && FAST ? 4 : 1][4];
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
+            if (FIXED && FAST && has_p && (m & 3) == 0) {              // 16 pair sums per batch, two batches
+#pragma unroll
+                for (int mm = 0; mm < 4; ++mm)
+#pragma unroll
+                    for (int nn = 0; nn < 4; ++nn) pall[mm][nn] = p_ws[(size_t)(((m + mm) * 8 + half * 4 + nn) * 256 + tid)];
+            }
             const int r = ty + 16 * m;
             const long long gi = (long long)bi * GV2_TILE + r;
             const bool oki = FAST || gi < n;
@@ -375,7 +418,9 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
             double pv[4];
 #pragma unroll
             for (int nn = 0; nn < 4; ++nn) {
-                if (FAST) {
+                if (FIXED && FAST) {
+                    pv[nn] = has_p ? pall[m & 3][nn] : 0.0;
+                } else if (FAST) {
                     pv[nn] = has_p ? p_ws[(size_t)((m * 8 + half * 4 + nn) * 256 + tid)] : 0.0;   // == gj_ws_index(r, c)
                 } else {
                     const int c = half * 64 + tx + 16 * nn;
@@ -392,7 +437,7 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
                 // (P * G) ** 0.5 (:214) as ONE reciprocal square root: sqrt(Np Ng / (Dp Dg)) = Np Ng rsqrt(Np Ng Dp Dg).
                 // N D > 0 says: sum(max) != 0, ratio positive, nothing NaN.
                 const bool diag = !FAST && gi == gj;
-                const double ng = diag ? gsi : sum[m][nn];             // diagonal: sum(min) == sum(a) exactly
+                const double ng = diag ? gsi : (FIXED ? (double)iacc[m][nn] : sum[m][nn]);   // diagonal: sum(min) == sum(a) exactly
                 const double dg = gsi + gsj[nn] - ng;
                 const double ag = ng * dg;
                 double sv;
@@ -701,10 +746,91 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
 
 static GjComp to_comp(const gv2_gj_component* c);
 
+// GOM signature tables of a job, fp64 [nb][n][g] -> unsigned fixed point [nb][n_pad][g_pad] (zero padded) for the FIXED fused
+// tail: q = rint(x * 2^k), k the largest exponent for which every row sum of the launch still fits 32 bits
+// (2^k * max row sum + g_pad / 2 < 2^32, k <= 30; GOM signatures are distance correlations in [0, 1], so k >= 24 for
+// G <= 224 and typically 26-27).  The scale cancels in sum(min) / sum(max).  Negative entries count as 0; NaN entries are
+// stored as 0 and flag their row (as in the fp32 image).  Row sums of the quantised values are exact integers, as doubles.
+// pass 1: grid = (n, nb), block = 128: largest fp64 row sum of the launch (bits of a non-negative double order like integers)
+__global__ void gom_rowmax_kernel(const double* __restrict__ src, long long n, long long g, unsigned long long* __restrict__ maxbits) {
+    const double* p = src + ((long long)blockIdx.y * n + blockIdx.x) * g;
+    double s = 0.0;
+    for (long long c = threadIdx.x; c < g; c += blockDim.x) {
+        const double v = p[c];
+        if (v > 0.0) s += v;                         // NaN and negatives contribute nothing
+    }
+    __shared__ double red[4];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double t = red[0] + red[1] + red[2] + red[3];
+        if (t > 0.0 && t < 1e300) atomicMax(maxbits, (unsigned long long)__double_as_longlong(t));
+    }
+}
+// pass 2: grid = (n_pad, nb), block = 128
+__global__ void gom_quantize_kernel(const double* __restrict__ src, long long n, long long g, const unsigned long long* __restrict__ maxbits,
+                                    unsigned* __restrict__ dst, long long n_pad, long long g_pad, double* __restrict__ rowsum,
+                                    unsigned char* __restrict__ nanflag) {
+    const long long r = blockIdx.x, b = blockIdx.y;
+    const double mx = __longlong_as_double((long long)*maxbits) * (1.0 + 1e-9);      // fp64 row sums are rounded themselves
+    int k = 30;
+    while (k > 0 && ldexp(mx, k) + 0.5 * (double)g_pad >= 4294967295.0) --k;
+    const double scale = ldexp(1.0, k);
+    unsigned* d = dst + (b * n_pad + r) * g_pad;
+    unsigned s = 0;
+    int has_nan = 0;
+    if (r < n) {
+        const double* p = src + (b * n + r) * g;
+        for (long long c = threadIdx.x; c < g_pad; c += blockDim.x) {
+            unsigned q = 0;
+            if (c < g) {
+                const double v = p[c];
+                if (isnan(v)) has_nan = 1;
+                else if (v > 0.0) q = (unsigned)fmin(rint(v * scale), 4294967295.0);
+            }
+            d[c] = q;
+            s += q;
+        }
+    } else {
+        for (long long c = threadIdx.x; c < g_pad; c += blockDim.x) d[c] = 0u;
+    }
+    __shared__ unsigned red[4];
+    __shared__ int rnan;
+    if (threadIdx.x == 0) rnan = 0;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    if (has_nan) rnan = 1;
+    __syncthreads();
+    if (threadIdx.x == 0 && r < n) {
+        rowsum[b * n + r] = (double)(red[0] + red[1] + red[2] + red[3]);
+        nanflag[b * n + r] = (unsigned char)rnan;
+    }
+}
+
+// scratch: 8 bytes of device memory (the launch's largest row sum)
+int gom_quantize_launch(gv2_ctx* ctx, const double* tab64, int64_t n, int64_t g, int64_t nb, unsigned* dst, int64_t n_pad, int64_t g_pad,
+                        double* rowsum, uint8_t* nanflag, unsigned long long* scratch) {
+    if (nb <= 0 || n_pad == 0) return GV2_OK;
+    if (nb > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "gom_quantize_launch: nb > 65535");
+    GV2_CUDA(ctx, cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), ctx->stream));
+    if (n > 0 && g > 0) {
+        dim3 g1((unsigned)n, (unsigned)nb);
+        gom_rowmax_kernel<<<g1, 128, 0, ctx->stream>>>(tab64, n, g, scratch);
+        GV2_LAUNCH_CHECK(ctx);
+    }
+    dim3 grid((unsigned)n_pad, (unsigned)nb);
+    gom_quantize_kernel<<<grid, 128, 0, ctx->stream>>>(tab64, n, g, scratch, dst, n_pad, g_pad, rowsum, nanflag);
+    GV2_LAUNCH_CHECK(ctx);
+    return GV2_OK;
+}
+
 // Fused GOM pair sums + epilogue for replicates [0, nb): one table per replicate (tab_stride), all tiles, schemes G and PG.
+// fixed != 0: `tab` holds the unsigned fixed-point image written by gom_quantize_launch (exact integer cell arithmetic).
 int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k, int64_t k_pad, int64_t nb,
                     const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
-                    double* out, int64_t out_replicate_stride) {
+                    double* out, int64_t out_replicate_stride, int fixed) {
     if (scheme != GV2_SCHEME_G && scheme != GV2_SCHEME_PG) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: scheme %d", scheme);
     if (!tab || !comp_g || !comp_g->rowsums || !out || (k_pad % GV2_BK) || (n_pad % GV2_TILE) || k < 0 || k > k_pad ||
         (scheme == GV2_SCHEME_PG && (!comp_p || !comp_p->min_sums || !comp_p->rowsums || comp_p->ksplit != 1)))
@@ -715,7 +841,8 @@ int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t 
     const size_t smem = gf_smem_bytes();
     static_assert(GF_STAGES * GF_STAGE_FLOATS * sizeof(float) >= 64 * GJ_STAGE_LD * sizeof(double), "transpose stage must fit the ring");
     if (!(ctx->smem_attr_done & GV2_ATTR_FUSED)) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->smem_attr_done |= GV2_ATTR_FUSED;
     }
     GjFuse fz{};
@@ -728,7 +855,10 @@ int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t 
     timer.begin();
     const int k_groups = (int)((k + 3) / 4);                     // 4-column groups that hold real columns
     const int nkb = (int)((k + GV2_BK - 1) / GV2_BK);            // stages that hold real columns
-    gj_fused_kernel<<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, nkb, k_groups, (int)(n_pad / GV2_TILE), fz);
+    if (fixed)
+        gj_fused_kernel<true><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, nkb, k_groups, (int)(n_pad / GV2_TILE), fz, 1u);
+    else
+        gj_fused_kernel<false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, nkb, k_groups, (int)(n_pad / GV2_TILE), fz, 1u);
     GV2_LAUNCH_CHECK(ctx);
     timer.end();
     return GV2_OK;
@@ -740,7 +870,7 @@ extern "C" int gv2_dev_gj_fused(gv2_ctx* ctx, const float* tab, int64_t tab_repl
                                 int64_t out_replicate_stride) {
     if (!ctx) return GV2_ERR_ARG;
     return gj_fused_launch(ctx, tab, tab_replicate_stride, n, n_pad, k, k_pad, nb, comp_p, comp_g, scheme, p, out_kind, out,
-                           out_replicate_stride);
+                           out_replicate_stride, 0);
 }
 
 extern "C" int gv2_dev_gj_min_sums(gv2_ctx* ctx, const float* tab, int64_t n_pad, int64_t k_pad,
