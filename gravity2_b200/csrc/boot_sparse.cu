@@ -406,7 +406,9 @@ bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowt
 #define BSS_CH 4                                     // groups per chunk
 #define BSS_LIST_BYTES (BSS_CH * 32)                 // 128
 #define BSS_W_BYTES (BSS_CH * 4 * 128)               // 2048
-#define BSS_WARP_BYTES (3 * BSS_LIST_BYTES + 2 * BSS_W_BYTES)
+#define BSS_OUT_LD 132                               // doubles per staged pair: 128 replicates + 4 (bank spread)
+#define BSS_OUT_BYTES (8 * BSS_OUT_LD * 8)           // eight pairs (half an i-row) x 128 replicates
+#define BSS_WARP_BYTES (3 * BSS_LIST_BYTES + 2 * BSS_W_BYTES + BSS_OUT_BYTES)
 
 __device__ __forceinline__ void bss_cp_async8(void* smem, const void* gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -427,7 +429,7 @@ boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* 
                           long long ws_rep_stride, double quantum, double* __restrict__ ws) {
     constexpr int RG = 8 / RW;                       // row groups per block
     constexpr int NR = 16 / RG;                      // i-rows per warp
-    __shared__ __align__(16) uint8_t smem[8 * BSS_WARP_BYTES];
+    extern __shared__ __align__(16) uint8_t smem[];   // 8 * BSS_WARP_BYTES
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rw = warp % RW, rg = warp / RW;
     const int sub = blockIdx.x, si = sub >> 3, sj = sub & 7;
@@ -436,12 +438,12 @@ boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* 
     if (bi == bj && si > sj) return;                 // block entirely below the diagonal (never read)
     uint8_t* lbuf = smem + warp * BSS_WARP_BYTES;    // three list chunks
     uint8_t* wbuf = lbuf + 3 * BSS_LIST_BYTES;       // two chunks of multiplicities: [entry][128 replicates]
+    double* obuf = reinterpret_cast<double*>(wbuf + 2 * BSS_W_BYTES);   // [pair & 7][replicate]: results of eight pairs
     const long long row_first = ((tile_begin + blockIdx.y) * 64 + sub) * 16 + rg * NR;
     const long long e_begin = rowptr[row_first];
     const int ngroups = (int)((rowptr[row_first + NR] - e_begin) >> 2);
     const uint8_t* gsrc = ent + e_begin * 8;
     const long long repw = ((long long)blockIdx.z * RW + rw) * 128;      // first replicate of this warp
-    const int rep0 = (int)repw + 4 * lane;                               // first replicate of this lane
     const uint8_t* wsrc = wT + repw + 16 * (lane & 7);
     const int esub = lane >> 3;                      // entry of a group this lane gathers for
     double* wsblk = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + (size_t)(((si << 3) + sj) << 8);
@@ -491,31 +493,37 @@ boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* 
     for (int k = 0; k < 6; ++k)
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[k][r] = 0u;
-    double res[4][4];                                // [pair & 3][replicate]: four pairs leave as whole 32-byte sectors
+    // Results leave through shared memory: a lane owns four REPLICATES, i.e. four different 0.4 GB planes of the workspace, so
+    // storing from registers costs one memory request per lane and instruction (32 per warp store) -- the load/store unit, not
+    // HBM, was the limit.  Eight pairs (half an i-row: 64 contiguous bytes per replicate) are staged as [pair][replicate] and
+    // written by lanes (pair, replicate): four 64-byte requests per warp store.
     auto flush_pair = [&]() {
+        double v4[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             // planes 2..5 are the high 32-bit limb, planes 0..1 the low 16-bit limb of the 48-bit values
             unsigned long long hi = (unsigned long long)acc[2][r] + ((unsigned long long)acc[3][r] << 8) +
                                     ((unsigned long long)acc[4][r] << 16) + ((unsigned long long)acc[5][r] << 24);
             const unsigned lo = acc[0][r] + (acc[1][r] << 8);            // <= 255 * 65536 * 257 < 2^32
-            const double v = bs_to_double(hi, lo, q_hi, quantum);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if ((pf & 3) == q) res[q][r] = v;
+            v4[r] = bs_to_double(hi, lo, q_hi, quantum);
 #pragma unroll
             for (int k = 0; k < 6; ++k) acc[k][r] = 0u;
         }
-        if ((pf & 3) == 3) {
+        double* od = obuf + (pf & 7) * BSS_OUT_LD + 4 * lane;
+        *reinterpret_cast<double2*>(od) = make_double2(v4[0], v4[1]);
+        *reinterpret_cast<double2*>(od + 2) = make_double2(v4[2], v4[3]);
+        if ((pf & 7) == 7) {
+            __syncwarp();
             const int ii = rg * NR + (pf >> 4);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                if (rep0 + r < nb_total) {
-                    double* o = wsblk + (size_t)(rep0 + r) * ws_rep_stride + (ii << 4) + (pf & 12);
-                    *reinterpret_cast<double2*>(o) = make_double2(res[0][r], res[1][r]);
-                    *reinterpret_cast<double2*>(o + 2) = make_double2(res[2][r], res[3][r]);
-                }
+            const int pj = lane & 7;                                     // pair of the half row
+            double* o = wsblk + (ii << 4) + (pf & 8) + pj;
+            const double* os = obuf + pj * BSS_OUT_LD + (lane >> 3);
+#pragma unroll 4
+            for (int it = 0; it < 32; ++it) {
+                const long long rep = repw + 4 * it + (lane >> 3);
+                if (rep < nb_total) o[(size_t)rep * ws_rep_stride] = os[4 * it];
             }
+            __syncwarp();
         }
         ++pf;
         pair_end = pf < NR * 16 ? end_of(pf) : 0x7fffffff;
@@ -872,16 +880,24 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     if (use_lists) {                                 // (the lists exist only when all tiles fit one grid: ntl <= 65535)
         const BsLists& L = s->lists;
         const int rwp = bss_rw(nb);
+        const size_t ssm = (size_t)8 * BSS_WARP_BYTES;
+        if (!(ctx->smem_attr_done & GV2_ATTR_STREAM)) {
+            GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+            GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+            GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_stream_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+            GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+            ctx->smem_attr_done |= GV2_ATTR_STREAM;
+        }
         dim3 gl(64, (unsigned)ntl, (unsigned)(w_ld / (128 * rwp)));
         const int ntt = (int)(n_pad / GV2_TILE);
         if (rwp == 1)
-            boot_sparse_stream_kernel<1><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+            boot_sparse_stream_kernel<1><<<gl, BS_THREADS, ssm, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
         else if (rwp == 2)
-            boot_sparse_stream_kernel<2><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+            boot_sparse_stream_kernel<2><<<gl, BS_THREADS, ssm, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
         else if (rwp == 4)
-            boot_sparse_stream_kernel<4><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+            boot_sparse_stream_kernel<4><<<gl, BS_THREADS, ssm, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
         else
-            boot_sparse_stream_kernel<8><<<gl, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+            boot_sparse_stream_kernel<8><<<gl, BS_THREADS, ssm, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
         GV2_LAUNCH_CHECK(ctx);
         timer.end();
         return GV2_OK;

@@ -52,6 +52,7 @@ struct Gv2Timer {
 #define GV2_ATTR_MMA 4u
 #define GV2_ATTR_SPARSE 8u
 #define GV2_ATTR_POPC 16u
+#define GV2_ATTR_STREAM 32u
 
 #define GV2_TILE 128          // genome-pair tile edge of the similarity kernels
 #define GV2_BK 32             // PPHMM columns staged per pipeline stage

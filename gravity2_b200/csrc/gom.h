@@ -25,18 +25,19 @@ struct GomDb {
     int* mem_ptr = nullptr; long long* mem_row = nullptr;
     int* pt_ptr = nullptr; int* pt_col = nullptr; int* pos = nullptr;
     long long* x_off = nullptr; long long* a_off = nullptr;
-    double* X = nullptr; double* nrm = nullptr; double* A = nullptr;
+    double* X = nullptr; double* nrm = nullptr; double* nrm2 = nullptr; double* A = nullptr;
     // per-chunk scratch (32 replicates)
-    double* wT = nullptr; double* arT = nullptr; double* sqT = nullptr; double* rT = nullptr;
+    double* wT = nullptr; double* arT = nullptr; double* rT = nullptr;
     double* gagg = nullptr; double* vagg = nullptr;
     unsigned char* wT8 = nullptr; double* wG = nullptr; int* flag = nullptr;   // uint8 weights, per-GOM gathered weights, flags
     long long* heavy_list = nullptr;   // (genome, GOM) pairs whose intersection list overflows the light kernel
     int n_heavy = 0;
     bool weights_validated = false;    // the caller has checked 0 <= w <= 255 for every call (device jobs): no flag read-back per call
-    // replicate-independent intersection lists I0 = R_v & R_g of every (GOM, genome) pair, built once per database:
-    // entries [is_ptr[g*n+v], is_ptr[g*n+v+1]) of is_ent, each (GOM point index k, genome hit index c)
-    long long* is_ptr = nullptr;
-    int2* is_ent = nullptr;
+    // replicate-independent pair records, genome-major (pair id = v * G + g): record of pair w at rec + pr_ptr[w] =
+    // pr_ni[w] entries of 32 bytes (GOM point, genome hit, column, |X|, y), then the lower triangle of M (doubles)
+    int* pr_ni = nullptr;
+    long long* pr_ptr = nullptr;
+    unsigned char* rec = nullptr;
 };
 
 int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t ld_loc,

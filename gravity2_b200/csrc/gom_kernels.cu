@@ -86,7 +86,7 @@ __global__ void gom_fill_kernel(const double* __restrict__ rowtab, long long ld,
                                 const int* __restrict__ flag, const int* __restrict__ scan,
                                 const long long* __restrict__ x_off, int* __restrict__ pos,
                                 int* __restrict__ pt_col, double* __restrict__ X,
-                                double* __restrict__ nrm) {
+                                double* __restrict__ nrm, double* __restrict__ nrm2) {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
     if (c >= p) return;
@@ -108,6 +108,7 @@ __global__ void gom_fill_kernel(const double* __restrict__ rowtab, long long ld,
         s += v * v;
     }
     nrm[pt] = sqrt(s);
+    nrm2[pt] = s;
 }
 
 // A_g[k][l] = |X_k - X_l|.  grid = (ceil(ng/16), ceil(ng/16), G), block (16,16)
@@ -162,18 +163,20 @@ __global__ void gom_gather_weights_kernel(const int* __restrict__ pt_col, long l
     wG[i] = wT[(long long)pt_col[i / NBC] * NBC + (i % NBC)];
 }
 
-// GA: arT[pt][b] = sum_l w_l A[k][l],  sqT[pt][b] = sum_l w_l A[k][l]^2  (per GOM a [ng x ng] x [ng x 32] product).
-// grid = (ceil(max_ng/64), G), block = (32 b, 8): the block owns 64 rows k, a thread 8 of them for its replicate lane.
-// 32 columns l at a time go through shared memory (A tile 64 x 32 read as whole 256-byte row segments, weight tile
-// 32 x 32), so the inner loop is one conflict-free LDS of the weight and eight broadcast LDS of the distances per
-// 16 FMAs instead of global loads; the sums run over l in ascending order exactly as before.
-#define GA_ROWS 64
+// GA: arT[pt][b] = sum_l w_l A[k][l]  (per GOM a [ng x ng] x [ng x 32] product; the squared-distance sums the centred
+// variance also needs do not go through this O(ng^2) loop any more: see gom_aggregates_kernel).
+// grid = (ceil(max_ng/128), G), block = (32 b, 8): the block owns 128 rows k, a thread 16 of them for its replicate lane.
+// 32 columns l at a time go through shared memory (A tile 128 x 32 read as whole 256-byte row segments, weight tile
+// 32 x 32); the distances are warp-uniform, so they are read two columns at a time (LDS.128 broadcast): per pair of
+// columns 16 + 2 shared-memory loads feed 32 DFMA -- the fp64 pipe, not the load pipe, is the limit.
+#define GA_ROWS 128
 #define GA_LC 32
+#define GA_LD (GA_LC + 2)            // even row stride: 16-byte aligned column pairs
 __global__ void __launch_bounds__(256)
 gom_rowsums_kernel(const int* __restrict__ pt_ptr, const long long* __restrict__ a_off,
                    const double* __restrict__ A, const double* __restrict__ wG,
-                   double* __restrict__ arT, double* __restrict__ sqT) {
-    __shared__ double sA[GA_ROWS][GA_LC + 1];
+                   double* __restrict__ arT) {
+    __shared__ __align__(16) double sA[GA_ROWS][GA_LD];
     __shared__ double sW[GA_LC][NBC];
     const int g = blockIdx.y;
     const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
@@ -182,14 +185,14 @@ gom_rowsums_kernel(const int* __restrict__ pt_ptr, const long long* __restrict__
     const int b = threadIdx.x, ty = threadIdx.y;
     const double* a = A + a_off[g];
     const double* w = wG + (long long)p0 * NBC;
-    double s1[8], s2[8];
+    double s1[16];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) { s1[r] = 0.0; s2[r] = 0.0; }
+    for (int r = 0; r < 16; ++r) s1[r] = 0.0;
     for (int l0 = 0; l0 < ng; l0 += GA_LC) {
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int row = ty * 8 + r, k = min(kb + row, ng - 1), l = l0 + b;
+        for (int r = 0; r < 16; ++r) {
+            const int row = ty * 16 + r, k = min(kb + row, ng - 1), l = l0 + b;
             sA[row][b] = l < ng ? a[(long long)k * ng + l] : 0.0;
         }
 #pragma unroll
@@ -198,49 +201,77 @@ gom_rowsums_kernel(const int* __restrict__ pt_ptr, const long long* __restrict__
             sW[l][b] = l0 + l < ng ? w[(long long)(l0 + l) * NBC + b] : 0.0;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int l = 0; l < GA_LC; ++l) {
-            const double wv = sW[l][b];
+#pragma unroll 4
+        for (int l = 0; l < GA_LC; l += 2) {
+            const double w0 = sW[l][b], w1 = sW[l + 1][b];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const double d = sA[ty * 8 + r][l];
-                s1[r] = fma(wv, d, s1[r]);
-                s2[r] = fma(wv * d, d, s2[r]);
+            for (int r = 0; r < 16; ++r) {
+                const double2 d = *reinterpret_cast<const double2*>(&sA[ty * 16 + r][l]);
+                s1[r] = fma(w0, d.x, s1[r]);         // columns in ascending order, as before
+                s1[r] = fma(w1, d.y, s1[r]);
             }
         }
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-        const int k = kb + ty * 8 + r;
-        if (k < ng) {
-            arT[(long long)(p0 + k) * NBC + b] = s1[r];
-            sqT[(long long)(p0 + k) * NBC + b] = s2[r];
-        }
+    for (int r = 0; r < 16; ++r) {
+        const int k = kb + ty * 16 + r;
+        if (k < ng) arT[(long long)(p0 + k) * NBC + b] = s1[r];
     }
 }
 
-// GB: per-GOM aggregates, lane = replicate.  gagg[g][q][b], q in 0..GAGG-1.  grid = G, block = 32
-#define GAGG 7   // n_g, N1, N2, AR1, AR2, ARN, SAA
-__global__ void gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ pt_col,
-                                      const double* __restrict__ nrm, const double* __restrict__ wT,
-                                      const double* __restrict__ arT, const double* __restrict__ sqT,
-                                      double* __restrict__ gagg) {
-    const int g = blockIdx.x, b = threadIdx.x;
-    double n = 0, N1 = 0, N2 = 0, AR1 = 0, AR2 = 0, ARN = 0, SAA = 0;
-    for (int pt = pt_ptr[g]; pt < pt_ptr[g + 1]; ++pt) {
-        const double w = wT[(long long)pt_col[pt] * NBC + b];
-        const double nr = nrm[pt], ar = arT[(long long)pt * NBC + b], sq = sqT[(long long)pt * NBC + b];
+// GB: per-GOM aggregates, lane = replicate.  gagg[g][q][b], q in 0..GAGG-1.  grid = G, block = 256 (8 warps).
+//   phase 1: the sums over the GOM's points (n_g, N1, N2, AR1, AR2, ARN), points dealt to the warps, reduced in shared memory;
+//   phase 2: SAA = sum_kl w_k w_l |X_k - X_l|^2 = 2 (W sum_k w_k |X_k|^2 - |sum_k w_k X_k|^2): the weighted centroid, one member
+//            coordinate per warp at a time -- O(n_g m_g) instead of the O(n_g^2) pass over the distance cache;
+//   XDEG = 1 when all drawn points coincide (the distances from the first drawn point sum to exactly 0): the reference's
+//            centred matrix is then exactly 0 (dcor.py:54-60), which the moment formula does not reproduce bit for bit.
+#define GAGG 8   // n_g, N1, N2, AR1, AR2, ARN, SAA, XDEG
+__global__ void __launch_bounds__(256)
+gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ mem_ptr, const long long* __restrict__ x_off,
+                      const double* __restrict__ X, const double* __restrict__ nrm, const double* __restrict__ nrm2,
+                      const double* __restrict__ wG, const double* __restrict__ arT, double* __restrict__ gagg) {
+    __shared__ double red[8][7][NBC];
+    const int g = blockIdx.x, b = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
+    const int mg = mem_ptr[g + 1] - mem_ptr[g];
+    double n = 0, N1 = 0, N2 = 0, AR1 = 0, AR2 = 0, ARN = 0, CS = 0;
+    for (int k = wi; k < ng; k += 8) {
+        const double w = wG[(long long)(p0 + k) * NBC + b];
+        const double nr = nrm[p0 + k], ar = arT[(long long)(p0 + k) * NBC + b];
         n += w;
         N1 = fma(w, nr, N1);
-        N2 = fma(w * nr, nr, N2);
+        N2 = fma(w, nrm2[p0 + k], N2);
         AR1 = fma(w, ar, AR1);
         AR2 = fma(w * ar, ar, AR2);
         ARN = fma(w * ar, nr, ARN);
-        SAA = fma(w, sq, SAA);
     }
-    double* o = gagg + (long long)g * GAGG * NBC + b;
-    o[0 * NBC] = n; o[1 * NBC] = N1; o[2 * NBC] = N2; o[3 * NBC] = AR1;
-    o[4 * NBC] = AR2; o[5 * NBC] = ARN; o[6 * NBC] = SAA;
+    const double* x = X + x_off[g];
+    for (int j = wi; j < mg; j += 8) {
+        double c = 0.0;
+        for (int k = 0; k < ng; ++k) c = fma(wG[(long long)(p0 + k) * NBC + b], x[(long long)k * mg + j], c);
+        CS = fma(c, c, CS);
+    }
+    red[wi][0][b] = n; red[wi][1][b] = N1; red[wi][2][b] = N2; red[wi][3][b] = AR1; red[wi][4][b] = AR2; red[wi][5][b] = ARN;
+    red[wi][6][b] = CS;
+    __syncthreads();
+    if (wi == 0) {
+        double t[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            t[q] = 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[q] += red[u][q][b];
+        }
+        // first drawn point of the replicate and its distance row sum
+        double xdeg = 1.0;
+        for (int k = 0; k < ng; ++k)
+            if (wG[(long long)(p0 + k) * NBC + b] > 0.0) { xdeg = arT[(long long)(p0 + k) * NBC + b] == 0.0 ? 1.0 : 0.0; break; }
+        double* o = gagg + (long long)g * GAGG * NBC + b;
+        o[0 * NBC] = t[0]; o[1 * NBC] = t[1]; o[2 * NBC] = t[2]; o[3 * NBC] = t[3];
+        o[4 * NBC] = t[4]; o[5 * NBC] = t[5];
+        o[6 * NBC] = xdeg != 0.0 ? 0.0 : 2.0 * (t[0] * t[2] - t[6]);
+        o[7 * NBC] = xdeg;
+    }
 }
 
 #define VAGG 8   // t, Y1, Y2, Ys, RR1, RR2, RY, YC (1 = all drawn hits share one location value): per-genome aggregates of the weighted row sums r_c = sum_d w_d |y_c - y_d|
@@ -316,34 +347,41 @@ genome_rowsums_sorted_kernel(long long n, const long long* __restrict__ ptr, con
 }
 
 // VG: score (genome, GOM) pairs; lane = replicate.  out[b][v][g].
-// The intersection list I0 = R_v & R_g (replicate independent) is staged in shared memory: y, |X| norm, GOM
-// point index, genome hit index and the 32 uint8 weights of each entry (56 bytes), so that the |I|^2 pair
-// loop reads shared memory plus one L2-resident distance-cache entry per iteration.
-//   light kernel: one WARP per pair, room for VG_LIGHT_CAP entries (the handful of PPHMMs a genome shares with
-//                 a foreign taxon) -> full occupancy; longer lists are appended to a work list instead;
-//   heavy kernel: one BLOCK per listed pair (a genome against its own taxon: |I| ~ all of its hits), the four
-//                 warps split the outer loop of the pair sums and reduce through shared memory.
+// Everything about a pair that does not depend on the replicate is computed ONCE per database and stored as the pair's
+// RECORD (genome-major: pair id = v * G + g), so that the per-chunk scoring kernels stream contiguous data instead of
+// gathering 8-byte elements from the distance cache:
+//   entries  the intersection list I = R_v & R_g, 32 bytes each: GOM point index k, genome hit index c, PPHMM column,
+//            |X_k| and the genome's (signed) location value y;
+//   M        the lower triangle (a > e, row-major) of the replicate-independent pair matrix
+//            M_ae = 2 [ d_ae (|y_a - y_e| - |y_a| - |y_e|) - (|X_a| + |X_e|) |y_a - y_e| ],  d_ae = |X_a - X_e|:
+//            the three I x I double sums of the expansion enter S_ab only as Q1 - 2 Q2 - 2 Q3 = sum_{a>e} w_a w_e M_ae.
+//   light kernel: one block per genome, its warps walk the genome's GOMs (the per-genome aggregates stay in registers, the
+//                 genome's weighted row sums stay in L1/L2); pairs with up to VG_LIGHT_CAP entries (a genome against a
+//                 foreign taxon);
+//   heavy kernel: one block per listed pair (a genome against its own taxon: |I| ~ all of its hits); the four warps split
+//                 the rows of M, each row is one coalesced read.
 #define VG_ENTRY_BYTES 56
 #define VG_LIGHT_CAP 32
-#define VG_LIGHT_BYTES (VG_LIGHT_CAP * VG_ENTRY_BYTES + VG_LIGHT_CAP * (VG_LIGHT_CAP - 1) / 2 * 8)   // entries + distance triangle
+#define VG_LIGHT_BYTES (VG_LIGHT_CAP * 32 + VG_LIGHT_CAP * (VG_LIGHT_CAP - 1) / 2 * 8 + VG_LIGHT_CAP * NBC)   // entries + M triangle + weights
 #define VG_NSUM 12
 
+struct VgEntry { int k, c, col, pad; double nr, y; };      // 32 bytes
 struct VgSums { double v[VG_NSUM]; };   // SW S_ar S_nrm S_r S_y C_arr C_ary C_nr C_ny Q1 Q2 Q3
 
 __device__ __forceinline__ double vg_finish(const VgSums& S, const double* __restrict__ ga, const double* __restrict__ va) {
     const double SW = S.v[0], S_ar = S.v[1], S_nrm = S.v[2], S_r = S.v[3], S_y = S.v[4], C_arr = S.v[5], C_ary = S.v[6],
                  C_nr = S.v[7], C_ny = S.v[8], Q1 = S.v[9], Q2 = S.v[10], Q3 = S.v[11];
-    const double n_g = ga[0], N1 = ga[NBC], N2 = ga[2 * NBC], AR1 = ga[3 * NBC], AR2 = ga[4 * NBC],
-                 ARN = ga[5 * NBC], SAA = ga[6 * NBC];
-    const double T = va[0], Y1 = va[NBC], Y2 = va[2 * NBC], Ys = va[3 * NBC], RR1 = va[4 * NBC],
-                 RR2 = va[5 * NBC], RY = va[6 * NBC];
+    const double n_g = ga[0], N1 = ga[1], N2 = ga[2], AR1 = ga[3], AR2 = ga[4], ARN = ga[5], SAA = ga[6];
+    const double T = va[0], Y1 = va[1], Y2 = va[2], Ys = va[3], RR1 = va[4], RR2 = va[5], RY = va[6];
     const double e = T - SW, z = n_g - SW, nn = n_g + e;
     double res = 0.0;
     // Exactly degenerate Y: no zero-valued point (z == 0; the counts are small integers, exact) and every drawn hit at one
     // location value.  The reference's centred matrix is then exactly 0 and it returns 0.0 (dcor.py:54-60); the un-centred
-    // expansion below would leave rounding noise in sBB instead.  (A degenerate X leaves exact zeros in every term.)
-    const bool y_degenerate = z == 0.0 && va[7 * NBC] != 0.0;
-    if (nn > 0.0 && !y_degenerate) {
+    // expansion below would leave rounding noise in sBB instead.
+    const bool y_degenerate = z == 0.0 && va[7] != 0.0;
+    // Exactly degenerate X: no point outside the GOM's column set (e == 0) and all drawn GOM points coincide.
+    const bool x_degenerate = e == 0.0 && ga[7] != 0.0;
+    if (nn > 0.0 && !y_degenerate && !x_degenerate) {
         const double Sab = 2.0 * (C_ary - Q2) + 2.0 * (N1 - S_nrm) * (Y1 - S_y) + Q1 + 2.0 * (C_nr - Q3);
         const double cross = ((AR1 - S_ar) + e * (N1 - S_nrm)) * Y1 +
                              (C_arr + z * C_ary + e * C_nr + e * z * C_ny) +
@@ -365,158 +403,175 @@ __device__ __forceinline__ double vg_finish(const VgSums& S, const double* __res
     return res;
 }
 
-// Intersection lists, built once per database (they do not depend on the replicate): one warp per (GOM, genome)
-// pair counts / writes the genome's hits that fall in the GOM's column set, column order preserved.
-// FILL == false: cnt[wid] = |I0|;  FILL == true: entries written at is_ptr[wid].  grid = ceil(n*G/8), block = 256
-template <bool FILL>
+// Pair records, pass 1: |I| of every pair.  One warp per pair, genome-major.  grid = ceil(n*G/8), block = 256
 __global__ void __launch_bounds__(256)
-gom_isect_kernel(long long n, int G, long long p, const long long* __restrict__ ptr, const int* __restrict__ col,
-                 const int* __restrict__ pos, long long* __restrict__ cnt, const long long* __restrict__ is_ptr,
-                 int2* __restrict__ is_ent) {
+gom_pair_count_kernel(long long n, int G, long long p, const long long* __restrict__ ptr, const int* __restrict__ col,
+                      const int* __restrict__ pos, int* __restrict__ ni_out, long long* __restrict__ bytes_out) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (wid >= n * G) return;
-    const int g = (int)(wid / n);
-    const long long v = wid % n;
+    const long long v = wid / G;
+    const int g = (int)(wid % G);
     const long long o = ptr[v];
     const int t = (int)(ptr[v + 1] - o);
     const int* posg = pos + (long long)g * p;
-    long long w0 = FILL ? is_ptr[wid] : 0;
     int ni = 0;
     for (int c0 = 0; c0 < t; c0 += 32) {
         const int c = c0 + lane;
-        int k = -1;
-        if (c < t) k = posg[col[o + c]];
-        const unsigned m = __ballot_sync(0xffffffffu, k >= 0);
-        if (FILL && k >= 0) is_ent[w0 + ni + __popc(m & ((1u << lane) - 1u))] = make_int2(k, c);
-        ni += __popc(m);
+        const int k = c < t ? posg[col[o + c]] : -1;
+        ni += __popc(__ballot_sync(0xffffffffu, k >= 0));
     }
-    if (!FILL && lane == 0) cnt[wid] = ni;
+    if (lane == 0) {
+        ni_out[wid] = ni;
+        bytes_out[wid] = (long long)ni * 32 + (long long)ni * (ni - 1) / 2 * 8;
+    }
+}
+
+// pass 2: entries (column order preserved) and the M triangle of every pair
+__global__ void __launch_bounds__(256)
+gom_pair_fill_kernel(long long n, int G, long long p, const long long* __restrict__ ptr, const int* __restrict__ col,
+                     const double* __restrict__ val, const int* __restrict__ pos, const int* __restrict__ pt_ptr,
+                     const double* __restrict__ nrm, const long long* __restrict__ a_off, const double* __restrict__ A,
+                     const int* __restrict__ pr_ni, const long long* __restrict__ pr_ptr, unsigned char* __restrict__ rec) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (wid >= n * G) return;
+    const int ni = pr_ni[wid];
+    if (ni == 0) return;
+    const long long v = wid / G;
+    const int g = (int)(wid % G);
+    const long long o = ptr[v];
+    const int t = (int)(ptr[v + 1] - o);
+    const int* posg = pos + (long long)g * p;
+    const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
+    VgEntry* ent = reinterpret_cast<VgEntry*>(rec + pr_ptr[wid]);
+    int at = 0;
+    for (int c0 = 0; c0 < t; c0 += 32) {
+        const int c = c0 + lane;
+        int k = -1, cc = 0;
+        if (c < t) { cc = col[o + c]; k = posg[cc]; }
+        const unsigned m = __ballot_sync(0xffffffffu, k >= 0);
+        if (k >= 0) {
+            VgEntry e;
+            e.k = k; e.c = c; e.col = cc; e.pad = 0; e.nr = nrm[p0 + k]; e.y = val[o + c];
+            ent[at + __popc(m & ((1u << lane) - 1u))] = e;
+        }
+        at += __popc(m);
+    }
+    __syncwarp();
+    double* M = reinterpret_cast<double*>(ent + ni);
+    const double* Ag = A + a_off[g];
+    const long long npair = (long long)ni * (ni - 1) / 2;
+    for (long long q = lane; q < npair; q += 32) {
+        int a = (int)((1.0 + sqrt(1.0 + 8.0 * (double)q)) * 0.5);
+        while ((long long)a * (a - 1) / 2 > q) --a;
+        while ((long long)(a + 1) * a / 2 <= q) ++a;
+        const int e = (int)(q - (long long)a * (a - 1) / 2);
+        const VgEntry ea = ent[a], ee = ent[e];
+        const double dist = Ag[(long long)ea.k * ng + ee.k];
+        const double dy = fabs(ea.y - ee.y);
+        M[q] = 2.0 * (dist * (dy - fabs(ea.y) - fabs(ee.y)) - (ea.nr + ee.nr) * dy);
+    }
 }
 
 // work list of the heavy kernel: pairs whose list does not fit the light kernel's shared-memory slots
-__global__ void gom_heavy_list_kernel(long long total, const long long* __restrict__ is_ptr, int cap,
+__global__ void gom_heavy_list_kernel(long long total, const int* __restrict__ pr_ni, int cap,
                                       long long* __restrict__ heavy_list, int* __restrict__ heavy_count) {
     const long long wid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (wid >= total) return;
-    if (is_ptr[wid + 1] - is_ptr[wid] > cap) heavy_list[atomicAdd(heavy_count, 1)] = wid;
+    if (pr_ni[wid] > cap) heavy_list[atomicAdd(heavy_count, 1)] = wid;
 }
 
-// sum over pairs of |I| (|I| - 1) / 2: the pair-sum terms one replicate costs (roofline bookkeeping)
-__global__ void gom_mentries_kernel(long long total, const long long* __restrict__ is_ptr, unsigned long long* __restrict__ out) {
-    unsigned long long s = 0;
+// sum over pairs of |I| (|I| - 1) / 2 and of |I|: the pair-sum terms one replicate costs (roofline bookkeeping)
+__global__ void gom_mentries_kernel(long long total, const int* __restrict__ pr_ni, unsigned long long* __restrict__ out) {
+    unsigned long long s = 0, e = 0;
     for (long long wid = (long long)blockIdx.x * blockDim.x + threadIdx.x; wid < total; wid += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long ni = (unsigned long long)(is_ptr[wid + 1] - is_ptr[wid]);
+        const unsigned long long ni = (unsigned long long)pr_ni[wid];
         s += ni * (ni - (ni ? 1 : 0)) / 2;
+        e += ni;
     }
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); e += __shfl_xor_sync(0xffffffffu, e, o); }
+    if ((threadIdx.x & 31) == 0) { if (s) atomicAdd(out, s); if (e) atomicAdd(out + 1, e); }
 }
 
-// load a precomputed intersection list into the staging arrays (threads tid, tid + nthreads, ...)
-__device__ __forceinline__ void vg_load(int tid, int nthreads, int ni, const int2* __restrict__ ent, long long o,
-                                        const double* __restrict__ val, const double* __restrict__ nrm, int p0,
-                                        double* sy, double* sn, int* sk, int* sc) {
-    for (int a = tid; a < ni; a += nthreads) {
-        const int2 e = ent[a];
-        sy[a] = val[o + e.y];
-        sn[a] = nrm[p0 + e.x];
-        sk[a] = e.x;
-        sc[a] = e.y;
-    }
-}
-
+// grid = n (one block per genome), block = 128 (4 warps over the genome's GOMs)
 __global__ void __launch_bounds__(128)
-gom_score_light_kernel(long long n, int G, long long p, const long long* __restrict__ ptr,
-                       const int* __restrict__ col, const double* __restrict__ val,
-                       const int* __restrict__ pt_ptr, const int* __restrict__ pos,
-                       const double* __restrict__ nrm, const long long* __restrict__ a_off,
-                       const double* __restrict__ A, const unsigned char* __restrict__ wT8,
-                       const double* __restrict__ arT, const double* __restrict__ rT,
-                       const double* __restrict__ gagg, const double* __restrict__ vagg, int nb,
-                       double* __restrict__ out, const long long* __restrict__ is_ptr, const int2* __restrict__ is_ent) {
+gom_score_light_kernel(long long n, int G, const long long* __restrict__ ptr, const int* __restrict__ pt_ptr,
+                       const int* __restrict__ pr_ni, const long long* __restrict__ pr_ptr, const unsigned char* __restrict__ rec,
+                       const unsigned char* __restrict__ wT8, const double* __restrict__ arT, const double* __restrict__ rT,
+                       const double* __restrict__ gagg, const double* __restrict__ vagg, int nb, double* __restrict__ out) {
     __shared__ __align__(16) unsigned char smem[4 * VG_LIGHT_BYTES];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const long long wid = (long long)blockIdx.x * 4 + wib;
-    if (wid >= n * G) return;
-    // GOM-major order keeps one GOM's distance cache hot in L2 while all genomes are scored
-    const int g = (int)(wid / n);
-    const long long v = wid % n;
+    const long long v = blockIdx.x;
     const long long o = ptr[v];
-    const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
     unsigned char* base = smem + wib * VG_LIGHT_BYTES;
-    double* sy = reinterpret_cast<double*>(base);
-    double* sn = sy + VG_LIGHT_CAP;
-    double* sd = sn + VG_LIGHT_CAP;                                      // [a (a - 1) / 2 + e], e < a: |X_a - X_e|
-    int* sk = reinterpret_cast<int*>(sd + VG_LIGHT_CAP * (VG_LIGHT_CAP - 1) / 2);
-    int* sc = sk + VG_LIGHT_CAP;
-    unsigned char* sw = reinterpret_cast<unsigned char*>(sc + VG_LIGHT_CAP);
-    const long long e0 = is_ptr[wid];
-    const int ni = (int)(is_ptr[wid + 1] - e0);
-    if (ni > VG_LIGHT_CAP) return;                                      // on the heavy kernel's work list
-    vg_load(lane, 32, ni, is_ent + e0, o, val, nrm, p0, sy, sn, sk, sc);
-    __syncwarp();
-    for (int i = lane; i < ni * 8; i += 32)                             // weights: 4 bytes per lane and trip
-        reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + sc[i >> 3]] * NBC)[i & 7];
-    // The three pair sums of the expansion enter S_ab only as Q1 - 2 Q2 - 2 Q3 = sum_{a>e} w_a w_e M_ae with the
-    // replicate-independent M_ae = 2 [ d_ae (|y_a - y_e| - |y_a| - |y_e|) - (|X_a| + |X_e|) |y_a - y_e| ], d_ae the
-    // distance-cache entry.  Lanes-as-entries build the M triangle once per pair (every load independent: one L2
-    // latency for the whole gather); lanes-as-replicates then need one FMA per entry.
-    const double* Ag = A + a_off[g];
-    const int npair = ni * (ni - 1) / 2;
-    for (int q = lane; q < npair; q += 32) {
-        int a = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
-        while (a * (a - 1) / 2 > q) --a;
-        while ((a + 1) * a / 2 <= q) ++a;
-        const int e = q - a * (a - 1) / 2;
-        const double dist = Ag[(long long)sk[a] * ng + sk[e]];
-        const double ya = sy[a], ye = sy[e], dy = fabs(ya - ye);
-        sd[q] = 2.0 * (dist * (dy - fabs(ya) - fabs(ye)) - (sn[a] + sn[e]) * dy);
-    }
-    __syncwarp();
-    VgSums S;
-#pragma unroll
-    for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
+    VgEntry* se = reinterpret_cast<VgEntry*>(base);
+    double* sd = reinterpret_cast<double*>(base + VG_LIGHT_CAP * 32);    // [a (a - 1) / 2 + e], e < a
+    unsigned char* sw = base + VG_LIGHT_CAP * 32 + VG_LIGHT_CAP * (VG_LIGHT_CAP - 1) / 2 * 8;
     const int b = lane;
-    for (int a = 0; a < ni; ++a) {
-        const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
-        const double wc = (double)sw[a * NBC + b];
-        const double ar = arT[(long long)(p0 + sk[a]) * NBC + b];
-        const double r = rT[(o + sc[a]) * NBC + b];
-        S.v[0] += wc;
-        S.v[1] = fma(wc, ar, S.v[1]);
-        S.v[2] = fma(wc, nr, S.v[2]);
-        S.v[3] = fma(wc, r, S.v[3]);
-        S.v[4] = fma(wc, ayc, S.v[4]);
-        S.v[5] = fma(wc * ar, r, S.v[5]);
-        S.v[6] = fma(wc * ar, ayc, S.v[6]);
-        S.v[7] = fma(wc * nr, r, S.v[7]);
-        S.v[8] = fma(wc * nr, ayc, S.v[8]);
-        const double* mrow = sd + a * (a - 1) / 2;
-        double q0 = 0.0, q1 = 0.0;
-        int e = 0;
-        for (; e + 1 < a; e += 2) {             // unordered pairs e < a
-            q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
-            q1 = fma((double)sw[(e + 1) * NBC + b], mrow[e + 1], q1);
+    double va[VAGG];
+#pragma unroll
+    for (int q = 0; q < VAGG; ++q) va[q] = vagg[(v * VAGG + q) * NBC + b];
+    for (int g = wib; g < G; g += 4) {
+        const long long wid = v * G + g;
+        const int ni = pr_ni[wid];
+        if (ni > VG_LIGHT_CAP) continue;                                // on the heavy kernel's work list
+        const int p0 = pt_ptr[g];
+        const unsigned char* rp = rec + pr_ptr[wid];
+        __syncwarp();                                                   // the previous pair's staging is fully consumed
+        if (lane < ni) {
+            const uint4* src = reinterpret_cast<const uint4*>(rp) + 2 * lane;
+            uint4* dst = reinterpret_cast<uint4*>(se) + 2 * lane;
+            dst[0] = __ldg(src);
+            dst[1] = __ldg(src + 1);
         }
-        if (e < a) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
-        S.v[9] = fma(wc, q0 + q1, S.v[9]);      // enters vg_finish as Q1 (Q2 = Q3 = 0)
+        const int npair = ni * (ni - 1) / 2;
+        const double* Mrec = reinterpret_cast<const double*>(rp + (size_t)ni * 32);
+        for (int q = lane; q < npair; q += 32) sd[q] = __ldg(Mrec + q);
+        __syncwarp();
+        for (int a = 0; a < ni; ++a) sw[a * NBC + b] = wT8[(long long)se[a].col * NBC + b];
+        VgSums S;
+#pragma unroll
+        for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
+        for (int a = 0; a < ni; ++a) {
+            const VgEntry ea = se[a];
+            const double ayc = fabs(ea.y), nr = ea.nr;
+            const double wc = (double)sw[a * NBC + b];
+            const double ar = arT[(long long)(p0 + ea.k) * NBC + b];
+            const double r = rT[(o + ea.c) * NBC + b];
+            S.v[0] += wc;
+            S.v[1] = fma(wc, ar, S.v[1]);
+            S.v[2] = fma(wc, nr, S.v[2]);
+            S.v[3] = fma(wc, r, S.v[3]);
+            S.v[4] = fma(wc, ayc, S.v[4]);
+            S.v[5] = fma(wc * ar, r, S.v[5]);
+            S.v[6] = fma(wc * ar, ayc, S.v[6]);
+            S.v[7] = fma(wc * nr, r, S.v[7]);
+            S.v[8] = fma(wc * nr, ayc, S.v[8]);
+            const double* mrow = sd + a * (a - 1) / 2;
+            double q0 = 0.0, q1 = 0.0;
+            int e = 0;
+            for (; e + 1 < a; e += 2) {             // unordered pairs e < a
+                q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+                q1 = fma((double)sw[(e + 1) * NBC + b], mrow[e + 1], q1);
+            }
+            if (e < a) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+            S.v[9] = fma(wc, q0 + q1, S.v[9]);      // enters vg_finish as Q1 (Q2 = Q3 = 0)
+        }
+        double ga[GAGG];
+#pragma unroll
+        for (int q = 0; q < GAGG; ++q) ga[q] = gagg[((long long)g * GAGG + q) * NBC + b];
+        if (lane < nb) out[((long long)lane * n + v) * G + g] = vg_finish(S, ga, va);
     }
-    if (lane < nb)
-        out[((long long)lane * n + v) * G + g] = vg_finish(S, gagg + (long long)g * GAGG * NBC + lane, vagg + v * VAGG * NBC + lane);
 }
 
-// persistent blocks over the heavy list; dynamic shared memory: cap * 56 bytes + reduction scratch
+// persistent blocks over the heavy list; dynamic shared memory: cap * 56 bytes + reduction scratch + 4 rows of M
 __global__ void __launch_bounds__(128)
-gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long long* __restrict__ ptr,
-                       const int* __restrict__ col, const double* __restrict__ val,
-                       const int* __restrict__ pt_ptr, const int* __restrict__ pos,
-                       const double* __restrict__ nrm, const long long* __restrict__ a_off,
-                       const double* __restrict__ A, const unsigned char* __restrict__ wT8,
-                       const double* __restrict__ arT, const double* __restrict__ rT,
-                       const double* __restrict__ gagg, const double* __restrict__ vagg, int nb,
-                       double* __restrict__ out, const long long* __restrict__ heavy_list,
-                       int total, const long long* __restrict__ is_ptr, const int2* __restrict__ is_ent) {
+gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restrict__ ptr, const int* __restrict__ pt_ptr,
+                       const int* __restrict__ pr_ni, const long long* __restrict__ pr_ptr, const unsigned char* __restrict__ rec,
+                       const unsigned char* __restrict__ wT8, const double* __restrict__ arT, const double* __restrict__ rT,
+                       const double* __restrict__ gagg, const double* __restrict__ vagg, int nb, double* __restrict__ out,
+                       const long long* __restrict__ heavy_list, int total) {
     extern __shared__ __align__(16) unsigned char vg_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int cap = (max_t + 1) & ~1;
@@ -529,39 +584,36 @@ gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long lo
     double* mrows = red + 3 * VG_NSUM * 32;                                             // [4][cap]
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
         const long long wid = heavy_list[it];
-        const int g = (int)(wid / n);
-        const long long v = wid % n;
+        const long long v = wid / G;
+        const int g = (int)(wid % G);
         const long long o = ptr[v];
-        const int t = (int)(ptr[v + 1] - o);
-        const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
+        const int p0 = pt_ptr[g];
         __syncthreads();                                                // previous pair fully consumed
-        const long long e0 = is_ptr[wid];
-        const int ni = (int)(is_ptr[wid + 1] - e0);
-        vg_load(threadIdx.x, 128, ni, is_ent + e0, o, val, nrm, p0, sy, sn, sk, sc);
-        __syncthreads();
-        for (int i = threadIdx.x; i < ni * 8; i += 128)
-            reinterpret_cast<unsigned*>(sw)[i] = reinterpret_cast<const unsigned*>(wT8 + (long long)col[o + sc[i >> 3]] * NBC)[i & 7];
+        const int ni = pr_ni[wid];
+        const VgEntry* ent = reinterpret_cast<const VgEntry*>(rec + pr_ptr[wid]);
+        const double* Mrec = reinterpret_cast<const double*>(ent + ni);
+        for (int a = threadIdx.x; a < ni; a += 128) {
+            const VgEntry e = ent[a];
+            sy[a] = e.y; sn[a] = e.nr; sk[a] = e.k; sc[a] = e.c;
+            // (the 32 multiplicity bytes of the entry's column: 8 words)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                reinterpret_cast<unsigned*>(sw)[a * 8 + q] = reinterpret_cast<const unsigned*>(wT8 + (long long)e.col * NBC)[q];
+        }
         __syncthreads();
         VgSums S;
 #pragma unroll
         for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
-        // The four warps split the outer index a (cost ~ a inner trips): a = wib, wib + 4, ...  Per a, lanes-as-entries
-        // build the replicate-independent row M_a. (see the light kernel) in the warp's shared-memory row with
-        // independent distance-cache loads, then lanes-as-replicates take one FMA per entry.
+        // The four warps split the rows a of M (cost ~ a): a = wib, wib + 4, ...  Row a is one coalesced read of a doubles
+        // into the warp's shared-memory row; lanes-as-replicates then take one FMA per entry.
         {
-            const double* Ag = A + a_off[g];
             double* mrow = mrows + wib * cap;
             const int b = lane;
             for (int a = wib; a < ni; a += 4) {
                 const int k = sk[a];
                 const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
-                const double* arow = Ag + (long long)k * ng;
-#pragma unroll 4
-                for (int e = lane; e < a; e += 32) {
-                    const double dist = arow[sk[e]];
-                    const double ye = sy[e], dy = fabs(yc - ye);
-                    mrow[e] = 2.0 * (dist * (dy - ayc - fabs(ye)) - (nr + sn[e]) * dy);
-                }
+                const double* mr = Mrec + (long long)a * (a - 1) / 2;
+                for (int e = lane; e < a; e += 32) mrow[e] = __ldg(mr + e);
                 const double wc = (double)sw[a * NBC + b];
                 const double ar = arT[(long long)(p0 + k) * NBC + b];
                 const double r = rT[(o + sc[a]) * NBC + b];
@@ -597,8 +649,12 @@ gom_score_heavy_kernel(long long n, int G, long long p, int max_t, const long lo
 #pragma unroll
             for (int i = 0; i < VG_NSUM; ++i)
                 S.v[i] += red[(0 * VG_NSUM + i) * 32 + lane] + red[(1 * VG_NSUM + i) * 32 + lane] + red[(2 * VG_NSUM + i) * 32 + lane];
-            if (lane < nb)
-                out[((long long)lane * n + v) * G + g] = vg_finish(S, gagg + (long long)g * GAGG * NBC + lane, vagg + v * VAGG * NBC + lane);
+            double ga[GAGG], va[VAGG];
+#pragma unroll
+            for (int q = 0; q < GAGG; ++q) ga[q] = gagg[((long long)g * GAGG + q) * NBC + lane];
+#pragma unroll
+            for (int q = 0; q < VAGG; ++q) va[q] = vagg[(v * VAGG + q) * NBC + lane];
+            if (lane < nb) out[((long long)lane * n + v) * G + g] = vg_finish(S, ga, va);
         }
     }
 }
@@ -623,10 +679,10 @@ void gom_db_free(GomDb* db) {
     if (!db) return;
     cudaFree(db->g_ptr); cudaFree(db->g_col); cudaFree(db->g_val); cudaFree(db->g_ord);
     cudaFree(db->mem_ptr); cudaFree(db->mem_row); cudaFree(db->pt_ptr); cudaFree(db->pt_col);
-    cudaFree(db->pos); cudaFree(db->x_off); cudaFree(db->a_off); cudaFree(db->X); cudaFree(db->nrm);
-    cudaFree(db->A); cudaFree(db->wT); cudaFree(db->arT); cudaFree(db->sqT); cudaFree(db->rT);
+    cudaFree(db->pos); cudaFree(db->x_off); cudaFree(db->a_off); cudaFree(db->X); cudaFree(db->nrm); cudaFree(db->nrm2);
+    cudaFree(db->A); cudaFree(db->wT); cudaFree(db->arT); cudaFree(db->rT);
     cudaFree(db->gagg); cudaFree(db->vagg); cudaFree(db->wT8); cudaFree(db->wG); cudaFree(db->flag); cudaFree(db->heavy_list);
-    cudaFree(db->is_ptr); cudaFree(db->is_ent);
+    cudaFree(db->pr_ni); cudaFree(db->pr_ptr); cudaFree(db->rec);
     delete db;
 }
 
@@ -722,11 +778,12 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
     CK(cudaMemcpy(db->a_off, a_off_h.data(), (G + 1) * sizeof(long long), cudaMemcpyHostToDevice));
     CK(dalloc(&db->pt_col, db->npt, &db->bytes));
     CK(dalloc(&db->nrm, db->npt, &db->bytes));
+    CK(dalloc(&db->nrm2, db->npt, &db->bytes));
     CK(dalloc(&db->X, x_off_h[G], &db->bytes));
     CK(dalloc(&db->A, a_off_h[G], &db->bytes));
     if (G && p) {
         gom_fill_kernel<<<gridc, 256, 0, st>>>(rowtab, ld_row, p, db->mem_row, db->mem_ptr, flag, scan,
-                                               db->x_off, db->pos, db->pt_col, db->X, db->nrm);
+                                               db->x_off, db->pos, db->pt_col, db->X, db->nrm, db->nrm2);
         ctx->launches++;
     }
     if (max_ng) {
@@ -737,7 +794,6 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
     // ---- per-chunk (32 replicates) scratch
     CK(dalloc(&db->wT, p * NBC, &db->bytes));
     CK(dalloc(&db->arT, (size_t)db->npt * NBC, &db->bytes));
-    CK(dalloc(&db->sqT, (size_t)db->npt * NBC, &db->bytes));
     CK(dalloc(&db->rT, (size_t)db->nnz * NBC, &db->bytes));
     CK(dalloc(&db->gagg, (size_t)G * GAGG * NBC, &db->bytes));
     CK(dalloc(&db->vagg, (size_t)n * VAGG * NBC, &db->bytes));
@@ -761,46 +817,56 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
     CK(dalloc(&db->wG, (size_t)db->npt * NBC, &db->bytes));
     CK(dalloc(&db->flag, 2, &db->bytes));          // [0] weight overflow, [1] heavy-list length
     CK(cudaMemsetAsync(db->flag, 0, 2 * sizeof(int), st));
-    // shared-memory staging of the scoring kernels: 56 bytes per genome hit and warp
-    // ---- intersection lists + the heavy kernel's work list (replicate independent)
+    // ---- pair records (replicate independent): intersection entries + M triangle of every (genome, GOM) pair, genome-major
     {
         const long long total_w = n * G;
-        long long* icnt = nullptr;
-        CK(dalloc(&icnt, total_w + 1, nullptr));
-        CK(dalloc(&db->is_ptr, total_w + 1, &db->bytes));
-        CK(cudaMemsetAsync(icnt, 0, (size_t)(total_w + 1) * sizeof(long long), st));
+        long long* pbytes = nullptr;
+        CK(dalloc(&pbytes, total_w + 1, nullptr));
+        CK(dalloc(&db->pr_ni, total_w + 1, &db->bytes));
+        CK(dalloc(&db->pr_ptr, total_w + 1, &db->bytes));
+        CK(cudaMemsetAsync(pbytes, 0, (size_t)(total_w + 1) * sizeof(long long), st));
         if (total_w) {
-            gom_isect_kernel<false><<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->pos, icnt, nullptr, nullptr);
+            gom_pair_count_kernel<<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->pos, db->pr_ni, pbytes);
             ctx->launches++;
         }
         void* tmp = nullptr; size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, icnt, db->is_ptr, (int)(total_w + 1), st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, pbytes, db->pr_ptr, (int)(total_w + 1), st);
         CK(cudaMalloc(&tmp, tb ? tb : 1));
-        cub::DeviceScan::ExclusiveSum(tmp, tb, icnt, db->is_ptr, (int)(total_w + 1), st);
+        cub::DeviceScan::ExclusiveSum(tmp, tb, pbytes, db->pr_ptr, (int)(total_w + 1), st);
         ctx->launches++;
-        long long n_ent = 0;
-        CK(cudaMemcpyAsync(&n_ent, db->is_ptr + total_w, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        long long rec_bytes = 0;
+        CK(cudaMemcpyAsync(&rec_bytes, db->pr_ptr + total_w, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        cudaFree(tmp); cudaFree(icnt);
-        CK(dalloc(&db->is_ent, (size_t)std::max<long long>(1, n_ent), &db->bytes));
+        cudaFree(tmp); cudaFree(pbytes);
+        size_t free_b2 = 0, total_b2 = 0;
+        cudaMemGetInfo(&free_b2, &total_b2);
+        if ((double)rec_bytes > 0.5 * (double)free_b2) {
+            int rc = gv2_fail(ctx, GV2_ERR_NOMEM, "GOM pair records need %.1f GB (sum over (genome, GOM) pairs of |I|^2 / 2 doubles), %.1f GB free: "
+                              "location tables this dense are outside the GOM kernel's design range", rec_bytes / 1e9, free_b2 / 1e9);
+            gom_db_free(db);
+            cudaFree(flag); cudaFree(scan);
+            return rc;
+        }
+        CK(dalloc(&db->rec, (size_t)std::max<long long>(16, rec_bytes), &db->bytes));
         CK(dalloc(&db->heavy_list, (size_t)std::max<long long>(1, total_w), &db->bytes));
         if (total_w) {
-            gom_isect_kernel<true><<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->pos, nullptr, db->is_ptr, db->is_ent);
+            gom_pair_fill_kernel<<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->g_val, db->pos, db->pt_ptr,
+                                                                                 db->nrm, db->a_off, db->A, db->pr_ni, db->pr_ptr, db->rec);
             ctx->launches++;
-            gom_heavy_list_kernel<<<(unsigned)((total_w + 255) / 256), 256, 0, st>>>(total_w, db->is_ptr, VG_LIGHT_CAP, db->heavy_list, db->flag + 1);
+            gom_heavy_list_kernel<<<(unsigned)((total_w + 255) / 256), 256, 0, st>>>(total_w, db->pr_ni, VG_LIGHT_CAP, db->heavy_list, db->flag + 1);
             ctx->launches++;
             CK(cudaMemcpyAsync(&db->n_heavy, db->flag + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
             unsigned long long* d_me = nullptr;
-            CK(dalloc(&d_me, 1, nullptr));
-            CK(cudaMemsetAsync(d_me, 0, sizeof(unsigned long long), st));
-            gom_mentries_kernel<<<(unsigned)std::min<long long>(2048, (total_w + 255) / 256), 256, 0, st>>>(total_w, db->is_ptr, d_me);
+            CK(dalloc(&d_me, 2, nullptr));
+            CK(cudaMemsetAsync(d_me, 0, 2 * sizeof(unsigned long long), st));
+            gom_mentries_kernel<<<(unsigned)std::min<long long>(2048, (total_w + 255) / 256), 256, 0, st>>>(total_w, db->pr_ni, d_me);
             ctx->launches++;
-            unsigned long long me = 0;
-            CK(cudaMemcpyAsync(&me, d_me, sizeof me, cudaMemcpyDeviceToHost, st));
+            unsigned long long me[2] = {0, 0};
+            CK(cudaMemcpyAsync(me, d_me, sizeof me, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             cudaFree(d_me);
-            db->n_mentries = (long long)me;
-            db->n_isect = n_ent;
+            db->n_mentries = (long long)me[0];
+            db->n_isect = (long long)me[1];
         }
     }
     const size_t vg_smem = (size_t)((max_t + 1) & ~1) * (VG_ENTRY_BYTES + 4 * sizeof(double)) + 3 * VG_NSUM * 32 * sizeof(double);
@@ -840,24 +906,22 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
             gom_gather_weights_kernel<<<(unsigned)(((long long)db->npt * NBC + 255) / 256), 256, 0, st>>>(db->pt_col, db->npt, db->wT, db->wG);
             ctx->launches++;
             dim3 g1((unsigned)((db->max_ng + GA_ROWS - 1) / GA_ROWS), (unsigned)G), b1(32, 8);
-            gom_rowsums_kernel<<<g1, b1, 0, st>>>(db->pt_ptr, db->a_off, db->A, db->wG, db->arT, db->sqT);
+            gom_rowsums_kernel<<<g1, b1, 0, st>>>(db->pt_ptr, db->a_off, db->A, db->wG, db->arT);
             ctx->launches++;
         }
-        gom_aggregates_kernel<<<(unsigned)G, 32, 0, st>>>(db->pt_ptr, db->pt_col, db->nrm, db->wT, db->arT, db->sqT, db->gagg);
+        gom_aggregates_kernel<<<(unsigned)G, 256, 0, st>>>(db->pt_ptr, db->mem_ptr, db->x_off, db->X, db->nrm, db->nrm2, db->wG, db->arT, db->gagg);
         ctx->launches++;
         genome_rowsums_sorted_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(n, db->g_ptr, db->g_col, db->g_val, db->g_ord, db->wT8, db->rT, db->vagg);
         ctx->launches++;
         {
             const long long total_w = n * G;
-            gom_score_light_kernel<<<(unsigned)((total_w + 3) / 4), 128, 0, st>>>(
-                n, (int)G, p, db->g_ptr, db->g_col, db->g_val, db->pt_ptr, db->pos, db->nrm, db->a_off, db->A,
-                db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G, db->is_ptr, db->is_ent);
+            gom_score_light_kernel<<<(unsigned)n, 128, 0, st>>>(n, (int)G, db->g_ptr, db->pt_ptr, db->pr_ni, db->pr_ptr, db->rec, db->wT8, db->arT,
+                                                                db->rT, db->gagg, db->vagg, cb, out + b0 * n * G);
             ctx->launches++;
             if (db->n_heavy) {
                 gom_score_heavy_kernel<<<(unsigned)std::min<long long>(db->n_heavy, ctx->sm_count * 8), 128, db->vg_smem, st>>>(
-                    n, (int)G, p, db->max_t, db->g_ptr, db->g_col, db->g_val, db->pt_ptr, db->pos, db->nrm, db->a_off, db->A,
-                    db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb, out + b0 * n * G, db->heavy_list, db->n_heavy,
-                    db->is_ptr, db->is_ent);
+                    n, (int)G, db->max_t, db->g_ptr, db->pt_ptr, db->pr_ni, db->pr_ptr, db->rec, db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb,
+                    out + b0 * n * G, db->heavy_list, db->n_heavy);
                 ctx->launches++;
             }
         }
