@@ -423,7 +423,8 @@ gom_pair_count_kernel(long long n, int G, long long p, const long long* __restri
     }
     if (lane == 0) {
         ni_out[wid] = ni;
-        bytes_out[wid] = (long long)ni * 32 + (long long)ni * (ni - 1) / 2 * 8;
+        // records start 32-byte aligned: the entries are read and written with 16-byte accesses
+        bytes_out[wid] = (long long)ni * 32 + (((long long)ni * (ni - 1) / 2 * 8 + 31) & ~31LL);
     }
 }
 
