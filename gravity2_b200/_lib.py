@@ -68,6 +68,7 @@ PROTOTYPES = {
     "gv2_job_base": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp]),
     "gv2_job_replicates": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "gv2_job_replicates_stream": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "gv2_job_replicates_device": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "gv2_dev_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),
     "gv2_dev_free": (C.c_int, [c_vp, c_vp]),
     "gv2_host_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),
@@ -81,6 +82,8 @@ PROTOTYPES = {
     "gv2_dev_shared_counts_packed": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "gv2_dev_unpack_tiles_i32": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gv2_dev_popc_peak": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_double)]),
+    "gv2_dev_rowmax_block": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "gv2_dev_gather_cells": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "gv2_num_tiles": (c_i64, [c_i64]),
     "gv2_dev_prepare_table": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, C.c_double, C.c_int, c_vp, c_i64, c_i64,
                                         c_vp, c_vp]),

@@ -1,2 +1,6 @@
 """Mirror of app/utils/gomdb_constructor.py."""
-from ...dropin import GOMDB_Constructor  # noqa: F401
+# native failures surface as the reference's SystemExit("FATAL ERROR: ...") here (gravity2_b200/errors.py)
+from ... import dropin as _d
+from ...errors import reference_errors as _ref
+
+GOMDB_Constructor = _ref(_d.GOMDB_Constructor)

@@ -667,7 +667,7 @@ struct TreeSink {
 };
 
 static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring, int64_t ring_len,
-                           double* host_out, gv2_replicate_cb cb_fn, void* cb_user, TreeSink* sink) {
+                           double* host_out, gv2_replicate_cb cb_fn, void* cb_user, TreeSink* sink, gv2_replicate_cb dev_cb = nullptr) {
     if (!job || !dev_weights || !dev_ring || nb < 0 || ring_len <= 0 || (cb_fn && !host_out))
         return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_stream: bad arguments");
     // host delivery ping-pongs two halves of the ring (one computing, one draining): a single slot cannot do that
@@ -809,6 +809,12 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
                                               dev_ring + slot * n * n, n * n))) return rc;
             }
+            if (dev_cb) {   // device consumer: the sub-chunk's matrices are complete in the ring; hand over the device pointers
+                GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                for (int64_t k = 0; k < cb; ++k)
+                    if (dev_cb(s0 + c0 + k, dev_ring + (slot + k) * n * n, cb_user) != 0)
+                        return gv2_fail(ctx, GV2_ERR_ARG, "replicate callback asked to stop at replicate %lld", (long long)(s0 + c0 + k));
+            }
             if (sink) {     // cluster this sub-chunk on the device; meanwhile finish the previous one on the host
                 if ((rc = sink->enqueue(dev_ring + slot * n * n, s0 + c0, cb))) return rc;
                 if ((rc = sink->drain(sink->cur))) return rc;
@@ -864,6 +870,14 @@ extern "C" int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weight
     if (rc) return rc;
     sink.names = leaf_names; sink.cb = cb; sink.user = user; sink.method = mth;
     return replicates_impl(job, dev_weights, nb, dev_ring, ring_len, nullptr, nullptr, nullptr, &sink);
+}
+
+// Device consumer: callback(b, DEVICE pointer of the replicate's matrix, user) on the calling thread once the matrix is
+// complete in the ring (replicate order); the pointer is valid until the callback returns.
+extern "C" int gv2_job_replicates_device(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring, int64_t ring_len,
+                                         gv2_replicate_cb callback, void* user) {
+    if (!callback) return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_device: callback is NULL");
+    return replicates_impl(job, dev_weights, nb, dev_ring, ring_len, nullptr, nullptr, user, nullptr, callback);
 }
 
 extern "C" int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_out) {

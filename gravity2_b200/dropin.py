@@ -183,6 +183,135 @@ def binary_jaccard(trait_table, engine: Optional[Engine] = None):
         return inter / union
 
 
+def braycurtis_matrix(arr, engine: Optional[Engine] = None):
+    """sklearn ``pairwise_distances(arr, metric="braycurtis")`` for a NON-NEGATIVE table: sum|u - v| / sum|u + v|.
+    For u, v >= 0 that is (1 - J) / (1 + J) with J = sum(min) / sum(max) the generalised Jaccard of the similarity engine
+    (sum|u - v| = sum(max) - sum(min), sum(u + v) = sum(max) + sum(min)), so the all-pairs work is the (min, +) tile
+    kernel; two all-zero rows give 0 / 0 = NaN as scipy does."""
+    A = np.ascontiguousarray(arr, dtype=np.float64)
+    if A.size and np.nanmin(A) < 0:
+        raise NotImplementedError("braycurtis_matrix is built for non-negative tables (PPHMM location distances)")
+    J = (engine or default_engine()).similarity(A, None, None, "P", 1.0)
+    out = (1.0 - J) / (1.0 + J)
+    empty = ~(A != 0).any(axis=1)
+    if empty.any():
+        out[np.ix_(empty, empty)] = np.nan
+    np.fill_diagonal(out, np.where(empty, np.nan, 0.0))
+    return out
+
+
+def pphmm_loc_diffs_pairwise(fnames, label_order, labels=None, engine: Optional[Engine] = None):
+    """app/utils/shared_pphmm_graphs.py:202-207: Bray-Curtis matrix of the genomes' PPHMM location rows.  The reference
+    takes ``distance_arr`` from get_dist_data (:138-162): the location CSV with zeros -> NaN, columns permuted by median
+    position (irrelevant for a pairwise sum), rows in ``label_order``; then ``nan_to_num`` -> 0."""
+    import pandas as pd
+    loc_df = pd.read_csv(fnames["PphmmLocs"], index_col=False)
+    arr = np.asarray(loc_df.iloc[:, 1:].apply(pd.to_numeric), dtype=np.float64)
+    arr = np.nan_to_num(arr, nan=0.0)[np.asarray(label_order)]
+    return braycurtis_matrix(arr, engine)
+
+
+# ---------------------------------------------------------------------- virus grouping
+def _conditional_entropy(x, y):
+    """virus_grouping_estimator.py:16-36 (summation in first-occurrence order, as collections.Counter iterates)."""
+    from collections import Counter
+    y_counter = Counter(y)
+    xy_counter = Counter(list(zip(x, y)))
+    total = float(sum(y_counter.values()))
+    h = 0.0
+    for xy in xy_counter.keys():
+        p_xy = xy_counter[xy] / total
+        p_y = y_counter[xy[1]] / total
+        h += p_xy * np.log(p_y / p_xy)
+    return h
+
+
+def theils_u(x, y, symmetrical=False):
+    """virus_grouping_estimator.py:39-71."""
+    from collections import Counter
+    from scipy.stats import entropy
+
+    def marginal(v):
+        c = Counter(v)
+        tot = float(sum(c.values()))
+        return entropy(list(map(lambda k: k / tot, c.values())))
+
+    s_xy = _conditional_entropy(x, y)
+    s_x = marginal(x)
+    if not symmetrical:
+        return 1.0 if s_x == 0 else (s_x - s_xy) / float(s_x)
+    s_yx = _conditional_entropy(y, x)
+    s_y = marginal(y)
+    return 1.0 if s_x + s_y == 0.0 else ((s_x - s_xy) + (s_y - s_yx)) / float(s_x + s_y)
+
+
+def VirusGrouping_Estimator(DistMat, Dendrogram_LinkageMethod, TaxoGroupingList, engine: Optional[Engine] = None):
+    """app/utils/virus_grouping_estimator.py:74-89: the O(N^2) clustering runs on the device (bit-identical linkage matrix),
+    the scalar search over the cut height and Theil's U stay on the host as in the reference (scipy)."""
+    from scipy.cluster.hierarchy import fcluster
+    from scipy.optimize import minimize_scalar
+    if Dendrogram_LinkageMethod not in LINKAGE_METHODS:
+        raise NotImplementedError(f"device linkage is built for methods {LINKAGE_METHODS} (got {Dendrogram_LinkageMethod!r})")
+    linkageMat = (engine or default_engine()).linkage(np.asarray(DistMat, dtype=np.float64), Dendrogram_LinkageMethod)
+
+    def anti_u(cut):
+        return -1 * theils_u(x=fcluster(Z=linkageMat, t=cut, criterion="distance"), y=TaxoGroupingList, symmetrical=True)
+
+    res = minimize_scalar(anti_u, bounds=[0, 1], method="bounded")
+    groups = np.array(fcluster(Z=linkageMat, t=res.x, criterion="distance"))
+    return (groups, res.x, -1 * res.fun, theils_u(x=TaxoGroupingList, y=groups), theils_u(x=groups, y=TaxoGroupingList))
+
+
+# ------------------------------------------------------------- classification epilogue (pipeline II)
+from .classification import (  # noqa: E402,F401
+    PairwiseSimilarityScore_Cutoff_Dict_Constructor, max_similarity, draw_class_cells, cutoff_dict_from_cells, DeviceMatrix,
+)
+
+
+def bootstrap_classification(PPHMMSignatureTable_AllVirus, PPHMMLocationTable_AllVirus, TaxoGroupingList_RefVirus, GOMIDList,
+                             payload, N_UcfViruses: int, N_Bootstrap: Optional[int] = None, indices=None, batch: int = 64,
+                             engine: Optional[Engine] = None):
+    """The numeric part of pipeline II's bootstrap loop body (app/src/virus_classification.py:290-344) with the similarity
+    matrix resident in HBM: per replicate yields ``(cutoff_dict, MaxSimScoreList, TaxoOfMaxSimScoreList)`` -- what
+    PairwiseSimilarityScore_Cutoff_Dict_Constructor(S[:N_ref, :N_ref], ...) and the 1-NN lines of
+    TaxonomicAssignmentProposerAndEvaluator(S[-N_ucf:, :N_ref], ...) return -- reading only the listed cells and the row
+    maxima from the device.  Every draw from numpy's global RNG happens in the reference's order (replicate b: resample
+    indices, then per class the list subsamples and the SVC seed), which does not depend on device results."""
+    from .engine import Job
+    eng = engine or default_engine()
+    sig = np.ascontiguousarray(PPHMMSignatureTable_AllVirus, dtype=np.float64)
+    loc = np.ascontiguousarray(PPHMMLocationTable_AllVirus, dtype=np.float64)
+    n, p = sig.shape
+    taxo_ref = np.asarray(TaxoGroupingList_RefVirus)
+    n_ref = len(taxo_ref)
+    nb = int(payload["N_Bootstrap"] if N_Bootstrap is None else N_Bootstrap)
+    n_pair = int(payload["N_PairwiseSimilarityScores"])
+    scheme = payload["SimilarityMeasurementScheme"]
+    if payload.get("PphmmNeighbourhoodWeight", 0) != 0 or payload.get("PphmmSigScoreThreshold", 0) != 0:
+        raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
+    gor = gom_membership(taxo_ref, GOMIDList) if "G" in scheme else None
+    job = Job(eng, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance=False)
+    try:
+        for b0 in range(0, nb, batch):
+            cb = min(batch, nb - b0)
+            ws, cells = [], []
+            for k in range(cb):             # the reference's draw order, replicate by replicate
+                idx = draw_resample_indices(p, sort=True) if indices is None else indices[b0 + k]
+                ws.append(weights_from_indices(idx, p))
+                cells.append(draw_class_cells(taxo_ref, n_pair))
+            out = []
+
+            def consume(b, S):
+                mx, tx = max_similarity(S, taxo_ref, row_begin=n - N_UcfViruses, n_ref=n_ref)
+                out.append((cutoff_dict_from_cells(S, cells[b]), mx, tx))
+
+            job.for_each_replicate_device(np.stack(ws), consume)
+            for item in out:
+                yield item
+    finally:
+        job.close()
+
+
 def sort_pphmm_distances(PPHMMSignatureTable, engine: Optional[Engine] = None):
     """The matrix RefVirusAnnotator.sort_pphmm hands to DistMat2Tree (app/src/ref_virus_annotator.py:143-165):
     ``1 - SimMat_traits`` of the 0/1 transposed signature table, (P, P) float64, NaN where both PPHMMs are empty."""

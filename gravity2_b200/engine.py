@@ -332,6 +332,58 @@ class Job:
         finally:
             self.lib.gv2_dev_free(self.ctx, d_w)
 
+    def base_device(self, fn):
+        """fn(DeviceMatrix) on the un-resampled matrix, computed into device memory and never shipped."""
+        from .classification import DeviceMatrix
+        n = self.n
+        d = C.c_void_p()
+        _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, max(8, n * n * 8), C.byref(d)))
+        try:
+            _lib.check(self.ctx, self.lib.gv2_job_base(self.job, 0, self.ntiles, 0, d))
+            self.eng.synchronize()
+            return fn(DeviceMatrix(self.eng, d.value, n))
+        finally:
+            self.lib.gv2_dev_free(self.ctx, d)
+
+    def for_each_replicate_device(self, weights, fn, ring_bytes: int = 16 << 30) -> None:
+        """fn(b, DeviceMatrix) for every replicate in order; the matrix stays in HBM (a slot of the device ring) and is
+        valid until fn returns -- the consumer reads what it needs with DeviceMatrix.rowmax / .gather."""
+        from .classification import DeviceMatrix
+        w = np.ascontiguousarray(weights, dtype=np.int32)
+        if w.ndim == 1:
+            w = w[None, :]
+        nb = w.shape[0]
+        if nb == 0:
+            return
+        if w.shape[1] != self.p:
+            raise ValueError("weights must be (B, P)")
+        n = self.n
+        ring_len = max(1, min(nb, int(ring_bytes // max(1, n * n * 8))))
+        dev_ring, d_w = C.c_void_p(), C.c_void_p()
+        _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, ring_len * max(1, n * n * 8), C.byref(dev_ring)))
+        err = []
+
+        def _cb(b, ptr, _user):
+            try:
+                fn(int(b), DeviceMatrix(self.eng, ptr, n))
+                return 0
+            except BaseException as e:      # never let an exception cross the C frame
+                err.append(e)
+                return 1
+
+        cb = _lib.REPLICATE_CB(_cb)
+        try:
+            _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, w.nbytes, C.byref(d_w)))
+            _lib.check(self.ctx, self.lib.gv2_memcpy_h2d(self.ctx, d_w, _ptr(w), w.nbytes))
+            rc = self.lib.gv2_job_replicates_device(self.job, d_w, nb, dev_ring, ring_len, C.cast(cb, C.c_void_p), None)
+            if err:
+                raise err[0]
+            _lib.check(self.ctx, rc)
+        finally:
+            if d_w:
+                self.lib.gv2_dev_free(self.ctx, d_w)
+            self.lib.gv2_dev_free(self.ctx, dev_ring)
+
     def for_each_tree(self, weights, leaf_names, fn, method: str = "average", ring_bytes: Optional[int] = None) -> None:
         """fn(b, newick) for every replicate in order: the replicate's distance matrix is clustered on the device
         (UPGMA) and printed as DistMat2Tree prints it; the matrices never leave HBM.  ``ring_bytes`` of device memory

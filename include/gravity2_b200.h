@@ -194,6 +194,11 @@ int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, dou
  * computes the next sub-chunk; the matrix is valid until the callback returns; non-zero return stops. */
 int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
                               int64_t ring_len, double* host_out, gv2_replicate_cb callback, void* user);
+/* Device consumer (classification epilogue of pipeline II): callback(b, matrix, user) receives
+ * the DEVICE pointer of replicate b's matrix in the ring, on the calling thread, in replicate order, after the stream has
+ * been synchronised; valid until the callback returns (gv2_dev_rowmax_block / gv2_dev_gather_cells read it in place). */
+int gv2_job_replicates_device(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring, int64_t ring_len,
+                              gv2_replicate_cb callback, void* user);
 /* Replicate dendrograms without shipping the matrices: each replicate's distance matrix is
  * clustered on the device (scipy.cluster.hierarchy.linkage(..., method): the nearest-neighbour chain behind "average"
  * (UPGMA, the default), "complete", "weighted" and "ward", the minimum spanning tree behind "single"; scipy's tie order;
@@ -279,6 +284,17 @@ int gv2_dev_unpack_tiles_i32(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_
 /* POPC-pipe peak of the context's device, measured (register-resident AND + POPC + add chains on every SM):
  * the roofline denominator of the presence / absence path. */
 int gv2_dev_popc_peak(gv2_ctx* ctx, int iters, double* popc_per_s);
+
+/* ---- classification epilogue of pipeline II on a device-resident matrix ------------ */
+/* np.max / np.argmax along axis 1 of mat[row_begin:row_end, col_begin:col_end] (first occurrence of the maximum, index
+ * relative to col_begin): the 1-nearest-neighbour proposal of TaxonomicAssignmentProposerAndEvaluator
+ * (app/utils/classification_utils.py:63-68) on SimMat[-N_ucf:, :N_ref] without shipping the matrix. */
+int gv2_dev_rowmax_block(gv2_ctx* ctx, const double* mat, int64_t ld, int64_t row_begin, int64_t row_end,
+                         int64_t col_begin, int64_t col_end, double* out_max, int64_t* out_arg);
+/* out[k] = mat[rows[k]][cols[k]] (device index arrays): the cells of the intra- / inter-class lists of
+ * PairwiseSimilarityScore_Cutoff_Dict_Constructor (classification_utils.py:10-43), in the order the host lists them. */
+int gv2_dev_gather_cells(gv2_ctx* ctx, const double* mat, int64_t ld, const int64_t* rows, const int64_t* cols,
+                         int64_t count, double* out);
 
 #ifdef __cplusplus
 }

@@ -258,8 +258,63 @@ def main_sort_pphmm():
     print("wrote reference_golden_sort_pphmm.npz", len(gold), "arrays")
 
 
+def main_classification():
+    """next-2: PairwiseSimilarityScore_Cutoff_Dict_Constructor (app/utils/classification_utils.py:10-60), UNMODIFIED, on
+    seeded similarity matrices: lists longer and shorter than N_PairwiseSimilarityScores, a single-member class, and the
+    state of numpy's global RNG afterwards (the drop-in must consume it identically)."""
+    for k in [k for k in sys.modules if k.split(".")[0] in _AutoMock.PREFIXES]:
+        del sys.modules[k]
+    sys.meta_path.insert(0, _AutoMock())
+    from app.utils.classification_utils import PairwiseSimilarityScore_Cutoff_Dict_Constructor as ref_fn
+    gold = {}
+    for tag, (n, classes, n_pair, seed) in {"H": (60, [25, 20, 14, 1], 40, 11), "I": (33, [12, 11, 10], 1000, 12)}.items():
+        rng = np.random.default_rng(seed)
+        taxo = np.array(sum([[f"C{k}"] * m for k, m in enumerate(classes)], []))
+        taxo = taxo[rng.permutation(n)]
+        lab = np.array([int(t[1:]) for t in taxo])
+        S = rng.random((n, n)) * 0.3 + 0.55 * (lab[:, None] == lab[None, :])
+        S = (S + S.T) / 2
+        np.fill_diagonal(S, 1.0)
+        np.random.seed(100 + seed)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            d = ref_fn(S, taxo, n_pair)
+        gold[f"{tag}_S"], gold[f"{tag}_taxo"], gold[f"{tag}_npair"], gold[f"{tag}_seed"] = S, taxo, np.int64(n_pair), np.int64(100 + seed)
+        gold[f"{tag}_classes"] = np.array(list(d.keys()))
+        for cls, v in d.items():
+            gold[f"{tag}_{cls}_intra"] = np.array(v["PairwiseSimilarityScore_IntraClass_List"], dtype=np.float64)
+            gold[f"{tag}_{cls}_inter"] = np.array(v["PairwiseSimilarityScore_InterClass_List"], dtype=np.float64)
+            gold[f"{tag}_{cls}_cutoff"] = np.float64(v["CutOff"])
+        gold[f"{tag}_rng_next"] = np.float64(np.random.random())
+    np.savez_compressed(os.path.join(OUT, "reference_golden_classification.npz"), **gold)
+    print("wrote reference_golden_classification.npz", len(gold), "arrays")
+
+
+def main_grouping():
+    """next-3: VirusGrouping_Estimator (app/utils/virus_grouping_estimator.py:74-89), UNMODIFIED, on block-structured distance
+    matrices."""
+    from app.utils.virus_grouping_estimator import VirusGrouping_Estimator as ref_fn
+    gold = {}
+    for tag, (n, k, seed) in {"J": (48, 4, 21), "K": (30, 3, 22)}.items():
+        rng = np.random.default_rng(seed)
+        lab = rng.integers(0, k, n)
+        taxo = np.array([f"G{x}" for x in lab])
+        D = rng.random((n, n)) * 0.25 + 0.6 * (lab[:, None] != lab[None, :])
+        D = (D + D.T) / 2
+        np.fill_diagonal(D, 0.0)
+        groups, cut, score, u1, u2 = ref_fn(D, "average", taxo)
+        gold[f"{tag}_D"], gold[f"{tag}_taxo"] = D, taxo
+        gold[f"{tag}_groups"], gold[f"{tag}_stats"] = np.asarray(groups), np.array([cut, score, u1, u2])
+    np.savez_compressed(os.path.join(OUT, "reference_golden_grouping.npz"), **gold)
+    print("wrote reference_golden_grouping.npz", len(gold), "arrays")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "neighbourhood":
+    if len(sys.argv) > 1 and sys.argv[1] == "grouping":
+        main_grouping()
+    elif len(sys.argv) > 1 and sys.argv[1] == "classification":
+        main_classification()
+    elif len(sys.argv) > 1 and sys.argv[1] == "neighbourhood":
         main_neighbourhood()
     elif len(sys.argv) > 1 and sys.argv[1] == "sort_pphmm":
         main_sort_pphmm()

@@ -330,3 +330,100 @@ def test_degenerate_dcor_constant_location_values(eng):
             bl = sig[:, idx]
             ref = O.gom_table(bl, O.gomdb(taxo, bl, ids), ids)
             assert np.allclose(gw[b], ref, rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
+# ------------------------------------------------------------------ next-2 / next-3 rows of SURVEY 8f
+def test_classification_epilogue_on_device_matrix(eng):
+    """PairwiseSimilarityScore_Cutoff_Dict_Constructor + the 1-NN proposal on a matrix that stays in HBM == the same functions
+    on the host copy == the reference golden; and the batched PL2 helper against per-replicate host evaluation."""
+    import gravity2_b200 as G
+    from gravity2_b200 import classification as CL
+    from gravity2_b200.engine import Job
+    g = dict(np.load(os.path.join(REPO, "tests", "golden", "reference_golden_classification.npz"), allow_pickle=False))
+    S, taxo, n_pair = g["H_S"], g["H_taxo"], int(g["H_npair"])
+    import torch
+    d_S = torch.from_numpy(S).cuda()
+    dm = CL.DeviceMatrix(eng, d_S.data_ptr(), S.shape[0])
+    np.random.seed(int(g["H_seed"]))
+    d = CL.PairwiseSimilarityScore_Cutoff_Dict_Constructor(dm, taxo, n_pair)
+    for cls, v in d.items():
+        assert np.array_equal(np.array(v["PairwiseSimilarityScore_IntraClass_List"]), g[f"H_{cls}_intra"])
+        assert np.array_equal(np.array(v["PairwiseSimilarityScore_InterClass_List"]), g[f"H_{cls}_inter"])
+        assert v["CutOff"] == float(g[f"H_{cls}_cutoff"])
+    assert np.random.random() == float(g["H_rng_next"])
+    mx, arg = dm.rowmax(40, 60, 0, 40)
+    assert np.array_equal(mx, S[40:, :40].max(axis=1)) and np.array_equal(arg, S[40:, :40].argmax(axis=1))
+    S2 = S.copy(); S2[45, 3] = S2[45, 17] = 5.0; S2[50, 9] = np.nan
+    d_S2 = torch.from_numpy(S2).cuda()
+    mx, arg = CL.DeviceMatrix(eng, d_S2.data_ptr(), 60).rowmax(40, 60, 0, 40)
+    assert arg[5] == 3 and arg[10] == 9 and np.isnan(mx[10])             # first maximum; NaN wins, as numpy
+    # batched PL2 helper: device-resident similarity, cells and row maxima only
+    t = synth.make_tables(90, 500, 5, 0.1, seed=15)
+    n_ref, n_ucf = 70, 20
+    payload = {"N_Bootstrap": 3, "SimilarityMeasurementScheme": "PG", "p": 1.0, "N_PairwiseSimilarityScores": 150}
+    np.random.seed(8)
+    got = list(G.bootstrap_classification(t.sig, t.loc, t.taxo[:n_ref], t.gom_ids, payload, n_ucf))
+    np.random.seed(8)
+    gor = G.gom_membership(t.taxo[:n_ref], t.gom_ids)
+    for b in range(3):
+        idx = G.draw_resample_indices(500, sort=True)
+        w = G.weights_from_indices(idx, 500)
+        Sb = eng.bootstrap(t.sig, t.loc, gor, len(t.gom_ids), w[None, :], "PG", 1.0, distance=False)[0]
+        ref_d = CL.PairwiseSimilarityScore_Cutoff_Dict_Constructor(Sb[:n_ref][:, :n_ref], t.taxo[:n_ref], 150)
+        ref_mx, ref_tx = CL.max_similarity(Sb[-n_ucf:][:, :n_ref], t.taxo[:n_ref])
+        d_b, mx_b, tx_b = got[b]
+        assert list(d_b) == list(ref_d)
+        for cls in ref_d:
+            assert d_b[cls]["PairwiseSimilarityScore_InterClass_List"] == ref_d[cls]["PairwiseSimilarityScore_InterClass_List"]
+            assert d_b[cls]["PairwiseSimilarityScore_IntraClass_List"] == ref_d[cls]["PairwiseSimilarityScore_IntraClass_List"]
+            assert d_b[cls]["CutOff"] == ref_d[cls]["CutOff"]
+        assert np.array_equal(mx_b, ref_mx) and np.array_equal(tx_b, ref_tx)
+
+
+@pytest.mark.parametrize("tag", ["J", "K"])
+def test_virus_grouping_estimator_reference_golden(eng, tag):
+    import gravity2_b200 as G
+    g = dict(np.load(os.path.join(REPO, "tests", "golden", "reference_golden_grouping.npz"), allow_pickle=False))
+    groups, cut, score, u1, u2 = G.VirusGrouping_Estimator(g[f"{tag}_D"], "average", g[f"{tag}_taxo"])
+    assert np.array_equal(groups, g[f"{tag}_groups"])
+    assert np.array_equal(np.array([cut, score, u1, u2]), g[f"{tag}_stats"])
+
+
+def test_braycurtis_matrix_vs_sklearn(eng, tmp_path):
+    """pphmm_loc_diffs_pairwise (app/utils/shared_pphmm_graphs.py:202-207): the reference's own call,
+    sklearn pairwise_distances(..., metric="braycurtis"), on the location CSV laid out as pl1_graphs.py:317-319 writes it"""
+    import pandas as pd
+    from sklearn.metrics.pairwise import pairwise_distances
+    import gravity2_b200 as G
+    t = synth.make_tables(70, 900, 5, 0.08, seed=16)
+    naive = np.abs(t.loc)
+    naive[11] = 0.0; naive[29] = 0.0                                    # two genomes without any hit: 0 / 0
+    cols = [f"PPHMM {c}" for c in range(900)]
+    df = pd.DataFrame(naive, columns=cols)
+    df.insert(0, "Virus name", [f"v{i}" for i in range(70)])
+    f = os.path.join(tmp_path, "locs.csv")
+    df.to_csv(f, index=False)
+    order = np.random.default_rng(0).permutation(70)
+    got = G.pphmm_loc_diffs_pairwise({"PphmmLocs": f}, order, None)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = pairwise_distances(np.nan_to_num(naive[order], nan=0), metric="braycurtis")
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.abs(got[ok] - ref[ok]).max() <= 1e-6
+
+
+def test_native_errors_follow_the_reference_convention(eng):
+    """the modules mirroring the reference's import paths end a run the way the reference does:
+    raise_gravity_error -> SystemExit("FATAL ERROR: ...") (app/utils/error_handlers.py:3-4)"""
+    from gravity2_b200.app.utils.parallel_gom_sig_generator import GOMSignatureTable_Constructor
+    from gravity2_b200.app.utils.shared_pphmm_graphs import shared_norm_pphmm_ratio
+    import gravity2_b200 as G
+    loc = np.zeros((4, 6)); loc[:, 0] = [1.0, 2.0, 3.0, 4.0]
+    db = {"A": np.full((2, 7), 1.0)}                                   # GOM rows of the wrong width: native argument error
+    with pytest.raises((SystemExit, ValueError)) as ei:
+        GOMSignatureTable_Constructor(loc, db, ["A"], {"N_CPUs": 1})
+    if ei.type is SystemExit:
+        assert "FATAL ERROR" in str(ei.value)
+    with pytest.raises(ZeroDivisionError):                              # the reference's own Python error passes through
+        G.shared_norm_pphmm_ratio_from_array(np.zeros((3, 5)))
