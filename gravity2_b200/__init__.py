@@ -10,5 +10,6 @@ from .dropin import (  # noqa: F401
     VirusGrouping_Estimator, theils_u, PairwiseSimilarityScore_Cutoff_Dict_Constructor, max_similarity, bootstrap_classification,
 )
 from .engine import Engine, default_engine  # noqa: F401
+from .multi import MultiEngine, MultiJob  # noqa: F401
 
 __version__ = "0.1.0"

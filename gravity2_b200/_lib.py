@@ -82,6 +82,17 @@ PROTOTYPES = {
     "gv2_dev_shared_counts_packed": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "gv2_dev_unpack_tiles_i32": (C.c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gv2_dev_popc_peak": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_double)]),
+    "gv2_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(c_vp)]),
+    "gv2_multi_destroy": (None, [c_vp]),
+    "gv2_multi_last_error": (C.c_char_p, [c_vp]),
+    "gv2_multi_device_count": (C.c_int, [c_vp]),
+    "gv2_multi_uses_nccl": (C.c_int, [c_vp]),
+    "gv2_multi_context": (c_vp, [c_vp, C.c_int]),
+    "gv2_multi_job_create": (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, C.c_int, C.c_double, C.c_int, C.POINTER(c_vp)]),
+    "gv2_multi_job_destroy": (None, [c_vp]),
+    "gv2_multi_job_base_host": (C.c_int, [c_vp, c_vp]),
+    "gv2_multi_job_replicates_newick": (C.c_int, [c_vp, c_vp, c_i64, C.c_char_p, C.POINTER(C.c_char_p), c_i64, c_vp, c_vp]),
+    "gv2_multi_job_replicates_host": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "gv2_dev_rowmax_block": (C.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "gv2_dev_gather_cells": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "gv2_num_tiles": (c_i64, [c_i64]),

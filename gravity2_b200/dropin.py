@@ -357,8 +357,6 @@ def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, 
     app/src/pl1_graphs.py:78-117 (resample, GOM rebuild, distance matrix, DistMat2Tree) with everything up to the
     dendrogram on the device -- the 8 N^2 bytes of a replicate's distance matrix never cross PCIe.  Arguments as
     ``bootstrap_distance_matrices``; ``LeafList`` are the tree labels (TaxoLabelList)."""
-    from .engine import Job
-    eng = engine or default_engine()
     sig = np.ascontiguousarray(PPHMMSignatureTable, dtype=np.float64)
     n, p = sig.shape
     nb = int(payload["N_Bootstrap"] if N_Bootstrap is None else N_Bootstrap)
@@ -370,7 +368,7 @@ def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, 
         raise NotImplementedError(f"device linkage is built for methods {LINKAGE_METHODS} (got {method!r})")
     loc = sig if pipeline == "pl1" else np.ascontiguousarray(PPHMMLocationTable, dtype=np.float64)
     gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
-    job = Job(eng, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance=True)
+    job = _make_job(engine, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), True)
     try:
         for b0 in range(0, nb, batch):
             cb = min(batch, nb - b0)
@@ -388,6 +386,18 @@ def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, 
 
 
 # ------------------------------------------------------------------------------ bootstrap
+def _make_job(engine, sig, loc, gor, g, scheme, p, distance):
+    """One GPU (engine.Job) or every GPU of the node (multi.MultiJob): an explicit MultiEngine, or GRAVITY_B200_DEVICES
+    naming more than one device when no engine is given."""
+    from .engine import Job
+    from .multi import MultiEngine, MultiJob, default_multi_engine
+    if engine is None:
+        engine = default_multi_engine()
+    if isinstance(engine, MultiEngine):
+        return MultiJob(engine, sig, loc, gor, g, scheme, p, distance=distance)
+    return Job(engine or default_engine(), sig, loc, gor, g, scheme, p, distance=distance)
+
+
 def draw_resample_indices(n_pphmms: int, sort: bool = False):
     """The reference's own draw from numpy's global legacy RNG (pl1_graphs.py:81-82; sorted in
     virus_classification.py:295-296), keeping that stream in step with the reference's later draws."""
@@ -422,8 +432,6 @@ def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGro
     exactly as the reference draws them, replicate by replicate.
     Each yielded matrix is a zero-copy view into a pinned host ring: it is valid until the next one is
     requested (copy it to keep it), which is how the reference's loop uses it (tree, then discard)."""
-    from .engine import Job
-    eng = engine or default_engine()
     sig = np.ascontiguousarray(PPHMMSignatureTable, dtype=np.float64)
     n, p = sig.shape
     nb = int(payload["N_Bootstrap"] if N_Bootstrap is None else N_Bootstrap)
@@ -432,7 +440,7 @@ def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGro
         raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
     loc = sig if pipeline == "pl1" else np.ascontiguousarray(PPHMMLocationTable, dtype=np.float64)
     gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
-    job = Job(eng, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance=distance)
+    job = _make_job(engine, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance)
     try:
         # tables are uploaded once; replicates go through in batches big enough to fill the tensor-core
         # blocks (128 replicates per CTA) and the 32-replicate lanes of the GOM kernels

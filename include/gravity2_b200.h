@@ -285,6 +285,31 @@ int gv2_dev_unpack_tiles_i32(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_
  * the roofline denominator of the presence / absence path. */
 int gv2_dev_popc_peak(gv2_ctx* ctx, int iters, double* popc_per_s);
 
+/* ---- every GPU of the node behind one caller (SURVEY.md section 8b "Threading / processes", 8e) ------------------------
+ * One process, one host thread + one context per GPU inside the library.  Tables: one upload, then a broadcast over NVLink.
+ * Replicates: by index (replicate b on GPU b mod N), no exchange.  Un-resampled matrix: one upper-triangular tile range per
+ * GPU, packed blocks all-gathered with NCCL (ncclCommInitAll in this process; libnccl.so.2 is dlopen'ed, and without it the
+ * blocks travel by cudaMemcpyPeerAsync).  Callbacks run on the CALLING thread, in replicate order. */
+typedef struct gv2_multi gv2_multi;
+typedef struct gv2_multi_job gv2_multi_job;
+int gv2_multi_create(const int* devices /* NULL: all visible */, int ndev, gv2_multi** out);
+void gv2_multi_destroy(gv2_multi* m);
+const char* gv2_multi_last_error(const gv2_multi* m);
+int gv2_multi_device_count(const gv2_multi* m);
+int gv2_multi_uses_nccl(const gv2_multi* m);
+gv2_ctx* gv2_multi_context(gv2_multi* m, int i); /* the i-th GPU's context (launch counts, timing) */
+/* Arguments as gv2_job_create with HOST tables (loc == sig: one table). */
+int gv2_multi_job_create(gv2_multi* m, const double* sig, const double* loc, int64_t n, int64_t p, const int32_t* gom_of_row,
+                         int64_t n_gom_rows, int64_t g, int scheme, double power, int out_kind, gv2_multi_job** out);
+void gv2_multi_job_destroy(gv2_multi_job* job);
+int gv2_multi_job_base_host(gv2_multi_job* job, double* host_out /* [n][n] */);
+/* host_weights [nb][p]; ring_len <= 0: chosen from the free memory.  Semantics of gv2_job_replicates_newick /
+ * gv2_job_replicates_stream (callback mode) respectively. */
+int gv2_multi_job_replicates_newick(gv2_multi_job* job, const int32_t* host_weights, int64_t nb, const char* method,
+                                    const char* const* leaf_names, int64_t ring_len, gv2_newick_cb callback, void* user);
+int gv2_multi_job_replicates_host(gv2_multi_job* job, const int32_t* host_weights, int64_t nb, int64_t ring_len,
+                                  gv2_replicate_cb callback, void* user);
+
 /* ---- classification epilogue of pipeline II on a device-resident matrix ------------ */
 /* np.max / np.argmax along axis 1 of mat[row_begin:row_end, col_begin:col_end] (first occurrence of the maximum, index
  * relative to col_begin): the 1-nearest-neighbour proposal of TaxonomicAssignmentProposerAndEvaluator

@@ -427,3 +427,72 @@ def test_native_errors_follow_the_reference_convention(eng):
         assert "FATAL ERROR" in str(ei.value)
     with pytest.raises(ZeroDivisionError):                              # the reference's own Python error passes through
         G.shared_norm_pphmm_ratio_from_array(np.zeros((3, 5)))
+
+
+# ------------------------------------------------------------------ every GPU of the node behind one caller
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_multi_engine_single_process_equals_one_gpu(eng):
+    """gv2_multi_*: one process, one host thread per GPU inside the library.  With one visible GPU the same entry points run
+    on a one-device set; with several, replicates are dealt by index and the base matrix is tile-sharded + all-gathered (NCCL
+    when libnccl.so.2 can be dlopen'ed).  Results must be bit-identical to the single-GPU job."""
+    import gravity2_b200 as G
+    from gravity2_b200.engine import Job
+    ndev = min(_n_gpus(), 8)
+    meng = G.MultiEngine(list(range(ndev)))
+    assert meng.n_devices == ndev
+    t = synth.make_tables(300, 1200, 6, 0.05, seed=17)
+    gor = G.gom_membership(t.taxo, t.gom_ids)
+    w = _weights(1200, 21, seed=3)
+    names = [f"v{i}" for i in range(300)]
+    one = Job(eng, t.sig, t.sig, gor, len(t.gom_ids), "PG", 1.0, distance=True)
+    base1 = one.base()
+    trees1, mats1 = {}, {}
+    one.for_each_tree(w, names, lambda b, s: trees1.__setitem__(b, s))
+    one.for_each_replicate(w, lambda b, m: mats1.__setitem__(b, m.copy()))
+    one.close()
+    mj = G.MultiJob(meng, t.sig, t.sig, gor, len(t.gom_ids), "PG", 1.0, distance=True)
+    try:
+        assert np.array_equal(mj.base(), base1)
+        order, trees, mats = [], {}, {}
+        mj.for_each_tree(w, names, lambda b, s: (order.append(b), trees.__setitem__(b, s)))
+        assert order == list(range(21)) and trees == trees1
+        order2 = []
+        mj.for_each_replicate(w, lambda b, m: (order2.append(b), mats.__setitem__(b, m.copy())))
+        assert order2 == list(range(21))
+        for b in range(21):
+            assert np.array_equal(mats[b], mats1[b])
+        gen = [m.copy() for m in mj.replicates(w[:5])]
+        assert all(np.array_equal(gen[b], mats1[b]) for b in range(5))
+    finally:
+        mj.close()
+    # the batched drop-in on every GPU: same lines as on one
+    payload = {"N_Bootstrap": 7, "SimilarityMeasurementScheme": "PG", "p": 1.0}
+    np.random.seed(5)
+    a = list(G.bootstrap_newick(t.sig, None, t.taxo, t.gom_ids, payload, names, pipeline="pl1", engine=eng))
+    np.random.seed(5)
+    b = list(G.bootstrap_newick(t.sig, None, t.taxo, t.gom_ids, payload, names, pipeline="pl1", engine=meng))
+    assert a == b
+    print(f"multi engine: {ndev} device(s), nccl={meng.uses_nccl}")
+    meng.close()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least two GPUs")
+def test_multi_engine_uses_nccl_allgather_on_two_or_more_gpus(eng):
+    import gravity2_b200 as G
+    meng = G.MultiEngine(None)
+    assert meng.n_devices >= 2 and meng.uses_nccl
+    t = synth.make_tables(700, 2000, 8, 0.03, seed=18)
+    gor = G.gom_membership(t.taxo, t.gom_ids)
+    mj = G.MultiJob(meng, t.sig, t.loc, gor, len(t.gom_ids), "PG", 1.0, distance=False)
+    try:
+        S = mj.base()
+    finally:
+        mj.close()
+    ref = eng.similarity(t.sig, eng.gom_table(t.loc, t.loc[np.argsort(gor, kind="stable")],
+                                              np.concatenate([[0], np.cumsum(np.bincount(gor, minlength=len(t.gom_ids)))])), None, "PG", 1.0)
+    assert np.abs(S - ref).max() <= 1e-6 and np.array_equal(S, S.T)
+    meng.close()
