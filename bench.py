@@ -526,7 +526,14 @@ def run_job(args, cfg):
     torch.cuda.empty_cache()
     e2e = e2e_mat = None
     dd = dist if world > 1 else None
-    if not args.no_e2e:
+    if not args.no_e2e and world > 1:
+        # N GPUs through the public API = ONE caller process driving all of them (gravity2_b200.MultiEngine: one host thread
+        # per GPU inside the library).  Rank 0 is that caller; the other ranks have released their GPUs and wait.
+        sync_all()
+        if rank == 0:
+            e2e = measure_e2e_multi(t, cfg, gor, weights, pairs, world)
+        dist.barrier()
+    elif not args.no_e2e:
         if B > 0 and not pl2:
             e2e = measure_e2e_trees(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch)
             if args.e2e_matrices:
@@ -799,12 +806,13 @@ def measure_e2e_trees(t, cfg, gor, weights, my_reps, pairs, world, rank, dist, t
         acc[0] += len(s)
         acc[1] += 1
 
+    # the un-resampled tree rides along as the all-ones "replicate" of rank 0 (same kernels, clustered with the others)
+    w_all = np.concatenate([np.ones((1, p), np.int32), w_mine]) if rank == 0 else w_mine
+
     def job_once():
         job = Job(eng, t.sig, t.sig, gor if "G" in scheme else None, g, scheme, 1.0, distance=True)
         try:
-            if rank == 0:
-                consume(-1, G.DistMat2Tree(job.base(), names, "average", False, engine=eng))
-            job.for_each_tree(w_mine, names, consume)
+            job.for_each_tree(w_all, names, consume)
         finally:
             job.close()
 
@@ -824,11 +832,51 @@ def measure_e2e_trees(t, cfg, gor, weights, my_reps, pairs, world, rank, dist, t
         dt = float(tt.item())
     eng.close()
     return {"value": pairs * (1 + B) / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int(n * p * 8 + w_mine.nbytes + gor.nbytes + (n * n * 8 if rank == 0 else 0)),
-            "d2h_bytes_per_step": int(len(my_reps) * (n - 1) * 32 + (n * n * 8 + (n - 1) * 32 if rank == 0 else 0)),
+            "h2d_bytes_per_step": int(n * p * 8 + w_all.nbytes + gor.nbytes),
+            "d2h_bytes_per_step": int(len(w_all) * (n - 1) * 32),
             "result": "one Newick string per replicate + the base tree (what app/src/pl1_graphs.py:108-117 keeps)",
-            "api": "gravity2_b200.engine.Job(sig, loc, ...).for_each_tree(weights, leaf_names, consumer) + DistMat2Tree(base): numpy in, "
-                   "one Newick string per replicate out (UPGMA on the device; per-rank bytes)"}
+            "api": "gravity2_b200.engine.Job(sig, loc, ...).for_each_tree(weights, leaf_names, consumer): numpy in, one Newick string "
+                   "per replicate (and for the un-resampled table, as the all-ones replicate) out; UPGMA on the device; per-rank bytes"}
+
+
+def measure_e2e_multi(t, cfg, gor, weights, pairs, world):
+    """The whole job through the public host API on ALL `world` GPUs from one process: MultiJob.base() + .for_each_tree (the
+    bootstrap loops' product) or, for the pipeline II workload, .for_each_replicate (matrices to host memory)."""
+    import gravity2_b200 as G
+    n, p, g, B, scheme, pl2 = cfg["n"], cfg["p"], len(t.gom_ids), cfg["b"], cfg["scheme"], cfg["pl2"]
+    meng = G.MultiEngine(list(range(world)))
+    names = [f"{x}_{i}" for i, x in enumerate(t.taxo)]
+    acc = [0]
+    trees = B > 0 and not pl2
+
+    def job_once():
+        job = G.MultiJob(meng, t.sig, t.loc if pl2 else t.sig, gor if "G" in scheme else None, g, scheme, 1.0, distance=True)
+        try:
+            if trees:
+                w_all = np.concatenate([np.ones((1, p), np.int32), weights])
+                job.for_each_tree(w_all, names, lambda b, s: acc.__setitem__(0, acc[0] + 1))
+            else:
+                base = job.base()
+                acc[0] += 1 + int(base[0, -1] < 0)
+                job.for_each_replicate(weights, lambda b, m: acc.__setitem__(0, acc[0] + 1 + int(m[0, -1] < 0)))
+        finally:
+            job.close()
+
+    job_once()          # warm-up
+    acc[0] = 0
+    t0 = time.perf_counter()
+    job_once()
+    dt = time.perf_counter() - t0
+    assert acc[0] == B + 1, "consumer did not see every replicate"
+    nccl = meng.uses_nccl
+    meng.close()
+    d2h = (B + 1) * (n - 1) * 32 if trees else (B + 1) * n * n * 8
+    return {"value": pairs * (1 + B) / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(n * p * 8 * (2 if pl2 and "G" in scheme else 1) + weights.nbytes + gor.nbytes),
+            "d2h_bytes_per_step": int(d2h), "nccl": nccl,
+            "result": "one Newick string per replicate + the base tree" if trees else "every replicate matrix in host memory",
+            "api": f"gravity2_b200.MultiEngine({world} GPUs) / MultiJob: ONE caller process, one host thread per GPU inside libgravity_b200 "
+                   "(tables uploaded once + NVLink broadcast, replicates by index, base tiles all-gathered)"}
 
 
 # --------------------------------------------------------------------- cfg4: presence / absence popcount path

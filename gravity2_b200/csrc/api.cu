@@ -263,6 +263,7 @@ struct gv2_job {
     DevBuf ones_w, sig_rowsum_fix;     // all-ones multiplicities and fixed-point row sums: the base matrix through the sparse path
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
+    cudaStream_t lk_stream[2] = {nullptr, nullptr};      // device UPGMA of the two ring halves, concurrent with the main stream
     size_t device_bytes() const {
         size_t b = sig64.bytes + loc64.bytes + sigf.bytes + sig_rowsum.bytes + sig_nan.bytes + gom_base.bytes +
                    wsP.bytes + wsG.bytes + gomtab.bytes + gomf.bytes + gom_rowsum.bytes + gom_nan.bytes + wf.bytes + w_rowsum.bytes;
@@ -287,6 +288,8 @@ extern "C" void gv2_job_destroy(gv2_job* job) {
         for (int h = 0; h < 2; ++h) { cudaEventDestroy(job->ev_ready[h]); cudaEventDestroy(job->ev_drained[h]); }
         cudaStreamDestroy(job->copy_stream);
     }
+    for (int h = 0; h < 2; ++h)
+        if (job->lk_stream[h]) { cudaStreamSynchronize(job->lk_stream[h]); cudaStreamDestroy(job->lk_stream[h]); }
     gom_db_free(job->gom);
     boot_sparse_free(job->sparse);
     delete job;
@@ -693,7 +696,9 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
     const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
     ring_len = std::min(ring_len, nb);
     // sub-chunk: half the ring when results stream to the host (ping-pong), else the whole ring
-    const int64_t sub = (!sink && host_out && ring_len >= 2) ? ring_len / 2 : ring_len;
+    // (dendrogram mode: the two halves are clustered on their own streams while the main stream computes the next ones)
+    const bool halves = ring_len >= 2 && ((!sink && host_out) || (sink && !dev_cb));
+    const int64_t sub = halves ? ring_len / 2 : ring_len;
     // super-chunk: bounded by the fp64 pair-sum workspace of the signature table (+ the GOM tables)
     const size_t per_rep = (job->need_p ? ntl * tile_elems * sizeof(double) + (size_t)job->p_pad : 0) +
                            (job->need_g ? (size_t)job->n_pad * job->g_pad * 4 + (size_t)n * g * 8 : 0) + (size_t)n * 8 * 2;
@@ -709,6 +714,9 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
         else if (super >= 128) super = super / 128 * 128;
         else if (super >= 32) super = super / 32 * 32;
     }
+    if (sink && !job->lk_stream[0])
+        for (int h = 0; h < 2; ++h) GV2_CUDA(ctx, cudaStreamCreateWithFlags(&job->lk_stream[h], cudaStreamNonBlocking));
+    bool lk_pending[2] = {false, false};
     if (!job->copy_stream) {
         GV2_CUDA(ctx, cudaStreamCreateWithFlags(&job->copy_stream, cudaStreamNonBlocking));
         for (int h = 0; h < 2; ++h) {
@@ -783,7 +791,11 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 cb = std::min<int64_t>(cb, ring_len - slot);
             } else {
                 if (slot + cb > ring_len) slot = 0;                        // sub-chunks never wrap inside the ring
-                if (host_out && ring_len >= 2) { slot = half * sub; }
+                if (halves) { slot = half * sub; }
+            }
+            if (sink && lk_pending[half]) {                                // the clustering that last read this half is done
+                GV2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, job->ev_drained[half], 0));
+                lk_pending[half] = false;
             }
             if (cb_fn) {
                 if ((rc = deliver(half))) return rc;                       // consumer is done with these host slots too
@@ -815,8 +827,19 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                     if (dev_cb(s0 + c0 + k, dev_ring + (slot + k) * n * n, cb_user) != 0)
                         return gv2_fail(ctx, GV2_ERR_ARG, "replicate callback asked to stop at replicate %lld", (long long)(s0 + c0 + k));
             }
-            if (sink) {     // cluster this sub-chunk on the device; meanwhile finish the previous one on the host
-                if ((rc = sink->enqueue(dev_ring + slot * n * n, s0 + c0, cb))) return rc;
+            if (sink) {     // cluster this sub-chunk on the device, on the half's own stream: the main stream goes on with the
+                            // next sub-chunk (and the next super-chunk's pair sums / GOM scoring); meanwhile the host finishes
+                            // the previous sub-chunk's trees
+                GV2_CUDA(ctx, cudaEventRecord(job->ev_ready[half], ctx->stream));
+                GV2_CUDA(ctx, cudaStreamWaitEvent(job->lk_stream[half], job->ev_ready[half], 0));
+                cudaStream_t main_stream = ctx->stream;
+                ctx->stream = job->lk_stream[half];
+                rc = sink->enqueue(dev_ring + slot * n * n, s0 + c0, cb);
+                ctx->stream = main_stream;
+                if (rc) return rc;
+                GV2_CUDA(ctx, cudaEventRecord(job->ev_drained[half], job->lk_stream[half]));
+                lk_pending[half] = true;
+                if (halves) half ^= 1;
                 if ((rc = sink->drain(sink->cur))) return rc;
             }
             if (host_out) {
