@@ -64,6 +64,8 @@ PROTOTYPES = {
     "gv2_dev_philox_weights": (C.c_int, [c_vp, C.c_uint64, c_i64, c_i64, c_i64, c_vp]),
     "gv2_job_create": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_i64, c_i64, c_vp, c_i64, c_i64, C.c_int, C.c_double,
                                  C.c_int, C.POINTER(c_vp)]),
+    "gv2_job_create_coo": (C.c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int,
+                                     C.c_double, C.c_int, C.POINTER(c_vp)]),
     "gv2_job_destroy": (None, [c_vp]),
     "gv2_job_base": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp]),
     "gv2_job_replicates": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),

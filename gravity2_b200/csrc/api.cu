@@ -480,6 +480,66 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
     return GV2_OK;
 }
 
+// ---- sparse (COO) input: the reference pickles its tables also as scipy coo_matrix (app/src/ref_virus_annotator.py:395-400);
+// real tables are ~99 % zeros, so the triplets are what crosses PCIe (16 bytes per hit instead of 8 bytes per cell) and the
+// dense float64 image the kernels convert from is rebuilt in HBM.
+__global__ void coo_scatter_kernel(const int* __restrict__ rows, const int* __restrict__ cols, const double* __restrict__ vals,
+                                   long long nnz, long long n, long long p, double* __restrict__ dense, int* __restrict__ bad) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    const long long r = rows[k], c = cols[k];
+    if (r < 0 || r >= n || c < 0 || c >= p) { atomicExch(bad, 1); return; }
+    dense[r * p + c] = vals[k];
+}
+
+static int coo_to_dense(gv2_ctx* ctx, const int32_t* rows, const int32_t* cols, const double* vals, int64_t nnz, int64_t n, int64_t p,
+                        DevBuf& dense) {
+    ALLOC(ctx, dense, (size_t)std::max<int64_t>(1, n * p) * sizeof(double));
+    GV2_CUDA(ctx, cudaMemsetAsync(dense.p, 0, dense.bytes, ctx->stream));
+    if (nnz == 0) return GV2_OK;
+    DevBuf r, c, v, flag;
+    ALLOC(ctx, r, (size_t)nnz * sizeof(int32_t));
+    ALLOC(ctx, c, (size_t)nnz * sizeof(int32_t));
+    ALLOC(ctx, v, (size_t)nnz * sizeof(double));
+    ALLOC(ctx, flag, sizeof(int));
+    GV2_CUDA(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
+    GV2_CUDA(ctx, cudaMemcpyAsync(r.p, rows, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    GV2_CUDA(ctx, cudaMemcpyAsync(c.p, cols, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    GV2_CUDA(ctx, cudaMemcpyAsync(v.p, vals, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    coo_scatter_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, ctx->stream>>>(r.as<int>(), c.as<int>(), v.as<double>(), nnz, n, p,
+                                                                               dense.as<double>(), flag.as<int>());
+    GV2_LAUNCH_CHECK(ctx);
+    int bad = 0;
+    GV2_CUDA(ctx, cudaMemcpyAsync(&bad, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GV2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad) return gv2_fail(ctx, GV2_ERR_ARG, "COO input: an entry lies outside the %lld x %lld table", (long long)n, (long long)p);
+    return GV2_OK;
+}
+
+extern "C" int gv2_job_create_coo(gv2_ctx* ctx, int64_t n, int64_t p, const int32_t* sig_rows, const int32_t* sig_cols,
+                                  const double* sig_vals, int64_t sig_nnz, const int32_t* loc_rows, const int32_t* loc_cols,
+                                  const double* loc_vals, int64_t loc_nnz, const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g,
+                                  int scheme, double power, int out_kind, gv2_job** out) {
+    if (!ctx || !out || n < 0 || p < 0 || sig_nnz < 0 || loc_nnz < 0 || (sig_nnz && (!sig_rows || !sig_cols || !sig_vals)) ||
+        (loc_nnz && (!loc_rows || !loc_cols || !loc_vals)))
+        return gv2_fail(ctx, GV2_ERR_ARG, "gv2_job_create_coo: bad arguments");
+    *out = nullptr;
+    GV2_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf sig, loc;
+    int rc;
+    if ((rc = coo_to_dense(ctx, sig_rows, sig_cols, sig_vals, sig_nnz, n, p, sig))) return rc;
+    const bool own_loc = loc_rows != nullptr;                     // NULL triplets: the signature table doubles as location table (PL1)
+    if (own_loc && (rc = coo_to_dense(ctx, loc_rows, loc_cols, loc_vals, loc_nnz, n, p, loc))) return rc;
+    gv2_job* j = nullptr;
+    rc = gv2_job_create(ctx, sig.as<double>(), scheme == GV2_SCHEME_P ? nullptr : (own_loc ? loc.as<double>() : sig.as<double>()), 1, n, p,
+                        gom_of_row, n_gom_rows, g, scheme, power, out_kind, &j);
+    if (rc) return rc;
+    j->sig64.p = sig.p; j->sig64.bytes = sig.bytes; sig.p = nullptr;      // the job owns the dense images now
+    if (own_loc) { j->loc64.p = loc.p; j->loc64.bytes = loc.bytes; loc.p = nullptr; }
+    *out = j;
+    return GV2_OK;
+}
+
 // GOM table (fp64 [nb][n][g]) -> padded tables [nb][n_pad][g_pad] + row sums + NaN flags: unsigned fixed point for the
 // replicates' fused tail (fixed != 0, one launch for all nb tables), fp32 for the base matrix's tile kernel
 static int job_prepare_gom(gv2_job* j, const double* tab64, int64_t nb, int fixed) {

@@ -357,7 +357,7 @@ def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, 
     app/src/pl1_graphs.py:78-117 (resample, GOM rebuild, distance matrix, DistMat2Tree) with everything up to the
     dendrogram on the device -- the 8 N^2 bytes of a replicate's distance matrix never cross PCIe.  Arguments as
     ``bootstrap_distance_matrices``; ``LeafList`` are the tree labels (TaxoLabelList)."""
-    sig = np.ascontiguousarray(PPHMMSignatureTable, dtype=np.float64)
+    sig = _as_table(PPHMMSignatureTable)
     n, p = sig.shape
     nb = int(payload["N_Bootstrap"] if N_Bootstrap is None else N_Bootstrap)
     scheme = payload["SimilarityMeasurementScheme"]
@@ -366,7 +366,7 @@ def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, 
         raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
     if method not in LINKAGE_METHODS:
         raise NotImplementedError(f"device linkage is built for methods {LINKAGE_METHODS} (got {method!r})")
-    loc = sig if pipeline == "pl1" else np.ascontiguousarray(PPHMMLocationTable, dtype=np.float64)
+    loc = sig if pipeline == "pl1" else _as_table(PPHMMLocationTable)
     gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
     job = _make_job(engine, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), True)
     try:
@@ -386,6 +386,33 @@ def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, 
 
 
 # ------------------------------------------------------------------------------ bootstrap
+def _as_table(tab):
+    """dense float64 C-order, or a scipy sparse matrix as it is (the *_coo tables of
+    RefVirusAnnotator.p go to the device as triplets)"""
+    from .engine import _is_sparse
+    return tab if _is_sparse(tab) else np.ascontiguousarray(tab, dtype=np.float64)
+
+
+def load_annotator_tables(pickle_file_or_dict, sparse: bool = True) -> dict:
+    """The tables of RefVirusAnnotator.p / UcfVirusAnnotator.p (app/src/ref_virus_annotator.py:390-402,
+    app/src/ucf_virus_annotator.py:53-58) in the form the batched entry points take: ``PPHMMSignatureTable`` and
+    ``PPHMMLocationTable`` as scipy COO matrices when the pickle carries them (sparse=True), else dense; every other key is
+    passed through."""
+    import pickle
+    d = pickle_file_or_dict
+    if not isinstance(d, dict):
+        with open(d, "rb") as fh:
+            d = pickle.load(fh)
+    out = dict(d)
+    for key in ("PPHMMSignatureTable", "PPHMMLocationTable"):
+        coo = d.get(key + "_coo")
+        if coo is not None:
+            from scipy.sparse import coo_matrix, issparse
+            # the unclassified-virus pickle stores `coo_matrix(T).toarray()` under the _coo key (ucf_virus_annotator.py:56-57)
+            out[key] = (coo if issparse(coo) else coo_matrix(np.asarray(coo))) if sparse else (coo.toarray() if issparse(coo) else np.asarray(coo))
+    return out
+
+
 def _make_job(engine, sig, loc, gor, g, scheme, p, distance):
     """One GPU (engine.Job) or every GPU of the node (multi.MultiJob): an explicit MultiEngine, or GRAVITY_B200_DEVICES
     naming more than one device when no engine is given."""
@@ -394,7 +421,9 @@ def _make_job(engine, sig, loc, gor, g, scheme, p, distance):
     if engine is None:
         engine = default_multi_engine()
     if isinstance(engine, MultiEngine):
-        return MultiJob(engine, sig, loc, gor, g, scheme, p, distance=distance)
+        from .engine import _is_sparse
+        dense = lambda a: a.toarray() if _is_sparse(a) else a  # noqa: E731  (the multi-GPU entry takes dense host tables)
+        return MultiJob(engine, dense(sig), sig if loc is sig else dense(loc), gor, g, scheme, p, distance=distance)
     return Job(engine or default_engine(), sig, loc, gor, g, scheme, p, distance=distance)
 
 
@@ -432,13 +461,13 @@ def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGro
     exactly as the reference draws them, replicate by replicate.
     Each yielded matrix is a zero-copy view into a pinned host ring: it is valid until the next one is
     requested (copy it to keep it), which is how the reference's loop uses it (tree, then discard)."""
-    sig = np.ascontiguousarray(PPHMMSignatureTable, dtype=np.float64)
+    sig = _as_table(PPHMMSignatureTable)
     n, p = sig.shape
     nb = int(payload["N_Bootstrap"] if N_Bootstrap is None else N_Bootstrap)
     scheme = payload["SimilarityMeasurementScheme"]
     if payload.get("PphmmNeighbourhoodWeight", 0) != 0 or payload.get("PphmmSigScoreThreshold", 0) != 0:
         raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
-    loc = sig if pipeline == "pl1" else np.ascontiguousarray(PPHMMLocationTable, dtype=np.float64)
+    loc = sig if pipeline == "pl1" else _as_table(PPHMMLocationTable)
     gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
     job = _make_job(engine, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance)
     try:

@@ -24,6 +24,19 @@ def _f64(a, name) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+def _is_sparse(a) -> bool:
+    return hasattr(a, "tocoo") and hasattr(a, "nnz")
+
+
+def _coo_triplets(a):
+    """(rows int32, cols int32, vals float64) of a scipy sparse matrix, explicit zeros dropped, duplicates summed"""
+    c = a.tocoo(copy=True)
+    c.sum_duplicates()
+    c.eliminate_zeros()
+    return (np.ascontiguousarray(c.row, dtype=np.int32), np.ascontiguousarray(c.col, dtype=np.int32),
+            np.ascontiguousarray(c.data, dtype=np.float64))
+
+
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -227,17 +240,31 @@ class Job:
         if scheme not in ("P", "G", "PG"):
             raise NotImplementedError(f"device jobs cover schemes P, G, PG (got {scheme!r})")
         self.eng, self.lib, self.ctx = eng, eng.lib, eng.ctx
-        sig = _f64(sig, "PPHMMSignatureTable")
-        self.n, self.p = sig.shape
         self.g = int(g)
-        loc_arr = sig if (loc is sig or loc is None) else _f64(loc, "PPHMMLocationTable")
         gor = None if gom_of_row is None else np.ascontiguousarray(gom_of_row, dtype=np.int32)
         self.job = C.c_void_p()
-        # the same host pointer for sig and loc (PL1, quirk Q3) is uploaded once by the library
-        _lib.check(self.ctx, self.lib.gv2_job_create(
-            self.ctx, _ptr(sig), _ptr(loc_arr if "G" in scheme else None), 0, self.n, self.p, _ptr(gor),
-            0 if gor is None else len(gor), int(g), SCHEMES[scheme], float(p),
-            OUT_DISTANCE if distance else OUT_SIMILARITY, C.byref(self.job)))
+        if _is_sparse(sig):
+            # scipy sparse tables (the *_coo entries of RefVirusAnnotator.p, app/src/ref_virus_annotator.py:395-400): only the
+            # triplets cross PCIe, the dense images are rebuilt in HBM
+            self.n, self.p = sig.shape
+            sr, sc, sv = _coo_triplets(sig)
+            same = loc is sig or loc is None
+            if not same and not _is_sparse(loc):
+                raise TypeError("sparse signature table with a dense location table: pass both as scipy sparse or both dense")
+            lr, lc, lv = (None, None, None) if same or "G" not in scheme else _coo_triplets(loc)
+            _lib.check(self.ctx, self.lib.gv2_job_create_coo(
+                self.ctx, self.n, self.p, _ptr(sr), _ptr(sc), _ptr(sv), len(sv), _ptr(lr), _ptr(lc), _ptr(lv), 0 if lv is None else len(lv),
+                _ptr(gor), 0 if gor is None else len(gor), int(g), SCHEMES[scheme], float(p),
+                OUT_DISTANCE if distance else OUT_SIMILARITY, C.byref(self.job)))
+        else:
+            sig = _f64(sig, "PPHMMSignatureTable")
+            self.n, self.p = sig.shape
+            loc_arr = sig if (loc is sig or loc is None) else _f64(loc, "PPHMMLocationTable")
+            # the same host pointer for sig and loc (PL1, quirk Q3) is uploaded once by the library
+            _lib.check(self.ctx, self.lib.gv2_job_create(
+                self.ctx, _ptr(sig), _ptr(loc_arr if "G" in scheme else None), 0, self.n, self.p, _ptr(gor),
+                0 if gor is None else len(gor), int(g), SCHEMES[scheme], float(p),
+                OUT_DISTANCE if distance else OUT_SIMILARITY, C.byref(self.job)))
         self.ntiles = int(self.lib.gv2_num_tiles(self.n))
         mat = max(1, self.n * self.n * 8)
         self.ring_len = max(2, int(ring_bytes // mat))       # two halves: one computing, one draining

@@ -176,6 +176,14 @@ typedef int (*gv2_replicate_cb)(int64_t replicate, const double* matrix /* [n][n
 int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc, int tables_are_device,
                    int64_t n, int64_t p, const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g,
                    int scheme, double power, int out_kind, gv2_job** out);
+/* The same job from COO triplets in HOST memory (rows / cols int32, vals float64, no duplicate cells): the form the reference
+ * pickles beside the dense tables (PPHMMSignatureTable_coo / PPHMMLocationTable_coo, app/src/ref_virus_annotator.py:395-400).
+ * 16 bytes per hit cross PCIe instead of 8 bytes per cell; the dense images are rebuilt in HBM.  loc_rows == NULL: the
+ * signature table doubles as location table (PL1, quirk Q3). */
+int gv2_job_create_coo(gv2_ctx* ctx, int64_t n, int64_t p, const int32_t* sig_rows, const int32_t* sig_cols, const double* sig_vals,
+                       int64_t sig_nnz, const int32_t* loc_rows, const int32_t* loc_cols, const double* loc_vals, int64_t loc_nnz,
+                       const int32_t* gom_of_row, int64_t n_gom_rows, int64_t g, int scheme, double power, int out_kind,
+                       gv2_job** out);
 void gv2_job_destroy(gv2_job* job);
 /* Base (un-resampled) matrix for pair tiles [tile_begin, tile_end) of the upper triangle:
  *   packed == 0: writes the tiles (and their mirrors) into dev_out [n][n];

@@ -496,3 +496,38 @@ def test_multi_engine_uses_nccl_allgather_on_two_or_more_gpus(eng):
                                               np.concatenate([[0], np.cumsum(np.bincount(gor, minlength=len(t.gom_ids)))])), None, "PG", 1.0)
     assert np.abs(S - ref).max() <= 1e-6 and np.array_equal(S, S.T)
     meng.close()
+
+
+def test_sparse_coo_tables_equal_dense_tables(eng, tmp_path):
+    """the *_coo tables the reference pickles (app/src/ref_virus_annotator.py:395-400) go to the device as
+    triplets; everything downstream is bit-identical to the dense upload"""
+    import pickle
+    from scipy.sparse import coo_matrix
+    import gravity2_b200 as G
+    from gravity2_b200.engine import Job
+    t = synth.make_tables(200, 1500, 6, 0.04, seed=19)
+    gor = G.gom_membership(t.taxo, t.gom_ids)
+    w = _weights(1500, 9, seed=4)
+    f = os.path.join(tmp_path, "RefVirusAnnotator.p")
+    with open(f, "wb") as fh:       # the keys pl1 writes
+        pickle.dump({"PPHMMSignatureTable": t.sig, "PPHMMLocationTable": t.loc, "GOMIDList": t.gom_ids,
+                     "PPHMMSignatureTable_coo": coo_matrix(t.sig), "PPHMMLocationTable_coo": coo_matrix(t.loc)}, fh)
+    tabs = G.load_annotator_tables(f)
+    assert tabs["PPHMMSignatureTable"].nnz == np.count_nonzero(t.sig)
+    out = {}
+    for kind, (sg, lc) in {"dense": (t.sig, t.loc), "coo": (tabs["PPHMMSignatureTable"], tabs["PPHMMLocationTable"])}.items():
+        job = Job(eng, sg, lc, gor, len(t.gom_ids), "PG", 1.0, distance=True)
+        reps = {}
+        job.for_each_replicate(w, lambda b, m: reps.__setitem__(b, m.copy()))
+        out[kind] = (job.base(), reps)
+        job.close()
+    assert np.array_equal(out["dense"][0], out["coo"][0])
+    for b in range(9):
+        assert np.array_equal(out["dense"][1][b], out["coo"][1][b])
+    payload = {"N_Bootstrap": 3, "SimilarityMeasurementScheme": "PG", "p": 1.0}
+    names = [f"v{i}" for i in range(200)]
+    np.random.seed(2)
+    a = list(G.bootstrap_newick(t.sig, None, t.taxo, t.gom_ids, payload, names, pipeline="pl1"))
+    np.random.seed(2)
+    b = list(G.bootstrap_newick(tabs["PPHMMSignatureTable"], None, t.taxo, t.gom_ids, payload, names, pipeline="pl1"))
+    assert a == b
