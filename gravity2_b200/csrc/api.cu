@@ -18,7 +18,7 @@ int gj_min_sums_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64
                        double* ws);
 int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k, int64_t k_pad, int64_t nb,
                     const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
-                    double* out, int64_t out_replicate_stride, int fixed);
+                    double* out, int64_t out_replicate_stride, int fixed, double p_scale);
 int gom_quantize_launch(gv2_ctx* ctx, const double* tab64, int64_t n, int64_t g, int64_t nb, unsigned* dst, int64_t n_pad, int64_t g_pad,
                         double* rowsum, uint8_t* nanflag, unsigned long long* scratch);
 
@@ -253,6 +253,7 @@ struct gv2_job {
     int64_t n_nan_cells = 0;
     DevBuf sigfix;                     // 32-bit fixed-point signature table for the tensor-core path
     double quantum = 0.0;
+    double p_scale = 1.0;              // power of two <= 1 / (largest possible weighted row sum): the fused tail's PPHMM sums land in (0, 1]
     bool mma_ok = false;
     BootSparse* sparse = nullptr;      // CSR of the fixed-point table when the sparse replicate path is chosen
     GomDb* gom = nullptr;
@@ -421,6 +422,11 @@ extern "C" int gv2_job_create(gv2_ctx* ctx, const double* sig, const double* loc
             int neg = 0;
             if ((rc = boot_table_stats(ctx, j->d_sig, n, p, p, &mx, &neg))) return bail(rc);
             (void)neg;                                   // negative entries are zeroed by the threshold: x <= 0 -> 0 in both images
+            if (isfinite(mx) && mx > 0.0) {              // sum_c w_c x_c <= max(x) * sum_c w_c, multiplicities are <= 255 each
+                int e = 0;
+                frexp(mx * 255.0 * (double)std::max<int64_t>(1, p), &e);
+                j->p_scale = ldexp(1.0, -e);
+            }
             const bool usable = isfinite(mx);
             const char* path = getenv("GV2_BOOT_PATH");
             const bool want_fp32 = path && !strcmp(path, "fp32");
@@ -876,7 +882,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 cg.ksplit = 1; cg.replicate_stride_rows = n; cg.replicate_stride_nan = n;
                 if ((rc = gj_fused_launch(ctx, job->gomf.as<float>() + (size_t)c0 * job->n_pad * job->g_pad, job->n_pad * job->g_pad, n,
                                           job->n_pad, g, job->g_pad, cb, job->need_p ? &cp : nullptr, &cg, job->scheme, job->power,
-                                          job->out_kind, dev_ring + slot * n * n, n * n, 1))) return rc;
+                                          job->out_kind, dev_ring + slot * n * n, n * n, 1, job->p_scale))) return rc;
             } else {
                 if ((rc = gv2_dev_gj_epilogue(ctx, n, 0, ntl, cb, &cp, &cg, nullptr, job->scheme, job->power, job->out_kind, 0,
                                               dev_ring + slot * n * n, n * n))) return rc;

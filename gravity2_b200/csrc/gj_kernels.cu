@@ -75,6 +75,7 @@ struct GjFuse {
     long long n;
     int scheme, out_kind;
     double pw;
+    double p_scale;          // power of two that brings the PPHMM sums to <= 1 (FIXED epilogue: fp32-safe reciprocal square root seed)
     double* out;             // [nb][n][n]
     long long out_b_stride;
 };
@@ -100,6 +101,13 @@ __device__ __forceinline__ double gj_rcp(double x) {
     r = r * fma(-x, r, 2.0);
     r = r * fma(-x, r, 2.0);
     return r * sc;
+}
+
+// one MUFU.RSQ: the operand is a normal fp32 number by construction (no denormal handling needed)
+__device__ __forceinline__ float gj_rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 __device__ __forceinline__ void gj_mad1(unsigned& acc, unsigned m, unsigned one) {
@@ -266,7 +274,9 @@ static size_t gf_smem_bytes() { return (size_t)GF_STAGES * GF_STAGE_FLOATS * siz
 // all 32 PPHMM pair sums of the thread in one batch -- and duplicate genomes give exactly S = 1.  The add is written as a
 // multiply-add by `one` (a kernel argument equal to 1) so that it issues on the FMA pipe (IMAD) while the min issues on the ALU
 // pipe: one instruction per pipe and cell, as in the fp32 variant (FMNMX + FADD).
-template <bool FIXED>
+// HAS_P / POWERED are compile-time so that the common case (scheme PG, p == 1) carries neither the pow() call nor its
+// divergence bookkeeping: the epilogue is ~40 straight-line instructions per cell (it was ~200, half the main loop's cost).
+template <bool FIXED, bool HAS_P, bool POWERED>
 __global__ void __launch_bounds__(GJ_THREADS, 2)
 gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int nkb, int k_groups, int nt, const GjFuse fz, unsigned one) {
     extern __shared__ __align__(16) float smem[];
@@ -310,7 +320,7 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
         if (s < nkb) load_stage(s, s);
         cp_async_commit();
     }
-    if (fz.P.ws != nullptr) {
+    if (HAS_P) {
         // the 64 KB of PPHMM pair sums this CTA reads in its epilogue: pull them into L2 now, under the main loop
         // (element (r, c) of the tile is at [r/16][c/16][r%16][c%16]: per r/16 the CTA's half is 8 KB contiguous)
         const double* pw = fz.P.ws + b * fz.P.b_stride_ws + t * (long long)(GV2_TILE * GV2_TILE);
@@ -377,34 +387,36 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
     const double qnan = nan("");
     const double* g_rs = fz.g_rowsum + b * fz.g_stride_row;
     const unsigned char* g_nf = fz.g_nan ? fz.g_nan + b * fz.g_stride_nan : nullptr;
-    const bool has_p = fz.P.ws != nullptr;
-    const double* p_ws = has_p ? fz.P.ws + b * fz.P.b_stride_ws + t * (long long)(GV2_TILE * GV2_TILE) : nullptr;
-    const double* p_rs = has_p ? fz.P.rowsum + b * fz.P.b_stride_row : nullptr;
-    const unsigned char* p_nf = (has_p && fz.P.nan) ? fz.P.nan + b * fz.P.b_stride_nan : nullptr;
+    const double* p_ws = HAS_P ? fz.P.ws + b * fz.P.b_stride_ws + t * (long long)(GV2_TILE * GV2_TILE) : nullptr;
+    const double* p_rs = HAS_P ? fz.P.rowsum + b * fz.P.b_stride_row : nullptr;
+    const unsigned char* p_nf = (HAS_P && fz.P.nan) ? fz.P.nan + b * fz.P.b_stride_nan : nullptr;
     double* o = fz.out + b * fz.out_b_stride;
     double* stage = reinterpret_cast<double*>(smem);                 // [64 columns][GJ_STAGE_LD]: the mirror transpose
-    const bool powered = fz.pw != 1.0, as_distance = fz.out_kind == GV2_OUT_DISTANCE;
+    const bool as_distance = fz.out_kind == GV2_OUT_DISTANCE;
+    const double psc = fz.p_scale;
     // row sums of the partner genomes; a genome with a NaN entry gets NaN sums, which the `> 0` tests below turn into 0
+    // (the PPHMM sums are scaled by a power of two: exact, and the ratio does not see it)
     double gsj[4], psj[4];
 #pragma unroll
     for (int nn = 0; nn < 4; ++nn) {
         const long long gj = (long long)bj * GV2_TILE + half * 64 + tx + 16 * nn;
         const bool ok = gj < n;
         gsj[nn] = ok ? ((g_nf && g_nf[gj]) ? qnan : g_rs[gj]) : 0.0;
-        psj[nn] = (ok && has_p) ? ((p_nf && p_nf[gj]) ? qnan : p_rs[gj]) : 0.0;
+        psj[nn] = (ok && HAS_P) ? ((p_nf && p_nf[gj]) ? qnan : p_rs[gj] * psc) : 0.0;
     }
     __syncthreads();                                                 // the ring is dead: reuse it as the transpose stage
     // Two instances of the same loop body: interior off-diagonal tiles (all but ~2 n/128 of them) need no bounds tests,
-    // no diagonal special case and no index swap, which removes about a third of the epilogue's instructions.
+    // no diagonal special case and no index swap.
     auto rows = [&](auto fast_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
         double* orow = o + ((long long)bi * GV2_TILE + ty) * n + (long long)bj * GV2_TILE + half * 64 + tx;
-        // FIXED frees the registers of the fp64 running sums: all 32 pair sums of the thread are requested at once (one
-        // memory latency for the whole epilogue instead of one per row group)
-        double pall[FIXED && FAST ? 4 : 1][4];
+        const long long row_step = 16 * n;
+        // FIXED frees the registers of the fp64 running sums: the pair sums of the thread are requested 16 at a time (one
+        // memory latency per batch instead of one per row group)
+        double pall[(FIXED && FAST && HAS_P) ? 4 : 1][4];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            if (FIXED && FAST && has_p && (m & 3) == 0) {              // 16 pair sums per batch, two batches
+        for (int m = 0; m < 8; ++m, orow += row_step) {
+            if (FIXED && FAST && HAS_P && (m & 3) == 0) {
 #pragma unroll
                 for (int mm = 0; mm < 4; ++mm)
 #pragma unroll
@@ -414,19 +426,21 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
             const long long gi = (long long)bi * GV2_TILE + r;
             const bool oki = FAST || gi < n;
             const double gsi = oki ? ((g_nf && g_nf[gi]) ? qnan : g_rs[gi]) : 0.0;
-            const double psi = (oki && has_p) ? ((p_nf && p_nf[gi]) ? qnan : p_rs[gi]) : 0.0;
+            const double psi = (oki && HAS_P) ? ((p_nf && p_nf[gi]) ? qnan : p_rs[gi] * psc) : 0.0;
             double pv[4];
 #pragma unroll
             for (int nn = 0; nn < 4; ++nn) {
-                if (FIXED && FAST) {
-                    pv[nn] = has_p ? pall[m & 3][nn] : 0.0;
+                if (!HAS_P) {
+                    pv[nn] = 0.0;
+                } else if (FIXED && FAST) {
+                    pv[nn] = pall[m & 3][nn] * psc;
                 } else if (FAST) {
-                    pv[nn] = has_p ? p_ws[(size_t)((m * 8 + half * 4 + nn) * 256 + tid)] : 0.0;   // == gj_ws_index(r, c)
+                    pv[nn] = p_ws[(size_t)((m * 8 + half * 4 + nn) * 256 + tid)] * psc;   // == gj_ws_index(r, c)
                 } else {
                     const int c = half * 64 + tx + 16 * nn;
                     // diagonal tiles: the replicate kernels leave the entries below the diagonal unwritten
                     const int rr = (bi == bj && r > c) ? c : r, cc = (bi == bj && r > c) ? r : c;
-                    pv[nn] = has_p ? p_ws[gj_ws_index(rr, cc)] : 0.0;
+                    pv[nn] = p_ws[gj_ws_index(rr, cc)] * psc;
                 }
             }
 #pragma unroll
@@ -435,26 +449,35 @@ gj_fused_kernel(const float* __restrict__ tab, long long tab_stride, int ld, int
                 const long long gj = (long long)bj * GV2_TILE + half * 64 + cl;
                 // GJ = sum(min) / sum(max), 0 when sum(max) == 0 (:168), NaN and negatives cleaned to 0 (:204-205), then
                 // (P * G) ** 0.5 (:214) as ONE reciprocal square root: sqrt(Np Ng / (Dp Dg)) = Np Ng rsqrt(Np Ng Dp Dg).
-                // N D > 0 says: sum(max) != 0, ratio positive, nothing NaN.
+                // num > 0 and den > 0 say: both sum(max) != 0, both ratios positive, nothing NaN (all sums are >= 0).
                 const bool diag = !FAST && gi == gj;
                 const double ng = diag ? gsi : (FIXED ? (double)iacc[m][nn] : sum[m][nn]);   // diagonal: sum(min) == sum(a) exactly
                 const double dg = gsi + gsj[nn] - ng;
-                const double ag = ng * dg;
                 double sv;
-                if (has_p) {
+                if (HAS_P) {
                     const double np_ = diag ? psi : pv[nn];
                     const double dp = psi + psj[nn] - np_;
-                    const double ap = np_ * dp;
-                    const double num = np_ * ng, den = dp * dg, x = ag * ap;
-                    sv = (num == den) ? 1.0 : fabs(num) * gj_rsqrt(x);   // == : diagonal, duplicate genomes
-                    if (!(ag > 0.0 && ap > 0.0)) sv = 0.0;
+                    const double num = np_ * ng, den = dp * dg, x = num * den;
+                    double rq;
+                    if (FIXED) {
+                        // Ng, Dg are integers in [1, 2^32], Np, Dp lie in [2^-71, 1] after the scaling: both products are fp32
+                        // normal numbers, so the seed needs no range handling; two Newton steps in fp64 (22 -> 44 -> 88 bits)
+                        rq = (double)(gj_rsqrt_approx((float)num) * gj_rsqrt_approx((float)den));
+                        const double hx = 0.5 * x;
+                        rq = rq * fma(-hx * rq, rq, 1.5);
+                        rq = rq * fma(-hx * rq, rq, 1.5);
+                    } else {
+                        rq = gj_rsqrt(x);
+                    }
+                    sv = (num == den) ? 1.0 : num * rq;              // == : diagonal, duplicate genomes
+                    if (!(num > 0.0 && den > 0.0)) sv = 0.0;
                 } else {
-                    sv = (ng == dg) ? 1.0 : fabs(ng) * gj_rcp(fabs(dg));
-                    if (!(ag > 0.0)) sv = 0.0;
+                    sv = (ng == dg) ? 1.0 : ng * gj_rcp(fabs(dg));
+                    if (!(ng > 0.0 && dg > 0.0)) sv = 0.0;
                 }
-                if (powered) sv = pow(sv, fz.pw);                    // :226 (sv >= 0 already, :224)
+                if (POWERED) sv = pow(sv, fz.pw);                    // :226 (sv >= 0 already, :224)
                 if (as_distance) sv = fmax(1.0 - sv, 0.0);           // pl1_graphs.py:52-53
-                if (FAST || (oki && gj < n)) orow[(long long)(16 * m) * n + 16 * nn] = sv;
+                if (FAST || (oki && gj < n)) orow[16 * nn] = sv;
                 stage[cl * GJ_STAGE_LD + r] = sv;
             }
         }
@@ -830,7 +853,7 @@ int gom_quantize_launch(gv2_ctx* ctx, const double* tab64, int64_t n, int64_t g,
 // fixed != 0: `tab` holds the unsigned fixed-point image written by gom_quantize_launch (exact integer cell arithmetic).
 int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t n, int64_t n_pad, int64_t k, int64_t k_pad, int64_t nb,
                     const gv2_gj_component* comp_p, const gv2_gj_component* comp_g, int scheme, double power, int out_kind,
-                    double* out, int64_t out_replicate_stride, int fixed) {
+                    double* out, int64_t out_replicate_stride, int fixed, double p_scale) {
     if (scheme != GV2_SCHEME_G && scheme != GV2_SCHEME_PG) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: scheme %d", scheme);
     if (!tab || !comp_g || !comp_g->rowsums || !out || (k_pad % GV2_BK) || (n_pad % GV2_TILE) || k < 0 || k > k_pad ||
         (scheme == GV2_SCHEME_PG && (!comp_p || !comp_p->min_sums || !comp_p->rowsums || comp_p->ksplit != 1)))
@@ -840,9 +863,13 @@ int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t 
     if (nb > 65535) return gv2_fail(ctx, GV2_ERR_ARG, "gj_fused_launch: nb > 65535");
     const size_t smem = gf_smem_bytes();
     static_assert(GF_STAGES * GF_STAGE_FLOATS * sizeof(float) >= 64 * GJ_STAGE_LD * sizeof(double), "transpose stage must fit the ring");
+    typedef void (*fused_fn)(const float*, long long, int, int, int, int, const GjFuse, unsigned);
+    static const fused_fn table[8] = {gj_fused_kernel<false, false, false>, gj_fused_kernel<false, false, true>,
+                                      gj_fused_kernel<false, true, false>,  gj_fused_kernel<false, true, true>,
+                                      gj_fused_kernel<true, false, false>,  gj_fused_kernel<true, false, true>,
+                                      gj_fused_kernel<true, true, false>,   gj_fused_kernel<true, true, true>};
     if (!(ctx->smem_attr_done & GV2_ATTR_FUSED)) {
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GV2_CUDA(ctx, cudaFuncSetAttribute(gj_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int v = 0; v < 8; ++v) GV2_CUDA(ctx, cudaFuncSetAttribute((const void*)table[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->smem_attr_done |= GV2_ATTR_FUSED;
     }
     GjFuse fz{};
@@ -850,15 +877,14 @@ int gj_fused_launch(gv2_ctx* ctx, const float* tab, int64_t tab_stride, int64_t 
     fz.g_rowsum = comp_g->rowsums; fz.g_nan = comp_g->nanflags;
     fz.g_stride_row = comp_g->replicate_stride_rows; fz.g_stride_nan = comp_g->replicate_stride_nan;
     fz.n = n; fz.scheme = scheme; fz.out_kind = out_kind; fz.pw = power; fz.out = out; fz.out_b_stride = out_replicate_stride;
+    fz.p_scale = p_scale > 0.0 ? p_scale : 1.0;
     dim3 grid((unsigned)(2 * ntl), 1, (unsigned)nb);
     Gv2Timer timer(ctx, GV2_TIME_TAIL);
     timer.begin();
     const int k_groups = (int)((k + 3) / 4);                     // 4-column groups that hold real columns
     const int nkb = (int)((k + GV2_BK - 1) / GV2_BK);            // stages that hold real columns
-    if (fixed)
-        gj_fused_kernel<true><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, nkb, k_groups, (int)(n_pad / GV2_TILE), fz, 1u);
-    else
-        gj_fused_kernel<false><<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, nkb, k_groups, (int)(n_pad / GV2_TILE), fz, 1u);
+    const int variant = (fixed ? 4 : 0) + (scheme == GV2_SCHEME_PG ? 2 : 0) + (power != 1.0 ? 1 : 0);
+    table[variant]<<<grid, GJ_THREADS, smem, ctx->stream>>>(tab, tab_stride, (int)k_pad, nkb, k_groups, (int)(n_pad / GV2_TILE), fz, 1u);
     GV2_LAUNCH_CHECK(ctx);
     timer.end();
     return GV2_OK;
@@ -870,7 +896,7 @@ extern "C" int gv2_dev_gj_fused(gv2_ctx* ctx, const float* tab, int64_t tab_repl
                                 int64_t out_replicate_stride) {
     if (!ctx) return GV2_ERR_ARG;
     return gj_fused_launch(ctx, tab, tab_replicate_stride, n, n_pad, k, k_pad, nb, comp_p, comp_g, scheme, p, out_kind, out,
-                           out_replicate_stride, 0);
+                           out_replicate_stride, 0, 1.0);
 }
 
 extern "C" int gv2_dev_gj_min_sums(gv2_ctx* ctx, const float* tab, int64_t n_pad, int64_t k_pad,

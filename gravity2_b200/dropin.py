@@ -196,7 +196,7 @@ def braycurtis_matrix(arr, engine: Optional[Engine] = None):
     empty = ~(A != 0).any(axis=1)
     if empty.any():
         out[np.ix_(empty, empty)] = np.nan
-    np.fill_diagonal(out, np.where(empty, np.nan, 0.0))
+    np.fill_diagonal(out, 0.0)                      # pairwise_distances pins the diagonal to 0, also for all-zero rows
     return out
 
 
