@@ -231,6 +231,7 @@ gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ me
                       const double* __restrict__ X, const double* __restrict__ nrm, const double* __restrict__ nrm2,
                       const double* __restrict__ wG, const double* __restrict__ arT, double* __restrict__ gagg) {
     __shared__ double red[8][7][NBC];
+    __shared__ double cred[8][8][NBC];
     const int g = blockIdx.x, b = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
     const int mg = mem_ptr[g + 1] - mem_ptr[g];
@@ -245,14 +246,39 @@ gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ me
         AR2 = fma(w * ar, ar, AR2);
         ARN = fma(w * ar, nr, ARN);
     }
+    // weighted centroid C_j = sum_k w_k X_kj, eight member coordinates at a time: the warps split the points, every point
+    // costs one multiplicity load and eight broadcast coordinate loads for eight FMAs; the partial centroids meet in shared
+    // memory and warp 0 accumulates |C|^2
     const double* x = X + x_off[g];
-    for (int j = wi; j < mg; j += 8) {
-        double c = 0.0;
-        for (int k = 0; k < ng; ++k) c = fma(wG[(long long)(p0 + k) * NBC + b], x[(long long)k * mg + j], c);
-        CS = fma(c, c, CS);
+    for (int j0 = 0; j0 < mg; j0 += 8) {
+        double c[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c[q] = 0.0;
+        const int jn = min(8, mg - j0);
+#pragma unroll 2
+        for (int k = wi; k < ng; k += 8) {
+            const double w = wG[(long long)(p0 + k) * NBC + b];
+            const double* xr = x + (long long)k * mg + j0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (q < jn) c[q] = fma(w, __ldg(xr + q), c[q]);
+        }
+        __syncthreads();                                         // cred of the previous tile has been consumed
+#pragma unroll
+        for (int q = 0; q < 8; ++q) cred[wi][q][b] = c[q];
+        __syncthreads();
+        if (wi == 0) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                double t = 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t += cred[u][q][b];
+                CS = fma(t, t, CS);
+            }
+        }
     }
     red[wi][0][b] = n; red[wi][1][b] = N1; red[wi][2][b] = N2; red[wi][3][b] = AR1; red[wi][4][b] = AR2; red[wi][5][b] = ARN;
-    red[wi][6][b] = CS;
+    red[wi][6][b] = wi == 0 ? CS : 0.0;
     __syncthreads();
     if (wi == 0) {
         double t[7];
@@ -391,14 +417,14 @@ __device__ __forceinline__ double vg_finish(const VgSums& S, const double* __res
         const double rowB = RR2 + 2.0 * z * RY + z * z * Y2 + z * Y1 * Y1;
         const double Saa = SAA + 2.0 * e * N2;
         const double Sbb = 2.0 * T * Y2 - 2.0 * Ys * Ys + 2.0 * z * Y2;
-        const double sAB = Sab - 2.0 / nn * cross + a_tot * b_tot / (nn * nn);
-        const double sAA = Saa - 2.0 / nn * rowA + a_tot * a_tot / (nn * nn);
-        const double sBB = Sbb - 2.0 / nn * rowB + b_tot * b_tot / (nn * nn);
-        // dcor.py:10,17,54-60
-        const double dcov = sqrt(sAB) / nn;            // NaN if the sum rounds below zero, as numpy
-        const double dvA = sqrt(sAA / (nn * nn));
-        const double dvB = sqrt(sBB / (nn * nn));
-        if (dvA > 0.0 && dvB > 0.0) res = dcov / sqrt(dvA * dvB);
+        // one reciprocal instead of nine divisions: centred sums = un-centred sum - 2/n (row products) + (total products)/n^2
+        const double inn = 1.0 / nn, inn2 = inn * inn;
+        const double sAB = Sab - 2.0 * inn * cross + a_tot * b_tot * inn2;
+        const double sAA = Saa - 2.0 * inn * rowA + a_tot * a_tot * inn2;
+        const double sBB = Sbb - 2.0 * inn * rowB + b_tot * b_tot * inn2;
+        // dcor.py:10,17,54-60: dcov = sqrt(sAB) / n, dvar = sqrt(s..) / n, dcor = dcov / sqrt(dvarA dvarB) -- the n cancel:
+        // dcor = sqrt(sAB / sqrt(sAA sBB)); NaN if sAB rounds below zero, as numpy; 0 unless both variances are > 0
+        if (sAA > 0.0 && sBB > 0.0) res = sqrt(sAB / sqrt(sAA * sBB));
     }
     return res;
 }
@@ -406,7 +432,7 @@ __device__ __forceinline__ double vg_finish(const VgSums& S, const double* __res
 // Pair records, pass 1: |I| of every pair.  One warp per pair, genome-major.  grid = ceil(n*G/8), block = 256
 __global__ void __launch_bounds__(256)
 gom_pair_count_kernel(long long n, int G, long long p, const long long* __restrict__ ptr, const int* __restrict__ col,
-                      const int* __restrict__ pos, int* __restrict__ ni_out, long long* __restrict__ bytes_out) {
+                      const int* __restrict__ pos, int cap, int* __restrict__ ni_out, long long* __restrict__ bytes_out) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (wid >= n * G) return;
@@ -423,8 +449,11 @@ gom_pair_count_kernel(long long n, int G, long long p, const long long* __restri
     }
     if (lane == 0) {
         ni_out[wid] = ni;
-        // records start 32-byte aligned: the entries are read and written with 16-byte accesses
-        bytes_out[wid] = (long long)ni * 32 + (((long long)ni * (ni - 1) / 2 * 8 + 31) & ~31LL);
+        // records start 32-byte aligned: the entries are read and written with 16-byte accesses.  Light records (|I| <= cap)
+        // are laid out first, genome-major, so that a genome's light records are ONE contiguous range; heavy ones follow
+        const long long sz = (long long)ni * 32 + (((long long)ni * (ni - 1) / 2 * 8 + 31) & ~31LL);
+        bytes_out[wid] = ni <= cap ? sz : 0;
+        bytes_out[n * G + wid] = ni <= cap ? 0 : sz;
     }
 }
 
@@ -433,7 +462,7 @@ __global__ void __launch_bounds__(256)
 gom_pair_fill_kernel(long long n, int G, long long p, const long long* __restrict__ ptr, const int* __restrict__ col,
                      const double* __restrict__ val, const int* __restrict__ pos, const int* __restrict__ pt_ptr,
                      const double* __restrict__ nrm, const long long* __restrict__ a_off, const double* __restrict__ A,
-                     const int* __restrict__ pr_ni, const long long* __restrict__ pr_ptr, unsigned char* __restrict__ rec) {
+                     const int* __restrict__ pr_ni, const long long* __restrict__ pr_ptr, int cap, unsigned char* __restrict__ rec) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (wid >= n * G) return;
@@ -445,7 +474,7 @@ gom_pair_fill_kernel(long long n, int G, long long p, const long long* __restric
     const int t = (int)(ptr[v + 1] - o);
     const int* posg = pos + (long long)g * p;
     const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
-    VgEntry* ent = reinterpret_cast<VgEntry*>(rec + pr_ptr[wid]);
+    VgEntry* ent = reinterpret_cast<VgEntry*>(rec + pr_ptr[ni <= cap ? wid : n * G + wid]);
     int at = 0;
     for (int c0 = 0; c0 < t; c0 += 32) {
         const int c = c0 + lane;
@@ -495,74 +524,116 @@ __global__ void gom_mentries_kernel(long long total, const int* __restrict__ pr_
     if ((threadIdx.x & 31) == 0) { if (s) atomicAdd(out, s); if (e) atomicAdd(out + 1, e); }
 }
 
-// grid = n (one block per genome), block = 128 (4 warps over the genome's GOMs)
-__global__ void __launch_bounds__(128)
+// grid = n (one block per genome), block = 128 (4 warps over the genome's GOMs).
+// A genome's light records are one contiguous range: the block copies them to shared memory in large coalesced pieces
+// (LIGHT_REC_BYTES at a time) together with the pairs' offsets, so a pair's replicate-independent data costs no global
+// round trip of its own; per pair the replicate-dependent gathers (multiplicity byte, GOM-side row sum, genome-side row sum
+// of each entry) are issued four entries at a time before they are consumed, and the per-GOM aggregates are requested up
+// front -- one memory latency per pair instead of five dependent ones.
+#define LIGHT_GCHUNK 128                 // pairs whose offsets are staged at a time: one per thread
+#define LIGHT_REC_BYTES (24 * 1024)
+__global__ void __launch_bounds__(128, 5)
 gom_score_light_kernel(long long n, int G, const long long* __restrict__ ptr, const int* __restrict__ pt_ptr,
                        const int* __restrict__ pr_ni, const long long* __restrict__ pr_ptr, const unsigned char* __restrict__ rec,
                        const unsigned char* __restrict__ wT8, const double* __restrict__ arT, const double* __restrict__ rT,
                        const double* __restrict__ gagg, const double* __restrict__ vagg, int nb, double* __restrict__ out) {
-    __shared__ __align__(16) unsigned char smem[4 * VG_LIGHT_BYTES];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    __shared__ __align__(16) unsigned char srec[LIGHT_REC_BYTES];
+    __shared__ long long soff[LIGHT_GCHUNK + 1];
+    __shared__ int sni[LIGHT_GCHUNK];
+    __shared__ int spt[LIGHT_GCHUNK];
+    __shared__ unsigned char sw_all[4][VG_LIGHT_CAP * NBC];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const long long v = blockIdx.x;
     const long long o = ptr[v];
-    unsigned char* base = smem + wib * VG_LIGHT_BYTES;
-    VgEntry* se = reinterpret_cast<VgEntry*>(base);
-    double* sd = reinterpret_cast<double*>(base + VG_LIGHT_CAP * 32);    // [a (a - 1) / 2 + e], e < a
-    unsigned char* sw = base + VG_LIGHT_CAP * 32 + VG_LIGHT_CAP * (VG_LIGHT_CAP - 1) / 2 * 8;
+    unsigned char* sw = sw_all[wib];
     const int b = lane;
     double va[VAGG];
 #pragma unroll
     for (int q = 0; q < VAGG; ++q) va[q] = vagg[(v * VAGG + q) * NBC + b];
-    for (int g = wib; g < G; g += 4) {
-        const long long wid = v * G + g;
-        const int ni = pr_ni[wid];
-        if (ni > VG_LIGHT_CAP) continue;                                // on the heavy kernel's work list
-        const int p0 = pt_ptr[g];
-        const unsigned char* rp = rec + pr_ptr[wid];
-        __syncwarp();                                                   // the previous pair's staging is fully consumed
-        if (lane < ni) {
-            const uint4* src = reinterpret_cast<const uint4*>(rp) + 2 * lane;
-            uint4* dst = reinterpret_cast<uint4*>(se) + 2 * lane;
-            dst[0] = __ldg(src);
-            dst[1] = __ldg(src + 1);
-        }
-        const int npair = ni * (ni - 1) / 2;
-        const double* Mrec = reinterpret_cast<const double*>(rp + (size_t)ni * 32);
-        for (int q = lane; q < npair; q += 32) sd[q] = __ldg(Mrec + q);
-        __syncwarp();
-        for (int a = 0; a < ni; ++a) sw[a * NBC + b] = wT8[(long long)se[a].col * NBC + b];
-        VgSums S;
-#pragma unroll
-        for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
-        for (int a = 0; a < ni; ++a) {
-            const VgEntry ea = se[a];
-            const double ayc = fabs(ea.y), nr = ea.nr;
-            const double wc = (double)sw[a * NBC + b];
-            const double ar = arT[(long long)(p0 + ea.k) * NBC + b];
-            const double r = rT[(o + ea.c) * NBC + b];
-            S.v[0] += wc;
-            S.v[1] = fma(wc, ar, S.v[1]);
-            S.v[2] = fma(wc, nr, S.v[2]);
-            S.v[3] = fma(wc, r, S.v[3]);
-            S.v[4] = fma(wc, ayc, S.v[4]);
-            S.v[5] = fma(wc * ar, r, S.v[5]);
-            S.v[6] = fma(wc * ar, ayc, S.v[6]);
-            S.v[7] = fma(wc * nr, r, S.v[7]);
-            S.v[8] = fma(wc * nr, ayc, S.v[8]);
-            const double* mrow = sd + a * (a - 1) / 2;
-            double q0 = 0.0, q1 = 0.0;
-            int e = 0;
-            for (; e + 1 < a; e += 2) {             // unordered pairs e < a
-                q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
-                q1 = fma((double)sw[(e + 1) * NBC + b], mrow[e + 1], q1);
+    for (int gc0 = 0; gc0 < G; gc0 += LIGHT_GCHUNK) {
+        const int gcn = min(LIGHT_GCHUNK, G - gc0);
+        __syncthreads();
+        if (tid <= gcn) soff[tid] = pr_ptr[v * G + gc0 + tid];
+        if (tid == 0 && gcn == LIGHT_GCHUNK) soff[LIGHT_GCHUNK] = pr_ptr[v * G + gc0 + LIGHT_GCHUNK];
+        if (tid < gcn) { sni[tid] = pr_ni[v * G + gc0 + tid]; spt[tid] = pt_ptr[gc0 + tid]; }
+        __syncthreads();
+        int g0 = 0;
+        while (g0 < gcn) {
+            // pairs [g0, g1) of the chunk whose records fit the staging buffer (offsets are non-decreasing, a light record is at
+            // most 5 KB: at least one pair fits; heavy pairs take no room here)
+            const long long base_off = soff[g0];
+            const int g1 = g0 + __syncthreads_count(tid >= g0 && tid < gcn && soff[tid + 1] - base_off <= LIGHT_REC_BYTES);
+            const int bytes = (int)(soff[g1] - base_off);
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(rec + base_off);
+                uint4* dst = reinterpret_cast<uint4*>(srec);
+                for (int i = tid; i < bytes / 16; i += 128) dst[i] = __ldg(src + i);
             }
-            if (e < a) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
-            S.v[9] = fma(wc, q0 + q1, S.v[9]);      // enters vg_finish as Q1 (Q2 = Q3 = 0)
-        }
-        double ga[GAGG];
+            __syncthreads();
+            for (int gi = g0 + wib; gi < g1; gi += 4) {
+                const int ni = sni[gi];
+                if (ni > VG_LIGHT_CAP) continue;                        // on the heavy kernel's work list
+                const int g = gc0 + gi;
+                const int p0 = spt[gi];
+                double ga[GAGG];
 #pragma unroll
-        for (int q = 0; q < GAGG; ++q) ga[q] = gagg[((long long)g * GAGG + q) * NBC + b];
-        if (lane < nb) out[((long long)lane * n + v) * G + g] = vg_finish(S, ga, va);
+                for (int q = 0; q < GAGG; ++q) ga[q] = gagg[((long long)g * GAGG + q) * NBC + b];
+                const VgEntry* se = reinterpret_cast<const VgEntry*>(srec + (soff[gi] - base_off));
+                const double* sd = reinterpret_cast<const double*>(se + ni);    // [a (a - 1) / 2 + e], e < a
+                VgSums S;
+#pragma unroll
+                for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
+                __syncwarp();                                           // the previous pair's weights have been consumed
+                for (int a0 = 0; a0 < ni; a0 += 4) {
+                    // four entries' gathers in flight before the first is consumed
+                    double ar4[4], r4[4], nr4[4], ay4[4];
+                    unsigned char w4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int a = min(a0 + u, ni - 1);
+                        const VgEntry ea = se[a];
+                        w4[u] = wT8[(long long)ea.col * NBC + b];
+                        ar4[u] = arT[(long long)(p0 + ea.k) * NBC + b];
+                        r4[u] = rT[(o + ea.c) * NBC + b];
+                        nr4[u] = ea.nr;
+                        ay4[u] = fabs(ea.y);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (a0 + u < ni) {
+                            const double wc = (double)w4[u], ar = ar4[u], r = r4[u], nr = nr4[u], ayc = ay4[u];
+                            sw[(a0 + u) * NBC + b] = w4[u];
+                            S.v[0] += wc;
+                            S.v[1] = fma(wc, ar, S.v[1]);
+                            S.v[2] = fma(wc, nr, S.v[2]);
+                            S.v[3] = fma(wc, r, S.v[3]);
+                            S.v[4] = fma(wc, ayc, S.v[4]);
+                            S.v[5] = fma(wc * ar, r, S.v[5]);
+                            S.v[6] = fma(wc * ar, ayc, S.v[6]);
+                            S.v[7] = fma(wc * nr, r, S.v[7]);
+                            S.v[8] = fma(wc * nr, ayc, S.v[8]);
+                        }
+                    }
+                }
+                // the pair sums: sum_{a > e} w_a w_e M_ae (every lane reads only the multiplicity bytes it wrote itself)
+                double qs = 0.0;
+                for (int a = 1; a < ni; ++a) {
+                    const double* mrow = sd + a * (a - 1) / 2;
+                    double q0 = 0.0, q1 = 0.0;
+                    int e = 0;
+                    for (; e + 1 < a; e += 2) {
+                        q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+                        q1 = fma((double)sw[(e + 1) * NBC + b], mrow[e + 1], q1);
+                    }
+                    if (e < a) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+                    qs = fma((double)sw[a * NBC + b], q0 + q1, qs);
+                }
+                S.v[9] = qs;                                            // enters vg_finish as Q1 (Q2 = Q3 = 0)
+                if (lane < nb) out[((long long)lane * n + v) * G + g] = vg_finish(S, ga, va);
+            }
+            __syncthreads();
+            g0 = g1;
+        }
     }
 }
 
@@ -582,7 +653,7 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
     int* sc = sk + cap;
     unsigned char* sw = reinterpret_cast<unsigned char*>(sc + cap);
     double* red = reinterpret_cast<double*>(vg_smem + (size_t)cap * VG_ENTRY_BYTES);   // [3][VG_NSUM][32]
-    double* mrows = red + 3 * VG_NSUM * 32;                                             // [4][cap]
+    double* mrows = red + 3 * VG_NSUM * 32;                                             // [4 warps][2 rows][cap]
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
         const long long wid = heavy_list[it];
         const long long v = wid / G;
@@ -591,7 +662,7 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
         const int p0 = pt_ptr[g];
         __syncthreads();                                                // previous pair fully consumed
         const int ni = pr_ni[wid];
-        const VgEntry* ent = reinterpret_cast<const VgEntry*>(rec + pr_ptr[wid]);
+        const VgEntry* ent = reinterpret_cast<const VgEntry*>(rec + pr_ptr[n * G + wid]);     // heavy records follow the light ones
         const double* Mrec = reinterpret_cast<const double*>(ent + ni);
         for (int a = threadIdx.x; a < ni; a += 128) {
             const VgEntry e = ent[a];
@@ -605,19 +676,35 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
         VgSums S;
 #pragma unroll
         for (int i = 0; i < VG_NSUM; ++i) S.v[i] = 0.0;
-        // The four warps split the rows a of M (cost ~ a): a = wib, wib + 4, ...  Row a is one coalesced read of a doubles
-        // into the warp's shared-memory row; lanes-as-replicates then take one FMA per entry.
+        // The four warps split the rows a of M (cost ~ a): a = wib, wib + 4, ...  Row a is one coalesced asynchronous copy of a
+        // doubles into one of the warp's two shared-memory rows: the next row is in flight while lanes-as-replicates take
+        // one FMA per entry of the current one.
         {
-            double* mrow = mrows + wib * cap;
+            double* mrow2 = mrows + wib * 2 * cap;
             const int b = lane;
-            for (int a = wib; a < ni; a += 4) {
+            auto fetch_row = [&](int a, int buf) {
+                if (a < ni) {
+                    const double* mr = Mrec + (long long)a * (a - 1) / 2;
+                    double* dst = mrow2 + buf * cap;
+                    for (int e = lane; e < a; e += 32) {
+                        unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(mr + e));
+                    }
+                }
+                asm volatile("cp.async.commit_group;\n" ::);
+            };
+            fetch_row(wib, 0);
+            int it = 0;
+            for (int a = wib; a < ni; a += 4, ++it) {
+                fetch_row(a + 4, (it + 1) & 1);
                 const int k = sk[a];
                 const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
-                const double* mr = Mrec + (long long)a * (a - 1) / 2;
-                for (int e = lane; e < a; e += 32) mrow[e] = __ldg(mr + e);
                 const double wc = (double)sw[a * NBC + b];
                 const double ar = arT[(long long)(p0 + k) * NBC + b];
                 const double r = rT[(o + sc[a]) * NBC + b];
+                asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                __syncwarp();
+                const double* mrow = mrow2 + (it & 1) * cap;
                 S.v[0] += wc;
                 S.v[1] = fma(wc, ar, S.v[1]);
                 S.v[2] = fma(wc, nr, S.v[2]);
@@ -627,7 +714,6 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
                 S.v[6] = fma(wc * ar, ayc, S.v[6]);
                 S.v[7] = fma(wc * nr, r, S.v[7]);
                 S.v[8] = fma(wc * nr, ayc, S.v[8]);
-                __syncwarp();
                 double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
                 int e = 0;
                 for (; e + 3 < a; e += 4) {
@@ -638,8 +724,9 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
                 }
                 for (; e < a; ++e) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
                 S.v[9] = fma(wc, (q0 + q1) + (q2 + q3), S.v[9]);       // enters vg_finish as Q1 (Q2 = Q3 = 0)
-                __syncwarp();                                           // the row is rewritten for the next a
+                __syncwarp();                                           // the row is overwritten by the fetch after next
             }
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
         if (wib > 0) {
 #pragma unroll
@@ -822,21 +909,24 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
     {
         const long long total_w = n * G;
         long long* pbytes = nullptr;
-        CK(dalloc(&pbytes, total_w + 1, nullptr));
+        // offsets: [0, total) light records (0 bytes for heavy pairs), [total, 2 total) heavy records, one scan over both
+        if (2 * total_w + 1 >= (long long)INT32_MAX) { gom_db_free(db); cudaFree(flag); cudaFree(scan);
+            return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "GOM pair table: %lld (genome, GOM) pairs exceed 2^30", (long long)total_w); }
+        CK(dalloc(&pbytes, 2 * total_w + 1, nullptr));
         CK(dalloc(&db->pr_ni, total_w + 1, &db->bytes));
-        CK(dalloc(&db->pr_ptr, total_w + 1, &db->bytes));
-        CK(cudaMemsetAsync(pbytes, 0, (size_t)(total_w + 1) * sizeof(long long), st));
+        CK(dalloc(&db->pr_ptr, 2 * total_w + 1, &db->bytes));
+        CK(cudaMemsetAsync(pbytes, 0, (size_t)(2 * total_w + 1) * sizeof(long long), st));
         if (total_w) {
-            gom_pair_count_kernel<<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->pos, db->pr_ni, pbytes);
+            gom_pair_count_kernel<<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->pos, VG_LIGHT_CAP, db->pr_ni, pbytes);
             ctx->launches++;
         }
         void* tmp = nullptr; size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, pbytes, db->pr_ptr, (int)(total_w + 1), st);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, pbytes, db->pr_ptr, (int)(2 * total_w + 1), st);
         CK(cudaMalloc(&tmp, tb ? tb : 1));
-        cub::DeviceScan::ExclusiveSum(tmp, tb, pbytes, db->pr_ptr, (int)(total_w + 1), st);
+        cub::DeviceScan::ExclusiveSum(tmp, tb, pbytes, db->pr_ptr, (int)(2 * total_w + 1), st);
         ctx->launches++;
         long long rec_bytes = 0;
-        CK(cudaMemcpyAsync(&rec_bytes, db->pr_ptr + total_w, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&rec_bytes, db->pr_ptr + 2 * total_w, sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         cudaFree(tmp); cudaFree(pbytes);
         size_t free_b2 = 0, total_b2 = 0;
@@ -852,7 +942,7 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
         CK(dalloc(&db->heavy_list, (size_t)std::max<long long>(1, total_w), &db->bytes));
         if (total_w) {
             gom_pair_fill_kernel<<<(unsigned)((total_w + 7) / 8), 256, 0, st>>>(n, (int)G, p, db->g_ptr, db->g_col, db->g_val, db->pos, db->pt_ptr,
-                                                                                 db->nrm, db->a_off, db->A, db->pr_ni, db->pr_ptr, db->rec);
+                                                                                 db->nrm, db->a_off, db->A, db->pr_ni, db->pr_ptr, VG_LIGHT_CAP, db->rec);
             ctx->launches++;
             gom_heavy_list_kernel<<<(unsigned)((total_w + 255) / 256), 256, 0, st>>>(total_w, db->pr_ni, VG_LIGHT_CAP, db->heavy_list, db->flag + 1);
             ctx->launches++;
@@ -870,7 +960,7 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
             db->n_isect = (long long)me[1];
         }
     }
-    const size_t vg_smem = (size_t)((max_t + 1) & ~1) * (VG_ENTRY_BYTES + 4 * sizeof(double)) + 3 * VG_NSUM * 32 * sizeof(double);
+    const size_t vg_smem = (size_t)((max_t + 1) & ~1) * (VG_ENTRY_BYTES + 8 * sizeof(double)) + 3 * VG_NSUM * 32 * sizeof(double);
     if (vg_smem > 200 * 1024) {
         gom_db_free(db);
         return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a genome has %d location hits; the GOM scoring kernels stage at most %d per genome "
