@@ -360,7 +360,7 @@ static int mat_handover_cb(int64_t b_local, const double* matrix, void* user) {
     s->h->ready_b[(size_t)s->dev_i] = b_local * s->stride + s->dev_i;
     s->h->cv.notify_all();
     s->h->cv.wait(lk, [&] { return s->h->ready[(size_t)s->dev_i] == nullptr || s->h->stop; });
-    return s->h->stop ? 1 : 0;
+    return s->h->ready[(size_t)s->dev_i] == nullptr ? 0 : 1;      // consumed: go on; stop asked while still pending: give up
 }
 
 extern "C" int gv2_multi_job_replicates_host(gv2_multi_job* mj, const int32_t* host_weights, int64_t nb, int64_t ring_len,
