@@ -694,14 +694,16 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
                 asm volatile("cp.async.commit_group;\n" ::);
             };
             fetch_row(wib, 0);
+            // the two per-replicate row sums of entry a + 4 are requested while entry a is consumed
+            double ar_n = 0.0, r_n = 0.0;
+            if (wib < ni) { ar_n = arT[(long long)(p0 + sk[wib]) * NBC + b]; r_n = rT[(o + sc[wib]) * NBC + b]; }
             int it = 0;
             for (int a = wib; a < ni; a += 4, ++it) {
                 fetch_row(a + 4, (it + 1) & 1);
-                const int k = sk[a];
                 const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
                 const double wc = (double)sw[a * NBC + b];
-                const double ar = arT[(long long)(p0 + k) * NBC + b];
-                const double r = rT[(o + sc[a]) * NBC + b];
+                const double ar = ar_n, r = r_n;
+                if (a + 4 < ni) { ar_n = arT[(long long)(p0 + sk[a + 4]) * NBC + b]; r_n = rT[(o + sc[a + 4]) * NBC + b]; }
                 asm volatile("cp.async.wait_group 1;\n" ::: "memory");
                 __syncwarp();
                 const double* mrow = mrow2 + (it & 1) * cap;
