@@ -29,6 +29,7 @@ struct GomDb {
     // per-chunk scratch (32 replicates)
     double* wT = nullptr; double* arT = nullptr; double* rT = nullptr;
     double* gagg = nullptr; double* vagg = nullptr;
+    double* cpart = nullptr; int n_ctile = 0;   // partial |centroid|^2 per (GOM, tile of eight members)
     unsigned char* wT8 = nullptr; double* wG = nullptr; int* flag = nullptr;   // uint8 weights, per-GOM gathered weights, flags
     long long* heavy_list = nullptr;   // (genome, GOM) pairs whose intersection list overflows the light kernel
     int n_heavy = 0;

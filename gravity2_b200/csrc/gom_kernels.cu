@@ -219,23 +219,65 @@ gom_rowsums_kernel(const int* __restrict__ pt_ptr, const long long* __restrict__
     }
 }
 
-// GB: per-GOM aggregates, lane = replicate.  gagg[g][q][b], q in 0..GAGG-1.  grid = G, block = 256 (8 warps).
-//   phase 1: the sums over the GOM's points (n_g, N1, N2, AR1, AR2, ARN), points dealt to the warps, reduced in shared memory;
-//   phase 2: SAA = sum_kl w_k w_l |X_k - X_l|^2 = 2 (W sum_k w_k |X_k|^2 - |sum_k w_k X_k|^2): the weighted centroid, one member
-//            coordinate per warp at a time -- O(n_g m_g) instead of the O(n_g^2) pass over the distance cache;
+// GB: per-GOM aggregates, lane = replicate.  gagg[g][q][b], q in 0..GAGG-1.
+//   gom_centroid_kernel   SAA = sum_kl w_k w_l |X_k - X_l|^2 = 2 (W sum_k w_k |X_k|^2 - |sum_k w_k X_k|^2) needs the weighted
+//            centroid C_j = sum_k w_k X_kj: O(n_g m_g) instead of the O(n_g^2) pass over the distance cache.  One block per
+//            (GOM, tile of eight member coordinates): the warps split the points, a point costs one multiplicity load and
+//            eight broadcast coordinate loads for eight FMAs; partial |C|^2 per tile go to cpart[g][tile][b]
+//            (grid = (G, tiles): enough blocks to hide the load latency that a one-block-per-GOM loop exposed);
+//   gom_aggregates_kernel the sums over the GOM's points (n_g, N1, N2, AR1, AR2, ARN), points dealt to the warps, reduced in
+//            shared memory, plus the tiles' |C|^2 in tile order (deterministic);
 //   XDEG = 1 when all drawn points coincide (the distances from the first drawn point sum to exactly 0): the reference's
 //            centred matrix is then exactly 0 (dcor.py:54-60), which the moment formula does not reproduce bit for bit.
 #define GAGG 8   // n_g, N1, N2, AR1, AR2, ARN, SAA, XDEG
 __global__ void __launch_bounds__(256)
-gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ mem_ptr, const long long* __restrict__ x_off,
-                      const double* __restrict__ X, const double* __restrict__ nrm, const double* __restrict__ nrm2,
-                      const double* __restrict__ wG, const double* __restrict__ arT, double* __restrict__ gagg) {
-    __shared__ double red[8][7][NBC];
+gom_centroid_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ mem_ptr, const long long* __restrict__ x_off,
+                    const double* __restrict__ X, const double* __restrict__ wG, int ntile, double* __restrict__ cpart) {
     __shared__ double cred[8][8][NBC];
-    const int g = blockIdx.x, b = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int g = blockIdx.x, tile = blockIdx.y, b = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
     const int mg = mem_ptr[g + 1] - mem_ptr[g];
-    double n = 0, N1 = 0, N2 = 0, AR1 = 0, AR2 = 0, ARN = 0, CS = 0;
+    const int j0 = tile * 8;
+    double* o = cpart + ((long long)g * ntile + tile) * NBC + b;
+    if (j0 >= mg) { if (wi == 0) *o = 0.0; return; }
+    const double* x = X + x_off[g] + j0;
+    const int jn = min(8, mg - j0);
+    double c[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = 0.0;
+#pragma unroll 4
+    for (int k = wi; k < ng; k += 8) {
+        const double w = wG[(long long)(p0 + k) * NBC + b];
+        const double* xr = x + (long long)k * mg;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < jn) c[q] = fma(w, __ldg(xr + q), c[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) cred[wi][q][b] = c[q];
+    __syncthreads();
+    if (wi == 0) {
+        double cs = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double t = 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t += cred[u][q][b];
+            cs = fma(t, t, cs);
+        }
+        *o = cs;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gom_aggregates_kernel(const int* __restrict__ pt_ptr, const double* __restrict__ nrm, const double* __restrict__ nrm2,
+                      const double* __restrict__ wG, const double* __restrict__ arT, const double* __restrict__ cpart, int ntile,
+                      double* __restrict__ gagg) {
+    __shared__ double red[8][6][NBC];
+    const int g = blockIdx.x, b = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
+    double n = 0, N1 = 0, N2 = 0, AR1 = 0, AR2 = 0, ARN = 0;
+#pragma unroll 4
     for (int k = wi; k < ng; k += 8) {
         const double w = wG[(long long)(p0 + k) * NBC + b];
         const double nr = nrm[p0 + k], ar = arT[(long long)(p0 + k) * NBC + b];
@@ -246,48 +288,18 @@ gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ me
         AR2 = fma(w * ar, ar, AR2);
         ARN = fma(w * ar, nr, ARN);
     }
-    // weighted centroid C_j = sum_k w_k X_kj, eight member coordinates at a time: the warps split the points, every point
-    // costs one multiplicity load and eight broadcast coordinate loads for eight FMAs; the partial centroids meet in shared
-    // memory and warp 0 accumulates |C|^2
-    const double* x = X + x_off[g];
-    for (int j0 = 0; j0 < mg; j0 += 8) {
-        double c[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) c[q] = 0.0;
-        const int jn = min(8, mg - j0);
-#pragma unroll 2
-        for (int k = wi; k < ng; k += 8) {
-            const double w = wG[(long long)(p0 + k) * NBC + b];
-            const double* xr = x + (long long)k * mg + j0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (q < jn) c[q] = fma(w, __ldg(xr + q), c[q]);
-        }
-        __syncthreads();                                         // cred of the previous tile has been consumed
-#pragma unroll
-        for (int q = 0; q < 8; ++q) cred[wi][q][b] = c[q];
-        __syncthreads();
-        if (wi == 0) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                double t = 0.0;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) t += cred[u][q][b];
-                CS = fma(t, t, CS);
-            }
-        }
-    }
     red[wi][0][b] = n; red[wi][1][b] = N1; red[wi][2][b] = N2; red[wi][3][b] = AR1; red[wi][4][b] = AR2; red[wi][5][b] = ARN;
-    red[wi][6][b] = wi == 0 ? CS : 0.0;
     __syncthreads();
     if (wi == 0) {
-        double t[7];
+        double t[6];
 #pragma unroll
-        for (int q = 0; q < 7; ++q) {
+        for (int q = 0; q < 6; ++q) {
             t[q] = 0.0;
 #pragma unroll
             for (int u = 0; u < 8; ++u) t[q] += red[u][q][b];
         }
+        double cs = 0.0;
+        for (int tile = 0; tile < ntile; ++tile) cs += cpart[((long long)g * ntile + tile) * NBC + b];
         // first drawn point of the replicate and its distance row sum
         double xdeg = 1.0;
         for (int k = 0; k < ng; ++k)
@@ -295,7 +307,7 @@ gom_aggregates_kernel(const int* __restrict__ pt_ptr, const int* __restrict__ me
         double* o = gagg + (long long)g * GAGG * NBC + b;
         o[0 * NBC] = t[0]; o[1 * NBC] = t[1]; o[2 * NBC] = t[2]; o[3 * NBC] = t[3];
         o[4 * NBC] = t[4]; o[5 * NBC] = t[5];
-        o[6 * NBC] = xdeg != 0.0 ? 0.0 : 2.0 * (t[0] * t[2] - t[6]);
+        o[6 * NBC] = xdeg != 0.0 ? 0.0 : 2.0 * (t[0] * t[2] - cs);
         o[7 * NBC] = xdeg;
     }
 }
@@ -771,7 +783,7 @@ void gom_db_free(GomDb* db) {
     cudaFree(db->mem_ptr); cudaFree(db->mem_row); cudaFree(db->pt_ptr); cudaFree(db->pt_col);
     cudaFree(db->pos); cudaFree(db->x_off); cudaFree(db->a_off); cudaFree(db->X); cudaFree(db->nrm); cudaFree(db->nrm2);
     cudaFree(db->A); cudaFree(db->wT); cudaFree(db->arT); cudaFree(db->rT);
-    cudaFree(db->gagg); cudaFree(db->vagg); cudaFree(db->wT8); cudaFree(db->wG); cudaFree(db->flag); cudaFree(db->heavy_list);
+    cudaFree(db->gagg); cudaFree(db->cpart); cudaFree(db->vagg); cudaFree(db->wT8); cudaFree(db->wG); cudaFree(db->flag); cudaFree(db->heavy_list);
     cudaFree(db->pr_ni); cudaFree(db->pr_ptr); cudaFree(db->rec);
     delete db;
 }
@@ -886,6 +898,12 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
     CK(dalloc(&db->arT, (size_t)db->npt * NBC, &db->bytes));
     CK(dalloc(&db->rT, (size_t)db->nnz * NBC, &db->bytes));
     CK(dalloc(&db->gagg, (size_t)G * GAGG * NBC, &db->bytes));
+    {
+        int max_mg = 0;
+        for (int64_t g = 0; g < G; ++g) max_mg = std::max<int>(max_mg, mem_ptr_h[g + 1] - mem_ptr_h[g]);
+        db->n_ctile = (max_mg + 7) / 8;
+        CK(dalloc(&db->cpart, (size_t)G * std::max(1, db->n_ctile) * NBC, &db->bytes));
+    }
     CK(dalloc(&db->vagg, (size_t)n * VAGG * NBC, &db->bytes));
     // intersection scratch: each (genome, GOM) warp needs 2 ints per hit of the genome
     int max_t = 0;
@@ -1002,7 +1020,12 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
             gom_rowsums_kernel<<<g1, b1, 0, st>>>(db->pt_ptr, db->a_off, db->A, db->wG, db->arT);
             ctx->launches++;
         }
-        gom_aggregates_kernel<<<(unsigned)G, 256, 0, st>>>(db->pt_ptr, db->mem_ptr, db->x_off, db->X, db->nrm, db->nrm2, db->wG, db->arT, db->gagg);
+        if (db->n_ctile) {
+            dim3 gc((unsigned)G, (unsigned)db->n_ctile);
+            gom_centroid_kernel<<<gc, 256, 0, st>>>(db->pt_ptr, db->mem_ptr, db->x_off, db->X, db->wG, db->n_ctile, db->cpart);
+            ctx->launches++;
+        }
+        gom_aggregates_kernel<<<(unsigned)G, 256, 0, st>>>(db->pt_ptr, db->nrm, db->nrm2, db->wG, db->arT, db->cpart, db->n_ctile, db->gagg);
         ctx->launches++;
         genome_rowsums_sorted_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(n, db->g_ptr, db->g_col, db->g_val, db->g_ord, db->wT8, db->rT, db->vagg);
         ctx->launches++;

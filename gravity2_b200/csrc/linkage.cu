@@ -68,8 +68,10 @@ __device__ __forceinline__ double lk_new_dist(double d_xi, double d_yi, double d
     return __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), -c));
 }
 
+// (registers capped at 32: a 1024-thread CTA then leaves half of the SM's register file to the similarity kernels, which run
+//  concurrently on the other streams while the dendrograms are built -- the clustering is latency bound and barely issues)
 template <int METHOD>
-__global__ void __launch_bounds__(LK_THREADS, 1)
+__global__ void __launch_bounds__(LK_THREADS, 2)
 lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
     extern __shared__ int lk_size[];
     __shared__ LkBest s_warp[LK_THREADS / 32];
