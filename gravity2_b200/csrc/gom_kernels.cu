@@ -544,6 +544,7 @@ __global__ void gom_mentries_kernel(long long total, const int* __restrict__ pr_
 // front -- one memory latency per pair instead of five dependent ones.
 #define LIGHT_GCHUNK 128                 // pairs whose offsets are staged at a time: one per thread
 #define LIGHT_REC_BYTES (24 * 1024)
+#define LIGHT_WSTRIDE (VG_LIGHT_CAP + 4)   // bytes per lane of the multiplicity staging: 9 words, odd -> no bank conflicts
 __global__ void __launch_bounds__(128, 5)
 gom_score_light_kernel(long long n, int G, const long long* __restrict__ ptr, const int* __restrict__ pt_ptr,
                        const int* __restrict__ pr_ni, const long long* __restrict__ pr_ptr, const unsigned char* __restrict__ rec,
@@ -553,7 +554,7 @@ gom_score_light_kernel(long long n, int G, const long long* __restrict__ ptr, co
     __shared__ long long soff[LIGHT_GCHUNK + 1];
     __shared__ int sni[LIGHT_GCHUNK];
     __shared__ int spt[LIGHT_GCHUNK];
-    __shared__ unsigned char sw_all[4][VG_LIGHT_CAP * NBC];
+    __shared__ __align__(4) unsigned char sw_all[4][NBC * LIGHT_WSTRIDE];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const long long v = blockIdx.x;
     const long long o = ptr[v];
@@ -614,7 +615,7 @@ gom_score_light_kernel(long long n, int G, const long long* __restrict__ ptr, co
                     for (int u = 0; u < 4; ++u) {
                         if (a0 + u < ni) {
                             const double wc = (double)w4[u], ar = ar4[u], r = r4[u], nr = nr4[u], ayc = ay4[u];
-                            sw[(a0 + u) * NBC + b] = w4[u];
+                            sw[b * LIGHT_WSTRIDE + a0 + u] = w4[u];
                             S.v[0] += wc;
                             S.v[1] = fma(wc, ar, S.v[1]);
                             S.v[2] = fma(wc, nr, S.v[2]);
@@ -627,18 +628,23 @@ gom_score_light_kernel(long long n, int G, const long long* __restrict__ ptr, co
                         }
                     }
                 }
-                // the pair sums: sum_{a > e} w_a w_e M_ae (every lane reads only the multiplicity bytes it wrote itself)
+                // the pair sums: sum_{a > e} w_a w_e M_ae.  A lane keeps its own multiplicity bytes contiguous (row stride 36 bytes:
+                // conflict-free word loads), so one 32-bit load feeds four FMAs
                 double qs = 0.0;
+                const unsigned char* wb = sw + b * LIGHT_WSTRIDE;
                 for (int a = 1; a < ni; ++a) {
                     const double* mrow = sd + a * (a - 1) / 2;
-                    double q0 = 0.0, q1 = 0.0;
+                    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
                     int e = 0;
-                    for (; e + 1 < a; e += 2) {
-                        q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
-                        q1 = fma((double)sw[(e + 1) * NBC + b], mrow[e + 1], q1);
+                    for (; e + 3 < a; e += 4) {
+                        const unsigned w4e = *reinterpret_cast<const unsigned*>(wb + e);
+                        q0 = fma((double)(w4e & 0xffu), mrow[e], q0);
+                        q1 = fma((double)((w4e >> 8) & 0xffu), mrow[e + 1], q1);
+                        q2 = fma((double)((w4e >> 16) & 0xffu), mrow[e + 2], q2);
+                        q3 = fma((double)(w4e >> 24), mrow[e + 3], q3);
                     }
-                    if (e < a) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
-                    qs = fma((double)sw[a * NBC + b], q0 + q1, qs);
+                    for (; e < a; ++e) q0 = fma((double)wb[e], mrow[e], q0);
+                    qs = fma((double)wb[a], (q0 + q1) + (q2 + q3), qs);
                 }
                 S.v[9] = qs;                                            // enters vg_finish as Q1 (Q2 = Q3 = 0)
                 if (lane < nb) out[((long long)lane * n + v) * G + g] = vg_finish(S, ga, va);
@@ -658,13 +664,14 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
                        const long long* __restrict__ heavy_list, int total) {
     extern __shared__ __align__(16) unsigned char vg_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int cap = (max_t + 1) & ~1;
+    const int cap = (max_t + 3) & ~3;                        // multiple of 4: 16-byte aligned rows of M
+    const int wstride = cap + ((cap >> 2) & 1 ? 0 : 4);      // bytes per replicate lane; wstride / 4 odd
     double* sy = reinterpret_cast<double*>(vg_smem);
     double* sn = sy + cap;
     int* sk = reinterpret_cast<int*>(sn + cap);
     int* sc = sk + cap;
     unsigned char* sw = reinterpret_cast<unsigned char*>(sc + cap);
-    double* red = reinterpret_cast<double*>(vg_smem + (size_t)cap * VG_ENTRY_BYTES);   // [3][VG_NSUM][32]
+    double* red = reinterpret_cast<double*>(vg_smem + (size_t)cap * VG_ENTRY_BYTES + 128);   // [3][VG_NSUM][32]  (sw: 32 * wstride <= 32 cap + 128)
     double* mrows = red + 3 * VG_NSUM * 32;                                             // [4 warps][2 rows][cap]
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
         const long long wid = heavy_list[it];
@@ -679,10 +686,16 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
         for (int a = threadIdx.x; a < ni; a += 128) {
             const VgEntry e = ent[a];
             sy[a] = e.y; sn[a] = e.nr; sk[a] = e.k; sc[a] = e.c;
-            // (the 32 multiplicity bytes of the entry's column: 8 words)
+            // (the 32 multiplicity bytes of the entry's column, stored per replicate lane: sw[b][a], so that a lane reads four
+            //  consecutive entries' multiplicities with one 32-bit load; wstride / 4 is odd: conflict-free)
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                reinterpret_cast<unsigned*>(sw)[a * 8 + q] = reinterpret_cast<const unsigned*>(wT8 + (long long)e.col * NBC)[q];
+            for (int q = 0; q < 8; ++q) {
+                const unsigned w4 = reinterpret_cast<const unsigned*>(wT8 + (long long)e.col * NBC)[q];
+                sw[(4 * q + 0) * wstride + a] = (unsigned char)(w4 & 0xffu);
+                sw[(4 * q + 1) * wstride + a] = (unsigned char)((w4 >> 8) & 0xffu);
+                sw[(4 * q + 2) * wstride + a] = (unsigned char)((w4 >> 16) & 0xffu);
+                sw[(4 * q + 3) * wstride + a] = (unsigned char)(w4 >> 24);
+            }
         }
         __syncthreads();
         VgSums S;
@@ -694,6 +707,7 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
         {
             double* mrow2 = mrows + wib * 2 * cap;
             const int b = lane;
+            const unsigned char* wb = sw + b * wstride;
             auto fetch_row = [&](int a, int buf) {
                 if (a < ni) {
                     const double* mr = Mrec + (long long)a * (a - 1) / 2;
@@ -713,7 +727,7 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
             for (int a = wib; a < ni; a += 4, ++it) {
                 fetch_row(a + 4, (it + 1) & 1);
                 const double yc = sy[a], ayc = fabs(yc), nr = sn[a];
-                const double wc = (double)sw[a * NBC + b];
+                const double wc = (double)wb[a];
                 const double ar = ar_n, r = r_n;
                 if (a + 4 < ni) { ar_n = arT[(long long)(p0 + sk[a + 4]) * NBC + b]; r_n = rT[(o + sc[a + 4]) * NBC + b]; }
                 asm volatile("cp.async.wait_group 1;\n" ::: "memory");
@@ -731,12 +745,14 @@ gom_score_heavy_kernel(long long n, int G, int max_t, const long long* __restric
                 double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
                 int e = 0;
                 for (; e + 3 < a; e += 4) {
-                    q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
-                    q1 = fma((double)sw[(e + 1) * NBC + b], mrow[e + 1], q1);
-                    q2 = fma((double)sw[(e + 2) * NBC + b], mrow[e + 2], q2);
-                    q3 = fma((double)sw[(e + 3) * NBC + b], mrow[e + 3], q3);
+                    const unsigned w4e = *reinterpret_cast<const unsigned*>(wb + e);
+                    const double2 m01 = *reinterpret_cast<const double2*>(mrow + e), m23 = *reinterpret_cast<const double2*>(mrow + e + 2);
+                    q0 = fma((double)(w4e & 0xffu), m01.x, q0);
+                    q1 = fma((double)((w4e >> 8) & 0xffu), m01.y, q1);
+                    q2 = fma((double)((w4e >> 16) & 0xffu), m23.x, q2);
+                    q3 = fma((double)(w4e >> 24), m23.y, q3);
                 }
-                for (; e < a; ++e) q0 = fma((double)sw[e * NBC + b], mrow[e], q0);
+                for (; e < a; ++e) q0 = fma((double)wb[e], mrow[e], q0);
                 S.v[9] = fma(wc, (q0 + q1) + (q2 + q3), S.v[9]);       // enters vg_finish as Q1 (Q2 = Q3 = 0)
                 __syncwarp();                                           // the row is overwritten by the fetch after next
             }
@@ -980,7 +996,7 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
             db->n_isect = (long long)me[1];
         }
     }
-    const size_t vg_smem = (size_t)((max_t + 1) & ~1) * (VG_ENTRY_BYTES + 8 * sizeof(double)) + 3 * VG_NSUM * 32 * sizeof(double);
+    const size_t vg_smem = (size_t)((max_t + 3) & ~3) * (VG_ENTRY_BYTES + 8 * sizeof(double)) + 128 + 3 * VG_NSUM * 32 * sizeof(double);
     if (vg_smem > 200 * 1024) {
         gom_db_free(db);
         return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "a genome has %d location hits; the GOM scoring kernels stage at most %d per genome "

@@ -36,6 +36,7 @@
 #include <vector>
 
 #define LK_THREADS 1024
+#define LK_MLP 4                 // row elements per thread in flight at a time
 
 struct LkBest { double d; int i; };
 
@@ -68,10 +69,8 @@ __device__ __forceinline__ double lk_new_dist(double d_xi, double d_yi, double d
     return __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), -c));
 }
 
-// (registers capped at 32: a 1024-thread CTA then leaves half of the SM's register file to the similarity kernels, which run
-//  concurrently on the other streams while the dendrograms are built -- the clustering is latency bound and barely issues)
 template <int METHOD>
-__global__ void __launch_bounds__(LK_THREADS, 2)
+__global__ void __launch_bounds__(LK_THREADS, 1)
 lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
     extern __shared__ int lk_size[];
     __shared__ LkBest s_warp[LK_THREADS / 32];
@@ -100,11 +99,24 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
             const int prev = len > 1 ? chain[len - 2] : -1;
             const double* row = D + (size_t)x * n;
             LkBest best{INFINITY, 0x7fffffff};
-            for (int i = tid; i < n; i += LK_THREADS) {
-                if (lk_size[i] == 0 || i == x) continue;
-                const double d = row[i];
-                if (i == prev) s_dp = d;                         // the incumbent's distance, for the final comparison
-                if (d < best.d) { best.d = d; best.i = i; }      // ascending i per thread: first minimum kept
+            // The step is one DRAM round trip long, not one per element: a thread's loads of the row are all issued before the
+            // first is looked at (dead clusters' entries are read and ignored: the row is dense), LK_MLP at a time.
+            for (int i0 = tid; i0 < n; i0 += LK_THREADS * LK_MLP) {
+                double dv[LK_MLP];
+                int sz[LK_MLP];
+#pragma unroll
+                for (int u = 0; u < LK_MLP; ++u) {
+                    const int i = i0 + u * LK_THREADS;
+                    dv[u] = i < n ? __ldcs(row + i) : INFINITY;
+                    sz[u] = i < n ? lk_size[i] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < LK_MLP; ++u) {
+                    const int i = i0 + u * LK_THREADS;
+                    if (sz[u] == 0 || i == x) continue;
+                    if (i == prev) s_dp = dv[u];                     // the incumbent's distance, for the final comparison
+                    if (dv[u] < best.d) { best.d = dv[u]; best.i = i; }   // ascending i per thread: first minimum kept
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -165,12 +177,24 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
         __syncthreads();
         const double* rx = D + (size_t)x * n;
         double* ry = D + (size_t)y * n;
-        for (int i = tid; i < n; i += LK_THREADS) {
-            const int ni = lk_size[i];
-            if (ni == 0 || i == y) continue;
-            const double v = lk_new_dist<METHOD>(rx[i], ry[i], dmin, nx, ny, ni);
-            ry[i] = v;
-            D[(size_t)i * n + y] = v;
+        for (int i0 = tid; i0 < n; i0 += LK_THREADS * LK_MLP) {
+            double ax[LK_MLP], ay[LK_MLP];
+            int sz[LK_MLP];
+#pragma unroll
+            for (int u = 0; u < LK_MLP; ++u) {
+                const int i = i0 + u * LK_THREADS;
+                ax[u] = i < n ? rx[i] : 0.0;
+                ay[u] = i < n ? ry[i] : 0.0;
+                sz[u] = i < n ? lk_size[i] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < LK_MLP; ++u) {
+                const int i = i0 + u * LK_THREADS;
+                if (sz[u] == 0 || i == y) continue;
+                const double v = lk_new_dist<METHOD>(ax[u], ay[u], dmin, nx, ny, sz[u]);
+                ry[i] = v;
+                D[(size_t)i * n + y] = v;
+            }
         }
         __syncthreads();
     }
