@@ -163,31 +163,37 @@ __global__ void gom_gather_weights_kernel(const int* __restrict__ pt_col, long l
     wG[i] = wT[(long long)pt_col[i / NBC] * NBC + (i % NBC)];
 }
 
-// GA: arT[pt][b] = sum_l w_l A[k][l]  (per GOM a [ng x ng] x [ng x 32] product; the squared-distance sums the centred
-// variance also needs do not go through this O(ng^2) loop any more: see gom_aggregates_kernel).
-// grid = (ceil(max_ng/128), G), block = (32 b, 8): the block owns 128 rows k, a thread 16 of them for its replicate lane.
-// 32 columns l at a time go through shared memory (A tile 128 x 32 read as whole 256-byte row segments, weight tile
-// 32 x 32); the distances are warp-uniform, so they are read two columns at a time (LDS.128 broadcast): per pair of
-// columns 16 + 2 shared-memory loads feed 32 DFMA -- the fp64 pipe, not the load pipe, is the limit.
+// GA: arT[pt][b] = sum_l w_l A[k][l]  (per GOM a [ng x ng] x [ng x 32 NH] product; the squared-distance sums the centred
+// variance also needs do not go through this O(ng^2) loop any more: see gom_centroid_kernel).
+// grid = (ceil(max_ng/128), G), block = (32 b, 8): the block owns 128 rows k, a thread 16 of them for its replicate lane --
+// of NH = 2 chunks of 32 replicates at once: every distance read from shared memory (warp-uniform, two columns per LDS.128)
+// then feeds two FMAs, which turns the kernel from shared-memory-load bound (16 + 2 loads per 32 DFMA, measured: l1tex 72 %,
+// fp64 pipe 30 %) into fp64-pipe bound (16 + 4 loads per 64 DFMA), and the 5 GB distance cache is read once per 64 replicates.
 #define GA_ROWS 128
 #define GA_LC 32
 #define GA_LD (GA_LC + 2)            // even row stride: 16-byte aligned column pairs
-__global__ void __launch_bounds__(256)
+static size_t ga_smem_bytes(int nh) { return (size_t)GA_ROWS * GA_LD * sizeof(double) + (size_t)nh * GA_LC * NBC * sizeof(double); }
+template <int NH>
+__global__ void __launch_bounds__(256, 2)
 gom_rowsums_kernel(const int* __restrict__ pt_ptr, const long long* __restrict__ a_off,
-                   const double* __restrict__ A, const double* __restrict__ wG,
-                   double* __restrict__ arT) {
-    __shared__ __align__(16) double sA[GA_ROWS][GA_LD];
-    __shared__ double sW[GA_LC][NBC];
+                   const double* __restrict__ A, const double* __restrict__ wG0, const double* __restrict__ wG1,
+                   double* __restrict__ arT0, double* __restrict__ arT1) {
+    extern __shared__ __align__(16) unsigned char ga_smem[];
+    double (*sA)[GA_LD] = reinterpret_cast<double (*)[GA_LD]>(ga_smem);
+    double (*sW)[GA_LC][NBC] = reinterpret_cast<double (*)[GA_LC][NBC]>(ga_smem + (size_t)GA_ROWS * GA_LD * sizeof(double));
     const int g = blockIdx.y;
     const int p0 = pt_ptr[g], ng = pt_ptr[g + 1] - p0;
     const int kb = blockIdx.x * GA_ROWS;
     if (kb >= ng) return;
     const int b = threadIdx.x, ty = threadIdx.y;
     const double* a = A + a_off[g];
-    const double* w = wG + (long long)p0 * NBC;
-    double s1[16];
+    const double* w0 = wG0 + (long long)p0 * NBC;
+    const double* w1 = NH > 1 ? wG1 + (long long)p0 * NBC : nullptr;
+    double s1[16][NH];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) s1[r] = 0.0;
+    for (int r = 0; r < 16; ++r)
+#pragma unroll
+        for (int h = 0; h < NH; ++h) s1[r][h] = 0.0;
     for (int l0 = 0; l0 < ng; l0 += GA_LC) {
         __syncthreads();
 #pragma unroll
@@ -198,24 +204,33 @@ gom_rowsums_kernel(const int* __restrict__ pt_ptr, const long long* __restrict__
 #pragma unroll
         for (int q = 0; q < GA_LC / 8; ++q) {
             const int l = ty + 8 * q;
-            sW[l][b] = l0 + l < ng ? w[(long long)(l0 + l) * NBC + b] : 0.0;
+            sW[0][l][b] = l0 + l < ng ? w0[(long long)(l0 + l) * NBC + b] : 0.0;
+            if (NH > 1) sW[1][l][b] = l0 + l < ng ? w1[(long long)(l0 + l) * NBC + b] : 0.0;
         }
         __syncthreads();
 #pragma unroll 4
         for (int l = 0; l < GA_LC; l += 2) {
-            const double w0 = sW[l][b], w1 = sW[l + 1][b];
+            double wa[NH], wb2[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) { wa[h] = sW[h][l][b]; wb2[h] = sW[h][l + 1][b]; }
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const double2 d = *reinterpret_cast<const double2*>(&sA[ty * 16 + r][l]);
-                s1[r] = fma(w0, d.x, s1[r]);         // columns in ascending order, as before
-                s1[r] = fma(w1, d.y, s1[r]);
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                    s1[r][h] = fma(wa[h], d.x, s1[r][h]);         // columns in ascending order
+                    s1[r][h] = fma(wb2[h], d.y, s1[r][h]);
+                }
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const int k = kb + ty * 16 + r;
-        if (k < ng) arT[(long long)(p0 + k) * NBC + b] = s1[r];
+        if (k < ng) {
+            arT0[(long long)(p0 + k) * NBC + b] = s1[r][0];
+            if (NH > 1) arT1[(long long)(p0 + k) * NBC + b] = s1[r][NH - 1];
+        }
     }
 }
 
@@ -911,7 +926,7 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
     }
     // ---- per-chunk (32 replicates) scratch
     CK(dalloc(&db->wT, p * NBC, &db->bytes));
-    CK(dalloc(&db->arT, (size_t)db->npt * NBC, &db->bytes));
+    CK(dalloc(&db->arT, (size_t)2 * db->npt * NBC, &db->bytes));      // two chunks of 32 replicates per pass
     CK(dalloc(&db->rT, (size_t)db->nnz * NBC, &db->bytes));
     CK(dalloc(&db->gagg, (size_t)G * GAGG * NBC, &db->bytes));
     {
@@ -937,8 +952,10 @@ int gom_db_build(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, int64_t 
         genome_order_kernel<<<(unsigned)n, 128, vo, st>>>(db->g_ptr, db->g_val, db->g_ord);
         ctx->launches++;
     }
-    CK(dalloc(&db->wT8, p * NBC, &db->bytes));
-    CK(dalloc(&db->wG, (size_t)db->npt * NBC, &db->bytes));
+    CK(dalloc(&db->wT8, 2 * p * NBC, &db->bytes));
+    CK(dalloc(&db->wG, (size_t)2 * db->npt * NBC, &db->bytes));
+    CK(cudaFuncSetAttribute(gom_rowsums_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ga_smem_bytes(1)));
+    CK(cudaFuncSetAttribute(gom_rowsums_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ga_smem_bytes(2)));
     CK(dalloc(&db->flag, 2, &db->bytes));          // [0] weight overflow, [1] heavy-list length
     CK(cudaMemsetAsync(db->flag, 0, 2 * sizeof(int), st));
     // ---- pair records (replicate independent): intersection entries + M triangle of every (genome, GOM) pair, genome-major
@@ -1020,40 +1037,55 @@ int gom_db_score(gv2_ctx* ctx, GomDb* db, const int32_t* weights, int64_t nb, do
         cudaError_t e0 = cudaMemsetAsync(db->flag, 0, sizeof(int), st);
         if (e0 != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "gom_db_score: %s", cudaGetErrorString(e0));
     }
-    for (int64_t b0 = 0; b0 < nb; b0 += NBC) {
-        const int cb = (int)std::min<int64_t>(NBC, nb - b0);
+    // Two chunks of 32 replicates (the lanes of a warp) per pass: the GOM-side row sums of both go through ONE sweep of the
+    // distance caches; everything else runs per chunk on that chunk's half of the scratch.
+    for (int64_t b0 = 0; b0 < nb; b0 += 2 * NBC) {
+        const int nh = nb - b0 > NBC ? 2 : 1;
         Gv2Timer timer(ctx, GV2_TIME_GOM);
         timer.begin();
-        if (p) {
-            weights_transpose_kernel<<<(unsigned)((p * NBC + 255) / 256), 256, 0, st>>>(
-                weights ? weights + b0 * p : nullptr, p, cb, db->wT, db->wT8, db->flag);
-            ctx->launches++;
+        for (int h = 0; h < nh; ++h) {
+            const int cb = (int)std::min<int64_t>(NBC, nb - b0 - h * NBC);
+            if (p) {
+                weights_transpose_kernel<<<(unsigned)((p * NBC + 255) / 256), 256, 0, st>>>(
+                    weights ? weights + (b0 + h * NBC) * p : nullptr, p, cb, db->wT, db->wT8 + (size_t)h * p * NBC, db->flag);
+                ctx->launches++;
+            }
+            if (db->max_ng) {
+                gom_gather_weights_kernel<<<(unsigned)(((long long)db->npt * NBC + 255) / 256), 256, 0, st>>>(db->pt_col, db->npt, db->wT,
+                                                                                                              db->wG + (size_t)h * db->npt * NBC);
+                ctx->launches++;
+            }
         }
+        double* wG1 = db->wG + (size_t)db->npt * NBC;
+        double* arT1 = db->arT + (size_t)db->npt * NBC;
         if (db->max_ng) {
-            gom_gather_weights_kernel<<<(unsigned)(((long long)db->npt * NBC + 255) / 256), 256, 0, st>>>(db->pt_col, db->npt, db->wT, db->wG);
-            ctx->launches++;
             dim3 g1((unsigned)((db->max_ng + GA_ROWS - 1) / GA_ROWS), (unsigned)G), b1(32, 8);
-            gom_rowsums_kernel<<<g1, b1, 0, st>>>(db->pt_ptr, db->a_off, db->A, db->wG, db->arT);
+            if (nh == 2) gom_rowsums_kernel<2><<<g1, b1, ga_smem_bytes(2), st>>>(db->pt_ptr, db->a_off, db->A, db->wG, wG1, db->arT, arT1);
+            else gom_rowsums_kernel<1><<<g1, b1, ga_smem_bytes(1), st>>>(db->pt_ptr, db->a_off, db->A, db->wG, nullptr, db->arT, nullptr);
             ctx->launches++;
         }
-        if (db->n_ctile) {
-            dim3 gc((unsigned)G, (unsigned)db->n_ctile);
-            gom_centroid_kernel<<<gc, 256, 0, st>>>(db->pt_ptr, db->mem_ptr, db->x_off, db->X, db->wG, db->n_ctile, db->cpart);
+        for (int h = 0; h < nh; ++h) {
+            const int cb = (int)std::min<int64_t>(NBC, nb - b0 - h * NBC);
+            const double* wG = db->wG + (size_t)h * db->npt * NBC;
+            const double* arT = db->arT + (size_t)h * db->npt * NBC;
+            const unsigned char* wT8 = db->wT8 + (size_t)h * p * NBC;
+            double* outh = out + (b0 + h * NBC) * n * G;
+            if (db->n_ctile) {
+                dim3 gc((unsigned)G, (unsigned)db->n_ctile);
+                gom_centroid_kernel<<<gc, 256, 0, st>>>(db->pt_ptr, db->mem_ptr, db->x_off, db->X, wG, db->n_ctile, db->cpart);
+                ctx->launches++;
+            }
+            gom_aggregates_kernel<<<(unsigned)G, 256, 0, st>>>(db->pt_ptr, db->nrm, db->nrm2, wG, arT, db->cpart, db->n_ctile, db->gagg);
             ctx->launches++;
-        }
-        gom_aggregates_kernel<<<(unsigned)G, 256, 0, st>>>(db->pt_ptr, db->nrm, db->nrm2, db->wG, db->arT, db->cpart, db->n_ctile, db->gagg);
-        ctx->launches++;
-        genome_rowsums_sorted_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(n, db->g_ptr, db->g_col, db->g_val, db->g_ord, db->wT8, db->rT, db->vagg);
-        ctx->launches++;
-        {
-            const long long total_w = n * G;
-            gom_score_light_kernel<<<(unsigned)n, 128, 0, st>>>(n, (int)G, db->g_ptr, db->pt_ptr, db->pr_ni, db->pr_ptr, db->rec, db->wT8, db->arT,
-                                                                db->rT, db->gagg, db->vagg, cb, out + b0 * n * G);
+            genome_rowsums_sorted_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(n, db->g_ptr, db->g_col, db->g_val, db->g_ord, wT8, db->rT, db->vagg);
+            ctx->launches++;
+            gom_score_light_kernel<<<(unsigned)n, 128, 0, st>>>(n, (int)G, db->g_ptr, db->pt_ptr, db->pr_ni, db->pr_ptr, db->rec, wT8, arT,
+                                                                db->rT, db->gagg, db->vagg, cb, outh);
             ctx->launches++;
             if (db->n_heavy) {
                 gom_score_heavy_kernel<<<(unsigned)std::min<long long>(db->n_heavy, ctx->sm_count * 8), 128, db->vg_smem, st>>>(
-                    n, (int)G, db->max_t, db->g_ptr, db->pt_ptr, db->pr_ni, db->pr_ptr, db->rec, db->wT8, db->arT, db->rT, db->gagg, db->vagg, cb,
-                    out + b0 * n * G, db->heavy_list, db->n_heavy);
+                    n, (int)G, db->max_t, db->g_ptr, db->pt_ptr, db->pr_ni, db->pr_ptr, db->rec, wT8, arT, db->rT, db->gagg, db->vagg, cb,
+                    outh, db->heavy_list, db->n_heavy);
                 ctx->launches++;
             }
         }
