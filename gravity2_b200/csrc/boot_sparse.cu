@@ -407,7 +407,8 @@ bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowt
 #define BSS_LIST_BYTES (BSS_CH * 32)                 // 128
 #define BSS_W_BYTES (BSS_CH * 4 * 128)               // 2048
 #define BSS_OUT_LD 132                               // doubles per staged pair: 128 replicates + 4 (bank spread)
-#define BSS_OUT_BYTES (8 * BSS_OUT_LD * 8)           // eight pairs (half an i-row) x 128 replicates
+#define BSS_OUT_PAIRS 4                              // pairs staged per flush: 4 x 8 bytes = one 32-byte sector per replicate
+#define BSS_OUT_BYTES (BSS_OUT_PAIRS * BSS_OUT_LD * 8)
 #define BSS_WARP_BYTES (3 * BSS_LIST_BYTES + 2 * BSS_W_BYTES + BSS_OUT_BYTES)
 
 __device__ __forceinline__ void bss_cp_async8(void* smem, const void* gmem) {
@@ -423,7 +424,7 @@ __device__ __forceinline__ void bss_wait2() { asm volatile("cp.async.wait_group 
 __device__ __forceinline__ void bss_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 template <int RW>
-__global__ void __launch_bounds__(BS_THREADS, 2)
+__global__ void __launch_bounds__(BS_THREADS, 3)
 boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* __restrict__ pend, const uint8_t* __restrict__ ent,
                           int nt, long long tile_begin, const uint8_t* __restrict__ wT, long long w_ld, int nb_total,
                           long long ws_rep_stride, double quantum, double* __restrict__ ws) {
@@ -495,8 +496,8 @@ boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* 
         for (int r = 0; r < 4; ++r) acc[k][r] = 0u;
     // Results leave through shared memory: a lane owns four REPLICATES, i.e. four different 0.4 GB planes of the workspace, so
     // storing from registers costs one memory request per lane and instruction (32 per warp store) -- the load/store unit, not
-    // HBM, was the limit.  Eight pairs (half an i-row: 64 contiguous bytes per replicate) are staged as [pair][replicate] and
-    // written by lanes (pair, replicate): four 64-byte requests per warp store.
+    // HBM, was the limit.  Four pairs (one 32-byte sector per replicate) are staged as [pair][replicate] and written by lanes
+    // (pair, replicate): eight whole-sector requests per warp store; the small stage keeps three CTAs on an SM.
     auto flush_pair = [&]() {
         double v4[4];
 #pragma unroll
@@ -509,19 +510,20 @@ boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* 
 #pragma unroll
             for (int k = 0; k < 6; ++k) acc[k][r] = 0u;
         }
-        double* od = obuf + (pf & 7) * BSS_OUT_LD + 4 * lane;
+        double* od = obuf + (pf & (BSS_OUT_PAIRS - 1)) * BSS_OUT_LD + 4 * lane;
         *reinterpret_cast<double2*>(od) = make_double2(v4[0], v4[1]);
         *reinterpret_cast<double2*>(od + 2) = make_double2(v4[2], v4[3]);
-        if ((pf & 7) == 7) {
+        if ((pf & (BSS_OUT_PAIRS - 1)) == BSS_OUT_PAIRS - 1) {
             __syncwarp();
             const int ii = rg * NR + (pf >> 4);
-            const int pj = lane & 7;                                     // pair of the half row
-            double* o = wsblk + (ii << 4) + (pf & 8) + pj;
-            const double* os = obuf + pj * BSS_OUT_LD + (lane >> 3);
+            const int pj = lane & (BSS_OUT_PAIRS - 1);                   // pair of the staged group
+            constexpr int RPI = 32 / BSS_OUT_PAIRS;                      // replicates per store instruction
+            double* o = wsblk + (ii << 4) + (pf & 15 & ~(BSS_OUT_PAIRS - 1)) + pj;
+            const double* os = obuf + pj * BSS_OUT_LD + lane / BSS_OUT_PAIRS;
 #pragma unroll 4
-            for (int it = 0; it < 32; ++it) {
-                const long long rep = repw + 4 * it + (lane >> 3);
-                if (rep < nb_total) o[(size_t)rep * ws_rep_stride] = os[4 * it];
+            for (int it = 0; it < 128 / RPI; ++it) {
+                const long long rep = repw + RPI * it + lane / BSS_OUT_PAIRS;
+                if (rep < nb_total) o[(size_t)rep * ws_rep_stride] = os[RPI * it];
             }
             __syncwarp();
         }

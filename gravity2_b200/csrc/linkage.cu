@@ -36,7 +36,7 @@
 #include <vector>
 
 #define LK_THREADS 1024
-#define LK_MLP 4                 // row elements per thread in flight at a time
+#define LK_MLP 10                // row elements per thread in flight at a time (one batch per 10 240-leaf row)
 
 struct LkBest { double d; int i; };
 
