@@ -407,7 +407,8 @@ bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowt
 #define BSS_LIST_BYTES (BSS_CH * 32)                 // 128
 #define BSS_W_BYTES (BSS_CH * 4 * 128)               // 2048
 #define BSS_OUT_LD 132                               // doubles per staged pair: 128 replicates + 4 (bank spread)
-#define BSS_OUT_PAIRS 4                              // pairs staged per flush: 4 x 8 bytes = one 32-byte sector per replicate
+#define BSS_OUT_PAIRS 8                              // pairs staged per flush: half an i-row, 64 contiguous bytes per replicate
+                                                     // (4 pairs / 32-byte requests / three CTAs per SM measured 1.65x slower)
 #define BSS_OUT_BYTES (BSS_OUT_PAIRS * BSS_OUT_LD * 8)
 #define BSS_WARP_BYTES (3 * BSS_LIST_BYTES + 2 * BSS_W_BYTES + BSS_OUT_BYTES)
 
@@ -424,7 +425,7 @@ __device__ __forceinline__ void bss_wait2() { asm volatile("cp.async.wait_group 
 __device__ __forceinline__ void bss_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
 template <int RW>
-__global__ void __launch_bounds__(BS_THREADS, 3)
+__global__ void __launch_bounds__(BS_THREADS, 2)
 boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* __restrict__ pend, const uint8_t* __restrict__ ent,
                           int nt, long long tile_begin, const uint8_t* __restrict__ wT, long long w_ld, int nb_total,
                           long long ws_rep_stride, double quantum, double* __restrict__ ws) {
@@ -496,8 +497,8 @@ boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* 
         for (int r = 0; r < 4; ++r) acc[k][r] = 0u;
     // Results leave through shared memory: a lane owns four REPLICATES, i.e. four different 0.4 GB planes of the workspace, so
     // storing from registers costs one memory request per lane and instruction (32 per warp store) -- the load/store unit, not
-    // HBM, was the limit.  Four pairs (one 32-byte sector per replicate) are staged as [pair][replicate] and written by lanes
-    // (pair, replicate): eight whole-sector requests per warp store; the small stage keeps three CTAs on an SM.
+    // HBM, was the limit.  Eight pairs (half an i-row: 64 contiguous bytes per replicate) are staged as [pair][replicate] and
+    // written by lanes (pair, replicate): four 64-byte requests per warp store.
     auto flush_pair = [&]() {
         double v4[4];
 #pragma unroll
