@@ -69,18 +69,22 @@ __device__ __forceinline__ double lk_new_dist(double d_xi, double d_yi, double d
     return __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), -c));
 }
 
-template <int METHOD>
-__global__ void __launch_bounds__(LK_THREADS, 1)
+// THREADS = 1024: the whole SM to one matrix (a single matrix: gv2_linkage_host).  THREADS = 512 at <= 64 registers: half an
+// SM's threads and registers, so that a CTA of the similarity kernels stays resident beside it -- in the dendrogram mode of
+// the bootstrap job the clustering (bound by DRAM operations: scattered 8-byte column updates) and the tail kernels (bound
+// by the ALU pipe) then share every SM instead of taking turns.
+template <int METHOD, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
     extern __shared__ int lk_size[];
-    __shared__ LkBest s_warp[LK_THREADS / 32];
+    __shared__ LkBest s_warp[THREADS / 32];
     __shared__ int s_x, s_y, s_len, s_merge, s_first;
     __shared__ double s_min, s_dp;
     double* D = Dall + (size_t)blockIdx.x * d_stride;
     int* chain = lk_size + n;
     double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n; i += LK_THREADS) lk_size[i] = 1;
+    for (int i = tid; i < n; i += THREADS) lk_size[i] = 1;
     if (tid == 0) { s_len = 0; s_first = 0; }
     __syncthreads();
     for (int k = 0; k < n - 1; ++k) {
@@ -101,18 +105,18 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
             LkBest best{INFINITY, 0x7fffffff};
             // The step is one DRAM round trip long, not one per element: a thread's loads of the row are all issued before the
             // first is looked at (dead clusters' entries are read and ignored: the row is dense), LK_MLP at a time.
-            for (int i0 = tid; i0 < n; i0 += LK_THREADS * LK_MLP) {
+            for (int i0 = tid; i0 < n; i0 += THREADS * LK_MLP) {
                 double dv[LK_MLP];
                 int sz[LK_MLP];
 #pragma unroll
                 for (int u = 0; u < LK_MLP; ++u) {
-                    const int i = i0 + u * LK_THREADS;
+                    const int i = i0 + u * THREADS;
                     dv[u] = i < n ? __ldcs(row + i) : INFINITY;
                     sz[u] = i < n ? lk_size[i] : 0;
                 }
 #pragma unroll
                 for (int u = 0; u < LK_MLP; ++u) {
-                    const int i = i0 + u * LK_THREADS;
+                    const int i = i0 + u * THREADS;
                     if (sz[u] == 0 || i == x) continue;
                     if (i == prev) s_dp = dv[u];                     // the incumbent's distance, for the final comparison
                     if (dv[u] < best.d) { best.d = dv[u]; best.i = i; }   // ascending i per thread: first minimum kept
@@ -177,19 +181,19 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
         __syncthreads();
         const double* rx = D + (size_t)x * n;
         double* ry = D + (size_t)y * n;
-        for (int i0 = tid; i0 < n; i0 += LK_THREADS * LK_MLP) {
+        for (int i0 = tid; i0 < n; i0 += THREADS * LK_MLP) {
             double ax[LK_MLP], ay[LK_MLP];
             int sz[LK_MLP];
 #pragma unroll
             for (int u = 0; u < LK_MLP; ++u) {
-                const int i = i0 + u * LK_THREADS;
+                const int i = i0 + u * THREADS;
                 ax[u] = i < n ? rx[i] : 0.0;
                 ay[u] = i < n ? ry[i] : 0.0;
                 sz[u] = i < n ? lk_size[i] : 0;
             }
 #pragma unroll
             for (int u = 0; u < LK_MLP; ++u) {
-                const int i = i0 + u * LK_THREADS;
+                const int i = i0 + u * THREADS;
                 if (sz[u] == 0 || i == y) continue;
                 const double v = lk_new_dist<METHOD>(ax[u], ay[u], dmin, nx, ny, sz[u]);
                 ry[i] = v;
@@ -372,10 +376,13 @@ int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t
         const int sz = (int)std::max<size_t>(smem, 1024);
         cudaError_t e = cudaSuccess;
         switch (method) {
-            case LK_AVERAGE: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_AVERAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
-            case LK_COMPLETE: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_COMPLETE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
-            case LK_WEIGHTED: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WEIGHTED>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
-            case LK_WARD: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
+            case LK_AVERAGE:
+                e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_AVERAGE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_AVERAGE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+                break;
+            case LK_COMPLETE: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_COMPLETE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
+            case LK_WEIGHTED: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WEIGHTED, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
+            case LK_WARD: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WARD, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
             default: e = cudaFuncSetAttribute(lk_mst_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
         }
         GV2_CUDA(ctx, e);
@@ -384,11 +391,18 @@ int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t
     Gv2Timer timer(ctx, GV2_TIME_LINKAGE);
     timer.begin();
     const unsigned g = (unsigned)nb;
+    // several matrices at once (the bootstrap job's dendrogram mode): half-SM CTAs, so that the similarity kernels of the next
+    // replicates run beside the clustering (GV2_LK_THREADS=1024 / 512 overrides)
+    const char* lkenv = getenv("GV2_LK_THREADS");
+    const bool half_sm = lkenv ? atoi(lkenv) == 512 : nb > 1;
     switch (method) {
-        case LK_AVERAGE: lk_nn_chain_kernel<LK_AVERAGE><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
-        case LK_COMPLETE: lk_nn_chain_kernel<LK_COMPLETE><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
-        case LK_WEIGHTED: lk_nn_chain_kernel<LK_WEIGHTED><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
-        case LK_WARD: lk_nn_chain_kernel<LK_WARD><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+        case LK_AVERAGE:
+            if (half_sm) lk_nn_chain_kernel<LK_AVERAGE, 512><<<g, 512, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+            else lk_nn_chain_kernel<LK_AVERAGE, 1024><<<g, 1024, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+            break;
+        case LK_COMPLETE: lk_nn_chain_kernel<LK_COMPLETE, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+        case LK_WEIGHTED: lk_nn_chain_kernel<LK_WEIGHTED, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+        case LK_WARD: lk_nn_chain_kernel<LK_WARD, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
         default: lk_mst_single_kernel<<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
     }
     GV2_LAUNCH_CHECK(ctx);
