@@ -580,6 +580,94 @@ boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* 
     while (pf < NR * 16) flush_pair();               // the remaining (possibly empty) pairs of the warp's rows
 }
 
+// Few replicates (<= 12: the base matrix is ONE all-ones replicate, the PL2 loop of the reference draws 10): with replicates
+// on the lanes most of a warp would idle and every pair would cost a warp a flush.  Here the lanes are the 32 PAIRS of two
+// i-rows of a 16 x 16 block and every lane walks its own list (1.6 groups on average) with its replicates in registers:
+// same byte planes, same dp4a, same limb recombination -- bit-identical to the streaming kernel.  Stores: the 16 pairs of an
+// i-row are 128 contiguous bytes of a replicate's plane.  NQ = replicate quads per lane (nb <= 4 NQ).
+// grid = (64 sub-blocks, tiles), block = 8 warps x 2 i-rows
+template <int NQ>
+__global__ void __launch_bounds__(BS_THREADS, NQ == 1 ? 3 : 2)
+boot_sparse_pairlane_kernel(const long long* __restrict__ rowptr, const uint32_t* __restrict__ pend, const uint8_t* __restrict__ ent,
+                            int nt, long long tile_begin, const uint8_t* __restrict__ wT, long long w_ld, int nb_total,
+                            long long ws_rep_stride, double quantum, double* __restrict__ ws) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = blockIdx.x, si = sub >> 3, sj = sub & 7;
+    int bi, bj;
+    bs_tile_coords(tile_begin + blockIdx.y, nt, &bi, &bj);
+    if (bi == bj && si > sj) return;                 // block entirely below the diagonal (never read)
+    const int ii = 2 * warp + (lane >> 4), jj = lane & 15;
+    const long long rr = ((tile_begin + blockIdx.y) * 64 + sub) * 16 + ii;
+    const uint32_t pe = pend[rr * 16 + jj];
+    uint32_t pb = __shfl_up_sync(0xffffffffu, pe, 1);
+    if (jj == 0) pb = 0u;
+    const uint8_t* gp = ent + (size_t)(rowptr[rr] + pb) * 8;
+    const int ng = (int)((pe - pb) >> 2);
+    unsigned acc[NQ][6][4];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[q][k][r] = 0u;
+    uint4 A = make_uint4(0, 0, 0, 0), B = A;
+    if (ng > 0) {
+        A = __ldg(reinterpret_cast<const uint4*>(gp));
+        B = __ldg(reinterpret_cast<const uint4*>(gp + 16));
+    }
+    for (int g = 0; g < ng; ++g) {
+        uint4 An = A, Bn = B;
+        if (g + 1 < ng) {                            // the next group is on its way while this one's multiplicities are gathered
+            An = __ldg(reinterpret_cast<const uint4*>(gp + 32 * (g + 1)));
+            Bn = __ldg(reinterpret_cast<const uint4*>(gp + 32 * (g + 1) + 16));
+        }
+        const uint8_t* w0 = wT + (size_t)(A.x & 0xffffu) * (size_t)w_ld;
+        const uint8_t* w1 = wT + (size_t)(A.x >> 16) * (size_t)w_ld;
+        const uint8_t* w2 = wT + (size_t)(A.y & 0xffffu) * (size_t)w_ld;
+        const uint8_t* w3 = wT + (size_t)(A.y >> 16) * (size_t)w_ld;
+        unsigned x[NQ][4];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            x[q][0] = __ldg(reinterpret_cast<const unsigned*>(w0) + q);
+            x[q][1] = __ldg(reinterpret_cast<const unsigned*>(w1) + q);
+            x[q][2] = __ldg(reinterpret_cast<const unsigned*>(w2) + q);
+            x[q][3] = __ldg(reinterpret_cast<const unsigned*>(w3) + q);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const unsigned t0 = __byte_perm(x[q][0], x[q][1], 0x5140), t1 = __byte_perm(x[q][2], x[q][3], 0x5140);
+            const unsigned t2 = __byte_perm(x[q][0], x[q][1], 0x7362), t3 = __byte_perm(x[q][2], x[q][3], 0x7362);
+            unsigned y[4];
+            y[0] = __byte_perm(t0, t1, 0x5410); y[1] = __byte_perm(t0, t1, 0x7632);
+            y[2] = __byte_perm(t2, t3, 0x5410); y[3] = __byte_perm(t2, t3, 0x7632);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[q][0][r] = __dp4a(A.z, y[r], acc[q][0][r]);
+                acc[q][1][r] = __dp4a(A.w, y[r], acc[q][1][r]);
+                acc[q][2][r] = __dp4a(B.x, y[r], acc[q][2][r]);
+                acc[q][3][r] = __dp4a(B.y, y[r], acc[q][3][r]);
+                acc[q][4][r] = __dp4a(B.z, y[r], acc[q][4][r]);
+                acc[q][5][r] = __dp4a(B.w, y[r], acc[q][5][r]);
+            }
+        }
+        A = An;
+        B = Bn;
+    }
+    const double q_hi = quantum * 65536.0;
+    double* o = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + (size_t)(((si << 3) + sj) << 8) + (ii << 4) + jj;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int rep = 4 * q + r;
+            if (rep >= nb_total) continue;
+            const unsigned long long hi = (unsigned long long)acc[q][2][r] + ((unsigned long long)acc[q][3][r] << 8) +
+                                          ((unsigned long long)acc[q][4][r] << 16) + ((unsigned long long)acc[q][5][r] << 24);
+            const unsigned lo = acc[q][0][r] + (acc[q][1][r] << 8);
+            __stcs(o + (size_t)rep * ws_rep_stride, bs_to_double(hi, lo, q_hi, quantum));
+        }
+}
+
 // ---------------------------------------------------------------------------------- CSR of the fixed-point table
 // entries: x > 0 (NaN rows are flagged separately by prepare_table; negative tables do not come here)
 __device__ __forceinline__ unsigned long long bs_fixed48(double x, double scale) {
@@ -893,7 +981,15 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
         }
         dim3 gl(64, (unsigned)ntl, (unsigned)(w_ld / (128 * rwp)));
         const int ntt = (int)(n_pad / GV2_TILE);
-        if (rwp == 1)
+        if (nb <= 12) {                              // few replicates: lanes = pairs
+            dim3 gp(64, (unsigned)ntl);
+            if (nb <= 4)
+                boot_sparse_pairlane_kernel<1><<<gp, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+            else if (nb <= 8)
+                boot_sparse_pairlane_kernel<2><<<gp, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+            else
+                boot_sparse_pairlane_kernel<3><<<gp, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
+        } else if (rwp == 1)
             boot_sparse_stream_kernel<1><<<gl, BS_THREADS, ssm, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);
         else if (rwp == 2)
             boot_sparse_stream_kernel<2><<<gl, BS_THREADS, ssm, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);

@@ -69,10 +69,10 @@ __device__ __forceinline__ double lk_new_dist(double d_xi, double d_yi, double d
     return __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), -c));
 }
 
-// THREADS = 1024: the whole SM to one matrix (a single matrix: gv2_linkage_host).  THREADS = 512 at <= 64 registers: half an
-// SM's threads and registers, so that a CTA of the similarity kernels stays resident beside it -- in the dendrogram mode of
-// the bootstrap job the clustering (bound by DRAM operations: scattered 8-byte column updates) and the tail kernels (bound
-// by the ALU pipe) then share every SM instead of taking turns.
+// THREADS = 1024: the whole SM to one matrix.  (Half-SM CTAs of 512 threads, which leave room for a CTA of the similarity
+// kernels beside the clustering in the bootstrap job's dendrogram mode, were measured and change nothing -- 5.20 s against
+// 5.19 s for 1001 trees of 10 000 leaves: the clustering is bound by DRAM operations, the n scattered 8-byte column updates
+// of every merge, and whatever runs beside it shares that budget.)
 template <int METHOD, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
@@ -132,7 +132,7 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
             if (lane == 0) s_warp[warp] = best;
             __syncthreads();
             if (warp == 0) {
-                best = s_warp[lane];
+                best = lane < THREADS / 32 ? s_warp[lane] : LkBest{INFINITY, 0x7fffffff};
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     LkBest other;
@@ -378,7 +378,6 @@ int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t
         switch (method) {
             case LK_AVERAGE:
                 e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_AVERAGE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_AVERAGE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
                 break;
             case LK_COMPLETE: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_COMPLETE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
             case LK_WEIGHTED: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WEIGHTED, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
@@ -391,15 +390,8 @@ int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t
     Gv2Timer timer(ctx, GV2_TIME_LINKAGE);
     timer.begin();
     const unsigned g = (unsigned)nb;
-    // several matrices at once (the bootstrap job's dendrogram mode): half-SM CTAs, so that the similarity kernels of the next
-    // replicates run beside the clustering (GV2_LK_THREADS=1024 / 512 overrides)
-    const char* lkenv = getenv("GV2_LK_THREADS");
-    const bool half_sm = lkenv ? atoi(lkenv) == 512 : nb > 1;
     switch (method) {
-        case LK_AVERAGE:
-            if (half_sm) lk_nn_chain_kernel<LK_AVERAGE, 512><<<g, 512, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
-            else lk_nn_chain_kernel<LK_AVERAGE, 1024><<<g, 1024, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
-            break;
+        case LK_AVERAGE: lk_nn_chain_kernel<LK_AVERAGE, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
         case LK_COMPLETE: lk_nn_chain_kernel<LK_COMPLETE, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
         case LK_WEIGHTED: lk_nn_chain_kernel<LK_WEIGHTED, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
         case LK_WARD: lk_nn_chain_kernel<LK_WARD, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;

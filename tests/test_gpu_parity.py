@@ -354,11 +354,13 @@ def test_tensor_core_path_is_exact_integer_arithmetic(eng):
 
 
 @pytest.mark.parametrize("n,p,dens,nb", [(150, 700, 0.1, 5), (200, 1500, 0.6, 24), (131, 40000, 0.02, 300),
-                                         (40, 3000, 1.0, 9), (300, 900, 0.03, 600)])
+                                         (40, 3000, 1.0, 9), (300, 900, 0.03, 600), (170, 900, 0.05, 3),
+                                         (140, 2000, 0.08, 12), (140, 2000, 0.08, 13)])
 def test_replicate_paths_agree(eng, monkeypatch, n, p, dens, nb):
     """The three replicate paths (CSR walk of sparse tables, tensor-core contraction, fp32 tile kernel) against the
     weighted oracle and each other.  Rows longer than one 256-entry segment, a table wider than one 32768-column
-    window, empty and duplicate genomes, diagonal blocks, and all three replicate-lane configurations."""
+    window, empty and duplicate genomes, diagonal blocks, all three replicate-lane configurations, and the lanes-are-pairs
+    kernel of launches with at most 12 replicates (1, 2, 3 replicate quads per lane) beside the streaming kernel."""
     t = synth.make_tables(n, p, 5, dens, seed=n + nb)
     t.sig[7] = 0.0
     t.sig[n - 1] = t.sig[2]
