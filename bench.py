@@ -372,6 +372,9 @@ def main():
         run_job(args, cfg)
 
 
+CPU_GROUP = None
+
+
 def init_dist(local_rank, world):
     import torch
     import torch.distributed as dist
@@ -380,6 +383,11 @@ def init_dist(local_rank, world):
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # its banner goes to stdout, ahead of the JSON line
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a host-side group: ranks that wait for rank 0's single-process multi-GPU leg must not spin in a NCCL kernel on the
+        # GPUs that leg is measured on
+        global CPU_GROUP
+        import datetime
+        CPU_GROUP = dist.new_group(backend="gloo", timeout=datetime.timedelta(minutes=60))
     return torch, dist
 
 
@@ -532,7 +540,7 @@ def run_job(args, cfg):
         sync_all()
         if rank == 0:
             e2e = measure_e2e_multi(t, cfg, gor, weights, pairs, world)
-        dist.barrier()
+        dist.barrier(group=CPU_GROUP)
     elif not args.no_e2e:
         if B > 0 and not pl2:
             e2e = measure_e2e_trees(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch)

@@ -1,7 +1,8 @@
 """Turn ncu outputs into the committed summaries under profiles/.
 
   python tools/profile_summary.py launches <ncu --csv launch list> <out.csv> "<command line>"
-  python tools/profile_summary.py full <report.ncu-rep> <out.csv>          (needs ncu on PATH; one row block per kernel)
+  python tools/profile_summary.py full <report.ncu-rep | raw.csv> <out.csv>   (one row block per kernel; a .ncu-rep needs ncu on
+                                                                             PATH, a `--page raw --csv` export made on the box does not)
 """
 import collections
 import csv
@@ -51,7 +52,10 @@ def launches(src, dst, cmd):
 
 
 def full(rep, dst):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(dst, "w") as f:
