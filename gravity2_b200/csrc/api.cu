@@ -239,6 +239,9 @@ static int pick_ksplit(gv2_ctx* ctx, int64_t ntl, int64_t nb, int64_t k_pad) {
 }
 
 // ------------------------------------------------------------------------- device job
+// parts of the device ring in the dendrogram mode: one computing, the others being clustered (host delivery uses two)
+#define GV2_RING_PARTS 4
+
 struct gv2_job {
     gv2_ctx* ctx = nullptr;
     int64_t n = 0, p = 0, g = 0, n_pad = 0, p_pad = 0, g_pad = 0, ntiles = 0;
@@ -263,8 +266,8 @@ struct gv2_job {
     DevBuf wsP, wsG, gomtab, gomf, gom_rowsum, gom_nan, gom_qmax, wf, w_rowsum, wbf16, mma_flag;
     DevBuf ones_w, sig_rowsum_fix;     // all-ones multiplicities and fixed-point row sums: the base matrix through the sparse path
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
-    cudaStream_t lk_stream[2] = {nullptr, nullptr};      // device UPGMA of the two ring halves, concurrent with the main stream
+    cudaEvent_t ev_ready[GV2_RING_PARTS] = {}, ev_drained[GV2_RING_PARTS] = {};
+    cudaStream_t lk_stream[GV2_RING_PARTS] = {};         // device UPGMA of the ring's parts, concurrent with the main stream
     size_t device_bytes() const {
         size_t b = sig64.bytes + loc64.bytes + sigf.bytes + sig_rowsum.bytes + sig_nan.bytes + gom_base.bytes +
                    wsP.bytes + wsG.bytes + gomtab.bytes + gomf.bytes + gom_rowsum.bytes + gom_nan.bytes + wf.bytes + w_rowsum.bytes;
@@ -286,10 +289,10 @@ extern "C" void gv2_job_destroy(gv2_job* job) {
     cudaStreamSynchronize(job->ctx->stream);
     if (job->copy_stream) {
         cudaStreamSynchronize(job->copy_stream);
-        for (int h = 0; h < 2; ++h) { cudaEventDestroy(job->ev_ready[h]); cudaEventDestroy(job->ev_drained[h]); }
+        for (int h = 0; h < GV2_RING_PARTS; ++h) { cudaEventDestroy(job->ev_ready[h]); cudaEventDestroy(job->ev_drained[h]); }
         cudaStreamDestroy(job->copy_stream);
     }
-    for (int h = 0; h < 2; ++h)
+    for (int h = 0; h < GV2_RING_PARTS; ++h)
         if (job->lk_stream[h]) { cudaStreamSynchronize(job->lk_stream[h]); cudaStreamDestroy(job->lk_stream[h]); }
     gom_db_free(job->gom);
     boot_sparse_free(job->sparse);
@@ -677,19 +680,19 @@ struct TreeSink {
     const char* const* names = nullptr;
     gv2_newick_cb cb = nullptr;
     void* user = nullptr;
-    double* zdev[2] = {nullptr, nullptr};
-    double* zhost[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    int64_t pend_b0[2] = {0, 0}, pend_cnt[2] = {0, 0};
-    int cur = 0;
+    double* zdev[GV2_RING_PARTS] = {};
+    double* zhost[GV2_RING_PARTS] = {};
+    cudaEvent_t ev[GV2_RING_PARTS] = {};
+    int64_t pend_b0[GV2_RING_PARTS] = {}, pend_cnt[GV2_RING_PARTS] = {};
+    int cur = 0, nparts = 2;
     std::vector<std::string> texts;
     ~TreeSink() {
-        for (int h = 0; h < 2; ++h) { cudaFree(zdev[h]); cudaFreeHost(zhost[h]); if (ev[h]) cudaEventDestroy(ev[h]); }
+        for (int h = 0; h < GV2_RING_PARTS; ++h) { cudaFree(zdev[h]); cudaFreeHost(zhost[h]); if (ev[h]) cudaEventDestroy(ev[h]); }
     }
-    int init(gv2_ctx* c, int64_t n_, int64_t cap_) {
-        ctx = c; n = n_; cap = cap_;
+    int init(gv2_ctx* c, int64_t n_, int64_t cap_, int nparts_) {
+        ctx = c; n = n_; cap = cap_; nparts = nparts_;
         const size_t zb = (size_t)cap * std::max<int64_t>(1, n - 1) * 4 * sizeof(double);
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < nparts; ++h) {
             GV2_CUDA(ctx, cudaMalloc((void**)&zdev[h], zb));
             GV2_CUDA(ctx, cudaMallocHost((void**)&zhost[h], zb));
             GV2_CUDA(ctx, cudaEventCreateWithFlags(&ev[h], cudaEventDisableTiming));
@@ -704,7 +707,7 @@ struct TreeSink {
             GV2_CUDA(ctx, cudaMemcpyAsync(zhost[cur], zdev[cur], (size_t)cnt * (n - 1) * 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         GV2_CUDA(ctx, cudaEventRecord(ev[cur], ctx->stream));
         pend_b0[cur] = b0; pend_cnt[cur] = cnt;
-        cur ^= 1;
+        cur = (cur + 1) % nparts;                    // now the OLDEST pending part: the one the caller drains next
         return GV2_OK;
     }
     int drain(int h) {
@@ -761,10 +764,13 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
     const int64_t n = job->n, p = job->p, g = job->g, ntl = job->ntiles;
     const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
     ring_len = std::min(ring_len, nb);
-    // sub-chunk: half the ring when results stream to the host (ping-pong), else the whole ring
-    // (dendrogram mode: the two halves are clustered on their own streams while the main stream computes the next ones)
+    // sub-chunk: half the ring when results stream to the host (ping-pong), else the whole ring.  Dendrogram mode: the ring is
+    // cut in (up to) four parts, each clustered on its own stream while the main stream computes into the free one -- the
+    // clustering is bound by DRAM operations and takes ~3x as long as the similarity kernels of the same replicates, so two or
+    // three clusterings are in flight at any time and the similarity kernels (ALU bound) run beside them
     const bool halves = ring_len >= 2 && ((!sink && host_out) || (sink && !dev_cb));
-    const int64_t sub = halves ? ring_len / 2 : ring_len;
+    const int nparts = sink ? sink->nparts : 2;
+    const int64_t sub = halves ? ring_len / nparts : ring_len;
     // super-chunk: bounded by the fp64 pair-sum workspace of the signature table (+ the GOM tables)
     const size_t per_rep = (job->need_p ? ntl * tile_elems * sizeof(double) + (size_t)job->p_pad : 0) +
                            (job->need_g ? (size_t)job->n_pad * job->g_pad * 4 + (size_t)n * g * 8 : 0) + (size_t)n * 8 * 2;
@@ -781,11 +787,11 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
         else if (super >= 32) super = super / 32 * 32;
     }
     if (sink && !job->lk_stream[0])
-        for (int h = 0; h < 2; ++h) GV2_CUDA(ctx, cudaStreamCreateWithFlags(&job->lk_stream[h], cudaStreamNonBlocking));
-    bool lk_pending[2] = {false, false};
+        for (int h = 0; h < GV2_RING_PARTS; ++h) GV2_CUDA(ctx, cudaStreamCreateWithFlags(&job->lk_stream[h], cudaStreamNonBlocking));
+    bool lk_pending[GV2_RING_PARTS] = {};
     if (!job->copy_stream) {
         GV2_CUDA(ctx, cudaStreamCreateWithFlags(&job->copy_stream, cudaStreamNonBlocking));
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < GV2_RING_PARTS; ++h) {
             GV2_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_ready[h], cudaEventDisableTiming));
             GV2_CUDA(ctx, cudaEventCreateWithFlags(&job->ev_drained[h], cudaEventDisableTiming));
         }
@@ -905,7 +911,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 if (rc) return rc;
                 GV2_CUDA(ctx, cudaEventRecord(job->ev_drained[half], job->lk_stream[half]));
                 lk_pending[half] = true;
-                if (halves) half ^= 1;
+                if (halves) half = (half + 1) % nparts;
                 if ((rc = sink->drain(sink->cur))) return rc;
             }
             if (host_out) {
@@ -928,10 +934,9 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
         if ((rc = deliver(half))) return rc;
         if ((rc = deliver(half ^ 1))) return rc;
     }
-    if (sink) {
-        if ((rc = sink->drain(sink->cur))) return rc;
-        if ((rc = sink->drain(sink->cur ^ 1))) return rc;
-    }
+    if (sink)
+        for (int k = 0; k < sink->nparts; ++k)                             // oldest first: trees leave in replicate order
+            if ((rc = sink->drain((sink->cur + k) % sink->nparts))) return rc;
     if (host_out) GV2_CUDA(ctx, cudaStreamSynchronize(job->copy_stream));
     (void)used_mma;
     return GV2_OK;
@@ -955,7 +960,10 @@ extern "C" int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weight
     if (nb <= 0 || job->n == 0) return GV2_OK;
     GV2_CUDA(job->ctx, cudaSetDevice(job->ctx->device));
     TreeSink sink;
-    int rc = sink.init(job->ctx, job->n, std::min<int64_t>(ring_len, nb));
+    int nparts = std::min<int64_t>(ring_len, nb) >= 8 ? GV2_RING_PARTS : 2;
+    if (const char* env = getenv("GV2_RING_PARTS_USED")) nparts = std::max(2, std::min(GV2_RING_PARTS, atoi(env)));
+    if (std::min<int64_t>(ring_len, nb) < nparts) nparts = 2;
+    int rc = sink.init(job->ctx, job->n, std::min<int64_t>(ring_len, nb), nparts);
     if (rc) return rc;
     sink.names = leaf_names; sink.cb = cb; sink.user = user; sink.method = mth;
     return replicates_impl(job, dev_weights, nb, dev_ring, ring_len, nullptr, nullptr, nullptr, &sink);
