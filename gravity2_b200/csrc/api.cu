@@ -786,6 +786,9 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
         else if (super >= 128) super = super / 128 * 128;
         else if (super >= 32) super = super / 32 * 32;
     }
+    // dendrogram mode: whole ring parts per super-chunk -- a remainder of a few matrices would hold a part of the ring (and a
+    // clustering launch of a few CTAs, as long as a full one) for itself
+    if (sink && halves && super < nb && super > sub) super = super / sub * sub;
     if (sink && !job->lk_stream[0])
         for (int h = 0; h < GV2_RING_PARTS; ++h) GV2_CUDA(ctx, cudaStreamCreateWithFlags(&job->lk_stream[h], cudaStreamNonBlocking));
     bool lk_pending[GV2_RING_PARTS] = {};

@@ -625,13 +625,21 @@ boot_sparse_pairlane_kernel(const long long* __restrict__ rowptr, const uint32_t
         const uint8_t* w1 = wT + (size_t)(A.x >> 16) * (size_t)w_ld;
         const uint8_t* w2 = wT + (size_t)(A.y & 0xffffu) * (size_t)w_ld;
         const uint8_t* w3 = wT + (size_t)(A.y >> 16) * (size_t)w_ld;
+        // (the multiplicity table of these launches is compact: 4 / 8 / 16 bytes per column, so that it stays in L1 -- with the
+        //  streaming kernel's 128-byte rows every entry cost an L2 sector)
         unsigned x[NQ][4];
+        const uint8_t* wp[4] = {w0, w1, w2, w3};
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            x[q][0] = __ldg(reinterpret_cast<const unsigned*>(w0) + q);
-            x[q][1] = __ldg(reinterpret_cast<const unsigned*>(w1) + q);
-            x[q][2] = __ldg(reinterpret_cast<const unsigned*>(w2) + q);
-            x[q][3] = __ldg(reinterpret_cast<const unsigned*>(w3) + q);
+        for (int e = 0; e < 4; ++e) {
+            if (NQ == 1) {
+                x[0][e] = __ldg(reinterpret_cast<const unsigned*>(wp[e]));
+            } else if (NQ == 2) {
+                const uint2 v = __ldg(reinterpret_cast<const uint2*>(wp[e]));
+                x[0][e] = v.x; x[NQ > 1 ? 1 : 0][e] = v.y;
+            } else {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(wp[e]));
+                x[0][e] = v.x; x[NQ > 1 ? 1 : 0][e] = v.y; x[NQ > 2 ? 2 : 0][e] = v.z;
+            }
         }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -953,7 +961,8 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
     if (ntl <= 0 || nb <= 0) return GV2_OK;
     const bool use_lists = s->lists.rowptr != nullptr;
     const int rl = bs_lanes(nb);
-    const int64_t w_ld = use_lists ? bsl_wld(nb) : bs_wld(nb);
+    const bool pairlane = use_lists && nb <= 12;     // few replicates: lanes = pairs, compact multiplicity rows
+    const int64_t w_ld = pairlane ? (nb <= 4 ? 4 : nb <= 8 ? 8 : 16) : use_lists ? bsl_wld(nb) : bs_wld(nb);
     uint8_t* wT = (uint8_t*)wT_scratch;
     dim3 gt((unsigned)((k_pad + 31) / 32), (unsigned)((w_ld + 31) / 32)), bt(32, 8);
     bs_weights_transpose_kernel<<<gt, bt, 0, ctx->stream>>>(w, nb, k, k_pad, w_ld, wT, overflow_flag);
@@ -979,9 +988,9 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
             GV2_CUDA(ctx, cudaFuncSetAttribute(boot_sparse_stream_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
             ctx->smem_attr_done |= GV2_ATTR_STREAM;
         }
-        dim3 gl(64, (unsigned)ntl, (unsigned)(w_ld / (128 * rwp)));
+        dim3 gl(64, (unsigned)ntl, (unsigned)std::max<int64_t>(1, w_ld / (128 * rwp)));
         const int ntt = (int)(n_pad / GV2_TILE);
-        if (nb <= 12) {                              // few replicates: lanes = pairs
+        if (pairlane) {
             dim3 gp(64, (unsigned)ntl);
             if (nb <= 4)
                 boot_sparse_pairlane_kernel<1><<<gp, BS_THREADS, 0, ctx->stream>>>(L.rowptr, L.pend, L.ent, ntt, tile_begin, wT, w_ld, (int)nb, rep_stride_l, s->quantum, ws);

@@ -69,15 +69,38 @@ __device__ __forceinline__ double lk_new_dist(double d_xi, double d_yi, double d
     return __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), -c));
 }
 
+// Minimum of (distance, index) over a warp in three REDUX instructions instead of fifteen shuffles: the distance as a
+// sortable 64-bit key (x + 0.0 folds -0.0 into +0.0, NaN -> the largest key: never chosen, as with a strict `<`), minimum of
+// the high words, then of the low words among the lanes that hold it, then of the indices among those -- "smaller distance,
+// on ties the lower index", what an upward scan with a strict `<` keeps.
+struct LkKey { unsigned hi, lo; int i; };
+__device__ __forceinline__ LkKey lk_key(double d, int i) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d + 0.0);
+    unsigned long long k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    if (d != d) k = ~0ull;
+    return LkKey{(unsigned)(k >> 32), (unsigned)k, i};
+}
+__device__ __forceinline__ double lk_key_value(unsigned hi, unsigned lo) {
+    const unsigned long long k = ((unsigned long long)hi << 32) | lo;
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+__device__ __forceinline__ LkKey lk_warp_min(LkKey k) {
+    const unsigned mh = __reduce_min_sync(0xffffffffu, k.hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, k.hi == mh ? k.lo : 0xffffffffu);
+    const int mi = (int)__reduce_min_sync(0xffffffffu, (k.hi == mh && k.lo == ml) ? (unsigned)k.i : 0x7fffffffu);
+    return LkKey{mh, ml, mi};
+}
+
 // THREADS = 1024: the whole SM to one matrix.  (Half-SM CTAs of 512 threads, which leave room for a CTA of the similarity
-// kernels beside the clustering in the bootstrap job's dendrogram mode, were measured and change nothing -- 5.20 s against
-// 5.19 s for 1001 trees of 10 000 leaves: the clustering is bound by DRAM operations, the n scattered 8-byte column updates
-// of every merge, and whatever runs beside it shares that budget.)
+// kernels beside the clustering in the bootstrap job's dendrogram mode, were measured twice: 5.20 s against 5.19 s for 1001
+// trees of 10 000 leaves with a two-part ring, 4.70 s against 4.42 s with the four-part ring.)
+// A thread owns the same row positions i = tid + e THREADS in every row, so which of them are live clusters is a register
+// bit mask (bit e): dead positions are neither loaded nor compared, and no shared-memory lookup sits in the scan.
 template <int METHOD, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
     extern __shared__ int lk_size[];
-    __shared__ LkBest s_warp[THREADS / 32];
+    __shared__ LkKey s_warp[THREADS / 32];
     __shared__ int s_x, s_y, s_len, s_merge, s_first;
     __shared__ double s_min, s_dp;
     double* D = Dall + (size_t)blockIdx.x * d_stride;
@@ -85,6 +108,9 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
     double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n; i += THREADS) lk_size[i] = 1;
+    unsigned alive = 0u;                              // n <= 32 THREADS (the shared-memory limit of the launcher is lower)
+    for (int e = 0; e < 32; ++e)
+        if (tid + e * THREADS < n) alive |= 1u << e;
     if (tid == 0) { s_len = 0; s_first = 0; }
     __syncthreads();
     for (int k = 0; k < n - 1; ++k) {
@@ -102,52 +128,39 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
             const int x = chain[len - 1];
             const int prev = len > 1 ? chain[len - 2] : -1;
             const double* row = D + (size_t)x * n;
-            LkBest best{INFINITY, 0x7fffffff};
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
             // The step is one DRAM round trip long, not one per element: a thread's loads of the row are all issued before the
-            // first is looked at (dead clusters' entries are read and ignored: the row is dense), LK_MLP at a time.
-            for (int i0 = tid; i0 < n; i0 += THREADS * LK_MLP) {
+            // first is looked at, LK_MLP at a time.
+            for (int e0 = 0, i0 = tid; i0 < n; e0 += LK_MLP, i0 += THREADS * LK_MLP) {
                 double dv[LK_MLP];
-                int sz[LK_MLP];
+                const unsigned live = alive >> e0;
+#pragma unroll
+                for (int u = 0; u < LK_MLP; ++u) dv[u] = (live >> u) & 1u ? __ldcs(row + i0 + u * THREADS) : INFINITY;
 #pragma unroll
                 for (int u = 0; u < LK_MLP; ++u) {
                     const int i = i0 + u * THREADS;
-                    dv[u] = i < n ? __ldcs(row + i) : INFINITY;
-                    sz[u] = i < n ? lk_size[i] : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < LK_MLP; ++u) {
-                    const int i = i0 + u * THREADS;
-                    if (sz[u] == 0 || i == x) continue;
+                    if (!((live >> u) & 1u) || i == x) continue;
                     if (i == prev) s_dp = dv[u];                     // the incumbent's distance, for the final comparison
-                    if (dv[u] < best.d) { best.d = dv[u]; best.i = i; }   // ascending i per thread: first minimum kept
+                    if (dv[u] < bd) { bd = dv[u]; bi = i; }          // ascending i per thread: first minimum kept
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                LkBest other;
-                other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
-                other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-                best = lk_min(best, other);
-            }
+            LkKey best = lk_warp_min(lk_key(bd, bi));
             if (lane == 0) s_warp[warp] = best;
             __syncthreads();
             if (warp == 0) {
-                best = lane < THREADS / 32 ? s_warp[lane] : LkBest{INFINITY, 0x7fffffff};
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    LkBest other;
-                    other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
-                    other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-                    best = lk_min(best, other);
-                }
+                best = lane < THREADS / 32 ? s_warp[lane] : LkKey{0xffffffffu, 0xffffffffu, 0x7fffffff};
+                best = lk_warp_min(best);
                 if (lane == 0) {
                     // the previous chain element is the incumbent: a scanned cluster replaces it only if strictly closer
                     int y = best.i;
-                    double cur = best.d;
+                    double cur = lk_key_value(best.hi, best.lo);
+                    const bool none = best.hi == 0xffffffffu && best.lo == 0xffffffffu;   // nothing comparable (all NaN)
+                    if (none) { y = 0x7fffffff; cur = INFINITY; }
                     if (prev >= 0) {
                         const double dp = s_dp;
-                        if (!(best.d < dp)) { y = prev; cur = dp; }
-                    } else if (best.i == 0x7fffffff) {
+                        if (!(cur < dp)) { y = prev; cur = dp; }
+                    } else if (y == 0x7fffffff) {
                         y = 0;                        // every distance NaN: scipy keeps its stale y; unreachable for cleaned matrices
                     }
                     if (prev >= 0 && y == prev) {
@@ -168,6 +181,7 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
         if (x > y) { const int t = x; x = y; y = t; }
         const int nx = lk_size[x], ny = lk_size[y];
         const double dmin = s_min;
+        if ((x & (THREADS - 1)) == tid) alive &= ~(1u << (x / THREADS));   // x dies; its owner drops it
         __syncthreads();                              // everyone has read the sizes and s_* before they change
         if (tid == 0) {
             Z[(size_t)k * 4 + 0] = (double)x;
@@ -178,23 +192,24 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
             lk_size[y] = nx + ny;
             s_len -= 2;
         }
-        __syncthreads();
         const double* rx = D + (size_t)x * n;
         double* ry = D + (size_t)y * n;
-        for (int i0 = tid; i0 < n; i0 += THREADS * LK_MLP) {
+        for (int e0 = 0, i0 = tid; i0 < n; e0 += LK_MLP, i0 += THREADS * LK_MLP) {
             double ax[LK_MLP], ay[LK_MLP];
             int sz[LK_MLP];
+            const unsigned live = alive >> e0;
 #pragma unroll
             for (int u = 0; u < LK_MLP; ++u) {
                 const int i = i0 + u * THREADS;
-                ax[u] = i < n ? rx[i] : 0.0;
-                ay[u] = i < n ? ry[i] : 0.0;
-                sz[u] = i < n ? lk_size[i] : 0;
+                const bool on = ((live >> u) & 1u) && i != y;
+                ax[u] = on ? rx[i] : 0.0;
+                ay[u] = on ? ry[i] : 0.0;
+                sz[u] = on ? lk_size[i] : 0;         // (i != x, y: not the two entries thread 0 is changing)
             }
 #pragma unroll
             for (int u = 0; u < LK_MLP; ++u) {
                 const int i = i0 + u * THREADS;
-                if (sz[u] == 0 || i == y) continue;
+                if (sz[u] == 0) continue;
                 const double v = lk_new_dist<METHOD>(ax[u], ay[u], dmin, nx, ny, sz[u]);
                 ry[i] = v;
                 D[(size_t)i * n + y] = v;
