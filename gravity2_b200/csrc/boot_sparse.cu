@@ -582,10 +582,16 @@ boot_sparse_stream_kernel(const long long* __restrict__ rowptr, const uint32_t* 
 
 // Few replicates (<= 12: the base matrix is ONE all-ones replicate, the PL2 loop of the reference draws 10): with replicates
 // on the lanes most of a warp would idle and every pair would cost a warp a flush.  Here the lanes are the 32 PAIRS of two
-// i-rows of a 16 x 16 block and every lane walks its own list (1.6 groups on average) with its replicates in registers:
-// same byte planes, same dp4a, same limb recombination -- bit-identical to the streaming kernel.  Stores: the 16 pairs of an
-// i-row are 128 contiguous bytes of a replicate's plane.  NQ = replicate quads per lane (nb <= 4 NQ).
+// i-rows of a 16 x 16 block with their replicates in registers: same byte planes, same dp4a, same limb recombination --
+// bit-identical to the streaming kernel.  List lengths are very uneven (two genomes of one taxon share hundreds of columns,
+// two of different taxa a handful), so
+//   long lists (more than PL_SHORT groups) are walked by the whole warp, 32 groups per step, and their plane sums meet in
+//                REDUX additions (exact integers: order does not matter);
+//   short lists are walked by their own lane.
+// Stores: the 16 pairs of an i-row are 128 contiguous bytes of a replicate's plane.  The multiplicity table of these launches
+// is compact (4 / 8 / 16 bytes per column: L1 resident).  NQ = replicate quads per lane (nb <= 4 NQ).
 // grid = (64 sub-blocks, tiles), block = 8 warps x 2 i-rows
+#define PL_SHORT 3
 template <int NQ>
 __global__ void __launch_bounds__(BS_THREADS, NQ == 1 ? 3 : 2)
 boot_sparse_pairlane_kernel(const long long* __restrict__ rowptr, const uint32_t* __restrict__ pend, const uint8_t* __restrict__ ent,
@@ -603,32 +609,22 @@ boot_sparse_pairlane_kernel(const long long* __restrict__ rowptr, const uint32_t
     if (jj == 0) pb = 0u;
     const uint8_t* gp = ent + (size_t)(rowptr[rr] + pb) * 8;
     const int ng = (int)((pe - pb) >> 2);
+    const double q_hi = quantum * 65536.0;
+    double* o = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + (size_t)(((si << 3) + sj) << 8) + (ii << 4) + jj;
     unsigned acc[NQ][6][4];
+    auto clear = [&]() {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q)
+        for (int q = 0; q < NQ; ++q)
 #pragma unroll
-        for (int k = 0; k < 6; ++k)
+            for (int k = 0; k < 6; ++k)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[q][k][r] = 0u;
-    uint4 A = make_uint4(0, 0, 0, 0), B = A;
-    if (ng > 0) {
-        A = __ldg(reinterpret_cast<const uint4*>(gp));
-        B = __ldg(reinterpret_cast<const uint4*>(gp + 16));
-    }
-    for (int g = 0; g < ng; ++g) {
-        uint4 An = A, Bn = B;
-        if (g + 1 < ng) {                            // the next group is on its way while this one's multiplicities are gathered
-            An = __ldg(reinterpret_cast<const uint4*>(gp + 32 * (g + 1)));
-            Bn = __ldg(reinterpret_cast<const uint4*>(gp + 32 * (g + 1) + 16));
-        }
-        const uint8_t* w0 = wT + (size_t)(A.x & 0xffffu) * (size_t)w_ld;
-        const uint8_t* w1 = wT + (size_t)(A.x >> 16) * (size_t)w_ld;
-        const uint8_t* w2 = wT + (size_t)(A.y & 0xffffu) * (size_t)w_ld;
-        const uint8_t* w3 = wT + (size_t)(A.y >> 16) * (size_t)w_ld;
-        // (the multiplicity table of these launches is compact: 4 / 8 / 16 bytes per column, so that it stays in L1 -- with the
-        //  streaming kernel's 128-byte rows every entry cost an L2 sector)
+                for (int r = 0; r < 4; ++r) acc[q][k][r] = 0u;
+    };
+    // one group of four entries: gather the multiplicities of its columns, transpose 4 x 4 bytes, six dp4a per replicate
+    auto consume = [&](const uint4 A, const uint4 B) {
+        const uint8_t* wp[4] = {wT + (size_t)(A.x & 0xffffu) * (size_t)w_ld, wT + (size_t)(A.x >> 16) * (size_t)w_ld,
+                                wT + (size_t)(A.y & 0xffffu) * (size_t)w_ld, wT + (size_t)(A.y >> 16) * (size_t)w_ld};
         unsigned x[NQ][4];
-        const uint8_t* wp[4] = {w0, w1, w2, w3};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             if (NQ == 1) {
@@ -658,22 +654,46 @@ boot_sparse_pairlane_kernel(const long long* __restrict__ rowptr, const uint32_t
                 acc[q][5][r] = __dp4a(B.w, y[r], acc[q][5][r]);
             }
         }
-        A = An;
-        B = Bn;
+    };
+    auto store = [&](double* dst) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int rep = 4 * q + r;
+                if (rep >= nb_total) continue;
+                const unsigned long long hi = (unsigned long long)acc[q][2][r] + ((unsigned long long)acc[q][3][r] << 8) +
+                                              ((unsigned long long)acc[q][4][r] << 16) + ((unsigned long long)acc[q][5][r] << 24);
+                const unsigned lo = acc[q][0][r] + (acc[q][1][r] << 8);
+                __stcs(dst + (size_t)rep * ws_rep_stride, bs_to_double(hi, lo, q_hi, quantum));
+            }
+    };
+    // ---- long lists: the whole warp on one pair at a time
+    unsigned longs = __ballot_sync(0xffffffffu, ng > PL_SHORT);
+    while (longs) {
+        const int src = __ffs(longs) - 1;
+        longs &= longs - 1;
+        const uint8_t* gps = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, (unsigned long long)gp, src));
+        const int ngs = __shfl_sync(0xffffffffu, ng, src);
+        clear();
+        for (int g = lane; g < ngs; g += 32)
+            consume(__ldg(reinterpret_cast<const uint4*>(gps + 32 * (size_t)g)), __ldg(reinterpret_cast<const uint4*>(gps + 32 * (size_t)g + 16)));
+        // plane sums of a pair stay below 2^32 whatever the number of partial sums (255 * sum of multiplicities <= 2^24)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[q][k][r] = __reduce_add_sync(0xffffffffu, acc[q][k][r]);
+        if (lane == src) store(o);
     }
-    const double q_hi = quantum * 65536.0;
-    double* o = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + (size_t)(((si << 3) + sj) << 8) + (ii << 4) + jj;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int rep = 4 * q + r;
-            if (rep >= nb_total) continue;
-            const unsigned long long hi = (unsigned long long)acc[q][2][r] + ((unsigned long long)acc[q][3][r] << 8) +
-                                          ((unsigned long long)acc[q][4][r] << 16) + ((unsigned long long)acc[q][5][r] << 24);
-            const unsigned lo = acc[q][0][r] + (acc[q][1][r] << 8);
-            __stcs(o + (size_t)rep * ws_rep_stride, bs_to_double(hi, lo, q_hi, quantum));
-        }
+    // ---- short lists: every lane its own
+    clear();
+    if (ng <= PL_SHORT) {
+        for (int g = 0; g < ng; ++g)
+            consume(__ldg(reinterpret_cast<const uint4*>(gp + 32 * g)), __ldg(reinterpret_cast<const uint4*>(gp + 32 * g + 16)));
+        store(o);
+    }
 }
 
 // ---------------------------------------------------------------------------------- CSR of the fixed-point table
