@@ -257,6 +257,9 @@ def time_reference(args, cfg, n_boot, steps, warm):
         t = synth.make_tables_sparse(n_s, cfg["p"], cfg["g"], cfg["density"], synth.SEED_BASE + 4, with_loc=False)
         _G["arr"] = t.sig
         bounds = np.unique(np.linspace(0, n_s, 4 * cores + 1).astype(int))
+        for _ in range(int(warm)):
+            with mp.get_context("fork").Pool(cores) as pool:
+                pool.map(_ref_popc_rows, [(bounds[k], bounds[k + 1]) for k in range(len(bounds) - 1)], chunksize=1)
         t0 = time.perf_counter()
         for _ in range(steps):
             with mp.get_context("fork").Pool(cores) as pool:
@@ -267,9 +270,8 @@ def time_reference(args, cfg, n_boot, steps, warm):
                                        f"(shared_pphmm_graphs.py:63-76) over a {cores}-process pool; {dt:.1f} s per pass")
     t, n_s, g_s, n_ref_s = reference_sample(args, cfg)
     idx = synth.reference_resample_indices(cfg["p"], n_boot, seed=args.seed, sort=cfg["pl2"])
-    if warm:
-        k = max(8, n_s // 8)
-        reference_job(cores, t.sig[:k], t.loc[:k], t.taxo[:k], t.gom_ids, idx[:1], cfg["scheme"], cfg["pl2"])
+    for _ in range(int(warm)):
+        reference_job(cores, t.sig, t.loc, t.taxo[:n_ref_s], t.gom_ids, idx, cfg["scheme"], cfg["pl2"])
     t0 = time.perf_counter()
     units = 0
     for _ in range(steps):
@@ -282,9 +284,23 @@ def time_reference(args, cfg, n_boot, steps, warm):
 
 
 def run_reference(args, cfg):
-    steps = max(1, min(args.steps or 1, 2))          # each step is a bounded sample; keep the whole run to minutes
-    warm = 1 if (args.warmup is None or args.warmup > 0) else 0
+    """`--impl reference`: EXACTLY K timed steps after W warm-up steps, each one pass of the reference's CPU path over a bounded
+    sample of the workload; the sample's row count is sized from a calibration pass so that the K + W passes end within
+    REF_BUDGET_S seconds whatever the host (the cost of a pass grows with the square of the rows: pairs, and genome x GOM
+    scores at a fixed genomes-per-taxon ratio)."""
+    steps = max(1, args.steps if args.steps is not None else 2)
+    warm = max(0, args.warmup if args.warmup is not None else 1)
+    budget = float(os.environ.get("GV2_REF_BUDGET_S", "280")) / (steps + warm)
+    key = "ref_rows_popc" if args.config == "cfg4" else "ref_rows"
+    full, floor = getattr(args, key), (16 if args.config == "cfg4" else 32)
+    cal_rows = min(full, 48 if args.config != "cfg4" else 24)
+    setattr(args, key, cal_rows)
+    _, cal_dt, _, _ = time_reference(args, cfg, min(cfg["b"], args.ref_boot), 1, 0)
+    rows = int(cal_rows * (max(budget - 0.3, 0.05) / max(cal_dt - 0.3, 0.02)) ** 0.5)      # ~0.3 s of pool start-up per pass
+    rows = max(floor, min(full, min(cfg["n"], rows)))
+    setattr(args, key, rows)
     val, dt, cores, sample = time_reference(args, cfg, min(cfg["b"], args.ref_boot), steps, warm)
+    sample += f"; rows sized for {steps} + {warm} passes in ~{budget * (steps + warm):.0f} s"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -350,7 +366,7 @@ def main():
     ap.add_argument("--density", type=float, default=None, help="override the table density (1.0 = dense worst case)")
     ap.add_argument("--scheme", default=None, choices=["P", "PG", "G"])
     ap.add_argument("--seed", type=int, default=20241019)
-    ap.add_argument("--ref-rows", type=int, default=200)
+    ap.add_argument("--ref-rows", type=int, default=120)
     ap.add_argument("--ref-rows-popc", type=int, default=64)
     ap.add_argument("--ref-boot", type=int, default=1)
     ap.add_argument("--as-shipped-rows", type=int, default=48)
