@@ -60,12 +60,21 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures, keyed by kernel and
-    launch shape (profiles/traffic.json, written by tools/profile_summary.py from the committed captures)."""
+    """Measured DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel group over one step of a config, from
+    the committed ncu launch list of the same bench command (profiles/traffic.json, written by `tools/profile_summary.py
+    traffic`).  .get(key, launches_per_step) gives bytes per launch, like `achieved`."""
     try:
-        return json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+        raw = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
     except Exception:
-        return {}
+        raw = {}
+
+    class _T:
+        def get(self, key, launches_per_step=None):
+            e = raw.get(key)
+            if not e:
+                return None
+            return e["dram_bytes_per_step"] / (launches_per_step or e.get("launches_per_step") or 1.0)
+    return _T()
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -706,7 +715,7 @@ def make_roofline(times, path, cells, gstats, steps, n, p, g, nrep, region_ms, p
                                          "148 SMs x 128 lanes x sm_max_mhz",
                          "also": {"bound": "hbm", "achieved": bytes_step / sec / 1e9, "peak": hbm, "unit": "GB/s",
                                   "frac": bytes_step / sec / 1e9 / hbm},
-                         "traffic": traffic.get(f"gj_fused:{config}:{per_launch}rep"),
+                         "traffic": traffic.get(f"gj_fused:{config}", cnt / steps),
                          "launches_per_step": cnt / steps, "avg_launch_ms": ms / cnt, "share_of_step": ms / region_ms}
     ms, cnt = times["pairs"]
     if cnt:
@@ -721,14 +730,14 @@ def make_roofline(times, path, cells, gstats, steps, n, p, g, nrep, region_ms, p
                               "bound_detail": "ALGORITHMIC flops 2 x pairs x P x replicates against bf16_tflops_sustained",
                               "also": {"bound": "tensor ops issued (4 digit planes per value)", "achieved": 4 * flops / sec / 1e12,
                                        "peak": 2.0 * bf16, "unit": "int8 TOP/s", "frac": 4 * flops / sec / 1e12 / (2.0 * bf16)},
-                              "traffic": traffic.get(f"boot_mma:{config}:{per_launch}rep")}
+                              "traffic": traffic.get(f"boot_mma:{config}", cnt / steps)}
         else:
             bytes_step = 8.0 * pairs * nrep
             lines["pairs"] = {"kernel": f"replicate pair sums, path {path} (pair lists x uint8 multiplicities, exact integer sums -> fp64 workspace)",
                               "bound": "hbm", "achieved": bytes_step / sec / 1e9, "peak": hbm, "unit": "GB/s",
                               "frac": bytes_step / sec / 1e9 / hbm,
                               "bound_detail": "algorithmic bytes = the fp64 pair-sum workspace it writes (8 B x pairs x replicates)",
-                              "traffic": traffic.get(f"boot_sparse:{config}:{per_launch}rep"),
+                              "traffic": traffic.get(f"boot_sparse:{config}", cnt / steps),
                               "copresent_cells": int(cells), "cell_replicates_per_s": cells * nrep / sec if cells else None}
         lines["pairs"].update({"launches_per_step": cnt / steps, "avg_launch_ms": ms / cnt, "share_of_step": ms / region_ms})
     ms, cnt = times["gom"]
@@ -745,7 +754,7 @@ def make_roofline(times, path, cells, gstats, steps, n, p, g, nrep, region_ms, p
                         "also": {"bound": "hbm", "achieved": bytes_step / sec / 1e9, "peak": hbm, "unit": "GB/s",
                                  "frac": bytes_step / sec / 1e9 / hbm},
                         "scores_per_s": float(n) * g * nrep / sec,
-                        "traffic": traffic.get(f"gom:{config}:32rep"),
+                        "traffic": traffic.get(f"gom:{config}", chunks),
                         "launches_per_step": chunks, "avg_launch_ms": ms / cnt, "share_of_step": ms / region_ms}
     ms, cnt = times["base"]
     if cnt:
@@ -1035,7 +1044,7 @@ def run_popcount(args, cfg):
                     "peak_kind": "measured in this run: register-resident LOP3 + POPC + IADD chains, 8 per thread, full grid (gv2_dev_popc_peak)",
                     "also": {"bound": "hbm", "achieved": (4.0 * n * n / world + n_pad * words * 8) / sec / 1e9, "peak": peaks.get("hbm_gbs"),
                              "unit": "GB/s", "frac": (4.0 * n * n / world + n_pad * words * 8) / sec / 1e9 / peaks.get("hbm_gbs", 6550.0)},
-                    "traffic": load_traffic().get("shared_count_tile:cfg4"), "avg_launch_ms": kernel_ms,
+                    "traffic": load_traffic().get("shared_count_tile:cfg4", 1), "avg_launch_ms": kernel_ms,
                     "tiles_per_launch": my_tiles, "share_of_step": kernel_ms / ms_per_step}
         line = {"metric": METRIC, "value": pairs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -1,6 +1,8 @@
 """Turn ncu outputs into the committed summaries under profiles/.
 
   python tools/profile_summary.py launches <ncu --csv launch list> <out.csv> "<command line>"
+  python tools/profile_summary.py traffic <ncu --csv launch list with dram__bytes_read.sum,dram__bytes_write.sum> <steps in the run> <config> <traffic.json>
+                                                                             (DRAM bytes per step of each kernel group -> profiles/traffic.json, read by bench.py)
   python tools/profile_summary.py full <report.ncu-rep | raw.csv> <out.csv>   (one row block per kernel; a .ncu-rep needs ncu on
                                                                              PATH, a `--page raw --csv` export made on the box does not)
 """
@@ -51,6 +53,39 @@ def launches(src, dst, cmd):
             f.write(f"{k[:70]},{v[0]},{v[1]:.3f},{v[1] / tot:.4f}\n")
 
 
+GROUPS = {"gj_fused": ("gj_fused_kernel",), "boot_sparse": ("boot_sparse_", "bs_weights_transpose"), "boot_mma": ("boot_mma",),
+          "gom": ("gom_score", "gom_rowsums", "gom_aggregates", "gom_centroid", "gom_gather", "genome_rowsums", "gom_quantize", "gom_rowmax"),
+          "shared_count_tile": ("shared_count_tile",), "lk_nn_chain": ("lk_nn_chain",)}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def traffic(src, steps, config, dst):
+    import json
+    rows = list(csv.reader(open(src)))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    ci = {h: i for i, h in enumerate(rows[start])}
+    tot = collections.defaultdict(float)
+    cnt = collections.defaultdict(int)
+    for r in rows[start + 1:]:
+        if len(r) < len(ci) or not r[ci["Metric Name"]].startswith("dram__bytes_"):
+            continue
+        k = r[ci["Kernel Name"]].replace("void ", "")
+        v = float(r[ci["Metric Value"]].replace(",", "")) * UNIT.get(r[ci["Metric Unit"]], 1.0)
+        for g, pats in GROUPS.items():
+            if any(k.startswith(pt) for pt in pats):
+                tot[g] += v
+                if r[ci["Metric Name"]] == "dram__bytes_read.sum":
+                    cnt[g] += 1
+    try:
+        out = json.load(open(dst))
+    except Exception:
+        out = {}
+    for g in tot:
+        out[f"{g}:{config}"] = {"dram_bytes_per_step": tot[g] / steps, "launches_per_step": cnt[g] / steps,
+                                "source": f"{src.split('/')[-1]}: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, {steps} step(s)"}
+    json.dump(out, open(dst, "w"), indent=1, sort_keys=True)
+
+
 def full(rep, dst):
     if rep.endswith(".csv"):
         raw = open(rep).read()
@@ -74,5 +109,7 @@ def full(rep, dst):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], int(sys.argv[3]), sys.argv[4], sys.argv[5])
     else:
         full(sys.argv[2], sys.argv[3])
