@@ -212,7 +212,9 @@ int gv2_job_replicates_device(gv2_job* job, const int32_t* dev_weights, int64_t 
  * (UPGMA, the default), "complete", "weighted" and "ward", the minimum spanning tree behind "single"; scipy's tie order;
  * "centroid" / "median" are not built) and printed as DistMat2Tree + GetNewick print it (app/utils/dist_mat_to_tree.py:5-21,
  * app/utils/get_newick.py:1-13); callback(b, newick, length, user) runs on the calling thread in replicate order.
- * The job must have been created with GV2_OUT_DISTANCE.  dev_ring [ring_len][n][n] is scratch. */
+ * The job must have been created with GV2_OUT_DISTANCE.  dev_ring [ring_len][n][n] is scratch: with ring_len >= 8 it is used
+ * as four parts, one being computed while the others are clustered on their own streams (ring_len / 4 CTAs each; the
+ * clustering of a matrix takes ~3x as long as computing it); pick ring_len around half the SM count. */
 typedef int (*gv2_newick_cb)(int64_t replicate, const char* newick, size_t length, void* user);
 int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
                               int64_t ring_len, const char* method, const char* const* leaf_names,
@@ -294,7 +296,10 @@ int gv2_dev_unpack_tiles_i32(gv2_ctx* ctx, int64_t n, int64_t tile_begin, int64_
 int gv2_dev_popc_peak(gv2_ctx* ctx, int iters, double* popc_per_s);
 
 /* ---- every GPU of the node behind one caller (SURVEY.md section 8b "Threading / processes", 8e) ------------------------
- * One process, one host thread + one context per GPU inside the library.  Tables: one upload, then a broadcast over NVLink.
+ * Replaces nothing the reference has -- its only parallelism on this path is multiprocessing.Pool(N_CPUs) inside
+ * GOMSignatureTable_Constructor (app/utils/parallel_gom_sig_generator.py:18-24) around the single-threaded bootstrap loops of
+ * app/src/pl1_graphs.py:74-117 and app/src/virus_classification.py:290-344 -- and keeps that caller single-process:
+ * one process, one host thread + one context per GPU inside the library.  Tables: one upload, then a broadcast over NVLink.
  * Replicates: by index (replicate b on GPU b mod N), no exchange.  Un-resampled matrix: one upper-triangular tile range per
  * GPU, packed blocks all-gathered with NCCL (ncclCommInitAll in this process; libnccl.so.2 is dlopen'ed, and without it the
  * blocks travel by cudaMemcpyPeerAsync).  Callbacks run on the CALLING thread, in replicate order. */
