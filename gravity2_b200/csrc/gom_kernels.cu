@@ -569,6 +569,7 @@ gom_score_light_kernel(long long n, int G, const long long* __restrict__ ptr, co
     __shared__ long long soff[LIGHT_GCHUNK + 1];
     __shared__ int sni[LIGHT_GCHUNK];
     __shared__ int spt[LIGHT_GCHUNK];
+    __shared__ int s_next;
     __shared__ __align__(4) unsigned char sw_all[4][NBC * LIGHT_WSTRIDE];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const long long v = blockIdx.x;
@@ -597,8 +598,15 @@ gom_score_light_kernel(long long n, int G, const long long* __restrict__ ptr, co
                 uint4* dst = reinterpret_cast<uint4*>(srec);
                 for (int i = tid; i < bytes / 16; i += 128) dst[i] = __ldg(src + i);
             }
+            if (tid == 0) s_next = g0;
             __syncthreads();
-            for (int gi = g0 + wib; gi < g1; gi += 4) {
+            // the warps draw the staged pairs from a shared counter: their costs differ (|I|^2), a fixed split left warps
+            // waiting at the barrier below (ncu: 1.7 barrier-stalled warps per issue)
+            while (true) {
+                int gi = 0;
+                if (lane == 0) gi = atomicAdd(&s_next, 1);
+                gi = __shfl_sync(0xffffffffu, gi, 0);
+                if (gi >= g1) break;
                 const int ni = sni[gi];
                 if (ni > VG_LIGHT_CAP) continue;                        // on the heavy kernel's work list
                 const int g = gc0 + gi;
