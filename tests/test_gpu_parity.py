@@ -495,7 +495,8 @@ def test_fused_tail_equals_separate_kernels(eng, scheme, pw, kind):
 
 # ------------------------------------------------------------------------ dendrograms
 @pytest.mark.parametrize("method", ["average", "complete", "weighted", "ward", "single"])
-@pytest.mark.parametrize("n,kind", [(2, "random"), (3, "ties"), (17, "ties"), (130, "random"), (513, "ties"), (1500, "blocks")])
+@pytest.mark.parametrize("n,kind", [(2, "random"), (3, "ties"), (17, "ties"), (130, "random"), (513, "ties"), (1500, "blocks"),
+                                    (1400, "line")])
 def test_device_linkage_equals_scipy(eng, n, kind, method):
     """Device linkage == scipy.cluster.hierarchy.linkage(method) row for row, bit for bit: heights from the same
     separately rounded operations, ties resolved in the order scipy's nn_chain / mst_single_linkage resolve them."""
@@ -505,6 +506,9 @@ def test_device_linkage_equals_scipy(eng, n, kind, method):
         D = rng.random((n, n))
     elif kind == "ties":
         D = rng.integers(1, 6, (n, n)) / 5.0                       # five distinct distances: ties everywhere
+    elif kind == "line":                                           # points on a line with shrinking gaps: every point's nearest
+        pos = np.cumsum(1.0 + (n - np.arange(n)) * 1e-3)           # neighbour is the next one, the chain grows to n elements
+        D = np.abs(pos[:, None] - pos[None, :])                    # (a worst case for the chain's bookkeeping)
     else:                                                          # block structure like a taxon table: many exact 1.0
         grp = rng.integers(0, 12, n)
         D = np.where(grp[:, None] == grp[None, :], np.round(rng.random((n, n)) * 0.6, 3), 1.0)
