@@ -188,12 +188,14 @@ def _ref_rows(args):
     return outp, outg
 
 
-def _ref_gom(g):
+def _ref_gom(task):
+    """generate_gom_sigs of one GOM (parallel_gom_sig_generator.py:10-16) for genome rows [i0, i1)"""
+    g, i0, i1 = task
     from oracle import gravity_oracle as O
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        return O.generate_gom_sigs(_G["db"][g], _G["loc"])
+        return O.generate_gom_sigs(_G["db"][g], _G["loc"][i0:i1])
 
 
 def _ref_popc_rows(args):
@@ -227,8 +229,16 @@ def reference_job(cores, sig, loc, taxo_ref, gom_ids, idx_list, scheme, pl2):
         gom = None
         if "G" in scheme:
             _G.update(loc=loc_t, db=O.gomdb(taxo_ref, loc_t[:n_ref], gom_ids))
+            # The reference's pool works GOM by GOM (parallel_gom_sig_generator.py:18-24): at the workload's G = 200 that keeps
+            # every core busy, in a bounded sample with a handful of GOMs it would not -- so the sample's genome rows are cut
+            # in chunks as well (same calls on the same rows, all cores busy as at full scale).
+            nch = max(1, -(-2 * cores // max(1, len(gom_ids))))
+            rb = np.unique(np.linspace(0, n, nch + 1).astype(int))
+            tasks = [(g, int(rb[k]), int(rb[k + 1])) for g in gom_ids for k in range(len(rb) - 1)]
             with ctxmp.Pool(cores) as pool:
-                cols = pool.map(_ref_gom, list(gom_ids))
+                parts = pool.map(_ref_gom, tasks, chunksize=1)
+            per = len(rb) - 1
+            cols = [np.concatenate([np.asarray(parts[gi * per + k]).reshape(-1) for k in range(per)]) for gi in range(len(gom_ids))]
             gom = np.column_stack(cols) if cols else np.zeros((n, 0))
         _G.update(sig=sig_t, gom=gom)
         bounds = np.unique(np.linspace(0, n, 8 * cores + 1).astype(int))     # balance the triangle: many small row blocks
@@ -288,7 +298,8 @@ def time_reference(args, cfg, n_boot, steps, warm):
     dt = time.perf_counter() - t0
     sample = (f"{n_s} of {cfg['n']} genomes at full P={cfg['p']}, G={g_s} (same genomes-per-taxon ratio as the workload), "
               f"base + {n_boot} of {cfg['b']} replicates ({'PL2' if cfg['pl2'] else 'PL1'} body); numpy pair expressions of "
-              f"similarity_matrix_constructor.py:167-177 + dcor GOM scoring over a {cores}-process pool; {dt / steps:.1f} s per step")
+              f"similarity_matrix_constructor.py:167-177 + dcor GOM scoring (tasks = GOM x genome chunk, so that every core works as at "
+              f"G = {cfg['g']}) over a {cores}-process pool; {dt / steps:.1f} s per step")
     return units / dt, dt / steps, cores, sample
 
 
