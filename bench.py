@@ -28,7 +28,10 @@ One "step" = the whole job.  pairs/s = N(N+1)/2 * (1+B) / time.
           (oracle/sampled_check.py); a mismatch makes the run fail (exit code 3).
   --impl reference : the reference's numpy pair expressions and dcor-based GOM scoring (CPU oracle port of
           app/utils/similarity_matrix_constructor.py:167-177 and parallel_gom_sig_generator.py:30-37) on all host
-          cores, on a bounded row sample that keeps the workload's genomes-per-taxon ratio.
+          cores, on a bounded row sample that keeps the workload's genomes-per-taxon ratio: exactly K timed passes
+          after W warm-up passes, the sample's row count sized by a calibration pass so that the run ends within ~5 min.
+  roofline.traffic : measured DRAM bytes per launch (profiles/traffic.json: ncu dram__bytes_* of the same bench command).
+  N > 1 (torchrun): `value` from one rank per GPU; `e2e` from rank 0 driving all GPUs through gravity2_b200.MultiEngine.
 """
 from __future__ import annotations
 
