@@ -21,8 +21,10 @@ One "step" = the whole job.  pairs/s = N(N+1)/2 * (1+B) / time.
   e2e   : the same job through the public host API with numpy tables in host memory, H2D and D2H inside the timed
           region.  For the bootstrap-loop workloads the product of a replicate is its dendrogram
           (app/src/pl1_graphs.py:108-117 keeps nothing else), so e2e delivers one Newick string per replicate
-          (gravity2_b200.engine.Job.for_each_tree: UPGMA on the device); `e2e_matrices` is the variant that ships every
-          distance matrix to host memory.
+          (gravity2_b200.engine.Job.for_each_tree: UPGMA on the device); for the pipeline II workload (cfg5) the product is the
+          classification epilogue's input -- sampled class cells and query-row maxima of every similarity matrix
+          (Job.for_each_replicate_device: matrices stay in HBM); `e2e_matrices` is the variant that ships every matrix to
+          host memory.
   parity_check : cells of the LAST timed step's device results (base matrix, replicate matrices still in the device
           ring, their GOM tables) against the CPU oracle's single-cell restatement of the reference
           (oracle/sampled_check.py); a mismatch makes the run fail (exit code 3).
@@ -585,6 +587,9 @@ def run_job(args, cfg):
             e2e = measure_e2e_trees(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch)
             if args.e2e_matrices:
                 e2e_mat = measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch, steps=1)
+        elif pl2 and B > 0:
+            e2e = measure_e2e_classification(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch)
+            e2e_mat = measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch, steps=1)
         else:
             e2e = measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch, steps=max(1, min(steps, 2)))
     if rank == 0:
@@ -836,6 +841,66 @@ def measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dist
             "ms_per_step": dt * 1e3,
             "api": "gravity2_b200.engine.Job(sig, loc, ...).base() + .for_each_replicate(weights, consumer): numpy in, "
                    "numpy views of a pinned host ring out (per-rank bytes)"}
+
+
+def measure_e2e_classification(t, cfg, gor, weights, my_reps, pairs, world, rank, dist, torch):
+    """Pipeline II keeps, of every replicate's similarity matrix, the sampled intra / inter class cells behind the cut-offs and
+    the row maxima of the query block (app/src/virus_classification.py:318-344, classification_utils.py:10-68): numpy tables
+    in -> gravity2_b200.engine.Job -> per replicate those cells and maxima out, the matrices never leave HBM
+    (Job.base_device / for_each_replicate_device + DeviceMatrix.gather / rowmax: what bootstrap_classification runs on).
+    The reference's host-side list sampling (np.random.choice, seconds per replicate) and SVC fits are not on this path:
+    ONE cell set is drawn before the timed region and read from every matrix."""
+    from gravity2_b200.engine import Job
+    from gravity2_b200.classification import draw_class_cells, max_similarity
+    n, p, g, B, scheme = cfg["n"], cfg["p"], len(t.gom_ids), cfg["b"], cfg["scheme"]
+    n_ref = cfg["n_ref"]
+    G, eng, w_mine = _engine_and_weights(weights, my_reps, p)
+    taxo_ref = np.asarray(t.taxo[:n_ref])
+    state = np.random.get_state()
+    np.random.seed(7)
+    cells = draw_class_cells(taxo_ref, 10000)                  # payload default N_PairwiseSimilarityScores (api_classes.py:82)
+    np.random.set_state(state)
+    rows = np.concatenate([np.concatenate((c[0], c[2])) for c in cells.values()]).astype(np.int64)
+    cols = np.concatenate([np.concatenate((c[1], c[3])) for c in cells.values()]).astype(np.int64)
+    acc = [0.0, 0]
+
+    def consume(b, S):
+        mx, _ = max_similarity(S, taxo_ref, row_begin=n_ref, n_ref=n_ref)
+        vals = S.gather(rows, cols)
+        acc[0] += float(vals[0]) + float(vals[-1]) + float(mx[0])
+        acc[1] += 1
+
+    def job_once():
+        job = Job(eng, t.sig, t.loc, gor if "G" in scheme else None, g, scheme, 1.0, distance=False)
+        try:
+            if rank == 0:
+                job.base_device(lambda S: consume(-1, S))
+            job.for_each_replicate_device(w_mine, consume)
+        finally:
+            job.close()
+
+    job_once()          # warm-up
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    acc[1] = 0
+    t0 = time.perf_counter()
+    job_once()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    assert acc[1] == len(my_reps) + (1 if rank == 0 else 0), "consumer did not see every matrix"
+    per_matrix = len(rows) * 8 + (n - n_ref) * 16
+    return {"value": pairs * (1 + B) / dt, "unit": UNIT, "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(2 * n * p * 8 + w_mine.nbytes + gor.nbytes + (len(my_reps) + 1) * len(rows) * 16),
+            "d2h_bytes_per_step": int((len(my_reps) + 1) * per_matrix),
+            "result": f"per matrix {len(rows)} sampled class cells + the {n - n_ref} row maxima / argmaxima of the query block "
+                      "(what virus_classification.py:318-344 reads of it)",
+            "api": "gravity2_b200.engine.Job(sig, loc, ...).base_device + .for_each_replicate_device(weights, consumer) with "
+                   "DeviceMatrix.gather / max_similarity: numpy in, cells and maxima out, matrices stay in HBM (per-rank bytes)"}
 
 
 def measure_e2e_trees(t, cfg, gor, weights, my_reps, pairs, world, rank, dist, torch):
