@@ -573,7 +573,7 @@ def run_job(args, cfg):
     job = None
     del d_out, d_base, d_sig, d_loc
     torch.cuda.empty_cache()
-    e2e = e2e_mat = None
+    e2e = e2e_mat = e2e_cond = None
     dd = dist if world > 1 else None
     if not args.no_e2e and world > 1:
         # N GPUs through the public API = ONE caller process driving all of them (gravity2_b200.MultiEngine: one host thread
@@ -587,6 +587,7 @@ def run_job(args, cfg):
             e2e = measure_e2e_trees(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch)
             if args.e2e_matrices:
                 e2e_mat = measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch, steps=1)
+                e2e_cond = measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch, steps=1, condensed=True)
         elif pl2 and B > 0:
             e2e = measure_e2e_classification(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch)
             e2e_mat = measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dd, torch, steps=1)
@@ -605,6 +606,8 @@ def run_job(args, cfg):
                 "base_only_ms": base_ms}
         if e2e_mat:
             line["e2e_matrices"] = e2e_mat
+        if e2e_cond:
+            line["e2e_condensed"] = e2e_cond
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -797,7 +800,7 @@ def _engine_and_weights(weights, my_reps, p):
     return gravity2_b200, eng, w_mine
 
 
-def measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dist, torch, steps):
+def measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dist, torch, steps, condensed=False):
     """Whole job through the package's public host API: numpy tables in host memory -> gravity2_b200.engine.Job (one
     H2D upload of the tables per step) -> base matrix as a numpy array -> every replicate matrix delivered in host
     memory (pinned ring, zero-copy view) to a consumer that reads it.  H2D and D2H inside the timed region."""
@@ -807,7 +810,7 @@ def measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dist
     acc = [0.0, 0]
 
     def consume(b, m):              # the device->host read of the step's result: touch every delivered matrix
-        acc[0] += float(m[0, -1]) + float(m[-1, 0]) + float(m[n // 2, n // 3])
+        acc[0] += (float(m[0]) + float(m[-1]) + float(m[len(m) // 2])) if m.ndim == 1 else (float(m[0, -1]) + float(m[-1, 0]) + float(m[n // 2, n // 3]))
         acc[1] += 1
 
     def job_once():
@@ -815,7 +818,7 @@ def measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dist
         try:
             if rank == 0:
                 consume(-1, job.base())
-            job.for_each_replicate(w_mine, consume)
+            job.for_each_replicate(w_mine, consume, condensed=condensed)
         finally:
             job.close()
 
@@ -835,12 +838,14 @@ def measure_e2e_matrices(t, cfg, gor, weights, my_reps, pairs, world, rank, dist
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
     h2d = n * p * 8 * (2 if pl2 and "G" in scheme else 1) + w_mine.nbytes + gor.nbytes
-    d2h = ((1 if rank == 0 else 0) + len(my_reps)) * n * n * 8
+    d2h = (1 if rank == 0 else 0) * n * n * 8 + len(my_reps) * (n * (n - 1) // 2 if condensed else n * n) * 8
     eng.close()
     return {"value": pairs * (1 + B) / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": dt * 1e3,
-            "api": "gravity2_b200.engine.Job(sig, loc, ...).base() + .for_each_replicate(weights, consumer): numpy in, "
-                   "numpy views of a pinned host ring out (per-rank bytes)"}
+            "format": "condensed upper triangle (scipy squareform order: what dist_mat_to_tree.py:8-9 feeds linkage)" if condensed
+                      else "full (N, N) matrices",
+            "api": "gravity2_b200.engine.Job(sig, loc, ...).base() + .for_each_replicate(weights, consumer"
+                   + (", condensed=True" if condensed else "") + "): numpy in, numpy views of a pinned host ring out (per-rank bytes)"}
 
 
 def measure_e2e_classification(t, cfg, gor, weights, my_reps, pairs, world, rank, dist, torch):

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gv2_job_base": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp]),
     "gv2_job_replicates": (C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     "gv2_job_replicates_stream": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "gv2_job_replicates_condensed": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "gv2_job_replicates_device": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "gv2_dev_alloc": (C.c_int, [c_vp, C.c_size_t, C.POINTER(c_vp)]),
     "gv2_dev_free": (C.c_int, [c_vp, c_vp]),

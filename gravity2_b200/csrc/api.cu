@@ -265,6 +265,7 @@ struct gv2_job {
     // workspaces, grown on demand
     DevBuf wsP, wsG, gomtab, gomf, gom_rowsum, gom_nan, gom_qmax, wf, w_rowsum, wbf16, mma_flag;
     DevBuf ones_w, sig_rowsum_fix;     // all-ones multiplicities and fixed-point row sums: the base matrix through the sparse path
+    DevBuf cond[2];                    // condensed (upper-triangle) images of the two ring halves, for host delivery in that format
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_ready[GV2_RING_PARTS] = {}, ev_drained[GV2_RING_PARTS] = {};
     cudaStream_t lk_stream[GV2_RING_PARTS] = {};         // device UPGMA of the ring's parts, concurrent with the main stream
@@ -738,8 +739,19 @@ struct TreeSink {
     }
 };
 
+// scipy's condensed form of a symmetric matrix (squareform order: row i contributes D[i][i+1 .. n-1]), what
+// dist_mat_to_tree.py:8-9 hands to linkage(): half the bytes of the square matrix on the way to the host.
+// grid = (n - 1 rows, matrices)
+__global__ void condense_kernel(const double* __restrict__ ring, long long n, double* __restrict__ out) {
+    const long long i = blockIdx.x, m = n * (n - 1) / 2;
+    const double* src = ring + (size_t)blockIdx.y * n * n + i * n + i + 1;
+    double* dst = out + (size_t)blockIdx.y * m + i * n - i * (i + 1) / 2;
+    for (long long j = threadIdx.x; j < n - 1 - i; j += blockDim.x) dst[j] = src[j];
+}
+
 static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring, int64_t ring_len,
-                           double* host_out, gv2_replicate_cb cb_fn, void* cb_user, TreeSink* sink, gv2_replicate_cb dev_cb = nullptr) {
+                           double* host_out, gv2_replicate_cb cb_fn, void* cb_user, TreeSink* sink, gv2_replicate_cb dev_cb = nullptr,
+                           bool condensed = false) {
     if (!job || !dev_weights || !dev_ring || nb < 0 || ring_len <= 0 || (cb_fn && !host_out))
         return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_stream: bad arguments");
     // host delivery ping-pongs two halves of the ring (one computing, one draining): a single slot cannot do that
@@ -763,6 +775,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
     }
     const int64_t n = job->n, p = job->p, g = job->g, ntl = job->ntiles;
     const size_t tile_elems = (size_t)GV2_TILE * GV2_TILE;
+    const int64_t hstride = condensed ? n * (n - 1) / 2 : n * n;      // doubles per delivered replicate
     ring_len = std::min(ring_len, nb);
     // sub-chunk: half the ring when results stream to the host (ping-pong), else the whole ring.  Dendrogram mode: the ring is
     // cut in (up to) four parts, each clustered on its own stream while the main stream computes into the free one -- the
@@ -812,7 +825,7 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
         cudaError_t e = cudaEventSynchronize(job->ev_drained[h]);
         if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "replicate copy: %s", cudaGetErrorString(e));
         for (int64_t k = 0; k < pend_cb[h]; ++k)
-            if (cb_fn(pend_b0[h] + k, host_out + (pend_slot[h] + k) * n * n, cb_user) != 0)
+            if (cb_fn(pend_b0[h] + k, host_out + (pend_slot[h] + k) * hstride, cb_user) != 0)
                 return gv2_fail(ctx, GV2_ERR_ARG, "replicate callback asked to stop at replicate %lld", (long long)(pend_b0[h] + k));
         drained_pending[h] = false;
         return GV2_OK;
@@ -918,11 +931,18 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
                 if ((rc = sink->drain(sink->cur))) return rc;
             }
             if (host_out) {
+                const double* dsrc = dev_ring + slot * n * n;
+                if (condensed && n > 1) {            // upper triangles of the sub-chunk, packed (the half's own staging buffer)
+                    if ((rc = ensure(ctx, job->cond[half], (size_t)sub * hstride * sizeof(double)))) return rc;
+                    condense_kernel<<<dim3((unsigned)(n - 1), (unsigned)cb), 256, 0, ctx->stream>>>(dsrc, n, job->cond[half].as<double>());
+                    GV2_LAUNCH_CHECK(ctx);
+                    dsrc = job->cond[half].as<double>();
+                }
                 GV2_CUDA(ctx, cudaEventRecord(job->ev_ready[half], ctx->stream));
                 GV2_CUDA(ctx, cudaStreamWaitEvent(job->copy_stream, job->ev_ready[half], 0));
-                double* hdst = cb_fn ? host_out + slot * n * n : host_out + (s0 + c0) * n * n;   // host ring vs linear output
-                GV2_CUDA(ctx, cudaMemcpyAsync(hdst, dev_ring + slot * n * n, (size_t)cb * n * n * sizeof(double),
-                                              cudaMemcpyDeviceToHost, job->copy_stream));
+                double* hdst = cb_fn ? host_out + slot * hstride : host_out + (s0 + c0) * hstride;   // host ring vs linear output
+                if (hstride > 0)
+                    GV2_CUDA(ctx, cudaMemcpyAsync(hdst, dsrc, (size_t)cb * hstride * sizeof(double), cudaMemcpyDeviceToHost, job->copy_stream));
                 GV2_CUDA(ctx, cudaEventRecord(job->ev_drained[half], job->copy_stream));
                 drained_pending[half] = true;
                 pend_b0[half] = s0 + c0; pend_cb[half] = cb; pend_slot[half] = slot;
@@ -948,6 +968,14 @@ static int replicates_impl(gv2_job* job, const int32_t* dev_weights, int64_t nb,
 extern "C" int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
                                          int64_t ring_len, double* host_out, gv2_replicate_cb cb_fn, void* cb_user) {
     return replicates_impl(job, dev_weights, nb, dev_ring, ring_len, host_out, cb_fn, cb_user, nullptr);
+}
+
+// Same, with every replicate delivered in scipy's condensed form (n (n - 1) / 2 doubles, squareform order): host_out is
+// [nb][n(n-1)/2] (no callback) or a host ring [ring_len][n(n-1)/2] (callback).  Half the device-to-host bytes.
+extern "C" int gv2_job_replicates_condensed(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
+                                            int64_t ring_len, double* host_out, gv2_replicate_cb cb_fn, void* cb_user) {
+    if (!host_out) return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_condensed: host_out is NULL");
+    return replicates_impl(job, dev_weights, nb, dev_ring, ring_len, host_out, cb_fn, cb_user, nullptr, nullptr, true);
 }
 
 // The bootstrap loops keep only the dendrogram of a replicate (app/src/pl1_graphs.py:108-117): replicate distance

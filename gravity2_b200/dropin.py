@@ -450,8 +450,10 @@ def gom_membership(TaxoGroupingList, GOMIDList, n_rows: Optional[int] = None):
 def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, GOMIDList, payload,
                                 N_Bootstrap: Optional[int] = None, pipeline: str = "pl1", indices=None,
                                 batch: int = 256, distance: bool = True,
-                                engine: Optional[Engine] = None) -> Iterator[np.ndarray]:
+                                engine: Optional[Engine] = None, condensed: bool = False) -> Iterator[np.ndarray]:
     """Yields one (N, N) float64 matrix per bootstrap replicate, in the reference's order.
+    condensed=True (one GPU): yields scipy's condensed form instead -- the N (N - 1) / 2 entries above the diagonal, what
+    dist_mat_to_tree.py:8-9 computes before linkage() -- so half the bytes cross PCIe.
 
     pipeline="pl1": app/src/pl1_graphs.py:78-107 -- unsorted indices, and the bootstrapped SIGNATURE
     table doubles as the location table; yields D.
@@ -470,6 +472,9 @@ def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGro
     loc = sig if pipeline == "pl1" else _as_table(PPHMMLocationTable)
     gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
     job = _make_job(engine, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), distance)
+    if condensed and not hasattr(job, "ntiles"):
+        job.close()
+        raise NotImplementedError("condensed delivery is built for the single-GPU engine")
     try:
         # tables are uploaded once; replicates go through in batches big enough to fill the tensor-core
         # blocks (128 replicates per CTA) and the 32-replicate lanes of the GOM kernels
@@ -480,7 +485,7 @@ def bootstrap_distance_matrices(PPHMMSignatureTable, PPHMMLocationTable, TaxoGro
             else:
                 idx = indices[b0:b0 + cb]
             w = np.stack([weights_from_indices(i, p) for i in idx])
-            for m in job.replicates(w):
+            for m in (job.replicates(w, condensed=True) if condensed else job.replicates(w)):
                 yield m
     finally:
         job.close()

@@ -322,8 +322,10 @@ class Job:
             self.lib.gv2_dev_free(self.ctx, d_out)
         return out if weights is not None else out[0]
 
-    def for_each_replicate(self, weights, fn) -> None:
-        """fn(b, matrix) for every replicate in order; matrix is a zero-copy view into the pinned ring."""
+    def for_each_replicate(self, weights, fn, condensed: bool = False) -> None:
+        """fn(b, matrix) for every replicate in order; matrix is a zero-copy view into the pinned ring.
+        condensed=True: fn receives scipy's condensed form instead (1-D, n (n - 1) / 2 entries, squareform order -- what
+        dist_mat_to_tree.py:8-9 hands to linkage()): half the bytes cross PCIe."""
         w = np.ascontiguousarray(weights, dtype=np.int32)
         if w.ndim == 1:
             w = w[None, :]
@@ -339,20 +341,26 @@ class Job:
         _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, w.nbytes, C.byref(d_w)))
         err = []
 
+        m = n * (n - 1) // 2
+
         def _cb(b, ptr, _user):
             try:
-                buf = (C.c_double * (n * n)).from_address(ptr)
-                fn(int(b), np.frombuffer(buf, dtype=np.float64).reshape(n, n))
+                if condensed:
+                    vec = np.frombuffer((C.c_double * m).from_address(ptr), dtype=np.float64) if m else np.zeros(0)
+                    fn(int(b), vec)
+                else:
+                    buf = (C.c_double * (n * n)).from_address(ptr)
+                    fn(int(b), np.frombuffer(buf, dtype=np.float64).reshape(n, n))
                 return 0
             except BaseException as e:      # never let an exception cross the C frame
                 err.append(e)
                 return 1
 
         cb = _lib.REPLICATE_CB(_cb)
+        entry = self.lib.gv2_job_replicates_condensed if condensed else self.lib.gv2_job_replicates_stream
         try:
             _lib.check(self.ctx, self.lib.gv2_memcpy_h2d(self.ctx, d_w, _ptr(w), w.nbytes))
-            rc = self.lib.gv2_job_replicates_stream(self.job, d_w, nb, dev_ring, ring_len, host_ring,
-                                                    C.cast(cb, C.c_void_p), None)
+            rc = entry(self.job, d_w, nb, dev_ring, ring_len, host_ring, C.cast(cb, C.c_void_p), None)
             if err:
                 raise err[0]
             _lib.check(self.ctx, rc)
@@ -463,7 +471,7 @@ class Job:
                 self.lib.gv2_dev_free(self.ctx, d_w)
             self.lib.gv2_dev_free(self.ctx, dev_ring)
 
-    def replicates(self, weights) -> Iterator[np.ndarray]:
+    def replicates(self, weights, condensed: bool = False) -> Iterator[np.ndarray]:
         """Generator form of for_each_replicate: the native call runs on a worker thread and hands each
         matrix over without copying; the GPU keeps computing ahead while the consumer holds a matrix."""
         import queue
@@ -481,7 +489,7 @@ class Job:
 
         def run():
             try:
-                self.for_each_replicate(weights, hand_over)
+                self.for_each_replicate(weights, hand_over, condensed=condensed)
                 q.put(None)
             except StopIteration:
                 q.put(None)

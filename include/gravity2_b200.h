@@ -202,6 +202,11 @@ int gv2_job_replicates(gv2_job* job, const int32_t* dev_weights, int64_t nb, dou
  * computes the next sub-chunk; the matrix is valid until the callback returns; non-zero return stops. */
 int gv2_job_replicates_stream(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
                               int64_t ring_len, double* host_out, gv2_replicate_cb callback, void* user);
+/* The same with every replicate delivered in scipy's condensed form -- the n (n - 1) / 2 entries above the diagonal in
+ * squareform order, what app/utils/dist_mat_to_tree.py:8-9 hands to linkage() -- so half the bytes cross PCIe: host_out is
+ * [nb][n(n-1)/2] (callback == NULL) or a host ring [ring_len][n(n-1)/2]; the callback receives the condensed vector. */
+int gv2_job_replicates_condensed(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
+                                 int64_t ring_len, double* host_out, gv2_replicate_cb callback, void* user);
 /* Device consumer (classification epilogue of pipeline II): callback(b, matrix, user) receives
  * the DEVICE pointer of replicate b's matrix in the ring, on the calling thread, in replicate order, after the stream has
  * been synchronised; valid until the callback returns (gv2_dev_rowmax_block / gv2_dev_gather_cells read it in place). */

@@ -337,6 +337,41 @@ def test_streaming_job_matches_batch_and_oracle(eng):
     close(base, ref0, rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("n,nb", [(140, 23), (2, 3), (1, 2)])
+def test_condensed_delivery_equals_squareform(eng, n, nb):
+    """Replicates delivered in scipy's condensed form (half the D2H bytes) == squareform of the full matrices, callback
+    hand-over and generator, through several ring wraps; the drop-in generator's condensed option; then the reference's own
+    tree code on the condensed vector."""
+    import gravity2_b200 as G
+    from gravity2_b200.engine import Job
+    from scipy.spatial.distance import squareform
+    t = synth.make_tables(n, 600, max(1, min(4, n)), 0.08, seed=5 + n)
+    rng = np.random.default_rng(n)
+    w = np.stack([np.bincount(rng.integers(0, 600, 600), minlength=600) for _ in range(nb)]).astype(np.int32)
+    gor = G.gom_membership(t.taxo, t.gom_ids)
+    job = Job(eng, t.sig, t.sig, gor, len(t.gom_ids), "PG", 1.0, distance=True, ring_bytes=5 * n * n * 8)
+    full, cond = {}, {}
+    job.for_each_replicate(w, lambda b, m: full.__setitem__(b, m.copy()))
+    job.for_each_replicate(w, lambda b, v: cond.__setitem__(b, v.copy()), condensed=True)
+    gen = [v.copy() for v in job.replicates(w[:4], condensed=True)]
+    job.close()
+    assert sorted(cond) == list(range(nb))
+    for b in range(nb):
+        assert cond[b].shape == (n * (n - 1) // 2,)
+        assert np.array_equal(cond[b], squareform(full[b], checks=False) if n > 1 else np.zeros(0))
+    for b in range(min(4, nb)):
+        assert np.array_equal(gen[b], cond[b])
+    if n > 2:
+        from scipy.cluster.hierarchy import linkage
+        assert np.array_equal(linkage(cond[0], method="average"), eng.linkage(full[0], "average"))
+        payload = {"N_Bootstrap": 3, "SimilarityMeasurementScheme": "PG", "p": 1.0}
+        np.random.seed(4)
+        a = [m.copy() for m in G.bootstrap_distance_matrices(t.sig, None, t.taxo, t.gom_ids, payload, pipeline="pl1")]
+        np.random.seed(4)
+        c = [v.copy() for v in G.bootstrap_distance_matrices(t.sig, None, t.taxo, t.gom_ids, payload, pipeline="pl1", condensed=True)]
+        assert all(np.array_equal(squareform(x, checks=False), y) for x, y in zip(a, c))
+
+
 def test_tensor_core_path_is_exact_integer_arithmetic(eng):
     """scheme P replicates through tcgen05 (>= 8 replicates): error is the 2^-33 input quantisation only"""
     t = synth.make_tables(200, 1500, 5, 0.3, seed=41)
