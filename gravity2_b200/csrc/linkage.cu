@@ -96,7 +96,16 @@ __device__ __forceinline__ LkKey lk_warp_min(LkKey k) {
 // trees of 10 000 leaves with a two-part ring, 4.70 s against 4.42 s with the four-part ring.)
 // A thread owns the same row positions i = tid + e THREADS in every row, so which of them are live clusters is a register
 // bit mask (bit e): dead positions are neither loaded nor compared, and no shared-memory lookup sits in the scan.
-template <int METHOD, int THREADS>
+// LAZY: a merge does not write the new cluster's COLUMN (n scattered 8-byte stores, one 32-byte sector each: half of the
+// kernel's DRAM operations and most of a merge's time in the load/store unit).  The matrix is symmetric and a new cluster's
+// ROW is complete when it is written, so an entry (x, j) of an older row is simply read from the other side, D[j][x], when it
+// is next needed: per cluster born[j] (merges done when row j was written) and fresh[x] (merges done when row x was last
+// brought up to date); entry (x, j) is stale iff born[j] > fresh[x].  A scan of row x loads every element from whichever
+// side is current -- one load per element either way, the address is chosen from shared-memory state before any load is
+// issued, so a step is still one round trip -- writes the patched values back into row x and sets fresh[x]; a merge does
+// the same for the two rows it reads.  Same values, same operations, same order: the linkage matrix stays bit-identical.
+// Dynamic shared memory: 2 n ints (cluster sizes, the chain) [+ 2 n ints (born, fresh)].
+template <int METHOD, int THREADS, bool LAZY>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
     extern __shared__ int lk_size[];
@@ -105,9 +114,14 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
     __shared__ double s_min, s_dp;
     double* D = Dall + (size_t)blockIdx.x * d_stride;
     int* chain = lk_size + n;
+    int* born = chain + n;                            // LAZY only
+    int* fresh = born + n;                            // LAZY only
     double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < n; i += THREADS) lk_size[i] = 1;
+    for (int i = tid; i < n; i += THREADS) {
+        lk_size[i] = 1;
+        if (LAZY) { born[i] = 0; fresh[i] = 0; }
+    }
     unsigned alive = 0u;                              // n <= 32 THREADS (the shared-memory limit of the launcher is lower)
     for (int e = 0; e < 32; ++e)
         if (tid + e * THREADS < n) alive |= 1u << e;
@@ -127,7 +141,8 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
             const int len = s_len;
             const int x = chain[len - 1];
             const int prev = len > 1 ? chain[len - 2] : -1;
-            const double* row = D + (size_t)x * n;
+            double* row = D + (size_t)x * n;
+            const int fx = LAZY ? fresh[x] : 0;
             double bd = INFINITY;
             int bi = 0x7fffffff;
             // The step is one DRAM round trip long, not one per element: a thread's loads of the row are all issued before the
@@ -135,12 +150,20 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
             for (int e0 = 0, i0 = tid; i0 < n; e0 += LK_MLP, i0 += THREADS * LK_MLP) {
                 double dv[LK_MLP];
                 const unsigned live = alive >> e0;
+                unsigned stale = 0u;
 #pragma unroll
-                for (int u = 0; u < LK_MLP; ++u) dv[u] = (live >> u) & 1u ? __ldcs(row + i0 + u * THREADS) : INFINITY;
+                for (int u = 0; u < LK_MLP; ++u) {
+                    const int i = i0 + u * THREADS;
+                    const bool on = (live >> u) & 1u;
+                    const bool st = LAZY && on && born[i] > fx;          // row i is younger than row x's last refresh
+                    if (st) stale |= 1u << u;
+                    dv[u] = on ? (st ? D[(size_t)i * n + x] : __ldcs(row + i)) : INFINITY;
+                }
 #pragma unroll
                 for (int u = 0; u < LK_MLP; ++u) {
                     const int i = i0 + u * THREADS;
                     if (!((live >> u) & 1u) || i == x) continue;
+                    if (LAZY && ((stale >> u) & 1u)) row[i] = dv[u];     // row x is current again
                     if (i == prev) s_dp = dv[u];                     // the incumbent's distance, for the final comparison
                     if (dv[u] < bd) { bd = dv[u]; bi = i; }          // ascending i per thread: first minimum kept
                 }
@@ -171,6 +194,7 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
                         s_len = len + 1;
                     }
                     s_x = x; s_y = y; s_min = cur;
+                    if (LAZY) fresh[x] = k;           // k merges so far: every younger row has been read from its own side
                 }
             }
             __syncthreads();
@@ -181,6 +205,7 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
         if (x > y) { const int t = x; x = y; y = t; }
         const int nx = lk_size[x], ny = lk_size[y];
         const double dmin = s_min;
+        const int fx = LAZY ? fresh[x] : 0, fy = LAZY ? fresh[y] : 0;
         if ((x & (THREADS - 1)) == tid) alive &= ~(1u << (x / THREADS));   // x dies; its owner drops it
         __syncthreads();                              // everyone has read the sizes and s_* before they change
         if (tid == 0) {
@@ -202,9 +227,10 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
             for (int u = 0; u < LK_MLP; ++u) {
                 const int i = i0 + u * THREADS;
                 const bool on = ((live >> u) & 1u) && i != y;
-                ax[u] = on ? rx[i] : 0.0;
-                ay[u] = on ? ry[i] : 0.0;
-                sz[u] = on ? lk_size[i] : 0;         // (i != x, y: not the two entries thread 0 is changing)
+                const int bi2 = (LAZY && on) ? born[i] : 0;  // (i != x, y: not entries thread 0 is changing)
+                ax[u] = on ? (bi2 > fx ? D[(size_t)i * n + x] : rx[i]) : 0.0;
+                ay[u] = on ? (bi2 > fy ? D[(size_t)i * n + y] : ry[i]) : 0.0;
+                sz[u] = on ? lk_size[i] : 0;
             }
 #pragma unroll
             for (int u = 0; u < LK_MLP; ++u) {
@@ -212,9 +238,10 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
                 if (sz[u] == 0) continue;
                 const double v = lk_new_dist<METHOD>(ax[u], ay[u], dmin, nx, ny, sz[u]);
                 ry[i] = v;
-                D[(size_t)i * n + y] = v;
+                if (!LAZY) D[(size_t)i * n + y] = v;
             }
         }
+        if (LAZY && tid == 0) { born[y] = k + 1; fresh[y] = k + 1; }   // (read by others only after the barrier below)
         __syncthreads();
     }
 }
@@ -377,43 +404,51 @@ int lk_method(const char* method) {
 size_t lk_smem_bytes(int64_t n, int method) {
     return method == LK_SINGLE ? (size_t)((n + 1) & ~1) * sizeof(int) + (size_t)n * sizeof(double) : (size_t)n * 2 * sizeof(int);
 }
+#define LK_SMEM_MAX (220 * 1024)
 
-// dev_D [nb][n][n] (stride d_stride elements) is clustered in place (destroyed); dev_Zraw [nb][n-1][4] receives the
+template <int METHOD>
+static cudaError_t lk_launch_chain(gv2_ctx* ctx, bool lazy, size_t smem, unsigned g, double* dev_D, int64_t d_stride, int64_t n,
+                                   double* dev_Zraw) {
+    const int sz = (int)std::max<size_t>(smem, 1024);
+    cudaError_t e = lazy ? cudaFuncSetAttribute(lk_nn_chain_kernel<METHOD, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz)
+                         : cudaFuncSetAttribute(lk_nn_chain_kernel<METHOD, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+    if (e != cudaSuccess) return e;
+    if (lazy) lk_nn_chain_kernel<METHOD, 1024, true><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+    else lk_nn_chain_kernel<METHOD, 1024, false><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+    return cudaGetLastError();
+}
+
+// dev_D [nb][n][n] (stride d_stride elements; symmetric) is clustered in place (destroyed); dev_Zraw [nb][n-1][4] receives the
 // merge-ordered rows.  Enqueued on the context's stream.
 int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw) {
     if (n <= 1 || nb <= 0) return GV2_OK;
     if (method < 0 || method > LK_SINGLE) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage: methods average, complete, weighted, ward, single");
-    const size_t smem = lk_smem_bytes(n, method);
-    if (smem > 200 * 1024)
+    // lazy column updates need 16 bytes of shared memory per leaf (n <= 14 080); larger trees write the columns
+    const char* env = getenv("GV2_LK_LAZY");
+    const bool lazy = method != LK_SINGLE && (size_t)n * 16 <= LK_SMEM_MAX && !(env && atoi(env) == 0);
+    const size_t smem = lazy ? (size_t)n * 16 : lk_smem_bytes(n, method);
+    if (smem > LK_SMEM_MAX)
         return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage keeps its per-cluster state in shared memory: n = %lld needs %zu bytes", (long long)n, smem);
-    size_t* attr = ctx->lk_smem_attr;
-    if (smem > attr[method]) {
-        const int sz = (int)std::max<size_t>(smem, 1024);
-        cudaError_t e = cudaSuccess;
-        switch (method) {
-            case LK_AVERAGE:
-                e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_AVERAGE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
-                break;
-            case LK_COMPLETE: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_COMPLETE, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
-            case LK_WEIGHTED: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WEIGHTED, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
-            case LK_WARD: e = cudaFuncSetAttribute(lk_nn_chain_kernel<LK_WARD, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
-            default: e = cudaFuncSetAttribute(lk_mst_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sz); break;
-        }
-        GV2_CUDA(ctx, e);
-        attr[method] = smem;
-    }
     Gv2Timer timer(ctx, GV2_TIME_LINKAGE);
     timer.begin();
     const unsigned g = (unsigned)nb;
+    cudaError_t e = cudaSuccess;
     switch (method) {
-        case LK_AVERAGE: lk_nn_chain_kernel<LK_AVERAGE, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
-        case LK_COMPLETE: lk_nn_chain_kernel<LK_COMPLETE, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
-        case LK_WEIGHTED: lk_nn_chain_kernel<LK_WEIGHTED, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
-        case LK_WARD: lk_nn_chain_kernel<LK_WARD, 1024><<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
-        default: lk_mst_single_kernel<<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw); break;
+        case LK_AVERAGE: e = lk_launch_chain<LK_AVERAGE>(ctx, lazy, smem, g, dev_D, d_stride, n, dev_Zraw); break;
+        case LK_COMPLETE: e = lk_launch_chain<LK_COMPLETE>(ctx, lazy, smem, g, dev_D, d_stride, n, dev_Zraw); break;
+        case LK_WEIGHTED: e = lk_launch_chain<LK_WEIGHTED>(ctx, lazy, smem, g, dev_D, d_stride, n, dev_Zraw); break;
+        case LK_WARD: e = lk_launch_chain<LK_WARD>(ctx, lazy, smem, g, dev_D, d_stride, n, dev_Zraw); break;
+        default:
+            e = cudaFuncSetAttribute(lk_mst_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+            if (e == cudaSuccess) {
+                lk_mst_single_kernel<<<g, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+                e = cudaGetLastError();
+            }
+            break;
     }
-    GV2_LAUNCH_CHECK(ctx);
+    ctx->launches++;
     timer.end();
+    GV2_CUDA(ctx, e);
     return GV2_OK;
 }
 
