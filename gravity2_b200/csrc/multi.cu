@@ -311,7 +311,7 @@ extern "C" int gv2_multi_job_replicates_newick(gv2_multi_job* mj, const int32_t*
         double* ring = nullptr;
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
-        int64_t rl = ring_len > 0 ? ring_len : std::min<int64_t>(84, (int64_t)(0.62 * (double)free_b / std::max<double>(1.0, (double)n * n * 8)));
+        int64_t rl = ring_len > 0 ? ring_len : std::min<int64_t>(128, (int64_t)(0.62 * (double)free_b / std::max<double>(1.0, (double)n * n * 8)));
         rl = std::max<int64_t>(1, std::min<int64_t>(rl, mine));
         NewickSlot slot{&col, N, i};
         int rc = GV2_OK;

@@ -438,13 +438,14 @@ class Job:
             raise IndexError("fewer leaf names than genomes")
         arr = (C.c_char_p * len(names))(*names)
         mat = max(1, n * n * 8)
+        cap = 128
         if ring_bytes is None:
             free_b, total_b = C.c_size_t(0), C.c_size_t(0)
             _lib.check(self.ctx, self.lib.gv2_mem_info(self.ctx, C.byref(free_b), C.byref(total_b)))
             ring_bytes = int(0.62 * free_b.value)
-        # 84 matrices = four ring parts of 21: three clusterings (63 CTAs) in flight beside the similarity kernels; measured at
-        # 10 000 leaves: 64 -> 4.53 s, 84 -> 4.28 s, 104 -> 4.55 s, 126 -> 4.43 s per 1001 trees
-        ring_len = max(1, min(nb, 84, int(ring_bytes // mat)))
+        # four ring parts, three clusterings in flight beside the similarity kernels; measured at 10 000 leaves (lazy column
+        # updates): 48 matrices -> 4.70 s, 64 -> 4.01 s, 84 -> 3.45 s, 104 -> 3.42 s, 126 -> 3.20 s per 1001 trees
+        ring_len = max(1, min(nb, cap, int(ring_bytes // mat)))
         dev_ring, d_w = C.c_void_p(), C.c_void_p()
         _lib.check(self.ctx, self.lib.gv2_dev_alloc(self.ctx, ring_len * mat, C.byref(dev_ring)))
         err = []

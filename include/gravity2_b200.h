@@ -219,7 +219,7 @@ int gv2_job_replicates_device(gv2_job* job, const int32_t* dev_weights, int64_t 
  * app/utils/get_newick.py:1-13); callback(b, newick, length, user) runs on the calling thread in replicate order.
  * The job must have been created with GV2_OUT_DISTANCE.  dev_ring [ring_len][n][n] is scratch: with ring_len >= 8 it is used
  * as four parts, one being computed while the others are clustered on their own streams (ring_len / 4 CTAs each; the
- * clustering of a matrix takes ~3x as long as computing it); ~84 on a 148-SM part (measured best for 10 000 leaves). */
+ * clustering of a matrix takes ~2x as long as computing it); as many matrices as memory allows, up to ~128 on a 148-SM part. */
 typedef int (*gv2_newick_cb)(int64_t replicate, const char* newick, size_t length, void* user);
 int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weights, int64_t nb, double* dev_ring,
                               int64_t ring_len, const char* method, const char* const* leaf_names,
