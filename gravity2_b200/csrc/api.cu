@@ -48,7 +48,7 @@ int boot_sparse_launch(gv2_ctx* ctx, const BootSparse* s, int64_t n_pad, int64_t
 
 int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw);
 int lk_method(const char* method);
-void lk_finalize_host(const double* raw, int64_t n, double* Z);
+void lk_finalize_host(const double* raw, int64_t n, int method, double* Z);
 void lk_newick_host(const double* Z, int64_t n, const char* const* names, std::string& out);
 
 static thread_local std::string g_create_error;
@@ -723,7 +723,7 @@ struct TreeSink {
         auto work = [&](int t) {
             std::vector<double> Zl((size_t)std::max<int64_t>(1, n - 1) * 4);
             for (int64_t k = t; k < cnt; k += nthreads) {
-                if (n > 1) lk_finalize_host(zhost[h] + (size_t)k * (n - 1) * 4, n, Zl.data());
+                if (n > 1) lk_finalize_host(zhost[h] + (size_t)k * (n - 1) * 4, n, method, Zl.data());
                 lk_newick_host(Zl.data(), n, names, texts[(size_t)k]);
             }
         };
@@ -986,7 +986,7 @@ extern "C" int gv2_job_replicates_newick(gv2_job* job, const int32_t* dev_weight
     if (!job || !leaf_names || !cb) return gv2_fail(job ? job->ctx : nullptr, GV2_ERR_ARG, "gv2_job_replicates_newick: bad arguments");
     const int mth = lk_method(method);
     if (mth < 0)
-        return gv2_fail(job->ctx, GV2_ERR_UNSUPPORTED, "gv2_job_replicates_newick: linkage method '%s' (built: average, complete, weighted, ward, single)", method ? method : "");
+        return gv2_fail(job->ctx, GV2_ERR_UNSUPPORTED, "gv2_job_replicates_newick: linkage method '%s' (built: average, complete, weighted, ward, single, centroid, median)", method ? method : "");
     if (job->out_kind != GV2_OUT_DISTANCE) return gv2_fail(job->ctx, GV2_ERR_ARG, "gv2_job_replicates_newick: the job must produce distances");
     if (nb <= 0 || job->n == 0) return GV2_OK;
     GV2_CUDA(job->ctx, cudaSetDevice(job->ctx->device));

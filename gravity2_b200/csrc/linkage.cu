@@ -4,7 +4,8 @@
 // triangle is handed to scipy.cluster.hierarchy.linkage(method) (scipy is a third-party dependency of the
 // reference, pinned scipy==1.14.0 in requirements.txt:4; its published algorithm for method "average" is the
 // nearest-neighbour chain of scipy/cluster/_hierarchy.pyx `nn_chain` -- also behind complete, weighted and ward -- and
-// for "single" `mst_single_linkage`, restated here (the test suite holds the same loops in Python, pinned bit for
+// for "single" `mst_single_linkage`, for "centroid" / "median" `fast_linkage` (nearest-neighbour candidates in a binary
+// heap), restated here (the test suite holds the same loops in Python, pinned bit for
 // bit to the installed scipy), to_tree() turns the linkage
 // matrix into nodes and GetNewick (app/utils/get_newick.py:1-13) prints them.  The bootstrap loops
 // (app/src/pl1_graphs.py:108-117, app/src/virus_classification.py:316-330) do this once per replicate and keep
@@ -35,61 +36,7 @@
 #include <string>
 #include <vector>
 
-#define LK_THREADS 1024
-#define LK_MLP 10                // row elements per thread in flight at a time (one batch per 10 240-leaf row)
-
-struct LkBest { double d; int i; };
-
-__device__ __forceinline__ LkBest lk_min(LkBest a, LkBest b) {
-    // smaller distance; on equal distances the lower index (what an upward scan with a strict `<` keeps)
-    if (b.d < a.d || (b.d == a.d && b.i < a.i)) return b;
-    return a;
-}
-
-// grid = matrices, block = LK_THREADS; dynamic shared memory: 2 n ints (cluster sizes, the chain)
-// D: [nb][n][n] float64, destroyed; Zraw: [nb][n-1][4] float64 in merge order
-// linkage_methods[...] of scipy/cluster/_hierarchy_distance_update.pxi; every operation rounded on its own (the host
-// builds of scipy do not contract to FMA), so the heights are bit-identical
-#define LK_AVERAGE 0
-#define LK_COMPLETE 1
-#define LK_WEIGHTED 2
-#define LK_WARD 3
-#define LK_SINGLE 4
-template <int METHOD>
-__device__ __forceinline__ double lk_new_dist(double d_xi, double d_yi, double d_xy, int nx, int ny, int ni) {
-    if (METHOD == LK_AVERAGE)
-        return __ddiv_rn(__dadd_rn(__dmul_rn((double)nx, d_xi), __dmul_rn((double)ny, d_yi)), (double)(nx + ny));
-    if (METHOD == LK_COMPLETE) return d_xi > d_yi ? d_xi : d_yi;
-    if (METHOD == LK_WEIGHTED) return __dmul_rn(0.5, __dadd_rn(d_xi, d_yi));
-    // ward: t = 1 / (nx + ny + ni); sqrt((ni + nx) t d_xi^2 + (ni + ny) t d_yi^2 - ni t d_xy^2), products left to right
-    const double t = __ddiv_rn(1.0, (double)(nx + ny + ni));
-    const double a = __dmul_rn(__dmul_rn(__dmul_rn((double)(ni + nx), t), d_xi), d_xi);
-    const double b = __dmul_rn(__dmul_rn(__dmul_rn((double)(ni + ny), t), d_yi), d_yi);
-    const double c = __dmul_rn(__dmul_rn(__dmul_rn((double)ni, t), d_xy), d_xy);
-    return __dsqrt_rn(__dadd_rn(__dadd_rn(a, b), -c));
-}
-
-// Minimum of (distance, index) over a warp in three REDUX instructions instead of fifteen shuffles: the distance as a
-// sortable 64-bit key (x + 0.0 folds -0.0 into +0.0, NaN -> the largest key: never chosen, as with a strict `<`), minimum of
-// the high words, then of the low words among the lanes that hold it, then of the indices among those -- "smaller distance,
-// on ties the lower index", what an upward scan with a strict `<` keeps.
-struct LkKey { unsigned hi, lo; int i; };
-__device__ __forceinline__ LkKey lk_key(double d, int i) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(d + 0.0);
-    unsigned long long k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-    if (d != d) k = ~0ull;
-    return LkKey{(unsigned)(k >> 32), (unsigned)k, i};
-}
-__device__ __forceinline__ double lk_key_value(unsigned hi, unsigned lo) {
-    const unsigned long long k = ((unsigned long long)hi << 32) | lo;
-    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
-}
-__device__ __forceinline__ LkKey lk_warp_min(LkKey k) {
-    const unsigned mh = __reduce_min_sync(0xffffffffu, k.hi);
-    const unsigned ml = __reduce_min_sync(0xffffffffu, k.hi == mh ? k.lo : 0xffffffffu);
-    const int mi = (int)__reduce_min_sync(0xffffffffu, (k.hi == mh && k.lo == ml) ? (unsigned)k.i : 0x7fffffffu);
-    return LkKey{mh, ml, mi};
-}
+#include "linkage_generic.cuh"
 
 // THREADS = 1024: the whole SM to one matrix.  (Half-SM CTAs of 512 threads, which leave room for a CTA of the similarity
 // kernels beside the clustering in the bootstrap job's dendrogram mode, were measured twice: 5.20 s against 5.19 s for 1001
@@ -316,8 +263,12 @@ __global__ void lk_mirror_upper_kernel(double* __restrict__ D, long long n) {
 // ---------------------------------------------------------------------------------- host: sort, relabel, Newick
 // Rows in merge order -> scipy's linkage matrix: stable sort by distance, then union-find labels
 // (scipy/cluster/_hierarchy.pyx: nn_chain tail + label()).
-static void lk_finalize(const double* raw, int64_t n, double* Z) {
+static void lk_finalize(const double* raw, int64_t n, int method, double* Z) {
     const int64_t m = n - 1;
+    if (method == LK_CENTROID || method == LK_MEDIAN) {       // fast_linkage returns its rows as they are
+        memcpy(Z, raw, (size_t)m * 4 * sizeof(double));
+        return;
+    }
     std::vector<int64_t> order(m);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return raw[a * 4 + 2] < raw[b * 4 + 2]; });
@@ -398,7 +349,9 @@ int lk_method(const char* method) {
     if (!strcmp(method, "weighted")) return LK_WEIGHTED;
     if (!strcmp(method, "ward")) return LK_WARD;
     if (!strcmp(method, "single")) return LK_SINGLE;
-    return -1;      // centroid / median (scipy's fast_linkage) are not built
+    if (!strcmp(method, "centroid")) return LK_CENTROID;
+    if (!strcmp(method, "median")) return LK_MEDIAN;
+    return -1;
 }
 
 size_t lk_smem_bytes(int64_t n, int method) {
@@ -422,7 +375,26 @@ static cudaError_t lk_launch_chain(gv2_ctx* ctx, bool lazy, size_t smem, unsigne
 // merge-ordered rows.  Enqueued on the context's stream.
 int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t n, int64_t nb, double* dev_Zraw) {
     if (n <= 1 || nb <= 0) return GV2_OK;
-    if (method < 0 || method > LK_SINGLE) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage: methods average, complete, weighted, ward, single");
+    if (method < 0 || method > LK_MEDIAN) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage: methods average, complete, weighted, ward, single, centroid, median");
+    if (method == LK_CENTROID || method == LK_MEDIAN) {
+        const size_t smem = lk_generic_smem_bytes(n);
+        if (smem > LK_SMEM_MAX)
+            return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "device linkage (centroid / median) keeps its heap in shared memory: n = %lld needs %zu bytes", (long long)n, smem);
+        Gv2Timer timer(ctx, GV2_TIME_LINKAGE);
+        timer.begin();
+        cudaError_t e = method == LK_CENTROID
+            ? cudaFuncSetAttribute(lk_generic_kernel<LK_CENTROID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024))
+            : cudaFuncSetAttribute(lk_generic_kernel<LK_MEDIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024));
+        if (e == cudaSuccess) {
+            if (method == LK_CENTROID) lk_generic_kernel<LK_CENTROID><<<(unsigned)nb, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+            else lk_generic_kernel<LK_MEDIAN><<<(unsigned)nb, LK_THREADS, smem, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+            e = cudaGetLastError();
+        }
+        ctx->launches++;
+        timer.end();
+        GV2_CUDA(ctx, e);
+        return GV2_OK;
+    }
     // lazy column updates need 16 bytes of shared memory per leaf (n <= 14 080); larger trees write the columns
     const char* env = getenv("GV2_LK_LAZY");
     const bool lazy = method != LK_SINGLE && (size_t)n * 16 <= LK_SMEM_MAX && !(env && atoi(env) == 0);
@@ -452,7 +424,7 @@ int lk_launch(gv2_ctx* ctx, int method, double* dev_D, int64_t d_stride, int64_t
     return GV2_OK;
 }
 
-void lk_finalize_host(const double* raw, int64_t n, double* Z) { lk_finalize(raw, n, Z); }
+void lk_finalize_host(const double* raw, int64_t n, int method, double* Z) { lk_finalize(raw, n, method, Z); }
 void lk_newick_host(const double* Z, int64_t n, const char* const* names, std::string& out) { lk_newick(Z, n, names, out); }
 
 extern "C" int gv2_newick_from_linkage(const double* Z, int64_t n, const char* const* leaf_names, char* out, size_t out_cap,
@@ -470,7 +442,7 @@ extern "C" int gv2_newick_from_linkage(const double* Z, int64_t n, const char* c
 extern "C" int gv2_linkage_host(gv2_ctx* ctx, const double* dist, int64_t n, const char* method, double* Z) {
     if (!ctx || !dist || !Z || n < 1) return gv2_fail(ctx, GV2_ERR_ARG, "gv2_linkage_host: bad arguments");
     const int mth = lk_method(method);
-    if (mth < 0) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "gv2_linkage_host: method '%s' (built: average, complete, weighted, ward, single)", method ? method : "");
+    if (mth < 0) return gv2_fail(ctx, GV2_ERR_UNSUPPORTED, "gv2_linkage_host: method '%s' (built: average, complete, weighted, ward, single, centroid, median)", method ? method : "");
     GV2_CUDA(ctx, cudaSetDevice(ctx->device));
     if (n == 1) return GV2_OK;
     double *d_D = nullptr, *d_Z = nullptr;
@@ -491,6 +463,6 @@ extern "C" int gv2_linkage_host(gv2_ctx* ctx, const double* dist, int64_t n, con
     cleanup();
     if (rc) return rc;
     if (e != cudaSuccess) return gv2_fail(ctx, GV2_ERR_CUDA, "gv2_linkage_host: %s", cudaGetErrorString(e));
-    lk_finalize(raw.data(), n, Z);
+    lk_finalize(raw.data(), n, mth, Z);
     return GV2_OK;
 }

@@ -250,8 +250,7 @@ def VirusGrouping_Estimator(DistMat, Dendrogram_LinkageMethod, TaxoGroupingList,
     the scalar search over the cut height and Theil's U stay on the host as in the reference (scipy)."""
     from scipy.cluster.hierarchy import fcluster
     from scipy.optimize import minimize_scalar
-    if Dendrogram_LinkageMethod not in LINKAGE_METHODS:
-        raise NotImplementedError(f"device linkage is built for methods {LINKAGE_METHODS} (got {Dendrogram_LinkageMethod!r})")
+    _check_linkage_method(Dendrogram_LinkageMethod)
     linkageMat = (engine or default_engine()).linkage(np.asarray(DistMat, dtype=np.float64), Dendrogram_LinkageMethod)
 
     def anti_u(cut):
@@ -331,17 +330,23 @@ def sort_pphmm_tree(PPHMMSignatureTable, do_logscale=False, engine: Optional[Eng
 
 
 # ------------------------------------------------------------------------------ dendrograms
-LINKAGE_METHODS = ("average", "complete", "weighted", "ward", "single")
+LINKAGE_METHODS = ("average", "complete", "weighted", "ward", "single", "centroid", "median")
+
+
+def _check_linkage_method(method):
+    """Every method scipy's ``linkage`` knows is built (api_classes.py:123 allows exactly these); anything else fails as
+    scipy fails it."""
+    if method not in LINKAGE_METHODS:
+        raise ValueError(f"Invalid method: {method}")
 
 
 def DistMat2Tree(DistMat, LeafList, Dendrogram_LinkageMethod, do_logscale=False, engine: Optional[Engine] = None):
     """app/utils/dist_mat_to_tree.py:5-21: Newick string of the UPGMA dendrogram of a distance matrix.  The clustering
     (scipy ``linkage`` of the upper triangle) runs on the device, to_tree + GetNewick natively on the host.  Like the
-    reference, negative entries of the caller's matrix are zeroed in place.  Built for scipy's nearest-neighbour-chain
-    methods (average -- the default of every shipped payload --, complete, weighted, ward) and single; centroid and
-    median raise."""
-    if Dendrogram_LinkageMethod not in LINKAGE_METHODS:
-        raise NotImplementedError(f"device linkage is built for methods {LINKAGE_METHODS} (got {Dendrogram_LinkageMethod!r})")
+    reference, negative entries of the caller's matrix are zeroed in place.  Every method of scipy's ``linkage`` is built:
+    the nearest-neighbour-chain methods (average -- the default of every shipped payload --, complete, weighted, ward), single
+    (minimum spanning tree) and centroid / median (the heap-based generic algorithm; trees of at most 12 000 leaves)."""
+    _check_linkage_method(Dendrogram_LinkageMethod)
     eng = engine or default_engine()
     DistMat[DistMat < 0] = 0
     D = np.asarray(DistMat, dtype=np.float64)
@@ -364,8 +369,7 @@ def bootstrap_newick(PPHMMSignatureTable, PPHMMLocationTable, TaxoGroupingList, 
     method = payload.get("Dendrogram_LinkageMethod", "average")
     if payload.get("PphmmNeighbourhoodWeight", 0) != 0 or payload.get("PphmmSigScoreThreshold", 0) != 0:
         raise NotImplementedError("batched bootstrap is built for PphmmNeighbourhoodWeight == 0 and threshold == 0")
-    if method not in LINKAGE_METHODS:
-        raise NotImplementedError(f"device linkage is built for methods {LINKAGE_METHODS} (got {method!r})")
+    _check_linkage_method(method)
     loc = sig if pipeline == "pl1" else _as_table(PPHMMLocationTable)
     gor = gom_membership(TaxoGroupingList, GOMIDList) if "G" in scheme else None
     job = _make_job(engine, sig, loc, gor, len(GOMIDList), scheme, float(payload.get("p", 1.0)), True)

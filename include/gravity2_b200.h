@@ -131,8 +131,9 @@ int gv2_gom_table_host(gv2_ctx* ctx, const double* loc, int64_t n, int64_t p, in
                                  (plain dcor(X, Y) of app/utils/dcor.py:34-62) */
 
 /* Replaces the clustering of DistMat2Tree (app/utils/dist_mat_to_tree.py:7-12): scipy.cluster.hierarchy.linkage of the
- * upper triangle of `dist` [n][n] (host), method "average" | "complete" | "weighted" | "ward" | "single"; Z [n-1][4]
- * float64 as scipy returns it (sorted, relabelled), bit for bit. */
+ * upper triangle of `dist` [n][n] (host), method "average" | "complete" | "weighted" | "ward" | "single" | "centroid" |
+ * "median" (all seven of scipy, api_classes.py:123); Z [n-1][4] float64 as scipy returns it (sorted and relabelled; for
+ * centroid / median in merge order, heights not monotone), bit for bit.  centroid / median: n <= 12 000. */
 int gv2_linkage_host(gv2_ctx* ctx, const double* dist, int64_t n, const char* method, double* Z);
 /* to_tree + GetNewick (app/utils/get_newick.py:1-13) of a linkage matrix: host only, no context.  *out_len = length
  * without the terminator; with out == NULL only the length is returned. */
@@ -214,8 +215,8 @@ int gv2_job_replicates_device(gv2_job* job, const int32_t* dev_weights, int64_t 
                               gv2_replicate_cb callback, void* user);
 /* Replicate dendrograms without shipping the matrices: each replicate's distance matrix is
  * clustered on the device (scipy.cluster.hierarchy.linkage(..., method): the nearest-neighbour chain behind "average"
- * (UPGMA, the default), "complete", "weighted" and "ward", the minimum spanning tree behind "single"; scipy's tie order;
- * "centroid" / "median" are not built) and printed as DistMat2Tree + GetNewick print it (app/utils/dist_mat_to_tree.py:5-21,
+ * (UPGMA, the default), "complete", "weighted" and "ward", the minimum spanning tree behind "single", the heap-based generic
+ * algorithm behind "centroid" / "median" (n <= 12 000); scipy's tie order) and printed as DistMat2Tree + GetNewick print it (app/utils/dist_mat_to_tree.py:5-21,
  * app/utils/get_newick.py:1-13); callback(b, newick, length, user) runs on the calling thread in replicate order.
  * The job must have been created with GV2_OUT_DISTANCE.  dev_ring [ring_len][n][n] is scratch: with ring_len >= 8 it is used
  * as four parts, one being computed while the others are clustered on their own streams (ring_len / 4 CTAs each; the

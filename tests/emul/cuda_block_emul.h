@@ -1,0 +1,80 @@
+// One CUDA thread block on host threads: enough of the CUDA surface for gravity2_b200/csrc/linkage_generic.cuh to compile
+// with g++ and run as written -- one OS thread per CUDA thread, a barrier for __syncthreads, per-warp barriers for the
+// warp reductions.  TEST INFRASTRUCTURE: lets the CPU test suite check a kernel's LOGIC (barrier placement, shared-memory
+// hand-overs, tie order) against scipy where there is no GPU; the product path never sees this file.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+
+struct EmuDim { int x = 0, y = 0, z = 0; };
+static thread_local EmuDim threadIdx;
+static EmuDim blockIdx;
+
+class EmuBarrier {
+  public:
+    explicit EmuBarrier(int count = 1) : count_(count) {}
+    void reset(int count) { count_ = count; waiting_ = 0; }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        const unsigned long gen = gen_;
+        if (++waiting_ == count_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen_ != gen; });
+    }
+  private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int count_, waiting_ = 0;
+    unsigned long gen_ = 0;
+};
+
+static EmuBarrier emu_block_barrier;
+struct EmuWarp { EmuBarrier bar{32}; unsigned slot[32]; };
+static std::vector<EmuWarp>* emu_warps;
+
+static inline void __syncthreads() { emu_block_barrier.wait(); }
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
+    w.slot[threadIdx.x & 31] = v;
+    w.bar.wait();
+    unsigned m = w.slot[0];
+    for (int l = 1; l < 32; ++l) m = w.slot[l] < m ? w.slot[l] : m;
+    w.bar.wait();
+    return m;
+}
+static inline long long __double_as_longlong(double d) { long long b; memcpy(&b, &d, 8); return b; }
+static inline double __longlong_as_double(long long b) { double d; memcpy(&d, &b, 8); return d; }
+// separately rounded operations (this file is compiled with -ffp-contract=off)
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline double __dsqrt_rn(double a) { return sqrt(a); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+
+// dynamic shared memory of the one emulated block
+alignas(16) static unsigned char emu_dynamic_smem[256 * 1024];
+
+template <class F>
+static void emu_launch_block(int threads, F&& body) {
+    std::vector<EmuWarp> warps((size_t)(threads + 31) / 32);
+    emu_warps = &warps;
+    emu_block_barrier.reset(threads);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&, t] { threadIdx.x = t; body(); });
+    for (auto& th : pool) th.join();
+}

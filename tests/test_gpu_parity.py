@@ -529,12 +529,14 @@ def test_fused_tail_equals_separate_kernels(eng, scheme, pw, kind):
 
 
 # ------------------------------------------------------------------------ dendrograms
-@pytest.mark.parametrize("method", ["average", "complete", "weighted", "ward", "single"])
+@pytest.mark.parametrize("method", ["average", "complete", "weighted", "ward", "single", "centroid", "median"])
 @pytest.mark.parametrize("n,kind", [(2, "random"), (3, "ties"), (17, "ties"), (130, "random"), (513, "ties"), (1500, "blocks"),
                                     (1400, "line")])
 def test_device_linkage_equals_scipy(eng, n, kind, method):
     """Device linkage == scipy.cluster.hierarchy.linkage(method) row for row, bit for bit: heights from the same
-    separately rounded operations, ties resolved in the order scipy's nn_chain / mst_single_linkage resolve them."""
+    separately rounded operations, ties resolved in the order scipy's nn_chain / mst_single_linkage / fast_linkage (heap)
+    resolve them.  (centroid / median on distances that are not Euclidean take square roots of negative numbers: NaN
+    entries of the working matrix are never chosen, by scipy or here; rows are compared NaN == NaN.)"""
     from scipy.cluster.hierarchy import linkage
     rng = np.random.default_rng(n)
     if kind == "random":
@@ -550,11 +552,12 @@ def test_device_linkage_equals_scipy(eng, n, kind, method):
     D = np.triu(D, 1)
     D = D + D.T
     Z = eng.linkage(D, method)
-    ref = linkage(D[np.triu_indices_from(D, k=1)], method=method)
-    assert Z.shape == ref.shape and np.array_equal(Z, ref)
+    with np.errstate(all="ignore"):
+        ref = linkage(D[np.triu_indices_from(D, k=1)], method=method)
+    assert Z.shape == ref.shape and np.array_equal(Z, ref, equal_nan=True)
     # an asymmetric matrix is clustered by its upper triangle, as the reference does
     A = D + np.tril(rng.random((n, n)), -1)
-    assert np.array_equal(eng.linkage(A, method), ref)
+    assert np.array_equal(eng.linkage(A, method), ref, equal_nan=True)
 
 
 @pytest.mark.parametrize("tag", ["A", "B"])
@@ -571,8 +574,10 @@ def test_dist_mat_to_tree_golden(golden, eng, tag):
     Dn[D == 0] = -0.5
     assert G.DistMat2Tree(Dn, names, "average", False) == str(golden[f"{tag}_newick_avg"]) and np.array_equal(Dn, D)
     assert G.DistMat2Tree(D.copy(), names, "complete", True) == O.dist_mat_to_tree(D.copy(), names, "complete", True)
-    with pytest.raises(NotImplementedError):
-        G.DistMat2Tree(D, names, "centroid", False)
+    for method in ("centroid", "median"):          # non-monotone heights: negative branch lengths print as the reference's
+        assert G.DistMat2Tree(D.copy(), names, method, False) == O.dist_mat_to_tree(D.copy(), names, method, False)
+    with pytest.raises(ValueError):                # scipy's own refusal of an unknown method
+        G.DistMat2Tree(D, names, "upgma", False)
 
 
 def test_bootstrap_newick_equals_matrices_then_scipy(eng):
@@ -593,7 +598,7 @@ def test_bootstrap_newick_equals_matrices_then_scipy(eng):
         assert tree.count(",") == len(names) - 1 and tree.endswith(");")
 
 
-@pytest.mark.parametrize("n,method", [(1, "average"), (2, "average"), (5, "ward"), (70, "single")])
+@pytest.mark.parametrize("n,method", [(1, "average"), (2, "average"), (5, "ward"), (70, "single"), (60, "centroid"), (33, "median")])
 def test_bootstrap_newick_small_and_pl2(eng, n, method):
     """Tree path edge cases: one and two genomes, PL2 (sorted indices, real location table, GOMDB from the reference rows
     only), the other linkage methods -- always against the matrix path of the same engine + the reference's tree code."""
