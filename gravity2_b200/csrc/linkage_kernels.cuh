@@ -1,6 +1,7 @@
-// Device helpers shared by the linkage kernels and the "centroid" / "median" kernel (linkage.cu includes this file; so does
-// tests/emul/lk_generic_emul.cpp, which runs the SAME kernel source on host threads -- one per CUDA thread, barriers for
-// __syncthreads and the warp reductions -- so that its logic is checked against scipy where there is no GPU).
+// The linkage kernels (nearest-neighbour chain, minimum spanning tree, heap-based generic algorithm) and their device
+// helpers.  linkage.cu includes this file; so does tests/emul/lk_emul.cpp, which runs the SAME kernel source on host
+// threads -- one per CUDA thread, barriers for __syncthreads and the warp reductions / shuffles -- so that the kernels'
+// logic is checked against scipy where there is no GPU.
 #pragma once
 
 #ifndef LK_THREADS
@@ -75,6 +76,221 @@ __device__ __forceinline__ LkKey lk_warp_min(LkKey k) {
     const unsigned ml = __reduce_min_sync(0xffffffffu, k.hi == mh ? k.lo : 0xffffffffu);
     const int mi = (int)__reduce_min_sync(0xffffffffu, (k.hi == mh && k.lo == ml) ? (unsigned)k.i : 0x7fffffffu);
     return LkKey{mh, ml, mi};
+}
+
+// THREADS = 1024: the whole SM to one matrix.  (Half-SM CTAs of 512 threads, which leave room for a CTA of the similarity
+// kernels beside the clustering in the bootstrap job's dendrogram mode, were measured twice: 5.20 s against 5.19 s for 1001
+// trees of 10 000 leaves with a two-part ring, 4.70 s against 4.42 s with the four-part ring.)
+// A thread owns the same row positions i = tid + e THREADS in every row, so which of them are live clusters is a register
+// bit mask (bit e): dead positions are neither loaded nor compared, and no shared-memory lookup sits in the scan.
+// LAZY: a merge does not write the new cluster's COLUMN (n scattered 8-byte stores, one 32-byte sector each: half of the
+// kernel's DRAM operations and most of a merge's time in the load/store unit).  The matrix is symmetric and a new cluster's
+// ROW is complete when it is written, so an entry (x, j) of an older row is simply read from the other side, D[j][x], when it
+// is next needed: per cluster born[j] (merges done when row j was written) and fresh[x] (merges done when row x was last
+// brought up to date); entry (x, j) is stale iff born[j] > fresh[x].  A scan of row x loads every element from whichever
+// side is current -- one load per element either way, the address is chosen from shared-memory state before any load is
+// issued, so a step is still one round trip -- writes the patched values back into row x and sets fresh[x]; a merge does
+// the same for the two rows it reads.  Same values, same operations, same order: the linkage matrix stays bit-identical.
+// Dynamic shared memory: 2 n ints (cluster sizes, the chain) [+ 2 n ints (born, fresh)].
+template <int METHOD, int THREADS, bool LAZY>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
+    LK_DYNAMIC_SMEM(lk_size);
+    __shared__ LkKey s_warp[THREADS / 32];
+    __shared__ int s_x, s_y, s_len, s_merge, s_first;
+    __shared__ double s_min, s_dp;
+    double* D = Dall + (size_t)blockIdx.x * d_stride;
+    int* chain = lk_size + n;
+    int* born = chain + n;                            // LAZY only
+    int* fresh = born + n;                            // LAZY only
+    double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += THREADS) {
+        lk_size[i] = 1;
+        if (LAZY) { born[i] = 0; fresh[i] = 0; }
+    }
+    unsigned alive = 0u;                              // n <= 32 THREADS (the shared-memory limit of the launcher is lower)
+    for (int e = 0; e < 32; ++e)
+        if (tid + e * THREADS < n) alive |= 1u << e;
+    if (tid == 0) { s_len = 0; s_first = 0; }
+    __syncthreads();
+    for (int k = 0; k < n - 1; ++k) {
+        if (tid == 0 && s_len == 0) {
+            int f = s_first;
+            while (lk_size[f] == 0) ++f;              // lowest-numbered live cluster (dead ones never come back)
+            s_first = f;
+            chain[0] = f;
+            s_len = 1;
+        }
+        __syncthreads();
+        // grow the chain until its two top elements are mutual nearest neighbours
+        while (true) {
+            const int len = s_len;
+            const int x = chain[len - 1];
+            const int prev = len > 1 ? chain[len - 2] : -1;
+            double* row = D + (size_t)x * n;
+            const int fx = LAZY ? fresh[x] : 0;
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            // The step is one DRAM round trip long, not one per element: a thread's loads of the row are all issued before the
+            // first is looked at, LK_MLP at a time.
+            for (int e0 = 0, i0 = tid; i0 < n; e0 += LK_MLP, i0 += THREADS * LK_MLP) {
+                double dv[LK_MLP];
+                const unsigned live = alive >> e0;
+                unsigned stale = 0u;
+#pragma unroll
+                for (int u = 0; u < LK_MLP; ++u) {
+                    const int i = i0 + u * THREADS;
+                    const bool on = (live >> u) & 1u;
+                    const bool st = LAZY && on && born[i] > fx;          // row i is younger than row x's last refresh
+                    if (st) stale |= 1u << u;
+                    dv[u] = on ? (st ? D[(size_t)i * n + x] : __ldcs(row + i)) : INFINITY;
+                }
+#pragma unroll
+                for (int u = 0; u < LK_MLP; ++u) {
+                    const int i = i0 + u * THREADS;
+                    if (!((live >> u) & 1u) || i == x) continue;
+                    if (LAZY && ((stale >> u) & 1u)) row[i] = dv[u];     // row x is current again
+                    if (i == prev) s_dp = dv[u];                     // the incumbent's distance, for the final comparison
+                    if (dv[u] < bd) { bd = dv[u]; bi = i; }          // ascending i per thread: first minimum kept
+                }
+            }
+            LkKey best = lk_warp_min(lk_key(bd, bi));
+            if (lane == 0) s_warp[warp] = best;
+            __syncthreads();
+            if (warp == 0) {
+                best = lane < THREADS / 32 ? s_warp[lane] : LkKey{0xffffffffu, 0xffffffffu, 0x7fffffff};
+                best = lk_warp_min(best);
+                if (lane == 0) {
+                    // the previous chain element is the incumbent: a scanned cluster replaces it only if strictly closer
+                    int y = best.i;
+                    double cur = lk_key_value(best.hi, best.lo);
+                    const bool none = best.hi == 0xffffffffu && best.lo == 0xffffffffu;   // nothing comparable (all NaN)
+                    if (none) { y = 0x7fffffff; cur = INFINITY; }
+                    if (prev >= 0) {
+                        const double dp = s_dp;
+                        if (!(cur < dp)) { y = prev; cur = dp; }
+                    } else if (y == 0x7fffffff) {
+                        y = 0;                        // every distance NaN: scipy keeps its stale y; unreachable for cleaned matrices
+                    }
+                    if (prev >= 0 && y == prev) {
+                        s_merge = 1;
+                    } else {
+                        s_merge = 0;
+                        chain[len] = y;
+                        s_len = len + 1;
+                    }
+                    s_x = x; s_y = y; s_min = cur;
+                    if (LAZY) fresh[x] = k;           // k merges so far: every younger row has been read from its own side
+                }
+            }
+            __syncthreads();
+            if (s_merge) break;
+        }
+        // merge the two top elements
+        int x = s_x, y = s_y;
+        if (x > y) { const int t = x; x = y; y = t; }
+        const int nx = lk_size[x], ny = lk_size[y];
+        const double dmin = s_min;
+        const int fx = LAZY ? fresh[x] : 0, fy = LAZY ? fresh[y] : 0;
+        if ((x & (THREADS - 1)) == tid) alive &= ~(1u << (x / THREADS));   // x dies; its owner drops it
+        __syncthreads();                              // everyone has read the sizes and s_* before they change
+        if (tid == 0) {
+            Z[(size_t)k * 4 + 0] = (double)x;
+            Z[(size_t)k * 4 + 1] = (double)y;
+            Z[(size_t)k * 4 + 2] = dmin;
+            Z[(size_t)k * 4 + 3] = (double)(nx + ny);
+            lk_size[x] = 0;
+            lk_size[y] = nx + ny;
+            s_len -= 2;
+        }
+        const double* rx = D + (size_t)x * n;
+        double* ry = D + (size_t)y * n;
+        for (int e0 = 0, i0 = tid; i0 < n; e0 += LK_MLP, i0 += THREADS * LK_MLP) {
+            double ax[LK_MLP], ay[LK_MLP];
+            int sz[LK_MLP];
+            const unsigned live = alive >> e0;
+#pragma unroll
+            for (int u = 0; u < LK_MLP; ++u) {
+                const int i = i0 + u * THREADS;
+                const bool on = ((live >> u) & 1u) && i != y;
+                const int bi2 = (LAZY && on) ? born[i] : 0;  // (i != x, y: not entries thread 0 is changing)
+                ax[u] = on ? (bi2 > fx ? D[(size_t)i * n + x] : rx[i]) : 0.0;
+                ay[u] = on ? (bi2 > fy ? D[(size_t)i * n + y] : ry[i]) : 0.0;
+                sz[u] = on ? lk_size[i] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < LK_MLP; ++u) {
+                const int i = i0 + u * THREADS;
+                if (sz[u] == 0) continue;
+                const double v = lk_new_dist<METHOD>(ax[u], ay[u], dmin, nx, ny, sz[u]);
+                ry[i] = v;
+                if (!LAZY) D[(size_t)i * n + y] = v;
+            }
+        }
+        if (LAZY && tid == 0) { born[y] = k + 1; fresh[y] = k + 1; }   // (read by others only after the barrier below)
+        __syncthreads();
+    }
+}
+
+// Method "single": mst_single_linkage of scipy/cluster/_hierarchy.pyx -- Prim's minimum spanning tree from node 0; per
+// step the row of the newest tree node lowers the running distances of the others, the closest (lowest index on
+// ties: upward scan, strict `<`) joins.  Dynamic shared memory: n ints (merged flags) + n doubles (running distances).
+__global__ void __launch_bounds__(LK_THREADS, 1)
+lk_mst_single_kernel(const double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
+    LK_DYNAMIC_SMEM(lk_size);
+    __shared__ LkBest s_warp[LK_THREADS / 32];
+    __shared__ LkBest s_best;
+    int* merged = lk_size;
+    double* dmin = reinterpret_cast<double*>(lk_size + ((n + 1) & ~1));
+    const double* D = Dall + (size_t)blockIdx.x * d_stride;
+    double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += LK_THREADS) { merged[i] = 0; dmin[i] = INFINITY; }
+    __syncthreads();
+    int x = 0;
+    for (int k = 0; k < n - 1; ++k) {
+        if (tid == 0) merged[x] = 1;
+        __syncthreads();
+        const double* row = D + (size_t)x * n;
+        LkBest best{INFINITY, 0x7fffffff};
+        for (int i = tid; i < n; i += LK_THREADS) {
+            if (merged[i]) continue;
+            const double d = row[i];
+            double m = dmin[i];
+            if (m > d) { m = d; dmin[i] = d; }
+            if (m < best.d) { best.d = m; best.i = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            LkBest other;
+            other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+            other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+            best = lk_min(best, other);
+        }
+        if (lane == 0) s_warp[warp] = best;
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < LK_THREADS / 32 ? s_warp[lane] : LkBest{INFINITY, 0x7fffffff};
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                LkBest other;
+                other.d = __shfl_xor_sync(0xffffffffu, best.d, o);
+                other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+                best = lk_min(best, other);
+            }
+            if (lane == 0) {
+                if (best.i == 0x7fffffff) best.i = 0;     // all NaN / infinite: scipy keeps its stale y; unreachable for cleaned matrices
+                s_best = best;
+                Z[(size_t)k * 4 + 0] = (double)x;
+                Z[(size_t)k * 4 + 1] = (double)best.i;
+                Z[(size_t)k * 4 + 2] = best.d;
+                Z[(size_t)k * 4 + 3] = 0.0;               // sizes come from the relabelling pass
+            }
+        }
+        __syncthreads();
+        x = s_best.i;
+    }
 }
 
 // Methods "centroid" and "median": fast_linkage of scipy/cluster/_hierarchy.pyx (Muellner's generic algorithm).  Their

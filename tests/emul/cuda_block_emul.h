@@ -1,4 +1,4 @@
-// One CUDA thread block on host threads: enough of the CUDA surface for gravity2_b200/csrc/linkage_generic.cuh to compile
+// One CUDA thread block on host threads: enough of the CUDA surface for gravity2_b200/csrc/linkage_kernels.cuh to compile
 // with g++ and run as written -- one OS thread per CUDA thread, a barrier for __syncthreads, per-warp barriers for the
 // warp reductions.  TEST INFRASTRUCTURE: lets the CPU test suite check a kernel's LOGIC (barrier placement, shared-memory
 // hand-overs, tie order) against scipy where there is no GPU; the product path never sees this file.
@@ -42,7 +42,7 @@ class EmuBarrier {
 };
 
 static EmuBarrier emu_block_barrier;
-struct EmuWarp { EmuBarrier bar{32}; unsigned slot[32]; };
+struct EmuWarp { EmuBarrier bar{32}; unsigned slot[32]; unsigned long long wide[32]; };
 static std::vector<EmuWarp>* emu_warps;
 
 static inline void __syncthreads() { emu_block_barrier.wait(); }
@@ -55,6 +55,19 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
     w.bar.wait();
     return m;
 }
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
+    memcpy(&w.wide[threadIdx.x & 31], &v, sizeof(T));
+    w.bar.wait();
+    T r;
+    memcpy(&r, &w.wide[(threadIdx.x & 31) ^ lane_mask], sizeof(T));
+    w.bar.wait();
+    return r;
+}
+template <class T>
+static inline T __ldcs(const T* p) { return *p; }
 static inline long long __double_as_longlong(double d) { long long b; memcpy(&b, &d, 8); return b; }
 static inline double __longlong_as_double(long long b) { double d; memcpy(&d, &b, 8); return d; }
 // separately rounded operations (this file is compiled with -ffp-contract=off)

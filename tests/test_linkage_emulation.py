@@ -1,8 +1,10 @@
-"""The centroid / median linkage kernel, run on the CPU: tests/emul/cuda_block_emul.h supplies one CUDA thread block as host
-threads (a barrier for __syncthreads, per-warp barriers for the REDUX reductions), tests/emul/lk_generic_emul.cpp includes the
-SAME source the GPU build compiles (gravity2_b200/csrc/linkage_generic.cuh).  What is checked here is the kernel's logic
--- barrier placement, the hand-overs through shared memory, the order of the heap operations that decides how ties fall --
-against scipy; the GPU tests (test_gpu_parity.py::test_device_linkage_equals_scipy) check the compiled kernel itself."""
+"""The linkage kernels, run on the CPU: tests/emul/cuda_block_emul.h supplies one CUDA thread block as host threads (a barrier
+for __syncthreads, per-warp barriers for the REDUX reductions and shuffles), tests/emul/lk_emul.cpp includes the SAME source
+the GPU build compiles (gravity2_b200/csrc/linkage_kernels.cuh).  What is checked here is the kernels' logic -- barrier
+placement, the hand-overs through shared memory, the lazy column bookkeeping, the order of the comparisons and heap
+operations that decides how ties fall -- against scipy; the GPU tests (test_gpu_parity.py::test_device_linkage_equals_scipy)
+check the compiled kernels themselves.  (Built with -fsanitize=thread the emulation doubles as a race detector for the
+kernels' shared-memory protocol: see DESIGN.md section 4.)"""
 import os
 import shutil
 import subprocess
@@ -11,15 +13,16 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CODES = {"average": 0, "complete": 1, "weighted": 2, "ward": 3, "single": 4, "centroid": 5, "median": 6}
 
 
 @pytest.fixture(scope="module")
 def emul(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("no host compiler")
-    exe = str(tmp_path_factory.mktemp("emul") / "lk_generic_emul")
+    exe = str(tmp_path_factory.mktemp("emul") / "lk_emul")
     subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-o", exe,
-                    os.path.join(ROOT, "tests", "emul", "lk_generic_emul.cpp")], check=True)
+                    os.path.join(ROOT, "tests", "emul", "lk_emul.cpp")], check=True)
     return exe
 
 
@@ -34,6 +37,9 @@ def _matrix(kind, n, rng):
     elif kind == "blocks":                                       # taxon-like: many exact 1.0
         grp = rng.integers(0, 6, n)
         D = np.where(grp[:, None] == grp[None, :], np.round(rng.random((n, n)) * 0.6, 2), 1.0)
+    elif kind == "line":                                         # the chain grows to n elements
+        pos = np.cumsum(1.0 + (n - np.arange(n)) * 1e-3)
+        D = np.abs(pos[:, None] - pos[None, :])
     else:                                                        # 1 - binary Jaccard, the sort_pphmm distances
         a = rng.random((n, 30)) < 0.2
         a[:, 0] = True
@@ -42,15 +48,39 @@ def _matrix(kind, n, rng):
     return D + D.T
 
 
-@pytest.mark.parametrize("method,code", [("centroid", 5), ("median", 6)])
+def _run(emul, method, D, lazy):
+    n = len(D)
+    out = subprocess.run([emul, str(CODES[method]), str(n), str(int(lazy))], input=np.ascontiguousarray(D).tobytes(),
+                         capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    return np.frombuffer(out.stdout, dtype=np.float64).reshape(n - 1, 4).copy()
+
+
+@pytest.mark.parametrize("method", ["centroid", "median"])
 @pytest.mark.parametrize("kind,n", [("euclid", 2), ("ties", 3), ("euclid", 97), ("random", 140), ("ties", 129), ("blocks", 260),
                                     ("jaccard", 75)])
-def test_emulated_generic_linkage_kernel_equals_scipy(emul, kind, n, method, code):
+def test_emulated_generic_linkage_kernel_equals_scipy(emul, kind, n, method):
+    """lk_generic_kernel (scipy's fast_linkage): rows come out final, in merge order."""
     from scipy.cluster.hierarchy import linkage
     D = _matrix(kind, n, np.random.default_rng(n))
     with np.errstate(all="ignore"):
         ref = linkage(D[np.triu_indices(n, 1)], method)
-    out = subprocess.run([emul, str(code), str(n)], input=np.ascontiguousarray(D).tobytes(), capture_output=True, timeout=600)
-    assert out.returncode == 0, out.stderr
-    Z = np.frombuffer(out.stdout, dtype=np.float64).reshape(n - 1, 4)
-    assert np.array_equal(Z, ref, equal_nan=True)
+    assert np.array_equal(_run(emul, method, D, False), ref, equal_nan=True)
+
+
+@pytest.mark.parametrize("lazy", [False, True])
+@pytest.mark.parametrize("method,kind,n", [("average", "ties", 3), ("average", "blocks", 200), ("average", "jaccard", 131),
+                                           ("average", "line", 150), ("complete", "ties", 90), ("weighted", "random", 77),
+                                           ("ward", "euclid", 110), ("single", "ties", 140), ("single", "euclid", 65)])
+def test_emulated_chain_and_mst_kernels_equal_scipy(emul, method, kind, n, lazy):
+    """lk_nn_chain_kernel (eager and lazy column updates) and lk_mst_single_kernel: rows in merge order, then the stable sort
+    and union-find relabelling scipy applies (the library does them on the host: lk_finalize; here the oracle's restatement)."""
+    from scipy.cluster.hierarchy import linkage
+    from oracle import linkage_oracle as L
+    if method == "single" and lazy:
+        pytest.skip("the spanning-tree kernel has no lazy variant")
+    D = _matrix(kind, n, np.random.default_rng(1000 + n))
+    raw = _run(emul, method, D, lazy)
+    Z = raw[np.argsort(raw[:, 2], kind="mergesort")]
+    L.label(Z, n)
+    assert np.array_equal(Z, linkage(D[np.triu_indices(n, 1)], method))
