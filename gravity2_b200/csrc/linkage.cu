@@ -147,6 +147,15 @@ size_t lk_smem_bytes(int64_t n, int method) {
 template <int METHOD>
 static cudaError_t lk_launch_chain(gv2_ctx* ctx, bool lazy, size_t smem, unsigned g, double* dev_D, int64_t d_stride, int64_t n,
                                    double* dev_Zraw) {
+    // live-list kernel (lazy columns + work that follows the number of live clusters): 18 bytes of shared memory per leaf
+    const char* env = getenv("GV2_LK_LIST");
+    if (lazy && n <= (int64_t)LK_LIST_PER * LK_THREADS && lk_list_smem_bytes(n) <= LK_SMEM_MAX && !(env && atoi(env) == 0)) {
+        const size_t lsm = lk_list_smem_bytes(n);
+        cudaError_t e = cudaFuncSetAttribute(lk_nn_chain_list_kernel<METHOD, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(lsm, 1024));
+        if (e != cudaSuccess) return e;
+        lk_nn_chain_list_kernel<METHOD, 1024><<<g, LK_THREADS, lsm, ctx->stream>>>(dev_D, d_stride, (int)n, dev_Zraw);
+        return cudaGetLastError();
+    }
     const int sz = (int)std::max<size_t>(smem, 1024);
     cudaError_t e = lazy ? cudaFuncSetAttribute(lk_nn_chain_kernel<METHOD, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz)
                          : cudaFuncSetAttribute(lk_nn_chain_kernel<METHOD, 1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);

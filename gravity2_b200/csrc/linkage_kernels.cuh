@@ -233,6 +233,232 @@ lk_nn_chain_kernel(double* __restrict__ Dall, long long d_stride, int n, double*
     }
 }
 
+// The chain kernel with a LIVE LIST (lazy column updates as above).  ncu on one 10 000-leaf matrix showed the kernel above
+// issue-bound as much as memory-bound (issue slots 52 % busy with one CTA on the SM; 63 % of the instructions in the row
+// scan, 33 % in the merge) and every scan walking all n positions, ~45 instructions each, whether the cluster there is
+// alive or not -- while on average half of them are dead.  Here the live clusters are an ascending list in shared memory,
+// one 32-bit entry each: (born << 16) | index, so that one LDS brings the cluster and the stamp that says which side of the
+// matrix holds the current value.  Scans and merges walk the list (lane -> list slot, so the loads stay as coalesced as the
+// survivors allow), a merge tombstones the entry of the cluster that dies and re-stamps the one that survives, and whenever
+// an eighth of the list is tombstones the block compacts it in place (order preserving: per-thread contiguous pieces,
+// counts, a two-level prefix sum).  Work per scan follows the number of live clusters: about half the element visits over a
+// run, and element offsets are 32-bit (n * n < 2^32), one address computation whichever side is read.  Per thread the list
+// slots ascend and the block minimum is taken on (distance, index): "first minimum of an upward scan", as before --
+// bit-identical rows.  Dynamic shared memory: 3 n ints (sizes, chain, fresh) + n list entries = 16 bytes per leaf.
+#define LK_TOMB 0xffffffffu
+// Keep a value in its register: without this ptxas re-derives the matrix pointer (block index x stride + base, three
+// constant-bank loads and a 64-bit multiply-add) and n for EVERY element under the 64-register cap of a 1024-thread CTA.
+#ifdef __CUDA_ARCH__
+#define LK_KEEP_PTR(p) asm volatile("" : "+l"(p))
+#define LK_KEEP_U32(v) asm volatile("" : "+r"(v))
+#else
+#define LK_KEEP_PTR(p)
+#define LK_KEEP_U32(v)
+#endif
+#define LK_LIST_PER 14           // list entries per thread in a compaction: n <= 14 * THREADS
+static inline size_t lk_list_smem_bytes(long long n) { return (size_t)n * 16; }
+
+// One row scan over the live list, MLP entries per thread in flight (the caller picks MLP from the list length, so that the
+// instructions issued follow the number of live clusters -- predicated-off slots of a fixed batch of ten would not).
+template <int MLP, int THREADS>
+__device__ __forceinline__ void lk_list_scan(double* D, const unsigned* live, int len, int tid, unsigned un, unsigned ux,
+                                             unsigned xrow, unsigned fx, int prev, double* dp_out, double& bd, int& bi) {
+    for (int s0 = tid; s0 < len; s0 += THREADS * MLP) {
+        double dv[MLP];
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) {
+            const int slot = s0 + u * THREADS;
+            const unsigned e = slot < len ? live[slot] : LK_TOMB;
+            const unsigned i = e & 0xffffu;
+            // row i younger than row x's last refresh: the current value is on its side of the matrix
+            const unsigned off = (e >> 16) > fx ? i * un + ux : xrow + i;
+            dv[u] = e != LK_TOMB ? __ldcs(D + off) : INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) {
+            const int slot = s0 + u * THREADS;
+            const unsigned e = slot < len ? live[slot] : LK_TOMB;     // (re-read: entries held in registers cost more)
+            const unsigned i = e & 0xffffu;                            // (a tombstone's 0xffff is no cluster: n <= 14 336)
+            if (e != LK_TOMB && (e >> 16) > fx) D[xrow + i] = dv[u];   // row x is current again
+            if ((int)i == prev) *dp_out = dv[u];                       // the incumbent's distance, for the final comparison
+            if (dv[u] < bd) { bd = dv[u]; bi = (int)i; }               // ascending i per thread: first minimum kept
+        }
+    }
+}
+
+// The merge's pass over the live list: distances of every other live cluster to the union, written to the union's row.
+template <int METHOD, int MLP, int THREADS>
+__device__ __forceinline__ void lk_list_merge(double* D, unsigned* live, const int* sizes, int len, int tid, unsigned un,
+                                              unsigned ux, unsigned uy, unsigned fx, unsigned fy, unsigned stamp, double dmin,
+                                              int nx, int ny) {
+    const unsigned xrow = ux * un, yrow = uy * un;
+    for (int s0 = tid; s0 < len; s0 += THREADS * MLP) {
+        double ax[MLP], ay[MLP];
+        int sz[MLP];
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) {
+            const int slot = s0 + u * THREADS;
+            const unsigned e = slot < len ? live[slot] : LK_TOMB;
+            const unsigned i = e & 0xffffu;
+            const bool on = e != LK_TOMB && i != ux && i != uy;
+            if (e != LK_TOMB && i == ux) live[slot] = LK_TOMB;              // x dies: a tombstone
+            if (e != LK_TOMB && i == uy) live[slot] = (stamp << 16) | uy;   // the union's row is written now
+            const unsigned bi2 = e >> 16;
+            ax[u] = on ? D[bi2 > fx ? i * un + ux : xrow + i] : 0.0;
+            ay[u] = on ? D[bi2 > fy ? i * un + uy : yrow + i] : 0.0;
+            sz[u] = on ? sizes[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) {
+            if (sz[u] == 0) continue;
+            const unsigned i = live[s0 + u * THREADS] & 0xffffu;            // (this thread's own slot, re-read)
+            D[yrow + i] = lk_new_dist<METHOD>(ax[u], ay[u], dmin, nx, ny, sz[u]);
+        }
+    }
+}
+
+template <int METHOD, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+lk_nn_chain_list_kernel(double* __restrict__ Dall, long long d_stride, int n, double* __restrict__ Zall) {
+    LK_DYNAMIC_SMEM(lk_size);
+    __shared__ LkKey s_warp[THREADS / 32];
+    __shared__ int s_x, s_y, s_len, s_merge, s_first;
+    __shared__ double s_min, s_dp;
+    __shared__ int s_cnt[THREADS];
+    __shared__ int s_wtot[THREADS / 32];
+    double* D = Dall + (size_t)blockIdx.x * d_stride;
+    int* chain = lk_size + n;
+    int* fresh = chain + n;
+    unsigned* live = reinterpret_cast<unsigned*>(fresh + n);
+    double* Z = Zall + (size_t)blockIdx.x * (size_t)(n > 1 ? n - 1 : 0) * 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned un = (unsigned)n;
+    LK_KEEP_PTR(D);
+    LK_KEEP_U32(un);
+    for (int i = tid; i < n; i += THREADS) {
+        lk_size[i] = 1;
+        fresh[i] = 0;
+        live[i] = (unsigned)i;                        // born 0
+        D[(size_t)i * un + i] = INFINITY;             // a cluster is never its own neighbour: no `i != x` in the scan
+    }
+    int len = n, dead = 0;                            // list length and tombstones in it (uniform over the block)
+    if (tid == 0) { s_len = 0; s_first = 0; }
+    __syncthreads();
+    for (int k = 0; k < n - 1; ++k) {
+        if (tid == 0 && s_len == 0) {
+            int f = s_first;
+            while (lk_size[f] == 0) ++f;              // lowest-numbered live cluster (dead ones never come back)
+            s_first = f;
+            chain[0] = f;
+            s_len = 1;
+        }
+        __syncthreads();
+        // grow the chain until its two top elements are mutual nearest neighbours
+        while (true) {
+            const int clen = s_len;
+            const int x = chain[clen - 1];
+            const int prev = clen > 1 ? chain[clen - 2] : -1;
+            const unsigned ux = (unsigned)x, xrow = ux * un;
+            const unsigned fx = (unsigned)fresh[x];
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            {
+                const int per = (len + THREADS - 1) / THREADS;       // uniform over the block
+                if (per > 7) lk_list_scan<10, THREADS>(D, live, len, tid, un, ux, xrow, fx, prev, &s_dp, bd, bi);
+                else if (per > 5) lk_list_scan<7, THREADS>(D, live, len, tid, un, ux, xrow, fx, prev, &s_dp, bd, bi);
+                else if (per > 3) lk_list_scan<5, THREADS>(D, live, len, tid, un, ux, xrow, fx, prev, &s_dp, bd, bi);
+                else if (per > 2) lk_list_scan<3, THREADS>(D, live, len, tid, un, ux, xrow, fx, prev, &s_dp, bd, bi);
+                else if (per > 1) lk_list_scan<2, THREADS>(D, live, len, tid, un, ux, xrow, fx, prev, &s_dp, bd, bi);
+                else lk_list_scan<1, THREADS>(D, live, len, tid, un, ux, xrow, fx, prev, &s_dp, bd, bi);
+            }
+            LkKey best = lk_warp_min(lk_key(bd, bi));
+            if (lane == 0) s_warp[warp] = best;
+            __syncthreads();
+            if (warp == 0) {
+                best = lane < THREADS / 32 ? s_warp[lane] : LkKey{0xffffffffu, 0xffffffffu, 0x7fffffff};
+                best = lk_warp_min(best);
+                if (lane == 0) {
+                    // the previous chain element is the incumbent: a scanned cluster replaces it only if strictly closer
+                    int y = best.i;
+                    double cur = lk_key_value(best.hi, best.lo);
+                    const bool none = best.hi == 0xffffffffu && best.lo == 0xffffffffu;   // nothing comparable (all NaN)
+                    if (none) { y = 0x7fffffff; cur = INFINITY; }
+                    if (prev >= 0) {
+                        const double dp = s_dp;
+                        if (!(cur < dp)) { y = prev; cur = dp; }
+                    } else if (y == 0x7fffffff) {
+                        y = 0;                        // every distance NaN: scipy keeps its stale y; unreachable for cleaned matrices
+                    }
+                    if (prev >= 0 && y == prev) {
+                        s_merge = 1;
+                    } else {
+                        s_merge = 0;
+                        chain[clen] = y;
+                        s_len = clen + 1;
+                    }
+                    s_x = x; s_y = y; s_min = cur;
+                    fresh[x] = k;                     // k merges so far: every younger row has been read from its own side
+                }
+            }
+            __syncthreads();
+            if (s_merge) break;
+        }
+        // merge the two top elements
+        int x = s_x, y = s_y;
+        if (x > y) { const int t = x; x = y; y = t; }
+        const int nx = lk_size[x], ny = lk_size[y];
+        const double dmin = s_min;
+        const unsigned fx = (unsigned)fresh[x], fy = (unsigned)fresh[y];
+        const unsigned ux = (unsigned)x, uy = (unsigned)y;
+        __syncthreads();                              // everyone has read the sizes and s_* before they change
+        if (tid == 0) {
+            Z[(size_t)k * 4 + 0] = (double)x;
+            Z[(size_t)k * 4 + 1] = (double)y;
+            Z[(size_t)k * 4 + 2] = dmin;
+            Z[(size_t)k * 4 + 3] = (double)(nx + ny);
+            lk_size[x] = 0;                           // (the loop below reads the sizes of clusters other than x and y)
+            lk_size[y] = nx + ny;
+            fresh[y] = k + 1;                         // (read by others only after the barrier below)
+            s_len -= 2;
+        }
+        {
+            const int per = (len + THREADS - 1) / THREADS;
+            const unsigned stamp = (unsigned)(k + 1);
+            if (per > 3) lk_list_merge<METHOD, 5, THREADS>(D, live, lk_size, len, tid, un, ux, uy, fx, fy, stamp, dmin, nx, ny);
+            else if (per > 2) lk_list_merge<METHOD, 3, THREADS>(D, live, lk_size, len, tid, un, ux, uy, fx, fy, stamp, dmin, nx, ny);
+            else if (per > 1) lk_list_merge<METHOD, 2, THREADS>(D, live, lk_size, len, tid, un, ux, uy, fx, fy, stamp, dmin, nx, ny);
+            else lk_list_merge<METHOD, 1, THREADS>(D, live, lk_size, len, tid, un, ux, uy, fx, fy, stamp, dmin, nx, ny);
+        }
+        ++dead;
+        // compaction of the live list (every thread takes the same decision: len and dead are uniform)
+        if (dead >= 32 && dead * 8 >= len) {
+            __syncthreads();                          // this merge's tombstone is in the list
+            const int per = (len + THREADS - 1) / THREADS;
+            const int start = tid * per;
+            unsigned e[LK_LIST_PER];
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < LK_LIST_PER; ++j) {
+                e[j] = (j < per && start + j < len) ? live[start + j] : LK_TOMB;
+                cnt += e[j] != LK_TOMB;
+            }
+            s_cnt[tid] = cnt;
+            __syncthreads();                          // every piece is in registers; the counts are visible
+            int off = 0;
+            for (int l = 0; l < lane; ++l) off += s_cnt[(warp << 5) + l];
+            if (lane == 31) s_wtot[warp] = off + cnt;
+            __syncthreads();
+            for (int w = 0; w < warp; ++w) off += s_wtot[w];
+#pragma unroll
+            for (int j = 0; j < LK_LIST_PER; ++j)
+                if (e[j] != LK_TOMB) live[off++] = e[j];
+            len -= dead;
+            dead = 0;
+        }
+        __syncthreads();
+    }
+}
+
 // Method "single": mst_single_linkage of scipy/cluster/_hierarchy.pyx -- Prim's minimum spanning tree from node 0; per
 // step the row of the newest tree node lowers the running distances of the others, the closest (lowest index on
 // ties: upward scan, strict `<`) joins.  Dynamic shared memory: n ints (merged flags) + n doubles (running distances).

@@ -560,6 +560,32 @@ def test_device_linkage_equals_scipy(eng, n, kind, method):
     assert np.array_equal(eng.linkage(A, method), ref, equal_nan=True)
 
 
+@pytest.mark.parametrize("method", ["average", "ward", "complete"])
+@pytest.mark.parametrize("n,kind", [(513, "ties"), (1500, "blocks"), (2300, "random")])
+def test_device_linkage_kernel_variants_agree(eng, monkeypatch, n, kind, method):
+    """The three chain kernels -- eager column updates (trees too large for the shared-memory stamps), lazy columns, lazy
+    columns + live list (the default) -- give the same bit-identical linkage matrix (GV2_LK_LAZY / GV2_LK_LIST are read at
+    every launch)."""
+    from scipy.cluster.hierarchy import linkage
+    rng = np.random.default_rng(n)
+    if kind == "ties":
+        D = rng.integers(1, 6, (n, n)) / 5.0
+    elif kind == "random":
+        D = rng.random((n, n))
+    else:
+        grp = rng.integers(0, 12, n)
+        D = np.where(grp[:, None] == grp[None, :], np.round(rng.random((n, n)) * 0.6, 3), 1.0)
+    D = np.triu(D, 1)
+    D = D + D.T
+    ref = linkage(D[np.triu_indices_from(D, k=1)], method=method)
+    for env in ({"GV2_LK_LAZY": "0"}, {"GV2_LK_LIST": "0"}, {}):
+        monkeypatch.delenv("GV2_LK_LAZY", raising=False)
+        monkeypatch.delenv("GV2_LK_LIST", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        assert np.array_equal(eng.linkage(D, method), ref), env
+
+
 @pytest.mark.parametrize("tag", ["A", "B"])
 def test_dist_mat_to_tree_golden(golden, eng, tag):
     """DistMat2Tree drop-in against the Newick string the unmodified reference printed for the same similarity matrix."""

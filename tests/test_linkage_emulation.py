@@ -68,13 +68,14 @@ def test_emulated_generic_linkage_kernel_equals_scipy(emul, kind, n, method):
     assert np.array_equal(_run(emul, method, D, False), ref, equal_nan=True)
 
 
-@pytest.mark.parametrize("lazy", [False, True])
+@pytest.mark.parametrize("lazy", [0, 1, 2])
 @pytest.mark.parametrize("method,kind,n", [("average", "ties", 3), ("average", "blocks", 200), ("average", "jaccard", 131),
                                            ("average", "line", 150), ("complete", "ties", 90), ("weighted", "random", 77),
-                                           ("ward", "euclid", 110), ("single", "ties", 140), ("single", "euclid", 65)])
+                                           ("ward", "euclid", 110), ("average", "blocks", 520), ("single", "ties", 140), ("single", "euclid", 65)])
 def test_emulated_chain_and_mst_kernels_equal_scipy(emul, method, kind, n, lazy):
-    """lk_nn_chain_kernel (eager and lazy column updates) and lk_mst_single_kernel: rows in merge order, then the stable sort
-    and union-find relabelling scipy applies (the library does them on the host: lk_finalize; here the oracle's restatement)."""
+    """lk_nn_chain_kernel (0: eager, 1: lazy column updates), lk_nn_chain_list_kernel (2: lazy + live list) and
+    lk_mst_single_kernel: rows in merge order, then the stable sort and union-find relabelling scipy applies (the library does
+    them on the host: lk_finalize; here the oracle's restatement)."""
     from scipy.cluster.hierarchy import linkage
     from oracle import linkage_oracle as L
     if method == "single" and lazy:
