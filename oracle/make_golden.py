@@ -309,8 +309,38 @@ def main_grouping():
     print("wrote reference_golden_grouping.npz", len(gold), "arrays")
 
 
+def main_linkage():
+    """next-1, every linkage method api_classes.py:123 allows: the UNMODIFIED DistMat2Tree (app/utils/dist_mat_to_tree.py:5-21)
+    on the distance matrices of the A / B fixtures (1 - S_PG, as dist_mat_constructor builds them) and on a block-structured
+    matrix with exact ties; centroid and median give non-monotone heights (negative branch lengths in the Newick string)."""
+    base = np.load(os.path.join(OUT, "reference_golden.npz"))
+    gold = {}
+    mats = {}
+    for tag in ("A", "B"):
+        D = 1 - base[f"{tag}_S_PG_p1"]
+        D[D < 0] = 0
+        mats[tag] = D
+    rng = np.random.default_rng(77)
+    grp = rng.integers(0, 5, 40)
+    T = np.where(grp[:, None] == grp[None, :], np.round(rng.random((40, 40)) * 0.5, 2), 1.0)
+    T = np.triu(T, 1)
+    mats["T"] = T + T.T
+    for tag, D in mats.items():
+        gold[f"{tag}_D"] = D
+        for method in ("single", "complete", "average", "weighted", "centroid", "median", "ward"):
+            for logscale in (False, True):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    nwk = DistMat2Tree(D.copy(), [f"v{i}" for i in range(len(D))], method, logscale)
+                gold[f"{tag}_{method}_{int(logscale)}"] = np.array(nwk)
+    np.savez_compressed(os.path.join(OUT, "reference_golden_linkage.npz"), **gold)
+    print("wrote reference_golden_linkage.npz", len(gold), "arrays")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "grouping":
+    if len(sys.argv) > 1 and sys.argv[1] == "linkage":
+        main_linkage()
+    elif len(sys.argv) > 1 and sys.argv[1] == "grouping":
         main_grouping()
     elif len(sys.argv) > 1 and sys.argv[1] == "classification":
         main_classification()

@@ -85,3 +85,58 @@ def test_emulated_chain_and_mst_kernels_equal_scipy(emul, method, kind, n, lazy)
     Z = raw[np.argsort(raw[:, 2], kind="mergesort")]
     L.label(Z, n)
     assert np.array_equal(Z, linkage(D[np.triu_indices(n, 1)], method))
+
+
+# ------------------------------------------ the whole dendrogram step against the UNMODIFIED reference, without a GPU
+@pytest.fixture(scope="module")
+def linkage_golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_linkage.npz"))
+
+
+def _native_newick(Z, names):
+    import ctypes as C
+    from gravity2_b200 import _lib
+    lib = _lib.load()
+    Z = np.ascontiguousarray(Z, dtype=np.float64)
+    n = Z.shape[0] + 1
+    arr = (C.c_char_p * n)(*[s.encode() for s in names])
+    ln = C.c_size_t(0)
+    assert lib.gv2_newick_from_linkage(Z.ctypes.data_as(C.c_void_p), n, arr, None, 0, C.byref(ln)) == 0
+    buf = C.create_string_buffer(ln.value + 1)
+    assert lib.gv2_newick_from_linkage(Z.ctypes.data_as(C.c_void_p), n, arr, buf, ln.value + 1, C.byref(ln)) == 0
+    return buf.value.decode()
+
+
+@pytest.mark.parametrize("method", ["single", "complete", "average", "weighted", "centroid", "median", "ward"])
+@pytest.mark.parametrize("tag", ["A", "B", "T"])
+def test_oracle_dendrogram_equals_reference_dist_mat_to_tree(linkage_golden, tag, method):
+    """oracle.dist_mat_to_tree (what the GPU tests compare DistMat2Tree / bootstrap_newick with) == the Newick string the
+    UNMODIFIED app/utils/dist_mat_to_tree.py:5-21 printed, for all seven linkage methods, plain and log-scaled
+    (oracle/make_golden.py linkage)."""
+    from oracle import gravity_oracle as O
+    D = linkage_golden[f"{tag}_D"]
+    names = [f"v{i}" for i in range(len(D))]
+    for logscale in (False, True):
+        with np.errstate(all="ignore"):
+            assert O.dist_mat_to_tree(D.copy(), names, method, logscale) == str(linkage_golden[f"{tag}_{method}_{int(logscale)}"])
+
+
+@pytest.mark.parametrize("method", ["single", "complete", "average", "weighted", "centroid", "median", "ward"])
+@pytest.mark.parametrize("tag", ["A", "T"])
+def test_emulated_kernel_and_native_printer_equal_reference_newick(emul, linkage_golden, tag, method):
+    """The device kernel's source run on host threads (the default variant of each method), the host-side sort + relabelling
+    scipy applies to chain / spanning-tree rows, and the library's own Newick printer (gv2_newick_from_linkage: host code of
+    libgravity_b200.so) against the string the unmodified reference printed."""
+    from oracle import linkage_oracle as L
+    D = linkage_golden[f"{tag}_D"]
+    n = len(D)
+    names = [f"v{i}" for i in range(n)]
+    for logscale in (False, True):
+        M = 10 ** D if logscale else D
+        raw = _run(emul, method, M, 0 if method in ("single", "centroid", "median") else 2)
+        if method in ("centroid", "median"):
+            Z = raw
+        else:
+            Z = raw[np.argsort(raw[:, 2], kind="mergesort")]
+            L.label(Z, n)
+        assert _native_newick(Z, names) == str(linkage_golden[f"{tag}_{method}_{int(logscale)}"])
