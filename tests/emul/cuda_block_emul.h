@@ -1,4 +1,5 @@
-// One CUDA thread block on host threads: enough of the CUDA surface for gravity2_b200/csrc/linkage_kernels.cuh to compile
+// One CUDA thread block on host threads: enough of the CUDA surface for gravity2_b200/csrc/linkage_kernels.cuh and
+// popc_kernels.cuh to compile
 // with g++ and run as written -- one OS thread per CUDA thread, a barrier for __syncthreads, per-warp barriers for the
 // warp reductions.  TEST INFRASTRUCTURE: lets the CPU test suite check a kernel's LOGIC (barrier placement, shared-memory
 // hand-overs, tie order) against scipy where there is no GPU; the product path never sees this file.
@@ -19,10 +20,15 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __host__
+#define __align__(x) alignas(x)
 
 struct EmuDim { int x = 0, y = 0, z = 0; };
 static thread_local EmuDim threadIdx;
+static thread_local int emu_linear_tid;               // threadIdx.x + blockDim.x * threadIdx.y: warps are 32 consecutive
 static EmuDim blockIdx;
+static EmuDim blockDim{1, 1, 1}, gridDim{1, 1, 1};
+struct uint4 { unsigned x, y, z, w; };
 
 class EmuBarrier {
   public:
@@ -47,8 +53,8 @@ static std::vector<EmuWarp>* emu_warps;
 
 static inline void __syncthreads() { emu_block_barrier.wait(); }
 static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
-    EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
-    w.slot[threadIdx.x & 31] = v;
+    EmuWarp& w = (*emu_warps)[emu_linear_tid >> 5];
+    w.slot[emu_linear_tid & 31] = v;
     w.bar.wait();
     unsigned m = w.slot[0];
     for (int l = 1; l < 32; ++l) m = w.slot[l] < m ? w.slot[l] : m;
@@ -58,14 +64,24 @@ static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
 template <class T>
 static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
-    EmuWarp& w = (*emu_warps)[threadIdx.x >> 5];
-    memcpy(&w.wide[threadIdx.x & 31], &v, sizeof(T));
+    EmuWarp& w = (*emu_warps)[emu_linear_tid >> 5];
+    memcpy(&w.wide[emu_linear_tid & 31], &v, sizeof(T));
     w.bar.wait();
     T r;
-    memcpy(&r, &w.wide[(threadIdx.x & 31) ^ lane_mask], sizeof(T));
+    memcpy(&r, &w.wide[(emu_linear_tid & 31) ^ lane_mask], sizeof(T));
     w.bar.wait();
     return r;
 }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    EmuWarp& w = (*emu_warps)[emu_linear_tid >> 5];
+    w.slot[emu_linear_tid & 31] = pred ? 1u : 0u;
+    w.bar.wait();
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= w.slot[l] << l;
+    w.bar.wait();
+    return m;
+}
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <class T>
 static inline T __ldcs(const T* p) { return *p; }
 static inline long long __double_as_longlong(double d) { long long b; memcpy(&b, &d, 8); return b; }
@@ -86,8 +102,27 @@ static void emu_launch_block(int threads, F&& body) {
     std::vector<EmuWarp> warps((size_t)(threads + 31) / 32);
     emu_warps = &warps;
     emu_block_barrier.reset(threads);
+    if (blockDim.x * blockDim.y * blockDim.z != threads) blockDim = EmuDim{threads, 1, 1};
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; ++t)
-        pool.emplace_back([&, t] { threadIdx.x = t; body(); });
+        pool.emplace_back([&, t] {
+            emu_linear_tid = t;
+            threadIdx.x = t % blockDim.x;
+            threadIdx.y = (t / blockDim.x) % blockDim.y;
+            threadIdx.z = t / (blockDim.x * blockDim.y);
+            body();
+        });
     for (auto& th : pool) th.join();
+}
+
+// A grid, one block after the other (blocks of a launch do not communicate).  A kernel may `return` from some threads before
+// a later __syncthreads only if the whole block does (as on the GPU).
+template <class F>
+static void emu_launch_grid(int blocks, EmuDim block, F&& body) {
+    gridDim = EmuDim{blocks, 1, 1};
+    blockDim = block;
+    for (int b = 0; b < blocks; ++b) {
+        blockIdx.x = b;
+        emu_launch_block(block.x * block.y * block.z, body);
+    }
 }
