@@ -1,7 +1,7 @@
 // The presence / absence kernels (pack, all-pairs AND + POPC tiles, tile unpacking).  popc_kernels.cu includes this file; so
 // does tests/emul/popc_emul.cpp, which runs the SAME kernel source on host threads (cuda_block_emul.h) so that the kernels'
 // logic -- tile coordinates, ragged edges, the stage ring, the mirror through shared memory -- is checked against the
-// oracle where there is no GPU.
+// CPU restatement of the reference where there is no GPU.
 #pragma once
 #ifndef GV2_TILE
 #define GV2_TILE 128
