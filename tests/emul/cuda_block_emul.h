@@ -93,6 +93,7 @@ static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; 
 static inline double __dsqrt_rn(double a) { return sqrt(a); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 
 // dynamic shared memory of the one emulated block
 alignas(16) static unsigned char emu_dynamic_smem[256 * 1024];
@@ -118,11 +119,15 @@ static void emu_launch_block(int threads, F&& body) {
 // A grid, one block after the other (blocks of a launch do not communicate).  A kernel may `return` from some threads before
 // a later __syncthreads only if the whole block does (as on the GPU).
 template <class F>
-static void emu_launch_grid(int blocks, EmuDim block, F&& body) {
-    gridDim = EmuDim{blocks, 1, 1};
+static void emu_launch_grid(EmuDim grid, EmuDim block, F&& body) {
+    gridDim = EmuDim{grid.x, grid.y > 0 ? grid.y : 1, 1};
     blockDim = block;
-    for (int b = 0; b < blocks; ++b) {
-        blockIdx.x = b;
-        emu_launch_block(block.x * block.y * block.z, body);
-    }
+    for (int by = 0; by < gridDim.y; ++by)
+        for (int bx = 0; bx < gridDim.x; ++bx) {
+            blockIdx.x = bx;
+            blockIdx.y = by;
+            emu_launch_block(block.x * block.y * block.z, body);
+        }
 }
+template <class F>
+static void emu_launch_grid(int blocks, EmuDim block, F&& body) { emu_launch_grid(EmuDim{blocks, 1, 1}, block, body); }
