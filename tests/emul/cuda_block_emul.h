@@ -1,5 +1,5 @@
 // One CUDA thread block on host threads: enough of the CUDA surface for gravity2_b200/csrc/linkage_kernels.cuh and
-// popc_kernels.cuh to compile
+// popc_kernels.cuh, gj_kernels.cuh ... to compile
 // with g++ and run as written -- one OS thread per CUDA thread, a barrier for __syncthreads, per-warp barriers for the
 // warp reductions.  TEST INFRASTRUCTURE: lets the CPU test suite check a kernel's LOGIC (barrier placement, shared-memory
 // hand-overs, tie order) against scipy where there is no GPU; the product path never sees this file.
@@ -29,6 +29,14 @@ static thread_local int emu_linear_tid;               // threadIdx.x + blockDim.
 static EmuDim blockIdx;
 static EmuDim blockDim{1, 1, 1}, gridDim{1, 1, 1};
 struct uint4 { unsigned x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float __frcp_rn(float x) { return 1.0f / x; }
 
 class EmuBarrier {
   public:
@@ -94,6 +102,18 @@ static inline double __dsqrt_rn(double a) { return sqrt(a); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline double atomicAdd(double* p, double v) {              // (one thread per address in the kernels that use it)
+    static std::mutex m;
+    std::lock_guard<std::mutex> g(m);
+    const double old = *p;
+    *p = old + v;
+    return old;
+}
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
 
 // dynamic shared memory of the one emulated block
 alignas(16) static unsigned char emu_dynamic_smem[256 * 1024];
@@ -120,14 +140,16 @@ static void emu_launch_block(int threads, F&& body) {
 // a later __syncthreads only if the whole block does (as on the GPU).
 template <class F>
 static void emu_launch_grid(EmuDim grid, EmuDim block, F&& body) {
-    gridDim = EmuDim{grid.x, grid.y > 0 ? grid.y : 1, 1};
+    gridDim = EmuDim{grid.x, grid.y > 0 ? grid.y : 1, grid.z > 0 ? grid.z : 1};
     blockDim = block;
-    for (int by = 0; by < gridDim.y; ++by)
-        for (int bx = 0; bx < gridDim.x; ++bx) {
-            blockIdx.x = bx;
-            blockIdx.y = by;
-            emu_launch_block(block.x * block.y * block.z, body);
-        }
+    for (int bz = 0; bz < gridDim.z; ++bz)
+        for (int by = 0; by < gridDim.y; ++by)
+            for (int bx = 0; bx < gridDim.x; ++bx) {
+                blockIdx.x = bx;
+                blockIdx.y = by;
+                blockIdx.z = bz;
+                emu_launch_block(block.x * block.y * block.z, body);
+            }
 }
 template <class F>
 static void emu_launch_grid(int blocks, EmuDim block, F&& body) { emu_launch_grid(EmuDim{blocks, 1, 1}, block, body); }
