@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -118,22 +119,59 @@ static inline unsigned long long atomicMax(unsigned long long* p, unsigned long 
 // dynamic shared memory of the one emulated block
 alignas(16) static unsigned char emu_dynamic_smem[256 * 1024];
 
+// Worker threads are kept between blocks (a grid of a few hundred 256-thread blocks would otherwise spend its time in
+// pthread_create): workers wait at `start`, run the block body as CUDA thread t, meet at `done`.
+struct EmuPool {
+    int size = 0;
+    std::vector<std::thread> workers;
+    std::function<void()> body;
+    EmuBarrier start{1}, done{1};
+    bool quit = false;
+    void resize(int n) {
+        stop();
+        size = n;
+        quit = false;
+        start.reset(n + 1);
+        done.reset(n + 1);
+        for (int t = 0; t < n; ++t)
+            workers.emplace_back([this, t] {
+                for (;;) {
+                    start.wait();
+                    if (quit) return;
+                    emu_linear_tid = t;
+                    threadIdx.x = t % blockDim.x;
+                    threadIdx.y = (t / blockDim.x) % blockDim.y;
+                    threadIdx.z = t / (blockDim.x * blockDim.y);
+                    body();
+                    done.wait();
+                }
+            });
+    }
+    void stop() {
+        if (workers.empty()) return;
+        quit = true;
+        start.wait();
+        for (auto& w : workers) w.join();
+        workers.clear();
+        size = 0;
+    }
+    ~EmuPool() { stop(); }
+};
+static EmuPool emu_pool;
+static std::vector<EmuWarp> emu_warp_store;
+
 template <class F>
 static void emu_launch_block(int threads, F&& body) {
-    std::vector<EmuWarp> warps((size_t)(threads + 31) / 32);
-    emu_warps = &warps;
-    emu_block_barrier.reset(threads);
     if (blockDim.x * blockDim.y * blockDim.z != threads) blockDim = EmuDim{threads, 1, 1};
-    std::vector<std::thread> pool;
-    for (int t = 0; t < threads; ++t)
-        pool.emplace_back([&, t] {
-            emu_linear_tid = t;
-            threadIdx.x = t % blockDim.x;
-            threadIdx.y = (t / blockDim.x) % blockDim.y;
-            threadIdx.z = t / (blockDim.x * blockDim.y);
-            body();
-        });
-    for (auto& th : pool) th.join();
+    if (emu_pool.size != threads) {
+        emu_pool.resize(threads);
+        emu_warp_store = std::vector<EmuWarp>((size_t)(threads + 31) / 32);
+        emu_warps = &emu_warp_store;
+        emu_block_barrier.reset(threads);
+    }
+    emu_pool.body = [&] { body(); };
+    emu_pool.start.wait();
+    emu_pool.done.wait();
 }
 
 // A grid, one block after the other (blocks of a launch do not communicate).  A kernel may `return` from some threads before
