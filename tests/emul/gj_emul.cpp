@@ -5,6 +5,8 @@
 //        < sig (n*p f64) [if p > 0], gom (n*g f64) [if g > 0], aux (n*n f64) [schemes R, RG, PR, L, PL]   > out (n*n f64)
 //   gj_emul fused <n> <p> <g> <fixed> <power> <out_kind>      (p == 0: scheme G, else PG)
 //        < sig (n*p f64) [if p > 0], gom (n*g f64)                                                       > out (n*n f64)
+//   gj_emul nbhd <n> <p> <weight> <thr> <with_mul>            (gv2_similarity_nbhd_host)
+//        < sig (n*p f64), classes (n*p u8), mul (n*n f64) [if with_mul]                                    > out (n*n f64)
 #define GJ_EMULATED
 #include "cuda_block_emul.h"
 #include <stdio.h>
@@ -15,6 +17,7 @@
 
 #include "../../include/gravity2_b200.h"
 #include "../../gravity2_b200/csrc/gj_kernels.cuh"
+#include "../../gravity2_b200/csrc/nbhd_kernels.cuh"
 
 static long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 static bool read_all(std::vector<double>& v) { return v.empty() || fread(v.data(), 8, v.size(), stdin) == v.size(); }
@@ -127,6 +130,22 @@ int main(int argc, char** argv) {
                 case 6: gj_fused_kernel<true, true, false>(tab, 0, (int)g_pad, nkb, k_groups, (int)nt, fz, 1u); break;
                 default: gj_fused_kernel<true, true, true>(tab, 0, (int)g_pad, nkb, k_groups, (int)nt, fz, 1u); break;
             }
+        });
+        fwrite(out.data(), 8, out.size(), stdout);
+        return 0;
+    }
+    if (what == "nbhd" && argc == 7) {
+        const long long n = atoll(argv[2]), p = atoll(argv[3]);
+        const double w = atof(argv[4]), thr = atof(argv[5]);
+        const int with_mul = atoi(argv[6]);
+        std::vector<double> sig((size_t)n * p), mul(with_mul ? (size_t)n * n : 0), out((size_t)n * n, -5.0);
+        std::vector<uint8_t> cls((size_t)n * p);
+        if (!read_all(sig)) return 3;
+        if (!cls.empty() && fread(cls.data(), 1, cls.size(), stdin) != cls.size()) return 3;
+        if (!read_all(mul)) return 3;
+        const int nt = (int)((n + NB_T - 1) / NB_T);
+        emu_launch_grid(EmuDim{nt, nt, 1}, EmuDim{NB_T * NB_T, 1, 1}, [&] {
+            gj_nbhd_kernel(sig.data(), cls.data(), n, p, p, w, thr, with_mul ? mul.data() : nullptr, out.data());
         });
         fwrite(out.data(), 8, out.size(), stdout);
         return 0;

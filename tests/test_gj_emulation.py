@@ -126,3 +126,38 @@ def test_emulated_fused_tail_vs_oracle(emul, fixed, with_p, power, out_kind):
     assert np.array_equal(S, S.T)
     if fixed and not with_p:      # (the PPHMM sums of this driver come from the fp32 tile kernel; the job's are exact integers)
         assert S[3, 40] == (0.0 if out_kind else 1.0)
+
+
+# ------------------------------------------------------- a2: PphmmNeighbourhoodWeight != 0 (quirk Q1), reference goldens
+def nbhd(emul, sig, cls, w, thr, mul=None):
+    n, p = sig.shape
+    blob = np.ascontiguousarray(sig, dtype=np.float64).tobytes() + np.ascontiguousarray(cls, dtype=np.uint8).tobytes()
+    if mul is not None:
+        blob += np.ascontiguousarray(mul, dtype=np.float64).tobytes()
+    out = subprocess.run([emul, "nbhd", str(n), str(p), repr(float(w)), repr(float(thr)), str(int(mul is not None))], input=blob,
+                         capture_output=True, timeout=900)
+    assert out.returncode == 0, out.stderr
+    return np.frombuffer(out.stdout, dtype=np.float64).reshape(n, n)
+
+
+@pytest.mark.parametrize("tag", ["C", "D"])
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_emulated_neighbourhood_kernel_equals_reference_golden(emul, tag, case, tmp_path):
+    """gj_nbhd_kernel + the ordinary combine, wired as the drop-in wires them (dropin.SimilarityMat_Constructor): the
+    visit-count dependent in-place row scaling of the reference, first and second call on the same (mutated) table, against
+    the outputs of the unmodified reference (reference_golden_neighbourhood.npz)."""
+    from conftest import write_reference_csvs
+    from gravity2_b200 import neighbourhood as NB
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden_neighbourhood.npz"))
+    w, thr, pw = (float(x) for x in g[f"{tag}_case{case}"])
+    scheme = str(g[f"{tag}_case{case}_scheme"])
+    sig = g[f"{tag}_sig"].copy()
+    gom = g[f"{tag}_gom"]
+    fn = write_reference_csvs(str(tmp_path), g[f"{tag}_sig"], g[f"{tag}_naive_loc"])
+    cls = NB.neighbourhood_classes(*NB.read_neighbourhood_csvs(fn))
+    for key in ("S", "S_second_call"):
+        gjp = nbhd(emul, sig, cls, w, thr)
+        S = similarity(emul, np.zeros((len(sig), 0)), gom, gjp, {"P": "R", "PG": "RG"}[scheme], power=pw)
+        close(S, g[f"{tag}_case{case}_{key}"])
+        NB.apply_in_place(sig, cls, w, thr, len(sig) + 1)            # what the reference leaves in the caller's table
+    assert np.array_equal(sig, g[f"{tag}_case{case}_sig_after_two_calls"])
