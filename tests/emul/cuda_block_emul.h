@@ -30,11 +30,33 @@ static thread_local int emu_linear_tid;               // threadIdx.x + blockDim.
 static EmuDim blockIdx;
 static EmuDim blockDim{1, 1, 1}, gridDim{1, 1, 1};
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+struct alignas(16) double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned long long min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline unsigned long long __double2ull_rn(double x) { return (unsigned long long)rint(x); }
+// PRMT: byte i of the result is byte (selector nibble i) of the eight bytes {y : x}
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const unsigned long long v = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+    return r;
+}
+// IDP.4A, unsigned operands
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+    for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff);
+    return c;
+}
+template <class T>
+static inline T __ldg(const T* p) { return *p; }
+template <class T>
+static inline void __stcs(T* p, T v) { *p = v; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
@@ -81,6 +103,39 @@ static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     w.bar.wait();
     return r;
 }
+static inline void __syncwarp() { (*emu_warps)[emu_linear_tid >> 5].bar.wait(); }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    EmuWarp& w = (*emu_warps)[emu_linear_tid >> 5];
+    memcpy(&w.wide[emu_linear_tid & 31], &v, sizeof(T));
+    w.bar.wait();
+    T r;
+    memcpy(&r, &w.wide[src_lane & 31], sizeof(T));
+    w.bar.wait();
+    return r;
+}
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int delta, int width = 32) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    EmuWarp& w = (*emu_warps)[emu_linear_tid >> 5];
+    const int lane = emu_linear_tid & 31;
+    memcpy(&w.wide[lane], &v, sizeof(T));
+    w.bar.wait();
+    T r = v;
+    if ((lane % width) >= delta) memcpy(&r, &w.wide[lane - delta], sizeof(T));
+    w.bar.wait();
+    return r;
+}
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    EmuWarp& w = (*emu_warps)[emu_linear_tid >> 5];
+    w.slot[emu_linear_tid & 31] = v;
+    w.bar.wait();
+    unsigned s = 0;
+    for (int l = 0; l < 32; ++l) s += w.slot[l];
+    w.bar.wait();
+    return s;
+}
 static inline unsigned __ballot_sync(unsigned, int pred) {
     EmuWarp& w = (*emu_warps)[emu_linear_tid >> 5];
     w.slot[emu_linear_tid & 31] = pred ? 1u : 0u;
@@ -110,6 +165,8 @@ static inline double atomicAdd(double* p, double v) {              // (one threa
     *p = old + v;
     return old;
 }
+static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
     while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
