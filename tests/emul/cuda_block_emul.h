@@ -22,7 +22,7 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __host__
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 
 struct EmuDim { int x = 0, y = 0, z = 0; };
 static thread_local EmuDim threadIdx;
@@ -83,6 +83,17 @@ struct EmuWarp { EmuBarrier bar{32}; unsigned slot[32]; unsigned long long wide[
 static std::vector<EmuWarp>* emu_warps;
 
 static inline void __syncthreads() { emu_block_barrier.wait(); }
+static int emu_block_count;
+static inline int __syncthreads_count(int pred) {
+    emu_block_barrier.wait();
+    if (emu_linear_tid == 0) emu_block_count = 0;
+    emu_block_barrier.wait();
+    if (pred) __atomic_fetch_add(&emu_block_count, 1, __ATOMIC_SEQ_CST);
+    emu_block_barrier.wait();
+    const int r = emu_block_count;
+    emu_block_barrier.wait();
+    return r;
+}
 static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
     EmuWarp& w = (*emu_warps)[emu_linear_tid >> 5];
     w.slot[emu_linear_tid & 31] = v;
