@@ -5,6 +5,9 @@
 //        < sig (n*p f64) [if p > 0], gom (n*g f64) [if g > 0], aux (n*n f64) [schemes R, RG, PR, L, PL]   > out (n*n f64)
 //   gj_emul fused <n> <p> <g> <fixed> <power> <out_kind>      (p == 0: scheme G, else PG)
 //        < sig (n*p f64) [if p > 0], gom (n*g f64)                                                       > out (n*n f64)
+//   gj_emul job_tail <n> <g> <nb> <p_scale> <power> <out_kind>   (the fused tail as the bootstrap job runs it: api.cu replicates_impl)
+//        < PPHMM pair sums (nb * tiles * 128*128 f64, gj_ws_index layout), their row sums (nb*n f64), GOM tables (nb*n*g f64)
+//        > out (nb * n*n f64)
 //   gj_emul nbhd <n> <p> <weight> <thr> <with_mul>            (gv2_similarity_nbhd_host)
 //        < sig (n*p f64), classes (n*p u8), mul (n*n f64) [if with_mul]                                    > out (n*n f64)
 #define GJ_EMULATED
@@ -130,6 +133,38 @@ int main(int argc, char** argv) {
                 case 6: gj_fused_kernel<true, true, false>(tab, 0, (int)g_pad, nkb, k_groups, (int)nt, fz, 1u); break;
                 default: gj_fused_kernel<true, true, true>(tab, 0, (int)g_pad, nkb, k_groups, (int)nt, fz, 1u); break;
             }
+        });
+        fwrite(out.data(), 8, out.size(), stdout);
+        return 0;
+    }
+    if (what == "job_tail" && argc == 8) {
+        const long long n = atoll(argv[2]), g = atoll(argv[3]), nb = atoll(argv[4]);
+        const double p_scale = atof(argv[5]), power = atof(argv[6]);
+        const int out_kind = atoi(argv[7]);
+        const long long n_pad = round_up(n, GV2_TILE), nt = n_pad / GV2_TILE, ntl = nt * (nt + 1) / 2;
+        const long long g_pad = round_up(std::max<long long>(g, 1), GV2_BK);
+        std::vector<double> ws((size_t)nb * ntl * GV2_TILE * GV2_TILE), prs((size_t)nb * n), gom((size_t)nb * n * g), out((size_t)nb * n * n, -5.0);
+        if (!read_all(ws) || !read_all(prs) || !read_all(gom)) return 3;
+        // job_prepare_gom -> gom_quantize_launch: one scale for the whole launch
+        unsigned long long maxbits = 0;
+        std::vector<unsigned> qtab((size_t)nb * n_pad * g_pad, 0xffffffffu);
+        std::vector<double> grs((size_t)nb * n, -1.0);
+        std::vector<unsigned char> gnan((size_t)nb * n, 7);
+        emu_launch_grid(EmuDim{(int)n, (int)nb, 1}, EmuDim{128, 1, 1}, [&] { gom_rowmax_kernel(gom.data(), n, g, &maxbits); });
+        emu_launch_grid(EmuDim{(int)n_pad, (int)nb, 1}, EmuDim{128, 1, 1}, [&] {
+            gom_quantize_kernel(gom.data(), n, g, &maxbits, qtab.data(), n_pad, g_pad, grs.data(), gnan.data());
+        });
+        GjFuse fz{};
+        fz.P.ws = ws.data(); fz.P.rowsum = prs.data(); fz.P.nan = nullptr; fz.P.ksplit = 1;
+        fz.P.b_stride_ws = ntl * GV2_TILE * GV2_TILE; fz.P.b_stride_row = n;
+        fz.g_rowsum = grs.data(); fz.g_nan = gnan.data(); fz.g_stride_row = n; fz.g_stride_nan = n;
+        fz.n = n; fz.scheme = GV2_SCHEME_PG; fz.out_kind = out_kind; fz.pw = power; fz.out = out.data(); fz.out_b_stride = n * n;
+        fz.p_scale = p_scale;
+        const int k_groups = (int)((g + 3) / 4), nkb = (int)((g + GV2_BK - 1) / GV2_BK);
+        const float* tab = reinterpret_cast<const float*>(qtab.data());
+        emu_launch_grid(EmuDim{(int)(2 * ntl), 1, (int)nb}, EmuDim{GJ_THREADS, 1, 1}, [&] {
+            if (power != 1.0) gj_fused_kernel<true, true, true>(tab, n_pad * g_pad, (int)g_pad, nkb, k_groups, (int)nt, fz, 1u);
+            else gj_fused_kernel<true, true, false>(tab, n_pad * g_pad, (int)g_pad, nkb, k_groups, (int)nt, fz, 1u);
         });
         fwrite(out.data(), 8, out.size(), stdout);
         return 0;
