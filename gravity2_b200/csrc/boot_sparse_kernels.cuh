@@ -391,12 +391,12 @@ bs_lists_build_kernel(BsCsr csr, int nt, int k_pad, long long* __restrict__ rowt
 #define BSS_OUT_BYTES (BSS_OUT_PAIRS * BSS_OUT_LD * 8)
 #define BSS_WARP_BYTES (3 * BSS_LIST_BYTES + 2 * BSS_W_BYTES + BSS_OUT_BYTES)
 
-#ifdef BS_EMULATED             // tests/emul: the copies complete at once (the __syncwarp after every wait hands them to the warp)
-static inline void bss_cp_async8(void* smem, const void* gmem) { memcpy(smem, gmem, 8); }
-static inline void bss_cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
-static inline void bss_commit() {}
-static inline void bss_wait2() {}
-static inline void bss_wait1() {}
+#ifdef BS_EMULATED             // tests/emul: cp.async as cuda_block_emul.h models it (the __syncwarp after every wait hands the data to the warp)
+static inline void bss_cp_async8(void* smem, const void* gmem) { emu_cp_async(smem, gmem, 8); }
+static inline void bss_cp_async16(void* smem, const void* gmem) { emu_cp_async(smem, gmem, 16); }
+static inline void bss_commit() { emu_cp_commit(); }
+static inline void bss_wait2() { emu_cp_wait(2); }
+static inline void bss_wait1() { emu_cp_wait(1); }
 #else
 __device__ __forceinline__ void bss_cp_async8(void* smem, const void* gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);

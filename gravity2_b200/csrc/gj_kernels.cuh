@@ -29,11 +29,11 @@
 // ty+16m, columns tx+16n) read-modify-write 256 consecutive doubles per (m, n).
 __host__ __device__ inline int gj_ws_index(int r, int c) { return ((((r >> 4) << 3) + (c >> 4)) << 8) + ((r & 15) << 4) + (c & 15); }
 
-#ifdef GJ_EMULATED               // tests/emul: copies complete at once; approximate / PTX instructions restated
-static inline void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
-static inline void cp_async_commit() {}
+#ifdef GJ_EMULATED               // tests/emul: cp.async as cuda_block_emul.h models it; approximate / PTX instructions restated
+static inline void cp_async16(void* smem, const void* gmem) { emu_cp_async(smem, gmem, 16); }
+static inline void cp_async_commit() { emu_cp_commit(); }
 template <int N>
-static inline void cp_async_wait() {}
+static inline void cp_async_wait() { emu_cp_wait(N); }
 #define GJ_DYNAMIC_SMEM(name) float* name = reinterpret_cast<float*>(emu_dynamic_smem)
 #define GJ_PREFETCH_L2(ptr) (void)(ptr)
 #else

@@ -6,10 +6,10 @@
 #include <math.h>
 #include <stdint.h>
 
-#ifdef GOM_EMULATED            // tests/emul: the copies complete at once (the __syncwarp after the wait hands them to the warp)
-static inline void gom_cp_async8(void* smem, const void* gmem) { memcpy(smem, gmem, 8); }
-#define GOM_CP_COMMIT()
-#define GOM_CP_WAIT(n)
+#ifdef GOM_EMULATED            // tests/emul: cp.async as cuda_block_emul.h models it (the __syncwarp after the wait hands the data to the warp)
+static inline void gom_cp_async8(void* smem, const void* gmem) { emu_cp_async(smem, gmem, 8); }
+#define GOM_CP_COMMIT() emu_cp_commit()
+#define GOM_CP_WAIT(n) emu_cp_wait(n)
 #define GOM_DYNAMIC_SMEM(name) unsigned char* name = reinterpret_cast<unsigned char*>(emu_dynamic_smem)
 #else
 __device__ __forceinline__ void gom_cp_async8(void* smem, const void* gmem) {

@@ -12,10 +12,10 @@
 #define PC_LDS (PC_BK + 4)
 #define PC_STAGES 3
 
-#ifdef PC_EMULATED              // tests/emul: the copies complete at once, the group bookkeeping has nothing to wait for
-static inline void pc_cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
-#define PC_CP_COMMIT()
-#define PC_CP_WAIT(n)
+#ifdef PC_EMULATED              // tests/emul: cp.async as cuda_block_emul.h models it
+static inline void pc_cp_async16(void* smem, const void* gmem) { emu_cp_async(smem, gmem, 16); }
+#define PC_CP_COMMIT() emu_cp_commit()
+#define PC_CP_WAIT(n) emu_cp_wait(n)
 #define PC_DYNAMIC_SMEM(name) unsigned* name = reinterpret_cast<unsigned*>(emu_dynamic_smem)
 #else
 __device__ __forceinline__ void pc_cp_async16(void* smem, const void* gmem) {

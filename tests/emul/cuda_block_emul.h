@@ -6,6 +6,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -184,6 +185,36 @@ static inline unsigned long long atomicMax(unsigned long long* p, unsigned long 
     return old;
 }
 
+// cp.async, modelled at the two legal extremes (GV2_EMUL_CP_ASYNC, default "late"):
+//   late   a copy lands when the issuing thread executes the wait_group that covers it (or never, if the kernel forgets to
+//          wait): reading a stage before its wait -- a read-after-write hazard of the ring -- yields stale data and a wrong result;
+//   early  a copy lands at issue: prefetching into a stage other threads still read -- a write-after-read hazard -- is a data
+//          race ThreadSanitizer reports (tools/emul_tsan.py runs this mode).
+struct EmuCopy { void* dst; const void* src; int bytes; };
+static thread_local std::vector<std::vector<EmuCopy>> emu_cp_groups;   // committed groups, oldest first
+static thread_local std::vector<EmuCopy> emu_cp_open;                  // copies issued since the last commit
+static inline bool emu_cp_late() {
+    static const bool late = [] { const char* e = getenv("GV2_EMUL_CP_ASYNC"); return !(e && e[0] == 'e'); }();
+    return late;
+}
+static inline void emu_cp_async(void* dst, const void* src, int bytes) {
+    if (emu_cp_late()) emu_cp_open.push_back(EmuCopy{dst, src, bytes});
+    else memcpy(dst, src, (size_t)bytes);
+}
+static inline void emu_cp_commit() {
+    if (!emu_cp_late()) return;
+    emu_cp_groups.push_back(std::move(emu_cp_open));
+    emu_cp_open.clear();
+}
+static inline void emu_cp_wait(int keep) {                             // cp.async.wait_group keep
+    if (!emu_cp_late()) return;
+    while ((int)emu_cp_groups.size() > keep) {
+        for (const EmuCopy& c : emu_cp_groups.front()) memcpy(c.dst, c.src, (size_t)c.bytes);
+        emu_cp_groups.erase(emu_cp_groups.begin());
+    }
+}
+static inline void emu_cp_reset() { emu_cp_groups.clear(); emu_cp_open.clear(); }
+
 // dynamic shared memory of the one emulated block
 alignas(16) static unsigned char emu_dynamic_smem[256 * 1024];
 
@@ -210,6 +241,7 @@ struct EmuPool {
                     threadIdx.x = t % blockDim.x;
                     threadIdx.y = (t / blockDim.x) % blockDim.y;
                     threadIdx.z = t / (blockDim.x * blockDim.y);
+                    emu_cp_reset();
                     body();
                     done.wait();
                 }
