@@ -40,13 +40,16 @@ def to_double(hi, lo, quantum):
     return float(Fraction(hi) * Fraction(q_hi) + Fraction(float(lo) * quantum))
 
 
-@pytest.mark.parametrize("n,k,nb,density", [(140, 300, 3, 0.08), (140, 300, 10, 0.08), (130, 517, 40, 0.05), (40, 129, 1, 0.3),
+@pytest.mark.parametrize("n,k,nb,density", [(1, 1, 1, 1.0), (2, 3, 2, 0.9), (140, 300, 3, 0.08), (140, 300, 10, 0.08), (130, 517, 40, 0.05), (40, 129, 1, 0.3),
                                             (150, 260, 200, 0.06)])
 def test_emulated_sparse_pair_sums_are_exact(emul, n, k, nb, density):
     t = synth.make_tables(n, k, 5, density, seed=n + nb)
     tab = t.sig.copy()
-    tab[7] = 0.0                                                  # an empty genome
-    tab[3] = tab[min(n - 1, 35)]                                  # duplicates: pair sum == row sum exactly
+    if n > 8:
+        tab[7] = 0.0                                              # an empty genome
+        tab[3] = tab[min(n - 1, 35)]                              # duplicates: pair sum == row sum exactly
+    if tab.max() == 0.0:
+        tab[0, 0] = 1.5
     rng = np.random.default_rng(nb)
     if nb == 1:
         w = np.ones((1, k), dtype=np.int32)                       # the un-resampled table as the all-ones replicate
@@ -69,7 +72,7 @@ def test_emulated_sparse_pair_sums_are_exact(emul, n, k, nb, density):
     checked = 0
     pairs = [(i, j) for i in range(n) for j in range(i, n)]
     pick = rng.choice(len(pairs), size=min(len(pairs), 1500), replace=False)
-    must = [(3, min(n - 1, 35)), (7, 7), (7, 9), (0, 0), (n - 1, n - 1), (0, n - 1)]
+    must = [(3, min(n - 1, 35)), (7, 7), (7, 9), (0, 0), (n - 1, n - 1), (0, n - 1)] if n > 9 else [(0, 0), (0, n - 1)]
     for (i, j) in [pairs[q] for q in pick] + [(min(a, b), max(a, b)) for a, b in must]:
         tix = tiles.index((i // 128, j // 128))
         cell = ws_index(i % 128, j % 128)
@@ -79,8 +82,9 @@ def test_emulated_sparse_pair_sums_are_exact(emul, n, k, nb, density):
             assert ws[b, tix, cell] == expect, (i, j, b)
             checked += 1
     # duplicates: the pair sum IS the row sum of the replicate, so D = 0 exactly downstream
-    d = min(n - 1, 35)
-    tix, cell = tiles.index((0, 0)), ws_index(3, d)
-    for b in range(min(nb, 4)):
-        assert ws[b, tix, cell] == ws[b, tix, ws_index(3, 3)]
-    assert checked >= 800
+    if n > 8:
+        d = min(n - 1, 35)
+        tix, cell = tiles.index((0, 0)), ws_index(3, d)
+        for b in range(min(nb, 4)):
+            assert ws[b, tix, cell] == ws[b, tix, ws_index(3, 3)]
+    assert checked >= min(800, len(pairs))

@@ -161,3 +161,17 @@ def test_emulated_neighbourhood_kernel_equals_reference_golden(emul, tag, case, 
         close(S, g[f"{tag}_case{case}_{key}"])
         NB.apply_in_place(sig, cls, w, thr, len(sig) + 1)            # what the reference leaves in the caller's table
     assert np.array_equal(sig, g[f"{tag}_case{case}_sig_after_two_calls"])
+
+
+@pytest.mark.parametrize("n,p,g", [(1, 1, 1), (2, 1, 1), (129, 33, 33), (1, 40, 3)])
+def test_emulated_kernels_tiny_and_odd_shapes(emul, n, p, g):
+    """One genome, one column, one GOM; one row / column past a tile or stage boundary; all-zero tables."""
+    rng = np.random.default_rng(n * 100 + p)
+    sig = np.round(rng.gamma(2, 60, (n, p)), 1) * (rng.random((n, p)) < 0.6)
+    gom = rng.random((n, g)) * (rng.random((n, g)) < 0.8)
+    with np.errstate(all="ignore"):
+        ref = O.similarity_mat_fast(sig.copy(), gom, None, 0, "PG", 1.0)
+    close(similarity(emul, sig, gom, None, "PG", ksplit=2), ref, atol=1e-9)
+    close(fused(emul, sig, gom, 1), ref, rtol=2e-6, atol=1e-7)
+    assert np.all(similarity(emul, np.zeros((n, p)), None, None, "P") == 0.0)
+    assert np.all(fused(emul, np.zeros((n, p)), np.zeros((n, g)), 1) == 0.0)
