@@ -337,8 +337,50 @@ def main_linkage():
     print("wrote reference_golden_linkage.npz", len(gold), "arrays")
 
 
+def main_cfg1():
+    """BASELINE configs[0] at the shape of cli/example_run.py's run (20 genomes, 7 taxonomic groupings, 100 bootstrap
+    replicates; synthetic tables of gravity2_b200.synth cfg1 -- the example's hmmscan stage cannot run here): the base PG
+    matrix, then the UNMODIFIED PL1 loop body (app/src/pl1_graphs.py:78-117) for every replicate -- np.random.choice draw,
+    sig[:, idx] as signature AND location table (Q3), GOM database and table rebuilt, SimilarityMat_Constructor, 1 - S clamped,
+    DistMat2Tree(average) -- keeping every replicate's distance matrix and Newick string."""
+    from gravity2_b200.synth import CONFIGS, SEED_BASE
+    c = CONFIGS["cfg1"]
+    t = make_tables(c["n"], c["p"], c["g"], c["density"], SEED_BASE + 1)
+    sig, loc, n, p = t.sig, t.loc, c["n"], c["p"]
+    names = [f"v{i}" for i in range(n)]
+    gold = {"sig": sig, "loc": loc, "taxo": t.taxo, "gom_ids": np.array(t.gom_ids), "boot_seed": np.int64(SEED_BASE + 1)}
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = write_csvs(tmp, sig, loc)
+        db = GOMDB_Constructor(t.taxo, loc, t.gom_ids)
+        gom = ref_gom_table(loc, db, t.gom_ids)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            S = SimilarityMat_Constructor(sig.copy(), gom, loc, None, 0.0, 0, "PG", 1.0, fn)
+        D0 = 1 - np.array(S); D0[D0 < 0] = 0
+        gold["gom"], gold["D"] = gom, D0
+        gold["newick"] = np.array(DistMat2Tree(D0.copy(), names, "average", False))
+        np.random.seed(int(gold["boot_seed"]))
+        idxs, Ds, nwk = [], [], []
+        for _ in range(c["b"]):
+            idx = np.random.choice(list(range(p)), p, replace=True)
+            b_sig = sig[:, idx]; b_loc = sig[:, idx]
+            bdb = GOMDB_Constructor(t.taxo, b_loc, t.gom_ids)
+            bgom = ref_gom_table(b_loc, bdb, t.gom_ids)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                S = SimilarityMat_Constructor(b_sig, bgom, b_loc, None, 0.0, 0, "PG", 1.0, fn)
+            D = 1 - S; D[D < 0] = 0
+            idxs.append(idx); Ds.append(np.array(D))
+            nwk.append(DistMat2Tree(D.copy(), names, "average", False))
+    gold["pl1_idx"], gold["pl1_D"], gold["pl1_newick"] = np.array(idxs), np.array(Ds), np.array(nwk)
+    np.savez_compressed(os.path.join(OUT, "reference_golden_cfg1.npz"), **gold)
+    print("wrote reference_golden_cfg1.npz", len(gold), "arrays")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "linkage":
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        main_cfg1()
+    elif len(sys.argv) > 1 and sys.argv[1] == "linkage":
         main_linkage()
     elif len(sys.argv) > 1 and sys.argv[1] == "grouping":
         main_grouping()

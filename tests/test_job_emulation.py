@@ -41,11 +41,8 @@ def ws_index(r, c):
     return ((((r >> 4) << 3) + (c >> 4)) << 8) + ((r & 15) << 4) + (c & 15)
 
 
-@pytest.mark.parametrize("tag", ["A", "B"])
-def test_emulated_pl1_replicates_equal_reference_golden(exes, tag):
-    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
-    sig, taxo, ids = g[f"{tag}_sig"], g[f"{tag}_taxo"], [str(x) for x in g[f"{tag}_gom_ids"]]
-    idx, D_ref = g[f"{tag}_pl1_idx"], g[f"{tag}_pl1_D"]
+def emulated_pl1(exes, sig, taxo, ids, idx):
+    """Distance matrices (nb, n, n) of the PL1 replicates with resample indices idx (nb, p), stage by stage as the job runs them."""
     n, p = sig.shape
     G, nb = len(ids), len(idx)
     w = np.stack([np.bincount(i, minlength=p) for i in idx]).astype(np.int32)
@@ -64,11 +61,19 @@ def test_emulated_pl1_replicates_equal_reference_golden(exes, tag):
     ws = np.where(np.isnan(ws), 0.0, ws)                           # (blocks below the diagonal are never written, never read)
     # the fused tail, as the job runs it (p_scale: api.cu gv2_job_create)
     p_scale = math.ldexp(1.0, -math.frexp(sig.max() * 255.0 * p)[1])
-    D = run(exes["gj_emul"], ["job_tail", n, G, nb, repr(p_scale), 1.0, 1], ws.tobytes() + prs.tobytes() + gom.tobytes()).reshape(nb, n, n)
+    return run(exes["gj_emul"], ["job_tail", n, G, nb, repr(p_scale), 1.0, 1], ws.tobytes() + prs.tobytes() + gom.tobytes()).reshape(nb, n, n)
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_emulated_pl1_replicates_equal_reference_golden(exes, tag):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
+    sig, taxo, ids = g[f"{tag}_sig"], g[f"{tag}_taxo"], [str(x) for x in g[f"{tag}_gom_ids"]]
+    idx, D_ref = g[f"{tag}_pl1_idx"], g[f"{tag}_pl1_D"]
+    D = emulated_pl1(exes, sig, taxo, ids, idx)
     assert D.shape == D_ref.shape
     err = np.abs(D - D_ref)
     assert err.max() <= 1e-6, err.max()
-    for b in range(nb):
+    for b in range(len(idx)):
         assert np.array_equal(D[b], D[b].T)
 
 
