@@ -14,6 +14,26 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session")
+def emul_build(tmp_path_factory):
+    """build(name) -> path of tests/emul/<name>.cpp compiled with g++ (a kernel family's own source on host threads); each
+    program is built once per session, whichever test modules ask for it."""
+    import shutil
+    import subprocess
+    built = {}
+
+    def build(name):
+        if shutil.which("g++") is None:
+            pytest.skip("no host compiler")
+        if name not in built:
+            exe = str(tmp_path_factory.mktemp("emul") / name)
+            subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-o", exe,
+                            os.path.join(REPO, "tests", "emul", name + ".cpp")], check=True)
+            built[name] = exe
+        return built[name]
+    return build
+
+
+@pytest.fixture(scope="session")
 def golden():
     path = os.path.join(REPO, "tests", "golden", "reference_golden.npz")
     return dict(np.load(path, allow_pickle=False))

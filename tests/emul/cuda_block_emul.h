@@ -4,10 +4,14 @@
 // warp reductions.  TEST INFRASTRUCTURE: lets the CPU test suite check a kernel's LOGIC (barrier placement, shared-memory
 // hand-overs, tie order) against scipy where there is no GPU; the product path never sees this file.
 #pragma once
+#include <limits.h>
+#include <linux/futex.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -62,21 +66,27 @@ static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4);
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
 
+// Counter + generation word; waiters sleep on the generation with a futex.  (A mutex + condition variable here made every one
+// of up to 256 woken threads queue for the mutex again: three quarters of the CPU suite's time was spent in the kernel.)
 class EmuBarrier {
   public:
     explicit EmuBarrier(int count = 1) : count_(count) {}
-    void reset(int count) { count_ = count; waiting_ = 0; }
+    void reset(int count) { count_ = count; waiting_.store(0); }
     void wait() {
-        std::unique_lock<std::mutex> lk(m_);
-        const unsigned long gen = gen_;
-        if (++waiting_ == count_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
-        else cv_.wait(lk, [&] { return gen_ != gen; });
+        const unsigned gen = gen_.load(std::memory_order_acquire);
+        if (waiting_.fetch_add(1, std::memory_order_acq_rel) + 1 == count_) {
+            waiting_.store(0, std::memory_order_relaxed);         // before the release below: nobody re-enters until gen_ moves
+            gen_.store(gen + 1, std::memory_order_release);
+            syscall(SYS_futex, reinterpret_cast<unsigned*>(&gen_), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
+        } else {
+            while (gen_.load(std::memory_order_acquire) == gen)
+                syscall(SYS_futex, reinterpret_cast<unsigned*>(&gen_), FUTEX_WAIT_PRIVATE, gen, nullptr, nullptr, 0);
+        }
     }
   private:
-    std::mutex m_;
-    std::condition_variable cv_;
-    int count_, waiting_ = 0;
-    unsigned long gen_ = 0;
+    std::atomic<unsigned> gen_{0};
+    std::atomic<int> waiting_{0};
+    int count_;
 };
 
 static EmuBarrier emu_block_barrier;

@@ -7,7 +7,6 @@ the base matrix and the PL2 loop).  The path is exact integer arithmetic, so the
 S[b][i][j] = sum_c w[b][c] * min(T[i][c], T[j][c]) of app/src/pl1_graphs.py:81-86 + similarity_matrix_constructor.py:167 on the
 fixed-point image, and the limb recombination is one correctly rounded fused multiply-add."""
 import os
-import shutil
 import subprocess
 from fractions import Fraction
 
@@ -20,13 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    exe = str(tmp_path_factory.mktemp("emul") / "bs_emul")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-o", exe,
-                    os.path.join(ROOT, "tests", "emul", "bs_emul.cpp")], check=True)
-    return exe
+def emul(emul_build):
+    return emul_build("bs_emul")
 
 
 def ws_index(r, c):

@@ -8,8 +8,6 @@ matrices within the north_star tolerance and IDENTICAL DENDROGRAM TOPOLOGIES (th
 0.7 s per replicate).  The GPU version of the same comparison, all 100 replicates, is tests/test_zz_cfg1_gpu.py."""
 import os
 import re
-import shutil
-import subprocess
 import warnings
 
 import numpy as np
@@ -105,16 +103,8 @@ def test_cfg1_oracle_equals_reference_for_every_replicate(cfg1):
 
 
 @pytest.fixture(scope="module")
-def exes(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    d = tmp_path_factory.mktemp("emul")
-    out = {}
-    for name in ("gom_emul", "bs_emul", "gj_emul", "lk_emul"):
-        out[name] = str(d / name)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-o", out[name],
-                        os.path.join(ROOT, "tests", "emul", name + ".cpp")], check=True)
-    return out
+def exes(emul_build):
+    return {name: emul_build(name) for name in ("gom_emul", "bs_emul", "gj_emul", "lk_emul")}
 
 
 def test_cfg1_emulated_job_and_dendrograms_equal_reference(cfg1, exes):

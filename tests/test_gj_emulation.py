@@ -6,7 +6,6 @@ threshold 60) and, on larger ragged tables, against the oracle -- tolerance 1e-6
 copies complete at once here and the MUFU reciprocal square root seed is an exact 1/sqrt: ring accounting and the seed's 22
 bits are what the GPU tests cover.)"""
 import os
-import shutil
 import subprocess
 
 import numpy as np
@@ -21,13 +20,8 @@ RTOL, ATOL = 1e-6, 1e-12
 
 
 @pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    exe = str(tmp_path_factory.mktemp("emul") / "gj_emul")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-o", exe,
-                    os.path.join(ROOT, "tests", "emul", "gj_emul.cpp")], check=True)
-    return exe
+def emul(emul_build):
+    return emul_build("gj_emul")
 
 
 @pytest.fixture(scope="module")

@@ -6,7 +6,6 @@ against the reference's own known answer for dcor (app/utils/dcor.py:38-41), its
 the oracle on the resampled table ``loc[:, idx]`` -- 1e-9 relative, as for the GPU tests; exactly degenerate inputs give
 exactly 0."""
 import os
-import shutil
 import subprocess
 import warnings
 
@@ -20,13 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    exe = str(tmp_path_factory.mktemp("emul") / "gom_emul")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-o", exe,
-                    os.path.join(ROOT, "tests", "emul", "gom_emul.cpp")], check=True)
-    return exe
+def emul(emul_build):
+    return emul_build("gom_emul")
 
 
 def gom_table(emul, loc, rows, offs, weights=None, all_columns=False):

@@ -7,7 +7,6 @@ three emulated stages are chained as the bootstrap job chains them (api.cu, repl
 and the distance matrices are compared with the reference's (1e-6, the north_star tolerance)."""
 import math
 import os
-import shutil
 import subprocess
 
 import numpy as np
@@ -19,16 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
-def exes(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    d = tmp_path_factory.mktemp("emul")
-    out = {}
-    for name in ("gom_emul", "bs_emul", "gj_emul"):
-        out[name] = str(d / name)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-o", out[name],
-                        os.path.join(ROOT, "tests", "emul", name + ".cpp")], check=True)
-    return out
+def exes(emul_build):
+    return {name: emul_build(name) for name in ("gom_emul", "bs_emul", "gj_emul")}
 
 
 def run(exe, args, blob):

@@ -6,7 +6,6 @@ operations that decides how ties fall -- against scipy; the GPU tests (test_gpu_
 check the compiled kernels themselves.  (Built with -fsanitize=thread the emulation doubles as a race detector for the
 kernels' shared-memory protocol: see DESIGN.md section 4.)"""
 import os
-import shutil
 import subprocess
 
 import numpy as np
@@ -17,13 +16,8 @@ CODES = {"average": 0, "complete": 1, "weighted": 2, "ward": 3, "single": 4, "ce
 
 
 @pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    exe = str(tmp_path_factory.mktemp("emul") / "lk_emul")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-o", exe,
-                    os.path.join(ROOT, "tests", "emul", "lk_emul.cpp")], check=True)
-    return exe
+def emul(emul_build):
+    return emul_build("lk_emul")
 
 
 def _matrix(kind, n, rng):

@@ -5,7 +5,6 @@ column blocks, the mirror through shared memory, the packed-tile form of the mul
 for bit against the oracle's restatement of shared_pphmm_ratio (app/utils/shared_pphmm_graphs.py:59-77); the GPU tests check
 the compiled kernels."""
 import os
-import shutil
 import subprocess
 
 import numpy as np
@@ -15,13 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    exe = str(tmp_path_factory.mktemp("emul") / "popc_emul")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "emul", "popc_emul.cpp")],
-                   check=True)
-    return exe
+def emul(emul_build):
+    return emul_build("popc_emul")
 
 
 @pytest.mark.parametrize("packed", [0, 1])

@@ -3,7 +3,6 @@ includes the SAME source the GPU build compiles (gravity2_b200/csrc/classify_ker
 follow np.max / np.argmax (first maximum; a NaN wins, the first NaN is the arg-maximum: what
 app/utils/classification_utils.py:63-68 gets from numpy); Philox4x32-10 is held to the Random123 restatement."""
 import os
-import shutil
 import subprocess
 
 import numpy as np
@@ -13,13 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("no host compiler")
-    exe = str(tmp_path_factory.mktemp("emul") / "small_emul")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "emul", "small_emul.cpp")],
-                   check=True)
-    return exe
+def emul(emul_build):
+    return emul_build("small_emul")
 
 
 @pytest.mark.parametrize("rows,ld,r0,r1,c0,c1", [(5, 7, 0, 5, 0, 7), (9, 700, 2, 9, 13, 650), (6, 300, 1, 4, 255, 256)])
