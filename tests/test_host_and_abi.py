@@ -29,6 +29,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.gv2_version() >= 100
 
 
+def test_header_is_plain_c_and_cites_the_reference():
+    """The boundary is a C ABI: the header compiles as C99 on its own (no C++ types, no torch types in a signature), and every
+    entry point's comment cites the reference interface it replaces (file:line under app/)."""
+    import shutil
+    import subprocess
+    path = os.path.join(REPO, "include", "gravity2_b200.h")
+    if shutil.which("gcc") is not None:
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", path],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    src = open(path).read()
+    code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)                    # signatures only, comments stripped
+    assert 'extern "C"' in code and "torch" not in code and "std::" not in code and "&" not in code.replace("&&", "")
+    assert len(re.findall(r"[a-z_0-9]+\.py:\d+", src)) >= 20
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
