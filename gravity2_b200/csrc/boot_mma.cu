@@ -36,361 +36,7 @@
 #include <math.h>
 #include <string.h>
 
-#define BM_PAIRS 128
-#define BM_KC 128                      // columns per pipeline stage (= one 128-byte swizzle row of uint8)
-#define BM_STAGES 2
-#define BM_PLANES 2                    // uint8 digit planes per pass (two passes cover the 32-bit fixed-point min)
-#define BM_NMAX 256                    // replicates per CTA: BM_PLANES * BM_NMAX = 512 TMEM columns
-#define BM_TMEM_COLS 512
-#define BM_PRODUCERS 512               // producer threads (16 warps: two pair rows per thread and stage)
-#define BM_THREADS (BM_PRODUCERS + 64)
-#define BM_RING 3                      // table-row staging ring (chunks)
-#define BM_ROWS 24                     // 8 i-rows + 16 j-rows
-#define BM_A_BYTES (BM_PAIRS * BM_KC)                // 16 KB per plane
-#define BM_W_BYTES (BM_NMAX * BM_KC)                 // 32 KB
-#define BM_STAGE_BYTES (BM_PLANES * BM_A_BYTES + BM_W_BYTES) // 64 KB
-#define BM_RING_BYTES (BM_ROWS * BM_KC * 4)          // 12 KB per chunk
-#define BM_SMEM (BM_STAGES * BM_STAGE_BYTES + BM_RING * BM_RING_BYTES + 1024 /*align*/ + 256 /*barriers*/)
-
-__host__ __device__ inline int bm_ws_index(int r, int c) { return ((((r >> 4) << 3) + (c >> 4)) << 8) + ((r & 15) << 4) + (c & 15); }
-
-__host__ __device__ inline void bm_tile_coords(long long t, int nt, int* bi, int* bj) {
-    double disc = (2.0 * nt + 1.0) * (2.0 * nt + 1.0) - 8.0 * (double)t;
-    int r = (int)floor(((2.0 * nt + 1.0) - sqrt(disc)) * 0.5);
-    if (r < 0) r = 0;
-    while (r > 0 && (long long)r * nt - (long long)r * (r - 1) / 2 > t) --r;
-    while ((long long)(r + 1) * nt - (long long)(r + 1) * r / 2 <= t) ++r;
-    *bi = r;
-    *bj = r + (int)(t - ((long long)r * nt - (long long)r * (r - 1) / 2));
-}
-
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// bounded wait: a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address >> 4 in bits
-// [0,14), leading byte offset 0 (one swizzle atom along K), stride byte offset 1024 (8 rows x 128 B)
-// in bits [32,46), version 1 in bits [46,48), layout type 2 (SWIZZLE_128B) in bits [61,64).
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((1024u >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// instruction descriptor, kind::i8: D = S32 (bits [4,6) = 2), A = B = unsigned 8 bit (bits [7,10) =
-// [10,13) = 0), both K-major (bits 15, 16 = 0), N >> 3 in bits [17,23), M >> 4 in bits [24,29)
-__device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
-    return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, M = 128, K = 32 uint8 per instruction
-__device__ __forceinline__ void umma_u8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// 32 TMEM lanes (this warp's quarter) x 16 consecutive 32-bit columns -> 16 registers per thread
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void cp16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem));
-}
-
-// byte transpose of one half-word: v0..v3 = four consecutive columns (u32 each) -> p[0] = the low bytes,
-// p[1] = the high bytes of the selected half-word (HI: bytes 2,3; else bytes 0,1), column k in byte k
-// (little endian = element order of the K-major uint8 tile).  4 PRMT.
-template <bool HI>
-__device__ __forceinline__ void byte_planes(const uint32_t v0, const uint32_t v1, const uint32_t v2, const uint32_t v3,
-                                            uint32_t* p) {
-    const uint32_t t0 = __byte_perm(v0, v1, HI ? 0x7362 : 0x5140);   // v0.bA v1.bA v0.bB v1.bB
-    const uint32_t t1 = __byte_perm(v2, v3, HI ? 0x7362 : 0x5140);
-    p[0] = __byte_perm(t0, t1, 0x5410);
-    p[1] = __byte_perm(t0, t1, 0x7632);
-}
-
-// ---------------------------------------------------------------------------------- kernel
-// grid = (128 sub-tiles, genome tiles in [tile_begin, tile_end), replicate blocks)
-template <bool HI>
-__global__ void __launch_bounds__(BM_THREADS, 1)
-boot_mma_kernel(const uint32_t* __restrict__ tab, int ld, int kchunks, int nt, long long tile_begin,
-                const __grid_constant__ CUtensorMap wmap, int nb_total, int nblk, long long ws_rep_stride,
-                double quantum, double* __restrict__ ws) {
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B needs 1024-B alignment; offsetting the array (not casting through uintptr_t) keeps the
-    // pointers provably shared, so the producers get LDS/STS instead of generic LD/ST
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* stage_base = smem;
-    uint32_t* ring = (uint32_t*)(smem + BM_STAGES * BM_STAGE_BYTES);
-    uint64_t* bars = (uint64_t*)(smem + BM_STAGES * BM_STAGE_BYTES + BM_RING * BM_RING_BYTES);
-    uint64_t* full = bars;                  // [BM_STAGES]
-    uint64_t* empty = bars + BM_STAGES;     // [BM_STAGES]
-    uint64_t* tmem_full = bars + 2 * BM_STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * BM_STAGES + 1);
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int sub = blockIdx.x, si = sub >> 3, sj = sub & 7;      // 16 i-groups of 8 rows, 8 j-groups of 16 rows
-    int bi, bj;
-    bm_tile_coords(tile_begin + blockIdx.y, nt, &bi, &bj);
-    if (bi == bj && si * 8 > sj * 16 + 15) return;                 // sub-tile entirely below the diagonal
-    const int rep0 = blockIdx.z * nblk;
-    const int nrep = min(nblk, nb_total - rep0);                   // valid replicates of this block
-    const int umma_n = nblk;                                       // = TMA box rows; padded W rows are zero
-
-    if (tid == 0) {
-        for (int s = 0; s < BM_STAGES; ++s) {
-            mbar_init(&full[s], BM_PRODUCERS + 1);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(tmem_full, 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) {   // TMEM: 2 digit planes x 256 int32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BM_TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp < BM_PRODUCERS / 32) {
-        // ============================ producers ============================
-        const uint32_t* gI = tab + (size_t)(bi * GV2_TILE + si * 8) * ld;
-        const uint32_t* gJ = tab + (size_t)(bj * GV2_TILE + sj * 16) * ld;
-        auto ring_load = [&](int kc) {
-            uint32_t* dst = ring + (kc % BM_RING) * (BM_ROWS * BM_KC);
-            for (int q = tid; q < BM_ROWS * 32; q += BM_PRODUCERS) {       // 24 rows x 32 pieces of 16 B
-                const int row = q >> 5, piece = q & 31;
-                const uint32_t* src = (row < 8 ? gI + (size_t)row * ld : gJ + (size_t)(row - 8) * ld) + (size_t)kc * BM_KC + piece * 4;
-                cp16(dst + row * BM_KC + piece * 4, src);
-            }
-        };
-        for (int s = 0; s < BM_RING - 1; ++s) {
-            if (s < kchunks) ring_load(s);
-            asm volatile("cp.async.commit_group;");
-        }
-        static_assert(BM_PRODUCERS == 512 && BM_PAIRS == 128 && BM_KC == 128, "producer mapping: 16 warps x (2 x 4 pairs), 32 lanes x 4 columns");
-        for (int kc = 0; kc < kchunks; ++kc) {
-            const int st = kc % BM_STAGES;
-            const uint32_t ph = (kc / BM_STAGES) & 1;
-            asm volatile("cp.async.wait_group %0;" ::"n"(BM_RING - 2));
-            asm volatile("bar.sync 1, %0;" ::"n"(BM_PRODUCERS));             // chunk kc landed for every producer
-            if (kc + BM_RING - 1 < kchunks) ring_load(kc + BM_RING - 1);    // slot of chunk kc-1: free since the barrier
-            asm volatile("cp.async.commit_group;");
-            mbar_wait(&empty[st], ph ^ 1);                                   // MMA has drained this stage
-            const uint32_t* rg = ring + (kc % BM_RING) * (BM_ROWS * BM_KC);
-            uint8_t* a0 = stage_base + st * BM_STAGE_BYTES;
-            // Warp w owns a 2 x 4 block of pairs (i-rows 2*(w/4)+{0,1}, j-rows 4*(w%4)+{0..3}); lane = one group of
-            // four consecutive columns.  Per stage a thread loads 2 x-pieces + 4 y-pieces (6 LDS.128 for 8 pairs:
-            // the shared-memory data pipe, shared with the tensor core's operand reads, is this kernel's bound)
-            // and a warp's 32 STS.32 to one A row cover its 128 bytes exactly once under the XOR swizzle.
-            const int ii0 = (warp >> 2) * 2, jj0 = (warp & 3) * 4;
-            const int col = lane * 4;
-            uint4 x[2], y[4];
-#pragma unroll
-            for (int a = 0; a < 2; ++a) x[a] = *reinterpret_cast<const uint4*>(rg + (ii0 + a) * BM_KC + col);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) y[b] = *reinterpret_cast<const uint4*>(rg + (8 + jj0 + b) * BM_KC + col);
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int m = (ii0 + a) * 16 + jj0 + b;                 // pair row of the A tiles
-                    uint32_t p[BM_PLANES];
-                    byte_planes<HI>(min(x[a].x, y[b].x), min(x[a].y, y[b].y), min(x[a].z, y[b].z), min(x[a].w, y[b].w), p);
-                    // K-major SWIZZLE_128B: row m at (m/8)*1024 + (m%8)*128; columns col..col+3 are bytes col..col+3:
-                    // 16-byte piece col/16 (XOR m%8), word (col/4)%4
-                    uint8_t* dst = a0 + (uint32_t)(m >> 3) * 1024u + (uint32_t)(m & 7) * 128u +
-                                   (uint32_t)((((col >> 4) ^ (m & 7)) << 4) + (col & 12));
-#pragma unroll
-                    for (int d = 0; d < BM_PLANES; ++d) *reinterpret_cast<uint32_t*>(dst + d * BM_A_BYTES) = p[d];
-                }
-            }
-            fence_proxy_async();              // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            mbar_arrive(&full[st]);
-        }
-        // ============================ epilogue ============================
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        constexpr int kColGroups = BM_PRODUCERS / 128;      // warps sharing a TMEM lane quarter split the columns
-        constexpr int kColsPerGroup = BM_NMAX / kColGroups;
-        const int lg = warp & 3, half = warp >> 2;          // TMEM lanes 32*lg.., replicate columns half*kColsPerGroup..
-        const int m = lg * 32 + lane;
-        const int r = si * 8 + (m >> 4), c = sj * 16 + (m & 15);
-        double* out = ws + (size_t)blockIdx.y * (GV2_TILE * GV2_TILE) + bm_ws_index(r, c);
-        for (int cb = 0; cb < kColsPerGroup / 16; ++cb) {
-            const int col0 = half * kColsPerGroup + cb * 16;
-            if (col0 >= umma_n) break;
-            uint32_t v[BM_PLANES][16];
-#pragma unroll
-            for (int d = 0; d < BM_PLANES; ++d)
-                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * BM_NMAX + col0), v[d]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int rep = col0 + e;
-                // exact integers: each plane sum < 2^31; the low pass stores, the high pass adds 65536 x its sums
-                // (a second launch on the same stream: plain read-modify-write, deterministic)
-                const double sum = (double)(int)v[0][e] + 256.0 * (double)(int)v[1][e];
-                if (rep < nrep) {
-                    double* o = out + (size_t)(rep0 + rep) * ws_rep_stride;
-                    if (HI) *o += sum * 65536.0 * quantum;
-                    else *o = sum * quantum;
-                }
-            }
-        }
-    } else if (warp == BM_PRODUCERS / 32) {
-        // ============================ TMA: W tiles ============================
-        if (lane == 0) {
-            for (int kc = 0; kc < kchunks; ++kc) {
-                const int st = kc % BM_STAGES;
-                const uint32_t ph = (kc / BM_STAGES) & 1;
-                mbar_wait(&empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&full[st], (uint32_t)(umma_n * BM_KC));
-                tma_load_2d(stage_base + st * BM_STAGE_BYTES + BM_PLANES * BM_A_BYTES, &wmap, &full[st], kc * BM_KC, rep0);
-            }
-        }
-        __syncwarp();
-    } else {
-        // ============================ MMA issuer ============================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc(BM_PAIRS, umma_n);
-            for (int kc = 0; kc < kchunks; ++kc) {
-                const int st = kc % BM_STAGES;
-                const uint32_t ph = (kc / BM_STAGES) & 1;
-                mbar_wait(&full[st], ph);
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(stage_base + st * BM_STAGE_BYTES);
-                const uint32_t w0 = a0 + BM_PLANES * BM_A_BYTES;
-#pragma unroll
-                for (int d = 0; d < BM_PLANES; ++d) {
-#pragma unroll
-                    for (int k = 0; k < BM_KC / 32; ++k) {
-                        const uint64_t da = umma_desc(a0 + d * BM_A_BYTES + k * 32);
-                        const uint64_t db = umma_desc(w0 + k * 32);
-                        umma_u8(tmem_base + (uint32_t)(d * BM_NMAX), da, db, idesc, (kc | k) ? 1u : 0u);
-                    }
-                }
-                umma_commit(&empty[st]);                 // frees the stage when these MMAs have read it
-            }
-            umma_commit(tmem_full);                      // accumulators complete
-        }
-        __syncwarp();
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BM_TMEM_COLS));
-}
-
-// int32 multiplicities -> uint8 rows, zero padded: out [nb_pad][k_pad].  grid = (ceil(k_pad/256), nb_pad)
-__global__ void weights_to_u8_kernel(const int* __restrict__ w, long long nb, long long k, long long k_pad,
-                                     uint8_t* __restrict__ out, int* __restrict__ overflow) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (c >= k_pad) return;
-    int v = (b < nb && c < k) ? w[b * k + c] : 0;
-    if (v < 0 || v > 255) { atomicExch(overflow, 1); v = 0; }
-    out[b * k_pad + c] = (uint8_t)v;
-}
-
-// float64 table -> 32-bit fixed point, zero padded [n_pad][k_pad]; scale = (2^32-1)/max.  NaN and
-// negative entries become 0 (NaN rows are flagged by prepare_table; negatives disable this path).
-__global__ void table_to_fixed_kernel(const double* __restrict__ src, long long n, long long k, long long ld_src,
-                                      double scale, uint32_t* __restrict__ dst, long long k_pad) {
-    const long long r = blockIdx.x;
-    uint32_t* d = dst + r * k_pad;
-    for (long long c = threadIdx.x; c < k_pad; c += blockDim.x) {
-        uint32_t f = 0;
-        if (r < n && c < k) {
-            const double v = src[r * ld_src + c];
-            if (v > 0.0) f = (uint32_t)__double2ull_rn(fmin(v * scale, 4294967295.0));
-        }
-        d[c] = f;
-    }
-}
-
-// per-block max and "has negative" of a float64 table (ignoring NaN).  stats[0] = max bits (as ull of
-// the non-negative double), stats[1] = negative flag
-__global__ void table_stats_kernel(const double* __restrict__ src, long long n, long long k, long long ld_src,
-                                   unsigned long long* __restrict__ stats) {
-    const long long r = blockIdx.x;
-    double mx = 0.0;
-    int neg = 0;
-    for (long long c = threadIdx.x; c < k; c += blockDim.x) {
-        const double v = src[r * ld_src + c];
-        if (v > mx) mx = v;
-        if (v < 0.0) neg = 1;
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        neg |= __shfl_xor_sync(0xffffffffu, neg, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(&stats[0], (unsigned long long)__double_as_longlong(mx));   // order-preserving for non-negative doubles
-        if (neg) atomicExch(&stats[1], 1ull);
-    }
-}
-
-// Weighted row sums sum_c w[b][c] * x[i][c] are the diagonal pairs (i, i) of the contraction itself
-// (min(x, x) = x), so they are read back from the pair-sum workspace: exact, and identical to what the
-// off-diagonal sums are built from.  grid = (ceil(n/256), nb)
-__global__ void diag_rowsums_kernel(const double* __restrict__ ws, long long ws_rep_stride, int nt, long long n,
-                                    double* __restrict__ out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (i >= n) return;
-    const long long bi = i / GV2_TILE;
-    const int r = (int)(i % GV2_TILE);
-    const long long t = bi * nt - bi * (bi - 1) / 2;          // linear index of diagonal tile (bi, bi)
-    out[b * n + i] = ws[b * ws_rep_stride + t * (GV2_TILE * GV2_TILE) + bm_ws_index(r, r)];
-}
+#include "boot_mma_kernels.cuh"
 
 // ---------------------------------------------------------------------------------- host
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
