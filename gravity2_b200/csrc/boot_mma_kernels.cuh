@@ -73,6 +73,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+#endif   // descriptors: plain bit arithmetic, shared with the emulation (its tensor-core model DECODES what these encode)
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): start address >> 4 in bits
 // [0,14), leading byte offset 0 (one swizzle atom along K), stride byte offset 1024 (8 rows x 128 B)
 // in bits [32,46), version 1 in bits [46,48), layout type 2 (SWIZZLE_128B) in bits [61,64).
@@ -91,6 +92,7 @@ __device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
     return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+#ifndef BM_EMULATED
 // D[tmem] (+)= A[smem] * B[smem]^T, M = 128, K = 32 uint8 per instruction
 __device__ __forceinline__ void umma_u8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

@@ -19,7 +19,7 @@ from oracle import gravity_oracle as O  # noqa: E402
 
 tmp = tempfile.mkdtemp()
 exe = {}
-for name in ("lk_emul", "popc_emul", "small_emul", "gj_emul", "bs_emul", "gom_emul"):
+for name in ("lk_emul", "popc_emul", "small_emul", "gj_emul", "bs_emul", "gom_emul", "mma_emul"):
     exe[name] = os.path.join(tmp, name)
     subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-pthread", "-ffp-contract=off", "-fsanitize=thread", "-o", exe[name],
                     os.path.join(ROOT, "tests", "emul", name + ".cpp")], check=True, stderr=subprocess.DEVNULL)
@@ -71,3 +71,7 @@ rows = [np.asarray(db[k]).reshape(-1, 300) for k in t3.gom_ids]
 offs = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
 run("GOM scoring (build + 40 replicates, light and heavy pairs), 20 x 300", "gom_emul", [20, 300, 3, 40, 0, 1],
     t3.loc.tobytes() + offs.tobytes() + np.concatenate(rows).tobytes() + w.tobytes())
+t4 = synth.make_tables(24, 520, 4, 0.3, seed=5)
+w = np.stack([np.bincount(rng.integers(0, 520, 520), minlength=520) for _ in range(20)]).astype(np.int32)
+run("tensor-core pair sums (producers / TMA / MMA warps over the tcgen05 model), 24 x 520, 20 replicates", "mma_emul", [24, 520, 20],
+    t4.sig.tobytes() + w.tobytes())
