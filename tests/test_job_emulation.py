@@ -2,7 +2,8 @@
 for the golden replicates of oracle/make_golden.py (the reference's np.random.choice draws, app/src/pl1_graphs.py:78-107) the
 three emulated stages are chained as the bootstrap job chains them (api.cu, replicates_impl) --
   gom_emul   GOM signature tables of every replicate from column multiplicities (location table = signature table: quirk Q3),
-  bs_emul    exact PPHMM pair sums of every replicate from the pair lists; a replicate's row sums are its diagonal pair sums,
+  bs_emul    exact PPHMM pair sums of every replicate from the pair lists; a replicate's row sums are its diagonal pair sums
+             (or mma_emul: the same sums from the tensor-core kernel over the tcgen05 model, the dense tables' path),
   gj_emul    job_tail: fixed-point image of the GOM tables, then the fused tail (GOM Jaccard + combine + 1 - S + mirror) --
 and the distance matrices are compared with the reference's (1e-6, the north_star tolerance)."""
 import math
@@ -19,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def exes(emul_build):
-    return {name: emul_build(name) for name in ("gom_emul", "bs_emul", "gj_emul")}
+    return {name: emul_build(name) for name in ("gom_emul", "bs_emul", "gj_emul", "mma_emul")}
 
 
 def run(exe, args, blob):
@@ -32,8 +33,10 @@ def ws_index(r, c):
     return ((((r >> 4) << 3) + (c >> 4)) << 8) + ((r & 15) << 4) + (c & 15)
 
 
-def emulated_pl1(exes, sig, taxo, ids, idx):
-    """Distance matrices (nb, n, n) of the PL1 replicates with resample indices idx (nb, p), stage by stage as the job runs them."""
+def emulated_pl1(exes, sig, taxo, ids, idx, tensor_core=False):
+    """Distance matrices (nb, n, n) of the PL1 replicates with resample indices idx (nb, p), stage by stage as the job runs them.
+    tensor_core: the pair sums come from the tcgen05 kernel (the path the job's cost model picks for dense tables) instead of
+    the pair-list kernels."""
     n, p = sig.shape
     G, nb = len(ids), len(idx)
     w = np.stack([np.bincount(i, minlength=p) for i in idx]).astype(np.int32)
@@ -43,10 +46,14 @@ def emulated_pl1(exes, sig, taxo, ids, idx):
     offs = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
     gom = run(exes["gom_emul"], [n, p, G, nb, 0, 1], sig.tobytes() + offs.tobytes() + np.concatenate(rows).tobytes() + w.tobytes())
     # exact PPHMM pair sums of the replicates
-    buf = run(exes["bs_emul"], [n, p, nb], sig.tobytes() + w.tobytes())
     nt = (n + 127) // 128
     ntl = nt * (nt + 1) // 2
-    ws = buf[1 + n:].reshape(nb, ntl, 128 * 128)
+    if tensor_core:
+        buf = run(exes["mma_emul"], [n, p, nb], sig.tobytes() + w.tobytes())
+        ws = buf[2 + nb * n:].reshape(nb, ntl, 128 * 128)
+    else:
+        buf = run(exes["bs_emul"], [n, p, nb], sig.tobytes() + w.tobytes())
+        ws = buf[1 + n:].reshape(nb, ntl, 128 * 128)
     tile_of = {(bi, bj): t for t, (bi, bj) in enumerate((a, b) for a in range(nt) for b in range(a, nt))}
     prs = np.array([[ws[b, tile_of[(i // 128, i // 128)], ws_index(i % 128, i % 128)] for i in range(n)] for b in range(nb)])
     ws = np.where(np.isnan(ws), 0.0, ws)                           # (blocks below the diagonal are never written, never read)
@@ -55,12 +62,13 @@ def emulated_pl1(exes, sig, taxo, ids, idx):
     return run(exes["gj_emul"], ["job_tail", n, G, nb, repr(p_scale), 1.0, 1], ws.tobytes() + prs.tobytes() + gom.tobytes()).reshape(nb, n, n)
 
 
+@pytest.mark.parametrize("tensor_core", [False, True])
 @pytest.mark.parametrize("tag", ["A", "B"])
-def test_emulated_pl1_replicates_equal_reference_golden(exes, tag):
+def test_emulated_pl1_replicates_equal_reference_golden(exes, tag, tensor_core):
     g = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
     sig, taxo, ids = g[f"{tag}_sig"], g[f"{tag}_taxo"], [str(x) for x in g[f"{tag}_gom_ids"]]
     idx, D_ref = g[f"{tag}_pl1_idx"], g[f"{tag}_pl1_D"]
-    D = emulated_pl1(exes, sig, taxo, ids, idx)
+    D = emulated_pl1(exes, sig, taxo, ids, idx, tensor_core)
     assert D.shape == D_ref.shape
     err = np.abs(D - D_ref)
     assert err.max() <= 1e-6, err.max()
