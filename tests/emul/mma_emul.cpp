@@ -10,7 +10,8 @@
 //                  builds (start address, stride byte offset, SWIZZLE_128B applied to ABSOLUTE shared-address bits [4,7) ^=
 //                  bits [7,10)), M / N from the instruction descriptor, K = 32 bytes, D[m][n] (+)= sum_k A[m][k] * B[n][k] in
 //                  int32 into TMEM lane m, column n;
-//   tcgen05.commit arrives on the mbarrier (the model executes the MMAs at issue, so they are complete by then);
+//   tcgen05.commit executes the MMAs issued since the last commit (operands read at the last legal moment), then arrives on
+//                  the mbarrier;
 //   tcgen05.ld     32x32b.x16: a warp may only touch the TMEM lane quarter 32 * (warp % 4) -- asserted;
 //   cp.async       the emulator's two-extremes model (cuda_block_emul.h); bar.sync 1, 512: a second block barrier.
 // What this checks without a GPU: the warp-role protocol (no deadlock, every stage handed over in order), the swizzled A-tile
@@ -127,7 +128,15 @@ static inline uint8_t emu_operand_byte(uint64_t desc, int row, int kbyte) {
     return *emu_sptr(emu_swizzle128(logical));
 #endif
 }
+// The tensor core may read a stage's operands at any time between the issue of an MMA and the commit that covers it: the model
+// reads them at the LAST legal moment (tcgen05.commit executes the queued MMAs, then arrives), so a stage overwritten before
+// its commit -- a missing wait on the `empty` barrier -- corrupts the sums instead of going unnoticed.
+struct EmuMma { uint32_t tmem_d; uint64_t da, db; uint32_t idesc, accumulate; };
+static thread_local std::vector<EmuMma> emu_mma_queue;
 static inline void umma_u8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    emu_mma_queue.push_back(EmuMma{tmem_d, da, db, idesc, accumulate});
+}
+static inline void emu_mma_execute(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     const int n = (int)((idesc >> 17) & 0x3F) << 3, m = (int)((idesc >> 24) & 0x1F) << 4;
     assert(((idesc >> 4) & 3) == 2 && ((idesc >> 7) & 7) == 0 && ((idesc >> 10) & 7) == 0 && !((idesc >> 15) & 3));   // S32 <- U8 x U8, K-major
     assert(m == 128 && n >= 16 && n <= 256 && n % 16 == 0 && (tmem_d >> 16) == 0);
@@ -143,7 +152,11 @@ static inline void umma_u8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t i
             emu_tmem[r][col0 + c] = s;
         }
 }
-static inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }
+static inline void umma_commit(uint64_t* bar) {
+    for (const EmuMma& q : emu_mma_queue) emu_mma_execute(q.tmem_d, q.da, q.db, q.idesc, q.accumulate);
+    emu_mma_queue.clear();
+    mbar_arrive(bar);
+}
 static inline void tmem_ld16(uint32_t taddr, uint32_t* v) {
     const uint32_t lane0 = taddr >> 16, col = taddr & 0xFFFF;
     assert(lane0 == 32u * ((uint32_t)(emu_linear_tid >> 5) & 3u) && col + 16 <= 512);
