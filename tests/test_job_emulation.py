@@ -76,8 +76,9 @@ def test_emulated_pl1_replicates_equal_reference_golden(exes, tag, tensor_core):
         assert np.array_equal(D[b], D[b].T)
 
 
+@pytest.mark.parametrize("tensor_core", [False, True])
 @pytest.mark.parametrize("tag", ["A", "B"])
-def test_emulated_pl2_replicates_equal_reference_golden(exes, tag):
+def test_emulated_pl2_replicates_equal_reference_golden(exes, tag, tensor_core):
     """The PL2 loop body (row a9, app/src/virus_classification.py:290-315): sorted resample indices (multiplicities do not see
     the order), the real location table, the GOM database from the reference rows only, similarity (not distance) output."""
     g = np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
@@ -90,8 +91,10 @@ def test_emulated_pl2_replicates_equal_reference_golden(exes, tag):
     rows = [np.asarray(db[k], dtype=np.float64).reshape(-1, p) for k in ids]
     offs = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int32)
     gom = run(exes["gom_emul"], [n, p, G, nb, 0, 1], loc.tobytes() + offs.tobytes() + np.concatenate(rows).tobytes() + w.tobytes())
-    buf = run(exes["bs_emul"], [n, p, nb], sig.tobytes() + w.tobytes())
-    ws = buf[1 + n:].reshape(nb, 1, 128 * 128)
+    if tensor_core:
+        ws = run(exes["mma_emul"], [n, p, nb], sig.tobytes() + w.tobytes())[2 + nb * n:].reshape(nb, 1, 128 * 128)
+    else:
+        ws = run(exes["bs_emul"], [n, p, nb], sig.tobytes() + w.tobytes())[1 + n:].reshape(nb, 1, 128 * 128)
     prs = np.array([[ws[b, 0, ws_index(i, i)] for i in range(n)] for b in range(nb)])
     ws = np.where(np.isnan(ws), 0.0, ws)
     p_scale = math.ldexp(1.0, -math.frexp(sig.max() * 255.0 * p)[1])
