@@ -83,3 +83,17 @@ def test_mutants_are_caught(tmp_path, flag):
     subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-D" + flag, "-o", exe,
                     os.path.join(ROOT, "tests", "emul", "mma_emul.cpp")], check=True)
     assert mismatches(exe, *case(40, 700, 17, 0.1), properties=False) > 0
+
+
+def test_emulated_tensor_core_extreme_digits_and_multiplicities(emul):
+    """Every digit plane at 255 (all entries at the table's maximum -> fixed point 2^32 - 1), multiplicities at the uint8 limit,
+    a zero replicate: the int32 TMEM accumulators and the fp64 recombination stay exact."""
+    n, k = 9, 130
+    tab = np.full((n, k), 7.5)
+    tab[4, 100:] = 0.0
+    tab[5, :] = 7.5 / 3.0
+    w = np.ones((3, k), dtype=np.int32)
+    w[0, ::2] = 255
+    w[1, :] = 0
+    w[2, 129] = 255
+    assert mismatches(emul, tab, w, properties=False) == 0
