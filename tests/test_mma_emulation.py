@@ -97,3 +97,14 @@ def test_emulated_tensor_core_extreme_digits_and_multiplicities(emul):
     w[1, :] = 0
     w[2, 129] = 255
     assert mismatches(emul, tab, w, properties=False) == 0
+
+
+def test_emulated_weight_overflow_is_flagged(emul):
+    """A multiplicity above 255 (or negative) cannot enter the uint8 operand: weights_to_u8_kernel raises the flag the job reads
+    before any delivery (api.cu validates the multiplicities up front; this is the kernel-side guard)."""
+    tab = np.full((2, 5), 1.0)
+    for bad in (256, -1):
+        w = np.ones((1, 5), dtype=np.int32)
+        w[0, 2] = bad
+        out = subprocess.run([emul, "2", "5", "1"], input=tab.tobytes() + w.tobytes(), capture_output=True, timeout=600)
+        assert out.returncode == 0 and np.frombuffer(out.stdout, dtype=np.float64)[1] == 1.0
